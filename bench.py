@@ -1,0 +1,546 @@
+#!/usr/bin/env python
+"""bench.py -- masked-VGG16-BN training images/s (BASELINE.json metric) on N B200s.
+
+  python bench.py --gpus 1 --steps K --warmup W            # our arm (CUDA path through the C ABI)
+  python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port)
+  torchrun --nproc-per-node N bench.py --gpus N ...        # weak scaling, one rank per GPU
+
+A "step" is one pass of the hot path over one synthetic batch, exactly the step sequence of the
+reference's utils/manager.py:54-75:
+  zero_grad -> model(data) -> criterion -> backward -> do_weight_decay_and_make_grads_zero -> step.
+Workload = BASELINE.json configs[1]: VGG16-BN masked, CIFAR-100 task-1 synthetic 32x32, batch
+128 per GPU (regime R1 of SURVEY 8d: no piggymask, T==1).  The same run also measures regime
+R2 (task 2: piggymask on every sharable layer) and reports it under "regime_task2".
+
+One JSON line is printed by rank 0 (see the contract in the round prompt).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from cpg_b200.vgg_cifar import VGGCifar  # noqa: E402
+
+METRIC = 'masked-VGG16 train images/sec'
+WORKLOAD = 'VGG16-BN masked, CIFAR-100 task-1 synthetic 32x32, batch 128 per GPU'
+BATCH = 128
+WD, LR, LR_MASK = 4e-5, 1e-2, 5e-4   # experiment1/CPG_cifar100_scratch_mul_1.5.sh:38-39,59
+VGG_FWD_FLOP_PER_IMG = 0.6641e9      # SURVEY 8d, probed with forward hooks
+VGG_TRAIN_FLOP_PER_IMG = 1.989e9
+
+
+# --------------------------------------------------------------------------------------------
+# model / mask construction shared by both arms (SURVEY 8d "Synthetic inputs")
+# --------------------------------------------------------------------------------------------
+class _Wrap(nn.Module):
+    """nn.DataParallel stand-in: the reference pruner expects ``model.module.datasets``."""
+
+    def __init__(self, module):
+        super().__init__()
+        self.module = module
+
+    def forward(self, *a, **k):
+        return self.module(*a, **k)
+
+
+def build_model(conv_cls, linear_cls, regime, device):
+    torch.manual_seed(1)                      # --seed default, CPG_cifar100_main_normal.py:79
+    model = VGGCifar(conv_cls, linear_cls, width=1.0)
+    datasets = ['task1'] if regime == 'task1' else ['task1', 'task2']
+    for d in datasets:
+        model.add_dataset(d, 5)
+    model.set_dataset(datasets[-1])
+    model = model.to(device)
+    cur = len(datasets)
+    rng = np.random.RandomState(7)
+    masks = {}
+    for name, m in model.named_modules():
+        if isinstance(m, (conv_cls, linear_cls)):
+            shape = tuple(m.weight.shape)
+            if regime == 'task1':
+                t = np.ones(shape, dtype=np.uint8)                 # after make_finetuning_mask
+            else:
+                t = np.where(rng.rand(*shape) < 0.5, 1, cur).astype(np.uint8)
+                p = np.full(shape, 0.01, dtype=np.float32)
+                old = t < cur
+                p[old] = rng.uniform(0, 0.01, size=int(old.sum())).astype(np.float32)
+                m.piggymask = nn.Parameter(torch.from_numpy(p).to(device))
+            masks['module.' + name] = torch.from_numpy(t).to(device)
+    return _Wrap(model), masks, datasets, cur
+
+
+def make_args(datasets, mode='finetune'):
+    a = argparse.Namespace()
+    a.mode, a.dataset, a.weight_decay = mode, datasets[-1], WD
+    a.finetune_again = True           # cur = index(dataset)+1
+    a.pruning_frequency, a.initial_sparsity, a.target_sparsity = 10, 0.0, 0.1
+    a.network_width_multiplier, a.log_path, a.cuda = 1.0, None, True
+    return a
+
+
+def make_optimizers(net, capturable):
+    sgd_params, adam_params = [], []
+    head = '.{}.'.format(len(net.module.datasets) - 1)
+    for name, p in net.named_parameters():        # routing of CPG_cifar100_main_normal.py:326-346
+        if 'classifiers' in name:
+            if head in name:
+                sgd_params.append(p)
+        elif 'piggymask' in name:
+            adam_params.append(p)
+        else:
+            sgd_params.append(p)
+    opts = [torch.optim.SGD(sgd_params, lr=LR, weight_decay=0.0, momentum=0.9, nesterov=True)]
+    if adam_params:
+        opts.append(torch.optim.Adam(adam_params, lr=LR_MASK, capturable=capturable))
+    return opts
+
+
+def synth_batches(n, batch, seed):
+    g = torch.Generator().manual_seed(seed)
+    return [(torch.randn(batch, 3, 32, 32, generator=g), torch.randint(0, 5, (batch,), generator=g))
+            for _ in range(n)]
+
+
+# --------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.path = gpu_index, None, None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile('w', suffix='.csv', delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, power, reasons = [], [], [], set()
+        try:
+            for line in open(self.path):
+                f = [c.strip() for c in line.split(',')]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+                except ValueError:
+                    continue
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'),
+                                   f[5:9]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            # under load = samples in the upper half of observed power
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons),
+                       samples=len(sm), power_w_max=max(power))
+        return out
+
+
+# --------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------
+class Trainer:
+    """The training step of utils/manager.py:54-75 over the product layers/pruner, optionally
+    captured into one CUDA graph (static input buffers)."""
+
+    def __init__(self, regime, device, world, use_graph=True):
+        import cpg_b200.layers as nl
+        from cpg_b200.prune import SparsePruner
+        from cpg_b200.ddp import GradAllReducer
+        self.device, self.world = device, world
+        self.net, self.masks, datasets, self.cur = build_model(nl.SharableConv2d, nl.SharableLinear, regime, device)
+        self.pruner = SparsePruner(self.net, self.masks, make_args(datasets), 0, 1, self.cur)
+        self.opts = make_optimizers(self.net, capturable=use_graph)
+        self.crit = nn.CrossEntropyLoss()
+        self.reducer = GradAllReducer(self.net, world) if world > 1 else None
+        self.net.train()
+        self.x = torch.zeros(BATCH, 3, 32, 32, device=device)
+        self.t = torch.zeros(BATCH, dtype=torch.int64, device=device)
+        self.loss = torch.zeros((), device=device)
+        self.graph = None
+        self.use_graph = use_graph
+
+    def _step_body(self):
+        for o in self.opts:
+            o.zero_grad(set_to_none=True)
+        out = self.net(self.x)
+        loss = self.crit(out, self.t)
+        loss.backward()
+        if self.reducer is not None:
+            self.reducer.reduce()
+        self.pruner.do_weight_decay_and_make_grads_zero()
+        for o in self.opts:
+            o.step()
+        self.loss.copy_(loss.detach())
+
+    def prepare(self, eager_warmup=3):
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(eager_warmup):
+                self._step_body()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        if self.use_graph:
+            from cpg_b200 import _lib
+            lib = _lib.load()
+            before = lib.cpgb_launch_count()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._step_body()
+            self.launches_per_step = lib.cpgb_launch_count() - before
+        else:
+            from cpg_b200 import _lib
+            lib = _lib.load()
+            before = lib.cpgb_launch_count()
+            self._step_body()
+            self.launches_per_step = lib.cpgb_launch_count() - before
+        torch.cuda.synchronize()
+
+    def step(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._step_body()
+
+
+def dist_setup(gpus):
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    return world, rank, local
+
+
+def timed_region(tr, batches_dev, steps, warmup, world, e2e_host=None):
+    """Returns (ms_total_max_over_ranks, last_loss).  e2e_host: list of pinned (x, t) host
+    batches -> per step H2D of the inputs + D2H of the loss inside the timed region."""
+    import torch.distributed as dist
+    n = len(batches_dev) if e2e_host is None else len(e2e_host)
+
+    def feed(i):
+        if e2e_host is None:
+            xb, tb = batches_dev[i % n]
+            tr.x.copy_(xb); tr.t.copy_(tb)
+        else:
+            xb, tb = e2e_host[i % n]
+            tr.x.copy_(xb, non_blocking=True); tr.t.copy_(tb, non_blocking=True)
+
+    last = 0.0
+    for i in range(warmup):
+        feed(i); tr.step()
+        if e2e_host is not None:
+            last = tr.loss.item()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        feed(warmup + i); tr.step()
+        if e2e_host is not None:
+            last = tr.loss.item()          # D2H read of the step's result
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=tr.device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    if e2e_host is None:
+        last = tr.loss.item()
+    return ms, last
+
+
+def measure_tf32_peak(device):
+    """TF32 dense peak is not in MEASURED_PEAKS.json: measure it the way that file measures bf16
+    (torch.matmul 8192^3, best of 10, CUDA events)."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    a = torch.randn(8192, 8192, device=device)
+    b = torch.randn(8192, 8192, device=device)
+    best = 1e9
+    for i in range(13):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(a, b); e1.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            best = min(best, e0.elapsed_time(e1))
+    torch.backends.cuda.matmul.allow_tf32 = old
+    del a, b
+    return 2 * 8192 ** 3 / (best * 1e-3) / 1e12
+
+
+def kernel_table(device, regime_has_piggy, iters=5):
+    """Per-layer, per-pass device time of OUR conv/linear kernels at the bench workload, timed
+    with CUDA events on the launching stream, L2 flushed between launches.  Returns rows and
+    the dominant pass (largest summed time) with its algorithmic FLOPs."""
+    import cpg_b200.layers as nl
+    from cpg_b200 import _lib
+    lib = _lib.load()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    shapes = [(3, 64, 32), (64, 64, 32), (64, 128, 16), (128, 128, 16), (128, 256, 8), (256, 256, 8), (256, 256, 8),
+              (256, 512, 4), (512, 512, 4), (512, 512, 4), (512, 512, 2), (512, 512, 2), (512, 512, 2)]
+    rows = []
+
+    def time_call(fn):
+        ts = []
+        for i in range(iters + 2):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                ts.append(e0.elapsed_time(e1))
+        return statistics.median(ts)
+
+    def bench_layer(kind, d, x, w, p, y, dy, t, flops, first):
+        ws = torch.empty(lib.cpgb_workspace_bytes(d), dtype=torch.uint8, device=device)
+        dW, dP, dx = torch.empty_like(w), (torch.empty_like(w) if p is not None else None), torch.empty_like(x)
+        st = _lib.stream_ptr()
+        P = _lib.ptr
+        f = time_call(lambda: _lib.check(lib.cpgb_conv2d_fprop(d, P(x), P(w), P(p), None, P(y), 5e-3, P(ws),
+                                                                ws.numel(), st), 'fprop'))
+        dg = 0.0 if first else time_call(lambda: _lib.check(lib.cpgb_conv2d_dgrad(
+            d, P(dy), P(w), P(p), P(dx), 5e-3, P(ws), ws.numel(), st), 'dgrad'))
+        wg = time_call(lambda: _lib.check(lib.cpgb_conv2d_wgrad_fused(
+            d, P(x), P(dy), P(w), P(p), P(t), 1, WD, _lib.GRAD_FINETUNE, P(dW), P(dP), None, 5e-3, P(ws),
+            ws.numel(), st), 'wgrad'))
+        rows.append({'layer': kind, 'flop': flops, 'fprop_ms': f, 'dgrad_ms': dg, 'wgrad_ms': wg,
+                     'n_weights': w.numel()})
+
+    for i, (C, K, HW) in enumerate(shapes):
+        x = torch.randn(BATCH, C, HW, HW, device=device).contiguous(memory_format=torch.channels_last)
+        w = torch.randn(K, C, 3, 3, device=device) * 0.05
+        p = torch.rand_like(w) * 0.01 if regime_has_piggy else None
+        y = torch.empty(BATCH, K, HW, HW, device=device).contiguous(memory_format=torch.channels_last)
+        dy = torch.randn_like(y)
+        t = torch.ones(w.shape, dtype=torch.uint8, device=device)
+        d = _lib.conv_desc(x.shape, x.stride(), w.shape, y.shape, y.stride(), (1, 1), (1, 1), (1, 1), 1)
+        bench_layer(f'conv{C}x{K}@{HW}', d, x, w, p, y, dy, t, 2.0 * BATCH * K * C * 9 * HW * HW, i == 0)
+    for (I, O) in ((512, 4096), (4096, 4096)):
+        x = torch.randn(BATCH, I, device=device)
+        w = torch.randn(O, I, device=device) * 0.01
+        p = torch.rand_like(w) * 0.01 if regime_has_piggy else None
+        y = torch.empty(BATCH, O, device=device)
+        dy = torch.randn_like(y)
+        t = torch.ones(w.shape, dtype=torch.uint8, device=device)
+        d = _lib.ConvDesc()
+        lib.cpgb_linear_desc(d, BATCH, I, O)
+        bench_layer(f'fc{I}x{O}', d, x, w, p, y, dy, t, 2.0 * BATCH * I * O, False)
+    tot = {k: sum(r[k + '_ms'] for r in rows) for k in ('fprop', 'dgrad', 'wgrad')}
+    flops = {'fprop': sum(r['flop'] for r in rows), 'dgrad': sum(r['flop'] for r in rows[1:]),
+             'wgrad': sum(r['flop'] for r in rows)}
+    dom = max(tot, key=tot.get)
+    return rows, tot, flops, dom
+
+
+def cpu_port_step_time(regime, batch, steps, warmup, threads):
+    """The reference's CPU path (oracle port: OracleSharable* layers + OraclePruner), same step
+    sequence, on `threads` host cores."""
+    from oracle import cpg_oracle as O
+    torch.set_num_threads(threads)
+    net, masks, datasets, cur = build_model(O.OracleSharableConv2d, O.OracleSharableLinear, regime, 'cpu')
+    masks = {k[len('module.'):]: v for k, v in masks.items()}
+    pruner = O.OraclePruner(net.module, masks, mode='finetune', weight_decay=WD, cur=cur, inference_idx=cur)
+    opts = make_optimizers(net, capturable=False)
+    crit = nn.CrossEntropyLoss()
+    net.train()
+    data = synth_batches(2, batch, seed=11)
+    times = []
+    for i in range(warmup + steps):
+        x, t = data[i % 2]
+        t0 = time.perf_counter()
+        for o in opts:
+            o.zero_grad()
+        loss = crit(net(x), t)
+        loss.backward()
+        pruner.do_weight_decay_and_make_grads_zero()
+        for o in opts:
+            o.step()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return sum(times), float(loss.item())
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's own CPU implementation of the path (the oracle port --
+    the reference is Python and cannot travel to the GPU box) on all host cores."""
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    # calibrate the per-step sample so the whole run ends within a few minutes
+    t_cal, _ = cpu_port_step_time('task1', 16, 1, 1, cores)
+    per_img = t_cal / 16
+    budget = 150.0
+    sample = BATCH
+    while sample > 8 and per_img * sample * (args.steps + args.warmup) > budget:
+        sample //= 2
+    total, _ = cpu_port_step_time('task1', sample, args.steps, args.warmup, cores)
+    value = sample * args.steps / total
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total / args.steps * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'regime': 'task1 (R1: no piggymask, T==1)', 'batch_per_step': sample},
+        'cpu_baseline': {'value': value, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
+                         'sample': f'{args.steps} steps x {sample} images (torch {torch.__version__} CPU, '
+                                   f'{torch.get_num_threads()} threads)'},
+        'e2e': {'value': value, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--no-extras', action='store_true', help='skip kernel table / task-2 regime / cpu baseline')
+    ap.add_argument('--path', default='auto', choices=['auto', 'simt'])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == 'reference':
+        return run_reference_arm(args)
+
+    world, rank, local = dist_setup(args.gpus)
+    device = torch.device('cuda', local)
+    torch.cuda.set_device(device)
+    from cpg_b200 import _lib
+    lib = _lib.load()
+    if args.path == 'simt':
+        _lib.set_path(_lib.PATH_SIMT)
+
+    def run_regime(regime, want_e2e):
+        tr = Trainer(regime, device, world, use_graph=not args.no_graph)
+        tr.prepare()
+        batches = synth_batches(8, BATCH, seed=100 + rank)
+        dev_batches = [(x.to(device), t.to(device)) for x, t in batches]
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        ms, loss = timed_region(tr, dev_batches, args.steps, args.warmup, world)
+        clocks = sampler.stop() if rank == 0 else None
+        res = {'ms': ms, 'loss': loss, 'clocks': clocks, 'launches_per_step': tr.launches_per_step}
+        if want_e2e:
+            host = [(x.pin_memory(), t.pin_memory()) for x, t in batches]
+            ms2, loss2 = timed_region(tr, None, args.steps, args.warmup, world, e2e_host=host)
+            res.update(e2e_ms=ms2, e2e_loss=loss2,
+                       h2d=host[0][0].numel() * 4 + host[0][1].numel() * 8, d2h=4)
+        del tr
+        torch.cuda.empty_cache()
+        return res
+
+    r1 = run_regime('task1', True)
+    extras = not args.no_extras
+    r2 = run_regime('task2', True) if extras else None
+
+    line = None
+    if rank == 0:
+        imgs = BATCH * world * args.steps
+        value = imgs / (r1['ms'] * 1e-3)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:
+            pass
+        line = {
+            'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': r1['ms'] / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'tf32 (fp32 in/out, fp32 accumulate)' if args.path == 'auto' else 'f32',
+            'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'regime': 'task1 (R1: no piggymask, T==1, cur=1)',
+                       'global_batch': BATCH * world, 'parallelism': f'dp{world}',
+                       'step': 'utils/manager.py:54-75 sequence, SGD-nesterov (+Adam on piggymasks in task2)',
+                       'cuda_graph': not args.no_graph,
+                       'l2': 'per-step working set (weights+grads+momentum 400 MB, activations 280 MB) exceeds the 126 MB L2; 8 distinct input batches rotate'},
+            'clocks': {k: r1['clocks'].get(k) for k in ('sm_mhz', 'sm_max_mhz', 'reasons')} if r1['clocks'] else None,
+            'e2e': {'value': imgs / (r1['e2e_ms'] * 1e-3), 'unit': 'images/s', 'h2d_bytes_per_step': r1['h2d'],
+                    'd2h_bytes_per_step': r1['d2h'], 'ms_per_step': r1['e2e_ms'] / args.steps},
+            'gpu_launches': int(r1['launches_per_step'] * args.steps),
+            'loss': r1['loss'],
+        }
+        if r2 is not None:
+            line['regime_task2'] = {
+                'regime': 'task2 (R2: piggymask on all 15 sharable layers, 50% old weights, half picked)',
+                'value': imgs / (r2['ms'] * 1e-3), 'ms_per_step': r2['ms'] / args.steps,
+                'e2e_value': imgs / (r2['e2e_ms'] * 1e-3), 'gpu_launches': int(r2['launches_per_step'] * args.steps),
+                'loss': r2['loss']}
+    if extras and world == 1:
+        tf32_peak = measure_tf32_peak(device)
+        rows, tot, flops, dom = kernel_table(device, regime_has_piggy=False)
+        step_ms = r1['ms'] / args.steps
+        achieved = flops[dom] / (tot[dom] * 1e-3) / 1e12
+        line['roofline'] = {
+            'bound': 'tensor', 'kernel': f'masked implicit-GEMM {dom} (all 15 sharable layers of one step)',
+            'achieved': achieved, 'peak': tf32_peak, 'unit': 'TFLOP/s', 'frac': achieved / tf32_peak,
+            'traffic': None,
+            'peak_source': 'measured in this run: cuBLAS TF32 torch.matmul 8192^3 best of 10 (TF32 is not in MEASURED_PEAKS.json)',
+            'share_of_step': tot[dom] / step_ms,
+            'how': 'CUDA events on the launching stream around each launch, L2 flushed (256 MiB write) between launches, median of 5',
+        }
+        line['kernels'] = {'total_ms': tot, 'algorithmic_gflop': {k: v / 1e9 for k, v in flops.items()},
+                           'conv_linear_share_of_step': sum(tot.values()) / step_ms,
+                           'per_layer': [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()}
+                                         for r in rows]}
+        line['peaks'] = {'hbm_gbs': peaks.get('hbm_gbs'), 'bf16_tflops': peaks.get('bf16_tflops'),
+                         'tf32_tflops_measured_here': tf32_peak}
+        cores = os.cpu_count() or 1
+        total, _ = cpu_port_step_time('task1', BATCH, 3, 1, cores)
+        line['cpu_baseline'] = {'value': BATCH * 3 / total, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
+                                'sample': f'3 steps x {BATCH} images after 1 warm-up (oracle port of the reference '
+                                          f'step on torch {torch.__version__} CPU, {torch.get_num_threads()} threads)'}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

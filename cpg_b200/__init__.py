@@ -1,0 +1,33 @@
+"""cpg_b200 -- B200-native (sm_100a) implementation of CPG's masked-convolution train/prune
+hot path, behind the reference's own module API:
+
+    cpg_b200.layers  <->  models/layers.py   (Binarizer, SharableConv2d, SharableLinear)
+    cpg_b200.prune   <->  utils/prune.py     (SparsePruner)
+
+``install()`` aliases them into ``sys.modules`` so an unmodified CPG checkout picks them up.
+"""
+import sys
+
+__version__ = '0.1.0'
+
+
+def install():
+    """Make ``import models.layers`` / ``from utils.prune import SparsePruner`` resolve to this
+    package inside a CPG checkout (call before importing ``utils.manager``)."""
+    from . import layers, prune
+    sys.modules['models.layers'] = layers
+    try:
+        import models  # the checkout's package
+        models.layers = layers
+    except Exception:
+        pass
+    try:
+        import utils.prune as ref_prune
+        ref_prune.SparsePruner = prune.SparsePruner
+        ref_prune.nl = layers
+        import utils.manager as ref_manager
+        ref_manager.SparsePruner = prune.SparsePruner
+        ref_manager.nl = layers
+    except Exception:
+        pass
+    return layers, prune

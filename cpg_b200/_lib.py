@@ -1,0 +1,113 @@
+"""ctypes binding of libcpgb200.so (include/cpgb200.h).  There is no CPU or PyTorch
+fallback: a missing library, or a call with CPU tensors, raises."""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libcpgb200.so')
+
+GRAD_RAW, GRAD_FINETUNE, GRAD_PRUNE = 0, 1, 2
+PATH_AUTO, PATH_SIMT, PATH_TCGEN05 = 0, 1, 2
+
+EXPORTS = [
+    'cpgb_version', 'cpgb_last_error', 'cpgb_set_path', 'cpgb_get_path', 'cpgb_launch_count', 'cpgb_linear_desc',
+    'cpgb_workspace_bytes', 'cpgb_binarize', 'cpgb_conv2d_fprop', 'cpgb_conv2d_dgrad',
+    'cpgb_conv2d_wgrad_fused', 'cpgb_grad_epilogue', 'cpgb_prune_workspace_bytes', 'cpgb_prune_select',
+    'cpgb_apply_mask', 'cpgb_make_finetuning_mask', 'cpgb_mask_stats', 'cpgb_merge_grads',
+    'cpgb_split_merged_grad',
+]
+
+
+class ConvDesc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in
+                ('N', 'C', 'H', 'W', 'K', 'R', 'S', 'P', 'Q', 'stride_h', 'stride_w', 'pad_h', 'pad_w',
+                 'dil_h', 'dil_w', 'groups')] + [('xs', ctypes.c_int64 * 4), ('ys', ctypes.c_int64 * 4)]
+
+
+class CpgbError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load libcpgb200.so (built by ``__graft_entry__.build()`` / ``make -C cpg_b200/csrc``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CpgbError(f'{LIB_PATH} is missing: build it with `python -c "import __graft_entry__ as g; '
+                        f'g.build()"` (there is no CPU fallback for the masked-conv path)')
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, f32, i32, i64, sz, dbl = (ctypes.c_void_p, ctypes.c_float, ctypes.c_int32, ctypes.c_int64,
+                                  ctypes.c_size_t, ctypes.c_double)
+    dp = ctypes.POINTER(ConvDesc)
+    sig = {
+        'cpgb_version': (ctypes.c_int, []),
+        'cpgb_last_error': (ctypes.c_char_p, []),
+        'cpgb_set_path': (ctypes.c_int, [ctypes.c_int]),
+        'cpgb_get_path': (ctypes.c_int, []),
+        'cpgb_launch_count': (ctypes.c_int64, []),
+        'cpgb_linear_desc': (None, [dp, i32, i32, i32]),
+        'cpgb_workspace_bytes': (sz, [dp]),
+        'cpgb_binarize': (ctypes.c_int, [vp, vp, i64, f32, vp]),
+        'cpgb_conv2d_fprop': (ctypes.c_int, [dp, vp, vp, vp, vp, vp, f32, vp, sz, vp]),
+        'cpgb_conv2d_dgrad': (ctypes.c_int, [dp, vp, vp, vp, vp, f32, vp, sz, vp]),
+        'cpgb_conv2d_wgrad_fused': (ctypes.c_int, [dp, vp, vp, vp, vp, vp, i32, f32, i32, vp, vp, vp, f32,
+                                                  vp, sz, vp]),
+        'cpgb_grad_epilogue': (ctypes.c_int, [vp, vp, vp, vp, i64, i32, f32, i32, vp]),
+        'cpgb_prune_workspace_bytes': (sz, []),
+        'cpgb_prune_select': (ctypes.c_int, [vp, vp, i64, i32, dbl, vp, vp, sz, vp]),
+        'cpgb_apply_mask': (ctypes.c_int, [vp, vp, i64, i32, vp]),
+        'cpgb_make_finetuning_mask': (ctypes.c_int, [vp, i64, i32, vp]),
+        'cpgb_mask_stats': (ctypes.c_int, [vp, vp, i64, i32, vp, vp]),
+        'cpgb_merge_grads': (ctypes.c_int, [vp, vp, vp, i64, vp]),
+        'cpgb_split_merged_grad': (ctypes.c_int, [vp, vp, i64, i32, vp, vp, vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().cpgb_last_error()
+        raise CpgbError(f'{what} failed with code {rc}: {msg.decode() if msg else ""}')
+
+
+def ptr(t):
+    """Device pointer of a CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise CpgbError('cpg_b200 kernels need CUDA tensors; there is no CPU path '
+                        '(the CPU restatement lives in oracle/ and is test-only)')
+    return t.data_ptr()
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def set_path(path):
+    return load().cpgb_set_path(int(path))
+
+
+def conv_desc(x_shape, x_strides, w_shape, y_shape, y_strides, stride, padding, dilation, groups):
+    d = ConvDesc()
+    d.N, d.C, d.H, d.W = x_shape
+    d.K, _, d.R, d.S = w_shape
+    d.P, d.Q = y_shape[2], y_shape[3]
+    d.stride_h, d.stride_w = stride
+    d.pad_h, d.pad_w = padding
+    d.dil_h, d.dil_w = dilation
+    d.groups = groups
+    for i in range(4):
+        d.xs[i] = x_strides[i]
+        d.ys[i] = y_strides[i]
+    return d

@@ -1,0 +1,161 @@
+// extern "C" surface of libcpgb200.so: argument validation, path dispatch (tcgen05 implicit
+// GEMM vs CUDA-core kernels), workspace accounting.  See include/cpgb200.h for the contract.
+#include <atomic>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace cpgb {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int> g_path{CPGB_PATH_AUTO};
+static std::atomic<long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what) {
+  set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+  return CPGB_ECUDA;
+}
+
+int validate_desc(const cpgb_conv_desc *d) {
+  if (!d) { set_error("null descriptor"); return CPGB_EINVAL; }
+  if (d->N < 0 || d->C <= 0 || d->H <= 0 || d->W <= 0 || d->K <= 0 || d->R <= 0 || d->S <= 0) {
+    set_error("bad tensor extents"); return CPGB_EINVAL;
+  }
+  if (d->groups <= 0 || d->C % d->groups || d->K % d->groups) {
+    // models/layers.py:65-68 raises ValueError for these
+    set_error("in/out channels must be divisible by groups"); return CPGB_EINVAL;
+  }
+  if (d->stride_h <= 0 || d->stride_w <= 0 || d->dil_h <= 0 || d->dil_w <= 0 || d->pad_h < 0 || d->pad_w < 0) {
+    set_error("bad stride/dilation/padding"); return CPGB_EINVAL;
+  }
+  int P = (d->H + 2 * d->pad_h - d->dil_h * (d->R - 1) - 1) / d->stride_h + 1;
+  int Q = (d->W + 2 * d->pad_w - d->dil_w * (d->S - 1) - 1) / d->stride_w + 1;
+  if (P != d->P || Q != d->Q || P <= 0 || Q <= 0) {
+    set_error("output extent mismatch: expected P=%d Q=%d, got P=%d Q=%d", P, Q, d->P, d->Q);
+    return CPGB_EINVAL;
+  }
+  if ((long long)d->N * d->P * d->Q >= (1ll << 31) || (long long)d->N * d->H * d->W >= (1ll << 31) ||
+      (long long)(d->C / d->groups) * d->R * d->S >= (1ll << 31)) {
+    set_error("GEMM extent exceeds int32"); return CPGB_EINVAL;
+  }
+  return CPGB_OK;
+}
+
+static inline size_t weight_elems(const cpgb_conv_desc *d) {
+  return (size_t)d->K * (size_t)(d->C / d->groups) * (size_t)d->R * (size_t)d->S;
+}
+
+}  // namespace cpgb
+
+using namespace cpgb;
+
+extern "C" {
+
+int cpgb_version(void) { return CPGB_VERSION; }
+const char *cpgb_last_error(void) { return g_err; }
+int cpgb_set_path(int path) {
+  if (path < CPGB_PATH_AUTO || path > CPGB_PATH_TCGEN05) return g_path.load();
+  return g_path.exchange(path);
+}
+int cpgb_get_path(void) { return g_path.load(); }
+int64_t cpgb_launch_count(void) { return (int64_t)g_launches.load(); }
+
+void cpgb_linear_desc(cpgb_conv_desc *d, int32_t M, int32_t I, int32_t O) {
+  memset(d, 0, sizeof(*d));
+  d->N = M; d->C = I; d->H = 1; d->W = 1; d->K = O; d->R = 1; d->S = 1; d->P = 1; d->Q = 1;
+  d->stride_h = d->stride_w = 1; d->dil_h = d->dil_w = 1; d->pad_h = d->pad_w = 0; d->groups = 1;
+  d->xs[0] = I; d->xs[1] = 1; d->xs[2] = I; d->xs[3] = I;
+  d->ys[0] = O; d->ys[1] = 1; d->ys[2] = O; d->ys[3] = O;
+}
+
+size_t cpgb_workspace_bytes(const cpgb_conv_desc *d) {
+  if (!d || d->groups <= 0) return 0;
+  size_t g_bytes = weight_elems(d) * sizeof(float);           // raw weight gradient (wgrad)
+  size_t tc = tc_workspace_bytes(*d);
+  g_bytes = (g_bytes + 255) & ~(size_t)255;
+  return g_bytes + ((tc + 255) & ~(size_t)255);
+}
+
+static int pick_tc(const cpgb_conv_desc *d, int op, bool *use_tc) {
+  int path = g_path.load();
+  bool ok = path != CPGB_PATH_SIMT && tc_eligible(*d, op);
+  if (path == CPGB_PATH_TCGEN05 && !ok) {
+    set_error("tcgen05 path forced but shape not eligible (op %d)", op);
+    return CPGB_ENOTELIGIBLE;
+  }
+  *use_tc = ok;
+  return CPGB_OK;
+}
+
+int cpgb_conv2d_fprop(const cpgb_conv_desc *d, const float *x, const float *w, const float *piggy,
+                      const float *bias, float *y, float thr, void *ws, size_t ws_bytes, void *stream) {
+  int rc = validate_desc(d);
+  if (rc) return rc;
+  if (!x || !w || !y) { set_error("cpgb_conv2d_fprop: null pointer"); return CPGB_EINVAL; }
+  if (d->N == 0) return CPGB_OK;
+  bool use_tc;
+  if ((rc = pick_tc(d, 0, &use_tc))) return rc;
+  if (use_tc) return tc_fprop(*d, x, w, piggy, bias, y, thr, ws, ws_bytes, (cudaStream_t)stream);
+  return simt_fprop(make_geom(*d), x, w, piggy, bias, y, thr, (cudaStream_t)stream);
+}
+
+int cpgb_conv2d_dgrad(const cpgb_conv_desc *d, const float *dy, const float *w, const float *piggy, float *dx,
+                      float thr, void *ws, size_t ws_bytes, void *stream) {
+  int rc = validate_desc(d);
+  if (rc) return rc;
+  if (!dy || !w || !dx) { set_error("cpgb_conv2d_dgrad: null pointer"); return CPGB_EINVAL; }
+  if (d->N == 0) return CPGB_OK;
+  bool use_tc;
+  if ((rc = pick_tc(d, 1, &use_tc))) return rc;
+  if (use_tc) return tc_dgrad(*d, dy, w, piggy, dx, thr, ws, ws_bytes, (cudaStream_t)stream);
+  return simt_dgrad(make_geom(*d), dy, w, piggy, dx, thr, (cudaStream_t)stream);
+}
+
+int cpgb_conv2d_wgrad_fused(const cpgb_conv_desc *d, const float *x, const float *dy, const float *w,
+                            const float *piggy, const uint8_t *tmask, int32_t cur, float weight_decay,
+                            int32_t mode, float *dW, float *dP, float *dbias, float thr, void *ws,
+                            size_t ws_bytes, void *stream) {
+  int rc = validate_desc(d);
+  if (rc) return rc;
+  if (!x || !dy || !w || !dW) { set_error("cpgb_conv2d_wgrad_fused: null pointer"); return CPGB_EINVAL; }
+  if (mode < CPGB_GRAD_RAW || mode > CPGB_GRAD_PRUNE) { set_error("bad grad mode %d", mode); return CPGB_EINVAL; }
+  if (mode != CPGB_GRAD_RAW && !tmask) { set_error("fused grad modes need the task mask"); return CPGB_EINVAL; }
+  if ((piggy == nullptr) != (dP == nullptr)) { set_error("dP must be given iff piggy is"); return CPGB_EINVAL; }
+  const size_t n = weight_elems(d);
+  if (!ws || ws_bytes < cpgb_workspace_bytes(d)) {
+    set_error("workspace %zu < %zu", ws_bytes, cpgb_workspace_bytes(d));
+    return CPGB_EWORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  Geom g = make_geom(*d);
+  float *gbuf = reinterpret_cast<float *>(ws);
+  if (d->N == 0) {
+    CPGB_CUDA_OK(cudaMemsetAsync(gbuf, 0, n * sizeof(float), st));
+  } else {
+    bool use_tc;
+    if ((rc = pick_tc(d, 2, &use_tc))) return rc;
+    if (use_tc) {
+      // tensor-core wgrad accumulates straight into dense [K, C/g, R, S] order
+      const size_t goff = (n * sizeof(float) + 255) & ~(size_t)255;
+      if ((rc = tc_wgrad_raw(*d, x, dy, gbuf, (char *)ws + goff, ws_bytes - goff, st))) return rc;
+    } else {
+      if ((rc = simt_wgrad_raw(g, x, dy, gbuf, st))) return rc;
+    }
+  }
+  if ((rc = wgrad_epilogue(gbuf, w, piggy, tmask, (long long)n, cur, weight_decay, mode, thr, dW, dP, st))) return rc;
+  if (dbias) {
+    if (d->N == 0) CPGB_CUDA_OK(cudaMemsetAsync(dbias, 0, d->K * sizeof(float), st));
+    else if ((rc = bias_grad(g, dy, dbias, st))) return rc;
+  }
+  return CPGB_OK;
+}
+
+}  // extern "C"

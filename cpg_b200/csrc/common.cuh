@@ -1,0 +1,85 @@
+// Shared host/device helpers for libcpgb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/cpgb200.h"
+
+namespace cpgb {
+
+// thread-local error text behind cpgb_last_error()
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what);
+void count_launches(int n);
+
+#define CPGB_CUDA_OK(expr)                                   \
+  do {                                                       \
+    cudaError_t _e = (expr);                                 \
+    if (_e != cudaSuccess) return cpgb::cuda_fail(_e, #expr); \
+  } while (0)
+
+#define CPGB_LAUNCH_OK_N(what, n)                             \
+  do {                                                        \
+    cudaError_t _e = cudaGetLastError();                      \
+    if (_e != cudaSuccess) return cpgb::cuda_fail(_e, what);  \
+    cpgb::count_launches(n);                                  \
+  } while (0)
+#define CPGB_LAUNCH_OK(what) CPGB_LAUNCH_OK_N(what, 1)
+
+// Device-side copy of cpgb_conv_desc with the derived per-group sizes.
+struct Geom {
+  int N, C, H, W, K, R, S, P, Q;
+  int sh, sw, ph, pw, dh, dw, groups;
+  int Cg, Kg, RS, PQ, HW;
+  long long xs0, xs1, xs2, xs3, ys0, ys1, ys2, ys3;
+};
+
+inline Geom make_geom(const cpgb_conv_desc &d) {
+  Geom g;
+  g.N = d.N; g.C = d.C; g.H = d.H; g.W = d.W; g.K = d.K; g.R = d.R; g.S = d.S; g.P = d.P; g.Q = d.Q;
+  g.sh = d.stride_h; g.sw = d.stride_w; g.ph = d.pad_h; g.pw = d.pad_w; g.dh = d.dil_h; g.dw = d.dil_w;
+  g.groups = d.groups;
+  g.Cg = d.C / d.groups; g.Kg = d.K / d.groups; g.RS = d.R * d.S; g.PQ = d.P * d.Q; g.HW = d.H * d.W;
+  g.xs0 = d.xs[0]; g.xs1 = d.xs[1]; g.xs2 = d.xs[2]; g.xs3 = d.xs[3];
+  g.ys0 = d.ys[0]; g.ys1 = d.ys[1]; g.ys2 = d.ys[2]; g.ys3 = d.ys[3];
+  return g;
+}
+
+int validate_desc(const cpgb_conv_desc *d);
+
+// Binarizer applied to a weight: (piggy > thr ? 1 : piggy <= thr ? 0 : piggy[NaN]) * w,
+// a true multiply like models/layers.py:103 so NaN/Inf propagate exactly as in the reference.
+__device__ __forceinline__ float binarize_val(float p, float thr) {
+  return p > thr ? 1.0f : (p <= thr ? 0.0f : p);
+}
+__device__ __forceinline__ float masked_weight(float w, const float *piggy, long long idx, float thr) {
+  return piggy ? binarize_val(__ldg(piggy + idx), thr) * w : w;
+}
+
+// ---- entry points implemented in the individual .cu files ----
+// CUDA-core (fp32 FFMA) implicit GEMM, any geometry.
+int simt_fprop(const Geom &g, const float *x, const float *w, const float *piggy, const float *bias,
+               float *y, float thr, cudaStream_t st);
+int simt_dgrad(const Geom &g, const float *dy, const float *w, const float *piggy, float *dx, float thr,
+               cudaStream_t st);
+// raw weight gradient into gbuf[K*Cg*R*S] (fp32, overwritten)
+int simt_wgrad_raw(const Geom &g, const float *x, const float *dy, float *gbuf, cudaStream_t st);
+int bias_grad(const Geom &g, const float *dy, float *dbias, cudaStream_t st);
+
+// fused epilogue g -> (dW, dP)  
+int wgrad_epilogue(const float *gbuf, const float *w, const float *piggy, const uint8_t *tmask, long long n,
+                   int cur, float wd, int mode, float thr, float *dW, float *dP, cudaStream_t st);
+
+// tcgen05 implicit GEMM (tc_conv.cu).  *_eligible() says whether the shape is supported.
+bool tc_eligible(const cpgb_conv_desc &d, int op);  // op: 0 fprop, 1 dgrad, 2 wgrad
+size_t tc_workspace_bytes(const cpgb_conv_desc &d);
+int tc_fprop(const cpgb_conv_desc &d, const float *x, const float *w, const float *piggy, const float *bias,
+             float *y, float thr, void *ws, size_t ws_bytes, cudaStream_t st);
+int tc_dgrad(const cpgb_conv_desc &d, const float *dy, const float *w, const float *piggy, float *dx,
+             float thr, void *ws, size_t ws_bytes, cudaStream_t st);
+int tc_wgrad_raw(const cpgb_conv_desc &d, const float *x, const float *dy, float *gbuf_krsc, void *ws,
+                 size_t ws_bytes, cudaStream_t st);
+
+}  // namespace cpgb

@@ -1,0 +1,261 @@
+// HBM-bound element kernels of the path: Binarizer (a1), the fused wgrad epilogue (K6-K8),
+// the standalone grad mask (a6), apply_mask / make_finetuning_mask (a9/a10), mask statistics
+// (K12) and the data-parallel merge/split helpers.  All are 16-byte vectorised grid-stride
+// loops sized to a multiple of the SM count.
+#include "common.cuh"
+
+namespace cpgb {
+
+static int g_num_sms = 0;
+static inline int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    g_num_sms = n > 0 ? n : 148;
+  }
+  return g_num_sms;
+}
+static inline int grid_for(long long nvec, int threads = 256, int ctas_per_sm = 8) {
+  long long want = (nvec + threads - 1) / threads;
+  long long cap = (long long)num_sms() * ctas_per_sm;
+  if (want < 1) want = 1;
+  return (int)(want < cap ? want : cap);
+}
+static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// ---------------- a1 Binarizer.forward (models/layers.py:15-19) ----------------
+__global__ void __launch_bounds__(256) binarize_kernel(const float *__restrict__ p, float *__restrict__ out,
+                                                       long long n, float thr, bool vec) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (vec) {
+    const long long n4 = n >> 2;
+    for (long long v = i; v < n4; v += stride) {
+      float4 a = __ldg(reinterpret_cast<const float4 *>(p) + v);
+      float4 b = make_float4(binarize_val(a.x, thr), binarize_val(a.y, thr), binarize_val(a.z, thr),
+                             binarize_val(a.w, thr));
+      reinterpret_cast<float4 *>(out)[v] = b;
+    }
+    for (long long t = (n4 << 2) + i; t < n; t += stride) out[t] = binarize_val(p[t], thr);
+  } else {
+    for (; i < n; i += stride) out[i] = binarize_val(p[i], thr);
+  }
+}
+
+// ---------------- fused wgrad epilogue ----------------
+// g: raw weight gradient dL/dW_eff.  One pass produces what optimizers.step() must see:
+//   RAW      : dW = g*b                     dP = g*W                      (models/layers.py:21-23,103)
+//   FINETUNE : dW = (g*b + wd*W)[T==cur]    dP = (g*W)[1<=T<cur]          (utils/prune.py:203-208)
+//   PRUNE    : dW = (g*b + wd*W)[T==cur]    dP = 0                        (utils/prune.py:203-205,210)
+__device__ __forceinline__ void epi_one(float g, float w, float p, bool has_p, unsigned t, int cur, float wd,
+                                        int mode, float thr, float &dw, float &dp) {
+  float gb = has_p ? g * binarize_val(p, thr) : g;
+  if (mode == CPGB_GRAD_RAW) {
+    dw = gb;
+    dp = g * w;
+    return;
+  }
+  dw = (t == (unsigned)cur) ? fmaf(wd, w, gb) : 0.f;
+  dp = (mode == CPGB_GRAD_FINETUNE && t != 0u && t < (unsigned)cur) ? g * w : 0.f;
+}
+
+__global__ void __launch_bounds__(256)
+wgrad_epilogue_kernel(const float *__restrict__ g, const float *__restrict__ w, const float *__restrict__ piggy,
+                      const uint8_t *__restrict__ tmask, long long n, int cur, float wd, int mode, float thr,
+                      float *__restrict__ dW, float *__restrict__ dP, bool vec) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool has_p = piggy != nullptr;
+  long long tail = 0;
+  if (vec) {
+    const long long n4 = n >> 2;
+    for (long long v = i0; v < n4; v += stride) {
+      float4 gg = __ldg(reinterpret_cast<const float4 *>(g) + v);
+      float4 ww = __ldg(reinterpret_cast<const float4 *>(w) + v);
+      float4 pp = has_p ? __ldg(reinterpret_cast<const float4 *>(piggy) + v) : make_float4(0, 0, 0, 0);
+      uchar4 tt = tmask ? __ldg(reinterpret_cast<const uchar4 *>(tmask) + v) : make_uchar4(0, 0, 0, 0);
+      float4 ow, op;
+      epi_one(gg.x, ww.x, pp.x, has_p, tt.x, cur, wd, mode, thr, ow.x, op.x);
+      epi_one(gg.y, ww.y, pp.y, has_p, tt.y, cur, wd, mode, thr, ow.y, op.y);
+      epi_one(gg.z, ww.z, pp.z, has_p, tt.z, cur, wd, mode, thr, ow.z, op.z);
+      epi_one(gg.w, ww.w, pp.w, has_p, tt.w, cur, wd, mode, thr, ow.w, op.w);
+      reinterpret_cast<float4 *>(dW)[v] = ow;
+      if (dP) reinterpret_cast<float4 *>(dP)[v] = op;
+    }
+    tail = n4 << 2;
+  }
+  for (long long i = tail + i0; i < n; i += stride) {
+    float ow, op;
+    epi_one(g[i], w[i], has_p ? piggy[i] : 0.f, has_p, tmask ? tmask[i] : 0u, cur, wd, mode, thr, ow, op);
+    dW[i] = ow;
+    if (dP) dP[i] = op;
+  }
+}
+
+int wgrad_epilogue(const float *gbuf, const float *w, const float *piggy, const uint8_t *tmask, long long n,
+                   int cur, float wd, int mode, float thr, float *dW, float *dP, cudaStream_t st) {
+  bool vec = aligned16(gbuf) && aligned16(w) && aligned16(dW) && (!piggy || aligned16(piggy)) &&
+             (!dP || aligned16(dP)) && (!tmask || (reinterpret_cast<uintptr_t>(tmask) & 3) == 0);
+  wgrad_epilogue_kernel<<<grid_for(n / 4 + 1), 256, 0, st>>>(gbuf, w, piggy, tmask, n, cur, wd, mode, thr, dW,
+                                                            dP, vec);
+  CPGB_LAUNCH_OK("wgrad_epilogue");
+  return CPGB_OK;
+}
+
+// ---------------- a6 standalone, in place (utils/prune.py:195-211) ----------------
+__global__ void __launch_bounds__(256)
+grad_epilogue_kernel(float *__restrict__ dW, float *__restrict__ dP, const float *__restrict__ w,
+                     const uint8_t *__restrict__ tmask, long long n, int cur, float wd, int mode) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    unsigned t = tmask[i];
+    if (dW) dW[i] = (t == (unsigned)cur) ? fmaf(wd, w[i], dW[i]) : 0.f;
+    if (dP) {
+      bool keep = (mode == CPGB_GRAD_FINETUNE) && t != 0u && t < (unsigned)cur;
+      if (!keep) dP[i] = 0.f;
+    }
+  }
+}
+
+// ---------------- a9 apply_mask / make_pruned_zero (utils/prune.py:213-231) ----------------
+__global__ void __launch_bounds__(256)
+apply_mask_kernel(float *__restrict__ w, const uint8_t *__restrict__ tmask, long long n, int inference_idx) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    unsigned t = tmask[i];
+    if (t == 0u || t > (unsigned)inference_idx) w[i] = 0.f;
+  }
+}
+
+// ---------------- a10 make_finetuning_mask (utils/prune.py:233-243) ----------------
+__global__ void __launch_bounds__(256)
+finetuning_mask_kernel(uint8_t *__restrict__ tmask, long long n, int new_cur) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    if (tmask[i] == 0) tmask[i] = (uint8_t)new_cur;
+}
+
+// ---------------- K12 statistics (utils/prune.py:111-193) ----------------
+__global__ void __launch_bounds__(256)
+mask_stats_kernel(const uint8_t *__restrict__ tmask, const float *__restrict__ piggy, long long n, int idx,
+                  unsigned long long *__restrict__ out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  unsigned c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    unsigned t = tmask[i];
+    c0 += (t == 0u);
+    c1 += (t == (unsigned)idx);
+    bool shared = t > 0u && t < (unsigned)idx;
+    c2 += shared;
+    if (piggy && shared) c3 += (piggy[i] > 0.005f);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+    c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+    c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+    c3 += __shfl_xor_sync(0xffffffffu, c3, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (c0) atomicAdd(out + 0, (unsigned long long)c0);
+    if (c1) atomicAdd(out + 1, (unsigned long long)c1);
+    if (c2) atomicAdd(out + 2, (unsigned long long)c2);
+    if (c3) atomicAdd(out + 3, (unsigned long long)c3);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(out + 4, (unsigned long long)n);
+}
+
+// ---------------- data-parallel helpers ----------------
+__global__ void __launch_bounds__(256)
+merge_grads_kernel(const float *__restrict__ dW, const float *__restrict__ dP, float *__restrict__ m, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    m[i] = dW[i] + (dP ? dP[i] : 0.f);
+}
+__global__ void __launch_bounds__(256)
+split_grads_kernel(const float *__restrict__ m, const uint8_t *__restrict__ tmask, long long n, int cur,
+                   float *__restrict__ dW, float *__restrict__ dP) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    unsigned t = tmask[i];
+    float v = m[i];
+    dW[i] = (t == (unsigned)cur) ? v : 0.f;
+    if (dP) dP[i] = (t != 0u && t < (unsigned)cur) ? v : 0.f;
+  }
+}
+
+}  // namespace cpgb
+
+using namespace cpgb;
+
+extern "C" {
+
+int cpgb_binarize(const float *piggy, float *out, int64_t n, float thr, void *stream) {
+  if (n < 0 || (n > 0 && (!piggy || !out))) { set_error("cpgb_binarize: null pointer"); return CPGB_EINVAL; }
+  if (n == 0) return CPGB_OK;
+  bool vec = aligned16(piggy) && aligned16(out);
+  binarize_kernel<<<grid_for(n / 4 + 1), 256, 0, (cudaStream_t)stream>>>(piggy, out, n, thr, vec);
+  CPGB_LAUNCH_OK("cpgb_binarize");
+  return CPGB_OK;
+}
+
+int cpgb_grad_epilogue(float *dW, float *dP, const float *w, const uint8_t *tmask, int64_t n, int32_t cur,
+                       float weight_decay, int32_t mode, void *stream) {
+  if (n < 0 || !tmask || (dW && !w)) { set_error("cpgb_grad_epilogue: null pointer"); return CPGB_EINVAL; }
+  if (mode != CPGB_GRAD_FINETUNE && mode != CPGB_GRAD_PRUNE) {
+    set_error("cpgb_grad_epilogue: mode must be FINETUNE or PRUNE");
+    return CPGB_EINVAL;
+  }
+  if (n == 0 || (!dW && !dP)) return CPGB_OK;
+  grad_epilogue_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(dW, dP, w, tmask, n, cur, weight_decay, mode);
+  CPGB_LAUNCH_OK("cpgb_grad_epilogue");
+  return CPGB_OK;
+}
+
+int cpgb_apply_mask(float *w, const uint8_t *tmask, int64_t n, int32_t inference_idx, void *stream) {
+  if (n < 0 || (n > 0 && (!w || !tmask))) { set_error("cpgb_apply_mask: null pointer"); return CPGB_EINVAL; }
+  if (n == 0) return CPGB_OK;
+  apply_mask_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(w, tmask, n, inference_idx);
+  CPGB_LAUNCH_OK("cpgb_apply_mask");
+  return CPGB_OK;
+}
+
+int cpgb_make_finetuning_mask(uint8_t *tmask, int64_t n, int32_t new_cur, void *stream) {
+  if (n < 0 || (n > 0 && !tmask) || new_cur < 1 || new_cur > 255) {
+    set_error("cpgb_make_finetuning_mask: bad argument");
+    return CPGB_EINVAL;
+  }
+  if (n == 0) return CPGB_OK;
+  finetuning_mask_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(tmask, n, new_cur);
+  CPGB_LAUNCH_OK("cpgb_make_finetuning_mask");
+  return CPGB_OK;
+}
+
+int cpgb_mask_stats(const uint8_t *tmask, const float *piggy, int64_t n, int32_t inference_idx, int64_t *out,
+                    void *stream) {
+  if (n < 0 || !out || (n > 0 && !tmask)) { set_error("cpgb_mask_stats: null pointer"); return CPGB_EINVAL; }
+  if (n == 0) return CPGB_OK;
+  mask_stats_kernel<<<grid_for(n, 256, 4), 256, 0, (cudaStream_t)stream>>>(
+      tmask, piggy, n, inference_idx, reinterpret_cast<unsigned long long *>(out));
+  CPGB_LAUNCH_OK("cpgb_mask_stats");
+  return CPGB_OK;
+}
+
+int cpgb_merge_grads(const float *dW, const float *dP, float *merged, int64_t n, void *stream) {
+  if (n < 0 || (n > 0 && (!dW || !merged))) { set_error("cpgb_merge_grads: null pointer"); return CPGB_EINVAL; }
+  if (n == 0) return CPGB_OK;
+  merge_grads_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(dW, dP, merged, n);
+  CPGB_LAUNCH_OK("cpgb_merge_grads");
+  return CPGB_OK;
+}
+
+int cpgb_split_merged_grad(const float *merged, const uint8_t *tmask, int64_t n, int32_t cur, float *dW, float *dP,
+                           void *stream) {
+  if (n < 0 || (n > 0 && (!merged || !tmask || !dW))) { set_error("cpgb_split_merged_grad: null pointer"); return CPGB_EINVAL; }
+  if (n == 0) return CPGB_OK;
+  split_grads_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(merged, tmask, n, cur, dW, dP);
+  CPGB_LAUNCH_OK("cpgb_split_merged_grad");
+  return CPGB_OK;
+}
+
+}  // extern "C"

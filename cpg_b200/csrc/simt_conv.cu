@@ -1,0 +1,223 @@
+// CUDA-core (fp32 FFMA) implicit-GEMM kernels for the masked convolution: any stride /
+// padding / dilation / groups / memory format.  They are the exact-fp32 path for shapes the
+// tcgen05 kernels do not cover (C=3 stems, odd grown widths, grouped convs) and the on-GPU
+// cross-check for the tensor-core path.
+//
+// One generic 64x64x16 tile kernel; the three convolution passes differ only in how a GEMM
+// coordinate maps to memory:
+//   fprop : M = N*P*Q pixels,  cols = K/g,        Kd = C/g*R*S   (models/layers.py:108)
+//   dgrad : M = N*H*W pixels,  cols = C/g,        Kd = K/g*R*S   (autograd of the above)
+//   wgrad : M = K/g,           cols = C/g*R*S,    Kd = N*P*Q     (autograd of the above)
+// The piggyback predicate (models/layers.py:101-103) is evaluated while the weight tile is
+// loaded -- the masked weight is never written to memory.
+#include "common.cuh"
+
+namespace cpgb {
+
+constexpr int BM = 64, BN = 64, BK = 16, NTHREADS = 256;
+
+struct FpropProb {
+  Geom g; const float *x, *w, *piggy, *bias; float *y; float thr;
+  static constexpr bool A_M_FAST = true, B_N_FAST = false;
+  __device__ int M() const { return g.N * g.PQ; }
+  __device__ int Ncols() const { return g.Kg; }
+  __device__ int Kd() const { return g.Cg * g.RS; }
+  __device__ float loadA(int grp, int m, int kd) const {
+    int n = m / g.PQ, pq = m - n * g.PQ, p = pq / g.Q, q = pq - p * g.Q;
+    int c = kd / g.RS, rs = kd - c * g.RS, r = rs / g.S, s = rs - r * g.S;
+    int h = p * g.sh - g.ph + r * g.dh, ww = q * g.sw - g.pw + s * g.dw;
+    if ((unsigned)h >= (unsigned)g.H || (unsigned)ww >= (unsigned)g.W) return 0.f;
+    return __ldg(x + n * g.xs0 + (long long)(grp * g.Cg + c) * g.xs1 + h * g.xs2 + ww * g.xs3);
+  }
+  __device__ float loadB(int grp, int kd, int j) const {
+    long long idx = (long long)(grp * g.Kg + j) * g.Cg * g.RS + kd;
+    return masked_weight(__ldg(w + idx), piggy, idx, thr);
+  }
+  __device__ void store(int grp, int m, int j, float acc, bool) const {
+    int n = m / g.PQ, pq = m - n * g.PQ, p = pq / g.Q, q = pq - p * g.Q;
+    int k = grp * g.Kg + j;
+    y[n * g.ys0 + k * g.ys1 + p * g.ys2 + q * g.ys3] = acc + (bias ? __ldg(bias + k) : 0.f);
+  }
+};
+
+struct DgradProb {
+  Geom g; const float *dy, *w, *piggy; float *dx; float thr;
+  static constexpr bool A_M_FAST = true, B_N_FAST = false;
+  __device__ int M() const { return g.N * g.HW; }
+  __device__ int Ncols() const { return g.Cg; }
+  __device__ int Kd() const { return g.Kg * g.RS; }
+  __device__ float loadA(int grp, int m, int kd) const {
+    int n = m / g.HW, hw = m - n * g.HW, h = hw / g.W, ww = hw - h * g.W;
+    int kk = kd / g.RS, rs = kd - kk * g.RS, r = rs / g.S, s = rs - r * g.S;
+    int hp = h + g.ph - r * g.dh, wq = ww + g.pw - s * g.dw;
+    if (hp < 0 || wq < 0) return 0.f;
+    int p = hp / g.sh, q = wq / g.sw;
+    if (p * g.sh != hp || q * g.sw != wq || p >= g.P || q >= g.Q) return 0.f;
+    return __ldg(dy + n * g.ys0 + (long long)(grp * g.Kg + kk) * g.ys1 + p * g.ys2 + q * g.ys3);
+  }
+  __device__ float loadB(int grp, int kd, int c) const {
+    int kk = kd / g.RS, rs = kd - kk * g.RS;
+    long long idx = ((long long)(grp * g.Kg + kk) * g.Cg + c) * g.RS + rs;
+    return masked_weight(__ldg(w + idx), piggy, idx, thr);
+  }
+  __device__ void store(int grp, int m, int c, float acc, bool) const {
+    int n = m / g.HW, hw = m - n * g.HW, h = hw / g.W, ww = hw - h * g.W;
+    dx[n * g.xs0 + (long long)(grp * g.Cg + c) * g.xs1 + h * g.xs2 + ww * g.xs3] = acc;
+  }
+};
+
+struct WgradProb {
+  Geom g; const float *x, *dy; float *gbuf;
+  static constexpr bool A_M_FAST = false, B_N_FAST = false;
+  __device__ int M() const { return g.Kg; }
+  __device__ int Ncols() const { return g.Cg * g.RS; }
+  __device__ int Kd() const { return g.N * g.PQ; }
+  __device__ float loadA(int grp, int j, int pix) const {
+    int n = pix / g.PQ, pq = pix - n * g.PQ, p = pq / g.Q, q = pq - p * g.Q;
+    return __ldg(dy + n * g.ys0 + (long long)(grp * g.Kg + j) * g.ys1 + p * g.ys2 + q * g.ys3);
+  }
+  __device__ float loadB(int grp, int pix, int crs) const {
+    int n = pix / g.PQ, pq = pix - n * g.PQ, p = pq / g.Q, q = pq - p * g.Q;
+    int c = crs / g.RS, rs = crs - c * g.RS, r = rs / g.S, s = rs - r * g.S;
+    int h = p * g.sh - g.ph + r * g.dh, ww = q * g.sw - g.pw + s * g.dw;
+    if ((unsigned)h >= (unsigned)g.H || (unsigned)ww >= (unsigned)g.W) return 0.f;
+    return __ldg(x + n * g.xs0 + (long long)(grp * g.Cg + c) * g.xs1 + h * g.xs2 + ww * g.xs3);
+  }
+  __device__ void store(int grp, int j, int crs, float acc, bool split) const {
+    float *dst = gbuf + (long long)(grp * g.Kg + j) * g.Cg * g.RS + crs;
+    if (split) atomicAdd(dst, acc); else *dst = acc;
+  }
+};
+
+// grid: x = M tiles, y = column tiles, z = group * splits + split
+template <class Prob>
+__global__ void __launch_bounds__(NTHREADS) simt_gemm_kernel(const Prob pb, int splits, int kchunk) {
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int grp = blockIdx.z / splits, split = blockIdx.z - grp * splits;
+  const int M = pb.M(), NC = pb.Ncols(), KD = pb.Kd();
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int kbeg = split * kchunk;
+  const int kend = min(KD, kbeg + kchunk);
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = kbeg; k0 < kend; k0 += BK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int e = tid + i * NTHREADS;
+      int mm, kk;
+      if (Prob::A_M_FAST) { mm = e & (BM - 1); kk = e >> 6; } else { kk = e & (BK - 1); mm = e >> 4; }
+      float v = 0.f;
+      if (m0 + mm < M && k0 + kk < kend) v = pb.loadA(grp, m0 + mm, k0 + kk);
+      As[kk][mm] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int e = tid + i * NTHREADS;
+      int nn, kk;
+      if (Prob::B_N_FAST) { nn = e & (BN - 1); kk = e >> 6; } else { kk = e & (BK - 1); nn = e >> 4; }
+      float v = 0.f;
+      if (n0 + nn < NC && k0 + kk < kend) v = pb.loadB(grp, k0 + kk, n0 + nn);
+      Bs[kk][nn] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float4 a = *reinterpret_cast<const float4 *>(&As[kk][ty * 4]);
+      float4 b = *reinterpret_cast<const float4 *>(&Bs[kk][tx * 4]);
+      float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  const bool is_split = splits > 1;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + tx * 4 + j;
+      if (n < NC) pb.store(grp, m, n, acc[i][j], is_split);
+    }
+  }
+}
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+int simt_fprop(const Geom &g, const float *x, const float *w, const float *piggy, const float *bias,
+               float *y, float thr, cudaStream_t st) {
+  FpropProb pb{g, x, w, piggy, bias, y, thr};
+  dim3 grid(cdiv((long long)g.N * g.PQ, BM), cdiv(g.Kg, BN), g.groups);
+  simt_gemm_kernel<FpropProb><<<grid, NTHREADS, 0, st>>>(pb, 1, g.Cg * g.RS);
+  CPGB_LAUNCH_OK("simt_fprop");
+  return CPGB_OK;
+}
+
+int simt_dgrad(const Geom &g, const float *dy, const float *w, const float *piggy, float *dx, float thr,
+               cudaStream_t st) {
+  DgradProb pb{g, dy, w, piggy, dx, thr};
+  dim3 grid(cdiv((long long)g.N * g.HW, BM), cdiv(g.Cg, BN), g.groups);
+  simt_gemm_kernel<DgradProb><<<grid, NTHREADS, 0, st>>>(pb, 1, g.Kg * g.RS);
+  CPGB_LAUNCH_OK("simt_dgrad");
+  return CPGB_OK;
+}
+
+int simt_wgrad_raw(const Geom &g, const float *x, const float *dy, float *gbuf, cudaStream_t st) {
+  WgradProb pb{g, x, dy, gbuf};
+  const long long kd = (long long)g.N * g.PQ;
+  const int tiles = cdiv(g.Kg, BM) * cdiv((long long)g.Cg * g.RS, BN) * g.groups;
+  // split the pixel reduction so that ~2 waves of CTAs exist (148 SMs)
+  int splits = 1;
+  if (tiles < 296) splits = (int)min((long long)cdiv(296, tiles), (kd + 4 * BK - 1) / (4 * BK));
+  if (splits < 1) splits = 1;
+  int kchunk = (int)((kd + splits - 1) / splits);
+  kchunk = ((kchunk + BK - 1) / BK) * BK;
+  splits = (int)((kd + kchunk - 1) / kchunk);
+  if (splits > 1)
+    CPGB_CUDA_OK(cudaMemsetAsync(gbuf, 0, sizeof(float) * (size_t)g.K * g.Cg * g.RS, st));
+  dim3 grid(cdiv(g.Kg, BM), cdiv((long long)g.Cg * g.RS, BN), g.groups * splits);
+  simt_gemm_kernel<WgradProb><<<grid, NTHREADS, 0, st>>>(pb, splits, kchunk);
+  CPGB_LAUNCH_OK("simt_wgrad");
+  return CPGB_OK;
+}
+
+// dbias[k] = sum over n,p,q of dy  (autograd of the bias add, models/layers.py:108)
+__global__ void __launch_bounds__(256) bias_grad_kernel(Geom g, const float *__restrict__ dy,
+                                                        float *__restrict__ dbias) {
+  const int k = blockIdx.x;
+  const long long total = (long long)g.N * g.PQ;
+  float s = 0.f;
+  for (long long i = threadIdx.x; i < total; i += blockDim.x) {
+    int n = (int)(i / g.PQ), pq = (int)(i - (long long)n * g.PQ), p = pq / g.Q, q = pq - p * g.Q;
+    s += __ldg(dy + n * g.ys0 + k * g.ys1 + p * g.ys2 + q * g.ys3);
+  }
+  __shared__ float red[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < 8 ? red[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) dbias[k] = s;
+  }
+}
+
+int bias_grad(const Geom &g, const float *dy, float *dbias, cudaStream_t st) {
+  bias_grad_kernel<<<g.K, 256, 0, st>>>(g, dy, dbias);
+  CPGB_LAUNCH_OK("bias_grad");
+  return CPGB_OK;
+}
+
+}  // namespace cpgb

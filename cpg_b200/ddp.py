@@ -1,0 +1,87 @@
+"""Batch-sharded data parallelism for the masked-conv path.
+
+The reference's only multi-GPU mechanism is single-process nn.DataParallel (it re-broadcasts
+every parameter each forward and reduces gradients to GPU 0, CPG_cifar100_main_normal.py:199).
+Here: one process per GPU, weights/masks resident and identical on every rank, each rank runs
+its batch shard, and the gradients are averaged with NCCL all-reduce over NVLink.  Masks are
+rank-invariant, so masking commutes with the reduction: it does not matter whether the fused
+wgrad epilogue (weight decay + grad mask) ran before the all-reduce -- avg_r((g_r*b + wd*W)[T==cur])
+== (avg_r(g_r)*b + wd*W)[T==cur].
+
+Large gradients (the sharable layers: 134 MB for VGG16) are all-reduced asynchronously from
+post-accumulate-grad hooks, i.e. while the rest of the backward pass is still running (FC2's
+67 MB bucket goes first); small ones (BN, biases, heads) are flattened into one bucket at the
+end.  Prune steps need no collective: every rank holds the same W and T.
+"""
+import torch
+import torch.distributed as dist
+
+BIG = 1 << 18   # elements; tensors at least this large get their own overlapped all-reduce
+
+
+def shard_batch(batch, rank, world):
+    """rank r gets X[r*B/G:(r+1)*B/G] (SURVEY 8e 'Partitioning')."""
+    n = batch.shape[0]
+    if n % world != 0:
+        raise ValueError(f'global batch {n} is not divisible by world size {world}')
+    per = n // world
+    return batch[rank * per:(rank + 1) * per]
+
+
+class GradAllReducer:
+    def __init__(self, model, world=None, overlap=True, group=None):
+        self.world = world if world is not None else dist.get_world_size(group)
+        self.group = group
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        self.pending = []
+        self.overlap = overlap
+        self._hooks = []
+        if overlap and self.world > 1:
+            for p in self.params:
+                if p.numel() >= BIG:
+                    self._hooks.append(p.register_post_accumulate_grad_hook(self._hook))
+
+    def _hook(self, p):
+        if p.grad is not None:
+            self.pending.append((p.grad, dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=self.group,
+                                                         async_op=True)))
+
+    def reduce(self):
+        """Call after backward(): waits for the overlapped reductions, reduces everything else
+        in one flat bucket and divides by the world size (gradient of the global-batch mean)."""
+        if self.world <= 1:
+            return
+        done = set()
+        for g, work in self.pending:
+            work.wait()
+            g.div_(self.world)
+            done.add(g.data_ptr())
+        self.pending = []
+        rest = [p.grad for p in self.params if p.grad is not None and p.grad.data_ptr() not in done]
+        if rest:
+            flat = torch.cat([g.reshape(-1) for g in rest])
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            flat.div_(self.world)
+            off = 0
+            for g in rest:
+                n = g.numel()
+                g.copy_(flat[off:off + n].view_as(g))
+                off += n
+
+    def remove(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+
+
+def assert_masks_identical(masks, group=None):
+    """Debug check of SURVEY 8e: T must be bit-identical on all ranks after every prune event."""
+    for name in sorted(masks):
+        m = masks[name]
+        s = m.to(torch.int64).sum() * 31 + (m.to(torch.int64) * torch.arange(m.numel(), device=m.device)
+                                            .reshape(m.shape) % 65521).sum()
+        lo, hi = s.clone(), s.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+        if int(lo) != int(hi):
+            raise RuntimeError(f'task mask {name} differs across ranks')

@@ -1,0 +1,227 @@
+"""autograd.Functions over the C ABI (include/cpgb200.h).
+
+One Function per masked layer type replaces the reference's three-node autograd graph
+``Binarizer.apply -> mul -> F.conv2d / F.linear`` (models/layers.py:101-108, 187-194): the
+forward evaluates the piggyback predicate inside the convolution kernels, the backward
+produces dX, dW, dP (straight-through: dP = g * W, models/layers.py:21-23) and dbias, with
+the pruner's weight-decay / grad-mask step (utils/prune.py:195-211) optionally folded into
+the same epilogue.
+"""
+import torch
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+
+DEFAULT_THRESHOLD = 5e-3  # models/layers.py:9
+CL = torch.channels_last
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def _dense4(t):
+    """Return t if it is dense NCHW or dense NHWC, else a dense NCHW copy."""
+    if t.is_contiguous() or t.is_contiguous(memory_format=CL):
+        return t
+    return t.contiguous()
+
+
+class FuseCtx:
+    """What the fused wgrad epilogue needs from the pruner (utils/prune.py:195-211)."""
+    __slots__ = ('tmask', 'cur', 'weight_decay', 'mode')
+
+    def __init__(self, tmask, cur, weight_decay, mode):
+        self.tmask, self.cur, self.weight_decay, self.mode = tmask, int(cur), float(weight_decay), int(mode)
+
+
+def _check_params(weight, piggymask, bias):
+    for name, t in (('weight', weight), ('piggymask', piggymask), ('bias', bias)):
+        if t is None:
+            continue
+        if t.dtype != torch.float32:
+            raise _lib.CpgbError(f'{name} must be float32 (the reference path is fp32), got {t.dtype}')
+        if not t.is_cuda:
+            raise _lib.CpgbError(f'{name} is on {t.device}: cpg_b200 has no CPU path')
+    if piggymask is not None and piggymask.shape != weight.shape:
+        raise _lib.CpgbError('piggymask must have the weight\'s shape')
+
+
+class MaskedConv2dFn(torch.autograd.Function):
+    """y = conv2d(x, (piggymask > thr) * weight, bias, ...)  -- models/layers.py:98-109."""
+
+    @staticmethod
+    def forward(ctx, x, weight, piggymask, bias, stride, padding, dilation, groups, threshold, fuse,
+                module, channels_last_out):
+        lib = _lib.load()
+        _check_params(weight, piggymask, bias)
+        if x.dim() != 4:
+            raise _lib.CpgbError('SharableConv2d expects a 4-D input')
+        if x.dtype != torch.float32 or not x.is_cuda:
+            raise _lib.CpgbError(f'input must be a float32 CUDA tensor, got {x.dtype} on {x.device}')
+        x = _dense4(x)
+        w = weight.detach().contiguous()
+        p = piggymask.detach().contiguous() if piggymask is not None else None
+        b = bias.detach().contiguous() if bias is not None else None
+        N, C, H, W = x.shape
+        K, Cg, R, S = w.shape
+        if C != Cg * groups:
+            raise RuntimeError(f'expected input with {Cg * groups} channels, got {C}')
+        P = (H + 2 * padding[0] - dilation[0] * (R - 1) - 1) // stride[0] + 1
+        Q = (W + 2 * padding[1] - dilation[1] * (S - 1) - 1) // stride[1] + 1
+        if P <= 0 or Q <= 0:
+            raise RuntimeError('kernel size larger than the (padded) input')
+        fmt = CL if (channels_last_out or (x.is_contiguous(memory_format=CL) and not x.is_contiguous())) \
+            else torch.contiguous_format
+        y = torch.empty((N, K, P, Q), dtype=torch.float32, device=x.device, memory_format=fmt)
+        d = _lib.conv_desc(x.shape, x.stride(), w.shape, y.shape, y.stride(), stride, padding, dilation, groups)
+        ws_bytes = lib.cpgb_workspace_bytes(d)
+        ws = _ws(ws_bytes, x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(lib.cpgb_conv2d_fprop(d, _lib.ptr(x), _lib.ptr(w), _lib.ptr(p), _lib.ptr(b),
+                                             _lib.ptr(y), threshold, _lib.ptr(ws), ws.numel(),
+                                             _lib.stream_ptr()), 'cpgb_conv2d_fprop')
+        ctx.save_for_backward(x, w, p)
+        ctx.has_bias = bias is not None
+        ctx.geom = (stride, padding, dilation, groups, threshold)
+        ctx.fuse, ctx.module = fuse, module
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x, w, p = ctx.saved_tensors
+        stride, padding, dilation, groups, threshold = ctx.geom
+        dy = _dense4(dy)
+        d = _lib.conv_desc(x.shape, x.stride(), w.shape, dy.shape, dy.stride(), stride, padding, dilation, groups)
+        ws = _ws(lib.cpgb_workspace_bytes(d), x.device)
+        dx = dW = dP = db = None
+        with torch.cuda.device(x.device):
+            st = _lib.stream_ptr()
+            if ctx.needs_input_grad[0]:
+                dx = torch.empty_like(x)  # same strides as x (dense)
+                _lib.check(lib.cpgb_conv2d_dgrad(d, _lib.ptr(dy), _lib.ptr(w), _lib.ptr(p), _lib.ptr(dx),
+                                                 threshold, _lib.ptr(ws), ws.numel(), st), 'cpgb_conv2d_dgrad')
+            if ctx.needs_input_grad[1] or ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
+                dW = torch.empty_like(w)
+                dP = torch.empty_like(w) if p is not None else None
+                db = torch.empty(w.shape[0], dtype=torch.float32, device=x.device) if ctx.has_bias else None
+                fuse = ctx.fuse
+                mode = fuse.mode if fuse is not None else _lib.GRAD_RAW
+                _lib.check(lib.cpgb_conv2d_wgrad_fused(
+                    d, _lib.ptr(x), _lib.ptr(dy), _lib.ptr(w), _lib.ptr(p),
+                    _lib.ptr(fuse.tmask) if fuse is not None else None,
+                    fuse.cur if fuse is not None else 0, fuse.weight_decay if fuse is not None else 0.0, mode,
+                    _lib.ptr(dW), _lib.ptr(dP), _lib.ptr(db), threshold, _lib.ptr(ws), ws.numel(), st),
+                    'cpgb_conv2d_wgrad_fused')
+                if fuse is not None and ctx.module is not None:
+                    ctx.module._cpg_grads_final = True
+        return dx, dW, dP, db, None, None, None, None, None, None, None, None
+
+
+class MaskedLinearFn(torch.autograd.Function):
+    """y = linear(x, (piggymask > thr) * weight, bias)  -- models/layers.py:184-194."""
+
+    @staticmethod
+    def forward(ctx, x, weight, piggymask, bias, threshold, fuse, module):
+        lib = _lib.load()
+        _check_params(weight, piggymask, bias)
+        if x.dtype != torch.float32 or not x.is_cuda:
+            raise _lib.CpgbError(f'input must be a float32 CUDA tensor, got {x.dtype} on {x.device}')
+        w = weight.detach().contiguous()
+        p = piggymask.detach().contiguous() if piggymask is not None else None
+        b = bias.detach().contiguous() if bias is not None else None
+        O, I = w.shape
+        if x.shape[-1] != I:
+            raise RuntimeError(f'size mismatch: input features {x.shape[-1]} vs weight {tuple(w.shape)}')
+        x2 = x.reshape(-1, I).contiguous()
+        M = x2.shape[0]
+        y = torch.empty((M, O), dtype=torch.float32, device=x.device)
+        d = _lib.ConvDesc()
+        lib.cpgb_linear_desc(d, M, I, O)
+        ws = _ws(lib.cpgb_workspace_bytes(d), x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(lib.cpgb_conv2d_fprop(d, _lib.ptr(x2), _lib.ptr(w), _lib.ptr(p), _lib.ptr(b), _lib.ptr(y),
+                                             threshold, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+                       'cpgb_conv2d_fprop(linear)')
+        ctx.save_for_backward(x2, w, p)
+        ctx.has_bias, ctx.threshold, ctx.fuse, ctx.module = bias is not None, threshold, fuse, module
+        ctx.x_shape = x.shape
+        return y.reshape(*x.shape[:-1], O)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x2, w, p = ctx.saved_tensors
+        O, I = w.shape
+        M = x2.shape[0]
+        dy2 = dy.reshape(M, O).contiguous()
+        d = _lib.ConvDesc()
+        lib.cpgb_linear_desc(d, M, I, O)
+        ws = _ws(lib.cpgb_workspace_bytes(d), x2.device)
+        dx = dW = dP = db = None
+        with torch.cuda.device(x2.device):
+            st = _lib.stream_ptr()
+            if ctx.needs_input_grad[0]:
+                dx2 = torch.empty_like(x2)
+                _lib.check(lib.cpgb_conv2d_dgrad(d, _lib.ptr(dy2), _lib.ptr(w), _lib.ptr(p), _lib.ptr(dx2),
+                                                 ctx.threshold, _lib.ptr(ws), ws.numel(), st),
+                           'cpgb_conv2d_dgrad(linear)')
+                dx = dx2.reshape(ctx.x_shape)
+            if ctx.needs_input_grad[1] or ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
+                dW = torch.empty_like(w)
+                dP = torch.empty_like(w) if p is not None else None
+                db = torch.empty(O, dtype=torch.float32, device=x2.device) if ctx.has_bias else None
+                fuse = ctx.fuse
+                mode = fuse.mode if fuse is not None else _lib.GRAD_RAW
+                _lib.check(lib.cpgb_conv2d_wgrad_fused(
+                    d, _lib.ptr(x2), _lib.ptr(dy2), _lib.ptr(w), _lib.ptr(p),
+                    _lib.ptr(fuse.tmask) if fuse is not None else None,
+                    fuse.cur if fuse is not None else 0, fuse.weight_decay if fuse is not None else 0.0, mode,
+                    _lib.ptr(dW), _lib.ptr(dP), _lib.ptr(db), ctx.threshold, _lib.ptr(ws), ws.numel(), st),
+                    'cpgb_conv2d_wgrad_fused(linear)')
+                if fuse is not None and ctx.module is not None:
+                    ctx.module._cpg_grads_final = True
+        return dx, dW, dP, db, None, None, None
+
+
+class Binarizer(torch.autograd.Function):
+    """Binarizes {0, 1} a real valued tensor; straight-through backward.
+    Same call signature as the reference: ``Binarizer.apply(inputs, threshold)``
+    (models/layers.py:11-23)."""
+
+    @staticmethod
+    def forward(ctx, inputs, threshold):
+        lib = _lib.load()
+        if not inputs.is_cuda or inputs.dtype != torch.float32:
+            raise _lib.CpgbError('Binarizer needs a float32 CUDA tensor (no CPU path)')
+        src = inputs.detach().contiguous()
+        out = torch.empty_like(src)
+        with torch.cuda.device(src.device):
+            _lib.check(lib.cpgb_binarize(_lib.ptr(src), _lib.ptr(out), src.numel(), float(threshold),
+                                         _lib.stream_ptr()), 'cpgb_binarize')
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        return grad_out, None
+
+
+class Ternarizer(torch.autograd.Function):
+    """Ternarizes {-1, 0, 1}: -1 where x < 0, 1 where x > thr, else 0; straight-through backward.
+    The reference's class (models/layers.py:25-40) is a legacy non-static Function that modern
+    torch refuses to run and nothing selects it; kept for API completeness only,
+    implemented with torch ops (not on the accelerated path)."""
+
+    @staticmethod
+    def forward(ctx, inputs, threshold=DEFAULT_THRESHOLD):
+        out = torch.zeros_like(inputs)
+        out[inputs < 0] = -1
+        out[inputs > threshold] = 1
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        return grad_out, None

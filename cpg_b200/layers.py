@@ -1,0 +1,149 @@
+"""Drop-in replacement of the reference's ``models/layers.py`` (same names, constructor
+arguments, attributes and state_dict keys), with the forward/backward running on the
+hand-written sm_100a kernels behind include/cpgb200.h.
+
+Usage in a CPG checkout:  ``import cpg_b200.layers as nl``  instead of
+``import models.layers as nl`` (or ``cpg_b200.install()`` which aliases the module), see
+INTEGRATION.md.  Reference interface: models/layers.py:9-218.
+"""
+import torch
+import torch.nn as nn
+from torch.nn.modules.utils import _pair
+from torch.nn.parameter import Parameter
+
+from . import _lib
+from .functional import (DEFAULT_THRESHOLD, Binarizer, FuseCtx, MaskedConv2dFn, MaskedLinearFn,
+                         Ternarizer)
+
+__all__ = ['DEFAULT_THRESHOLD', 'Binarizer', 'Ternarizer', 'SharableConv2d', 'SharableLinear']
+
+# Conv outputs are produced physically NHWC (torch.channels_last; logically still NCHW) so
+# that the next masked conv can TMA-load them; BatchNorm/ReLU/MaxPool keep the format.
+OUTPUT_CHANNELS_LAST = True
+
+
+class _SharableBase(nn.Module):
+    def _init_common(self, mask_init, mask_scale, threshold_fn, threshold):
+        self.mask_scale = mask_scale
+        self.mask_init = mask_init
+        if threshold is None:
+            threshold = DEFAULT_THRESHOLD
+        self.info = {'threshold_fn': threshold_fn, 'threshold': threshold}
+        self._cpg_pruner = None       # set by cpg_b200.prune.SparsePruner
+        self._cpg_name = None
+        self._cpg_grads_final = False
+
+    def _finish_init(self, threshold_fn, threshold):
+        # Give real-valued mask weights per task to manage the shared part from previous tasks:
+        # a plain None attribute that becomes a registered Parameter when the training script
+        # assigns one (CPG_cifar100_main_normal.py:262-270).
+        self.piggymask = None
+        if threshold_fn == 'binarizer':
+            self.threshold_fn = Binarizer.apply
+        elif threshold_fn == 'ternarizer':
+            print('Calling ternarizer with threshold:', threshold)
+            self.threshold_fn = Ternarizer.apply
+
+    def _fuse_ctx(self):
+        """FuseCtx when an attached SparsePruner wants weight decay + grad masking folded
+        into the wgrad epilogue, else None."""
+        ref = self._cpg_pruner          # weakref.ref set by SparsePruner.attach()
+        pr = ref() if ref is not None else None
+        if pr is None or not torch.is_grad_enabled():
+            return None
+        return pr._fuse_ctx_for(self._cpg_name)
+
+    def _effective(self):
+        """(weight, piggymask) to hand to the fused kernels.  The ternarizer (dead code in the
+        reference) is applied with torch ops and then treated as 'no piggymask'."""
+        if self.piggymask is not None and self.info['threshold_fn'] != 'binarizer':
+            return self.threshold_fn(self.piggymask, self.info['threshold']) * self.weight, None
+        return self.weight, self.piggymask
+
+
+class SharableConv2d(_SharableBase):
+    """Modified conv with masks for weights (models/layers.py:43-145)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1,
+                 padding=0, dilation=1, groups=1, bias=True,
+                 mask_init='1s', mask_scale=1e-2,
+                 threshold_fn='binarizer', threshold=None):
+        super(SharableConv2d, self).__init__()
+        kernel_size = _pair(kernel_size)
+        stride = _pair(stride)
+        padding = _pair(padding)
+        dilation = _pair(dilation)
+        self._init_common(mask_init, mask_scale, threshold_fn, threshold)
+        if in_channels % groups != 0:
+            raise ValueError('in_channels must be divisible by groups')
+        if out_channels % groups != 0:
+            raise ValueError('out_channels must be divisible by groups')
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.kernel_size = kernel_size
+        self.stride = stride
+        self.padding = padding
+        self.dilation = dilation
+        self.transposed = False
+        self.output_padding = _pair(0)
+        self.groups = groups
+        # uninitialised storage, like the reference (models initialise it)
+        self.weight = Parameter(torch.empty(out_channels, in_channels // groups, *kernel_size),
+                                requires_grad=True)
+        if bias:
+            self.bias = Parameter(torch.empty(out_channels), requires_grad=True)
+        else:
+            self.register_parameter('bias', None)
+        self._finish_init(threshold_fn, self.info['threshold'])
+
+    def forward(self, input, layer_info=None, name=None):
+        weight, piggy = self._effective()
+        fuse = self._fuse_ctx() if piggy is self.piggymask and weight is self.weight else None
+        return MaskedConv2dFn.apply(input, weight, piggy, self.bias, self.stride, self.padding,
+                                    self.dilation, self.groups, float(self.info['threshold']), fuse,
+                                    self if fuse is not None else None, OUTPUT_CHANNELS_LAST)
+
+    def __repr__(self):
+        s = ('{name} ({in_channels}, {out_channels}, kernel_size={kernel_size}'
+             ', stride={stride}')
+        if self.padding != (0,) * len(self.padding):
+            s += ', padding={padding}'
+        if self.dilation != (1,) * len(self.dilation):
+            s += ', dilation={dilation}'
+        if self.output_padding != (0,) * len(self.output_padding):
+            s += ', output_padding={output_padding}'
+        if self.groups != 1:
+            s += ', groups={groups}'
+        if self.bias is None:
+            s += ', bias=False'
+        s += ')'
+        return s.format(name=self.__class__.__name__, **self.__dict__)
+
+
+class SharableLinear(_SharableBase):
+    """Modified linear layer (models/layers.py:147-218)."""
+
+    def __init__(self, in_features, out_features, bias=True,
+                 mask_init='1s', mask_scale=1e-2,
+                 threshold_fn='binarizer', threshold=None):
+        super(SharableLinear, self).__init__()
+        self.in_features = in_features
+        self.out_features = out_features
+        self._init_common(mask_init, mask_scale, threshold_fn, threshold)
+        self.weight = Parameter(torch.empty(out_features, in_features), requires_grad=True)
+        if bias:
+            self.bias = Parameter(torch.empty(out_features), requires_grad=True)
+        else:
+            self.register_parameter('bias', None)
+        self._finish_init(threshold_fn, self.info['threshold'])
+
+    def forward(self, input):
+        weight, piggy = self._effective()
+        fuse = self._fuse_ctx() if piggy is self.piggymask and weight is self.weight else None
+        return MaskedLinearFn.apply(input, weight, piggy, self.bias, float(self.info['threshold']), fuse,
+                                    self if fuse is not None else None)
+
+    def __repr__(self):
+        return self.__class__.__name__ + '(' \
+            + 'in_features=' + str(self.in_features) \
+            + ', out_features=' + str(self.out_features) + ')'

@@ -1,0 +1,269 @@
+"""Drop-in replacement of the reference's ``utils/prune.py`` SparsePruner: same constructor,
+attributes and method names (utils/prune.py:6-243); the five hot methods run as CUDA kernels
+behind include/cpgb200.h, the schedule arithmetic stays the reference's python doubles.
+
+Differences that are deliberate and invisible to ``Manager``:
+  * ``_pruning_mask`` never leaves the device (the reference does a D2H copy + CPU kthvalue,
+    utils/prune.py:39); the exit-2 condition is read back once per prune event;
+  * when ``fuse_grad_epilogue`` is on (default) the layers' backward already applies weight
+    decay and gradient masking in the wgrad epilogue, and
+    ``do_weight_decay_and_make_grads_zero`` only clears the per-layer "finalised" flag.
+"""
+import sys
+import weakref
+
+import torch
+
+from . import _lib
+from . import layers as nl
+from .functional import FuseCtx
+
+_MODES = {'finetune': _lib.GRAD_FINETUNE, 'prune': _lib.GRAD_PRUNE}
+
+
+class SparsePruner(object):
+    """Performs pruning on the given model."""
+
+    def __init__(self, model, masks, args, begin_prune_step, end_prune_step, inference_dataset_idx):
+        self.model = model
+        self.args = args
+        self.sparsity_func_exponent = 3
+        self.begin_prune_step = begin_prune_step
+        self.end_prune_step = end_prune_step
+        self.last_prune_step = begin_prune_step
+        self.masks = masks
+
+        finetune_again = False if not hasattr(args, 'finetune_again') else args.finetune_again
+        if args.mode == 'prune' or args.mode == 'inference' or (args.mode == 'finetune' and finetune_again):
+            self.current_dataset_idx = self.model.module.datasets.index(args.dataset) + 1
+        elif args.mode == 'finetune':
+            self.current_dataset_idx = len(self.model.module.datasets) - 1
+        else:
+            print('We do not support \'{}\' mode'.format(args.mode))
+            sys.exit(-1)
+
+        self.inference_dataset_idx = inference_dataset_idx
+        self.fuse_grad_epilogue = True
+        self._prune_ws = {}
+        self.attach()
+        return
+
+    # ------------------------------------------------------------------ helpers
+    def _sharable(self):
+        for name, module in self.model.named_modules():
+            if isinstance(module, nl.SharableConv2d) or isinstance(module, nl.SharableLinear):
+                yield name, module
+
+    def attach(self):
+        """Tell every sharable layer which pruner owns its task mask (enables the fused epilogue)."""
+        ref = weakref.ref(self)
+        for name, module in self._sharable():
+            module._cpg_pruner = ref
+            module._cpg_name = name
+            module._cpg_grads_final = False
+
+    def detach(self):
+        for name, module in self._sharable():
+            module._cpg_pruner = None
+            module._cpg_grads_final = False
+
+    def _fuse_ctx_for(self, name):
+        if not self.fuse_grad_epilogue or self.args.mode not in _MODES:
+            return None
+        mask = self.masks.get(name) if self.masks else None
+        if mask is None or not mask.is_cuda:
+            return None
+        return FuseCtx(self._mask(name), self.current_dataset_idx, self.args.weight_decay,
+                       _MODES[self.args.mode])
+
+    def _mask(self, name):
+        m = self.masks[name]
+        if m.dtype != torch.uint8:
+            raise _lib.CpgbError('task masks must be uint8 (torch.ByteTensor), as in the reference checkpoints')
+        if not m.is_contiguous():
+            raise _lib.CpgbError('task masks must be contiguous')
+        return m
+
+    @staticmethod
+    def _dense(t, what):
+        if not t.is_contiguous():
+            raise _lib.CpgbError(f'{what} must be contiguous for the in-place kernels')
+        return t
+
+    def _scratch(self, device):
+        key = str(device)
+        if key not in self._prune_ws:
+            lib = _lib.load()
+            self._prune_ws[key] = torch.empty(lib.cpgb_prune_workspace_bytes(), dtype=torch.uint8, device=device)
+        return self._prune_ws[key]
+
+    # ------------------------------------------------------------------ a7
+    def _launch_prune(self, weights, mask, pruning_ratio, info):
+        lib = _lib.load()
+        ws = self._scratch(weights.device)
+        with torch.cuda.device(weights.device):
+            _lib.check(lib.cpgb_prune_select(_lib.ptr(self._dense(weights, 'weight')), _lib.ptr(mask),
+                                             weights.numel(), self.current_dataset_idx, float(pruning_ratio),
+                                             _lib.ptr(info), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+                       'cpgb_prune_select')
+
+    @staticmethod
+    def _exit_not_enough():
+        print("Not enough weights for pruning, that is to say, too little space for new task, need expand the network.")
+        sys.exit(2)
+
+    def _pruning_mask(self, weights, mask, layer_name, pruning_ratio):
+        """Ranks weights by magnitude. Sets all below kth to 0.
+           Returns pruned mask.  (utils/prune.py:30-53)"""
+        info = torch.zeros(4, dtype=torch.int64, device=weights.device)
+        self._launch_prune(weights, mask, pruning_ratio, info)
+        if int(info[0].item()) != 0:
+            self._exit_not_enough()
+        return mask
+
+    # ------------------------------------------------------------------ a8 (python doubles, verbatim semantics)
+    def _adjust_sparsity(self, curr_prune_step):
+        p = min(1.0,
+                max(0.0,
+                    ((curr_prune_step - self.begin_prune_step)
+                     / (self.end_prune_step - self.begin_prune_step))
+                    ))
+        sparsity = self.args.target_sparsity + \
+            (self.args.initial_sparsity - self.args.target_sparsity) * pow(1 - p, self.sparsity_func_exponent)
+        return sparsity
+
+    def _time_to_update_masks(self, curr_prune_step):
+        is_step_within_pruning_range = \
+            (curr_prune_step >= self.begin_prune_step) and \
+            (curr_prune_step <= self.end_prune_step)
+        is_pruning_step = (
+            self.last_prune_step + self.args.pruning_frequency) <= curr_prune_step
+        return is_step_within_pruning_range and is_pruning_step
+
+    def gradually_prune(self, curr_prune_step):
+        if self._time_to_update_masks(curr_prune_step):
+            self.last_prune_step = curr_prune_step
+            curr_pruning_ratio = self._adjust_sparsity(curr_prune_step)
+            layers = list(self._sharable())
+            if layers:
+                dev = layers[0][1].weight.device
+                infos = torch.zeros(len(layers), 4, dtype=torch.int64, device=dev)
+                for i, (name, module) in enumerate(layers):
+                    self._launch_prune(module.weight.data, self._mask(name), curr_pruning_ratio, infos[i])
+                    # pruned weights are NOT zeroed here (utils/prune.py:88 is commented out)
+                if bool((infos[:, 0] != 0).any().item()):   # one read-back per prune event
+                    self._exit_not_enough()
+        else:
+            curr_pruning_ratio = self._adjust_sparsity(self.last_prune_step)
+        return curr_pruning_ratio
+
+    def one_shot_prune(self, one_shot_prune_perc):
+        """utils/prune.py:94-109."""
+        print('Pruning for dataset idx: %d' % (self.current_dataset_idx))
+        print('Pruning each layer by removing %.2f%% of values' % (100 * one_shot_prune_perc))
+        for name, module in self._sharable():
+            self.masks[name] = self._pruning_mask(module.weight.data, self._mask(name), name,
+                                                  pruning_ratio=one_shot_prune_perc)
+        self.make_pruned_zero()
+        return
+
+    # ------------------------------------------------------------------ K12 statistics
+    def _stats(self, with_piggy=False):
+        lib = _lib.load()
+        out = None
+        for name, module in self._sharable():
+            mask = self._mask(name)
+            if out is None:
+                out = torch.zeros(5, dtype=torch.int64, device=mask.device)
+            piggy = None
+            if with_piggy:
+                piggy = self._dense(module.piggymask.data, 'piggymask')
+            with torch.cuda.device(mask.device):
+                _lib.check(lib.cpgb_mask_stats(_lib.ptr(mask), _lib.ptr(piggy), mask.numel(),
+                                               self.inference_dataset_idx, _lib.ptr(out), _lib.stream_ptr()),
+                           'cpgb_mask_stats')
+        if out is None:
+            return [0, 0, 0, 0, 0]
+        return [int(v) for v in out.cpu().tolist()]
+
+    def calculate_sparsity(self):
+        zero, cur, _, _, _ = self._stats()
+        total = zero + cur
+        return float(zero) / float(total) if total != 0 else 0.0
+
+    def calculate_curr_task_ratio(self):
+        _, cur, _, _, numel = self._stats()
+        return float(cur) / numel * (self.args.network_width_multiplier ** 2)
+
+    def calculate_zero_ratio(self):
+        zero, _, _, _, numel = self._stats()
+        return float(zero) / numel * (self.args.network_width_multiplier ** 2)
+
+    def calculate_shared_part_ratio(self):
+        _, _, shared, picked, _ = self._stats(with_piggy=True)
+        return float(picked) / float(shared) if shared != 0 else 0.0
+
+    # ------------------------------------------------------------------ a6
+    def do_weight_decay_and_make_grads_zero(self):
+        """Sets grads of fixed weights to 0.  (utils/prune.py:195-211)"""
+        assert self.masks
+        lib = _lib.load()
+        mode = _MODES.get(self.args.mode)
+        for name, module in self._sharable():
+            if module._cpg_grads_final:
+                # the fused wgrad epilogue already produced (g*b + wd*W)[T==cur] / (g*W)[1<=T<cur]
+                module._cpg_grads_final = False
+                continue
+            mask = self._mask(name)
+            dW = module.weight.grad
+            dP = module.piggymask.grad if module.piggymask is not None else None
+            if mode is None:
+                # reference: weight grads are always decayed+masked; piggymask grads only in finetune/prune
+                dP, kmode = None, _lib.GRAD_PRUNE
+            else:
+                kmode = mode
+            if dW is None and dP is None:
+                continue
+            with torch.cuda.device(mask.device):
+                _lib.check(lib.cpgb_grad_epilogue(
+                    _lib.ptr(self._dense(dW.data, 'weight.grad')) if dW is not None else None,
+                    _lib.ptr(self._dense(dP.data, 'piggymask.grad')) if dP is not None else None,
+                    _lib.ptr(self._dense(module.weight.data, 'weight')), _lib.ptr(mask), mask.numel(),
+                    self.current_dataset_idx, float(self.args.weight_decay), kmode, _lib.stream_ptr()),
+                    'cpgb_grad_epilogue')
+        return
+
+    # ------------------------------------------------------------------ a9 / a10
+    def _zero_weights(self, inference_idx):
+        lib = _lib.load()
+        for name, module in self._sharable():
+            weight = self._dense(module.weight.data, 'weight')
+            mask = self._mask(name)
+            if mask.device != weight.device:
+                mask = mask.to(weight.device)   # the reference's `.cuda()` at utils/prune.py:228
+            with torch.cuda.device(weight.device):
+                _lib.check(lib.cpgb_apply_mask(_lib.ptr(weight), _lib.ptr(mask), weight.numel(), inference_idx,
+                                               _lib.stream_ptr()), 'cpgb_apply_mask')
+
+    def make_pruned_zero(self):
+        """Makes pruned weights 0.  (utils/prune.py:213-221)"""
+        assert self.masks
+        self._zero_weights(255)
+        return
+
+    def apply_mask(self):
+        """To be done to retrieve weights just for a particular dataset.  (utils/prune.py:223-231)"""
+        self._zero_weights(self.inference_dataset_idx)
+        return
+
+    def make_finetuning_mask(self):
+        """Turns previously pruned weights into trainable weights for
+           current dataset.  (utils/prune.py:233-243)"""
+        assert self.masks
+        self.current_dataset_idx += 1
+        lib = _lib.load()
+        for name, module in self._sharable():
+            mask = self._mask(name)
+            with torch.cuda.device(mask.device):
+                _lib.check(lib.cpgb_make_finetuning_mask(_lib.ptr(mask), mask.numel(), self.current_dataset_idx,
+                                                         _lib.stream_ptr()), 'cpgb_make_finetuning_mask')

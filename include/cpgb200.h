@@ -1,0 +1,143 @@
+/*
+ * cpgb200.h -- C ABI of libcpgb200.so: the B200 (sm_100a) implementation of CPG's
+ * masked-convolution train/prune hot path.
+ *
+ * The reference (ivclab/CPG) is pure Python and has no FFI; the functions below replace
+ * the *Python expressions* cited next to each of them (paths relative to the reference
+ * tree).  INTEGRATION.md shows the ctypes binding a CPG maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a caller-owned DEVICE pointer (PyTorch's allocator); the library
+ *     never allocates, frees or synchronises; scratch comes from the caller (`ws`);
+ *   - every call takes the cudaStream_t to launch on (as void*), is re-entrant and
+ *     capturable into a CUDA graph;
+ *   - returns 0 on success, a negative CPGB_E* code otherwise; cpgb_last_error() gives a
+ *     thread-local message;
+ *   - tensors are fp32; task masks are uint8 (0 = free/pruned, k = owned by task k), the
+ *     checkpoint layout of the reference (CPG_cifar100_main_normal.py:201-207);
+ *   - activations are addressed through explicit element strides (n,c,h,w), so NCHW and
+ *     channels_last (NHWC) both work; weights are dense [K, C/groups, R, S] as stored by
+ *     the reference's modules (models/layers.py:80-81, 169-170).
+ */
+#ifndef CPGB200_H_
+#define CPGB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CPGB_VERSION 100
+
+/* error codes */
+#define CPGB_OK 0
+#define CPGB_EINVAL (-1)    /* bad argument / unsupported shape               */
+#define CPGB_EWORKSPACE (-2) /* workspace too small (see cpgb_workspace_bytes) */
+#define CPGB_ECUDA (-3)     /* a CUDA runtime/driver call failed              */
+#define CPGB_ENOTELIGIBLE (-4) /* tcgen05 path forced but shape not eligible  */
+
+/* gradient-epilogue modes (SURVEY a4 + a6) */
+#define CPGB_GRAD_RAW 0      /* autograd contract: dW = g*b, dP = g*W  (models/layers.py:21-23,103) */
+#define CPGB_GRAD_FINETUNE 1 /* + utils/prune.py:203-208: dW=(g*b+wd*W)[T==cur]; dP=g*W[1<=T<cur]    */
+#define CPGB_GRAD_PRUNE 2    /* + utils/prune.py:203-205,209-210: same dW; dP = 0                     */
+
+/* kernel-path selection (process-wide, for tests/benchmarks) */
+#define CPGB_PATH_AUTO 0     /* tcgen05 implicit GEMM when eligible, else CUDA-core kernels */
+#define CPGB_PATH_SIMT 1     /* CUDA-core (fp32 FFMA) kernels only                         */
+#define CPGB_PATH_TCGEN05 2  /* tcgen05 only; CPGB_ENOTELIGIBLE when the shape is not      */
+
+/* Geometry of one SharableConv2d call: F.conv2d(input, weight, bias, stride, padding,
+ * dilation, groups) at models/layers.py:108.  SharableLinear (models/layers.py:194) is the
+ * same descriptor with H=W=R=S=P=Q=1 (see cpgb_linear_desc). */
+typedef struct cpgb_conv_desc {
+  int32_t N, C, H, W;          /* input  [N, C, H, W]                      */
+  int32_t K, R, S;             /* weight [K, C/groups, R, S]               */
+  int32_t P, Q;                /* output [N, K, P, Q]                      */
+  int32_t stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, groups;
+  int64_t xs[4];               /* element strides of input  (n, c, h, w)   */
+  int64_t ys[4];               /* element strides of output (n, k, p, q)   */
+} cpgb_conv_desc;
+
+int cpgb_version(void);
+const char *cpgb_last_error(void);
+int cpgb_set_path(int path);  /* CPGB_PATH_*; returns previous */
+int cpgb_get_path(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches claim) */
+int64_t cpgb_launch_count(void);
+
+/* Fill a descriptor for F.linear(x[M, I], W[O, I], bias) -- models/layers.py:194. */
+void cpgb_linear_desc(cpgb_conv_desc *d, int32_t M, int32_t I, int32_t O);
+
+/* Scratch bytes the conv/linear entry points need for descriptor `d` (max over
+ * fprop/dgrad/wgrad). */
+size_t cpgb_workspace_bytes(const cpgb_conv_desc *d);
+
+/* a1: Binarizer.forward, models/layers.py:15-19.  b = (p > thr) ? 1 : 0, NaN -> NaN. */
+int cpgb_binarize(const float *piggy, float *out, int64_t n, float thr, void *stream);
+
+/* a3/a5 forward: y = conv2d(x, (piggy > thr ? 1 : 0) * w, bias).  models/layers.py:98-109,
+ * 184-194.  piggy == NULL means "no piggymask" (task 1, models/layers.py:104-105).  The
+ * masked weight is never written to HBM on the CUDA-core path; the tcgen05 path stages a
+ * TF32, [K][R*S][C]-ordered operand copy in `ws`. */
+int cpgb_conv2d_fprop(const cpgb_conv_desc *d, const float *x, const float *w, const float *piggy,
+                      const float *bias, float *y, float thr, void *ws, size_t ws_bytes,
+                      void *stream);
+
+/* a4 dgrad: dx = conv_transpose(dy, W_eff).  dy uses d->ys strides, dx uses d->xs. */
+int cpgb_conv2d_dgrad(const cpgb_conv_desc *d, const float *dy, const float *w, const float *piggy,
+                      float *dx, float thr, void *ws, size_t ws_bytes, void *stream);
+
+/* a4 wgrad with the fused epilogue.  g = wgrad(x, dy) is reduced in `ws`
+ * and never returned; outputs:
+ *   dW [K,C/g,R,S] (always), dP (same shape; NULL iff piggy == NULL), dbias [K] (NULL ok).
+ * mode = CPGB_GRAD_RAW needs no tmask; the two fused modes read the uint8 task mask and
+ * apply utils/prune.py:195-211 in the same pass. */
+int cpgb_conv2d_wgrad_fused(const cpgb_conv_desc *d, const float *x, const float *dy, const float *w,
+                            const float *piggy, const uint8_t *tmask, int32_t cur, float weight_decay,
+                            int32_t mode, float *dW, float *dP, float *dbias, float thr, void *ws,
+                            size_t ws_bytes, void *stream);
+
+/* a6 standalone, in place on existing gradients: utils/prune.py:195-211.
+ * mode is CPGB_GRAD_FINETUNE or CPGB_GRAD_PRUNE; dW / dP may each be NULL
+ * ("if module.weight.grad is not None", "if module.piggymask is not None"). */
+int cpgb_grad_epilogue(float *dW, float *dP, const float *w, const uint8_t *tmask, int64_t n,
+                       int32_t cur, float weight_decay, int32_t mode, void *stream);
+
+/* a7: SparsePruner._pruning_mask, utils/prune.py:30-53, entirely on the device.
+ *   pool = {i : T[i]==cur or T[i]==0};  k = round_half_even(ratio * |pool|)  (python round());
+ *   cut = k-th smallest |w[pool]| (exact radix select on the fp32 bit pattern);
+ *   T[i] = 0 where |w[i]| <= cut and T[i] == cur.
+ * info (device, 4 x int64): [0]=status (0 ok, 2 = k outside 1..|pool| -> the reference's
+ * sys.exit(2) path, T untouched), [1]=|pool|, [2]=k, [3]=bit pattern of cut (low 32 bits).
+ * ws: cpgb_prune_workspace_bytes() bytes. */
+size_t cpgb_prune_workspace_bytes(void);
+int cpgb_prune_select(const float *w, uint8_t *tmask, int64_t n, int32_t cur, double ratio,
+                      int64_t *info, void *ws, size_t ws_bytes, void *stream);
+
+/* a9: apply_mask (utils/prune.py:223-231): w[T==0]=0; w[T>inference_idx]=0.
+ *     make_pruned_zero (utils/prune.py:213-221): pass inference_idx = 255. */
+int cpgb_apply_mask(float *w, const uint8_t *tmask, int64_t n, int32_t inference_idx, void *stream);
+
+/* a10: make_finetuning_mask (utils/prune.py:233-243): T[T==0] = new_cur. */
+int cpgb_make_finetuning_mask(uint8_t *tmask, int64_t n, int32_t new_cur, void *stream);
+
+/* K12: counts behind calculate_{sparsity,curr_task_ratio,zero_ratio,shared_part_ratio}
+ * (utils/prune.py:111-193).  Accumulates (+=) into out[5] (device int64):
+ * [0]=#(T==0) [1]=#(T==idx) [2]=#(0<T<idx) [3]=#(0<T<idx and piggy>0.005) [4]=n.
+ * piggy may be NULL. */
+int cpgb_mask_stats(const uint8_t *tmask, const float *piggy, int64_t n, int32_t inference_idx,
+                    int64_t *out, void *stream);
+
+/* Data-parallel helpers: dW and dP have disjoint support after a6, so one fp32
+ * buffer m = dW + dP travels through the all-reduce; cpgb_split_merged_grad restores
+ * dW = m[T==cur], dP = m[1<=T<cur]. */
+int cpgb_merge_grads(const float *dW, const float *dP, float *merged, int64_t n, void *stream);
+int cpgb_split_merged_grad(const float *merged, const uint8_t *tmask, int64_t n, int32_t cur,
+                           float *dW, float *dP, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPGB200_H_ */

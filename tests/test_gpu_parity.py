@@ -1,0 +1,404 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI via the
+product's module API, against (1) the golden vectors from the live reference and (2) the CPU
+oracle on seeded inputs; plus size-independent properties at BASELINE.json's full sizes.
+
+Bars (north_star): bit-exact for Binarizer outputs, task masks, prune indices and cut values;
+<= 1e-3 relative for fp32 activations / gradients (relative = max|a-b| / max|b|).  The
+CUDA-core path is plain fp32 and is held to 2e-5.
+"""
+import zlib
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+pytestmark = pytest.mark.gpu
+
+from cpg_b200 import _lib  # noqa: E402
+import cpg_b200.layers as nl  # noqa: E402
+import cpg_b200.prune as cpg_prune  # noqa: E402
+from oracle import cpg_oracle as O  # noqa: E402
+from tests.toy import load_toy  # noqa: E402
+
+DEV = 'cuda:0'
+TOL_TC = 1e-3      # north_star tolerance (TF32 tensor-core path)
+TOL_FP32 = 2e-5    # CUDA-core fp32 path (summation order only)
+
+
+def G(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
+
+
+@pytest.fixture(autouse=True)
+def _reset_path():
+    _lib.set_path(_lib.PATH_AUTO)
+    yield
+    _lib.set_path(_lib.PATH_AUTO)
+
+
+CONV_CASES = ['conv_cfg1', 'conv_cfg1_nopiggy', 'conv_c32', 'conv_s2_g2', 'conv_1x1_s2', 'conv_dil2',
+              'conv_7x7_s2']
+
+
+def _run_conv_case(g, path, channels_last_in):
+    stride, pad, dil, groups = [int(v) for v in g['conv']]
+    K, Cg, R, S = g['w'].shape
+    m = nl.SharableConv2d(Cg * groups, K, (R, S), stride=stride, padding=pad, dilation=dil, groups=groups,
+                          bias='b' in g).to(DEV)
+    with torch.no_grad():
+        m.weight.copy_(G(g['w']))
+        if 'b' in g:
+            m.bias.copy_(G(g['b']))
+    if 'p' in g:
+        m.piggymask = nn.Parameter(G(g['p'].copy()))
+    x = G(g['x'])
+    if channels_last_in:
+        x = x.contiguous(memory_format=torch.channels_last)
+    x.requires_grad_(True)
+    _lib.set_path(path)
+    y = m(x)
+    y.backward(G(g['dy']))
+    return m, x, y
+
+
+@pytest.mark.parametrize('name', CONV_CASES)
+@pytest.mark.parametrize('path', [_lib.PATH_SIMT, _lib.PATH_AUTO])
+@pytest.mark.parametrize('cl', [False, True])
+def test_conv_golden(golden, name, path, cl):
+    g = golden(name)
+    m, x, y = _run_conv_case(g, path, cl)
+    tol = TOL_FP32 if path == _lib.PATH_SIMT else TOL_TC
+    assert y.shape == g['y'].shape
+    assert rel(y, torch.from_numpy(g['y'])) <= tol
+    assert rel(x.grad, torch.from_numpy(g['dx'])) <= tol
+    assert rel(m.weight.grad, torch.from_numpy(g['dW'])) <= tol
+    if 'p' in g:
+        assert rel(m.piggymask.grad, torch.from_numpy(g['dP'])) <= tol
+        # dW must be exactly zero where the binarised mask is zero
+        assert (m.weight.grad.cpu()[torch.from_numpy(g['bin']) == 0] == 0).all()
+    if 'b' in g:
+        assert rel(m.bias.grad, torch.from_numpy(g['db'])) <= tol
+
+
+@pytest.mark.parametrize('name', ['linear_small', 'linear_nopiggy'])
+@pytest.mark.parametrize('path', [_lib.PATH_SIMT, _lib.PATH_AUTO])
+def test_linear_golden(golden, name, path):
+    g = golden(name)
+    O_, I = g['w'].shape
+    m = nl.SharableLinear(I, O_).to(DEV)
+    with torch.no_grad():
+        m.weight.copy_(G(g['w']))
+        m.bias.copy_(G(g['b']))
+    if 'p' in g:
+        m.piggymask = nn.Parameter(G(g['p'].copy()))
+    x = G(g['x']).requires_grad_(True)
+    _lib.set_path(path)
+    y = m(x)
+    y.backward(G(g['dy']))
+    tol = TOL_FP32 if path == _lib.PATH_SIMT else TOL_TC
+    assert rel(y, torch.from_numpy(g['y'])) <= tol
+    assert rel(x.grad, torch.from_numpy(g['dx'])) <= tol
+    assert rel(m.weight.grad, torch.from_numpy(g['dW'])) <= tol
+    assert rel(m.bias.grad, torch.from_numpy(g['db'])) <= tol
+    if 'p' in g:
+        assert rel(m.piggymask.grad, torch.from_numpy(g['dP'])) <= tol
+
+
+def test_binarizer_golden_bit_exact(golden):
+    g = golden('binarizer')
+    p = G(g['p']).requires_grad_(True)
+    b = nl.Binarizer.apply(p, nl.DEFAULT_THRESHOLD)
+    assert np.array_equal(b.detach().cpu().numpy(), g['b'], equal_nan=True)
+    b.backward(G(g['g']))
+    assert np.array_equal(p.grad.cpu().numpy(), g['dp'])
+    # odd length / unaligned view exercises the scalar tail
+    q = G(g['p'])[1:-2]
+    assert np.array_equal(nl.Binarizer.apply(q, 5e-3).cpu().numpy(), g['b'][1:-2], equal_nan=True)
+    assert nl.Binarizer.apply(torch.empty(0, device=DEV), 5e-3).numel() == 0
+
+
+def _names(g):
+    return [str(n) for n in g['names']]
+
+
+@pytest.mark.parametrize('mode', ['finetune', 'prune'])
+def test_a6_standalone_golden(golden, mode):
+    g = golden('pruner')
+    model, pr, masks = load_toy(g, nl, cpg_prune, mode, DEV)
+    assert pr.current_dataset_idx == 2
+    pr.do_weight_decay_and_make_grads_zero()
+    for name, mod in model.named_modules():
+        if name in masks:
+            k = name.replace('.', '_')
+            ref_w, ref_p = g[f'a6_{mode}_dW_{k}'], g[f'a6_{mode}_dP_{k}']
+            got_w, got_p = mod.weight.grad.cpu().numpy(), mod.piggymask.grad.cpu().numpy()
+            assert np.array_equal(got_w == 0, ref_w == 0) and np.array_equal(got_p, ref_p)
+            assert np.abs(got_w - ref_w).max() <= 1e-6 * np.abs(ref_w).max()
+
+
+def test_a7_prune_golden_bit_exact(golden):
+    g = golden('pruner')
+    for i, ratio in enumerate(g['a7_ratios']):
+        model, pr, masks = load_toy(g, nl, cpg_prune, 'prune', DEV)
+        for name, mod in model.named_modules():
+            if name not in masks:
+                continue
+            k = name.replace('.', '_')
+            if int(g[f'a7_{i}_exit_{k}']) == 2:
+                with pytest.raises(SystemExit) as e:
+                    pr._pruning_mask(mod.weight.data, masks[name], name, float(ratio))
+                assert e.value.code == 2
+                assert np.array_equal(masks[name].cpu().numpy(), g['T_' + k])  # untouched
+            else:
+                out = pr._pruning_mask(mod.weight.data, masks[name], name, float(ratio))
+                assert out is masks[name]
+                assert np.array_equal(out.cpu().numpy(), g[f'a7_{i}_T_{k}']), (ratio, name)
+
+
+def test_a8_schedule_golden(golden):
+    g = golden('pruner')
+    model, pr, masks = load_toy(g, nl, cpg_prune, 'prune', DEV)
+    names = _names(g)
+    ratios, zeros = [], []
+    for step in range(12):
+        ratios.append(pr.gradually_prune(step))
+        zeros.append([int(masks[n].eq(0).sum()) for n in names])
+    assert np.array_equal(np.array(ratios), g['a8_ratios'])
+    assert np.array_equal(np.array(zeros), g['a8_zero_counts'])
+    for n in names:
+        assert np.array_equal(masks[n].cpu().numpy(), g['a8_T_' + n.replace('.', '_')])
+
+
+def test_a9_a10_stats_golden(golden):
+    g = golden('pruner')
+    model, pr, masks = load_toy(g, nl, cpg_prune, 'prune', DEV)
+    stats = [pr.calculate_sparsity(), pr.calculate_curr_task_ratio(), pr.calculate_zero_ratio(),
+             pr.calculate_shared_part_ratio()]
+    assert np.array_equal(np.array(stats), g['stats'])
+    pr.apply_mask()
+    for name, mod in model.named_modules():
+        if name in masks:
+            assert np.array_equal(mod.weight.data.cpu().numpy(), g['a9_apply_' + name.replace('.', '_')])
+    model, pr, masks = load_toy(g, nl, cpg_prune, 'prune', DEV)
+    pr.make_pruned_zero()
+    for name, mod in model.named_modules():
+        if name in masks:
+            assert np.array_equal(mod.weight.data.cpu().numpy(), g['a9_zero_' + name.replace('.', '_')])
+    model, pr, masks = load_toy(g, nl, cpg_prune, 'prune', DEV)
+    pr.make_finetuning_mask()
+    assert pr.current_dataset_idx == int(g['a10_cur'])
+    for n in masks:
+        assert np.array_equal(masks[n].cpu().numpy(), g['a10_T_' + n.replace('.', '_')])
+
+
+@pytest.mark.parametrize('mode', ['finetune', 'prune'])
+@pytest.mark.parametrize('path', [_lib.PATH_SIMT, _lib.PATH_AUTO])
+def test_fused_epilogue_equals_a4_then_a6(mode, path):
+    """The fused wgrad epilogue must hand optimizers.step() the same tensors as
+    autograd followed by do_weight_decay_and_make_grads_zero (oracle.fused_weight_grads)."""
+    rng = np.random.RandomState(3)
+    N, C, H, K = 4, 32, 8, 64
+    x = rng.standard_normal((N, C, H, H)).astype(np.float32)
+    w = (rng.standard_normal((K, C, 3, 3)) * 0.1).astype(np.float32)
+    p = rng.uniform(0, 0.01, size=w.shape).astype(np.float32)
+    t = rng.randint(0, 5, size=w.shape).astype(np.uint8)
+    dy = rng.standard_normal((N, K, H, H)).astype(np.float32)
+    cur, wd = 3, 4e-5
+    _, _, _, _, g_raw = O.conv2d_backward(torch.from_numpy(x), torch.from_numpy(w), torch.from_numpy(p), None,
+                                          torch.from_numpy(dy), 1, 1, 1, 1)
+    ref_dW, ref_dP = O.fused_weight_grads(g_raw, torch.from_numpy(w), torch.from_numpy(p),
+                                          torch.from_numpy(t), cur, wd, mode)
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv = nl.SharableConv2d(C, K, 3, padding=1, bias=False)
+            self.datasets = ['a', 'b', 'c']
+
+    from tests.toy import Wrap, make_args
+    net = Wrap(Net()).to(DEV)
+    with torch.no_grad():
+        net.module.conv.weight.copy_(G(w))
+    net.module.conv.piggymask = nn.Parameter(G(p))
+    args = make_args(mode, dataset='c', wd=wd)     # prune: cur = index('c')+1 = 3
+    if mode == 'finetune':
+        args.finetune_again = True
+    masks = {'module.conv': G(t)}
+    pr = cpg_prune.SparsePruner(net, masks, args, 0, 8, 3)
+    assert pr.current_dataset_idx == cur
+    _lib.set_path(path)
+    tol = TOL_FP32 if path == _lib.PATH_SIMT else TOL_TC
+    for fused in (True, False):
+        pr.fuse_grad_epilogue = fused
+        net.zero_grad(set_to_none=True)
+        y = net.module.conv(G(x))
+        y.backward(G(dy))
+        assert net.module.conv._cpg_grads_final == fused
+        pr.do_weight_decay_and_make_grads_zero()
+        assert not net.module.conv._cpg_grads_final
+        dW, dP = net.module.conv.weight.grad, net.module.conv.piggymask.grad
+        assert rel(dW, ref_dW) <= tol and rel(dP, ref_dP) <= max(tol, 1e-30)
+        assert np.array_equal(dW.cpu().numpy() == 0, ref_dW.numpy() == 0) or path != _lib.PATH_SIMT
+        assert (dW.cpu()[torch.from_numpy(t) != cur] == 0).all()
+        keep = (torch.from_numpy(t) > 0) & (torch.from_numpy(t) < cur) if mode == 'finetune' else \
+            torch.zeros(t.shape, dtype=torch.bool)
+        assert (dP.cpu()[~keep] == 0).all()
+
+
+@pytest.mark.parametrize('n', [1, 5, 1023, 65537, (1 << 24) + 3])
+def test_prune_select_vs_oracle_large(n):
+    """Exact k-th order statistic and mask update at sizes up to FC2's 16.8 M weights
+    (SURVEY a7), with heavy ties and negative values."""
+    rng = np.random.RandomState(n % 1000)
+    w = rng.standard_normal(n).astype(np.float32)
+    w[::5] = np.float32(0.25)            # ties
+    w[1::7] *= 0
+    t = rng.randint(0, 4, size=n).astype(np.uint8)
+    lib = _lib.load()
+    ws = torch.empty(lib.cpgb_prune_workspace_bytes(), dtype=torch.uint8, device=DEV)
+    for ratio in (0.3, 0.5, 0.999):
+        tg = G(t.copy())
+        info = torch.zeros(4, dtype=torch.int64, device=DEV)
+        _lib.check(lib.cpgb_prune_select(_lib.ptr(G(w)), _lib.ptr(tg), n, 2, ratio, _lib.ptr(info),
+                                         _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), 'prune')
+        info = info.cpu().tolist()
+        tt = torch.from_numpy(t.copy())
+        try:
+            _, cut, k, pool = O.pruning_mask(torch.from_numpy(w), tt, 2, ratio)
+        except O.NotEnoughWeights:
+            assert info[0] == 2 and np.array_equal(tg.cpu().numpy(), t)
+            continue
+        assert info[0] == 0 and info[1] == pool and info[2] == k
+        assert info[3] == int(np.float32(cut).view(np.uint32))
+        assert np.array_equal(tg.cpu().numpy(), tt.numpy())
+
+
+@pytest.mark.parametrize('mode', ['prune', 'finetune'])
+def test_trajectory_vs_reference_golden(golden, mode):
+    """6 training steps of a narrow VGG16-BN (task-2 regime) through the product layers + product
+    pruner, against the reference's own Manager.train trajectory (tests/golden/traj_*.npz)."""
+    from tests.trajectory import run_trajectory
+    g = golden('traj_' + mode)
+    model, masks = run_trajectory(nl.SharableConv2d, nl.SharableLinear, mode, device=DEV, pruner_factory='product')
+    first = [m for _, m in model.named_modules() if isinstance(m, nl.SharableConv2d)][0]
+    assert rel(first.weight, torch.from_numpy(g['w_first'])) <= 5e-3
+    worst = 0.0
+    for n, p in model.named_parameters():
+        a = p.detach().double().cpu().numpy()
+        ref = g['sum_module.' + n]
+        worst = max(worst, abs(np.abs(a).sum() - ref[1]) / max(ref[1], 1e-12))
+    assert worst <= 5e-3, worst
+    for n in masks:
+        z, zr = int((masks[n].numpy() == 0).sum()), int(g['maskzeros_module.' + n])
+        assert abs(z - zr) <= max(2, 0.01 * zr), (n, z, zr)
+
+
+VGG_SHAPES = [  # (C, K, HW) of the VGG16-cifar sharable convs, batch 128
+    (3, 64, 32), (64, 64, 32), (64, 128, 16), (128, 128, 16), (128, 256, 8), (256, 256, 8),
+    (256, 512, 4), (512, 512, 4), (512, 512, 2)]
+
+
+@pytest.mark.parametrize('C,K,HW', VGG_SHAPES)
+def test_full_size_adjoint_properties(C, K, HW):
+    """At BASELINE.json's full size (batch 128) the oracle is too slow, so check size-independent
+    identities of the three kernels against each other and against torch/cuDNN on the same GPU:
+      <conv(x), dy> == <x, dgrad(dy)> == <W_eff, g>      (adjointness)
+      conv(a*x1 + x2) == a*conv(x1) + conv(x2)            (linearity)."""
+    torch.manual_seed(C + K + HW)
+    N = 128
+    m = nl.SharableConv2d(C, K, 3, padding=1, bias=False).to(DEV)
+    with torch.no_grad():
+        m.weight.normal_(0, (2.0 / (K * 9)) ** 0.5)
+    m.piggymask = nn.Parameter(torch.rand_like(m.weight) * 0.01)
+    x = torch.randn(N, C, HW, HW, device=DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    dy = torch.randn(N, K, HW, HW, device=DEV).contiguous(memory_format=torch.channels_last)
+    y = m(x)
+    y.backward(dy)
+    b = (m.piggymask > 5e-3).float()
+    w_eff = (m.weight * b).detach()
+    lhs = (y.detach().double() * dy.double()).sum().item()
+    mid = (x.detach().double() * x.grad.double()).sum().item()
+    # dW = g*b, so <W_eff, g> = <W, dW>
+    rhs = (m.weight.detach().double() * m.weight.grad.double()).sum().item()
+    scale = y.detach().double().norm().item() * dy.double().norm().item()
+    assert abs(lhs - mid) <= 1e-3 * scale and abs(lhs - rhs) <= 1e-3 * scale
+    # against cuDNN on the same device (fp32, TF32 off): the real bar named in SURVEY section 2
+    torch.backends.cudnn.allow_tf32 = False
+    y_ref = torch.nn.functional.conv2d(x.detach(), w_eff, None, 1, 1)
+    assert rel(y, y_ref) <= TOL_TC
+    dx_ref = torch.nn.grad.conv2d_input(x.shape, w_eff, dy, 1, 1)
+    g_ref = torch.nn.grad.conv2d_weight(x.detach(), w_eff.shape, dy, 1, 1)
+    assert rel(x.grad, dx_ref) <= TOL_TC
+    assert rel(m.weight.grad, g_ref * b) <= TOL_TC
+    assert rel(m.piggymask.grad, g_ref * m.weight.detach()) <= TOL_TC
+    with torch.no_grad():
+        x2 = torch.randn_like(x)
+        lin = m(1.5 * x.detach() + x2)
+        assert rel(lin, 1.5 * y.detach() + m(x2)) <= TOL_TC
+
+
+@pytest.mark.parametrize('I,O_', [(512, 4096), (4096, 4096)])
+def test_full_size_linear_vs_cublas(I, O_):
+    torch.manual_seed(I)
+    m = nl.SharableLinear(I, O_).to(DEV)
+    with torch.no_grad():
+        m.weight.normal_(0, 0.01)
+        m.bias.normal_(0, 0.01)
+    m.piggymask = nn.Parameter(torch.rand_like(m.weight) * 0.01)
+    x = torch.randn(128, I, device=DEV, requires_grad=True)
+    dy = torch.randn(128, O_, device=DEV)
+    y = m(x)
+    y.backward(dy)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    b = (m.piggymask > 5e-3).float()
+    w_eff = (m.weight * b).detach()
+    assert rel(y, x.detach() @ w_eff.t() + m.bias.detach()) <= TOL_TC
+    assert rel(x.grad, dy @ w_eff) <= TOL_TC
+    g_ref = dy.t() @ x.detach()
+    assert rel(m.weight.grad, g_ref * b) <= TOL_TC
+    assert rel(m.piggymask.grad, g_ref * m.weight.detach()) <= TOL_TC
+    assert rel(m.bias.grad, dy.sum(0)) <= TOL_TC
+
+
+def test_empty_batch_and_errors():
+    m = nl.SharableConv2d(8, 8, 3, padding=1).to(DEV)
+    with torch.no_grad():
+        m.weight.normal_()
+        m.bias.zero_()
+    y = m(torch.empty(0, 8, 5, 5, device=DEV))
+    assert y.shape == (0, 8, 5, 5)
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 4, 5, 5, device=DEV))      # channel mismatch
+    with pytest.raises(_lib.CpgbError):
+        m(torch.zeros(1, 8, 5, 5, device=DEV, dtype=torch.float64))
+
+
+def test_graph_capture_of_fwd_bwd():
+    """The C ABI never allocates or synchronises, so a whole fwd+bwd captures into a CUDA graph."""
+    m = nl.SharableConv2d(32, 64, 3, padding=1, bias=False).to(DEV)
+    with torch.no_grad():
+        m.weight.normal_(0, 0.05)
+    m.piggymask = nn.Parameter(torch.rand_like(m.weight) * 0.01)
+    x = torch.randn(8, 32, 16, 16, device=DEV).contiguous(memory_format=torch.channels_last)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            m.zero_grad(set_to_none=True)
+            m(x).square().mean().backward()
+    torch.cuda.current_stream().wait_stream(s)
+    ref = m.weight.grad.clone()
+    graph = torch.cuda.CUDAGraph()
+    m.zero_grad(set_to_none=True)
+    with torch.cuda.graph(graph):
+        m(x).square().mean().backward()
+    m.weight.grad.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert rel(m.weight.grad, ref) <= 1e-6
