@@ -337,14 +337,20 @@ def kernel_table(device, regime_has_piggy, iters=5):
         dW, dP, dx = torch.empty_like(w), (torch.empty_like(w) if p is not None else None), torch.empty_like(x)
         st = _lib.stream_ptr()
         P = _lib.ptr
-        f = time_call(lambda: _lib.check(lib.cpgb_conv2d_fprop(d, P(x), P(w), P(p), None, P(y), 5e-3, P(ws),
+        nst = lib.cpgb_staged_weight_bytes(d)
+        staged = torch.empty(max(nst, 256), dtype=torch.uint8, device=device)
+        stg = 0.0
+        if nst:
+            stg = time_call(lambda: _lib.check(lib.cpgb_stage_weights(d, P(w), P(p), 5e-3, P(staged), nst, st), 'stage'))
+        sp = P(staged) if nst else None
+        f = time_call(lambda: _lib.check(lib.cpgb_conv2d_fprop(d, P(x), P(w), P(p), None, P(y), 5e-3, sp, P(ws),
                                                                 ws.numel(), st), 'fprop'))
         dg = 0.0 if first else time_call(lambda: _lib.check(lib.cpgb_conv2d_dgrad(
-            d, P(dy), P(w), P(p), P(dx), 5e-3, P(ws), ws.numel(), st), 'dgrad'))
+            d, P(dy), P(w), P(p), P(dx), 5e-3, sp, P(ws), ws.numel(), st), 'dgrad'))
         wg = time_call(lambda: _lib.check(lib.cpgb_conv2d_wgrad_fused(
             d, P(x), P(dy), P(w), P(p), P(t), 1, WD, _lib.GRAD_FINETUNE, P(dW), P(dP), None, 5e-3, P(ws),
             ws.numel(), st), 'wgrad'))
-        rows.append({'layer': kind, 'flop': flops, 'fprop_ms': f, 'dgrad_ms': dg, 'wgrad_ms': wg,
+        rows.append({'layer': kind, 'flop': flops, 'stage_ms': stg, 'fprop_ms': f, 'dgrad_ms': dg, 'wgrad_ms': wg,
                      'n_weights': w.numel()})
 
     for i, (C, K, HW) in enumerate(shapes):

@@ -13,7 +13,7 @@ PATH_AUTO, PATH_SIMT, PATH_TCGEN05 = 0, 1, 2
 
 EXPORTS = [
     'cpgb_version', 'cpgb_last_error', 'cpgb_set_path', 'cpgb_get_path', 'cpgb_launch_count', 'cpgb_linear_desc',
-    'cpgb_workspace_bytes', 'cpgb_binarize', 'cpgb_conv2d_fprop', 'cpgb_conv2d_dgrad',
+    'cpgb_workspace_bytes', 'cpgb_staged_weight_bytes', 'cpgb_stage_weights', 'cpgb_binarize', 'cpgb_conv2d_fprop', 'cpgb_conv2d_dgrad',
     'cpgb_conv2d_wgrad_fused', 'cpgb_grad_epilogue', 'cpgb_prune_workspace_bytes', 'cpgb_prune_select',
     'cpgb_apply_mask', 'cpgb_make_finetuning_mask', 'cpgb_mask_stats', 'cpgb_merge_grads',
     'cpgb_split_merged_grad',
@@ -54,8 +54,10 @@ def load():
         'cpgb_linear_desc': (None, [dp, i32, i32, i32]),
         'cpgb_workspace_bytes': (sz, [dp]),
         'cpgb_binarize': (ctypes.c_int, [vp, vp, i64, f32, vp]),
-        'cpgb_conv2d_fprop': (ctypes.c_int, [dp, vp, vp, vp, vp, vp, f32, vp, sz, vp]),
-        'cpgb_conv2d_dgrad': (ctypes.c_int, [dp, vp, vp, vp, vp, f32, vp, sz, vp]),
+        'cpgb_staged_weight_bytes': (sz, [dp]),
+        'cpgb_stage_weights': (ctypes.c_int, [dp, vp, vp, f32, vp, sz, vp]),
+        'cpgb_conv2d_fprop': (ctypes.c_int, [dp, vp, vp, vp, vp, vp, f32, vp, vp, sz, vp]),
+        'cpgb_conv2d_dgrad': (ctypes.c_int, [dp, vp, vp, vp, vp, f32, vp, vp, sz, vp]),
         'cpgb_conv2d_wgrad_fused': (ctypes.c_int, [dp, vp, vp, vp, vp, vp, i32, f32, i32, vp, vp, vp, f32,
                                                   vp, sz, vp]),
         'cpgb_grad_epilogue': (ctypes.c_int, [vp, vp, vp, vp, i64, i32, f32, i32, vp]),

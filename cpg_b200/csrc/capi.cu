@@ -78,10 +78,17 @@ void cpgb_linear_desc(cpgb_conv_desc *d, int32_t M, int32_t I, int32_t O) {
 
 size_t cpgb_workspace_bytes(const cpgb_conv_desc *d) {
   if (!d || d->groups <= 0) return 0;
-  size_t g_bytes = weight_elems(d) * sizeof(float);           // raw weight gradient (wgrad)
-  size_t tc = tc_workspace_bytes(*d);
+  size_t g_bytes = weight_elems(d) * sizeof(float);           // raw weight gradient (CUDA-core wgrad)
+  size_t tc = tc_workspace_bytes(*d);                          // staged operand / split-K partial sums
   g_bytes = (g_bytes + 255) & ~(size_t)255;
-  return g_bytes + ((tc + 255) & ~(size_t)255);
+  return g_bytes > tc ? g_bytes : tc;
+}
+
+size_t cpgb_staged_weight_bytes(const cpgb_conv_desc *d) {
+  if (!d || validate_desc(d)) return 0;
+  if (g_path.load() == CPGB_PATH_SIMT) return 0;
+  if (!tc_eligible(*d, 0) && !tc_eligible(*d, 1)) return 0;
+  return tc_staged_bytes(*d);
 }
 
 static int pick_tc(const cpgb_conv_desc *d, int op, bool *use_tc) {
@@ -95,27 +102,62 @@ static int pick_tc(const cpgb_conv_desc *d, int op, bool *use_tc) {
   return CPGB_OK;
 }
 
-int cpgb_conv2d_fprop(const cpgb_conv_desc *d, const float *x, const float *w, const float *piggy,
-                      const float *bias, float *y, float thr, void *ws, size_t ws_bytes, void *stream) {
+// bring-up hook (not part of the public header): MN-major operand descriptor fields
+void cpgb_debug_set_mn(int layout, int lbo, int sbo, int kadv, int tma_swizzle) {
+  debug_set_mn(layout, lbo, sbo, kadv, tma_swizzle);
+}
+
+int cpgb_stage_weights(const cpgb_conv_desc *d, const float *w, const float *piggy, float thr, void *staged,
+                       size_t staged_bytes, void *stream) {
   int rc = validate_desc(d);
   if (rc) return rc;
+  if (!w || !staged) { set_error("cpgb_stage_weights: null pointer"); return CPGB_EINVAL; }
+  return tc_stage_weights(*d, w, piggy, thr, staged, staged_bytes, (cudaStream_t)stream);
+}
+
+// staged operand for a tensor-core call: the caller's, or built into ws
+static int staged_operand(const cpgb_conv_desc *d, const float *w, const float *piggy, float thr, const void *staged,
+                          void *ws, size_t ws_bytes, cudaStream_t st, const float **out) {
+  if (staged) { *out = reinterpret_cast<const float *>(staged); return CPGB_OK; }
+  if (!ws || ws_bytes < tc_staged_bytes(*d)) {
+    set_error("workspace %zu < %zu (staged weights)", ws_bytes, tc_staged_bytes(*d));
+    return CPGB_EWORKSPACE;
+  }
+  int rc = tc_stage_weights(*d, w, piggy, thr, ws, ws_bytes, st);
+  *out = reinterpret_cast<const float *>(ws);
+  return rc;
+}
+
+int cpgb_conv2d_fprop(const cpgb_conv_desc *d, const float *x, const float *w, const float *piggy,
+                      const float *bias, float *y, float thr, const void *staged, void *ws, size_t ws_bytes,
+                      void *stream) {
+  int rc = validate_desc(d);
+  if (rc) return rc;
+  if (d->N == 0) return CPGB_OK;  // empty batch: nothing to compute, y is empty
   if (!x || !w || !y) { set_error("cpgb_conv2d_fprop: null pointer"); return CPGB_EINVAL; }
-  if (d->N == 0) return CPGB_OK;
   bool use_tc;
   if ((rc = pick_tc(d, 0, &use_tc))) return rc;
-  if (use_tc) return tc_fprop(*d, x, w, piggy, bias, y, thr, ws, ws_bytes, (cudaStream_t)stream);
+  if (use_tc) {
+    const float *wt;
+    if ((rc = staged_operand(d, w, piggy, thr, staged, ws, ws_bytes, (cudaStream_t)stream, &wt))) return rc;
+    return tc_fprop(*d, x, wt, bias, y, (cudaStream_t)stream);
+  }
   return simt_fprop(make_geom(*d), x, w, piggy, bias, y, thr, (cudaStream_t)stream);
 }
 
 int cpgb_conv2d_dgrad(const cpgb_conv_desc *d, const float *dy, const float *w, const float *piggy, float *dx,
-                      float thr, void *ws, size_t ws_bytes, void *stream) {
+                      float thr, const void *staged, void *ws, size_t ws_bytes, void *stream) {
   int rc = validate_desc(d);
   if (rc) return rc;
-  if (!dy || !w || !dx) { set_error("cpgb_conv2d_dgrad: null pointer"); return CPGB_EINVAL; }
   if (d->N == 0) return CPGB_OK;
+  if (!dy || !w || !dx) { set_error("cpgb_conv2d_dgrad: null pointer"); return CPGB_EINVAL; }
   bool use_tc;
   if ((rc = pick_tc(d, 1, &use_tc))) return rc;
-  if (use_tc) return tc_dgrad(*d, dy, w, piggy, dx, thr, ws, ws_bytes, (cudaStream_t)stream);
+  if (use_tc) {
+    const float *wt;
+    if ((rc = staged_operand(d, w, piggy, thr, staged, ws, ws_bytes, (cudaStream_t)stream, &wt))) return rc;
+    return tc_dgrad(*d, dy, wt, dx, (cudaStream_t)stream);
+  }
   return simt_dgrad(make_geom(*d), dy, w, piggy, dx, thr, (cudaStream_t)stream);
 }
 
@@ -125,7 +167,7 @@ int cpgb_conv2d_wgrad_fused(const cpgb_conv_desc *d, const float *x, const float
                             size_t ws_bytes, void *stream) {
   int rc = validate_desc(d);
   if (rc) return rc;
-  if (!x || !dy || !w || !dW) { set_error("cpgb_conv2d_wgrad_fused: null pointer"); return CPGB_EINVAL; }
+  if ((d->N != 0 && (!x || !dy)) || !w || !dW) { set_error("cpgb_conv2d_wgrad_fused: null pointer"); return CPGB_EINVAL; }
   if (mode < CPGB_GRAD_RAW || mode > CPGB_GRAD_PRUNE) { set_error("bad grad mode %d", mode); return CPGB_EINVAL; }
   if (mode != CPGB_GRAD_RAW && !tmask) { set_error("fused grad modes need the task mask"); return CPGB_EINVAL; }
   if ((piggy == nullptr) != (dP == nullptr)) { set_error("dP must be given iff piggy is"); return CPGB_EINVAL; }
@@ -137,20 +179,21 @@ int cpgb_conv2d_wgrad_fused(const cpgb_conv_desc *d, const float *x, const float
   cudaStream_t st = (cudaStream_t)stream;
   Geom g = make_geom(*d);
   float *gbuf = reinterpret_cast<float *>(ws);
-  if (d->N == 0) {
-    CPGB_CUDA_OK(cudaMemsetAsync(gbuf, 0, n * sizeof(float), st));
+  bool use_tc = false;
+  if (d->N != 0 && (rc = pick_tc(d, 2, &use_tc))) return rc;
+  if (use_tc) {
+    // tensor-core wgrad: split-K partial sums in ws, summed inside the fused epilogue
+    if ((rc = tc_wgrad_fused(*d, x, dy, w, piggy, tmask, cur, weight_decay, mode, thr, dW, dP, ws, ws_bytes, st)))
+      return rc;
   } else {
-    bool use_tc;
-    if ((rc = pick_tc(d, 2, &use_tc))) return rc;
-    if (use_tc) {
-      // tensor-core wgrad accumulates straight into dense [K, C/g, R, S] order
-      const size_t goff = (n * sizeof(float) + 255) & ~(size_t)255;
-      if ((rc = tc_wgrad_raw(*d, x, dy, gbuf, (char *)ws + goff, ws_bytes - goff, st))) return rc;
-    } else {
-      if ((rc = simt_wgrad_raw(g, x, dy, gbuf, st))) return rc;
+    if (d->N == 0) {
+      CPGB_CUDA_OK(cudaMemsetAsync(gbuf, 0, n * sizeof(float), st));
+    } else if ((rc = simt_wgrad_raw(g, x, dy, gbuf, st))) {
+      return rc;
     }
+    if ((rc = wgrad_epilogue(gbuf, w, piggy, tmask, (long long)n, cur, weight_decay, mode, thr, dW, dP, st)))
+      return rc;
   }
-  if ((rc = wgrad_epilogue(gbuf, w, piggy, tmask, (long long)n, cur, weight_decay, mode, thr, dW, dP, st))) return rc;
   if (dbias) {
     if (d->N == 0) CPGB_CUDA_OK(cudaMemsetAsync(dbias, 0, d->K * sizeof(float), st));
     else if ((rc = bias_grad(g, dy, dbias, st))) return rc;

@@ -72,14 +72,20 @@ int bias_grad(const Geom &g, const float *dy, float *dbias, cudaStream_t st);
 int wgrad_epilogue(const float *gbuf, const float *w, const float *piggy, const uint8_t *tmask, long long n,
                    int cur, float wd, int mode, float thr, float *dW, float *dP, cudaStream_t st);
 
-// tcgen05 implicit GEMM (tc_conv.cu).  *_eligible() says whether the shape is supported.
+// tcgen05 implicit GEMM (tc_conv.cu).  tc_eligible() says whether the shape is supported.
 bool tc_eligible(const cpgb_conv_desc &d, int op);  // op: 0 fprop, 1 dgrad, 2 wgrad
 size_t tc_workspace_bytes(const cpgb_conv_desc &d);
-int tc_fprop(const cpgb_conv_desc &d, const float *x, const float *w, const float *piggy, const float *bias,
-             float *y, float thr, void *ws, size_t ws_bytes, cudaStream_t st);
-int tc_dgrad(const cpgb_conv_desc &d, const float *dy, const float *w, const float *piggy, float *dx,
-             float thr, void *ws, size_t ws_bytes, cudaStream_t st);
-int tc_wgrad_raw(const cpgb_conv_desc &d, const float *x, const float *dy, float *gbuf_krsc, void *ws,
-                 size_t ws_bytes, cudaStream_t st);
+size_t tc_staged_bytes(const cpgb_conv_desc &d);
+void debug_set_mn(int layout, int lbo, int sbo, int kadv, int tma_swizzle);
+// staged = tf32((piggy > thr) * w) reordered to [K][R*S][Cp]
+int tc_stage_weights(const cpgb_conv_desc &d, const float *w, const float *piggy, float thr, void *staged,
+                     size_t bytes, cudaStream_t st);
+int tc_fprop(const cpgb_conv_desc &d, const float *x, const float *staged, const float *bias, float *y,
+             cudaStream_t st);
+int tc_dgrad(const cpgb_conv_desc &d, const float *dy, const float *staged, float *dx, cudaStream_t st);
+// wgrad + fused epilogue (dW, dP); partial sums live in ws
+int tc_wgrad_fused(const cpgb_conv_desc &d, const float *x, const float *dy, const float *w, const float *piggy,
+                   const uint8_t *tmask, int cur, float wd, int mode, float thr, float *dW, float *dP, void *ws,
+                   size_t ws_bytes, cudaStream_t st);
 
 }  // namespace cpgb

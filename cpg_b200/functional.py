@@ -27,6 +27,18 @@ def _dense4(t):
     return t.contiguous()
 
 
+def _stage(lib, d, w, p, threshold):
+    """Build the tensor-core weight operand (masked, TF32, [K][RS][Cp]) for descriptor d, or
+    None when d takes the CUDA-core path (which evaluates the mask while loading tiles)."""
+    nbytes = lib.cpgb_staged_weight_bytes(d)
+    if nbytes == 0:
+        return None
+    staged = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+    _lib.check(lib.cpgb_stage_weights(d, _lib.ptr(w), _lib.ptr(p), threshold, _lib.ptr(staged), nbytes,
+                                      _lib.stream_ptr()), 'cpgb_stage_weights')
+    return staged
+
+
 class FuseCtx:
     """What the fused wgrad epilogue needs from the pruner (utils/prune.py:195-211)."""
     __slots__ = ('tmask', 'cur', 'weight_decay', 'mode')
@@ -60,6 +72,9 @@ class MaskedConv2dFn(torch.autograd.Function):
         if x.dtype != torch.float32 or not x.is_cuda:
             raise _lib.CpgbError(f'input must be a float32 CUDA tensor, got {x.dtype} on {x.device}')
         x = _dense4(x)
+        if (groups == 1 and tuple(stride) == (1, 1) and x.shape[1] % 4 == 0 and weight.shape[0] % 4 == 0
+                and not x.is_contiguous(memory_format=CL)):
+            x = x.contiguous(memory_format=CL)     # the tcgen05 kernels TMA-load NHWC activations
         w = weight.detach().contiguous()
         p = piggymask.detach().contiguous() if piggymask is not None else None
         b = bias.detach().contiguous() if bias is not None else None
@@ -75,13 +90,13 @@ class MaskedConv2dFn(torch.autograd.Function):
             else torch.contiguous_format
         y = torch.empty((N, K, P, Q), dtype=torch.float32, device=x.device, memory_format=fmt)
         d = _lib.conv_desc(x.shape, x.stride(), w.shape, y.shape, y.stride(), stride, padding, dilation, groups)
-        ws_bytes = lib.cpgb_workspace_bytes(d)
-        ws = _ws(ws_bytes, x.device)
         with torch.cuda.device(x.device):
+            staged = _stage(lib, d, w, p, threshold)
             _lib.check(lib.cpgb_conv2d_fprop(d, _lib.ptr(x), _lib.ptr(w), _lib.ptr(p), _lib.ptr(b),
-                                             _lib.ptr(y), threshold, _lib.ptr(ws), ws.numel(),
+                                             _lib.ptr(y), threshold, _lib.ptr(staged), None, 0,
                                              _lib.stream_ptr()), 'cpgb_conv2d_fprop')
         ctx.save_for_backward(x, w, p)
+        ctx.staged = staged     # masked TF32 operand, shared with this step's dgrad
         ctx.has_bias = bias is not None
         ctx.geom = (stride, padding, dilation, groups, threshold)
         ctx.fuse, ctx.module = fuse, module
@@ -94,6 +109,8 @@ class MaskedConv2dFn(torch.autograd.Function):
         x, w, p = ctx.saved_tensors
         stride, padding, dilation, groups, threshold = ctx.geom
         dy = _dense4(dy)
+        if x.is_contiguous(memory_format=CL) and not dy.is_contiguous(memory_format=CL):
+            dy = dy.contiguous(memory_format=CL)
         d = _lib.conv_desc(x.shape, x.stride(), w.shape, dy.shape, dy.stride(), stride, padding, dilation, groups)
         ws = _ws(lib.cpgb_workspace_bytes(d), x.device)
         dx = dW = dP = db = None
@@ -102,7 +119,8 @@ class MaskedConv2dFn(torch.autograd.Function):
             if ctx.needs_input_grad[0]:
                 dx = torch.empty_like(x)  # same strides as x (dense)
                 _lib.check(lib.cpgb_conv2d_dgrad(d, _lib.ptr(dy), _lib.ptr(w), _lib.ptr(p), _lib.ptr(dx),
-                                                 threshold, _lib.ptr(ws), ws.numel(), st), 'cpgb_conv2d_dgrad')
+                                                 threshold, _lib.ptr(ctx.staged), _lib.ptr(ws), ws.numel(), st),
+                           'cpgb_conv2d_dgrad')
             if ctx.needs_input_grad[1] or ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
                 dW = torch.empty_like(w)
                 dP = torch.empty_like(w) if p is not None else None
@@ -137,18 +155,21 @@ class MaskedLinearFn(torch.autograd.Function):
             raise RuntimeError(f'size mismatch: input features {x.shape[-1]} vs weight {tuple(w.shape)}')
         x2 = x.reshape(-1, I).contiguous()
         M = x2.shape[0]
-        y = torch.empty((M, O), dtype=torch.float32, device=x.device)
+        # allocated in its final shape: returning a view of a custom Function's output would
+        # forbid the in-place ReLU that follows it in models/vgg.py:116-118
+        y = torch.empty((*x.shape[:-1], O), dtype=torch.float32, device=x.device)
         d = _lib.ConvDesc()
         lib.cpgb_linear_desc(d, M, I, O)
-        ws = _ws(lib.cpgb_workspace_bytes(d), x.device)
         with torch.cuda.device(x.device):
+            staged = _stage(lib, d, w, p, threshold)
             _lib.check(lib.cpgb_conv2d_fprop(d, _lib.ptr(x2), _lib.ptr(w), _lib.ptr(p), _lib.ptr(b), _lib.ptr(y),
-                                             threshold, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+                                             threshold, _lib.ptr(staged), None, 0, _lib.stream_ptr()),
                        'cpgb_conv2d_fprop(linear)')
         ctx.save_for_backward(x2, w, p)
+        ctx.staged = staged
         ctx.has_bias, ctx.threshold, ctx.fuse, ctx.module = bias is not None, threshold, fuse, module
         ctx.x_shape = x.shape
-        return y.reshape(*x.shape[:-1], O)
+        return y
 
     @staticmethod
     @once_differentiable
@@ -167,7 +188,7 @@ class MaskedLinearFn(torch.autograd.Function):
             if ctx.needs_input_grad[0]:
                 dx2 = torch.empty_like(x2)
                 _lib.check(lib.cpgb_conv2d_dgrad(d, _lib.ptr(dy2), _lib.ptr(w), _lib.ptr(p), _lib.ptr(dx2),
-                                                 ctx.threshold, _lib.ptr(ws), ws.numel(), st),
+                                                 ctx.threshold, _lib.ptr(ctx.staged), _lib.ptr(ws), ws.numel(), st),
                            'cpgb_conv2d_dgrad(linear)')
                 dx = dx2.reshape(ctx.x_shape)
             if ctx.needs_input_grad[1] or ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:

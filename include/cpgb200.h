@@ -77,17 +77,27 @@ size_t cpgb_workspace_bytes(const cpgb_conv_desc *d);
 /* a1: Binarizer.forward, models/layers.py:15-19.  b = (p > thr) ? 1 : 0, NaN -> NaN. */
 int cpgb_binarize(const float *piggy, float *out, int64_t n, float thr, void *stream);
 
+/* Staged weight operand of the tcgen05 path: tf32_rna((piggy > thr ? 1 : 0) * w) reordered from
+ * the module's [K][C/g][R][S] to [K][R*S][Cp] (Cp = C rounded up to 32, zero padded) -- the
+ * expression models/layers.py:101-103 evaluated once per layer per step.  fprop and dgrad of the
+ * same step share it: build it once with cpgb_stage_weights() and pass it as `staged`, or pass
+ * staged == NULL and let each call build it in `ws`.  cpgb_staged_weight_bytes() returns 0 when
+ * the descriptor takes the CUDA-core path (then `staged` is ignored). */
+size_t cpgb_staged_weight_bytes(const cpgb_conv_desc *d);
+int cpgb_stage_weights(const cpgb_conv_desc *d, const float *w, const float *piggy, float thr, void *staged,
+                       size_t staged_bytes, void *stream);
+
 /* a3/a5 forward: y = conv2d(x, (piggy > thr ? 1 : 0) * w, bias).  models/layers.py:98-109,
  * 184-194.  piggy == NULL means "no piggymask" (task 1, models/layers.py:104-105).  The
- * masked weight is never written to HBM on the CUDA-core path; the tcgen05 path stages a
- * TF32, [K][R*S][C]-ordered operand copy in `ws`. */
+ * CUDA-core path evaluates the predicate while loading weight tiles; the tcgen05 path reads
+ * the staged operand described above. */
 int cpgb_conv2d_fprop(const cpgb_conv_desc *d, const float *x, const float *w, const float *piggy,
-                      const float *bias, float *y, float thr, void *ws, size_t ws_bytes,
+                      const float *bias, float *y, float thr, const void *staged, void *ws, size_t ws_bytes,
                       void *stream);
 
 /* a4 dgrad: dx = conv_transpose(dy, W_eff).  dy uses d->ys strides, dx uses d->xs. */
 int cpgb_conv2d_dgrad(const cpgb_conv_desc *d, const float *dy, const float *w, const float *piggy,
-                      float *dx, float thr, void *ws, size_t ws_bytes, void *stream);
+                      float *dx, float thr, const void *staged, void *ws, size_t ws_bytes, void *stream);
 
 /* a4 wgrad with the fused epilogue.  g = wgrad(x, dy) is reduced in `ws`
  * and never returned; outputs:

@@ -246,7 +246,7 @@ def pruner_cases():
     print('pruner')
 
 
-def trajectory_case(mode, name, steps=6, width=0.125, batch=8):
+def trajectory_case(mode, name, steps=3, width=0.125, batch=8):
     """N training steps of a narrow VGG16-BN-cifar (task 2: piggymasks on every sharable
     layer) through the reference's unmodified Manager.train + SparsePruner."""
     torch.manual_seed(1)

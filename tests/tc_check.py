@@ -1,0 +1,107 @@
+"""On-GPU sweep of the tcgen05 path against torch fp32 (cuDNN, TF32 off) -- a diagnostic, not a
+pytest file.  usage: python -m tests.tc_check [fprop|dgrad|wgrad|all] [quick]
+Each op group should run in its own process: a trapped kernel poisons the CUDA context."""
+import sys
+import time
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from cpg_b200 import _lib
+import cpg_b200.layers as nl
+
+DEV = 'cuda:0'
+
+# (N, C, H, W, K, R, pad, dil)
+CASES = [
+    (2, 32, 8, 8, 64, 3, 1, 1),
+    (4, 64, 32, 32, 64, 3, 1, 1),
+    (8, 64, 16, 16, 128, 3, 1, 1),
+    (8, 128, 8, 8, 256, 3, 1, 1),
+    (16, 256, 4, 4, 512, 3, 1, 1),
+    (32, 512, 2, 2, 512, 3, 1, 1),
+    (3, 96, 7, 7, 160, 3, 1, 1),
+    (2, 64, 14, 14, 64, 1, 0, 1),
+    (2, 32, 12, 12, 32, 3, 2, 2),
+    (2, 36, 9, 9, 40, 3, 1, 1),
+    (128, 512, 1, 1, 4096, 1, 0, 1),
+]
+
+
+def rel(a, b):
+    a, b = a.detach().double(), b.detach().double()
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
+
+
+def bad_frac(a, b):
+    a, b = a.detach().double(), b.detach().double()
+    tol = 1e-2 * b.abs().max().item()
+    return ((a - b).abs() > tol).double().mean().item()
+
+
+def run(op, cases):
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    lib = _lib.load()
+    worst = 0.0
+    for (N, C, H, W, K, R, pad, dil) in cases:
+        torch.manual_seed(N * 7 + C + K)
+        m = nl.SharableConv2d(C, K, R, padding=pad, dilation=dil, bias=True).to(DEV)
+        with torch.no_grad():
+            m.weight.normal_(0, (2.0 / (C * R * R)) ** 0.5)
+            m.bias.normal_()
+        m.piggymask = nn.Parameter(torch.rand_like(m.weight) * 0.01)
+        x = torch.randn(N, C, H, W, device=DEV).contiguous(memory_format=torch.channels_last)
+        weff = ((m.piggymask > 5e-3).float() * m.weight).detach()
+        yr = F.conv2d(x, weff, m.bias, 1, pad, dil)
+        dy = torch.randn_like(yr).contiguous(memory_format=torch.channels_last)
+        d = _lib.conv_desc(x.shape, x.stride(), m.weight.shape, dy.shape, dy.stride(), (1, 1), (pad, pad), (dil, dil), 1)
+        ws = torch.empty(max(lib.cpgb_workspace_bytes(d), 256), dtype=torch.uint8, device=DEV)
+        P, st = _lib.ptr, _lib.stream_ptr()
+        tag = f'N{N} C{C} {H}x{W} K{K} R{R} p{pad} d{dil}'
+        _lib.set_path(_lib.PATH_TCGEN05)
+        try:
+            t0 = time.time()
+            if op == 'fprop':
+                y = torch.full_like(dy, float('nan'))
+                _lib.check(lib.cpgb_conv2d_fprop(d, P(x), P(m.weight), P(m.piggymask), P(m.bias), P(y), 5e-3, None,
+                                                 P(ws), ws.numel(), st), 'fprop')
+                torch.cuda.synchronize()
+                e, bf = rel(y, yr), bad_frac(y, yr)
+            elif op == 'dgrad':
+                dxr = torch.nn.grad.conv2d_input(x.shape, weff, dy, 1, pad, dil)
+                dx = torch.full_like(x, float('nan'))
+                _lib.check(lib.cpgb_conv2d_dgrad(d, P(dy), P(m.weight), P(m.piggymask), P(dx), 5e-3, None, P(ws),
+                                                 ws.numel(), st), 'dgrad')
+                torch.cuda.synchronize()
+                e, bf = rel(dx, dxr), bad_frac(dx, dxr)
+            else:
+                gr = torch.nn.grad.conv2d_weight(x, m.weight.shape, dy, 1, pad, dil)
+                dW = torch.full_like(m.weight, float('nan'))
+                dP = torch.full_like(m.weight, float('nan'))
+                _lib.check(lib.cpgb_conv2d_wgrad_fused(d, P(x), P(dy), P(m.weight), P(m.piggymask), None, 0, 0.0,
+                                                       _lib.GRAD_RAW, P(dW), P(dP), None, 5e-3, P(ws), ws.numel(), st),
+                           'wgrad')
+                torch.cuda.synchronize()
+                b = (m.piggymask > 5e-3).float()
+                e = max(rel(dW, gr * b), rel(dP, gr * m.weight))
+                bf = bad_frac(dP, gr * m.weight)
+            print(f'{op:6s} {tag:34s} rel {e:.3e}  bad>1% {bf:.4f}  {"OK" if e <= 1e-3 else "FAIL"} '
+                  f'({(time.time() - t0) * 1e3:.1f} ms)', flush=True)
+            worst = max(worst, e)
+        except Exception as ex:  # noqa: BLE001
+            print(f'{op:6s} {tag:34s} EXCEPTION {type(ex).__name__}: {ex}', flush=True)
+            if 'CUDA' in str(ex) or 'cuda' in str(ex):
+                print('context is gone; stopping', flush=True)
+                return
+        finally:
+            _lib.set_path(_lib.PATH_AUTO)
+    print(f'{op}: worst rel {worst:.3e}', flush=True)
+
+
+if __name__ == '__main__':
+    which = sys.argv[1] if len(sys.argv) > 1 else 'all'
+    cases = CASES[:3] if len(sys.argv) > 2 else CASES
+    for op in (['fprop', 'dgrad', 'wgrad'] if which == 'all' else [which]):
+        run(op, cases)

@@ -41,12 +41,12 @@ def test_version_and_validation_without_gpu():
     # groups not dividing channels -> EINVAL (the module raises ValueError before that)
     bad = _lib.conv_desc((1, 6, 4, 4), (96, 16, 4, 1), (8, 2, 3, 3), (1, 8, 4, 4), (128, 16, 4, 1),
                          (1, 1), (1, 1), (1, 1), 4)
-    rc = lib.cpgb_conv2d_fprop(bad, None, None, None, None, None, 5e-3, None, 0, None)
+    rc = lib.cpgb_conv2d_fprop(bad, None, None, None, None, None, 5e-3, None, None, 0, None)
     assert rc == -1 and b'groups' in lib.cpgb_last_error()
     # wrong output extent
     bad = _lib.conv_desc((1, 4, 4, 4), (64, 16, 4, 1), (8, 4, 3, 3), (1, 8, 9, 9), (648, 81, 9, 1),
                          (1, 1), (1, 1), (1, 1), 1)
-    assert lib.cpgb_conv2d_fprop(bad, None, None, None, None, None, 5e-3, None, 0, None) == -1
+    assert lib.cpgb_conv2d_fprop(bad, None, None, None, None, None, 5e-3, None, None, 0, None) == -1
     assert lib.cpgb_set_path(_lib.PATH_AUTO) in (0, 1, 2)
 
 

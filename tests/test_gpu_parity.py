@@ -279,24 +279,54 @@ def test_prune_select_vs_oracle_large(n):
         assert np.array_equal(tg.cpu().numpy(), tt.numpy())
 
 
+@pytest.mark.parametrize('path', [_lib.PATH_SIMT])
 @pytest.mark.parametrize('mode', ['prune', 'finetune'])
-def test_trajectory_vs_reference_golden(golden, mode):
-    """6 training steps of a narrow VGG16-BN (task-2 regime) through the product layers + product
-    pruner, against the reference's own Manager.train trajectory (tests/golden/traj_*.npz)."""
+def test_trajectory_vs_reference_golden(golden, mode, path):
+    """3 training steps (one prune event in 'prune' mode) of a narrow VGG16-BN (task-2 regime)
+    through the product layers + product pruner, against the reference's own Manager.train
+    trajectory (tests/golden/traj_*.npz).  The trajectory is kept short because this tiny net
+    (batch 8, 8..64 channels) amplifies rounding differences chaotically (ReLU / max-pool
+    switches): lock-stepped against the oracle the fp32 CUDA-core path is at 2e-5 after three
+    steps and at 1e-1 after six.  The fp32 path is held to 1e-3 here; the TF32 tensor-core path
+    is checked per step in test_one_step_tc_vs_fp32_path (it drifts by 2e-1 over these three
+    steps for the same reason)."""
     from tests.trajectory import run_trajectory
     g = golden('traj_' + mode)
+    _lib.set_path(path)
+    tol = 1e-3 if path == _lib.PATH_SIMT else 5e-2
     model, masks = run_trajectory(nl.SharableConv2d, nl.SharableLinear, mode, device=DEV, pruner_factory='product')
     first = [m for _, m in model.named_modules() if isinstance(m, nl.SharableConv2d)][0]
-    assert rel(first.weight, torch.from_numpy(g['w_first'])) <= 5e-3
+    assert rel(first.weight, torch.from_numpy(g['w_first'])) <= tol
     worst = 0.0
     for n, p in model.named_parameters():
         a = p.detach().double().cpu().numpy()
         ref = g['sum_module.' + n]
         worst = max(worst, abs(np.abs(a).sum() - ref[1]) / max(ref[1], 1e-12))
-    assert worst <= 5e-3, worst
+    assert worst <= tol, worst
     for n in masks:
         z, zr = int((masks[n].numpy() == 0).sum()), int(g['maskzeros_module.' + n])
         assert abs(z - zr) <= max(2, 0.01 * zr), (n, z, zr)
+        if path == _lib.PATH_SIMT:
+            assert zlib.crc32(masks[n].numpy().tobytes()) == int(g['maskcrc_module.' + n]), n
+
+
+def test_one_step_tc_vs_fp32_path():
+    """One fwd+bwd of the narrow VGG16-BN from identical state: every parameter gradient produced
+    by the TF32 tensor-core path (AUTO) against the fp32 CUDA-core path.  Per-layer TF32 error is
+    ~3e-4 (test_conv_golden); through 15 layers with batch-8 BatchNorm it compounds, bar 2e-2."""
+    from tests.trajectory import build
+    grads = {}
+    for path in (_lib.PATH_SIMT, _lib.PATH_AUTO):
+        _lib.set_path(path)
+        model, masks, loader = build(nl.SharableConv2d, nl.SharableLinear, DEV, width=0.5, batch=16)
+        model.train()
+        data, target = loader[0]
+        loss = nn.CrossEntropyLoss()(model(data.to(DEV)), target.to(DEV))
+        loss.backward()
+        grads[path] = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+        grads[path]['__loss__'] = loss.detach()
+    worst = max(rel(grads[_lib.PATH_AUTO][n], grads[_lib.PATH_SIMT][n]) for n in grads[_lib.PATH_SIMT])
+    assert worst <= 2e-2, worst
 
 
 VGG_SHAPES = [  # (C, K, HW) of the VGG16-cifar sharable convs (SURVEY appendix A1), batch 128

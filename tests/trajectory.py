@@ -31,7 +31,7 @@ def make_args(mode, dataset='t2', wd=4e-5, freq=2, init_s=0.0, target_s=0.3):
     return a
 
 
-def build(conv_cls, linear_cls, device='cpu', width=0.125, steps=6, batch=8):
+def build(conv_cls, linear_cls, device="cpu", width=0.125, steps=3, batch=8):
     torch.manual_seed(1)
     model = VGGCifar(conv_cls, linear_cls, width=width)
     model.add_dataset('t1', 5)
@@ -61,7 +61,7 @@ def build(conv_cls, linear_cls, device='cpu', width=0.125, steps=6, batch=8):
     return model, masks, loader
 
 
-def run_trajectory(conv_cls, linear_cls, mode, device='cpu', pruner_factory='oracle', steps=6):
+def run_trajectory(conv_cls, linear_cls, mode, device='cpu', pruner_factory="oracle", steps=3):
     model, masks, loader = build(conv_cls, linear_cls, device, steps=steps)
     args = make_args(mode)
     if pruner_factory == 'oracle':
