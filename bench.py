@@ -325,6 +325,9 @@ def kernel_table(device, regime_has_piggy, iters=5):
         ts = []
         for i in range(iters + 2):
             flush.zero_()
+            # a ~100 us device-side spin lets the host enqueue (tensor-map encode + launch) ahead of
+            # the GPU, so the events bracket device time only
+            torch.cuda._sleep(200000)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); fn(); e1.record()
             torch.cuda.synchronize()

@@ -115,17 +115,25 @@ int cpgb_stage_weights(const cpgb_conv_desc *d, const float *w, const float *pig
   return tc_stage_weights(*d, w, piggy, thr, staged, staged_bytes, (cudaStream_t)stream);
 }
 
-// staged operand for a tensor-core call: the caller's, or built into ws
-static int staged_operand(const cpgb_conv_desc *d, const float *w, const float *piggy, float thr, const void *staged,
-                          void *ws, size_t ws_bytes, cudaStream_t st, const float **out) {
-  if (staged) { *out = reinterpret_cast<const float *>(staged); return CPGB_OK; }
-  if (!ws || ws_bytes < tc_staged_bytes(*d)) {
-    set_error("workspace %zu < %zu (staged weights)", ws_bytes, tc_staged_bytes(*d));
-    return CPGB_EWORKSPACE;
+// Operands of a tensor-core call out of (staged, ws): the staged weights are the caller's or are
+// built at the front of ws; the split-K scratch is what remains of ws.
+static int tc_operands(const cpgb_conv_desc *d, const float *w, const float *piggy, float thr, const void *staged,
+                       void *ws, size_t ws_bytes, cudaStream_t st, const float **wt, void **part, size_t *part_bytes) {
+  char *base = reinterpret_cast<char *>(ws);
+  size_t off = 0;
+  if (staged) {
+    *wt = reinterpret_cast<const float *>(staged);
+  } else {
+    const size_t sb = tc_staged_bytes(*d);
+    if (!ws || ws_bytes < sb) { set_error("workspace %zu < %zu (staged weights)", ws_bytes, sb); return CPGB_EWORKSPACE; }
+    int rc = tc_stage_weights(*d, w, piggy, thr, ws, ws_bytes, st);
+    if (rc) return rc;
+    *wt = reinterpret_cast<const float *>(ws);
+    off = sb;
   }
-  int rc = tc_stage_weights(*d, w, piggy, thr, ws, ws_bytes, st);
-  *out = reinterpret_cast<const float *>(ws);
-  return rc;
+  *part = ws && ws_bytes > off ? base + off : nullptr;
+  *part_bytes = ws && ws_bytes > off ? ws_bytes - off : 0;
+  return CPGB_OK;
 }
 
 int cpgb_conv2d_fprop(const cpgb_conv_desc *d, const float *x, const float *w, const float *piggy,
@@ -138,9 +146,10 @@ int cpgb_conv2d_fprop(const cpgb_conv_desc *d, const float *x, const float *w, c
   bool use_tc;
   if ((rc = pick_tc(d, 0, &use_tc))) return rc;
   if (use_tc) {
-    const float *wt;
-    if ((rc = staged_operand(d, w, piggy, thr, staged, ws, ws_bytes, (cudaStream_t)stream, &wt))) return rc;
-    return tc_fprop(*d, x, wt, bias, y, (cudaStream_t)stream);
+    const float *wt; void *part; size_t part_bytes;
+    if ((rc = tc_operands(d, w, piggy, thr, staged, ws, ws_bytes, (cudaStream_t)stream, &wt, &part, &part_bytes)))
+      return rc;
+    return tc_fprop(*d, x, wt, bias, y, part, part_bytes, (cudaStream_t)stream);
   }
   return simt_fprop(make_geom(*d), x, w, piggy, bias, y, thr, (cudaStream_t)stream);
 }
@@ -154,9 +163,10 @@ int cpgb_conv2d_dgrad(const cpgb_conv_desc *d, const float *dy, const float *w, 
   bool use_tc;
   if ((rc = pick_tc(d, 1, &use_tc))) return rc;
   if (use_tc) {
-    const float *wt;
-    if ((rc = staged_operand(d, w, piggy, thr, staged, ws, ws_bytes, (cudaStream_t)stream, &wt))) return rc;
-    return tc_dgrad(*d, dy, wt, dx, (cudaStream_t)stream);
+    const float *wt; void *part; size_t part_bytes;
+    if ((rc = tc_operands(d, w, piggy, thr, staged, ws, ws_bytes, (cudaStream_t)stream, &wt, &part, &part_bytes)))
+      return rc;
+    return tc_dgrad(*d, dy, wt, dx, part, part_bytes, (cudaStream_t)stream);
   }
   return simt_dgrad(make_geom(*d), dy, w, piggy, dx, thr, (cudaStream_t)stream);
 }

@@ -80,9 +80,11 @@ void debug_set_mn(int layout, int lbo, int sbo, int kadv, int tma_swizzle);
 // staged = tf32((piggy > thr) * w) reordered to [K][R*S][Cp]
 int tc_stage_weights(const cpgb_conv_desc &d, const float *w, const float *piggy, float thr, void *staged,
                      size_t bytes, cudaStream_t st);
-int tc_fprop(const cpgb_conv_desc &d, const float *x, const float *staged, const float *bias, float *y,
+// part: scratch for split-K partial sums (tc_workspace_bytes covers staged operand + partials)
+int tc_fprop(const cpgb_conv_desc &d, const float *x, const float *staged, const float *bias, float *y, void *part,
+             size_t part_bytes, cudaStream_t st);
+int tc_dgrad(const cpgb_conv_desc &d, const float *dy, const float *staged, float *dx, void *part, size_t part_bytes,
              cudaStream_t st);
-int tc_dgrad(const cpgb_conv_desc &d, const float *dy, const float *staged, float *dx, cudaStream_t st);
 // wgrad + fused epilogue (dW, dP); partial sums live in ws
 int tc_wgrad_fused(const cpgb_conv_desc &d, const float *x, const float *dy, const float *w, const float *piggy,
                    const uint8_t *tmask, int cur, float wd, int mode, float thr, float *dW, float *dP, void *ws,

@@ -15,6 +15,7 @@
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
 // warps 2..5 = epilogue (tcgen05.ld -> registers -> global).  smem ring of NSTAGE stages, each
 // guarded by a full (TMA -> MMA) and an empty (tcgen05.commit -> TMA) mbarrier.
+#include <algorithm>
 #include <mutex>
 
 #include "common.cuh"
@@ -118,6 +119,78 @@ stage_weights_kernel(const float *__restrict__ w, const float *__restrict__ pigg
   }
 }
 
+// RS == 1 and C == Cp: same element order, 16 bytes per thread
+__global__ void __launch_bounds__(256)
+stage_weights_flat_kernel(const float4 *__restrict__ w, const float4 *__restrict__ piggy, float4 *__restrict__ wt,
+                          long long n4, float thr) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 v = __ldg(w + i);
+    if (piggy) {
+      const float4 pv = __ldg(piggy + i);
+      v.x *= binarize_val(pv.x, thr); v.y *= binarize_val(pv.y, thr);
+      v.z *= binarize_val(pv.z, thr); v.w *= binarize_val(pv.w, thr);
+    }
+    wt[i] = make_float4(to_tf32_rna(v.x), to_tf32_rna(v.y), to_tf32_rna(v.z), to_tf32_rna(v.w));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// TF32 truncation debias.  tcgen05.mma kind::tf32 reads fp32 operands from shared memory and drops
+// the low 13 mantissa bits (truncation, not rounding): every truncated operand shrinks the product
+// by E[2^-11 / mantissa] = 2^-11 * 0.7213 = 3.52e-4 on average (log-uniform mantissas).  Measured on
+// B200 against fp32 cuDNN: <tc, ref>/<ref, ref> - 1 = -3.54e-4 for fprop/dgrad (activations
+// truncated, staged weights pre-rounded to nearest) and -7.07e-4 for wgrad (both operands raw).
+// The epilogues multiply the accumulator by the reciprocal, which turns a systematic 3.5e-4 / 7e-4
+// relative error into a zero-mean one of ~1e-4 (the parity bar is 1e-3).
+// ------------------------------------------------------------------------------------------
+constexpr float DEBIAS_ONE = 1.0f / (1.0f - 3.54e-4f);
+constexpr float DEBIAS_TWO = 1.0f / (1.0f - 7.07e-4f);
+
+// ------------------------------------------------------------------------------------------
+// shared pieces of the GEMM kernels
+// ------------------------------------------------------------------------------------------
+// tail of the dynamic smem, after the pipeline stages
+struct SmemTail {
+  uint64_t full[8];
+  uint64_t empty[8];
+  uint64_t acc_full;
+  uint32_t tmem_slot;
+  uint32_t pad;
+  float *rowptr[4][32];     // per epilogue warp: destination row pointers (nullptr = skip)
+};
+constexpr int TAIL_BYTES = 2048;
+static_assert(sizeof(SmemTail) <= TAIL_BYTES, "tail");
+
+// Epilogue helper.  The warp owns TMEM lanes [32*quad, +32) (one accumulator row per thread).
+// NC columns starting at TMEM column `col` are moved to registers, transposed through the warp's
+// smem scratch `ts` ([32][NC + 4] floats, conflict-free for 16-byte accesses) and handed to
+// f(row, c4, value) with the lanes of a warp covering consecutive 16-byte groups of ONE row, so
+// that global accesses made by f are fully coalesced.
+template <int NC, class F>
+__device__ __forceinline__ void epilogue_rows(uint32_t tmem_base, int quad, int col, float *ts, int lane, F f) {
+  constexpr int LD = NC + 4;
+#pragma unroll 1
+  for (int c = 0; c < NC; c += 32) {
+    float v[32];
+    tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + col + c, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; j += 4)
+      *reinterpret_cast<float4 *>(ts + lane * LD + c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+  }
+  __syncwarp();
+  constexpr int LPR = NC / 4;        // lanes per row
+  constexpr int RPP = 32 / LPR;      // rows per pass
+  const int rsub = lane / LPR, c4 = (lane % LPR) * 4;
+#pragma unroll 4
+  for (int r0 = 0; r0 < 32; r0 += RPP) {
+    const int rr = r0 + rsub;
+    f(rr, c4, *reinterpret_cast<const float4 *>(ts + rr * LD + c4));
+  }
+  __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------
 // fprop / dgrad kernel
 // ------------------------------------------------------------------------------------------
@@ -130,10 +203,12 @@ struct ConvGemmParams {
   int step_h, step_w;
   int kblocks;             // 32-wide reduction blocks per tap
   int ncols;               // valid output channels
+  int iters_per_split;     // split-K over the (tap, k-block) loop; blockIdx.z = split
   int mn_layout, mn_lbo, mn_sbo, mn_kadv;   // MN-major operand descriptor fields
   long long o_sn, o_sh, o_sw;
-  float *out;
-  const float *bias;
+  long long split_stride;  // elements between the partial outputs of consecutive splits
+  float *out;              // y / dx, or the partial-sum buffer when split
+  const float *bias;       // only when not split
 };
 
 constexpr int A_TILE_BYTES = 128 * 128;  // 128 pixels x 32 fp32
@@ -142,10 +217,12 @@ template <int BN, bool B_MN>
 struct ConvGemmCfg {
   static constexpr int B_TILE_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-  // two CTAs per SM when the tile is narrow (hides prologue/epilogue), one otherwise
-  static constexpr int NSTAGE = BN <= 128 ? 3 : 4;
-  static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  // narrow tiles: two CTAs per SM (one CTA's epilogue overlaps the other's main loop)
+  static constexpr int NSTAGE = BN == 256 ? 4 : BN == 128 ? 3 : 4;
+  static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align slack*/ + TAIL_BYTES;
   static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr int NC = BN < 128 ? BN : 128;       // columns per epilogue pass
+  static_assert(4 * 32 * (NC + 4) * 4 <= NSTAGE * STAGE_BYTES, "epilogue scratch must fit in the stage ring");
 };
 
 template <int BN, bool B_MN>
@@ -155,10 +232,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   using Cfg = ConvGemmCfg<BN, B_MN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t *full = reinterpret_cast<uint64_t *>(smem + Cfg::NSTAGE * Cfg::STAGE_BYTES);
-  uint64_t *empty = full + Cfg::NSTAGE;
-  uint64_t *acc_full = empty + Cfg::NSTAGE;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_full + 1);
+  SmemTail *tail = reinterpret_cast<SmemTail *>(smem + Cfg::NSTAGE * Cfg::STAGE_BYTES);
+  uint64_t *full = tail->full, *empty = tail->empty, *acc_full = &tail->acc_full;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // tile coordinates
@@ -168,7 +243,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int tni = tile;
   const int q0 = tqi << p.lq, p0 = tpi << p.lp, n0 = tni << (7 - p.lq - p.lp);
   const int col0 = blockIdx.y * BN;
-  const int iters = p.taps * p.kblocks;
+  const int it_beg = blockIdx.z * p.iters_per_split;
+  const int it_end = min(p.taps * p.kblocks, it_beg + p.iters_per_split);
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmA);
@@ -178,18 +254,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_alloc(&tail->tmem_slot, Cfg::TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = tail->tmem_slot;
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int it = 0; it < iters; ++it) {
+      for (int it = it_beg; it < it_end; ++it) {
         const int t = it / p.kblocks, kb = it - t * p.kblocks;
         const int r = t / p.S, s = t - r * p.S;
         mbar_wait(empty + stage, phase ^ 1);
@@ -206,7 +282,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_tf32(128, BN, false, B_MN);
       int stage = 0; uint32_t phase = 0;
-      for (int it = 0; it < iters; ++it) {
+      for (int it = it_beg; it < it_end; ++it) {
         mbar_wait(full + stage, phase);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -216,7 +292,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint64_t ad = make_smem_desc(sa + ks * 32, 16, 1024);
           const uint64_t bd = B_MN ? make_smem_desc(sb + ks * p.mn_kadv, p.mn_lbo, p.mn_sbo, p.mn_layout)
                                    : make_smem_desc(sb + ks * 32, 16, 1024);
-          mma_tf32_ss(tmem_base, ad, bd, idesc, (it | ks) != 0);
+          mma_tf32_ss(tmem_base, ad, bd, idesc, (it > it_beg) | (ks != 0));
         }
         mma_commit(empty + stage);
         if (++stage == Cfg::NSTAGE) { stage = 0; phase ^= 1; }
@@ -224,7 +300,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mma_commit(acc_full);
     }
   } else {
-    // epilogue: warp w reads TMEM lanes [32*(w%4), +32)
+    // epilogue: warp w reads TMEM lanes [32*(w%4), +32); row m of the tile = one output pixel
     const int quad = warp & 3;
     const int m = quad * 32 + lane;
     const int qi = m & ((1 << p.lq) - 1);
@@ -232,28 +308,29 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int ni = m >> (p.lq + p.lp);
     const int q = q0 + qi, pp = p0 + pi, n = n0 + ni;
     const bool valid = q < p.Qo && pp < p.Po && n < p.No;
-    float *orow = p.out + n * p.o_sn + pp * p.o_sh + q * p.o_sw + col0;
+    tail->rowptr[quad][lane] =
+        valid ? p.out + blockIdx.z * p.split_stride + n * p.o_sn + pp * p.o_sh + q * p.o_sw + col0 : nullptr;
+    __syncwarp();
     mbar_wait(acc_full, 0);
     tc_fence_after();
+    // the stage ring is idle now (every TMA load landed and every MMA retired): reuse it as scratch
+    float *ts = reinterpret_cast<float *>(smem) + quad * 32 * (Cfg::NC + 4);
+    float *const *rows = tail->rowptr[quad];
+    const float *bias = p.bias;
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      float v[32];
-      tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c, v);
-      tmem_ld_wait();
-      if (valid) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const int col = col0 + c + j;
-          if (col < p.ncols) {   // ncols % 4 == 0
-            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            if (p.bias) {
-              const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + col));
-              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-            }
-            *reinterpret_cast<float4 *>(orow + c + j) = o;
+    for (int h = 0; h < BN; h += Cfg::NC) {
+      epilogue_rows<Cfg::NC>(tmem_base, quad, h, ts, lane, [&](int rr, int c4, float4 v) {
+        float *rp = rows[rr];
+        const int col = col0 + h + c4;
+        if (rp != nullptr && col < p.ncols) {   // ncols % 4 == 0
+          v.x *= DEBIAS_ONE; v.y *= DEBIAS_ONE; v.z *= DEBIAS_ONE; v.w *= DEBIAS_ONE;
+          if (bias) {
+            const float4 b = __ldg(reinterpret_cast<const float4 *>(bias + col));
+            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
           }
+          *reinterpret_cast<float4 *>(rp + h + c4) = v;
         }
-      }
+      });
     }
     tc_fence_before();
   }
@@ -264,9 +341,36 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
+// out[i] = sum_s part[s][i] (+ bias[i % ncols])
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float4 *__restrict__ part, int splits, long long n4, long long split_stride4, int ncols4,
+                     const float4 *__restrict__ bias, float4 *__restrict__ out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 a = __ldg(part + i);
+    for (int s = 1; s < splits; ++s) {
+      const float4 b = __ldg(part + s * split_stride4 + i);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    if (bias) {
+      const float4 b = __ldg(bias + (i % ncols4));
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    out[i] = a;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
-// wgrad kernel: G[split][k][tap][c] partial sums over a range of 32-pixel chunks
+// wgrad kernel: G[k][tap][c] = sum over 32-pixel chunks of dY^T X, both operands MN-major
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void epi_one_tc(float g, float w, float pv, bool has_p, unsigned t, int cur, float wd,
+                                           int mode, float thr, float &dw, float &dp) {
+  float gb = has_p ? g * binarize_val(pv, thr) : g;
+  if (mode == CPGB_GRAD_RAW) { dw = gb; dp = g * w; return; }
+  dw = (t == (unsigned)cur) ? fmaf(wd, w, gb) : 0.f;
+  dp = (mode == CPGB_GRAD_FINETUNE && t != 0u && t < (unsigned)cur) ? g * w : 0.f;
+}
+
 struct WgradParams {
   int cq, cp, cn;          // chunk counts along q, p, n
   int lq, lp;              // log2 chunk extents (n extent = 32 >> (lq + lp))
@@ -277,6 +381,12 @@ struct WgradParams {
   int K, C;
   int mn_layout, mn_lbo, mn_sbo, mn_kadv;
   float *gpart;            // [splits][K][RS][C]
+  // fused epilogue (only RS == 1, one split): SURVEY K6-K8 applied straight from TMEM
+  int fused, cur, mode;
+  float wd, thr;
+  const float *w, *piggy;
+  const uint8_t *tmask;
+  float *dW, *dP;
 };
 
 template <int BN, int TG>
@@ -284,15 +394,17 @@ struct WgradCfg {
   static constexpr int A_BYTES = 128 * 128;            // [4 blocks][32 pixels][32 k]
   static constexpr int B_BYTES = BN * 128;             // [BN/32 blocks][32 pixels][32 c]
   static constexpr int STAGE_BYTES = A_BYTES + TG * B_BYTES;
-  static constexpr int NSTAGE = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
-  static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 + 256;
+  // TG == 1: three stages so that two CTAs share an SM (epilogue of one overlaps the other)
+  static constexpr int NSTAGE = TG == 1 ? 3 : ((200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES);
+  static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 + TAIL_BYTES;
   static constexpr int ACC_COLS = TG * BN;
   static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128
                                    : ACC_COLS <= 256 ? 256 : 512;
+  static_assert(4 * 32 * (BN + 4) * 4 <= NSTAGE * STAGE_BYTES, "epilogue scratch must fit in the stage ring");
 };
 
-// grid: x = ktiles * ctiles, y = filter rows R, z = splits.  One CTA accumulates the TG = S taps of
-// filter row r for a 128(k) x BN(c) tile over its range of pixel chunks.
+// grid: x = ktiles * ctiles, y = tap groups (R groups of TG = S taps, or R*S groups of one tap),
+// z = splits.  One CTA accumulates TG taps for a 128(k) x BN(c) tile over its pixel chunks.
 template <int BN, int TG>
 __global__ void __launch_bounds__(192)
 wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
@@ -300,15 +412,14 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   using Cfg = WgradCfg<BN, TG>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t *full = reinterpret_cast<uint64_t *>(smem + Cfg::NSTAGE * Cfg::STAGE_BYTES);
-  uint64_t *empty = full + Cfg::NSTAGE;
-  uint64_t *acc_full = empty + Cfg::NSTAGE;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_full + 1);
+  SmemTail *tail = reinterpret_cast<SmemTail *>(smem + Cfg::NSTAGE * Cfg::STAGE_BYTES);
+  uint64_t *full = tail->full, *empty = tail->empty, *acc_full = &tail->acc_full;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kt = blockIdx.x / p.ctiles, ct = blockIdx.x - kt * p.ctiles;
   const int k0 = kt * 128, c0 = ct * BN;
-  const int r = blockIdx.y;
+  const int tap0 = blockIdx.y * TG;               // first tap of this CTA
+  const int r = tap0 / p.S, s0 = tap0 - r * p.S;
   const int split = blockIdx.z;
   const int ch_beg = split * p.chunks_per_split;
   const int ch_end = min(p.chunks, ch_beg + p.chunks_per_split);
@@ -322,13 +433,13 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_alloc(&tail->tmem_slot, Cfg::TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = tail->tmem_slot;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -344,8 +455,8 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
         tma_load_5d(sa, &tmDY, full + stage, 0, q0, p0, n0, k0 >> 5);
 #pragma unroll
         for (int s = 0; s < TG; ++s)
-          tma_load_5d(sa + Cfg::A_BYTES + s * Cfg::B_BYTES, &tmX, full + stage, 0, q0 - p.pad_w + s * p.dil_w,
-                      p0 - p.pad_h + r * p.dil_h, n0, c0 >> 5);
+          tma_load_5d(sa + Cfg::A_BYTES + s * Cfg::B_BYTES, &tmX, full + stage, 0,
+                      q0 - p.pad_w + (s0 + s) * p.dil_w, p0 - p.pad_h + r * p.dil_h, n0, c0 >> 5);
         if (++stage == Cfg::NSTAGE) { stage = 0; phase ^= 1; }
       }
     }
@@ -374,24 +485,67 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     }
   } else {
     const int quad = warp & 3;
-    const int k = k0 + quad * 32 + lane;
+    const int kbase = k0 + quad * 32;               // accumulator row rr of this warp = out channel kbase + rr
     mbar_wait(acc_full, 0);
     tc_fence_after();
-#pragma unroll 1
-    for (int s = 0; s < TG; ++s) {
-      float *grow = p.gpart + (((long long)split * p.K + k) * p.RS + (r * p.S + s)) * p.C + c0;
+    float *ts = reinterpret_cast<float *>(smem) + quad * 32 * (BN + 4);
+    if (p.fused) {
+      // linear / 1x1 layer, single split: G has the module's [K][C] layout, finish the gradient here.
+      // Rows are processed in batches with all loads of a batch issued before the first use.
+      const bool has_p = p.piggy != nullptr;
+      constexpr int LD = BN + 4, LPR = BN / 4, RPP = 32 / LPR, BATCH = 8;
 #pragma unroll 1
       for (int c = 0; c < BN; c += 32) {
         float v[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + s * BN + c, v);
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c, v);
         tmem_ld_wait();
-        if (k < p.K) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            if (c0 + c + j < p.C)
-              *reinterpret_cast<float4 *>(grow + c + j) = iters > 0 ? make_float4(v[j], v[j + 1], v[j + 2], v[j + 3])
-                                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4 *>(ts + lane * LD + c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+      __syncwarp();
+      const int rsub = lane / LPR, c4 = (lane % LPR) * 4;
+      const int c = c0 + c4;
+#pragma unroll 1
+      for (int r0 = 0; r0 < 32; r0 += RPP * BATCH) {
+        float4 wv[BATCH], pv[BATCH];
+        uchar4 tv[BATCH];
+        bool ok[BATCH];
+#pragma unroll
+        for (int b = 0; b < BATCH; ++b) {
+          const int k = kbase + r0 + b * RPP + rsub;
+          ok[b] = k < p.K && c < p.C;
+          const long long idx = (long long)k * p.C + c;
+          wv[b] = ok[b] ? __ldg(reinterpret_cast<const float4 *>(p.w + idx)) : make_float4(0, 0, 0, 0);
+          pv[b] = (ok[b] && has_p) ? __ldg(reinterpret_cast<const float4 *>(p.piggy + idx)) : make_float4(0, 0, 0, 0);
+          tv[b] = (ok[b] && p.tmask) ? __ldg(reinterpret_cast<const uchar4 *>(p.tmask + idx)) : make_uchar4(0, 0, 0, 0);
         }
+#pragma unroll
+        for (int b = 0; b < BATCH; ++b) {
+          const int rr = r0 + b * RPP + rsub;
+          float4 g = *reinterpret_cast<const float4 *>(ts + rr * LD + c4);
+          g.x *= DEBIAS_TWO; g.y *= DEBIAS_TWO; g.z *= DEBIAS_TWO; g.w *= DEBIAS_TWO;
+          float4 ow, op;
+          epi_one_tc(g.x, wv[b].x, pv[b].x, has_p, tv[b].x, p.cur, p.wd, p.mode, p.thr, ow.x, op.x);
+          epi_one_tc(g.y, wv[b].y, pv[b].y, has_p, tv[b].y, p.cur, p.wd, p.mode, p.thr, ow.y, op.y);
+          epi_one_tc(g.z, wv[b].z, pv[b].z, has_p, tv[b].z, p.cur, p.wd, p.mode, p.thr, ow.z, op.z);
+          epi_one_tc(g.w, wv[b].w, pv[b].w, has_p, tv[b].w, p.cur, p.wd, p.mode, p.thr, ow.w, op.w);
+          if (ok[b]) {
+            const long long idx = (long long)(kbase + rr) * p.C + c;
+            *reinterpret_cast<float4 *>(p.dW + idx) = ow;
+            if (p.dP) *reinterpret_cast<float4 *>(p.dP + idx) = op;
+          }
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int s = 0; s < TG; ++s) {
+        float *gbase = p.gpart + (((long long)split * p.K + kbase) * p.RS + (tap0 + s)) * p.C + c0;
+        const long long row_stride = (long long)p.RS * p.C;
+        epilogue_rows<BN>(tmem_base, quad, s * BN, ts, lane, [&](int rr, int c4, float4 g) {
+          g.x *= DEBIAS_TWO; g.y *= DEBIAS_TWO; g.z *= DEBIAS_TWO; g.w *= DEBIAS_TWO;
+          if (kbase + rr < p.K && c0 + c4 < p.C) *reinterpret_cast<float4 *>(gbase + rr * row_stride + c4) = g;
+        });
       }
     }
     tc_fence_before();
@@ -407,15 +561,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
 // fused wgrad epilogue over the [split][K][RS][C] partial sums:
 //   g = sum_s part[s];  dW = (g*b + wd*W)[T==cur] ...  written in the module's [K][C][R][S] order
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void epi_one_tc(float g, float w, float pv, bool has_p, unsigned t, int cur, float wd,
-                                           int mode, float thr, float &dw, float &dp) {
-  float gb = has_p ? g * binarize_val(pv, thr) : g;
-  if (mode == CPGB_GRAD_RAW) { dw = gb; dp = g * w; return; }
-  dw = (t == (unsigned)cur) ? fmaf(wd, w, gb) : 0.f;
-  dp = (mode == CPGB_GRAD_FINETUNE && t != 0u && t < (unsigned)cur) ? g * w : 0.f;
-}
-
-constexpr int EPI_CC = 64;
+constexpr int EPI_CC = 128;
 __global__ void __launch_bounds__(256)
 wgrad_epilogue_krsc_kernel(const float *__restrict__ gpart, int splits, int K, int C, int RS,
                            const float *__restrict__ w, const float *__restrict__ piggy,
@@ -444,6 +590,33 @@ wgrad_epilogue_krsc_kernel(const float *__restrict__ gpart, int splits, int K, i
                thr, ow, op);
     dW[idx] = ow;
     if (dP) dP[idx] = op;
+  }
+}
+
+// RS == 1: [K][C] order already; sum the splits, 16 bytes per thread
+__global__ void __launch_bounds__(256)
+wgrad_epilogue_flat_kernel(const float4 *__restrict__ gpart, int splits, long long n4,
+                           const float4 *__restrict__ w, const float4 *__restrict__ piggy,
+                           const uchar4 *__restrict__ tmask, int cur, float wd, int mode, float thr,
+                           float4 *__restrict__ dW, float4 *__restrict__ dP) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const bool has_p = piggy != nullptr;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 g = __ldg(gpart + i);
+    for (int s = 1; s < splits; ++s) {
+      const float4 b = __ldg(gpart + s * n4 + i);
+      g.x += b.x; g.y += b.y; g.z += b.z; g.w += b.w;
+    }
+    const float4 ww = __ldg(w + i);
+    const float4 pv = has_p ? __ldg(piggy + i) : make_float4(0, 0, 0, 0);
+    const uchar4 t = tmask ? __ldg(tmask + i) : make_uchar4(0, 0, 0, 0);
+    float4 ow, op;
+    epi_one_tc(g.x, ww.x, pv.x, has_p, t.x, cur, wd, mode, thr, ow.x, op.x);
+    epi_one_tc(g.y, ww.y, pv.y, has_p, t.y, cur, wd, mode, thr, ow.y, op.y);
+    epi_one_tc(g.z, ww.z, pv.z, has_p, t.z, cur, wd, mode, thr, ow.z, op.z);
+    epi_one_tc(g.w, ww.w, pv.w, has_p, t.w, cur, wd, mode, thr, ow.w, op.w);
+    dW[i] = ow;
+    if (dP) dP[i] = op;
   }
 }
 
@@ -491,7 +664,54 @@ size_t tc_staged_bytes(const cpgb_conv_desc &d) {
   return align_up((size_t)d.K * d.R * d.S * cp_of(d) * sizeof(float) + 256, 256);
 }
 
-struct WgradPlan { int BN, ctiles, ktiles, splits, chunks, cps; PixBox box; };
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0, v = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n = v > 0 ? v : 148;
+  }
+  return n;
+}
+
+// ---- fprop / dgrad plan: tile width and split-K factor -------------------------------------
+struct GemmPlan { PixBox box; int BN, ntiles, iters, splits, ips; bool dense; long long out_elems; };
+static GemmPlan plan_gemm(int Qo, int Po, int No, int ncols, int iters, const Str4 &os) {
+  GemmPlan g;
+  g.box = make_pixbox(128, Qo, Po, No);
+  const long long mtiles = (long long)g.box.tq * g.box.tp * g.box.tn;
+  const int sms = num_sms();
+  if (ncols <= 64) g.BN = 64;
+  else if (ncols <= 128) g.BN = 128;
+  else g.BN = (mtiles * cdiv_i(ncols, 256) >= sms) ? 256 : 128;
+  g.ntiles = cdiv_i(ncols, g.BN);
+  g.iters = iters;
+  // partial sums are addressed like the output, so splitting needs a dense NHWC output
+  g.dense = os.s[3] == ncols && os.s[2] == (int64_t)Qo * os.s[3] && os.s[0] == (int64_t)Po * os.s[2];
+  g.out_elems = (long long)No * Po * Qo * ncols;
+  const long long ctas = mtiles * g.ntiles;
+  int splits = 1;
+  if (g.dense && ctas * 5 < sms * 4) {
+    splits = cdiv_i(sms * 3 / 2, ctas);
+    if (splits > iters / 4) splits = iters / 4;
+    if (splits < 1) splits = 1;
+  }
+  g.ips = cdiv_i(iters, splits);
+  g.splits = cdiv_i(iters, g.ips);
+  return g;
+}
+static GemmPlan plan_fprop(const cpgb_conv_desc &d) {
+  return plan_gemm(d.Q, d.P, d.N, d.K, d.R * d.S * (cp_of(d) / 32), y_strides(d));
+}
+static GemmPlan plan_dgrad(const cpgb_conv_desc &d) {
+  return plan_gemm(d.W, d.H, d.N, d.C, d.R * d.S * cdiv_i(d.K, 32), x_strides(d));
+}
+static size_t plan_partial_bytes(const GemmPlan &g) {
+  return g.splits > 1 ? (size_t)g.splits * g.out_elems * sizeof(float) : 0;
+}
+
+// ---- wgrad plan ------------------------------------------------------------------------------
+struct WgradPlan { int BN, TG, groups, ctiles, ktiles, splits, chunks, cps; PixBox box; };
 static WgradPlan plan_wgrad(const cpgb_conv_desc &d) {
   WgradPlan pl;
   pl.BN = d.C >= 128 ? 128 : 64;
@@ -499,31 +719,48 @@ static WgradPlan plan_wgrad(const cpgb_conv_desc &d) {
   pl.ktiles = cdiv_i(d.K, 128);
   pl.box = make_pixbox(32, d.Q, d.P, d.N);
   pl.chunks = pl.box.tq * pl.box.tp * pl.box.tn;
-  const int base = pl.ctiles * pl.ktiles * d.R;
-  int splits = cdiv_i(2 * 148, base);
-  if (splits > pl.chunks) splits = pl.chunks;
+  const int RS = d.R * d.S, sms = num_sms();
+  // Few pixel chunks: one CTA per tap (no split-K traffic).  Many: the S taps of a filter row share
+  // the dY tile of every chunk (TG = S accumulators) and the chunk range is split.
+  pl.TG = (d.S == 3 && pl.ctiles * pl.ktiles * RS * 2 > sms && pl.chunks <= 256) ? 1 : d.S;
+  pl.groups = RS / pl.TG;
+  const int base = pl.ctiles * pl.ktiles * pl.groups;
+  int splits = cdiv_i(sms * 3 / 2, base);
+  if (splits > pl.chunks / 4) splits = pl.chunks / 4;
   if (splits < 1) splits = 1;
   pl.cps = cdiv_i(pl.chunks, splits);
   pl.splits = cdiv_i(pl.chunks, pl.cps);
   return pl;
 }
+static bool wgrad_fusable(const cpgb_conv_desc &d, const WgradPlan &pl) { return d.R * d.S == 1 && pl.splits == 1; }
 
 size_t tc_workspace_bytes(const cpgb_conv_desc &d) {
   if (d.groups <= 0) return 0;
-  size_t b = 0;
-  if (tc_eligible(d, 0) || tc_eligible(d, 1)) b = tc_staged_bytes(d);
+  size_t staged = 0, b = 0;
+  if (tc_eligible(d, 0) || tc_eligible(d, 1)) staged = tc_staged_bytes(d);
+  if (tc_eligible(d, 0)) b = std::max(b, plan_partial_bytes(plan_fprop(d)));
+  if (tc_eligible(d, 1)) b = std::max(b, plan_partial_bytes(plan_dgrad(d)));
   if (tc_eligible(d, 2)) {
     WgradPlan pl = plan_wgrad(d);
-    size_t g = (size_t)pl.splits * d.K * d.R * d.S * d.C * sizeof(float);
-    if (g > b) b = g;
+    if (!wgrad_fusable(d, pl)) b = std::max(b, (size_t)pl.splits * d.K * d.R * d.S * d.C * sizeof(float));
   }
-  return align_up(b, 256);
+  // layout of ws: [staged operand (when the caller passes none)] [partial sums]
+  return staged + align_up(b, 256) + 256;
 }
 
 int tc_stage_weights(const cpgb_conv_desc &d, const float *w, const float *piggy, float thr, void *staged,
                      size_t bytes, cudaStream_t st) {
   if (bytes < tc_staged_bytes(d)) { set_error("staged-weight buffer %zu < %zu", bytes, tc_staged_bytes(d)); return CPGB_EWORKSPACE; }
   const int RS = d.R * d.S, Cp = cp_of(d);
+  if (RS == 1 && Cp == d.C && aligned16p(w) && aligned16p(staged) && (!piggy || aligned16p(piggy))) {
+    const long long n4 = (long long)d.K * d.C / 4;
+    int grid = (int)std::min<long long>((n4 + 255) / 256, (long long)num_sms() * 8);
+    stage_weights_flat_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4 *>(w),
+                                                    reinterpret_cast<const float4 *>(piggy),
+                                                    reinterpret_cast<float4 *>(staged), n4, thr);
+    CPGB_LAUNCH_OK("stage_weights_flat");
+    return CPGB_OK;
+  }
   dim3 grid(d.K, cdiv_i(Cp, STAGE_CC));
   size_t sh = (size_t)STAGE_CC * (RS | 1) * sizeof(float);
   stage_weights_kernel<<<grid, 256, sh, st>>>(w, piggy, reinterpret_cast<float *>(staged), d.C, Cp, RS, thr);
@@ -533,7 +770,7 @@ int tc_stage_weights(const cpgb_conv_desc &d, const float *w, const float *piggy
 
 template <int BN, bool B_MN>
 static int launch_conv_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const ConvGemmParams &p, int ntiles_n,
-                            cudaStream_t st) {
+                            int splits, cudaStream_t st) {
   using Cfg = ConvGemmCfg<BN, B_MN>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -541,18 +778,10 @@ static int launch_conv_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const 
                                       Cfg::SMEM_BYTES));
     attr_done = true;
   }
-  dim3 grid(p.tq * p.tp * p.tn, ntiles_n);
+  dim3 grid(p.tq * p.tp * p.tn, ntiles_n, splits);
   conv_gemm_kernel<BN, B_MN><<<grid, 192, Cfg::SMEM_BYTES, st>>>(ta, tb, p);
   CPGB_LAUNCH_OK("conv_gemm_kernel");
   return CPGB_OK;
-}
-
-static int pick_bn(int ncols, long long mtiles) {
-  // widest tile that still gives ~one wave of CTAs
-  if (ncols > 128 && mtiles * cdiv_i(ncols, 256) >= 120) return 256;
-  if (ncols > 64 && mtiles * cdiv_i(ncols, 128) >= 100) return 128;
-  if (ncols > 128 && mtiles * cdiv_i(ncols, 64) < 64) return 128;
-  return 64;
 }
 
 // map of an NHWC activation tensor: dims (C, W, H, N)
@@ -565,69 +794,83 @@ static int make_act_map(CUtensorMap *m, const float *base, int C, int W, int H, 
   return make_map(m, base, 4, dims, str, box);
 }
 
-int tc_fprop(const cpgb_conv_desc &d, const float *x, const float *staged, const float *bias, float *y,
-             cudaStream_t st) {
-  if (!aligned16p(x) || !aligned16p(y) || !aligned16p(staged) || (bias && !aligned16p(bias))) {
+// common tail of fprop / dgrad: launch the GEMM (split or not) and, when split, the reduction
+template <bool B_MN>
+static int run_gemm(const GemmPlan &g, const CUtensorMap &ta, const CUtensorMap &tb, ConvGemmParams &p, float *out,
+                    const float *bias, void *part, size_t part_bytes, cudaStream_t st) {
+  p.tq = g.box.tq; p.tp = g.box.tp; p.tn = g.box.tn; p.lq = g.box.lq; p.lp = g.box.lp;
+  p.iters_per_split = g.ips;
+  p.mn_layout = g_mn.layout; p.mn_lbo = g_mn.lbo; p.mn_sbo = g_mn.sbo; p.mn_kadv = g_mn.kadv;
+  if (g.splits > 1) {
+    if (!part || part_bytes < plan_partial_bytes(g)) {
+      set_error("workspace %zu < %zu (split-K partial sums)", part_bytes, plan_partial_bytes(g));
+      return CPGB_EWORKSPACE;
+    }
+    p.out = reinterpret_cast<float *>(part); p.bias = nullptr; p.split_stride = g.out_elems;
+  } else {
+    p.out = out; p.bias = bias; p.split_stride = 0;
+  }
+  int rc;
+  if (g.BN == 256) rc = launch_conv_gemm<256, B_MN>(ta, tb, p, g.ntiles, g.splits, st);
+  else if (g.BN == 128) rc = launch_conv_gemm<128, B_MN>(ta, tb, p, g.ntiles, g.splits, st);
+  else rc = launch_conv_gemm<64, B_MN>(ta, tb, p, g.ntiles, g.splits, st);
+  if (rc || g.splits == 1) return rc;
+  const long long n4 = g.out_elems / 4;
+  int grid = (int)std::min<long long>((n4 + 255) / 256, (long long)num_sms() * 8);
+  splitk_reduce_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4 *>(part), g.splits, n4, n4, p.ncols / 4,
+                                             reinterpret_cast<const float4 *>(bias), reinterpret_cast<float4 *>(out));
+  CPGB_LAUNCH_OK("splitk_reduce");
+  return CPGB_OK;
+}
+
+int tc_fprop(const cpgb_conv_desc &d, const float *x, const float *staged, const float *bias, float *y, void *part,
+             size_t part_bytes, cudaStream_t st) {
+  if (!aligned16p(x) || !aligned16p(y) || !aligned16p(staged) || (bias && !aligned16p(bias)) || !aligned16p(part)) {
     set_error("tcgen05 path needs 16-byte aligned tensors"); return CPGB_EINVAL;
   }
   const int RS = d.R * d.S, Cp = cp_of(d);
-  PixBox b = make_pixbox(128, d.Q, d.P, d.N);
+  GemmPlan g = plan_fprop(d);
   CUtensorMap ta, tb;
   int rc;
-  if ((rc = make_act_map(&ta, x, d.C, d.W, d.H, d.N, x_strides(d), b))) return rc;
-  const long long mtiles = (long long)b.tq * b.tp * b.tn;
-  const int BN = pick_bn(d.K, mtiles);
+  if ((rc = make_act_map(&ta, x, d.C, d.W, d.H, d.N, x_strides(d), g.box))) return rc;
   {
     uint64_t dims[3] = {(uint64_t)Cp, (uint64_t)RS, (uint64_t)d.K};
     uint64_t str[2] = {(uint64_t)Cp * 4, (uint64_t)RS * Cp * 4};
-    uint32_t box[3] = {32, 1, (uint32_t)BN};
+    uint32_t box[3] = {32, 1, (uint32_t)g.BN};
     if ((rc = make_map(&tb, staged, 3, dims, str, box))) return rc;
   }
   ConvGemmParams p;
-  p.tq = b.tq; p.tp = b.tp; p.tn = b.tn; p.lq = b.lq; p.lp = b.lp;
   p.Qo = d.Q; p.Po = d.P; p.No = d.N; p.S = d.S; p.taps = RS;
   p.off_h = -d.pad_h; p.off_w = -d.pad_w; p.step_h = d.dil_h; p.step_w = d.dil_w;
   p.kblocks = Cp / 32; p.ncols = d.K;
-  p.mn_layout = g_mn.layout; p.mn_lbo = g_mn.lbo; p.mn_sbo = g_mn.sbo; p.mn_kadv = g_mn.kadv;
   { Str4 ys = y_strides(d); p.o_sn = ys.s[0]; p.o_sh = ys.s[2]; p.o_sw = ys.s[3]; }
-  p.out = y; p.bias = bias;
-  const int nt = cdiv_i(d.K, BN);
-  if (BN == 256) return launch_conv_gemm<256, false>(ta, tb, p, nt, st);
-  if (BN == 128) return launch_conv_gemm<128, false>(ta, tb, p, nt, st);
-  return launch_conv_gemm<64, false>(ta, tb, p, nt, st);
+  return run_gemm<false>(g, ta, tb, p, y, bias, part, part_bytes, st);
 }
 
-int tc_dgrad(const cpgb_conv_desc &d, const float *dy, const float *staged, float *dx, cudaStream_t st) {
-  if (!aligned16p(dy) || !aligned16p(dx) || !aligned16p(staged)) {
+int tc_dgrad(const cpgb_conv_desc &d, const float *dy, const float *staged, float *dx, void *part, size_t part_bytes,
+             cudaStream_t st) {
+  if (!aligned16p(dy) || !aligned16p(dx) || !aligned16p(staged) || !aligned16p(part)) {
     set_error("tcgen05 path needs 16-byte aligned tensors"); return CPGB_EINVAL;
   }
   const int RS = d.R * d.S, Cp = cp_of(d);
   // output pixels = input positions (h, w); A = dy read at (h + pad - r*dil, w + pad - s*dil)
-  PixBox b = make_pixbox(128, d.W, d.H, d.N);
+  GemmPlan g = plan_dgrad(d);
   CUtensorMap ta, tb;
   int rc;
-  if ((rc = make_act_map(&ta, dy, d.K, d.Q, d.P, d.N, y_strides(d), b))) return rc;
-  const long long mtiles = (long long)b.tq * b.tp * b.tn;
-  const int BN = pick_bn(d.C, mtiles);
+  if ((rc = make_act_map(&ta, dy, d.K, d.Q, d.P, d.N, y_strides(d), g.box))) return rc;
   {
     // Wt[k][t][c] as (c_in_block 32, k, t, c_block): B tile = [BN/32][32 k rows][32 c]
     uint64_t dims[4] = {32, (uint64_t)d.K, (uint64_t)RS, (uint64_t)(Cp / 32)};
     uint64_t str[3] = {(uint64_t)RS * Cp * 4, (uint64_t)Cp * 4, 128};
-    uint32_t box[4] = {32, 32, 1, (uint32_t)(BN / 32)};
+    uint32_t box[4] = {32, 32, 1, (uint32_t)(g.BN / 32)};
     if ((rc = make_map(&tb, staged, 4, dims, str, box, true))) return rc;
   }
   ConvGemmParams p;
-  p.tq = b.tq; p.tp = b.tp; p.tn = b.tn; p.lq = b.lq; p.lp = b.lp;
   p.Qo = d.W; p.Po = d.H; p.No = d.N; p.S = d.S; p.taps = RS;
   p.off_h = d.pad_h; p.off_w = d.pad_w; p.step_h = -d.dil_h; p.step_w = -d.dil_w;
   p.kblocks = cdiv_i(d.K, 32); p.ncols = d.C;
-  p.mn_layout = g_mn.layout; p.mn_lbo = g_mn.lbo; p.mn_sbo = g_mn.sbo; p.mn_kadv = g_mn.kadv;
   { Str4 xs = x_strides(d); p.o_sn = xs.s[0]; p.o_sh = xs.s[2]; p.o_sw = xs.s[3]; }
-  p.out = dx; p.bias = nullptr;
-  const int nt = cdiv_i(d.C, BN);
-  if (BN == 256) return launch_conv_gemm<256, true>(ta, tb, p, nt, st);
-  if (BN == 128) return launch_conv_gemm<128, true>(ta, tb, p, nt, st);
-  return launch_conv_gemm<64, true>(ta, tb, p, nt, st);
+  return run_gemm<true>(g, ta, tb, p, dx, nullptr, part, part_bytes, st);
 }
 
 template <int BN, int TG>
@@ -663,7 +906,10 @@ int tc_wgrad_fused(const cpgb_conv_desc &d, const float *x, const float *dy, con
   }
   WgradPlan pl = plan_wgrad(d);
   const int RS = d.R * d.S;
-  const size_t need = (size_t)pl.splits * d.K * RS * d.C * sizeof(float);
+  const bool vec_ok = aligned16p(w) && aligned16p(dW) && (!piggy || aligned16p(piggy)) && (!dP || aligned16p(dP)) &&
+                      (!tmask || (reinterpret_cast<uintptr_t>(tmask) & 3) == 0);
+  const bool fused = wgrad_fusable(d, pl) && vec_ok;
+  const size_t need = fused ? 0 : (size_t)pl.splits * d.K * RS * d.C * sizeof(float);
   if (ws_bytes < need) { set_error("workspace %zu < %zu", ws_bytes, need); return CPGB_EWORKSPACE; }
   CUtensorMap tdy, tx;
   int rc;
@@ -675,13 +921,25 @@ int tc_wgrad_fused(const cpgb_conv_desc &d, const float *x, const float *dy, con
   p.chunks = pl.chunks; p.chunks_per_split = pl.cps; p.ctiles = pl.ctiles; p.K = d.K; p.C = d.C;
   p.mn_layout = g_mn.layout; p.mn_lbo = g_mn.lbo; p.mn_sbo = g_mn.sbo; p.mn_kadv = g_mn.kadv;
   p.gpart = reinterpret_cast<float *>(ws);
-  dim3 grid(pl.ktiles * pl.ctiles, d.R, pl.splits);
-  if (d.S == 3) {
+  p.fused = fused ? 1 : 0; p.cur = cur; p.mode = mode; p.wd = wd; p.thr = thr;
+  p.w = w; p.piggy = piggy; p.tmask = tmask; p.dW = dW; p.dP = dP;
+  dim3 grid(pl.ktiles * pl.ctiles, pl.groups, pl.splits);
+  if (pl.TG == 3) {
     rc = pl.BN == 128 ? launch_wgrad<128, 3>(tdy, tx, p, grid, st) : launch_wgrad<64, 3>(tdy, tx, p, grid, st);
   } else {
     rc = pl.BN == 128 ? launch_wgrad<128, 1>(tdy, tx, p, grid, st) : launch_wgrad<64, 1>(tdy, tx, p, grid, st);
   }
-  if (rc) return rc;
+  if (rc || fused) return rc;
+  if (RS == 1 && vec_ok) {
+    const long long n4 = (long long)d.K * d.C / 4;
+    int egrid = (int)std::min<long long>((n4 + 255) / 256, (long long)num_sms() * 8);
+    wgrad_epilogue_flat_kernel<<<egrid, 256, 0, st>>>(
+        reinterpret_cast<const float4 *>(p.gpart), pl.splits, n4, reinterpret_cast<const float4 *>(w),
+        reinterpret_cast<const float4 *>(piggy), reinterpret_cast<const uchar4 *>(tmask), cur, wd, mode, thr,
+        reinterpret_cast<float4 *>(dW), reinterpret_cast<float4 *>(dP));
+    CPGB_LAUNCH_OK("wgrad_epilogue_flat");
+    return CPGB_OK;
+  }
   dim3 egrid(d.K, cdiv_i(d.C, EPI_CC));
   size_t sh = (size_t)RS * (EPI_CC + 1) * sizeof(float);
   wgrad_epilogue_krsc_kernel<<<egrid, 256, sh, st>>>(p.gpart, pl.splits, d.K, d.C, RS, w, piggy, tmask, cur, wd, mode,

@@ -29,14 +29,16 @@ def _dense4(t):
 
 def _stage(lib, d, w, p, threshold):
     """Build the tensor-core weight operand (masked, TF32, [K][RS][Cp]) for descriptor d, or
-    None when d takes the CUDA-core path (which evaluates the mask while loading tiles)."""
+    None when d takes the CUDA-core path (which evaluates the mask while loading tiles).
+    Returns (staged, scratch): scratch is the split-K workspace of the fprop/dgrad call."""
     nbytes = lib.cpgb_staged_weight_bytes(d)
     if nbytes == 0:
-        return None
+        return None, None
     staged = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
     _lib.check(lib.cpgb_stage_weights(d, _lib.ptr(w), _lib.ptr(p), threshold, _lib.ptr(staged), nbytes,
                                       _lib.stream_ptr()), 'cpgb_stage_weights')
-    return staged
+    # cpgb_workspace_bytes = [staged operand][partial sums]; the operand is supplied separately
+    return staged, _ws(lib.cpgb_workspace_bytes(d) - nbytes, w.device)
 
 
 class FuseCtx:
@@ -91,9 +93,10 @@ class MaskedConv2dFn(torch.autograd.Function):
         y = torch.empty((N, K, P, Q), dtype=torch.float32, device=x.device, memory_format=fmt)
         d = _lib.conv_desc(x.shape, x.stride(), w.shape, y.shape, y.stride(), stride, padding, dilation, groups)
         with torch.cuda.device(x.device):
-            staged = _stage(lib, d, w, p, threshold)
+            staged, ws = _stage(lib, d, w, p, threshold)
             _lib.check(lib.cpgb_conv2d_fprop(d, _lib.ptr(x), _lib.ptr(w), _lib.ptr(p), _lib.ptr(b),
-                                             _lib.ptr(y), threshold, _lib.ptr(staged), None, 0,
+                                             _lib.ptr(y), threshold, _lib.ptr(staged), _lib.ptr(ws),
+                                             ws.numel() if ws is not None else 0,
                                              _lib.stream_ptr()), 'cpgb_conv2d_fprop')
         ctx.save_for_backward(x, w, p)
         ctx.staged = staged     # masked TF32 operand, shared with this step's dgrad
@@ -161,9 +164,10 @@ class MaskedLinearFn(torch.autograd.Function):
         d = _lib.ConvDesc()
         lib.cpgb_linear_desc(d, M, I, O)
         with torch.cuda.device(x.device):
-            staged = _stage(lib, d, w, p, threshold)
+            staged, ws = _stage(lib, d, w, p, threshold)
             _lib.check(lib.cpgb_conv2d_fprop(d, _lib.ptr(x2), _lib.ptr(w), _lib.ptr(p), _lib.ptr(b), _lib.ptr(y),
-                                             threshold, _lib.ptr(staged), None, 0, _lib.stream_ptr()),
+                                             threshold, _lib.ptr(staged), _lib.ptr(ws),
+                                             ws.numel() if ws is not None else 0, _lib.stream_ptr()),
                        'cpgb_conv2d_fprop(linear)')
         ctx.save_for_backward(x2, w, p)
         ctx.staged = staged
