@@ -378,9 +378,9 @@ struct WgradParams {
   int pad_h, pad_w, dil_h, dil_w;
   int chunks, chunks_per_split;
   int ctiles;              // number of BN-wide channel tiles
-  int K, C;
+  int K, C, Cg;            // Cg = C rounded up to 4: row stride of gpart
   int mn_layout, mn_lbo, mn_sbo, mn_kadv;
-  float *gpart;            // [splits][K][RS][C]
+  float *gpart;            // [splits][K][RS][Cg]
   // fused epilogue (only RS == 1, one split): SURVEY K6-K8 applied straight from TMEM
   int fused, cur, mode;
   float wd, thr;
@@ -540,11 +540,11 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     } else {
 #pragma unroll 1
       for (int s = 0; s < TG; ++s) {
-        float *gbase = p.gpart + (((long long)split * p.K + kbase) * p.RS + (tap0 + s)) * p.C + c0;
-        const long long row_stride = (long long)p.RS * p.C;
+        float *gbase = p.gpart + (((long long)split * p.K + kbase) * p.RS + (tap0 + s)) * p.Cg + c0;
+        const long long row_stride = (long long)p.RS * p.Cg;
         epilogue_rows<BN>(tmem_base, quad, s * BN, ts, lane, [&](int rr, int c4, float4 g) {
           g.x *= DEBIAS_TWO; g.y *= DEBIAS_TWO; g.z *= DEBIAS_TWO; g.w *= DEBIAS_TWO;
-          if (kbase + rr < p.K && c0 + c4 < p.C) *reinterpret_cast<float4 *>(gbase + rr * row_stride + c4) = g;
+          if (kbase + rr < p.K && c0 + c4 < p.Cg) *reinterpret_cast<float4 *>(gbase + rr * row_stride + c4) = g;
         });
       }
     }
@@ -561,30 +561,81 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
 // fused wgrad epilogue over the [split][K][RS][C] partial sums:
 //   g = sum_s part[s];  dW = (g*b + wd*W)[T==cur] ...  written in the module's [K][C][R][S] order
 // ------------------------------------------------------------------------------------------
-constexpr int EPI_CC = 128;
+// One block handles `kb` consecutive output channels.  Phase 1: sum the splits of G[k][t][c]
+// (contiguous per k, 16-byte loads) into smem [t][c]; phase 2: walk the module's [k][c][t] order
+// (contiguous per k) with 16-byte accesses to W / P / T / dW / dP.  RS_T > 0: compile-time tap count.
+template <int RS_T>
 __global__ void __launch_bounds__(256)
-wgrad_epilogue_krsc_kernel(const float *__restrict__ gpart, int splits, int K, int C, int RS,
+wgrad_epilogue_krsc_kernel(const float *__restrict__ gpart, int splits, int K, int C, int Cg, int RS_rt, int kb,
                            const float *__restrict__ w, const float *__restrict__ piggy,
                            const uint8_t *__restrict__ tmask, int cur, float wd, int mode, float thr,
                            float *__restrict__ dW, float *__restrict__ dP) {
-  extern __shared__ float sh[];  // [RS][EPI_CC + 1]
-  const int k = blockIdx.x, c0 = blockIdx.y * EPI_CC;
-  const int cc = min(EPI_CC, C - c0);
-  const long long split_stride = (long long)K * RS * C;
-  for (int i = threadIdx.x; i < RS * cc; i += blockDim.x) {
-    const int t = i / cc, c = i - t * cc;
-    const float *src = gpart + ((long long)k * RS + t) * C + c0 + c;
-    float s = 0.f;
-    for (int sp = 0; sp < splits; ++sp) s += __ldg(src + sp * split_stride);
-    sh[t * (EPI_CC + 1) + c] = s;
+  extern __shared__ float sh[];  // [kb][RS][Cg + 1]
+  const int RS = RS_T > 0 ? RS_T : RS_rt;
+  const int k0 = blockIdx.x * kb;
+  const int nk = min(kb, K - k0);
+  const int ld = Cg + 1;
+  const long long split_stride = (long long)K * RS * Cg;
+  const int row4 = Cg >> 2;                      // float4 per (k, t) row of G
+  const float4 *g4 = reinterpret_cast<const float4 *>(gpart + (long long)k0 * RS * Cg);
+  for (int i = threadIdx.x; i < nk * RS * row4; i += blockDim.x) {
+    float4 a = __ldg(g4 + i);
+    for (int sp = 1; sp < splits; ++sp) {
+      const float4 b = __ldg(reinterpret_cast<const float4 *>(gpart + sp * split_stride + (long long)k0 * RS * Cg) + i);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    const int row = i / row4, c = (i - row * row4) * 4;     // row = kk * RS + t
+    float *d = sh + row * ld + c;
+    d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w;
   }
   __syncthreads();
-  const long long base = ((long long)k * C + c0) * RS;
   const bool has_p = piggy != nullptr;
-  for (int i = threadIdx.x; i < cc * RS; i += blockDim.x) {
-    const int c = i / RS, t = i - c * RS;
-    const float g = sh[t * (EPI_CC + 1) + c];
+  const int per_k = C * RS;                      // C % 4 == 0 on this path => per_k % 4 == 0
+  const long long base = (long long)k0 * per_k;
+  for (int i4 = threadIdx.x; i4 < (nk * per_k) >> 2; i4 += blockDim.x) {
+    const int i = i4 << 2;
     const long long idx = base + i;
+    const float4 wv = __ldg(reinterpret_cast<const float4 *>(w + idx));
+    const float4 pv = has_p ? __ldg(reinterpret_cast<const float4 *>(piggy + idx)) : make_float4(0, 0, 0, 0);
+    const uchar4 tv = tmask ? __ldg(reinterpret_cast<const uchar4 *>(tmask + idx)) : make_uchar4(0, 0, 0, 0);
+    const int kk = i / per_k;
+    int rem = i - kk * per_k;
+    int c = rem / RS, t = rem - c * RS;
+    const float *srow = sh + kk * RS * ld;
+    float g[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      g[j] = srow[t * ld + c];
+      if (++t == RS) { t = 0; ++c; }
+    }
+    float4 ow, op;
+    epi_one_tc(g[0], wv.x, pv.x, has_p, tv.x, cur, wd, mode, thr, ow.x, op.x);
+    epi_one_tc(g[1], wv.y, pv.y, has_p, tv.y, cur, wd, mode, thr, ow.y, op.y);
+    epi_one_tc(g[2], wv.z, pv.z, has_p, tv.z, cur, wd, mode, thr, ow.z, op.z);
+    epi_one_tc(g[3], wv.w, pv.w, has_p, tv.w, cur, wd, mode, thr, ow.w, op.w);
+    *reinterpret_cast<float4 *>(dW + idx) = ow;
+    if (dP) *reinterpret_cast<float4 *>(dP + idx) = op;
+  }
+}
+
+// scalar variant for channel counts that are not a multiple of 4 (the 3-channel stem)
+__global__ void __launch_bounds__(256)
+wgrad_epilogue_krsc_scalar_kernel(const float *__restrict__ gpart, int splits, int K, int C, int Cg, int RS,
+                                  const float *__restrict__ w, const float *__restrict__ piggy,
+                                  const uint8_t *__restrict__ tmask, int cur, float wd, int mode, float thr,
+                                  float *__restrict__ dW, float *__restrict__ dP) {
+  const long long n = (long long)K * C * RS;
+  const long long split_stride = (long long)K * RS * Cg;
+  const bool has_p = piggy != nullptr;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += stride) {
+    const int t = (int)(idx % RS);
+    const long long kc = idx / RS;
+    const int c = (int)(kc % C);
+    const long long k = kc / C;
+    const float *src = gpart + (k * RS + t) * Cg + c;
+    float g = 0.f;
+    for (int sp = 0; sp < splits; ++sp) g += __ldg(src + sp * split_stride);
     float ow, op;
     epi_one_tc(g, __ldg(w + idx), has_p ? __ldg(piggy + idx) : 0.f, has_p, tmask ? tmask[idx] : 0u, cur, wd, mode,
                thr, ow, op);
@@ -645,18 +696,25 @@ static bool nhwc_ok(const Str4 &st, int C) {
 static Str4 x_strides(const cpgb_conv_desc &d) { return norm_strides(d.xs, d.C, d.H, d.W, d.N); }
 static Str4 y_strides(const cpgb_conv_desc &d) { return norm_strides(d.ys, d.K, d.P, d.Q, d.N); }
 
+// Shapes the tensor-core kernels take (everything else runs on the CUDA-core kernels):
+// stride 1, groups 1, NHWC activations whose pixel stride is a multiple of 16 bytes (the channel
+// count itself may be odd, e.g. the 3-channel stem stored with a pixel stride of 4), K % 4 == 0
+// for vector stores; dgrad additionally C % 4 == 0; wgrad K % 32 == 0, C % 32 == 0 or C < 32,
+// filter width 1 or 3.
 bool tc_eligible(const cpgb_conv_desc &d, int op) {
   if (d.groups != 1 || d.stride_h != 1 || d.stride_w != 1) return false;
-  if (d.C % 4 || d.K % 4) return false;
+  if (d.K % 4) return false;
   if (d.R * d.S > 49 || d.N < 1) return false;
   if (!nhwc_ok(x_strides(d), d.C) || !nhwc_ok(y_strides(d), d.K)) return false;
   if (d.W > 4096 || d.H > 4096) return false;
+  if (op == 1 && d.C % 4) return false;
   if (op == 2) {
-    if (d.C % 32 || d.K % 32) return false;
+    if ((d.C % 32 && d.C > 32) || d.K % 32) return false;
     if (d.S != 1 && d.S != 3) return false;
   }
   return true;
 }
+static inline int cg_of(const cpgb_conv_desc &d) { return (d.C + 3) & ~3; }   // row stride of the wgrad partials
 
 static inline int cp_of(const cpgb_conv_desc &d) { return (d.C + 31) / 32 * 32; }
 
@@ -732,7 +790,9 @@ static WgradPlan plan_wgrad(const cpgb_conv_desc &d) {
   pl.splits = cdiv_i(pl.chunks, pl.cps);
   return pl;
 }
-static bool wgrad_fusable(const cpgb_conv_desc &d, const WgradPlan &pl) { return d.R * d.S == 1 && pl.splits == 1; }
+static bool wgrad_fusable(const cpgb_conv_desc &d, const WgradPlan &pl) {
+  return d.R * d.S == 1 && pl.splits == 1 && d.C % 4 == 0;
+}
 
 size_t tc_workspace_bytes(const cpgb_conv_desc &d) {
   if (d.groups <= 0) return 0;
@@ -742,7 +802,7 @@ size_t tc_workspace_bytes(const cpgb_conv_desc &d) {
   if (tc_eligible(d, 1)) b = std::max(b, plan_partial_bytes(plan_dgrad(d)));
   if (tc_eligible(d, 2)) {
     WgradPlan pl = plan_wgrad(d);
-    if (!wgrad_fusable(d, pl)) b = std::max(b, (size_t)pl.splits * d.K * d.R * d.S * d.C * sizeof(float));
+    if (!wgrad_fusable(d, pl)) b = std::max(b, (size_t)pl.splits * d.K * d.R * d.S * cg_of(d) * sizeof(float));
   }
   // layout of ws: [staged operand (when the caller passes none)] [partial sums]
   return staged + align_up(b, 256) + 256;
@@ -888,11 +948,11 @@ static int launch_wgrad(const CUtensorMap &tdy, const CUtensorMap &tx, const Wgr
   return CPGB_OK;
 }
 
-// 5-D map (32 channels of a block, W, H, N, channel block) of an NHWC tensor with C % 32 == 0
+// 5-D map (32 channels of a block, W, H, N, channel block) of an NHWC tensor with C % 32 == 0 or C < 32
 static int make_act_map5(CUtensorMap *m, const float *base, int C, int W, int H, int N, const Str4 &sv,
                          const PixBox &b, int nblk_box) {
   const int64_t *s = sv.s;
-  uint64_t dims[5] = {32, (uint64_t)W, (uint64_t)H, (uint64_t)N, (uint64_t)(C / 32)};
+  uint64_t dims[5] = {(uint64_t)(C < 32 ? C : 32), (uint64_t)W, (uint64_t)H, (uint64_t)N, (uint64_t)((C + 31) / 32)};
   uint64_t str[4] = {(uint64_t)s[3] * 4, (uint64_t)s[2] * 4, (uint64_t)s[0] * 4, 128};
   uint32_t box[5] = {32, 1u << b.lq, 1u << b.lp, 1u << b.ln, (uint32_t)nblk_box};
   return make_map(m, base, 5, dims, str, box, true);
@@ -909,7 +969,7 @@ int tc_wgrad_fused(const cpgb_conv_desc &d, const float *x, const float *dy, con
   const bool vec_ok = aligned16p(w) && aligned16p(dW) && (!piggy || aligned16p(piggy)) && (!dP || aligned16p(dP)) &&
                       (!tmask || (reinterpret_cast<uintptr_t>(tmask) & 3) == 0);
   const bool fused = wgrad_fusable(d, pl) && vec_ok;
-  const size_t need = fused ? 0 : (size_t)pl.splits * d.K * RS * d.C * sizeof(float);
+  const size_t need = fused ? 0 : (size_t)pl.splits * d.K * RS * cg_of(d) * sizeof(float);
   if (ws_bytes < need) { set_error("workspace %zu < %zu", ws_bytes, need); return CPGB_EWORKSPACE; }
   CUtensorMap tdy, tx;
   int rc;
@@ -918,7 +978,7 @@ int tc_wgrad_fused(const cpgb_conv_desc &d, const float *x, const float *dy, con
   WgradParams p;
   p.cq = pl.box.tq; p.cp = pl.box.tp; p.cn = pl.box.tn; p.lq = pl.box.lq; p.lp = pl.box.lp;
   p.S = d.S; p.RS = RS; p.pad_h = d.pad_h; p.pad_w = d.pad_w; p.dil_h = d.dil_h; p.dil_w = d.dil_w;
-  p.chunks = pl.chunks; p.chunks_per_split = pl.cps; p.ctiles = pl.ctiles; p.K = d.K; p.C = d.C;
+  p.chunks = pl.chunks; p.chunks_per_split = pl.cps; p.ctiles = pl.ctiles; p.K = d.K; p.C = d.C; p.Cg = cg_of(d);
   p.mn_layout = g_mn.layout; p.mn_lbo = g_mn.lbo; p.mn_sbo = g_mn.sbo; p.mn_kadv = g_mn.kadv;
   p.gpart = reinterpret_cast<float *>(ws);
   p.fused = fused ? 1 : 0; p.cur = cur; p.mode = mode; p.wd = wd; p.thr = thr;
@@ -930,7 +990,7 @@ int tc_wgrad_fused(const cpgb_conv_desc &d, const float *x, const float *dy, con
     rc = pl.BN == 128 ? launch_wgrad<128, 1>(tdy, tx, p, grid, st) : launch_wgrad<64, 1>(tdy, tx, p, grid, st);
   }
   if (rc || fused) return rc;
-  if (RS == 1 && vec_ok) {
+  if (RS == 1 && vec_ok && d.C % 4 == 0) {
     const long long n4 = (long long)d.K * d.C / 4;
     int egrid = (int)std::min<long long>((n4 + 255) / 256, (long long)num_sms() * 8);
     wgrad_epilogue_flat_kernel<<<egrid, 256, 0, st>>>(
@@ -940,11 +1000,34 @@ int tc_wgrad_fused(const cpgb_conv_desc &d, const float *x, const float *dy, con
     CPGB_LAUNCH_OK("wgrad_epilogue_flat");
     return CPGB_OK;
   }
-  dim3 egrid(d.K, cdiv_i(d.C, EPI_CC));
-  size_t sh = (size_t)RS * (EPI_CC + 1) * sizeof(float);
-  wgrad_epilogue_krsc_kernel<<<egrid, 256, sh, st>>>(p.gpart, pl.splits, d.K, d.C, RS, w, piggy, tmask, cur, wd, mode,
-                                                     thr, dW, dP);
-  CPGB_LAUNCH_OK("wgrad_epilogue_krsc");
+  if (d.C % 4 == 0 && vec_ok) {
+    // ~18 KB of G per block: 1 output channel at C*RS = 4608, 8 at 576
+    int kb = std::max(1, 4608 / (d.C * RS));
+    kb = std::min(kb, std::max(1, d.K / (2 * num_sms())));   // but keep >= 2 blocks per SM
+    size_t sh = (size_t)kb * RS * (p.Cg + 1) * sizeof(float);
+    if (sh <= 96 * 1024) {
+      static bool attr_done = false;
+      if (!attr_done) {
+        CPGB_CUDA_OK(cudaFuncSetAttribute(wgrad_epilogue_krsc_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        CPGB_CUDA_OK(cudaFuncSetAttribute(wgrad_epilogue_krsc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr_done = true;
+      }
+      const int egrid = cdiv_i(d.K, kb);
+      if (RS == 9)
+        wgrad_epilogue_krsc_kernel<9><<<egrid, 256, sh, st>>>(p.gpart, pl.splits, d.K, d.C, p.Cg, RS, kb, w, piggy, tmask,
+                                                             cur, wd, mode, thr, dW, dP);
+      else
+        wgrad_epilogue_krsc_kernel<0><<<egrid, 256, sh, st>>>(p.gpart, pl.splits, d.K, d.C, p.Cg, RS, kb, w, piggy, tmask,
+                                                             cur, wd, mode, thr, dW, dP);
+      CPGB_LAUNCH_OK("wgrad_epilogue_krsc");
+      return CPGB_OK;
+    }
+  }
+  const long long n = (long long)d.K * d.C * RS;
+  int egrid = (int)std::min<long long>((n + 255) / 256, (long long)num_sms() * 8);
+  wgrad_epilogue_krsc_scalar_kernel<<<egrid, 256, 0, st>>>(p.gpart, pl.splits, d.K, d.C, p.Cg, RS, w, piggy, tmask, cur,
+                                                          wd, mode, thr, dW, dP);
+  CPGB_LAUNCH_OK("wgrad_epilogue_krsc_scalar");
   return CPGB_OK;
 }
 

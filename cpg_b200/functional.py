@@ -74,9 +74,19 @@ class MaskedConv2dFn(torch.autograd.Function):
         if x.dtype != torch.float32 or not x.is_cuda:
             raise _lib.CpgbError(f'input must be a float32 CUDA tensor, got {x.dtype} on {x.device}')
         x = _dense4(x)
-        if (groups == 1 and tuple(stride) == (1, 1) and x.shape[1] % 4 == 0 and weight.shape[0] % 4 == 0
-                and not x.is_contiguous(memory_format=CL)):
-            x = x.contiguous(memory_format=CL)     # the tcgen05 kernels TMA-load NHWC activations
+        if groups == 1 and tuple(stride) == (1, 1) and weight.shape[0] % 4 == 0:
+            # the tcgen05 kernels TMA-load NHWC activations whose pixel stride is a multiple of 16 B
+            if x.shape[1] % 4 == 0:
+                if not x.is_contiguous(memory_format=CL):
+                    x = x.contiguous(memory_format=CL)
+            else:
+                # odd channel count (the 3-channel stem): NHWC with the pixel stride padded to 4; the
+                # pad lanes are never read (TMA bounds the channel dimension at C)
+                n_, c_, h_, w_ = x.shape
+                xp = torch.empty((n_, (c_ + 3) // 4 * 4, h_, w_), dtype=x.dtype, device=x.device, memory_format=CL)
+                xv = xp[:, :c_]
+                xv.copy_(x)
+                x = xv
         w = weight.detach().contiguous()
         p = piggymask.detach().contiguous() if piggymask is not None else None
         b = bias.detach().contiguous() if bias is not None else None
@@ -120,7 +130,7 @@ class MaskedConv2dFn(torch.autograd.Function):
         with torch.cuda.device(x.device):
             st = _lib.stream_ptr()
             if ctx.needs_input_grad[0]:
-                dx = torch.empty_like(x)  # same strides as x (dense)
+                dx = torch.empty_strided(x.shape, x.stride(), dtype=x.dtype, device=x.device)
                 _lib.check(lib.cpgb_conv2d_dgrad(d, _lib.ptr(dy), _lib.ptr(w), _lib.ptr(p), _lib.ptr(dx),
                                                  threshold, _lib.ptr(ctx.staged), _lib.ptr(ws), ws.numel(), st),
                            'cpgb_conv2d_dgrad')

@@ -30,6 +30,8 @@ CASES = [
     (128, 64, 32, 32, 64, 3, 1, 1),
     (128, 512, 4, 4, 512, 3, 1, 1),
     (128, 512, 2, 2, 512, 3, 1, 1),
+    (128, 3, 32, 32, 64, 3, 1, 1),
+    (5, 3, 20, 20, 32, 3, 1, 1),
 ]
 
 
@@ -63,6 +65,12 @@ def run(op, cases):
             m.bias.normal_()
         m.piggymask = nn.Parameter(torch.rand_like(m.weight) * 0.01)
         x = torch.randn(N, C, H, W, device=DEV).contiguous(memory_format=torch.channels_last)
+        if C % 4:
+            xp = torch.empty((N, (C + 3) // 4 * 4, H, W), device=DEV).contiguous(memory_format=torch.channels_last)
+            xp.fill_(float('nan'))      # pad lanes must never be read
+            xv = xp[:, :C]
+            xv.copy_(x)
+            x = xv
         weff = ((m.piggymask > 5e-3).float() * m.weight).detach()
         yr = F.conv2d(x, weff, m.bias, 1, pad, dil)
         dy = torch.randn_like(yr).contiguous(memory_format=torch.channels_last)
