@@ -337,7 +337,8 @@ def kernel_table(device, regime_has_piggy, iters=5):
 
     def bench_layer(kind, d, x, w, p, y, dy, t, flops, first):
         ws = torch.empty(lib.cpgb_workspace_bytes(d), dtype=torch.uint8, device=device)
-        dW, dP, dx = torch.empty_like(w), (torch.empty_like(w) if p is not None else None), torch.empty_like(x)
+        dW, dP = torch.empty_like(w), (torch.empty_like(w) if p is not None else None)
+        dx = torch.empty_strided(x.shape, x.stride(), dtype=x.dtype, device=device)
         st = _lib.stream_ptr()
         P = _lib.ptr
         nst = lib.cpgb_staged_weight_bytes(d)
@@ -358,6 +359,10 @@ def kernel_table(device, regime_has_piggy, iters=5):
 
     for i, (C, K, HW) in enumerate(shapes):
         x = torch.randn(BATCH, C, HW, HW, device=device).contiguous(memory_format=torch.channels_last)
+        if C % 4:   # the stem: NHWC with the pixel stride padded to 4, as cpg_b200.functional stores it
+            xp = torch.empty(BATCH, 4, HW, HW, device=device).contiguous(memory_format=torch.channels_last)
+            xp[:, :C].copy_(x)
+            x = xp[:, :C]
         w = torch.randn(K, C, 3, 3, device=device) * 0.05
         p = torch.rand_like(w) * 0.01 if regime_has_piggy else None
         y = torch.empty(BATCH, K, HW, HW, device=device).contiguous(memory_format=torch.channels_last)

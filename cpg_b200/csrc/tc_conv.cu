@@ -16,6 +16,7 @@
 // warps 2..5 = epilogue (tcgen05.ld -> registers -> global).  smem ring of NSTAGE stages, each
 // guarded by a full (TMA -> MMA) and an empty (tcgen05.commit -> TMA) mbarrier.
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -791,7 +792,12 @@ static WgradPlan plan_wgrad(const cpgb_conv_desc &d) {
   return pl;
 }
 static bool wgrad_fusable(const cpgb_conv_desc &d, const WgradPlan &pl) {
-  return d.R * d.S == 1 && pl.splits == 1 && d.C % 4 == 0;
+  // Measured on B200 (tests/time_ops.py, FC 4096x4096 @ batch 128): finishing the gradient inside
+  // the GEMM epilogue costs 133 us (4 epilogue warps per CTA expose the latency of the W / T loads),
+  // writing G and running the streaming epilogue kernel 75 us.  Off until the W / T tiles are
+  // prefetched into shared memory by TMA during the main loop.
+  static const bool fuse = getenv("CPGB_WGRAD_FUSE") != nullptr;
+  return fuse && d.R * d.S == 1 && pl.splits == 1 && d.C % 4 == 0;
 }
 
 size_t tc_workspace_bytes(const cpgb_conv_desc &d) {

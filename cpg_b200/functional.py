@@ -41,6 +41,59 @@ def _stage(lib, d, w, p, threshold):
     return staged, _ws(lib.cpgb_workspace_bytes(d) - nbytes, w.device)
 
 
+_SIDE_STREAMS = {}
+OVERLAP_BACKWARD = True   # run wgrad on a side stream next to dgrad (both read dy; no data dependence)
+
+
+def _side_stream(device):
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = torch.cuda.Stream(device=device)
+        _SIDE_STREAMS[key] = st
+    return st
+
+
+def _backward_kernels(lib, ctx, d, x, dy, w, p, threshold, staged, need_dx, need_w, has_bias, dx):
+    """dgrad (+) wgrad with the fused epilogue for descriptor d.  Everything is allocated on the
+    current stream; when both passes are needed the wgrad launch is forked onto a side stream and
+    joined before returning (capturable: the fork/join become parallel branches of a CUDA graph)."""
+    dW = dP = db = None
+    device = x.device
+    with torch.cuda.device(device):
+        main = torch.cuda.current_stream()
+        wbytes = lib.cpgb_workspace_bytes(d)
+        ws_d = _ws(wbytes, device) if need_dx else None
+        if need_w:
+            ws_w = _ws(wbytes, device)
+            dW = torch.empty_like(w)
+            dP = torch.empty_like(w) if p is not None else None
+            db = torch.empty(w.shape[0], dtype=torch.float32, device=device) if has_bias else None
+        fork = OVERLAP_BACKWARD and need_dx and need_w
+        if need_w:
+            wstream = main
+            if fork:
+                wstream = _side_stream(device)
+                wstream.wait_stream(main)
+            fuse = ctx.fuse
+            mode = fuse.mode if fuse is not None else _lib.GRAD_RAW
+            _lib.check(lib.cpgb_conv2d_wgrad_fused(
+                d, _lib.ptr(x), _lib.ptr(dy), _lib.ptr(w), _lib.ptr(p),
+                _lib.ptr(fuse.tmask) if fuse is not None else None,
+                fuse.cur if fuse is not None else 0, fuse.weight_decay if fuse is not None else 0.0, mode,
+                _lib.ptr(dW), _lib.ptr(dP), _lib.ptr(db), threshold, _lib.ptr(ws_w), ws_w.numel(),
+                wstream.cuda_stream), 'cpgb_conv2d_wgrad_fused')
+            if fuse is not None and ctx.module is not None:
+                ctx.module._cpg_grads_final = True
+        if need_dx:
+            _lib.check(lib.cpgb_conv2d_dgrad(d, _lib.ptr(dy), _lib.ptr(w), _lib.ptr(p), _lib.ptr(dx),
+                                             threshold, _lib.ptr(staged), _lib.ptr(ws_d), ws_d.numel(),
+                                             main.cuda_stream), 'cpgb_conv2d_dgrad')
+        if fork:
+            main.wait_stream(wstream)
+    return dW, dP, db
+
+
 class FuseCtx:
     """What the fused wgrad epilogue needs from the pruner (utils/prune.py:195-211)."""
     __slots__ = ('tmask', 'cur', 'weight_decay', 'mode')
@@ -125,29 +178,11 @@ class MaskedConv2dFn(torch.autograd.Function):
         if x.is_contiguous(memory_format=CL) and not dy.is_contiguous(memory_format=CL):
             dy = dy.contiguous(memory_format=CL)
         d = _lib.conv_desc(x.shape, x.stride(), w.shape, dy.shape, dy.stride(), stride, padding, dilation, groups)
-        ws = _ws(lib.cpgb_workspace_bytes(d), x.device)
-        dx = dW = dP = db = None
-        with torch.cuda.device(x.device):
-            st = _lib.stream_ptr()
-            if ctx.needs_input_grad[0]:
-                dx = torch.empty_strided(x.shape, x.stride(), dtype=x.dtype, device=x.device)
-                _lib.check(lib.cpgb_conv2d_dgrad(d, _lib.ptr(dy), _lib.ptr(w), _lib.ptr(p), _lib.ptr(dx),
-                                                 threshold, _lib.ptr(ctx.staged), _lib.ptr(ws), ws.numel(), st),
-                           'cpgb_conv2d_dgrad')
-            if ctx.needs_input_grad[1] or ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
-                dW = torch.empty_like(w)
-                dP = torch.empty_like(w) if p is not None else None
-                db = torch.empty(w.shape[0], dtype=torch.float32, device=x.device) if ctx.has_bias else None
-                fuse = ctx.fuse
-                mode = fuse.mode if fuse is not None else _lib.GRAD_RAW
-                _lib.check(lib.cpgb_conv2d_wgrad_fused(
-                    d, _lib.ptr(x), _lib.ptr(dy), _lib.ptr(w), _lib.ptr(p),
-                    _lib.ptr(fuse.tmask) if fuse is not None else None,
-                    fuse.cur if fuse is not None else 0, fuse.weight_decay if fuse is not None else 0.0, mode,
-                    _lib.ptr(dW), _lib.ptr(dP), _lib.ptr(db), threshold, _lib.ptr(ws), ws.numel(), st),
-                    'cpgb_conv2d_wgrad_fused')
-                if fuse is not None and ctx.module is not None:
-                    ctx.module._cpg_grads_final = True
+        need_dx = ctx.needs_input_grad[0]
+        need_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
+        dx = torch.empty_strided(x.shape, x.stride(), dtype=x.dtype, device=x.device) if need_dx else None
+        dW, dP, db = _backward_kernels(lib, ctx, d, x, dy, w, p, threshold, ctx.staged, need_dx, need_w,
+                                       ctx.has_bias, dx)
         return dx, dW, dP, db, None, None, None, None, None, None, None, None
 
 
@@ -195,30 +230,12 @@ class MaskedLinearFn(torch.autograd.Function):
         dy2 = dy.reshape(M, O).contiguous()
         d = _lib.ConvDesc()
         lib.cpgb_linear_desc(d, M, I, O)
-        ws = _ws(lib.cpgb_workspace_bytes(d), x2.device)
-        dx = dW = dP = db = None
-        with torch.cuda.device(x2.device):
-            st = _lib.stream_ptr()
-            if ctx.needs_input_grad[0]:
-                dx2 = torch.empty_like(x2)
-                _lib.check(lib.cpgb_conv2d_dgrad(d, _lib.ptr(dy2), _lib.ptr(w), _lib.ptr(p), _lib.ptr(dx2),
-                                                 ctx.threshold, _lib.ptr(ctx.staged), _lib.ptr(ws), ws.numel(), st),
-                           'cpgb_conv2d_dgrad(linear)')
-                dx = dx2.reshape(ctx.x_shape)
-            if ctx.needs_input_grad[1] or ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
-                dW = torch.empty_like(w)
-                dP = torch.empty_like(w) if p is not None else None
-                db = torch.empty(O, dtype=torch.float32, device=x2.device) if ctx.has_bias else None
-                fuse = ctx.fuse
-                mode = fuse.mode if fuse is not None else _lib.GRAD_RAW
-                _lib.check(lib.cpgb_conv2d_wgrad_fused(
-                    d, _lib.ptr(x2), _lib.ptr(dy2), _lib.ptr(w), _lib.ptr(p),
-                    _lib.ptr(fuse.tmask) if fuse is not None else None,
-                    fuse.cur if fuse is not None else 0, fuse.weight_decay if fuse is not None else 0.0, mode,
-                    _lib.ptr(dW), _lib.ptr(dP), _lib.ptr(db), ctx.threshold, _lib.ptr(ws), ws.numel(), st),
-                    'cpgb_conv2d_wgrad_fused(linear)')
-                if fuse is not None and ctx.module is not None:
-                    ctx.module._cpg_grads_final = True
+        need_dx = ctx.needs_input_grad[0]
+        need_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
+        dx2 = torch.empty_like(x2) if need_dx else None
+        dW, dP, db = _backward_kernels(lib, ctx, d, x2, dy2, w, p, ctx.threshold, ctx.staged, need_dx, need_w,
+                                       ctx.has_bias, dx2)
+        dx = dx2.reshape(ctx.x_shape) if need_dx else None
         return dx, dW, dP, db, None, None, None
 
 
