@@ -168,19 +168,83 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------
+# context arm: the reference's expressions in stock PyTorch on the same GPU (cuDNN / cuBLAS, torch
+# defaults: TF32 allowed for convs, fp32 matmul) -- what CPG runs today on a GPU ("the bar
+# to beat is torch eager + cuDNN on the same B200").  Not the oracle, not the product.
+# --------------------------------------------------------------------------------------------
+class _TorchBinarizer(torch.autograd.Function):          # models/layers.py:11-23
+    @staticmethod
+    def forward(ctx, inputs, threshold):
+        out = inputs.clone()
+        out[inputs.le(threshold)] = 0
+        out[inputs.gt(threshold)] = 1
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
+
+
+class TorchSharableConv2d(nn.Module):                    # models/layers.py:43-109
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, bias=True, **kw):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(out_channels, in_channels, kernel_size, kernel_size))
+        self.bias = nn.Parameter(torch.empty(out_channels)) if bias else None
+        self.stride, self.padding, self.piggymask = stride, padding, None
+
+    def forward(self, x):
+        w = self.weight if self.piggymask is None else _TorchBinarizer.apply(self.piggymask, 5e-3) * self.weight
+        return torch.nn.functional.conv2d(x, w, self.bias, self.stride, self.padding)
+
+
+class TorchSharableLinear(nn.Module):                    # models/layers.py:147-194
+    def __init__(self, in_features, out_features, bias=True, **kw):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(out_features, in_features))
+        self.bias = nn.Parameter(torch.empty(out_features)) if bias else None
+        self.piggymask = None
+
+    def forward(self, x):
+        w = self.weight if self.piggymask is None else _TorchBinarizer.apply(self.piggymask, 5e-3) * self.weight
+        return torch.nn.functional.linear(x, w, self.bias)
+
+
+class TorchPruner:
+    """do_weight_decay_and_make_grads_zero in stock torch ops (utils/prune.py:195-211), finetune mode."""
+
+    def __init__(self, net, masks, cur):
+        self.items = [(m, masks['module.' + n]) for n, m in net.module.named_modules()
+                      if isinstance(m, (TorchSharableConv2d, TorchSharableLinear))]
+        self.cur = cur
+
+    def do_weight_decay_and_make_grads_zero(self):
+        for m, t in self.items:
+            if m.weight.grad is not None:
+                m.weight.grad.add_(m.weight.data, alpha=WD)
+                m.weight.grad[t.ne(self.cur)] = 0
+            if m.piggymask is not None and m.piggymask.grad is not None:
+                m.piggymask.grad[t.eq(0) | t.ge(self.cur)] = 0
+
+
+# --------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------
 class Trainer:
     """The training step of utils/manager.py:54-75 over the product layers/pruner, optionally
     captured into one CUDA graph (static input buffers)."""
 
-    def __init__(self, regime, device, world, use_graph=True):
-        import cpg_b200.layers as nl
-        from cpg_b200.prune import SparsePruner
+    def __init__(self, regime, device, world, use_graph=True, impl='ours'):
         from cpg_b200.ddp import GradAllReducer
         self.device, self.world = device, world
-        self.net, self.masks, datasets, self.cur = build_model(nl.SharableConv2d, nl.SharableLinear, regime, device)
-        self.pruner = SparsePruner(self.net, self.masks, make_args(datasets), 0, 1, self.cur)
+        if impl == 'ours':
+            import cpg_b200.layers as nl
+            from cpg_b200.prune import SparsePruner
+            self.net, self.masks, datasets, self.cur = build_model(nl.SharableConv2d, nl.SharableLinear, regime, device)
+            self.pruner = SparsePruner(self.net, self.masks, make_args(datasets), 0, 1, self.cur)
+        else:
+            self.net, self.masks, datasets, self.cur = build_model(TorchSharableConv2d, TorchSharableLinear, regime,
+                                                                   device)
+            self.pruner = TorchPruner(self.net, self.masks, self.cur)
         self.opts = make_optimizers(self.net, capturable=use_graph)
         self.crit = nn.CrossEntropyLoss()
         self.reducer = GradAllReducer(self.net, world) if world > 1 else None
@@ -493,6 +557,19 @@ def main():
     extras = not args.no_extras
     r2 = run_regime('task2', True) if extras else None
 
+    def run_torch_gpu(regime, use_graph):
+        """stock-PyTorch arm on the same GPU (context only)."""
+        try:
+            tr = Trainer(regime, device, 1, use_graph=use_graph, impl='torch')
+            tr.prepare()
+            batches = [(x.to(device), t.to(device)) for x, t in synth_batches(8, BATCH, seed=100)]
+            ms, loss = timed_region(tr, batches, args.steps, args.warmup, 1)
+            del tr
+            torch.cuda.empty_cache()
+            return {'images_per_s': BATCH * args.steps / (ms * 1e-3), 'ms_per_step': ms / args.steps, 'loss': loss}
+        except Exception as ex:  # noqa: BLE001 -- context arm must never break the bench line
+            return {'error': f'{type(ex).__name__}: {ex}'[:200]}
+
     line = None
     if rank == 0:
         imgs = BATCH * world * args.steps
@@ -529,13 +606,25 @@ def main():
         rows, tot, flops, dom = kernel_table(device, regime_has_piggy=False)
         step_ms = r1['ms'] / args.steps
         achieved = flops[dom] / (tot[dom] * 1e-3) / 1e12
+        kname = {'fprop': 'conv_gemm_kernel<BN,false>', 'dgrad': 'conv_gemm_kernel<BN,true>',
+                 'wgrad': 'wgrad_gemm_kernel<BN,TG,HALO> + wgrad epilogue'}[dom]
         line['roofline'] = {
-            'bound': 'tensor', 'kernel': f'masked implicit-GEMM {dom} (all 15 sharable layers of one step)',
+            'bound': 'tensor', 'kernel': f'{kname}: masked implicit-GEMM {dom}, the 15 sharable layers of one step',
             'achieved': achieved, 'peak': tf32_peak, 'unit': 'TFLOP/s', 'frac': achieved / tf32_peak,
             'traffic': None,
-            'peak_source': 'measured in this run: cuBLAS TF32 torch.matmul 8192^3 best of 10 (TF32 is not in MEASURED_PEAKS.json)',
+            'peak_source': 'measured in this run: cuBLAS TF32 torch.matmul 8192^3 best of 10 (TF32 is not in '
+                           'MEASURED_PEAKS.json, which holds bf16 only); tcgen05 kind::tf32 issues at exactly half '
+                           'the bf16 rate (tests/mma_rate.py: 2047 MAC/clk/SM)',
             'share_of_step': tot[dom] / step_ms,
-            'how': 'CUDA events on the launching stream around each launch, L2 flushed (256 MiB write) between launches, median of 5',
+            'by_pass': {k: {'achieved_tflops': flops[k] / (tot[k] * 1e-3) / 1e12,
+                            'frac': flops[k] / (tot[k] * 1e-3) / 1e12 / tf32_peak, 'ms': tot[k]} for k in tot},
+            'best_layer': max(({'layer': r['layer'], 'pass': k, 'tflops': r['flop'] / (r[k + '_ms'] * 1e-3) / 1e12,
+                                'frac': r['flop'] / (r[k + '_ms'] * 1e-3) / 1e12 / tf32_peak}
+                               for r in rows for k in ('fprop', 'dgrad', 'wgrad') if r[k + '_ms'] > 0),
+                              key=lambda e: e['tflops']),
+            'how': 'CUDA events on the launching stream around each launch (a device-side spin hides host enqueue '
+                   'time), L2 flushed (256 MiB write) between launches, median of 5; algorithmic FLOPs = '
+                   '2*N*P*Q*K*C*R*S per layer and pass (SURVEY 8d)',
         }
         line['kernels'] = {'total_ms': tot, 'algorithmic_gflop': {k: v / 1e9 for k, v in flops.items()},
                            'conv_linear_share_of_step': sum(tot.values()) / step_ms,
@@ -543,6 +632,12 @@ def main():
                                          for r in rows]}
         line['peaks'] = {'hbm_gbs': peaks.get('hbm_gbs'), 'bf16_tflops': peaks.get('bf16_tflops'),
                          'tf32_tflops_measured_here': tf32_peak}
+        line['torch_cudnn_same_gpu'] = {
+            'what': 'the reference expressions (Binarizer*W -> F.conv2d/F.linear, utils/prune.py:195-211 in torch ops) '
+                    'in stock PyTorch on this GPU: cuDNN/cuBLAS, torch default TF32 flags, NCHW; context, not the '
+                    'graded reference arm',
+            'task1_cuda_graph': run_torch_gpu('task1', True), 'task1_eager': run_torch_gpu('task1', False),
+            'task2_cuda_graph': run_torch_gpu('task2', True)}
         cores = os.cpu_count() or 1
         total, _ = cpu_port_step_time('task1', BATCH, 3, 1, cores)
         line['cpu_baseline'] = {'value': BATCH * 3 / total, 'unit': 'images/s', 'cores': cores, 'kind': 'port',

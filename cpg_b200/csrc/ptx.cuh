@@ -134,8 +134,9 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 //   32-byte-atom 128 B swizzle (layout 1, TMA swizzle 128B_ATOM_32B): LBO = bytes between
 //   32-element MN blocks, SBO = bytes between 4-row K groups (512).
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
-                                                   uint32_t layout_type = 2) {
+                                                   uint32_t layout_type = 2, uint32_t base_offset = 0) {
   uint64_t d = 0;
+  d |= static_cast<uint64_t>(base_offset & 7) << 49;
   d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;

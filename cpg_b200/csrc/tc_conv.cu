@@ -49,7 +49,10 @@ static EncodeTiledFn get_encode() {
 // MN-major operand description (see ptx.cuh); overridable through cpgb_debug_set_mn for bring-up
 struct MnDesc { int layout, lbo, sbo, kadv, tma_swizzle; };
 static MnDesc g_mn = {1, 4096, 512, 1024, (int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B};
+static int g_halo_base_mode = 0;   // descriptor base_offset for row-shifted operands: 0 none, 1 (addr>>7)&7, 2 (addr>>7)&3
+static int g_halo_enable = 1;
 void debug_set_mn(int layout, int lbo, int sbo, int kadv, int tma_swizzle) {
+  if (layout == -1) { g_halo_base_mode = lbo; g_halo_enable = sbo; return; }   // (-1, base_mode, enable, *, *)
   g_mn = MnDesc{layout, lbo, sbo, kadv, tma_swizzle};
 }
 
@@ -205,6 +208,7 @@ struct ConvGemmParams {
   int kblocks;             // 32-wide reduction blocks per tap
   int ncols;               // valid output channels
   int iters_per_split;     // split-K over the (tap, k-block) loop; blockIdx.z = split
+  int nstage;              // depth of the smem ring (3: two CTAs share an SM; more: one CTA, deeper prefetch)
   int mn_layout, mn_lbo, mn_sbo, mn_kadv;   // MN-major operand descriptor fields
   long long o_sn, o_sh, o_sw;
   long long split_stride;  // elements between the partial outputs of consecutive splits
@@ -218,9 +222,12 @@ template <int BN, bool B_MN>
 struct ConvGemmCfg {
   static constexpr int B_TILE_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-  // narrow tiles: two CTAs per SM (one CTA's epilogue overlaps the other's main loop)
-  static constexpr int NSTAGE = BN == 256 ? 4 : BN == 128 ? 3 : 4;
-  static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align slack*/ + TAIL_BYTES;
+  // narrow tiles with >= 2 waves of CTAs: two CTAs per SM (one CTA's epilogue overlaps the other's
+  // main loop); otherwise one CTA per SM with as deep a ring as fits (the loop is latency-bound)
+  static constexpr int NSTAGE_PAIR = BN == 256 ? 4 : BN == 128 ? 3 : 4;
+  static constexpr int NSTAGE_SOLO = BN == 256 ? 4 : BN == 128 ? 6 : 8;
+  static constexpr int NSTAGE = NSTAGE_PAIR;   // minimum, for the scratch static_assert
+  static constexpr int smem_bytes(int nstage) { return nstage * STAGE_BYTES + 1024 /*align slack*/ + TAIL_BYTES; }
   static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
   static constexpr int NC = BN < 128 ? BN : 128;       // columns per epilogue pass
   static_assert(4 * 32 * (NC + 4) * 4 <= NSTAGE * STAGE_BYTES, "epilogue scratch must fit in the stage ring");
@@ -233,7 +240,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   using Cfg = ConvGemmCfg<BN, B_MN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  SmemTail *tail = reinterpret_cast<SmemTail *>(smem + Cfg::NSTAGE * Cfg::STAGE_BYTES);
+  const int NSTAGE = p.nstage;
+  SmemTail *tail = reinterpret_cast<SmemTail *>(smem + NSTAGE * Cfg::STAGE_BYTES);
   uint64_t *full = tail->full, *empty = tail->empty, *acc_full = &tail->acc_full;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -250,7 +258,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmA);
     prefetch_tensormap(&tmB);
-    for (int s = 0; s < Cfg::NSTAGE; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
@@ -276,7 +284,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tma_load_4d(sa, &tmA, full + stage, kb * 32, q0 + p.off_w + s * p.step_w, p0 + p.off_h + r * p.step_h, n0);
         if (!B_MN) tma_load_3d(sb, &tmB, full + stage, kb * 32, t, col0);               // [BN k][32 c]
         else       tma_load_4d(sb, &tmB, full + stage, 0, kb * 32, t, col0 >> 5);       // [BN/32][32 k][32 c]
-        if (++stage == Cfg::NSTAGE) { stage = 0; phase ^= 1; }
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -296,7 +304,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mma_tf32_ss(tmem_base, ad, bd, idesc, (it > it_beg) | (ks != 0));
         }
         mma_commit(empty + stage);
-        if (++stage == Cfg::NSTAGE) { stage = 0; phase ^= 1; }
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
       }
       mma_commit(acc_full);
     }
@@ -382,6 +390,12 @@ struct WgradParams {
   int K, C, Cg;            // Cg = C rounded up to 4: row stride of gpart
   int mn_layout, mn_lbo, mn_sbo, mn_kadv;
   float *gpart;            // [splits][K][RS][Cg]
+  // halo mode (HALO = true): one X tile per stage serves the S taps of a filter row
+  int h_pitch;             // bytes between the 32-channel blocks of the X tile (multiple of 512)
+  int h_box_bytes;         // bytes one X-block TMA box delivers
+  int h_stage_bytes, h_nstage;
+  int h_krow[4];           // first X-tile row of each 8-pixel K step (tap 0)
+  int h_base_mode;
   // fused epilogue (only RS == 1, one split): SURVEY K6-K8 applied straight from TMEM
   int fused, cur, mode;
   float wd, thr;
@@ -406,14 +420,16 @@ struct WgradCfg {
 
 // grid: x = ktiles * ctiles, y = tap groups (R groups of TG = S taps, or R*S groups of one tap),
 // z = splits.  One CTA accumulates TG taps for a 128(k) x BN(c) tile over its pixel chunks.
-template <int BN, int TG>
+template <int BN, int TG, bool HALO>
 __global__ void __launch_bounds__(192)
 wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
                   const WgradParams p) {
   using Cfg = WgradCfg<BN, TG>;
+  const int NSTAGE = HALO ? p.h_nstage : Cfg::NSTAGE;
+  const int STAGE_BYTES = HALO ? p.h_stage_bytes : Cfg::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  SmemTail *tail = reinterpret_cast<SmemTail *>(smem + Cfg::NSTAGE * Cfg::STAGE_BYTES);
+  SmemTail *tail = reinterpret_cast<SmemTail *>(smem + NSTAGE * STAGE_BYTES);
   uint64_t *full = tail->full, *empty = tail->empty, *acc_full = &tail->acc_full;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -429,7 +445,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmDY);
     prefetch_tensormap(&tmX);
-    for (int s = 0; s < Cfg::NSTAGE; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
@@ -451,14 +467,24 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
         const int cpi = ch % p.cp; ch /= p.cp;
         const int q0 = cqi << p.lq, p0 = cpi << p.lp, n0 = ch << (5 - p.lq - p.lp);
         mbar_wait(empty + stage, phase ^ 1);
-        uint8_t *sa = smem + stage * Cfg::STAGE_BYTES;
-        mbar_arrive_expect_tx(full + stage, Cfg::STAGE_BYTES);
-        tma_load_5d(sa, &tmDY, full + stage, 0, q0, p0, n0, k0 >> 5);
+        uint8_t *sa = smem + stage * STAGE_BYTES;
+        if (HALO) {
+          // one X tile with (S-1)*dil extra columns per block; the taps are row offsets into it
+          mbar_arrive_expect_tx(full + stage, Cfg::A_BYTES + (BN / 32) * p.h_box_bytes);
+          tma_load_5d(sa, &tmDY, full + stage, 0, q0, p0, n0, k0 >> 5);
 #pragma unroll
-        for (int s = 0; s < TG; ++s)
-          tma_load_5d(sa + Cfg::A_BYTES + s * Cfg::B_BYTES, &tmX, full + stage, 0,
-                      q0 - p.pad_w + (s0 + s) * p.dil_w, p0 - p.pad_h + r * p.dil_h, n0, c0 >> 5);
-        if (++stage == Cfg::NSTAGE) { stage = 0; phase ^= 1; }
+          for (int b = 0; b < BN / 32; ++b)
+            tma_load_5d(sa + Cfg::A_BYTES + b * p.h_pitch, &tmX, full + stage, 0, q0 - p.pad_w,
+                        p0 - p.pad_h + r * p.dil_h, n0, (c0 >> 5) + b);
+        } else {
+          mbar_arrive_expect_tx(full + stage, Cfg::STAGE_BYTES);
+          tma_load_5d(sa, &tmDY, full + stage, 0, q0, p0, n0, k0 >> 5);
+#pragma unroll
+          for (int s = 0; s < TG; ++s)
+            tma_load_5d(sa + Cfg::A_BYTES + s * Cfg::B_BYTES, &tmX, full + stage, 0,
+                        q0 - p.pad_w + (s0 + s) * p.dil_w, p0 - p.pad_h + r * p.dil_h, n0, c0 >> 5);
+        }
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -468,19 +494,25 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
       for (int it = 0; it < iters; ++it) {
         mbar_wait(full + stage, phase);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
 #pragma unroll
         for (int s = 0; s < TG; ++s) {
-          const uint32_t sb = sa + Cfg::A_BYTES + s * Cfg::B_BYTES;
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint64_t ad = make_smem_desc(sa + ks * p.mn_kadv, p.mn_lbo, p.mn_sbo, p.mn_layout);
-            const uint64_t bd = make_smem_desc(sb + ks * p.mn_kadv, p.mn_lbo, p.mn_sbo, p.mn_layout);
+            uint64_t bd;
+            if (HALO) {
+              const uint32_t baddr = sa + Cfg::A_BYTES + (p.h_krow[ks] + s * p.dil_w) * 128;
+              const uint32_t bo = p.h_base_mode == 1 ? (baddr >> 7) & 7 : p.h_base_mode == 2 ? (baddr >> 7) & 3 : 0;
+              bd = make_smem_desc(baddr, p.h_pitch, p.mn_sbo, p.mn_layout, bo);
+            } else {
+              bd = make_smem_desc(sa + Cfg::A_BYTES + s * Cfg::B_BYTES + ks * p.mn_kadv, p.mn_lbo, p.mn_sbo, p.mn_layout);
+            }
             mma_tf32_ss(tmem_base + s * BN, ad, bd, idesc, (it | ks) != 0);
           }
         }
         mma_commit(empty + stage);
-        if (++stage == Cfg::NSTAGE) { stage = 0; phase ^= 1; }
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
       }
       mma_commit(acc_full);
     }
@@ -770,7 +802,7 @@ static size_t plan_partial_bytes(const GemmPlan &g) {
 }
 
 // ---- wgrad plan ------------------------------------------------------------------------------
-struct WgradPlan { int BN, TG, groups, ctiles, ktiles, splits, chunks, cps; PixBox box; };
+struct WgradPlan { int BN, TG, groups, ctiles, ktiles, splits, chunks, cps; PixBox box; bool halo; };
 static WgradPlan plan_wgrad(const cpgb_conv_desc &d) {
   WgradPlan pl;
   pl.BN = d.C >= 128 ? 128 : 64;
@@ -781,10 +813,16 @@ static WgradPlan plan_wgrad(const cpgb_conv_desc &d) {
   const int RS = d.R * d.S, sms = num_sms();
   // Few pixel chunks: one CTA per tap (no split-K traffic).  Many: the S taps of a filter row share
   // the dY tile of every chunk (TG = S accumulators) and the chunk range is split.
-  pl.TG = (d.S == 3 && pl.ctiles * pl.ktiles * RS * 2 > sms && pl.chunks <= 256) ? 1 : d.S;
+  // Halo mode: chunks made of whole 8-pixel runs of an image row, filter width 3 -> the three taps of
+  // a filter row are row offsets into ONE X tile (loaded with (S-1)*dil extra columns).
+  pl.halo = g_halo_enable && d.S == 3 && (1 << pl.box.lq) >= 8 && (1 << pl.box.lq) + 2 * d.dil_w <= 256;
+  pl.TG = pl.halo ? 3 : (d.S == 3 && pl.ctiles * pl.ktiles * RS * 2 > sms && pl.chunks <= 256) ? 1 : d.S;
   pl.groups = RS / pl.TG;
   const int base = pl.ctiles * pl.ktiles * pl.groups;
-  int splits = cdiv_i(sms * 3 / 2, base);
+  // fill exactly one wave: TG = 3 CTAs own 384 TMEM columns and ~200 KB of smem (one per SM), TG = 1
+  // CTAs fit two per SM
+  const int target = pl.TG == 1 ? 2 * sms : sms;
+  int splits = target / base;
   if (splits > pl.chunks / 4) splits = pl.chunks / 4;
   if (splits < 1) splits = 1;
   pl.cps = cdiv_i(pl.chunks, splits);
@@ -835,17 +873,19 @@ int tc_stage_weights(const cpgb_conv_desc &d, const float *w, const float *piggy
 }
 
 template <int BN, bool B_MN>
-static int launch_conv_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const ConvGemmParams &p, int ntiles_n,
+static int launch_conv_gemm(const CUtensorMap &ta, const CUtensorMap &tb, ConvGemmParams &p, int ntiles_n,
                             int splits, cudaStream_t st) {
   using Cfg = ConvGemmCfg<BN, B_MN>;
   static bool attr_done = false;
   if (!attr_done) {
     CPGB_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<BN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      Cfg::SMEM_BYTES));
+                                      Cfg::smem_bytes(Cfg::NSTAGE_SOLO)));
     attr_done = true;
   }
   dim3 grid(p.tq * p.tp * p.tn, ntiles_n, splits);
-  conv_gemm_kernel<BN, B_MN><<<grid, 192, Cfg::SMEM_BYTES, st>>>(ta, tb, p);
+  const long long ctas = (long long)grid.x * grid.y * grid.z;
+  p.nstage = ctas > num_sms() ? Cfg::NSTAGE_PAIR : Cfg::NSTAGE_SOLO;   // solo only when no SM gets two CTAs anyway
+  conv_gemm_kernel<BN, B_MN><<<grid, 192, Cfg::smem_bytes(p.nstage), st>>>(ta, tb, p);
   CPGB_LAUNCH_OK("conv_gemm_kernel");
   return CPGB_OK;
 }
@@ -939,17 +979,18 @@ int tc_dgrad(const cpgb_conv_desc &d, const float *dy, const float *staged, floa
   return run_gemm<true>(g, ta, tb, p, dx, nullptr, part, part_bytes, st);
 }
 
-template <int BN, int TG>
+template <int BN, int TG, bool HALO>
 static int launch_wgrad(const CUtensorMap &tdy, const CUtensorMap &tx, const WgradParams &p, dim3 grid,
                         cudaStream_t st) {
   using Cfg = WgradCfg<BN, TG>;
+  const int smem_bytes = HALO ? p.h_nstage * p.h_stage_bytes + 1024 + TAIL_BYTES : Cfg::SMEM_BYTES;
   static bool attr_done = false;
   if (!attr_done) {
-    CPGB_CUDA_OK(cudaFuncSetAttribute(wgrad_gemm_kernel<BN, TG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      Cfg::SMEM_BYTES));
+    CPGB_CUDA_OK(cudaFuncSetAttribute(wgrad_gemm_kernel<BN, TG, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      HALO ? 227 * 1024 : Cfg::SMEM_BYTES));
     attr_done = true;
   }
-  wgrad_gemm_kernel<BN, TG><<<grid, 192, Cfg::SMEM_BYTES, st>>>(tdy, tx, p);
+  wgrad_gemm_kernel<BN, TG, HALO><<<grid, 192, smem_bytes, st>>>(tdy, tx, p);
   CPGB_LAUNCH_OK("wgrad_gemm_kernel");
   return CPGB_OK;
 }
@@ -980,8 +1021,31 @@ int tc_wgrad_fused(const cpgb_conv_desc &d, const float *x, const float *dy, con
   CUtensorMap tdy, tx;
   int rc;
   if ((rc = make_act_map5(&tdy, dy, d.K, d.Q, d.P, d.N, y_strides(d), pl.box, 4))) return rc;
-  if ((rc = make_act_map5(&tx, x, d.C, d.W, d.H, d.N, x_strides(d), pl.box, pl.BN / 32))) return rc;
   WgradParams p;
+  if (pl.halo) {
+    const int bq = 1 << pl.box.lq, bp = 1 << pl.box.lp, bn = 1 << pl.box.ln;
+    const int wq = bq + (d.S - 1) * d.dil_w;           // X-tile columns per image row
+    const int rows = bn * bp * wq;
+    const int rows_p = (rows + 3) & ~3;                // block pitch: whole 4-row swizzle atoms
+    p.h_pitch = rows_p * 128; p.h_box_bytes = rows * 128;
+    p.h_stage_bytes = (int)align_up((size_t)16384 + (pl.BN / 32) * p.h_pitch, 1024);
+    p.h_nstage = std::min(8, (224 * 1024 - 1024 - TAIL_BYTES) / p.h_stage_bytes);
+    for (int ks = 0; ks < 4; ++ks) {
+      const int pix = 8 * ks, qo = pix % bq, pi = (pix / bq) % bp, ni = pix / (bq * bp);
+      p.h_krow[ks] = (ni * bp + pi) * wq + qo;
+    }
+    p.h_base_mode = g_halo_base_mode;
+    const Str4 xs = x_strides(d);
+    uint64_t dims[5] = {(uint64_t)(d.C < 32 ? d.C : 32), (uint64_t)d.W, (uint64_t)d.H, (uint64_t)d.N,
+                        (uint64_t)((d.C + 31) / 32)};
+    uint64_t str[4] = {(uint64_t)xs.s[3] * 4, (uint64_t)xs.s[2] * 4, (uint64_t)xs.s[0] * 4, 128};
+    uint32_t box[5] = {32, (uint32_t)wq, (uint32_t)bp, (uint32_t)bn, 1};
+    if ((rc = make_map(&tx, x, 5, dims, str, box, true))) return rc;
+  } else {
+    p.h_pitch = p.h_box_bytes = p.h_stage_bytes = p.h_nstage = p.h_base_mode = 0;
+    for (int ks = 0; ks < 4; ++ks) p.h_krow[ks] = 0;
+    if ((rc = make_act_map5(&tx, x, d.C, d.W, d.H, d.N, x_strides(d), pl.box, pl.BN / 32))) return rc;
+  }
   p.cq = pl.box.tq; p.cp = pl.box.tp; p.cn = pl.box.tn; p.lq = pl.box.lq; p.lp = pl.box.lp;
   p.S = d.S; p.RS = RS; p.pad_h = d.pad_h; p.pad_w = d.pad_w; p.dil_h = d.dil_h; p.dil_w = d.dil_w;
   p.chunks = pl.chunks; p.chunks_per_split = pl.cps; p.ctiles = pl.ctiles; p.K = d.K; p.C = d.C; p.Cg = cg_of(d);
@@ -990,10 +1054,12 @@ int tc_wgrad_fused(const cpgb_conv_desc &d, const float *x, const float *dy, con
   p.fused = fused ? 1 : 0; p.cur = cur; p.mode = mode; p.wd = wd; p.thr = thr;
   p.w = w; p.piggy = piggy; p.tmask = tmask; p.dW = dW; p.dP = dP;
   dim3 grid(pl.ktiles * pl.ctiles, pl.groups, pl.splits);
-  if (pl.TG == 3) {
-    rc = pl.BN == 128 ? launch_wgrad<128, 3>(tdy, tx, p, grid, st) : launch_wgrad<64, 3>(tdy, tx, p, grid, st);
+  if (pl.halo) {
+    rc = pl.BN == 128 ? launch_wgrad<128, 3, true>(tdy, tx, p, grid, st) : launch_wgrad<64, 3, true>(tdy, tx, p, grid, st);
+  } else if (pl.TG == 3) {
+    rc = pl.BN == 128 ? launch_wgrad<128, 3, false>(tdy, tx, p, grid, st) : launch_wgrad<64, 3, false>(tdy, tx, p, grid, st);
   } else {
-    rc = pl.BN == 128 ? launch_wgrad<128, 1>(tdy, tx, p, grid, st) : launch_wgrad<64, 1>(tdy, tx, p, grid, st);
+    rc = pl.BN == 128 ? launch_wgrad<128, 1, false>(tdy, tx, p, grid, st) : launch_wgrad<64, 1, false>(tdy, tx, p, grid, st);
   }
   if (rc || fused) return rc;
   if (RS == 1 && vec_ok && d.C % 4 == 0) {
@@ -1038,3 +1104,59 @@ int tc_wgrad_fused(const cpgb_conv_desc &d, const float *x, const float *dy, con
 }
 
 }  // namespace cpgb
+
+// ------------------------------------------------------------------------------------------
+// bring-up microbenchmark: issue rate of tcgen05.mma kind::tf32 M=128 for the operand layouts the
+// kernels use (no loads: descriptors point at whatever is in shared memory).
+// ------------------------------------------------------------------------------------------
+namespace cpgb {
+template <int BN>
+__global__ void __launch_bounds__(128) mma_rate_kernel(int a_mn, int b_mn, int iters, long long *out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < (16384 + BN * 128) / 4; i += blockDim.x) reinterpret_cast<float *>(smem)[i] = 1.0f;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (warp == 0) { tmem_alloc(&slot, BN < 32 ? 32 : BN); tmem_relinquish(); }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = slot;
+  if (warp == 0 && lane == 0) {
+    const uint32_t sa = smem_u32(smem), sb = sa + 16384;
+    const uint32_t idesc = make_idesc_tf32(128, BN, a_mn != 0, b_mn != 0);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint64_t ad = a_mn ? make_smem_desc(sa + ks * 1024, 4096, 512, 1) : make_smem_desc(sa + ks * 32, 16, 1024);
+        const uint64_t bd = b_mn ? make_smem_desc(sb + ks * 1024, 4096, 512, 1) : make_smem_desc(sb + ks * 32, 16, 1024);
+        mma_tf32_ss(tmem, ad, bd, idesc, (it | ks) != 0);
+      }
+    }
+    mma_commit(&bar);
+    mbar_wait(&bar, 0);
+    const long long t1 = clock64();
+    if (blockIdx.x == 0) out[0] = t1 - t0;
+  }
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, BN < 32 ? 32 : BN); }
+}
+}  // namespace cpgb
+
+extern "C" int cpgb_debug_mma_rate(int bn, int a_mn, int b_mn, int iters, int grid, long long *out_dev, void *stream) {
+  using namespace cpgb;
+  const int smem = 16384 + bn * 128 + 1024;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (bn == 64) { cudaFuncSetAttribute(mma_rate_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                  mma_rate_kernel<64><<<grid, 128, smem, st>>>(a_mn, b_mn, iters, out_dev); }
+  else if (bn == 128) { cudaFuncSetAttribute(mma_rate_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                  mma_rate_kernel<128><<<grid, 128, smem, st>>>(a_mn, b_mn, iters, out_dev); }
+  else { cudaFuncSetAttribute(mma_rate_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                  mma_rate_kernel<256><<<grid, 128, smem, st>>>(a_mn, b_mn, iters, out_dev); }
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -3;
+}
