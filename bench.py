@@ -451,6 +451,39 @@ def kernel_table(device, regime_has_piggy, iters=5):
     return rows, tot, flops, dom
 
 
+def prune_table(device, iters=5):
+    """a7 on the device: one prune event (utils/prune.py:78-92 -> _pruning_mask per layer) over the 15
+    sharable layers of VGG16 (33.6 M weights), CUDA events, L2 flushed.  Algorithmic bytes = one pass:
+    read W 4 B + T 1 B, write T 1 B per element; the 3-digit radix select reads W and T four
+    times, which is what `passes` says."""
+    import cpg_b200.layers as nl
+    from cpg_b200.prune import SparsePruner
+    net, masks, datasets, cur = build_model(nl.SharableConv2d, nl.SharableLinear, 'task1', device)
+    args = make_args(datasets, mode='prune')
+    args.target_sparsity, args.initial_sparsity, args.pruning_frequency = 0.5, 0.0, 1
+    pruner = SparsePruner(net, masks, args, 0, 10 ** 6, cur)
+    n = sum(m.numel() for m in masks.values())
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    ts = []
+    for i in range(iters + 2):
+        for m in masks.values():
+            m.fill_(cur)
+        flush.zero_()
+        torch.cuda._sleep(4000000)     # ~2 ms head start: 105 launches are enqueued before the GPU gets to them
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        pruner.last_prune_step = -10
+        pruner.gradually_prune(1000 + i)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            ts.append(e0.elapsed_time(e1))
+    ms = statistics.median(ts)
+    zeros = sum(int((m == 0).sum()) for m in masks.values())
+    return {'ms_per_prune_event': ms, 'elements': n, 'algorithmic_bytes': 6 * n, 'passes': 4,
+            'achieved_gbs_algorithmic': 6 * n / (ms * 1e-3) / 1e9, 'pruned_fraction_check': zeros / n}
+
+
 def cpu_port_step_time(regime, batch, steps, warmup, threads):
     """The reference's CPU path (oracle port: OracleSharable* layers + OraclePruner), same step
     sequence, on `threads` host cores."""
@@ -632,6 +665,12 @@ def main():
                                          for r in rows]}
         line['peaks'] = {'hbm_gbs': peaks.get('hbm_gbs'), 'bf16_tflops': peaks.get('bf16_tflops'),
                          'tf32_tflops_measured_here': tf32_peak}
+        try:
+            pt = prune_table(device)
+            pt['frac_of_hbm_peak'] = pt['achieved_gbs_algorithmic'] / peaks['hbm_gbs'] if peaks.get('hbm_gbs') else None
+            line['prune_event'] = pt
+        except Exception as ex:  # noqa: BLE001
+            line['prune_event'] = {'error': f'{type(ex).__name__}: {ex}'[:200]}
         line['torch_cudnn_same_gpu'] = {
             'what': 'the reference expressions (Binarizer*W -> F.conv2d/F.linear, utils/prune.py:195-211 in torch ops) '
                     'in stock PyTorch on this GPU: cuDNN/cuBLAS, torch default TF32 flags, NCHW; context, not the '

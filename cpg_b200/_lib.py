@@ -15,6 +15,7 @@ EXPORTS = [
     'cpgb_version', 'cpgb_last_error', 'cpgb_set_path', 'cpgb_get_path', 'cpgb_launch_count', 'cpgb_linear_desc',
     'cpgb_workspace_bytes', 'cpgb_staged_weight_bytes', 'cpgb_stage_weights', 'cpgb_binarize', 'cpgb_conv2d_fprop', 'cpgb_conv2d_dgrad',
     'cpgb_conv2d_wgrad_fused', 'cpgb_grad_epilogue', 'cpgb_prune_workspace_bytes', 'cpgb_prune_select',
+    'cpgb_prune_batched_workspace_bytes', 'cpgb_prune_select_batched',
     'cpgb_apply_mask', 'cpgb_make_finetuning_mask', 'cpgb_mask_stats', 'cpgb_merge_grads',
     'cpgb_split_merged_grad',
 ]
@@ -63,6 +64,9 @@ def load():
         'cpgb_grad_epilogue': (ctypes.c_int, [vp, vp, vp, vp, i64, i32, f32, i32, vp]),
         'cpgb_prune_workspace_bytes': (sz, []),
         'cpgb_prune_select': (ctypes.c_int, [vp, vp, i64, i32, dbl, vp, vp, sz, vp]),
+        'cpgb_prune_batched_workspace_bytes': (sz, [i32]),
+        'cpgb_prune_select_batched': (ctypes.c_int, [i32, ctypes.POINTER(vp), ctypes.POINTER(vp),
+                                                     ctypes.POINTER(i64), i32, dbl, vp, vp, sz, vp]),
         'cpgb_apply_mask': (ctypes.c_int, [vp, vp, i64, i32, vp]),
         'cpgb_make_finetuning_mask': (ctypes.c_int, [vp, i64, i32, vp]),
         'cpgb_mask_stats': (ctypes.c_int, [vp, vp, i64, i32, vp, vp]),

@@ -107,6 +107,24 @@ class SparsePruner(object):
                                              _lib.ptr(info), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
                        'cpgb_prune_select')
 
+    def _launch_prune_batched(self, layers, pruning_ratio, infos):
+        import ctypes
+        lib = _lib.load()
+        nl_ = len(layers)
+        dev = layers[0][1].weight.device
+        W = (ctypes.c_void_p * nl_)(*[_lib.ptr(self._dense(m.weight.data, 'weight')) for _, m in layers])
+        T = (ctypes.c_void_p * nl_)(*[_lib.ptr(self._mask(n)) for n, _ in layers])
+        N = (ctypes.c_int64 * nl_)(*[m.weight.numel() for _, m in layers])
+        nbytes = lib.cpgb_prune_batched_workspace_bytes(nl_)
+        key = ('batched', str(dev), nbytes)
+        if key not in self._prune_ws:
+            self._prune_ws[key] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        ws = self._prune_ws[key]
+        with torch.cuda.device(dev):
+            _lib.check(lib.cpgb_prune_select_batched(nl_, W, T, N, self.current_dataset_idx, float(pruning_ratio),
+                                                     _lib.ptr(infos), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+                       'cpgb_prune_select_batched')
+
     @staticmethod
     def _exit_not_enough():
         print("Not enough weights for pruning, that is to say, too little space for new task, need expand the network.")
@@ -148,9 +166,10 @@ class SparsePruner(object):
             if layers:
                 dev = layers[0][1].weight.device
                 infos = torch.zeros(len(layers), 4, dtype=torch.int64, device=dev)
-                for i, (name, module) in enumerate(layers):
-                    self._launch_prune(module.weight.data, self._mask(name), curr_pruning_ratio, infos[i])
-                    # pruned weights are NOT zeroed here (utils/prune.py:88 is commented out)
+                # all layers in one batched call (7 launches per 64 layers); pruned weights are NOT
+                # zeroed here (utils/prune.py:88 is commented out)
+                for lo in range(0, len(layers), 64):
+                    self._launch_prune_batched(layers[lo:lo + 64], curr_pruning_ratio, infos[lo:lo + 64])
                 if bool((infos[:, 0] != 0).any().item()):   # one read-back per prune event
                     self._exit_not_enough()
         else:

@@ -126,6 +126,14 @@ size_t cpgb_prune_workspace_bytes(void);
 int cpgb_prune_select(const float *w, uint8_t *tmask, int64_t n, int32_t cur, double ratio,
                       int64_t *info, void *ws, size_t ws_bytes, void *stream);
 
+/* a7 for every sharable layer of the model in one call (what gradually_prune does at
+ * utils/prune.py:84-90): seven launches in total instead of seven per layer.  w / tmask / n are HOST
+ * arrays of nlayers (<= 64) device pointers / element counts; info is device [nlayers][4] with the
+ * per-layer meaning of cpgb_prune_select; ws: cpgb_prune_batched_workspace_bytes(nlayers). */
+size_t cpgb_prune_batched_workspace_bytes(int32_t nlayers);
+int cpgb_prune_select_batched(int32_t nlayers, const float *const *w, uint8_t *const *tmask, const int64_t *n,
+                              int32_t cur, double ratio, int64_t *info, void *ws, size_t ws_bytes, void *stream);
+
 /* a9: apply_mask (utils/prune.py:223-231): w[T==0]=0; w[T>inference_idx]=0.
  *     make_pruned_zero (utils/prune.py:213-221): pass inference_idx = 255. */
 int cpgb_apply_mask(float *w, const uint8_t *tmask, int64_t n, int32_t inference_idx, void *stream);

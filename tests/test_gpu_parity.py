@@ -161,6 +161,46 @@ def test_a7_prune_golden_bit_exact(golden):
                 assert np.array_equal(out.cpu().numpy(), g[f'a7_{i}_T_{k}']), (ratio, name)
 
 
+def test_prune_batched_equals_per_layer_and_oracle():
+    """cpgb_prune_select_batched (all layers, 7 launches) == cpgb_prune_select per layer == oracle,
+    on ragged layer sizes (odd lengths, one tiny layer, one exit-2 layer)."""
+    import ctypes
+    lib = _lib.load()
+    rng = np.random.RandomState(5)
+    sizes = [1, 7, 1000, 4099, 36864, 262145, 1 << 20]
+    ws_, ts_ = [], []
+    for n in sizes:
+        ws_.append(rng.standard_normal(n).astype(np.float32))
+        ts_.append(rng.randint(0, 4, size=n).astype(np.uint8))
+    ts_[1][:] = 1                                   # no prunable pool for cur = 2 -> exit-2 path, untouched
+    cur, ratio = 2, 0.37
+    wg = [G(w) for w in ws_]
+    tb = [G(t.copy()) for t in ts_]
+    ts1 = [G(t.copy()) for t in ts_]
+    nl_ = len(sizes)
+    info_b = torch.zeros(nl_, 4, dtype=torch.int64, device=DEV)
+    W = (ctypes.c_void_p * nl_)(*[t.data_ptr() for t in wg])
+    T = (ctypes.c_void_p * nl_)(*[t.data_ptr() for t in tb])
+    N = (ctypes.c_int64 * nl_)(*sizes)
+    wsb = torch.empty(lib.cpgb_prune_batched_workspace_bytes(nl_), dtype=torch.uint8, device=DEV)
+    _lib.check(lib.cpgb_prune_select_batched(nl_, W, T, N, cur, ratio, info_b.data_ptr(), wsb.data_ptr(), wsb.numel(),
+                                             _lib.stream_ptr()), 'batched')
+    ws1 = torch.empty(lib.cpgb_prune_workspace_bytes(), dtype=torch.uint8, device=DEV)
+    for i in range(nl_):
+        info = torch.zeros(4, dtype=torch.int64, device=DEV)
+        _lib.check(lib.cpgb_prune_select(wg[i].data_ptr(), ts1[i].data_ptr(), sizes[i], cur, ratio, info.data_ptr(),
+                                         ws1.data_ptr(), ws1.numel(), _lib.stream_ptr()), 'single')
+        assert torch.equal(info, info_b[i]), (i, info, info_b[i])
+        assert torch.equal(ts1[i], tb[i]), i
+        tt = torch.from_numpy(ts_[i].copy())
+        try:
+            O.pruning_mask(torch.from_numpy(ws_[i]), tt, cur, ratio)
+            assert int(info[0]) == 0
+        except O.NotEnoughWeights:
+            assert int(info[0]) == 2
+        assert np.array_equal(tb[i].cpu().numpy(), tt.numpy()), i
+
+
 def test_a8_schedule_golden(golden):
     g = golden('pruner')
     model, pr, masks = load_toy(g, nl, cpg_prune, 'prune', DEV)
