@@ -17,6 +17,7 @@
 // guarded by a full (TMA -> MMA) and an empty (tcgen05.commit -> TMA) mbarrier.
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 
 #include "common.cuh"
@@ -734,7 +735,7 @@ static Str4 y_strides(const cpgb_conv_desc &d) { return norm_strides(d.ys, d.K, 
 // count itself may be odd, e.g. the 3-channel stem stored with a pixel stride of 4), K % 4 == 0
 // for vector stores; dgrad additionally C % 4 == 0; wgrad K % 32 == 0, C % 32 == 0 or C < 32,
 // filter width 1 or 3.
-bool tc_eligible(const cpgb_conv_desc &d, int op) {
+static bool implicit_eligible(const cpgb_conv_desc &d, int op) {
   if (d.groups != 1 || d.stride_h != 1 || d.stride_w != 1) return false;
   if (d.K % 4) return false;
   if (d.R * d.S > 49 || d.N < 1) return false;
@@ -751,7 +752,7 @@ static inline int cg_of(const cpgb_conv_desc &d) { return (d.C + 3) & ~3; }   //
 
 static inline int cp_of(const cpgb_conv_desc &d) { return (d.C + 31) / 32 * 32; }
 
-size_t tc_staged_bytes(const cpgb_conv_desc &d) {
+static size_t implicit_staged_bytes(const cpgb_conv_desc &d) {
   return align_up((size_t)d.K * d.R * d.S * cp_of(d) * sizeof(float) + 256, 256);
 }
 
@@ -838,13 +839,13 @@ static bool wgrad_fusable(const cpgb_conv_desc &d, const WgradPlan &pl) {
   return fuse && d.R * d.S == 1 && pl.splits == 1 && d.C % 4 == 0;
 }
 
-size_t tc_workspace_bytes(const cpgb_conv_desc &d) {
+static size_t implicit_workspace_bytes(const cpgb_conv_desc &d) {
   if (d.groups <= 0) return 0;
   size_t staged = 0, b = 0;
-  if (tc_eligible(d, 0) || tc_eligible(d, 1)) staged = tc_staged_bytes(d);
-  if (tc_eligible(d, 0)) b = std::max(b, plan_partial_bytes(plan_fprop(d)));
-  if (tc_eligible(d, 1)) b = std::max(b, plan_partial_bytes(plan_dgrad(d)));
-  if (tc_eligible(d, 2)) {
+  if (implicit_eligible(d, 0) || implicit_eligible(d, 1)) staged = implicit_staged_bytes(d);
+  if (implicit_eligible(d, 0)) b = std::max(b, plan_partial_bytes(plan_fprop(d)));
+  if (implicit_eligible(d, 1)) b = std::max(b, plan_partial_bytes(plan_dgrad(d)));
+  if (implicit_eligible(d, 2)) {
     WgradPlan pl = plan_wgrad(d);
     if (!wgrad_fusable(d, pl)) b = std::max(b, (size_t)pl.splits * d.K * d.R * d.S * cg_of(d) * sizeof(float));
   }
@@ -852,9 +853,9 @@ size_t tc_workspace_bytes(const cpgb_conv_desc &d) {
   return staged + align_up(b, 256) + 256;
 }
 
-int tc_stage_weights(const cpgb_conv_desc &d, const float *w, const float *piggy, float thr, void *staged,
-                     size_t bytes, cudaStream_t st) {
-  if (bytes < tc_staged_bytes(d)) { set_error("staged-weight buffer %zu < %zu", bytes, tc_staged_bytes(d)); return CPGB_EWORKSPACE; }
+static int implicit_stage_weights(const cpgb_conv_desc &d, const float *w, const float *piggy, float thr, void *staged,
+                                  size_t bytes, cudaStream_t st) {
+  if (bytes < implicit_staged_bytes(d)) { set_error("staged-weight buffer %zu < %zu", bytes, implicit_staged_bytes(d)); return CPGB_EWORKSPACE; }
   const int RS = d.R * d.S, Cp = cp_of(d);
   if (RS == 1 && Cp == d.C && aligned16p(w) && aligned16p(staged) && (!piggy || aligned16p(piggy))) {
     const long long n4 = (long long)d.K * d.C / 4;
@@ -929,8 +930,8 @@ static int run_gemm(const GemmPlan &g, const CUtensorMap &ta, const CUtensorMap 
   return CPGB_OK;
 }
 
-int tc_fprop(const cpgb_conv_desc &d, const float *x, const float *staged, const float *bias, float *y, void *part,
-             size_t part_bytes, cudaStream_t st) {
+static int implicit_fprop(const cpgb_conv_desc &d, const float *x, const float *staged, const float *bias, float *y,
+                          void *part, size_t part_bytes, cudaStream_t st) {
   if (!aligned16p(x) || !aligned16p(y) || !aligned16p(staged) || (bias && !aligned16p(bias)) || !aligned16p(part)) {
     set_error("tcgen05 path needs 16-byte aligned tensors"); return CPGB_EINVAL;
   }
@@ -953,8 +954,8 @@ int tc_fprop(const cpgb_conv_desc &d, const float *x, const float *staged, const
   return run_gemm<false>(g, ta, tb, p, y, bias, part, part_bytes, st);
 }
 
-int tc_dgrad(const cpgb_conv_desc &d, const float *dy, const float *staged, float *dx, void *part, size_t part_bytes,
-             cudaStream_t st) {
+static int implicit_dgrad(const cpgb_conv_desc &d, const float *dy, const float *staged, float *dx, void *part,
+                          size_t part_bytes, cudaStream_t st) {
   if (!aligned16p(dy) || !aligned16p(dx) || !aligned16p(staged) || !aligned16p(part)) {
     set_error("tcgen05 path needs 16-byte aligned tensors"); return CPGB_EINVAL;
   }
@@ -1005,9 +1006,9 @@ static int make_act_map5(CUtensorMap *m, const float *base, int C, int W, int H,
   return make_map(m, base, 5, dims, str, box, true);
 }
 
-int tc_wgrad_fused(const cpgb_conv_desc &d, const float *x, const float *dy, const float *w, const float *piggy,
-                   const uint8_t *tmask, int cur, float wd, int mode, float thr, float *dW, float *dP, void *ws,
-                   size_t ws_bytes, cudaStream_t st) {
+static int implicit_wgrad_fused(const cpgb_conv_desc &d, const float *x, const float *dy, const float *w,
+                                const float *piggy, const uint8_t *tmask, int cur, float wd, int mode, float thr,
+                                float *dW, float *dP, void *ws, size_t ws_bytes, cudaStream_t st) {
   if (!aligned16p(x) || !aligned16p(dy) || !aligned16p(ws)) {
     set_error("tcgen05 path needs 16-byte aligned tensors"); return CPGB_EINVAL;
   }
@@ -1101,6 +1102,275 @@ int tc_wgrad_fused(const cpgb_conv_desc &d, const float *x, const float *dy, con
                                                           wd, mode, thr, dW, dP);
   CPGB_LAUNCH_OK("wgrad_epilogue_krsc_scalar");
   return CPGB_OK;
+}
+
+}  // namespace cpgb
+
+
+// ------------------------------------------------------------------------------------------
+// Explicit-im2col tier ("xcol"): any stride / padding / dilation, groups = 1, any channel count.
+// The convolution becomes a plain GEMM over X_col[pixels][R*S*C] (tight (tap, channel) packing,
+// padded to 32), materialised in workspace by im2col_kernel; dgrad is the GEMM into dX_col followed
+// by a gathering col2im.  Used where the in-place TMA gather does not apply: stride-2 layers
+// (ResNet / SphereNet down-sampling) and the 3-channel stems, whose implicit-GEMM K blocks would be
+// 29/32 padding.  The GEMMs are the same tcgen05 kernels in "linear" geometry.
+// ------------------------------------------------------------------------------------------
+namespace cpgb {
+
+static inline int kc_of(const cpgb_conv_desc &d) { return d.R * d.S * d.C; }
+static inline int kcp_of(const cpgb_conv_desc &d) { return (kc_of(d) + 31) / 32 * 32; }
+static inline long long pixels_of(const cpgb_conv_desc &d) { return (long long)d.N * d.P * d.Q; }
+
+static bool y_dense_nhwc(const cpgb_conv_desc &d) {
+  const Str4 ys = y_strides(d);
+  return ys.s[1] == 1 && ys.s[3] == d.K && ys.s[2] == (int64_t)d.Q * d.K && ys.s[0] == (int64_t)d.P * d.Q * d.K;
+}
+
+static bool xcol_eligible(const cpgb_conv_desc &d, int op) {
+  if (d.groups != 1 || d.N < 1 || d.K % 4) return false;
+  if (!y_dense_nhwc(d)) return false;
+  if (pixels_of(d) >= (1ll << 31) - 256) return false;
+  if ((size_t)pixels_of(d) * kcp_of(d) * sizeof(float) > ((size_t)8 << 30)) return false;   // X_col <= 8 GiB
+  if (op == 2 && d.K % 32) return false;
+  return true;
+}
+
+// ONE staging layout per descriptor (fprop and dgrad share the staged operand): xcol for strided
+// layers and for channel counts so small that the implicit K blocks would be mostly padding.
+static bool prefer_xcol(const cpgb_conv_desc &d) {
+  return d.stride_h != 1 || d.stride_w != 1 || d.C < 16;
+}
+enum TcMode { TC_NONE = 0, TC_IMPLICIT = 1, TC_XCOL = 2 };
+static TcMode tc_mode(const cpgb_conv_desc &d, int op) {
+  if (prefer_xcol(d)) return xcol_eligible(d, op) ? TC_XCOL : TC_NONE;
+  return implicit_eligible(d, op) ? TC_IMPLICIT : TC_NONE;
+}
+
+// derived "linear" descriptor: M pixels x KCp features -> K outputs
+static cpgb_conv_desc xcol_desc(const cpgb_conv_desc &d) {
+  cpgb_conv_desc l;
+  memset(&l, 0, sizeof(l));
+  const int kcp = kcp_of(d);
+  l.N = (int)pixels_of(d); l.C = kcp; l.H = l.W = 1; l.K = d.K; l.R = l.S = 1; l.P = l.Q = 1;
+  l.stride_h = l.stride_w = l.dil_h = l.dil_w = 1; l.groups = 1;
+  l.xs[0] = kcp; l.xs[1] = 1; l.xs[2] = kcp; l.xs[3] = kcp;
+  l.ys[0] = d.K; l.ys[1] = 1; l.ys[2] = d.K; l.ys[3] = d.K;
+  return l;
+}
+
+// X_col[pix][t*C + c] = x[n, p*sh - ph + r*dh, q*sw - pw + s*dw, c]   (0 outside, 0 for padding columns)
+__global__ void __launch_bounds__(256)
+im2col_kernel(Geom g, const float *__restrict__ x, float *__restrict__ xcol, int KC, int KCp, long long total4) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int row4 = KCp >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
+    const long long pix = i / row4;
+    const int kc0 = (int)(i - pix * row4) << 2;
+    const int n = (int)(pix / g.PQ), pq = (int)(pix - (long long)n * g.PQ), p = pq / g.Q, q = pq - p * g.Q;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int kc = kc0 + j;
+      float val = 0.f;
+      if (kc < KC) {
+        const int t = kc / g.C, c = kc - t * g.C, r = t / g.S, s = t - r * g.S;
+        const int h = p * g.sh - g.ph + r * g.dh, ww = q * g.sw - g.pw + s * g.dw;
+        if ((unsigned)h < (unsigned)g.H && (unsigned)ww < (unsigned)g.W)
+          val = __ldg(x + n * g.xs0 + c * g.xs1 + h * g.xs2 + ww * g.xs3);
+      }
+      v[j] = val;
+    }
+    reinterpret_cast<float4 *>(xcol)[i] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+// dx[n,h,w,c] = sum over taps (r,s) and output pixels (p,q) with p*sh - ph + r*dh == h, q*sw - pw + s*dw == w
+//               of dXcol[pix(n,p,q)][(r*S+s)*C + c]
+__global__ void __launch_bounds__(256)
+col2im_kernel(Geom g, const float *__restrict__ dxcol, float *__restrict__ dx, int KCp, long long total) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c = (int)(i % g.C);
+    long long rest = i / g.C;
+    const int ww = (int)(rest % g.W); rest /= g.W;
+    const int h = (int)(rest % g.H);
+    const int n = (int)(rest / g.H);
+    float acc = 0.f;
+    for (int r = 0; r < g.R; ++r) {
+      const int hp = h + g.ph - r * g.dh;
+      if (hp < 0) continue;
+      const int p = hp / g.sh;
+      if (p * g.sh != hp || p >= g.P) continue;
+      for (int s = 0; s < g.S; ++s) {
+        const int wq = ww + g.pw - s * g.dw;
+        if (wq < 0) continue;
+        const int q = wq / g.sw;
+        if (q * g.sw != wq || q >= g.Q) continue;
+        const long long pix = ((long long)n * g.P + p) * g.Q + q;
+        acc += __ldg(dxcol + pix * KCp + (r * g.S + s) * g.C + c);
+      }
+    }
+    dx[n * g.xs0 + c * g.xs1 + h * g.xs2 + ww * g.xs3] = acc;
+  }
+}
+
+// staged[k][t*C + c] = tf32_rna(binarize(P[k][c][t]) * W[k][c][t]), zero padded to KCp
+__global__ void __launch_bounds__(256)
+stage_weights_tight_kernel(const float *__restrict__ w, const float *__restrict__ piggy, float *__restrict__ wt, int C,
+                           int RS, int KCp, long long total, float thr) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int KC = C * RS;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long k = i / KCp;
+    const int kc = (int)(i - k * KCp);
+    float v = 0.f;
+    if (kc < KC) {
+      const int t = kc / C, c = kc - t * C;
+      const long long idx = (k * C + c) * RS + t;
+      v = to_tf32_rna(masked_weight(__ldg(w + idx), piggy, idx, thr));
+    }
+    wt[i] = v;
+  }
+}
+
+// (dW, dP) in the module's [K][C][R][S] order from G2[K][KCp] ((tap, channel) columns)
+__global__ void __launch_bounds__(256)
+wgrad_epilogue_xcol_kernel(const float *__restrict__ g2, int K, int C, int RS, int KCp, const float *__restrict__ w,
+                           const float *__restrict__ piggy, const uint8_t *__restrict__ tmask, int cur, float wd,
+                           int mode, float thr, float *__restrict__ dW, float *__restrict__ dP) {
+  const long long n = (long long)K * C * RS;
+  const bool has_p = piggy != nullptr;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += stride) {
+    const int t = (int)(idx % RS);
+    const long long kc_ = idx / RS;
+    const int c = (int)(kc_ % C);
+    const long long k = kc_ / C;
+    const float g = __ldg(g2 + k * KCp + t * C + c);
+    float ow, op;
+    epi_one_tc(g, __ldg(w + idx), has_p ? __ldg(piggy + idx) : 0.f, has_p, tmask ? tmask[idx] : 0u, cur, wd, mode,
+               thr, ow, op);
+    dW[idx] = ow;
+    if (dP) dP[idx] = op;
+  }
+}
+
+static size_t xcol_staged_bytes(const cpgb_conv_desc &d) {
+  return align_up((size_t)d.K * kcp_of(d) * sizeof(float) + 256, 256);
+}
+static size_t xcol_buffer_bytes(const cpgb_conv_desc &d) {
+  return align_up((size_t)pixels_of(d) * kcp_of(d) * sizeof(float), 256);
+}
+static size_t xcol_workspace_bytes(const cpgb_conv_desc &d) {
+  // [staged (when the caller passes none)] [X_col / dX_col] [G2] [workspace of the inner GEMM]
+  const cpgb_conv_desc l = xcol_desc(d);
+  return xcol_staged_bytes(d) + xcol_buffer_bytes(d) + align_up((size_t)d.K * kcp_of(d) * sizeof(float), 256) +
+         implicit_workspace_bytes(l) + 256;
+}
+
+static int xcol_stage_weights(const cpgb_conv_desc &d, const float *w, const float *piggy, float thr, void *staged,
+                              size_t bytes, cudaStream_t st) {
+  if (bytes < xcol_staged_bytes(d)) { set_error("staged-weight buffer %zu < %zu", bytes, xcol_staged_bytes(d)); return CPGB_EWORKSPACE; }
+  const long long total = (long long)d.K * kcp_of(d);
+  int grid = (int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 8);
+  stage_weights_tight_kernel<<<grid, 256, 0, st>>>(w, piggy, reinterpret_cast<float *>(staged), d.C, d.R * d.S,
+                                                   kcp_of(d), total, thr);
+  CPGB_LAUNCH_OK("stage_weights_tight");
+  return CPGB_OK;
+}
+
+static int run_im2col(const cpgb_conv_desc &d, const float *x, float *xcol, cudaStream_t st) {
+  const long long total4 = pixels_of(d) * (kcp_of(d) / 4);
+  int grid = (int)std::min<long long>((total4 + 255) / 256, (long long)num_sms() * 16);
+  im2col_kernel<<<grid, 256, 0, st>>>(make_geom(d), x, xcol, kc_of(d), kcp_of(d), total4);
+  CPGB_LAUNCH_OK("im2col");
+  return CPGB_OK;
+}
+
+static int xcol_fprop(const cpgb_conv_desc &d, const float *x, const float *staged, const float *bias, float *y,
+                      void *ws, size_t ws_bytes, cudaStream_t st) {
+  const size_t need = xcol_buffer_bytes(d);
+  if (!ws || ws_bytes < need) { set_error("workspace %zu < %zu (im2col buffer)", ws_bytes, need); return CPGB_EWORKSPACE; }
+  float *xcol = reinterpret_cast<float *>(ws);
+  int rc;
+  if ((rc = run_im2col(d, x, xcol, st))) return rc;
+  const cpgb_conv_desc l = xcol_desc(d);
+  return implicit_fprop(l, xcol, staged, bias, y, reinterpret_cast<char *>(ws) + need, ws_bytes - need, st);
+}
+
+static int xcol_dgrad(const cpgb_conv_desc &d, const float *dy, const float *staged, float *dx, void *ws,
+                      size_t ws_bytes, cudaStream_t st) {
+  const size_t need = xcol_buffer_bytes(d);
+  if (!ws || ws_bytes < need) { set_error("workspace %zu < %zu (col2im buffer)", ws_bytes, need); return CPGB_EWORKSPACE; }
+  float *dxcol = reinterpret_cast<float *>(ws);
+  const cpgb_conv_desc l = xcol_desc(d);
+  int rc;
+  if ((rc = implicit_dgrad(l, dy, staged, dxcol, reinterpret_cast<char *>(ws) + need, ws_bytes - need, st))) return rc;
+  const long long total = (long long)d.N * d.H * d.W * d.C;
+  int grid = (int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 16);
+  col2im_kernel<<<grid, 256, 0, st>>>(make_geom(d), dxcol, dx, kcp_of(d), total);
+  CPGB_LAUNCH_OK("col2im");
+  return CPGB_OK;
+}
+
+static int xcol_wgrad_fused(const cpgb_conv_desc &d, const float *x, const float *dy, const float *w,
+                            const float *piggy, const uint8_t *tmask, int cur, float wd, int mode, float thr,
+                            float *dW, float *dP, void *ws, size_t ws_bytes, cudaStream_t st) {
+  const size_t nb = xcol_buffer_bytes(d), ng = align_up((size_t)d.K * kcp_of(d) * sizeof(float), 256);
+  if (!ws || ws_bytes < nb + ng) { set_error("workspace %zu < %zu (im2col buffer)", ws_bytes, nb + ng); return CPGB_EWORKSPACE; }
+  float *xcol = reinterpret_cast<float *>(ws);
+  float *g2 = reinterpret_cast<float *>(reinterpret_cast<char *>(ws) + nb);
+  int rc;
+  if ((rc = run_im2col(d, x, xcol, st))) return rc;
+  const cpgb_conv_desc l = xcol_desc(d);
+  // raw G2 = dY^T X_col through the linear wgrad kernel (the "weight" pointer is only read to form a dP that
+  // is not requested: any K*KCp-float buffer will do, G2 itself is one)
+  if ((rc = implicit_wgrad_fused(l, xcol, dy, g2, nullptr, nullptr, 0, 0.f, CPGB_GRAD_RAW, thr, g2, nullptr,
+                                 reinterpret_cast<char *>(ws) + nb + ng, ws_bytes - nb - ng, st)))
+    return rc;
+  const long long n = (long long)d.K * d.C * d.R * d.S;
+  int grid = (int)std::min<long long>((n + 255) / 256, (long long)num_sms() * 8);
+  wgrad_epilogue_xcol_kernel<<<grid, 256, 0, st>>>(g2, d.K, d.C, d.R * d.S, kcp_of(d), w, piggy, tmask, cur, wd, mode, thr,
+                                                   dW, dP);
+  CPGB_LAUNCH_OK("wgrad_epilogue_xcol");
+  return CPGB_OK;
+}
+
+// ---- public dispatchers (common.cuh) -------------------------------------------------------
+bool tc_eligible(const cpgb_conv_desc &d, int op) { return tc_mode(d, op) != TC_NONE; }
+
+size_t tc_staged_bytes(const cpgb_conv_desc &d) { return prefer_xcol(d) ? xcol_staged_bytes(d) : implicit_staged_bytes(d); }
+
+size_t tc_workspace_bytes(const cpgb_conv_desc &d) {
+  if (d.groups <= 0) return 0;
+  if (prefer_xcol(d)) return (xcol_eligible(d, 0) || xcol_eligible(d, 1) || xcol_eligible(d, 2)) ? xcol_workspace_bytes(d) : 0;
+  return implicit_workspace_bytes(d);
+}
+
+int tc_stage_weights(const cpgb_conv_desc &d, const float *w, const float *piggy, float thr, void *staged, size_t bytes,
+                     cudaStream_t st) {
+  return prefer_xcol(d) ? xcol_stage_weights(d, w, piggy, thr, staged, bytes, st)
+                        : implicit_stage_weights(d, w, piggy, thr, staged, bytes, st);
+}
+
+int tc_fprop(const cpgb_conv_desc &d, const float *x, const float *staged, const float *bias, float *y, void *part,
+             size_t part_bytes, cudaStream_t st) {
+  return tc_mode(d, 0) == TC_XCOL ? xcol_fprop(d, x, staged, bias, y, part, part_bytes, st)
+                                  : implicit_fprop(d, x, staged, bias, y, part, part_bytes, st);
+}
+
+int tc_dgrad(const cpgb_conv_desc &d, const float *dy, const float *staged, float *dx, void *part, size_t part_bytes,
+             cudaStream_t st) {
+  return tc_mode(d, 1) == TC_XCOL ? xcol_dgrad(d, dy, staged, dx, part, part_bytes, st)
+                                  : implicit_dgrad(d, dy, staged, dx, part, part_bytes, st);
+}
+
+int tc_wgrad_fused(const cpgb_conv_desc &d, const float *x, const float *dy, const float *w, const float *piggy,
+                   const uint8_t *tmask, int cur, float wd, int mode, float thr, float *dW, float *dP, void *ws,
+                   size_t ws_bytes, cudaStream_t st) {
+  return tc_mode(d, 2) == TC_XCOL
+             ? xcol_wgrad_fused(d, x, dy, w, piggy, tmask, cur, wd, mode, thr, dW, dP, ws, ws_bytes, st)
+             : implicit_wgrad_fused(d, x, dy, w, piggy, tmask, cur, wd, mode, thr, dW, dP, ws, ws_bytes, st);
 }
 
 }  // namespace cpgb

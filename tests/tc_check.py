@@ -13,7 +13,7 @@ import cpg_b200.layers as nl
 
 DEV = 'cuda:0'
 
-# (N, C, H, W, K, R, pad, dil)
+# (N, C, H, W, K, R, pad, dil[, stride])
 CASES = [
     (2, 32, 8, 8, 64, 3, 1, 1),
     (4, 64, 32, 32, 64, 3, 1, 1),
@@ -32,6 +32,12 @@ CASES = [
     (128, 512, 2, 2, 512, 3, 1, 1),
     (128, 3, 32, 32, 64, 3, 1, 1),
     (5, 3, 20, 20, 32, 3, 1, 1),
+    # explicit-im2col tier: strided layers and stems
+    (4, 64, 16, 16, 128, 3, 1, 1, 2),
+    (4, 64, 16, 16, 128, 1, 0, 1, 2),
+    (3, 3, 33, 33, 64, 7, 3, 1, 2),
+    (6, 128, 14, 14, 256, 3, 1, 1, 2),
+    (2, 8, 9, 9, 32, 3, 1, 2, 1),
 ]
 
 
@@ -57,9 +63,10 @@ def run(op, cases):
     torch.backends.cuda.matmul.allow_tf32 = False
     lib = _lib.load()
     worst = 0.0
-    for (N, C, H, W, K, R, pad, dil) in cases:
+    for case in cases:
+        (N, C, H, W, K, R, pad, dil), stride = case[:8], (case[8] if len(case) > 8 else 1)
         torch.manual_seed(N * 7 + C + K)
-        m = nl.SharableConv2d(C, K, R, padding=pad, dilation=dil, bias=True).to(DEV)
+        m = nl.SharableConv2d(C, K, R, stride=stride, padding=pad, dilation=dil, bias=True).to(DEV)
         with torch.no_grad():
             m.weight.normal_(0, (2.0 / (C * R * R)) ** 0.5)
             m.bias.normal_()
@@ -72,12 +79,13 @@ def run(op, cases):
             xv.copy_(x)
             x = xv
         weff = ((m.piggymask > 5e-3).float() * m.weight).detach()
-        yr = F.conv2d(x, weff, m.bias, 1, pad, dil)
+        yr = F.conv2d(x, weff, m.bias, stride, pad, dil)
         dy = torch.randn_like(yr).contiguous(memory_format=torch.channels_last)
-        d = _lib.conv_desc(x.shape, x.stride(), m.weight.shape, dy.shape, dy.stride(), (1, 1), (pad, pad), (dil, dil), 1)
+        d = _lib.conv_desc(x.shape, x.stride(), m.weight.shape, dy.shape, dy.stride(), (stride, stride), (pad, pad),
+                           (dil, dil), 1)
         ws = torch.empty(max(lib.cpgb_workspace_bytes(d), 256), dtype=torch.uint8, device=DEV)
         P, st = _lib.ptr, _lib.stream_ptr()
-        tag = f'N{N} C{C} {H}x{W} K{K} R{R} p{pad} d{dil}'
+        tag = f'N{N} C{C} {H}x{W} K{K} R{R} p{pad} d{dil} s{stride}'
         _lib.set_path(_lib.PATH_TCGEN05)
         try:
             t0 = time.time()
@@ -88,14 +96,14 @@ def run(op, cases):
                 torch.cuda.synchronize()
                 e, bf = rel(y - m.bias.view(1, -1, 1, 1), yr - m.bias.view(1, -1, 1, 1)), proj(y - m.bias.view(1, -1, 1, 1), yr - m.bias.view(1, -1, 1, 1))
             elif op == 'dgrad':
-                dxr = torch.nn.grad.conv2d_input(x.shape, weff, dy, 1, pad, dil)
-                dx = torch.full_like(x, float('nan'))
+                dxr = torch.nn.grad.conv2d_input(x.shape, weff, dy, stride, pad, dil)
+                dx = torch.full_like(x, float('nan')) if C % 4 == 0 else torch.empty_strided(x.shape, x.stride(), device=DEV)
                 _lib.check(lib.cpgb_conv2d_dgrad(d, P(dy), P(m.weight), P(m.piggymask), P(dx), 5e-3, None, P(ws),
                                                  ws.numel(), st), 'dgrad')
                 torch.cuda.synchronize()
                 e, bf = rel(dx, dxr), proj(dx, dxr)
             else:
-                gr = torch.nn.grad.conv2d_weight(x, m.weight.shape, dy, 1, pad, dil)
+                gr = torch.nn.grad.conv2d_weight(x, m.weight.shape, dy, stride, pad, dil)
                 dW = torch.full_like(m.weight, float('nan'))
                 dP = torch.full_like(m.weight, float('nan'))
                 tm = torch.randint(0, 4, m.weight.shape, device=DEV, dtype=torch.uint8)
@@ -109,11 +117,11 @@ def run(op, cases):
                 rP = gr * m.weight * ((tm >= 1) & (tm < cur))
                 e = max(rel(dW, rW), rel(dP, rP))
                 bf = proj(dP, rP)
-            print(f'{op:6s} {tag:34s} rel {e:.3e}  proj {bf:+.3e}  {"OK" if e <= 1e-3 else "FAIL"} '
+            print(f'{op:6s} {tag:38s} rel {e:.3e}  proj {bf:+.3e}  {"OK" if e <= 1e-3 else "FAIL"} '
                   f'({(time.time() - t0) * 1e3:.1f} ms)', flush=True)
             worst = max(worst, e)
         except Exception as ex:  # noqa: BLE001
-            print(f'{op:6s} {tag:34s} EXCEPTION {type(ex).__name__}: {ex}', flush=True)
+            print(f'{op:6s} {tag:38s} EXCEPTION {type(ex).__name__}: {ex}', flush=True)
             if 'CUDA' in str(ex) or 'cuda' in str(ex):
                 print('context is gone; stopping', flush=True)
                 return

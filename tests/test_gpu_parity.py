@@ -350,6 +350,56 @@ def test_trajectory_vs_reference_golden(golden, mode, path):
             assert zlib.crc32(masks[n].numpy().tobytes()) == int(g['maskcrc_module.' + n]), n
 
 
+# (N, C, H, W, K, R, stride, pad, dil): tensor-core tiers -- in-place TMA gather (stride 1) and the
+# explicit-im2col tier (stride 2, stems) -- at layer shapes of VGG16 / ResNet-50 / SphereNet-20
+TC_SHAPES = [
+    (16, 64, 32, 32, 64, 3, 1, 1, 1), (8, 128, 16, 16, 256, 3, 1, 1, 1), (16, 512, 2, 2, 512, 3, 1, 1, 1),
+    (4, 256, 14, 14, 1024, 1, 1, 0, 1), (4, 64, 20, 20, 64, 3, 1, 2, 2),
+    (8, 3, 32, 32, 64, 3, 1, 1, 1),            # VGG stem
+    (2, 3, 64, 64, 64, 7, 2, 3, 1),            # ResNet stem (7x7 s2 p3)
+    (2, 3, 48, 40, 64, 3, 2, 1, 1),            # SphereNet stem (3x3 s2)
+    (4, 128, 28, 28, 128, 3, 2, 1, 1),         # ResNet 3x3 s2
+    (4, 256, 14, 14, 512, 1, 2, 0, 1),         # ResNet 1x1 s2 down-sample
+    (4, 64, 28, 24, 128, 3, 2, 1, 1),          # SphereNet conv2_1
+]
+
+
+@pytest.mark.parametrize('shape', TC_SHAPES)
+def test_tensor_core_tiers_vs_torch_fp32(shape):
+    """Forced tcgen05 path (raises if the shape is not eligible) against torch fp32 (cuDNN, TF32 off):
+    y, dX, dW, dP, dbias within the north_star 1e-3."""
+    N, C, H, W, K, R, stride, pad, dil = shape
+    torch.manual_seed(sum(shape))
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        m = nl.SharableConv2d(C, K, R, stride=stride, padding=pad, dilation=dil, bias=True).to(DEV)
+        with torch.no_grad():
+            m.weight.normal_(0, (2.0 / (C * R * R)) ** 0.5)
+            m.bias.normal_()
+        m.piggymask = nn.Parameter(torch.rand_like(m.weight) * 0.01)
+        x = torch.randn(N, C, H, W, device=DEV).contiguous(memory_format=torch.channels_last).requires_grad_(C > 4)
+        _lib.set_path(_lib.PATH_TCGEN05)
+        y = m(x)
+        dy = torch.randn_like(y)
+        y.backward(dy)
+        xr = x.detach().clone().requires_grad_(C > 4)
+        wr = m.weight.detach().clone().requires_grad_(True)
+        pr = m.piggymask.detach().clone().requires_grad_(True)
+        br = m.bias.detach().clone().requires_grad_(True)
+        b = (pr > 5e-3).float()
+        yr = torch.nn.functional.conv2d(xr, (b - pr).detach() * wr + pr * wr, br, stride, pad, dil)   # value b*W, STE grad
+        yr.backward(dy)
+        assert rel(y, yr) <= TOL_TC
+        assert rel(m.weight.grad, wr.grad) <= TOL_TC
+        assert rel(m.piggymask.grad, pr.grad) <= TOL_TC
+        assert rel(m.bias.grad, br.grad) <= 1e-5
+        if C > 4:
+            assert rel(x.grad, xr.grad) <= TOL_TC
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+
+
 def test_one_step_tc_vs_fp32_path():
     """One fwd+bwd of a VGG16-BN (width 0.5, batch 16) from identical state: the TF32 tensor-core
     path (AUTO) against the fp32 CUDA-core path.  Per-layer TF32 error is a few 1e-4
