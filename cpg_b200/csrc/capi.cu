@@ -102,6 +102,23 @@ static int pick_tc(const cpgb_conv_desc *d, int op, bool *use_tc) {
   return CPGB_OK;
 }
 
+size_t cpgb_staged_weight_bytes_for(int32_t K, int32_t C, int32_t R, int32_t S, int32_t stride_h, int32_t stride_w,
+                                    int32_t groups) {
+  if (g_path.load() == CPGB_PATH_SIMT) return 0;
+  return tc_staged_bytes_for_weight(K, C, R, S, stride_h, stride_w, groups);
+}
+
+int cpgb_stage_weights_batched(int32_t n, const float *const *w, const float *const *piggy, void *const *staged,
+                               const int32_t *K, const int32_t *C, const int32_t *R, const int32_t *S,
+                               const int32_t *stride_h, const int32_t *stride_w, const float *thr, void *stream) {
+  if (n < 0 || (n > 0 && (!w || !piggy || !staged || !K || !C || !R || !S || !stride_h || !stride_w || !thr))) {
+    set_error("cpgb_stage_weights_batched: null pointer");
+    return CPGB_EINVAL;
+  }
+  if (n == 0) return CPGB_OK;
+  return tc_stage_weights_batched(n, w, piggy, staged, K, C, R, S, stride_h, stride_w, thr, (cudaStream_t)stream);
+}
+
 // bring-up hook (not part of the public header): MN-major operand descriptor fields
 void cpgb_debug_set_mn(int layout, int lbo, int sbo, int kadv, int tma_swizzle) {
   debug_set_mn(layout, lbo, sbo, kadv, tma_swizzle);

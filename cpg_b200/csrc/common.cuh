@@ -80,6 +80,10 @@ void debug_set_mn(int layout, int lbo, int sbo, int kadv, int tma_swizzle);
 // staged = tf32((piggy > thr) * w) reordered to [K][R*S][Cp]
 int tc_stage_weights(const cpgb_conv_desc &d, const float *w, const float *piggy, float thr, void *staged,
                      size_t bytes, cudaStream_t st);
+size_t tc_staged_bytes_for_weight(int K, int C, int R, int S, int stride_h, int stride_w, int groups);
+int tc_stage_weights_batched(int n, const float *const *w, const float *const *piggy, void *const *staged,
+                             const int *K, const int *C, const int *R, const int *S, const int *stride_h,
+                             const int *stride_w, const float *thr, cudaStream_t st);
 // part: scratch for split-K partial sums (tc_workspace_bytes covers staged operand + partials)
 int tc_fprop(const cpgb_conv_desc &d, const float *x, const float *staged, const float *bias, float *y, void *part,
              size_t part_bytes, cudaStream_t st);

@@ -1336,6 +1336,123 @@ static int xcol_wgrad_fused(const cpgb_conv_desc &d, const float *x, const float
   return CPGB_OK;
 }
 
+// ---- batched staging: every sharable layer of a model in one launch ---------------------------
+constexpr int STAGE_MAX_ITEMS = 56;
+struct StageBatch {
+  const float *w[STAGE_MAX_ITEMS];
+  const float *piggy[STAGE_MAX_ITEMS];
+  float *out[STAGE_MAX_ITEMS];
+  int K[STAGE_MAX_ITEMS], C[STAGE_MAX_ITEMS], RS[STAGE_MAX_ITEMS];
+  int kind[STAGE_MAX_ITEMS];       // 0: [K][RS][Cp] through smem transpose, 1: flat copy, 2: tight [K][KCp]
+  int blk0[STAGE_MAX_ITEMS + 1];   // first block of each item
+  float thr[STAGE_MAX_ITEMS];
+  int n;
+};
+static_assert(sizeof(StageBatch) <= 4000, "kernel parameter space");
+
+constexpr int STAGE_FLAT_PER_BLOCK = 256 * 8;   // float4 per block of the flat / tight kinds
+__global__ void __launch_bounds__(256) stage_weights_batched_kernel(const __grid_constant__ StageBatch sb) {
+  extern __shared__ float sh[];
+  // which item does this block belong to (<= 56 items: linear search over the prefix sums)
+  int it = 0;
+  while (it + 1 < sb.n && (int)blockIdx.x >= sb.blk0[it + 1]) ++it;
+  const int b = blockIdx.x - sb.blk0[it];
+  const float *__restrict__ w = sb.w[it];
+  const float *__restrict__ piggy = sb.piggy[it];
+  float *__restrict__ wt = sb.out[it];
+  const int K = sb.K[it], C = sb.C[it], RS = sb.RS[it];
+  const float thr = sb.thr[it];
+  if (sb.kind[it] == 0) {
+    const int Cp = (C + 31) / 32 * 32, cchunks = (Cp + STAGE_CC - 1) / STAGE_CC;
+    const int k = b / cchunks, c0 = (b - k * cchunks) * STAGE_CC;
+    const int cc = min(STAGE_CC, Cp - c0), cv = max(0, min(STAGE_CC, C - c0)), ld = RS | 1;
+    const long long base = ((long long)k * C + c0) * RS;
+    for (int i = threadIdx.x; i < cv * RS; i += blockDim.x)
+      sh[(i / RS) * ld + (i % RS)] = to_tf32_rna(masked_weight(__ldg(w + base + i), piggy, base + i, thr));
+    __syncthreads();
+    float *dst = wt + (long long)k * RS * Cp + c0;
+    for (int i = threadIdx.x; i < cc * RS; i += blockDim.x) {
+      const int t = i / cc, c = i - t * cc;
+      dst[(long long)t * Cp + c] = c < cv ? sh[c * ld + t] : 0.f;
+    }
+  } else if (sb.kind[it] == 1) {
+    const long long n4 = (long long)K * C * RS / 4;
+    const long long beg = (long long)b * STAGE_FLAT_PER_BLOCK, end = min(n4, beg + STAGE_FLAT_PER_BLOCK);
+    for (long long i = beg + threadIdx.x; i < end; i += blockDim.x) {
+      float4 v = __ldg(reinterpret_cast<const float4 *>(w) + i);
+      if (piggy) {
+        const float4 pv = __ldg(reinterpret_cast<const float4 *>(piggy) + i);
+        v.x *= binarize_val(pv.x, thr); v.y *= binarize_val(pv.y, thr);
+        v.z *= binarize_val(pv.z, thr); v.w *= binarize_val(pv.w, thr);
+      }
+      reinterpret_cast<float4 *>(wt)[i] = make_float4(to_tf32_rna(v.x), to_tf32_rna(v.y), to_tf32_rna(v.z), to_tf32_rna(v.w));
+    }
+  } else {
+    const int KC = C * RS, KCp = (KC + 31) / 32 * 32;
+    const long long total = (long long)K * KCp;
+    const long long beg = (long long)b * STAGE_FLAT_PER_BLOCK * 4, end = min(total, beg + STAGE_FLAT_PER_BLOCK * 4);
+    for (long long i = beg + threadIdx.x; i < end; i += blockDim.x) {
+      const long long k = i / KCp;
+      const int kc = (int)(i - k * KCp);
+      float v = 0.f;
+      if (kc < KC) {
+        const int t = kc / C, c = kc - t * C;
+        const long long idx = (k * C + c) * RS + t;
+        v = to_tf32_rna(masked_weight(__ldg(w + idx), piggy, idx, thr));
+      }
+      wt[i] = v;
+    }
+  }
+}
+
+// weight-only view of the staging decision (the input shape is not known when a whole model is staged)
+static cpgb_conv_desc weight_desc(int K, int C, int R, int S, int stride_h, int stride_w, int groups) {
+  cpgb_conv_desc d;
+  memset(&d, 0, sizeof(d));
+  d.K = K; d.C = C; d.R = R; d.S = S; d.stride_h = stride_h; d.stride_w = stride_w; d.groups = groups;
+  d.N = 1; d.H = d.W = d.P = d.Q = 1; d.dil_h = d.dil_w = 1;
+  return d;
+}
+size_t tc_staged_bytes_for_weight(int K, int C, int R, int S, int stride_h, int stride_w, int groups) {
+  if (groups != 1 || K % 4 || K <= 0 || C <= 0 || R * S > 49) return 0;
+  return tc_staged_bytes(weight_desc(K, C, R, S, stride_h, stride_w, groups));
+}
+
+int tc_stage_weights_batched(int n, const float *const *w, const float *const *piggy, void *const *staged,
+                             const int *K, const int *C, const int *R, const int *S, const int *stride_h,
+                             const int *stride_w, const float *thr, cudaStream_t st) {
+  for (int base = 0; base < n; base += STAGE_MAX_ITEMS) {
+    StageBatch sb;
+    sb.n = std::min(STAGE_MAX_ITEMS, n - base);
+    int blocks = 0, rs_max = 1;
+    for (int j = 0; j < sb.n; ++j) {
+      const int i = base + j;
+      const cpgb_conv_desc d = weight_desc(K[i], C[i], R[i], S[i], stride_h[i], stride_w[i], 1);
+      sb.w[j] = w[i]; sb.piggy[j] = piggy[i]; sb.out[j] = reinterpret_cast<float *>(staged[i]);
+      sb.K[j] = K[i]; sb.C[j] = C[i]; sb.RS[j] = R[i] * S[i]; sb.thr[j] = thr[i];
+      sb.blk0[j] = blocks;
+      if (!w[i] || !staged[i] || !aligned16p(staged[i])) { set_error("stage_weights_batched: bad item %d", i); return CPGB_EINVAL; }
+      if (prefer_xcol(d)) {
+        sb.kind[j] = 2;
+        blocks += cdiv_i((long long)K[i] * kcp_of(d), STAGE_FLAT_PER_BLOCK * 4);
+      } else if (sb.RS[j] == 1 && C[i] % 32 == 0 && aligned16p(w[i]) && (!piggy[i] || aligned16p(piggy[i]))) {
+        sb.kind[j] = 1;
+        blocks += cdiv_i((long long)K[i] * C[i] / 4, STAGE_FLAT_PER_BLOCK);
+      } else {
+        sb.kind[j] = 0;
+        blocks += K[i] * cdiv_i(cp_of(d), STAGE_CC);
+        rs_max = std::max(rs_max, sb.RS[j]);
+      }
+    }
+    sb.blk0[sb.n] = blocks;
+    if (blocks == 0) continue;
+    size_t sh = (size_t)STAGE_CC * (rs_max | 1) * sizeof(float);
+    stage_weights_batched_kernel<<<blocks, 256, sh, st>>>(sb);
+    CPGB_LAUNCH_OK("stage_weights_batched");
+  }
+  return CPGB_OK;
+}
+
 // ---- public dispatchers (common.cuh) -------------------------------------------------------
 bool tc_eligible(const cpgb_conv_desc &d, int op) { return tc_mode(d, op) != TC_NONE; }
 

@@ -27,16 +27,21 @@ def _dense4(t):
     return t.contiguous()
 
 
-def _stage(lib, d, w, p, threshold):
+def _stage(lib, d, w, p, threshold, prestaged=None):
     """Build the tensor-core weight operand (masked, TF32, [K][RS][Cp]) for descriptor d, or
     None when d takes the CUDA-core path (which evaluates the mask while loading tiles).
+    `prestaged`: operand already built for this forward pass by the model-level batched staging
+    (cpg_b200.prune.SparsePruner pre-forward hook).
     Returns (staged, scratch): scratch is the split-K workspace of the fprop/dgrad call."""
     nbytes = lib.cpgb_staged_weight_bytes(d)
     if nbytes == 0:
         return None, None
-    staged = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
-    _lib.check(lib.cpgb_stage_weights(d, _lib.ptr(w), _lib.ptr(p), threshold, _lib.ptr(staged), nbytes,
-                                      _lib.stream_ptr()), 'cpgb_stage_weights')
+    if prestaged is not None and prestaged.numel() >= nbytes and prestaged.device == w.device:
+        staged = prestaged
+    else:
+        staged = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+        _lib.check(lib.cpgb_stage_weights(d, _lib.ptr(w), _lib.ptr(p), threshold, _lib.ptr(staged), nbytes,
+                                          _lib.stream_ptr()), 'cpgb_stage_weights')
     # cpgb_workspace_bytes = [staged operand][partial sums]; the operand is supplied separately
     return staged, _ws(lib.cpgb_workspace_bytes(d) - nbytes, w.device)
 
@@ -119,7 +124,7 @@ class MaskedConv2dFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, piggymask, bias, stride, padding, dilation, groups, threshold, fuse,
-                module, channels_last_out):
+                module, channels_last_out, prestaged=None):
         lib = _lib.load()
         _check_params(weight, piggymask, bias)
         if x.dim() != 4:
@@ -156,7 +161,7 @@ class MaskedConv2dFn(torch.autograd.Function):
         y = torch.empty((N, K, P, Q), dtype=torch.float32, device=x.device, memory_format=fmt)
         d = _lib.conv_desc(x.shape, x.stride(), w.shape, y.shape, y.stride(), stride, padding, dilation, groups)
         with torch.cuda.device(x.device):
-            staged, ws = _stage(lib, d, w, p, threshold)
+            staged, ws = _stage(lib, d, w, p, threshold, prestaged)
             _lib.check(lib.cpgb_conv2d_fprop(d, _lib.ptr(x), _lib.ptr(w), _lib.ptr(p), _lib.ptr(b),
                                              _lib.ptr(y), threshold, _lib.ptr(staged), _lib.ptr(ws),
                                              ws.numel() if ws is not None else 0,
@@ -183,14 +188,14 @@ class MaskedConv2dFn(torch.autograd.Function):
         dx = torch.empty_strided(x.shape, x.stride(), dtype=x.dtype, device=x.device) if need_dx else None
         dW, dP, db = _backward_kernels(lib, ctx, d, x, dy, w, p, threshold, ctx.staged, need_dx, need_w,
                                        ctx.has_bias, dx)
-        return dx, dW, dP, db, None, None, None, None, None, None, None, None
+        return dx, dW, dP, db, None, None, None, None, None, None, None, None, None
 
 
 class MaskedLinearFn(torch.autograd.Function):
     """y = linear(x, (piggymask > thr) * weight, bias)  -- models/layers.py:184-194."""
 
     @staticmethod
-    def forward(ctx, x, weight, piggymask, bias, threshold, fuse, module):
+    def forward(ctx, x, weight, piggymask, bias, threshold, fuse, module, prestaged=None):
         lib = _lib.load()
         _check_params(weight, piggymask, bias)
         if x.dtype != torch.float32 or not x.is_cuda:
@@ -209,7 +214,7 @@ class MaskedLinearFn(torch.autograd.Function):
         d = _lib.ConvDesc()
         lib.cpgb_linear_desc(d, M, I, O)
         with torch.cuda.device(x.device):
-            staged, ws = _stage(lib, d, w, p, threshold)
+            staged, ws = _stage(lib, d, w, p, threshold, prestaged)
             _lib.check(lib.cpgb_conv2d_fprop(d, _lib.ptr(x2), _lib.ptr(w), _lib.ptr(p), _lib.ptr(b), _lib.ptr(y),
                                              threshold, _lib.ptr(staged), _lib.ptr(ws),
                                              ws.numel() if ws is not None else 0, _lib.stream_ptr()),
@@ -236,7 +241,7 @@ class MaskedLinearFn(torch.autograd.Function):
         dW, dP, db = _backward_kernels(lib, ctx, d, x2, dy2, w, p, ctx.threshold, ctx.staged, need_dx, need_w,
                                        ctx.has_bias, dx2)
         dx = dx2.reshape(ctx.x_shape) if need_dx else None
-        return dx, dW, dP, db, None, None, None
+        return dx, dW, dP, db, None, None, None, None
 
 
 class Binarizer(torch.autograd.Function):

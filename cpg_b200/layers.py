@@ -32,6 +32,7 @@ class _SharableBase(nn.Module):
         self._cpg_pruner = None       # set by cpg_b200.prune.SparsePruner
         self._cpg_name = None
         self._cpg_grads_final = False
+        self._cpg_prestaged = None    # (buffer, weight ptr, piggymask ptr): one-shot, set by the model-level hook
 
     def _finish_init(self, threshold_fn, threshold):
         # Give real-valued mask weights per task to manage the shared part from previous tasks:
@@ -52,6 +53,17 @@ class _SharableBase(nn.Module):
         if pr is None or not torch.is_grad_enabled():
             return None
         return pr._fuse_ctx_for(self._cpg_name)
+
+    def _take_prestaged(self, weight, piggy):
+        """The operand the model-level batched staging built for THIS forward pass, if any (consumed:
+        a layer called again without the hook re-stages itself)."""
+        pre, self._cpg_prestaged = self._cpg_prestaged, None
+        if pre is None:
+            return None
+        buf, wptr, pptr = pre
+        if wptr != weight.data_ptr() or pptr != (piggy.data_ptr() if piggy is not None else 0):
+            return None          # e.g. a DataParallel replica on another device
+        return buf
 
     def _effective(self):
         """(weight, piggymask) to hand to the fused kernels.  The ternarizer (dead code in the
@@ -99,9 +111,10 @@ class SharableConv2d(_SharableBase):
     def forward(self, input, layer_info=None, name=None):
         weight, piggy = self._effective()
         fuse = self._fuse_ctx() if piggy is self.piggymask and weight is self.weight else None
+        pre = self._take_prestaged(weight, piggy) if weight is self.weight else None
         return MaskedConv2dFn.apply(input, weight, piggy, self.bias, self.stride, self.padding,
                                     self.dilation, self.groups, float(self.info['threshold']), fuse,
-                                    self if fuse is not None else None, OUTPUT_CHANNELS_LAST)
+                                    self if fuse is not None else None, OUTPUT_CHANNELS_LAST, pre)
 
     def __repr__(self):
         s = ('{name} ({in_channels}, {out_channels}, kernel_size={kernel_size}'
@@ -140,8 +153,9 @@ class SharableLinear(_SharableBase):
     def forward(self, input):
         weight, piggy = self._effective()
         fuse = self._fuse_ctx() if piggy is self.piggymask and weight is self.weight else None
+        pre = self._take_prestaged(weight, piggy) if weight is self.weight else None
         return MaskedLinearFn.apply(input, weight, piggy, self.bias, float(self.info['threshold']), fuse,
-                                    self if fuse is not None else None)
+                                    self if fuse is not None else None, pre)
 
     def __repr__(self):
         return self.__class__.__name__ + '(' \

@@ -44,7 +44,10 @@ class SparsePruner(object):
 
         self.inference_dataset_idx = inference_dataset_idx
         self.fuse_grad_epilogue = True
+        self.batched_staging = True     # build every layer's tensor-core weight operand in one launch
         self._prune_ws = {}
+        self._stage_bufs = {}
+        self._stage_hook = None
         self.attach()
         return
 
@@ -62,10 +65,65 @@ class SparsePruner(object):
             module._cpg_name = name
             module._cpg_grads_final = False
 
+        if self._stage_hook is None:
+            self._stage_hook = self.model.register_forward_pre_hook(self._prestage_hook)
+
     def detach(self):
         for name, module in self._sharable():
             module._cpg_pruner = None
             module._cpg_grads_final = False
+            module._cpg_prestaged = None
+        if self._stage_hook is not None:
+            self._stage_hook.remove()
+            self._stage_hook = None
+
+    def _prestage_hook(self, model, inputs):
+        """Forward pre-hook of the whole model: the masked TF32 weight operands of ALL sharable layers
+        in one launch (models/layers.py:101-103 for every layer at once).  Each layer consumes its
+        operand once; anything not covered here is staged by the layer itself."""
+        if not self.batched_staging:
+            return None
+        import ctypes
+        lib = _lib.load()
+        items = []
+        for name, m in self._sharable():
+            w = m.weight
+            if not w.is_cuda or w.dtype != torch.float32 or not w.is_contiguous() or m.info['threshold_fn'] != 'binarizer':
+                continue
+            if w.dim() == 4:
+                K, C, R, S = w.shape
+                sh, sw = m.stride
+                groups = m.groups
+                C = C * groups
+            else:
+                (K, C), R, S, sh, sw, groups = w.shape, 1, 1, 1, 1, 1
+            nbytes = lib.cpgb_staged_weight_bytes_for(K, C, R, S, sh, sw, groups)
+            p = m.piggymask
+            if nbytes == 0 or (p is not None and (not p.is_contiguous() or p.device != w.device)):
+                continue
+            key = (name, str(w.device))
+            buf = self._stage_bufs.get(key)
+            if buf is None or buf.numel() != nbytes:
+                buf = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+                self._stage_bufs[key] = buf
+            items.append((m, w, p, buf, K, C, R, S, sh, sw, float(m.info['threshold'])))
+        by_dev = {}
+        for it in items:
+            by_dev.setdefault(it[1].device, []).append(it)
+        for dev, its in by_dev.items():
+            n = len(its)
+            vp, i32 = ctypes.c_void_p, ctypes.c_int32
+            W = (vp * n)(*[it[1].data_ptr() for it in its])
+            P = (vp * n)(*[(it[2].data_ptr() if it[2] is not None else None) for it in its])
+            O = (vp * n)(*[it[3].data_ptr() for it in its])
+            arr = lambda j: (i32 * n)(*[int(it[j]) for it in its])
+            T = (ctypes.c_float * n)(*[it[10] for it in its])
+            with torch.cuda.device(dev):
+                _lib.check(lib.cpgb_stage_weights_batched(n, W, P, O, arr(4), arr(5), arr(6), arr(7), arr(8), arr(9), T,
+                                                          _lib.stream_ptr()), 'cpgb_stage_weights_batched')
+            for it in its:
+                it[0]._cpg_prestaged = (it[3], it[1].data_ptr(), it[2].data_ptr() if it[2] is not None else 0)
+        return None
 
     def _fuse_ctx_for(self, name):
         if not self.fuse_grad_epilogue or self.args.mode not in _MODES:

@@ -87,6 +87,18 @@ size_t cpgb_staged_weight_bytes(const cpgb_conv_desc *d);
 int cpgb_stage_weights(const cpgb_conv_desc *d, const float *w, const float *piggy, float thr, void *staged,
                        size_t staged_bytes, void *stream);
 
+/* The same staging for every sharable layer of a model in ONE launch (weights do not depend on the
+ * activations, so a model-level pre-forward hook can build all operands at once).  All arrays are HOST
+ * arrays of n entries; piggy[i] may be NULL; staged[i] must hold
+ * cpgb_staged_weight_bytes_for(K, C, R, S, stride_h, stride_w, groups) bytes (0 = this weight never takes
+ * the tensor-core path: skip it).  The layout produced is the one cpgb_conv2d_fprop / _dgrad expect for a
+ * descriptor with that weight shape and stride. */
+size_t cpgb_staged_weight_bytes_for(int32_t K, int32_t C, int32_t R, int32_t S, int32_t stride_h, int32_t stride_w,
+                                    int32_t groups);
+int cpgb_stage_weights_batched(int32_t n, const float *const *w, const float *const *piggy, void *const *staged,
+                               const int32_t *K, const int32_t *C, const int32_t *R, const int32_t *S,
+                               const int32_t *stride_h, const int32_t *stride_w, const float *thr, void *stream);
+
 /* a3/a5 forward: y = conv2d(x, (piggy > thr ? 1 : 0) * w, bias).  models/layers.py:98-109,
  * 184-194.  piggy == NULL means "no piggymask" (task 1, models/layers.py:104-105).  The
  * CUDA-core path evaluates the predicate while loading weight tiles; the tcgen05 path reads
