@@ -89,6 +89,9 @@ def make_args(datasets, mode='finetune'):
     return a
 
 
+FUSED_OPTIM = True   # torch.optim.{SGD,Adam}(fused=True): same update rule, one pass over the parameters
+
+
 def make_optimizers(net, capturable):
     sgd_params, adam_params = [], []
     head = '.{}.'.format(len(net.module.datasets) - 1)
@@ -100,9 +103,13 @@ def make_optimizers(net, capturable):
             adam_params.append(p)
         else:
             sgd_params.append(p)
-    opts = [torch.optim.SGD(sgd_params, lr=LR, weight_decay=0.0, momentum=0.9, nesterov=True)]
+    on_gpu = bool(sgd_params) and sgd_params[0].is_cuda
+    fused = FUSED_OPTIM and on_gpu
+    opts = [torch.optim.SGD(sgd_params, lr=LR, weight_decay=0.0, momentum=0.9, nesterov=True,
+                            **({'fused': True} if fused else {}))]
     if adam_params:
-        opts.append(torch.optim.Adam(adam_params, lr=LR_MASK, capturable=capturable))
+        opts.append(torch.optim.Adam(adam_params, lr=LR_MASK, capturable=capturable,
+                                     **({'fused': True} if fused else {})))
     return opts
 
 
@@ -619,7 +626,8 @@ def main():
             'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'regime': 'task1 (R1: no piggymask, T==1, cur=1)',
                        'global_batch': BATCH * world, 'parallelism': f'dp{world}',
-                       'step': 'utils/manager.py:54-75 sequence, SGD-nesterov (+Adam on piggymasks in task2)',
+                       'step': 'utils/manager.py:54-75 sequence, SGD-nesterov (+Adam on piggymasks in task2); '
+                               'torch.optim fused=True (same update rule as CPG_cifar100_main_normal.py:339-346)',
                        'cuda_graph': not args.no_graph,
                        'l2': 'per-step working set (weights+grads+momentum 400 MB, activations 280 MB) exceeds the 126 MB L2; 8 distinct input batches rotate'},
             'clocks': {k: r1['clocks'].get(k) for k in ('sm_mhz', 'sm_max_mhz', 'reasons')} if r1['clocks'] else None,

@@ -57,6 +57,22 @@ void debug_set_mn(int layout, int lbo, int sbo, int kadv, int tma_swizzle) {
   g_mn = MnDesc{layout, lbo, sbo, kadv, tma_swizzle};
 }
 
+// Launch with programmatic dependent launch enabled: the kernel's prologue (barrier init, TMEM
+// allocation, descriptor prefetch) overlaps the tail of the previous kernel on the stream; every
+// kernel launched through here calls griddep_wait() before its first global access.
+static bool g_pdl = getenv("CPGB_NO_PDL") == nullptr;
+template <class... KArgs, class... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // rank-`rank` fp32 tensor map with 128-byte swizzle; dims/strides innermost first; strides[0] is
 // implied (4 bytes) -- `strides_bytes[i]` is the stride of dim i+1.
 static int make_map(CUtensorMap *m, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes,
@@ -271,6 +287,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tail->tmem_slot;
+  griddep_launch_dependents();     // the next kernel may start its own prologue
+  griddep_wait();                  // ours ends here: inputs are produced by the previous kernel
 
   if (warp == 0) {
     if (lane == 0) {
@@ -355,6 +373,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float4 *__restrict__ part, int splits, long long n4, long long split_stride4, int ncols4,
                      const float4 *__restrict__ bias, float4 *__restrict__ out) {
+  griddep_launch_dependents();
+  griddep_wait();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 a = __ldg(part + i);
@@ -458,6 +478,8 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tail->tmem_slot;
+  griddep_launch_dependents();
+  griddep_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -605,6 +627,8 @@ wgrad_epilogue_krsc_kernel(const float *__restrict__ gpart, int splits, int K, i
                            const uint8_t *__restrict__ tmask, int cur, float wd, int mode, float thr,
                            float *__restrict__ dW, float *__restrict__ dP) {
   extern __shared__ float sh[];  // [kb][RS][Cg + 1]
+  griddep_launch_dependents();
+  griddep_wait();
   const int RS = RS_T > 0 ? RS_T : RS_rt;
   const int k0 = blockIdx.x * kb;
   const int nk = min(kb, K - k0);
@@ -684,6 +708,8 @@ wgrad_epilogue_flat_kernel(const float4 *__restrict__ gpart, int splits, long lo
                            const float4 *__restrict__ w, const float4 *__restrict__ piggy,
                            const uchar4 *__restrict__ tmask, int cur, float wd, int mode, float thr,
                            float4 *__restrict__ dW, float4 *__restrict__ dP) {
+  griddep_launch_dependents();
+  griddep_wait();
   const long long stride = (long long)gridDim.x * blockDim.x;
   const bool has_p = piggy != nullptr;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -886,7 +912,7 @@ static int launch_conv_gemm(const CUtensorMap &ta, const CUtensorMap &tb, ConvGe
   dim3 grid(p.tq * p.tp * p.tn, ntiles_n, splits);
   const long long ctas = (long long)grid.x * grid.y * grid.z;
   p.nstage = ctas > num_sms() ? Cfg::NSTAGE_PAIR : Cfg::NSTAGE_SOLO;   // solo only when no SM gets two CTAs anyway
-  conv_gemm_kernel<BN, B_MN><<<grid, 192, Cfg::smem_bytes(p.nstage), st>>>(ta, tb, p);
+  CPGB_CUDA_OK(launch_pdl(conv_gemm_kernel<BN, B_MN>, grid, dim3(192), Cfg::smem_bytes(p.nstage), st, ta, tb, p));
   CPGB_LAUNCH_OK("conv_gemm_kernel");
   return CPGB_OK;
 }
@@ -924,8 +950,9 @@ static int run_gemm(const GemmPlan &g, const CUtensorMap &ta, const CUtensorMap 
   if (rc || g.splits == 1) return rc;
   const long long n4 = g.out_elems / 4;
   int grid = (int)std::min<long long>((n4 + 255) / 256, (long long)num_sms() * 8);
-  splitk_reduce_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4 *>(part), g.splits, n4, n4, p.ncols / 4,
-                                             reinterpret_cast<const float4 *>(bias), reinterpret_cast<float4 *>(out));
+  CPGB_CUDA_OK(launch_pdl(splitk_reduce_kernel, dim3(grid), dim3(256), 0, st, reinterpret_cast<const float4 *>(part),
+                          g.splits, n4, n4, p.ncols / 4, reinterpret_cast<const float4 *>(bias),
+                          reinterpret_cast<float4 *>(out)));
   CPGB_LAUNCH_OK("splitk_reduce");
   return CPGB_OK;
 }
@@ -991,7 +1018,7 @@ static int launch_wgrad(const CUtensorMap &tdy, const CUtensorMap &tx, const Wgr
                                       HALO ? 227 * 1024 : Cfg::SMEM_BYTES));
     attr_done = true;
   }
-  wgrad_gemm_kernel<BN, TG, HALO><<<grid, 192, smem_bytes, st>>>(tdy, tx, p);
+  CPGB_CUDA_OK(launch_pdl(wgrad_gemm_kernel<BN, TG, HALO>, grid, dim3(192), (size_t)smem_bytes, st, tdy, tx, p));
   CPGB_LAUNCH_OK("wgrad_gemm_kernel");
   return CPGB_OK;
 }
@@ -1066,10 +1093,10 @@ static int implicit_wgrad_fused(const cpgb_conv_desc &d, const float *x, const f
   if (RS == 1 && vec_ok && d.C % 4 == 0) {
     const long long n4 = (long long)d.K * d.C / 4;
     int egrid = (int)std::min<long long>((n4 + 255) / 256, (long long)num_sms() * 8);
-    wgrad_epilogue_flat_kernel<<<egrid, 256, 0, st>>>(
-        reinterpret_cast<const float4 *>(p.gpart), pl.splits, n4, reinterpret_cast<const float4 *>(w),
-        reinterpret_cast<const float4 *>(piggy), reinterpret_cast<const uchar4 *>(tmask), cur, wd, mode, thr,
-        reinterpret_cast<float4 *>(dW), reinterpret_cast<float4 *>(dP));
+    CPGB_CUDA_OK(launch_pdl(wgrad_epilogue_flat_kernel, dim3(egrid), dim3(256), 0, st,
+                            reinterpret_cast<const float4 *>(p.gpart), pl.splits, n4, reinterpret_cast<const float4 *>(w),
+                            reinterpret_cast<const float4 *>(piggy), reinterpret_cast<const uchar4 *>(tmask), cur, wd,
+                            mode, thr, reinterpret_cast<float4 *>(dW), reinterpret_cast<float4 *>(dP)));
     CPGB_LAUNCH_OK("wgrad_epilogue_flat");
     return CPGB_OK;
   }
@@ -1087,11 +1114,11 @@ static int implicit_wgrad_fused(const cpgb_conv_desc &d, const float *x, const f
       }
       const int egrid = cdiv_i(d.K, kb);
       if (RS == 9)
-        wgrad_epilogue_krsc_kernel<9><<<egrid, 256, sh, st>>>(p.gpart, pl.splits, d.K, d.C, p.Cg, RS, kb, w, piggy, tmask,
-                                                             cur, wd, mode, thr, dW, dP);
+        CPGB_CUDA_OK(launch_pdl(wgrad_epilogue_krsc_kernel<9>, dim3(egrid), dim3(256), sh, st, (const float *)p.gpart,
+                                pl.splits, d.K, d.C, p.Cg, RS, kb, w, piggy, tmask, cur, wd, mode, thr, dW, dP));
       else
-        wgrad_epilogue_krsc_kernel<0><<<egrid, 256, sh, st>>>(p.gpart, pl.splits, d.K, d.C, p.Cg, RS, kb, w, piggy, tmask,
-                                                             cur, wd, mode, thr, dW, dP);
+        CPGB_CUDA_OK(launch_pdl(wgrad_epilogue_krsc_kernel<0>, dim3(egrid), dim3(256), sh, st, (const float *)p.gpart,
+                                pl.splits, d.K, d.C, p.Cg, RS, kb, w, piggy, tmask, cur, wd, mode, thr, dW, dP));
       CPGB_LAUNCH_OK("wgrad_epilogue_krsc");
       return CPGB_OK;
     }
