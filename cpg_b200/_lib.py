@@ -17,7 +17,7 @@ EXPORTS = [
     'cpgb_stage_weights_batched', 'cpgb_binarize', 'cpgb_conv2d_fprop', 'cpgb_conv2d_dgrad',
     'cpgb_conv2d_wgrad_fused', 'cpgb_grad_epilogue', 'cpgb_prune_workspace_bytes', 'cpgb_prune_select',
     'cpgb_prune_batched_workspace_bytes', 'cpgb_prune_select_batched',
-    'cpgb_apply_mask', 'cpgb_make_finetuning_mask', 'cpgb_mask_stats', 'cpgb_merge_grads',
+    'cpgb_apply_mask', 'cpgb_make_finetuning_mask', 'cpgb_mask_stats', 'cpgb_mask_stats_batched', 'cpgb_merge_grads',
     'cpgb_split_merged_grad',
 ]
 
@@ -74,6 +74,8 @@ def load():
         'cpgb_apply_mask': (ctypes.c_int, [vp, vp, i64, i32, vp]),
         'cpgb_make_finetuning_mask': (ctypes.c_int, [vp, i64, i32, vp]),
         'cpgb_mask_stats': (ctypes.c_int, [vp, vp, i64, i32, vp, vp]),
+        'cpgb_mask_stats_batched': (ctypes.c_int, [i32, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(i64),
+                                                   i32, vp, vp]),
         'cpgb_merge_grads': (ctypes.c_int, [vp, vp, vp, i64, vp]),
         'cpgb_split_merged_grad': (ctypes.c_int, [vp, vp, i64, i32, vp, vp, vp]),
     }

@@ -165,6 +165,60 @@ mask_stats_kernel(const uint8_t *__restrict__ tmask, const float *__restrict__ p
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(out + 4, (unsigned long long)n);
 }
 
+// all layers in one launch (grid.y = layer): what Manager.train asks for after every batch
+// (utils/manager.py:77-88 -> calculate_sparsity / calculate_curr_task_ratio / ...)
+constexpr int STATS_MAX_LAYERS = 64;
+struct StatsBatch {
+  const uint8_t *t[STATS_MAX_LAYERS];
+  const float *p[STATS_MAX_LAYERS];
+  long long n[STATS_MAX_LAYERS];
+};
+__global__ void __launch_bounds__(256)
+mask_stats_batched_kernel(const __grid_constant__ StatsBatch sb, int idx, unsigned long long *__restrict__ out) {
+  const int layer = blockIdx.y;
+  const uint8_t *__restrict__ tmask = sb.t[layer];
+  const float *__restrict__ piggy = sb.p[layer];
+  const long long n = sb.n[layer];
+  const long long n4 = n >> 2;
+  long long nblk = (n4 + blockDim.x - 1) / blockDim.x;
+  if (nblk < 1) nblk = 1;
+  const long long gx = nblk < (long long)gridDim.x ? nblk : (long long)gridDim.x;
+  if ((long long)blockIdx.x >= gx) return;
+  const long long stride = gx * blockDim.x;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+  auto visit = [&](unsigned t, long long i) {
+    c0 += (t == 0u);
+    c1 += (t == (unsigned)idx);
+    const bool shared = t > 0u && t < (unsigned)idx;
+    c2 += shared;
+    if (piggy && shared) c3 += (__ldg(piggy + i) > 0.005f);
+  };
+  long long tail = 0;
+  if ((reinterpret_cast<uintptr_t>(tmask) & 3) == 0) {
+    for (long long v = i0; v < n4; v += stride) {
+      const uchar4 t = __ldg(reinterpret_cast<const uchar4 *>(tmask) + v);
+      visit(t.x, 4 * v); visit(t.y, 4 * v + 1); visit(t.z, 4 * v + 2); visit(t.w, 4 * v + 3);
+    }
+    tail = n4 << 2;
+  }
+  for (long long i = tail + i0; i < n; i += stride) visit(tmask[i], i);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+    c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+    c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+    c3 += __shfl_xor_sync(0xffffffffu, c3, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (c0) atomicAdd(out + 0, (unsigned long long)c0);
+    if (c1) atomicAdd(out + 1, (unsigned long long)c1);
+    if (c2) atomicAdd(out + 2, (unsigned long long)c2);
+    if (c3) atomicAdd(out + 3, (unsigned long long)c3);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(out + 4, (unsigned long long)n);
+}
+
 // ---------------- data-parallel helpers ----------------
 __global__ void __launch_bounds__(256)
 merge_grads_kernel(const float *__restrict__ dW, const float *__restrict__ dP, float *__restrict__ m, long long n) {
@@ -238,6 +292,27 @@ int cpgb_mask_stats(const uint8_t *tmask, const float *piggy, int64_t n, int32_t
   mask_stats_kernel<<<grid_for(n, 256, 4), 256, 0, (cudaStream_t)stream>>>(
       tmask, piggy, n, inference_idx, reinterpret_cast<unsigned long long *>(out));
   CPGB_LAUNCH_OK("cpgb_mask_stats");
+  return CPGB_OK;
+}
+
+int cpgb_mask_stats_batched(int32_t nlayers, const uint8_t *const *tmask, const float *const *piggy, const int64_t *n,
+                            int32_t inference_idx, int64_t *out, void *stream) {
+  if (nlayers < 0 || !out || (nlayers > 0 && (!tmask || !n))) { set_error("cpgb_mask_stats_batched: null pointer"); return CPGB_EINVAL; }
+  for (int base = 0; base < nlayers; base += STATS_MAX_LAYERS) {
+    StatsBatch sb;
+    const int cnt = nlayers - base < STATS_MAX_LAYERS ? nlayers - base : STATS_MAX_LAYERS;
+    long long nmax = 0;
+    for (int j = 0; j < cnt; ++j) {
+      const int i = base + j;
+      if (n[i] < 0 || (n[i] > 0 && !tmask[i])) { set_error("cpgb_mask_stats_batched: bad layer %d", i); return CPGB_EINVAL; }
+      sb.t[j] = tmask[i]; sb.p[j] = piggy ? piggy[i] : nullptr; sb.n[j] = n[i];
+      if (n[i] > nmax) nmax = n[i];
+    }
+    dim3 grid(grid_for(nmax / 4 + 1, 256, 4), cnt);
+    mask_stats_batched_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(sb, inference_idx,
+                                                                      reinterpret_cast<unsigned long long *>(out));
+    CPGB_LAUNCH_OK("cpgb_mask_stats_batched");
+  }
   return CPGB_OK;
 }
 

@@ -246,22 +246,32 @@ class SparsePruner(object):
 
     # ------------------------------------------------------------------ K12 statistics
     def _stats(self, with_piggy=False):
+        """[#(T==0), #(T==idx), #(0<T<idx), #(0<T<idx and piggymask>0.005), numel] over all sharable
+        layers: one launch per device and one read-back (the reference does a .sum() + .cpu() per layer
+        and statistic, utils/prune.py:111-193)."""
+        import ctypes
         lib = _lib.load()
-        out = None
+        by_dev = {}
         for name, module in self._sharable():
             mask = self._mask(name)
-            if out is None:
-                out = torch.zeros(5, dtype=torch.int64, device=mask.device)
-            piggy = None
-            if with_piggy:
-                piggy = self._dense(module.piggymask.data, 'piggymask')
-            with torch.cuda.device(mask.device):
-                _lib.check(lib.cpgb_mask_stats(_lib.ptr(mask), _lib.ptr(piggy), mask.numel(),
-                                               self.inference_dataset_idx, _lib.ptr(out), _lib.stream_ptr()),
-                           'cpgb_mask_stats')
-        if out is None:
-            return [0, 0, 0, 0, 0]
-        return [int(v) for v in out.cpu().tolist()]
+            piggy = self._dense(module.piggymask.data, 'piggymask') if with_piggy else None
+            by_dev.setdefault(mask.device, []).append((mask, piggy))
+        total = [0, 0, 0, 0, 0]
+        outs = []
+        for dev, items in by_dev.items():
+            n = len(items)
+            out = torch.zeros(5, dtype=torch.int64, device=dev)
+            T = (ctypes.c_void_p * n)(*[_lib.ptr(m) for m, _ in items])
+            P = (ctypes.c_void_p * n)(*[(_lib.ptr(p) if p is not None else None) for _, p in items])
+            N = (ctypes.c_int64 * n)(*[m.numel() for m, _ in items])
+            with torch.cuda.device(dev):
+                _lib.check(lib.cpgb_mask_stats_batched(n, T, P, N, self.inference_dataset_idx, _lib.ptr(out),
+                                                       _lib.stream_ptr()), 'cpgb_mask_stats_batched')
+            outs.append(out)
+        for out in outs:
+            for i, v in enumerate(out.cpu().tolist()):
+                total[i] += int(v)
+        return total
 
     def calculate_sparsity(self):
         zero, cur, _, _, _ = self._stats()

@@ -160,6 +160,11 @@ int cpgb_make_finetuning_mask(uint8_t *tmask, int64_t n, int32_t new_cur, void *
 int cpgb_mask_stats(const uint8_t *tmask, const float *piggy, int64_t n, int32_t inference_idx,
                     int64_t *out, void *stream);
 
+/* The same counters accumulated over nlayers masks in one launch; tmask / piggy / n are HOST arrays
+ * (piggy may be NULL, or hold NULL entries). */
+int cpgb_mask_stats_batched(int32_t nlayers, const uint8_t *const *tmask, const float *const *piggy, const int64_t *n,
+                            int32_t inference_idx, int64_t *out, void *stream);
+
 /* Data-parallel helpers: dW and dP have disjoint support after a6, so one fp32
  * buffer m = dW + dP travels through the all-reduce; cpgb_split_merged_grad restores
  * dW = m[T==cur], dP = m[1<=T<cur]. */
