@@ -309,17 +309,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_tf32(128, BN, false, B_MN);
+      // descriptor = (constant upper half) | (start address >> 4): everything but the stage base is
+      // hoisted out of the loop -- this single thread issues every MMA of the CTA
+      const uint64_t a_tmpl = make_smem_desc(0, 16, 1024);
+      const uint64_t b_tmpl = B_MN ? make_smem_desc(0, p.mn_lbo, p.mn_sbo, p.mn_layout) : make_smem_desc(0, 16, 1024);
+      const uint32_t b_kstep = (B_MN ? p.mn_kadv : 32) >> 4;
       int stage = 0; uint32_t phase = 0;
       for (int it = it_beg; it < it_end; ++it) {
         mbar_wait(full + stage, phase);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-        const uint32_t sb = sa + A_TILE_BYTES;
+        const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES) >> 4;
+        const uint32_t sb = sa + (A_TILE_BYTES >> 4);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-          const uint64_t ad = make_smem_desc(sa + ks * 32, 16, 1024);
-          const uint64_t bd = B_MN ? make_smem_desc(sb + ks * p.mn_kadv, p.mn_lbo, p.mn_sbo, p.mn_layout)
-                                   : make_smem_desc(sb + ks * 32, 16, 1024);
+          const uint64_t ad = a_tmpl | (uint64_t)(sa + ks * 2);
+          const uint64_t bd = b_tmpl | (uint64_t)(sb + ks * b_kstep);
           mma_tf32_ss(tmem_base, ad, bd, idesc, (it > it_beg) | (ks != 0));
         }
         mma_commit(empty + stage);
@@ -513,24 +517,29 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_tf32(128, BN, true, true);
+      // all descriptor arithmetic hoisted: per MMA only "template | (stage base + constant offset)"
+      const uint64_t a_tmpl = make_smem_desc(0, p.mn_lbo, p.mn_sbo, p.mn_layout);
+      const uint64_t b_tmpl = make_smem_desc(0, HALO ? p.h_pitch : p.mn_lbo, p.mn_sbo, p.mn_layout);
+      uint32_t a_off[4], b_off[TG][4];
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        a_off[ks] = (ks * p.mn_kadv) >> 4;
+#pragma unroll
+        for (int s = 0; s < TG; ++s)
+          b_off[s][ks] = (HALO ? Cfg::A_BYTES + (p.h_krow[ks] + s * p.dil_w) * 128
+                               : Cfg::A_BYTES + s * Cfg::B_BYTES + ks * p.mn_kadv) >> 4;
+      }
       int stage = 0; uint32_t phase = 0;
       for (int it = 0; it < iters; ++it) {
         mbar_wait(full + stage, phase);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES) >> 4;
 #pragma unroll
         for (int s = 0; s < TG; ++s) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t ad = make_smem_desc(sa + ks * p.mn_kadv, p.mn_lbo, p.mn_sbo, p.mn_layout);
-            uint64_t bd;
-            if (HALO) {
-              const uint32_t baddr = sa + Cfg::A_BYTES + (p.h_krow[ks] + s * p.dil_w) * 128;
-              const uint32_t bo = p.h_base_mode == 1 ? (baddr >> 7) & 7 : p.h_base_mode == 2 ? (baddr >> 7) & 3 : 0;
-              bd = make_smem_desc(baddr, p.h_pitch, p.mn_sbo, p.mn_layout, bo);
-            } else {
-              bd = make_smem_desc(sa + Cfg::A_BYTES + s * Cfg::B_BYTES + ks * p.mn_kadv, p.mn_lbo, p.mn_sbo, p.mn_layout);
-            }
+            const uint64_t ad = a_tmpl | (uint64_t)(sa + a_off[ks]);
+            const uint64_t bd = b_tmpl | (uint64_t)(sa + b_off[s][ks]);
             mma_tf32_ss(tmem_base + s * BN, ad, bd, idesc, (it | ks) != 0);
           }
         }
@@ -617,47 +626,48 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
 // fused wgrad epilogue over the [split][K][RS][C] partial sums:
 //   g = sum_s part[s];  dW = (g*b + wd*W)[T==cur] ...  written in the module's [K][C][R][S] order
 // ------------------------------------------------------------------------------------------
-// One block handles `kb` consecutive output channels.  Phase 1: sum the splits of G[k][t][c]
-// (contiguous per k, 16-byte loads) into smem [t][c]; phase 2: walk the module's [k][c][t] order
-// (contiguous per k) with 16-byte accesses to W / P / T / dW / dP.  RS_T > 0: compile-time tap count.
+// One block handles `kb` consecutive output channels x `cc` input channels (blockIdx.y = channel
+// chunk).  Phase 1: sum the splits of G[k][t][c0..c0+cc) (16-byte loads) into smem [k][t][c]; phase 2:
+// walk the module's [k][c][t] order -- cc*RS contiguous elements per k -- with 16-byte accesses to
+// W / P / T / dW / dP.  RS_T > 0: compile-time tap count.
 template <int RS_T>
 __global__ void __launch_bounds__(256)
-wgrad_epilogue_krsc_kernel(const float *__restrict__ gpart, int splits, int K, int C, int Cg, int RS_rt, int kb,
+wgrad_epilogue_krsc_kernel(const float *__restrict__ gpart, int splits, int K, int C, int Cg, int RS_rt, int kb, int cc,
                            const float *__restrict__ w, const float *__restrict__ piggy,
                            const uint8_t *__restrict__ tmask, int cur, float wd, int mode, float thr,
                            float *__restrict__ dW, float *__restrict__ dP) {
-  extern __shared__ float sh[];  // [kb][RS][Cg + 1]
+  extern __shared__ float sh[];  // [kb][RS][cc + 1]
   griddep_launch_dependents();
   griddep_wait();
   const int RS = RS_T > 0 ? RS_T : RS_rt;
-  const int k0 = blockIdx.x * kb;
+  const int k0 = blockIdx.x * kb, c0 = blockIdx.y * cc;
   const int nk = min(kb, K - k0);
-  const int ld = Cg + 1;
+  const int ncc = min(cc, C - c0);               // multiple of 4
+  const int ld = cc + 1;
   const long long split_stride = (long long)K * RS * Cg;
-  const int row4 = Cg >> 2;                      // float4 per (k, t) row of G
-  const float4 *g4 = reinterpret_cast<const float4 *>(gpart + (long long)k0 * RS * Cg);
+  const int row4 = ncc >> 2;                     // float4 per (k, t) row segment
   for (int i = threadIdx.x; i < nk * RS * row4; i += blockDim.x) {
-    float4 a = __ldg(g4 + i);
+    const int row = i / row4, c = (i - row * row4) * 4;     // row = kk * RS + t
+    const float *src = gpart + ((long long)k0 * RS + row) * Cg + c0 + c;
+    float4 a = __ldg(reinterpret_cast<const float4 *>(src));
     for (int sp = 1; sp < splits; ++sp) {
-      const float4 b = __ldg(reinterpret_cast<const float4 *>(gpart + sp * split_stride + (long long)k0 * RS * Cg) + i);
+      const float4 b = __ldg(reinterpret_cast<const float4 *>(src + sp * split_stride));
       a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
     }
-    const int row = i / row4, c = (i - row * row4) * 4;     // row = kk * RS + t
     float *d = sh + row * ld + c;
     d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w;
   }
   __syncthreads();
   const bool has_p = piggy != nullptr;
-  const int per_k = C * RS;                      // C % 4 == 0 on this path => per_k % 4 == 0
-  const long long base = (long long)k0 * per_k;
+  const int per_k = ncc * RS;                    // contiguous elements of one k in this chunk (multiple of 4)
   for (int i4 = threadIdx.x; i4 < (nk * per_k) >> 2; i4 += blockDim.x) {
     const int i = i4 << 2;
-    const long long idx = base + i;
+    const int kk = i / per_k;
+    int rem = i - kk * per_k;
+    const long long idx = ((long long)(k0 + kk) * C + c0) * RS + rem;
     const float4 wv = __ldg(reinterpret_cast<const float4 *>(w + idx));
     const float4 pv = has_p ? __ldg(reinterpret_cast<const float4 *>(piggy + idx)) : make_float4(0, 0, 0, 0);
     const uchar4 tv = tmask ? __ldg(reinterpret_cast<const uchar4 *>(tmask + idx)) : make_uchar4(0, 0, 0, 0);
-    const int kk = i / per_k;
-    int rem = i - kk * per_k;
     int c = rem / RS, t = rem - c * RS;
     const float *srow = sh + kk * RS * ld;
     float g[4];
@@ -1101,24 +1111,27 @@ static int implicit_wgrad_fused(const cpgb_conv_desc &d, const float *x, const f
     return CPGB_OK;
   }
   if (d.C % 4 == 0 && vec_ok) {
-    // ~18 KB of G per block: 1 output channel at C*RS = 4608, 8 at 576
-    int kb = std::max(1, 4608 / (d.C * RS));
-    kb = std::min(kb, std::max(1, d.K / (2 * num_sms())));   // but keep >= 2 blocks per SM
-    size_t sh = (size_t)kb * RS * (p.Cg + 1) * sizeof(float);
-    if (sh <= 96 * 1024) {
+    // ~1152 elements of (k, channel chunk) per block, >= 2 blocks per SM: channel chunks of 128, or 32
+    // when the layer has few output channels
+    int cc = std::min(d.C, 128), kb = 1;
+    while (cc > 32 && (long long)d.K * cdiv_i(d.C, cc) < 2LL * num_sms()) cc >>= 1;
+    cc = (cc + 3) & ~3;
+    while (kb < 8 && (long long)(d.K / (2 * kb)) * cdiv_i(d.C, cc) >= 2LL * num_sms() && 2 * kb * cc * RS <= 4608) kb *= 2;
+    size_t sh = (size_t)kb * RS * (cc + 1) * sizeof(float);
+    if (sh <= 96 * 1024 && (cc * RS) % 4 == 0) {
       static bool attr_done = false;
       if (!attr_done) {
         CPGB_CUDA_OK(cudaFuncSetAttribute(wgrad_epilogue_krsc_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         CPGB_CUDA_OK(cudaFuncSetAttribute(wgrad_epilogue_krsc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         attr_done = true;
       }
-      const int egrid = cdiv_i(d.K, kb);
+      const dim3 egrid(cdiv_i(d.K, kb), cdiv_i(d.C, cc));
       if (RS == 9)
-        CPGB_CUDA_OK(launch_pdl(wgrad_epilogue_krsc_kernel<9>, dim3(egrid), dim3(256), sh, st, (const float *)p.gpart,
-                                pl.splits, d.K, d.C, p.Cg, RS, kb, w, piggy, tmask, cur, wd, mode, thr, dW, dP));
+        CPGB_CUDA_OK(launch_pdl(wgrad_epilogue_krsc_kernel<9>, egrid, dim3(256), sh, st, (const float *)p.gpart,
+                                pl.splits, d.K, d.C, p.Cg, RS, kb, cc, w, piggy, tmask, cur, wd, mode, thr, dW, dP));
       else
-        CPGB_CUDA_OK(launch_pdl(wgrad_epilogue_krsc_kernel<0>, dim3(egrid), dim3(256), sh, st, (const float *)p.gpart,
-                                pl.splits, d.K, d.C, p.Cg, RS, kb, w, piggy, tmask, cur, wd, mode, thr, dW, dP));
+        CPGB_CUDA_OK(launch_pdl(wgrad_epilogue_krsc_kernel<0>, egrid, dim3(256), sh, st, (const float *)p.gpart,
+                                pl.splits, d.K, d.C, p.Cg, RS, kb, cc, w, piggy, tmask, cur, wd, mode, thr, dW, dP));
       CPGB_LAUNCH_OK("wgrad_epilogue_krsc");
       return CPGB_OK;
     }
