@@ -176,6 +176,7 @@ struct SmemTail {
   uint64_t full[8];
   uint64_t empty[8];
   uint64_t acc_full;
+  uint64_t aux_full;        // fused wgrad epilogue: W / P / T tiles have landed
   uint32_t tmem_slot;
   uint32_t pad;
   float *rowptr[4][32];     // per epilogue warp: destination row pointers (nullptr = skip)
@@ -422,6 +423,7 @@ struct WgradParams {
   int h_krow[4];           // first X-tile row of each 8-pixel K step (tap 0)
   int h_base_mode;
   // fused epilogue (only RS == 1, one split): SURVEY K6-K8 applied straight from TMEM
+  int f_nstage, f_region_bytes;   // fused: ring depth, size of the [stage ring | epilogue scratch] region
   int fused, cur, mode;
   float wd, thr;
   const float *w, *piggy;
@@ -448,13 +450,21 @@ struct WgradCfg {
 template <int BN, int TG, bool HALO>
 __global__ void __launch_bounds__(192)
 wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
-                  const WgradParams p) {
+                  const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmP,
+                  const __grid_constant__ CUtensorMap tmT, const WgradParams p) {
   using Cfg = WgradCfg<BN, TG>;
-  const int NSTAGE = HALO ? p.h_nstage : Cfg::NSTAGE;
+  constexpr bool CAN_FUSE = TG == 1 && BN == 128 && !HALO;
+  const bool fused = CAN_FUSE && p.fused;
+  const int NSTAGE = HALO ? p.h_nstage : fused ? p.f_nstage : Cfg::NSTAGE;
   const int STAGE_BYTES = HALO ? p.h_stage_bytes : Cfg::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  SmemTail *tail = reinterpret_cast<SmemTail *>(smem + NSTAGE * STAGE_BYTES);
+  // fused: [ring / scratch region][W tile 64 KB][P tile 64 KB if piggy][T tile 16 KB][tail]
+  const bool f_has_p = fused && p.piggy != nullptr;
+  uint8_t *sW = smem + p.f_region_bytes;
+  uint8_t *sP = sW + 128 * 128 * 4;
+  uint8_t *sT = sP + (f_has_p ? 128 * 128 * 4 : 0);
+  SmemTail *tail = reinterpret_cast<SmemTail *>(fused ? sT + 128 * 128 : smem + NSTAGE * STAGE_BYTES);
   uint64_t *full = tail->full, *empty = tail->empty, *acc_full = &tail->acc_full;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -472,6 +482,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     prefetch_tensormap(&tmX);
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
     mbar_init(acc_full, 1);
+    mbar_init(&tail->aux_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -487,6 +498,13 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
 
   if (warp == 0) {
     if (lane == 0) {
+      if (fused) {
+        // the epilogue's operands: in flight during the whole main loop
+        mbar_arrive_expect_tx(&tail->aux_full, 128 * 128 * 4 * (f_has_p ? 2 : 1) + (p.tmask ? 128 * 128 : 0));
+        tma_load_2d(sW, &tmW, &tail->aux_full, c0, k0);
+        if (f_has_p) tma_load_2d(sP, &tmP, &tail->aux_full, c0, k0);
+        if (p.tmask) tma_load_2d(sT, &tmT, &tail->aux_full, c0, k0);
+      }
       int stage = 0; uint32_t phase = 0;
       for (int it = 0; it < iters; ++it) {
         int ch = ch_beg + it;
@@ -554,54 +572,30 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     mbar_wait(acc_full, 0);
     tc_fence_after();
     float *ts = reinterpret_cast<float *>(smem) + quad * 32 * (BN + 4);
-    if (p.fused) {
-      // linear / 1x1 layer, single split: G has the module's [K][C] layout, finish the gradient here.
-      // Rows are processed in batches with all loads of a batch issued before the first use.
-      const bool has_p = p.piggy != nullptr;
-      constexpr int LD = BN + 4, LPR = BN / 4, RPP = 32 / LPR, BATCH = 8;
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        float v[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4 *>(ts + lane * LD + c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-      }
-      __syncwarp();
-      const int rsub = lane / LPR, c4 = (lane % LPR) * 4;
-      const int c = c0 + c4;
-#pragma unroll 1
-      for (int r0 = 0; r0 < 32; r0 += RPP * BATCH) {
-        float4 wv[BATCH], pv[BATCH];
-        uchar4 tv[BATCH];
-        bool ok[BATCH];
-#pragma unroll
-        for (int b = 0; b < BATCH; ++b) {
-          const int k = kbase + r0 + b * RPP + rsub;
-          ok[b] = k < p.K && c < p.C;
-          const long long idx = (long long)k * p.C + c;
-          wv[b] = ok[b] ? __ldg(reinterpret_cast<const float4 *>(p.w + idx)) : make_float4(0, 0, 0, 0);
-          pv[b] = (ok[b] && has_p) ? __ldg(reinterpret_cast<const float4 *>(p.piggy + idx)) : make_float4(0, 0, 0, 0);
-          tv[b] = (ok[b] && p.tmask) ? __ldg(reinterpret_cast<const uchar4 *>(p.tmask + idx)) : make_uchar4(0, 0, 0, 0);
-        }
-#pragma unroll
-        for (int b = 0; b < BATCH; ++b) {
-          const int rr = r0 + b * RPP + rsub;
-          float4 g = *reinterpret_cast<const float4 *>(ts + rr * LD + c4);
+    if (fused) {
+      // linear / 1x1 layer, single split: G has the module's [K][C] layout -- finish the gradient here
+      // from the prefetched W / P / T tiles; the epilogue only stores to global memory.
+      const bool has_p = f_has_p;
+      mbar_wait(&tail->aux_full, 0);
+      const float *w_s = reinterpret_cast<const float *>(sW);
+      const float *p_s = reinterpret_cast<const float *>(sP);
+      epilogue_rows<BN>(tmem_base, quad, 0, ts, lane, [&](int rr, int c4, float4 g) {
+        const int row = quad * 32 + rr, k = kbase + rr, c = c0 + c4;
+        if (k < p.K && c < p.C) {
           g.x *= DEBIAS_TWO; g.y *= DEBIAS_TWO; g.z *= DEBIAS_TWO; g.w *= DEBIAS_TWO;
+          const float4 wv = *reinterpret_cast<const float4 *>(w_s + row * 128 + c4);
+          const float4 pv = has_p ? *reinterpret_cast<const float4 *>(p_s + row * 128 + c4) : make_float4(0, 0, 0, 0);
+          const uchar4 tv = p.tmask ? *reinterpret_cast<const uchar4 *>(sT + row * 128 + c4) : make_uchar4(0, 0, 0, 0);
           float4 ow, op;
-          epi_one_tc(g.x, wv[b].x, pv[b].x, has_p, tv[b].x, p.cur, p.wd, p.mode, p.thr, ow.x, op.x);
-          epi_one_tc(g.y, wv[b].y, pv[b].y, has_p, tv[b].y, p.cur, p.wd, p.mode, p.thr, ow.y, op.y);
-          epi_one_tc(g.z, wv[b].z, pv[b].z, has_p, tv[b].z, p.cur, p.wd, p.mode, p.thr, ow.z, op.z);
-          epi_one_tc(g.w, wv[b].w, pv[b].w, has_p, tv[b].w, p.cur, p.wd, p.mode, p.thr, ow.w, op.w);
-          if (ok[b]) {
-            const long long idx = (long long)(kbase + rr) * p.C + c;
-            *reinterpret_cast<float4 *>(p.dW + idx) = ow;
-            if (p.dP) *reinterpret_cast<float4 *>(p.dP + idx) = op;
-          }
+          epi_one_tc(g.x, wv.x, pv.x, has_p, tv.x, p.cur, p.wd, p.mode, p.thr, ow.x, op.x);
+          epi_one_tc(g.y, wv.y, pv.y, has_p, tv.y, p.cur, p.wd, p.mode, p.thr, ow.y, op.y);
+          epi_one_tc(g.z, wv.z, pv.z, has_p, tv.z, p.cur, p.wd, p.mode, p.thr, ow.z, op.z);
+          epi_one_tc(g.w, wv.w, pv.w, has_p, tv.w, p.cur, p.wd, p.mode, p.thr, ow.w, op.w);
+          const long long idx = (long long)k * p.C + c;
+          *reinterpret_cast<float4 *>(p.dW + idx) = ow;
+          if (p.dP) *reinterpret_cast<float4 *>(p.dP + idx) = op;
         }
-      }
+      });
     } else {
 #pragma unroll 1
       for (int s = 0; s < TG; ++s) {
@@ -867,12 +861,13 @@ static WgradPlan plan_wgrad(const cpgb_conv_desc &d) {
   return pl;
 }
 static bool wgrad_fusable(const cpgb_conv_desc &d, const WgradPlan &pl) {
-  // Measured on B200 (tests/time_ops.py, FC 4096x4096 @ batch 128): finishing the gradient inside
-  // the GEMM epilogue costs 133 us (4 epilogue warps per CTA expose the latency of the W / T loads),
-  // writing G and running the streaming epilogue kernel 75 us.  Off until the W / T tiles are
-  // prefetched into shared memory by TMA during the main loop.
+  // Linear / 1x1 layers with a single split CAN finish the gradient inside the GEMM (CPGB_WGRAD_FUSE=1): the
+  // CTA's W / P / T tiles are prefetched into shared memory by TMA during the main loop and the epilogue only
+  // stores.  Measured on B200 (tests/time_ops.py, FC 4096x4096 @ batch 128) it loses to "write G (stays in
+  // L2) + streaming epilogue kernel": 93 us fused with TMA prefetch (one 183 KB CTA per SM, 7 rounds), 133 us
+  // fused with the epilogue warps loading W / T themselves, 79 us unfused (two CTAs per SM).  Off by default.
   static const bool fuse = getenv("CPGB_WGRAD_FUSE") != nullptr;
-  return fuse && d.R * d.S == 1 && pl.splits == 1 && d.C % 4 == 0;
+  return fuse && d.R * d.S == 1 && pl.splits == 1 && pl.BN == 128 && pl.TG == 1 && !pl.halo && d.C % 16 == 0;
 }
 
 static size_t implicit_workspace_bytes(const cpgb_conv_desc &d) {
@@ -1017,18 +1012,21 @@ static int implicit_dgrad(const cpgb_conv_desc &d, const float *dy, const float 
   return run_gemm<true>(g, ta, tb, p, dx, nullptr, part, part_bytes, st);
 }
 
+struct FusedMaps { CUtensorMap w, p, t; };
 template <int BN, int TG, bool HALO>
-static int launch_wgrad(const CUtensorMap &tdy, const CUtensorMap &tx, const WgradParams &p, dim3 grid,
-                        cudaStream_t st) {
+static int launch_wgrad(const CUtensorMap &tdy, const CUtensorMap &tx, const FusedMaps &fm, const WgradParams &p,
+                        dim3 grid, cudaStream_t st) {
   using Cfg = WgradCfg<BN, TG>;
-  const int smem_bytes = HALO ? p.h_nstage * p.h_stage_bytes + 1024 + TAIL_BYTES : Cfg::SMEM_BYTES;
+  int smem_bytes = HALO ? p.h_nstage * p.h_stage_bytes + 1024 + TAIL_BYTES : Cfg::SMEM_BYTES;
+  if (p.fused) smem_bytes = p.f_region_bytes + 128 * 128 * 4 * (p.piggy ? 2 : 1) + 128 * 128 + 1024 + TAIL_BYTES;
   static bool attr_done = false;
   if (!attr_done) {
     CPGB_CUDA_OK(cudaFuncSetAttribute(wgrad_gemm_kernel<BN, TG, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      HALO ? 227 * 1024 : Cfg::SMEM_BYTES));
+                                      (HALO || (TG == 1 && BN == 128)) ? 227 * 1024 : Cfg::SMEM_BYTES));
     attr_done = true;
   }
-  CPGB_CUDA_OK(launch_pdl(wgrad_gemm_kernel<BN, TG, HALO>, grid, dim3(192), (size_t)smem_bytes, st, tdy, tx, p));
+  CPGB_CUDA_OK(launch_pdl(wgrad_gemm_kernel<BN, TG, HALO>, grid, dim3(192), (size_t)smem_bytes, st, tdy, tx, fm.w, fm.p,
+                          fm.t, p));
   CPGB_LAUNCH_OK("wgrad_gemm_kernel");
   return CPGB_OK;
 }
@@ -1053,7 +1051,7 @@ static int implicit_wgrad_fused(const cpgb_conv_desc &d, const float *x, const f
   const int RS = d.R * d.S;
   const bool vec_ok = aligned16p(w) && aligned16p(dW) && (!piggy || aligned16p(piggy)) && (!dP || aligned16p(dP)) &&
                       (!tmask || (reinterpret_cast<uintptr_t>(tmask) & 3) == 0);
-  const bool fused = wgrad_fusable(d, pl) && vec_ok;
+  const bool fused = wgrad_fusable(d, pl) && vec_ok && (!tmask || aligned16p(tmask));
   const size_t need = fused ? 0 : (size_t)pl.splits * d.K * RS * cg_of(d) * sizeof(float);
   if (ws_bytes < need) { set_error("workspace %zu < %zu", ws_bytes, need); return CPGB_EWORKSPACE; }
   CUtensorMap tdy, tx;
@@ -1092,12 +1090,41 @@ static int implicit_wgrad_fused(const cpgb_conv_desc &d, const float *x, const f
   p.fused = fused ? 1 : 0; p.cur = cur; p.mode = mode; p.wd = wd; p.thr = thr;
   p.w = w; p.piggy = piggy; p.tmask = tmask; p.dW = dW; p.dP = dP;
   dim3 grid(pl.ktiles * pl.ctiles, pl.groups, pl.splits);
+  FusedMaps fm;
+  fm.w = fm.p = fm.t = tdy;        // placeholders unless fused
+  p.f_nstage = 0; p.f_region_bytes = 0;
+  if (fused) {
+    // W / P tiles: fp32 [K][C] boxes of 128 x 128, T tile: uint8; no swizzle (read row-wise by the epilogue)
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return CPGB_ECUDA; }
+    cuuint64_t gd[2] = {(cuuint64_t)d.C, (cuuint64_t)d.K};
+    cuuint32_t bx[2] = {128, 128}, es[2] = {1, 1};
+    cuuint64_t gs4[1] = {(cuuint64_t)d.C * 4}, gs1[1] = {(cuuint64_t)d.C};
+    CUresult r1 = enc(&fm.w, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(w), gd, gs4, bx, es,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r2 = piggy ? enc(&fm.p, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(piggy), gd, gs4, bx, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)
+                        : CUDA_SUCCESS;
+    CUresult r3 = tmask ? enc(&fm.t, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t *>(tmask), gd, gs1, bx, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)
+                        : CUDA_SUCCESS;
+    if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS || r3 != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled failed for the fused wgrad epilogue tiles (%d %d %d)", (int)r1, (int)r2, (int)r3);
+      return CPGB_ECUDA;
+    }
+    p.f_nstage = piggy ? 2 : 3;
+    const int scratch = 4 * 32 * (128 + 4) * 4;
+    p.f_region_bytes = (int)align_up((size_t)std::max(p.f_nstage * WgradCfg<128, 1>::STAGE_BYTES, scratch), 1024);
+  }
   if (pl.halo) {
-    rc = pl.BN == 128 ? launch_wgrad<128, 3, true>(tdy, tx, p, grid, st) : launch_wgrad<64, 3, true>(tdy, tx, p, grid, st);
+    rc = pl.BN == 128 ? launch_wgrad<128, 3, true>(tdy, tx, fm, p, grid, st) : launch_wgrad<64, 3, true>(tdy, tx, fm, p, grid, st);
   } else if (pl.TG == 3) {
-    rc = pl.BN == 128 ? launch_wgrad<128, 3, false>(tdy, tx, p, grid, st) : launch_wgrad<64, 3, false>(tdy, tx, p, grid, st);
+    rc = pl.BN == 128 ? launch_wgrad<128, 3, false>(tdy, tx, fm, p, grid, st) : launch_wgrad<64, 3, false>(tdy, tx, fm, p, grid, st);
   } else {
-    rc = pl.BN == 128 ? launch_wgrad<128, 1, false>(tdy, tx, p, grid, st) : launch_wgrad<64, 1, false>(tdy, tx, p, grid, st);
+    rc = pl.BN == 128 ? launch_wgrad<128, 1, false>(tdy, tx, fm, p, grid, st) : launch_wgrad<64, 1, false>(tdy, tx, fm, p, grid, st);
   }
   if (rc || fused) return rc;
   if (RS == 1 && vec_ok && d.C % 4 == 0) {
