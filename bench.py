@@ -649,10 +649,17 @@ def main():
         achieved = flops[dom] / (tot[dom] * 1e-3) / 1e12
         kname = {'fprop': 'conv_gemm_kernel<BN,false>', 'dgrad': 'conv_gemm_kernel<BN,true>',
                  'wgrad': 'wgrad_gemm_kernel<BN,TG,HALO> + wgrad epilogue'}[dom]
+        traffic = None
+        try:   # DRAM bytes of the same launches from an ncu capture (profiles/dram_traffic_from_ncu.py)
+            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'r1_dram_traffic.json')))[dom]['dram_bytes']
+        except Exception:
+            pass
         line['roofline'] = {
             'bound': 'tensor', 'kernel': f'{kname}: masked implicit-GEMM {dom}, the 15 sharable layers of one step',
             'achieved': achieved, 'peak': tf32_peak, 'unit': 'TFLOP/s', 'frac': achieved / tf32_peak,
-            'traffic': None,
+            'traffic': traffic,
+            'traffic_note': 'dram__bytes_read+write summed over the 15 launches of this pass (ncu, cold caches; '
+                            'profiles/r1_dram_traffic.json); the pass is tensor/shared-memory bound, not HBM bound',
             'peak_source': 'measured in this run: cuBLAS TF32 torch.matmul 8192^3 best of 10 (TF32 is not in '
                            'MEASURED_PEAKS.json, which holds bf16 only); tcgen05 kind::tf32 issues at exactly half '
                            'the bf16 rate (tests/mma_rate.py: 2047 MAC/clk/SM)',

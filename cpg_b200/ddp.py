@@ -32,6 +32,9 @@ class GradAllReducer:
     def __init__(self, model, world=None, overlap=True, group=None):
         self.world = world if world is not None else dist.get_world_size(group)
         self.group = group
+        # NCCL averages inside the collective; gloo (CPU tests) only sums
+        self.avg = self.world > 1 and dist.get_backend(group) == 'nccl'
+        self.op = dist.ReduceOp.AVG if self.avg else dist.ReduceOp.SUM
         self.params = [p for p in model.parameters() if p.requires_grad]
         self.pending = []
         self.overlap = overlap
@@ -43,8 +46,7 @@ class GradAllReducer:
 
     def _hook(self, p):
         if p.grad is not None:
-            self.pending.append((p.grad, dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=self.group,
-                                                         async_op=True)))
+            self.pending.append((p.grad, dist.all_reduce(p.grad, op=self.op, group=self.group, async_op=True)))
 
     def reduce(self):
         """Call after backward(): waits for the overlapped reductions, reduces everything else
@@ -54,14 +56,16 @@ class GradAllReducer:
         done = set()
         for g, work in self.pending:
             work.wait()
-            g.div_(self.world)
+            if not self.avg:
+                g.div_(self.world)
             done.add(g.data_ptr())
         self.pending = []
         rest = [p.grad for p in self.params if p.grad is not None and p.grad.data_ptr() not in done]
         if rest:
             flat = torch.cat([g.reshape(-1) for g in rest])
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
-            flat.div_(self.world)
+            dist.all_reduce(flat, op=self.op, group=self.group)
+            if not self.avg:
+                flat.div_(self.world)
             off = 0
             for g in rest:
                 n = g.numel()
