@@ -78,7 +78,8 @@ void cpgb_linear_desc(cpgb_conv_desc *d, int32_t M, int32_t I, int32_t O) {
 
 size_t cpgb_workspace_bytes(const cpgb_conv_desc *d) {
   if (!d || d->groups <= 0) return 0;
-  size_t g_bytes = weight_elems(d) * sizeof(float);           // raw weight gradient (CUDA-core wgrad)
+  // raw weight-gradient partial sums of the CUDA-core wgrad: one tensor per split of the pixel reduction
+  size_t g_bytes = weight_elems(d) * sizeof(float) * (size_t)simt_wgrad_splits(make_geom(*d));
   size_t tc = tc_workspace_bytes(*d);                          // staged operand / split-K partial sums
   g_bytes = (g_bytes + 255) & ~(size_t)255;
   return g_bytes > tc ? g_bytes : tc;
@@ -213,12 +214,13 @@ int cpgb_conv2d_wgrad_fused(const cpgb_conv_desc *d, const float *x, const float
     if ((rc = tc_wgrad_fused(*d, x, dy, w, piggy, tmask, cur, weight_decay, mode, thr, dW, dP, ws, ws_bytes, st)))
       return rc;
   } else {
+    int splits = 1;
     if (d->N == 0) {
       CPGB_CUDA_OK(cudaMemsetAsync(gbuf, 0, n * sizeof(float), st));
-    } else if ((rc = simt_wgrad_raw(g, x, dy, gbuf, st))) {
+    } else if ((rc = simt_wgrad_raw(g, x, dy, gbuf, &splits, st))) {
       return rc;
     }
-    if ((rc = wgrad_epilogue(gbuf, w, piggy, tmask, (long long)n, cur, weight_decay, mode, thr, dW, dP, st)))
+    if ((rc = wgrad_epilogue(gbuf, splits, w, piggy, tmask, (long long)n, cur, weight_decay, mode, thr, dW, dP, st)))
       return rc;
   }
   if (dbias) {

@@ -64,13 +64,14 @@ int simt_fprop(const Geom &g, const float *x, const float *w, const float *piggy
                float *y, float thr, cudaStream_t st);
 int simt_dgrad(const Geom &g, const float *dy, const float *w, const float *piggy, float *dx, float thr,
                cudaStream_t st);
-// raw weight gradient into gbuf[K*Cg*R*S] (fp32, overwritten)
-int simt_wgrad_raw(const Geom &g, const float *x, const float *dy, float *gbuf, cudaStream_t st);
+// raw weight-gradient partial sums gbuf[splits][K*Cg*R*S] (fp32, overwritten; fixed reduction order)
+int simt_wgrad_splits(const Geom &g);
+int simt_wgrad_raw(const Geom &g, const float *x, const float *dy, float *gbuf, int *splits_out, cudaStream_t st);
 int bias_grad(const Geom &g, const float *dy, float *dbias, cudaStream_t st);
 
 // fused epilogue g -> (dW, dP)  
-int wgrad_epilogue(const float *gbuf, const float *w, const float *piggy, const uint8_t *tmask, long long n,
-                   int cur, float wd, int mode, float thr, float *dW, float *dP, cudaStream_t st);
+int wgrad_epilogue(const float *gbuf, int splits, const float *w, const float *piggy, const uint8_t *tmask,
+                   long long n, int cur, float wd, int mode, float thr, float *dW, float *dP, cudaStream_t st);
 
 // tcgen05 implicit GEMM (tc_conv.cu).  tc_eligible() says whether the shape is supported.
 bool tc_eligible(const cpgb_conv_desc &d, int op);  // op: 0 fprop, 1 dgrad, 2 wgrad

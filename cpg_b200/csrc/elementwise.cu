@@ -60,9 +60,9 @@ __device__ __forceinline__ void epi_one(float g, float w, float p, bool has_p, u
 }
 
 __global__ void __launch_bounds__(256)
-wgrad_epilogue_kernel(const float *__restrict__ g, const float *__restrict__ w, const float *__restrict__ piggy,
-                      const uint8_t *__restrict__ tmask, long long n, int cur, float wd, int mode, float thr,
-                      float *__restrict__ dW, float *__restrict__ dP, bool vec) {
+wgrad_epilogue_kernel(const float *__restrict__ g, int splits, const float *__restrict__ w,
+                      const float *__restrict__ piggy, const uint8_t *__restrict__ tmask, long long n, int cur, float wd,
+                      int mode, float thr, float *__restrict__ dW, float *__restrict__ dP, bool vec) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool has_p = piggy != nullptr;
@@ -71,6 +71,10 @@ wgrad_epilogue_kernel(const float *__restrict__ g, const float *__restrict__ w, 
     const long long n4 = n >> 2;
     for (long long v = i0; v < n4; v += stride) {
       float4 gg = __ldg(reinterpret_cast<const float4 *>(g) + v);
+      for (int sp = 1; sp < splits; ++sp) {     // fixed order: deterministic sums
+        const float4 b = __ldg(reinterpret_cast<const float4 *>(g + sp * n) + v);
+        gg.x += b.x; gg.y += b.y; gg.z += b.z; gg.w += b.w;
+      }
       float4 ww = __ldg(reinterpret_cast<const float4 *>(w) + v);
       float4 pp = has_p ? __ldg(reinterpret_cast<const float4 *>(piggy) + v) : make_float4(0, 0, 0, 0);
       uchar4 tt = tmask ? __ldg(reinterpret_cast<const uchar4 *>(tmask) + v) : make_uchar4(0, 0, 0, 0);
@@ -85,18 +89,20 @@ wgrad_epilogue_kernel(const float *__restrict__ g, const float *__restrict__ w, 
     tail = n4 << 2;
   }
   for (long long i = tail + i0; i < n; i += stride) {
-    float ow, op;
-    epi_one(g[i], w[i], has_p ? piggy[i] : 0.f, has_p, tmask ? tmask[i] : 0u, cur, wd, mode, thr, ow, op);
+    float ow, op, gs = g[i];
+    for (int sp = 1; sp < splits; ++sp) gs += g[sp * n + i];
+    epi_one(gs, w[i], has_p ? piggy[i] : 0.f, has_p, tmask ? tmask[i] : 0u, cur, wd, mode, thr, ow, op);
     dW[i] = ow;
     if (dP) dP[i] = op;
   }
 }
 
-int wgrad_epilogue(const float *gbuf, const float *w, const float *piggy, const uint8_t *tmask, long long n,
-                   int cur, float wd, int mode, float thr, float *dW, float *dP, cudaStream_t st) {
+int wgrad_epilogue(const float *gbuf, int splits, const float *w, const float *piggy, const uint8_t *tmask,
+                   long long n, int cur, float wd, int mode, float thr, float *dW, float *dP, cudaStream_t st) {
   bool vec = aligned16(gbuf) && aligned16(w) && aligned16(dW) && (!piggy || aligned16(piggy)) &&
-             (!dP || aligned16(dP)) && (!tmask || (reinterpret_cast<uintptr_t>(tmask) & 3) == 0);
-  wgrad_epilogue_kernel<<<grid_for(n / 4 + 1), 256, 0, st>>>(gbuf, w, piggy, tmask, n, cur, wd, mode, thr, dW,
+             (!dP || aligned16(dP)) && (!tmask || (reinterpret_cast<uintptr_t>(tmask) & 3) == 0) &&
+             (splits == 1 || n % 4 == 0);
+  wgrad_epilogue_kernel<<<grid_for(n / 4 + 1), 256, 0, st>>>(gbuf, splits, w, piggy, tmask, n, cur, wd, mode, thr, dW,
                                                             dP, vec);
   CPGB_LAUNCH_OK("wgrad_epilogue");
   return CPGB_OK;

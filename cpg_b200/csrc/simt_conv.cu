@@ -33,7 +33,7 @@ struct FpropProb {
     long long idx = (long long)(grp * g.Kg + j) * g.Cg * g.RS + kd;
     return masked_weight(__ldg(w + idx), piggy, idx, thr);
   }
-  __device__ void store(int grp, int m, int j, float acc, bool) const {
+  __device__ void store(int grp, int m, int j, float acc, int) const {
     int n = m / g.PQ, pq = m - n * g.PQ, p = pq / g.Q, q = pq - p * g.Q;
     int k = grp * g.Kg + j;
     y[n * g.ys0 + k * g.ys1 + p * g.ys2 + q * g.ys3] = acc + (bias ? __ldg(bias + k) : 0.f);
@@ -60,14 +60,14 @@ struct DgradProb {
     long long idx = ((long long)(grp * g.Kg + kk) * g.Cg + c) * g.RS + rs;
     return masked_weight(__ldg(w + idx), piggy, idx, thr);
   }
-  __device__ void store(int grp, int m, int c, float acc, bool) const {
+  __device__ void store(int grp, int m, int c, float acc, int) const {
     int n = m / g.HW, hw = m - n * g.HW, h = hw / g.W, ww = hw - h * g.W;
     dx[n * g.xs0 + (long long)(grp * g.Cg + c) * g.xs1 + h * g.xs2 + ww * g.xs3] = acc;
   }
 };
 
 struct WgradProb {
-  Geom g; const float *x, *dy; float *gbuf;
+  Geom g; const float *x, *dy; float *gbuf; long long split_stride;   // gbuf[split][K*Cg*R*S]
   static constexpr bool A_M_FAST = false, B_N_FAST = false;
   __device__ int M() const { return g.Kg; }
   __device__ int Ncols() const { return g.Cg * g.RS; }
@@ -83,9 +83,9 @@ struct WgradProb {
     if ((unsigned)h >= (unsigned)g.H || (unsigned)ww >= (unsigned)g.W) return 0.f;
     return __ldg(x + n * g.xs0 + (long long)(grp * g.Cg + c) * g.xs1 + h * g.xs2 + ww * g.xs3);
   }
-  __device__ void store(int grp, int j, int crs, float acc, bool split) const {
-    float *dst = gbuf + (long long)(grp * g.Kg + j) * g.Cg * g.RS + crs;
-    if (split) atomicAdd(dst, acc); else *dst = acc;
+  __device__ void store(int grp, int j, int crs, float acc, int split) const {
+    // every split owns a full partial tensor: the reduction order is fixed (summed by the epilogue)
+    gbuf[split * split_stride + (long long)(grp * g.Kg + j) * g.Cg * g.RS + crs] = acc;
   }
 };
 
@@ -139,7 +139,6 @@ __global__ void __launch_bounds__(NTHREADS) simt_gemm_kernel(const Prob pb, int 
     }
     __syncthreads();
   }
-  const bool is_split = splits > 1;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     int m = m0 + ty * 4 + i;
@@ -147,7 +146,7 @@ __global__ void __launch_bounds__(NTHREADS) simt_gemm_kernel(const Prob pb, int 
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int n = n0 + tx * 4 + j;
-      if (n < NC) pb.store(grp, m, n, acc[i][j], is_split);
+      if (n < NC) pb.store(grp, m, n, acc[i][j], split);
     }
   }
 }
@@ -172,8 +171,7 @@ int simt_dgrad(const Geom &g, const float *dy, const float *w, const float *pigg
   return CPGB_OK;
 }
 
-int simt_wgrad_raw(const Geom &g, const float *x, const float *dy, float *gbuf, cudaStream_t st) {
-  WgradProb pb{g, x, dy, gbuf};
+static void simt_wgrad_plan(const Geom &g, int *splits_out, int *kchunk_out) {
   const long long kd = (long long)g.N * g.PQ;
   const int tiles = cdiv(g.Kg, BM) * cdiv((long long)g.Cg * g.RS, BN) * g.groups;
   // split the pixel reduction so that ~2 waves of CTAs exist (148 SMs)
@@ -182,12 +180,25 @@ int simt_wgrad_raw(const Geom &g, const float *x, const float *dy, float *gbuf, 
   if (splits < 1) splits = 1;
   int kchunk = (int)((kd + splits - 1) / splits);
   kchunk = ((kchunk + BK - 1) / BK) * BK;
-  splits = (int)((kd + kchunk - 1) / kchunk);
-  if (splits > 1)
-    CPGB_CUDA_OK(cudaMemsetAsync(gbuf, 0, sizeof(float) * (size_t)g.K * g.Cg * g.RS, st));
+  *splits_out = (int)((kd + kchunk - 1) / kchunk);
+  *kchunk_out = kchunk;
+}
+
+int simt_wgrad_splits(const Geom &g) {
+  int splits, kchunk;
+  simt_wgrad_plan(g, &splits, &kchunk);
+  return splits;
+}
+
+// raw weight-gradient partial sums gbuf[split][K*Cg*R*S]; returns the number of splits
+int simt_wgrad_raw(const Geom &g, const float *x, const float *dy, float *gbuf, int *splits_out, cudaStream_t st) {
+  int splits, kchunk;
+  simt_wgrad_plan(g, &splits, &kchunk);
+  WgradProb pb{g, x, dy, gbuf, (long long)g.K * g.Cg * g.RS};
   dim3 grid(cdiv(g.Kg, BM), cdiv((long long)g.Cg * g.RS, BN), g.groups * splits);
   simt_gemm_kernel<WgradProb><<<grid, NTHREADS, 0, st>>>(pb, splits, kchunk);
   CPGB_LAUNCH_OK("simt_wgrad");
+  *splits_out = splits;
   return CPGB_OK;
 }
 
