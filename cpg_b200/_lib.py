@@ -14,7 +14,7 @@ PATH_AUTO, PATH_SIMT, PATH_TCGEN05 = 0, 1, 2
 EXPORTS = [
     'cpgb_version', 'cpgb_last_error', 'cpgb_set_path', 'cpgb_get_path', 'cpgb_launch_count', 'cpgb_linear_desc',
     'cpgb_workspace_bytes', 'cpgb_staged_weight_bytes', 'cpgb_stage_weights', 'cpgb_staged_weight_bytes_for',
-    'cpgb_stage_weights_batched', 'cpgb_binarize', 'cpgb_conv2d_fprop', 'cpgb_conv2d_dgrad',
+    'cpgb_stage_weights_batched', 'cpgb_weights_usable_raw', 'cpgb_weights_usable_raw_for', 'cpgb_binarize', 'cpgb_conv2d_fprop', 'cpgb_conv2d_dgrad',
     'cpgb_conv2d_wgrad_fused', 'cpgb_grad_epilogue', 'cpgb_prune_workspace_bytes', 'cpgb_prune_select',
     'cpgb_prune_batched_workspace_bytes', 'cpgb_prune_select_batched',
     'cpgb_apply_mask', 'cpgb_make_finetuning_mask', 'cpgb_mask_stats', 'cpgb_mask_stats_batched', 'cpgb_merge_grads',
@@ -59,6 +59,8 @@ def load():
         'cpgb_staged_weight_bytes': (sz, [dp]),
         'cpgb_stage_weights': (ctypes.c_int, [dp, vp, vp, f32, vp, sz, vp]),
         'cpgb_staged_weight_bytes_for': (sz, [i32] * 7),
+        'cpgb_weights_usable_raw': (ctypes.c_int, [dp, i32]),
+        'cpgb_weights_usable_raw_for': (ctypes.c_int, [i32] * 8),
         'cpgb_stage_weights_batched': (ctypes.c_int, [i32, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp)]
                                        + [ctypes.POINTER(i32)] * 6 + [ctypes.POINTER(f32), vp]),
         'cpgb_conv2d_fprop': (ctypes.c_int, [dp, vp, vp, vp, vp, vp, f32, vp, vp, sz, vp]),

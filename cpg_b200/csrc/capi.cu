@@ -103,6 +103,17 @@ static int pick_tc(const cpgb_conv_desc *d, int op, bool *use_tc) {
   return CPGB_OK;
 }
 
+int cpgb_weights_usable_raw(const cpgb_conv_desc *d, int32_t has_piggymask) {
+  if (!d || validate_desc(d) || has_piggymask || g_path.load() == CPGB_PATH_SIMT) return 0;
+  return (tc_eligible(*d, 0) || tc_eligible(*d, 1)) && tc_weights_usable_raw(*d) ? 1 : 0;
+}
+
+int cpgb_weights_usable_raw_for(int32_t K, int32_t C, int32_t R, int32_t S, int32_t stride_h, int32_t stride_w,
+                                int32_t groups, int32_t has_piggymask) {
+  if (has_piggymask || g_path.load() == CPGB_PATH_SIMT) return 0;
+  return groups == 1 && R * S == 1 && stride_h == 1 && stride_w == 1 && C % 32 == 0 && C >= 16 && K % 4 == 0;
+}
+
 size_t cpgb_staged_weight_bytes_for(int32_t K, int32_t C, int32_t R, int32_t S, int32_t stride_h, int32_t stride_w,
                                     int32_t groups) {
   if (g_path.load() == CPGB_PATH_SIMT) return 0;
@@ -136,10 +147,16 @@ int cpgb_stage_weights(const cpgb_conv_desc *d, const float *w, const float *pig
 // Operands of a tensor-core call out of (staged, ws): the staged weights are the caller's or are
 // built at the front of ws; the split-K scratch is what remains of ws.
 static int tc_operands(const cpgb_conv_desc *d, const float *w, const float *piggy, float thr, const void *staged,
-                       void *ws, size_t ws_bytes, cudaStream_t st, const float **wt, void **part, size_t *part_bytes) {
+                       void *ws, size_t ws_bytes, cudaStream_t st, const float **wt, void **part, size_t *part_bytes,
+                       bool *raw) {
   char *base = reinterpret_cast<char *>(ws);
   size_t off = 0;
-  if (staged) {
+  *raw = false;
+  if ((!staged || staged == w) && !piggy && tc_weights_usable_raw(*d) &&
+      (reinterpret_cast<uintptr_t>(w) & 15) == 0) {
+    *wt = w;              // linear / 1x1 layer without a piggymask: the weight tensor is the operand
+    *raw = true;
+  } else if (staged && staged != w) {
     *wt = reinterpret_cast<const float *>(staged);
   } else {
     const size_t sb = tc_staged_bytes(*d);
@@ -164,10 +181,10 @@ int cpgb_conv2d_fprop(const cpgb_conv_desc *d, const float *x, const float *w, c
   bool use_tc;
   if ((rc = pick_tc(d, 0, &use_tc))) return rc;
   if (use_tc) {
-    const float *wt; void *part; size_t part_bytes;
-    if ((rc = tc_operands(d, w, piggy, thr, staged, ws, ws_bytes, (cudaStream_t)stream, &wt, &part, &part_bytes)))
+    const float *wt; void *part; size_t part_bytes; bool raw;
+    if ((rc = tc_operands(d, w, piggy, thr, staged, ws, ws_bytes, (cudaStream_t)stream, &wt, &part, &part_bytes, &raw)))
       return rc;
-    return tc_fprop(*d, x, wt, bias, y, part, part_bytes, (cudaStream_t)stream);
+    return tc_fprop(*d, x, wt, bias, y, part, part_bytes, (cudaStream_t)stream, raw);
   }
   return simt_fprop(make_geom(*d), x, w, piggy, bias, y, thr, (cudaStream_t)stream);
 }
@@ -181,10 +198,10 @@ int cpgb_conv2d_dgrad(const cpgb_conv_desc *d, const float *dy, const float *w, 
   bool use_tc;
   if ((rc = pick_tc(d, 1, &use_tc))) return rc;
   if (use_tc) {
-    const float *wt; void *part; size_t part_bytes;
-    if ((rc = tc_operands(d, w, piggy, thr, staged, ws, ws_bytes, (cudaStream_t)stream, &wt, &part, &part_bytes)))
+    const float *wt; void *part; size_t part_bytes; bool raw;
+    if ((rc = tc_operands(d, w, piggy, thr, staged, ws, ws_bytes, (cudaStream_t)stream, &wt, &part, &part_bytes, &raw)))
       return rc;
-    return tc_dgrad(*d, dy, wt, dx, part, part_bytes, (cudaStream_t)stream);
+    return tc_dgrad(*d, dy, wt, dx, part, part_bytes, (cudaStream_t)stream, raw);
   }
   return simt_dgrad(make_geom(*d), dy, w, piggy, dx, thr, (cudaStream_t)stream);
 }

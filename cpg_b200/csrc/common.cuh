@@ -86,10 +86,12 @@ int tc_stage_weights_batched(int n, const float *const *w, const float *const *p
                              const int *K, const int *C, const int *R, const int *S, const int *stride_h,
                              const int *stride_w, const float *thr, cudaStream_t st);
 // part: scratch for split-K partial sums (tc_workspace_bytes covers staged operand + partials)
+// raw: `staged` is the module's fp32 weight tensor itself (tc_weights_usable_raw)
+bool tc_weights_usable_raw(const cpgb_conv_desc &d);
 int tc_fprop(const cpgb_conv_desc &d, const float *x, const float *staged, const float *bias, float *y, void *part,
-             size_t part_bytes, cudaStream_t st);
+             size_t part_bytes, cudaStream_t st, bool raw);
 int tc_dgrad(const cpgb_conv_desc &d, const float *dy, const float *staged, float *dx, void *part, size_t part_bytes,
-             cudaStream_t st);
+             cudaStream_t st, bool raw);
 // wgrad + fused epilogue (dW, dP); partial sums live in ws
 int tc_wgrad_fused(const cpgb_conv_desc &d, const float *x, const float *dy, const float *w, const float *piggy,
                    const uint8_t *tmask, int cur, float wd, int mode, float thr, float *dW, float *dP, void *ws,

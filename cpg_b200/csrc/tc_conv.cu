@@ -226,6 +226,7 @@ struct ConvGemmParams {
   int kblocks;             // 32-wide reduction blocks per tap
   int ncols;               // valid output channels
   int iters_per_split;     // split-K over the (tap, k-block) loop; blockIdx.z = split
+  float debias;            // DEBIAS_ONE (staged, pre-rounded weights) or DEBIAS_TWO (raw fp32 weights)
   int nstage;              // depth of the smem ring (3: two CTAs share an SM; more: one CTA, deeper prefetch)
   int mn_layout, mn_lbo, mn_sbo, mn_kadv;   // MN-major operand descriptor fields
   long long o_sn, o_sh, o_sw;
@@ -356,7 +357,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         float *rp = rows[rr];
         const int col = col0 + h + c4;
         if (rp != nullptr && col < p.ncols) {   // ncols % 4 == 0
-          v.x *= DEBIAS_ONE; v.y *= DEBIAS_ONE; v.z *= DEBIAS_ONE; v.w *= DEBIAS_ONE;
+          v.x *= p.debias; v.y *= p.debias; v.z *= p.debias; v.w *= p.debias;
           if (bias) {
             const float4 b = __ldg(reinterpret_cast<const float4 *>(bias + col));
             v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
@@ -963,7 +964,7 @@ static int run_gemm(const GemmPlan &g, const CUtensorMap &ta, const CUtensorMap 
 }
 
 static int implicit_fprop(const cpgb_conv_desc &d, const float *x, const float *staged, const float *bias, float *y,
-                          void *part, size_t part_bytes, cudaStream_t st) {
+                          void *part, size_t part_bytes, cudaStream_t st, bool raw = false) {
   if (!aligned16p(x) || !aligned16p(y) || !aligned16p(staged) || (bias && !aligned16p(bias)) || !aligned16p(part)) {
     set_error("tcgen05 path needs 16-byte aligned tensors"); return CPGB_EINVAL;
   }
@@ -981,13 +982,13 @@ static int implicit_fprop(const cpgb_conv_desc &d, const float *x, const float *
   ConvGemmParams p;
   p.Qo = d.Q; p.Po = d.P; p.No = d.N; p.S = d.S; p.taps = RS;
   p.off_h = -d.pad_h; p.off_w = -d.pad_w; p.step_h = d.dil_h; p.step_w = d.dil_w;
-  p.kblocks = Cp / 32; p.ncols = d.K;
+  p.kblocks = Cp / 32; p.ncols = d.K; p.debias = raw ? DEBIAS_TWO : DEBIAS_ONE;
   { Str4 ys = y_strides(d); p.o_sn = ys.s[0]; p.o_sh = ys.s[2]; p.o_sw = ys.s[3]; }
   return run_gemm<false>(g, ta, tb, p, y, bias, part, part_bytes, st);
 }
 
 static int implicit_dgrad(const cpgb_conv_desc &d, const float *dy, const float *staged, float *dx, void *part,
-                          size_t part_bytes, cudaStream_t st) {
+                          size_t part_bytes, cudaStream_t st, bool raw = false) {
   if (!aligned16p(dy) || !aligned16p(dx) || !aligned16p(staged) || !aligned16p(part)) {
     set_error("tcgen05 path needs 16-byte aligned tensors"); return CPGB_EINVAL;
   }
@@ -1007,7 +1008,7 @@ static int implicit_dgrad(const cpgb_conv_desc &d, const float *dy, const float 
   ConvGemmParams p;
   p.Qo = d.W; p.Po = d.H; p.No = d.N; p.S = d.S; p.taps = RS;
   p.off_h = d.pad_h; p.off_w = d.pad_w; p.step_h = -d.dil_h; p.step_w = -d.dil_w;
-  p.kblocks = cdiv_i(d.K, 32); p.ncols = d.C;
+  p.kblocks = cdiv_i(d.K, 32); p.ncols = d.C; p.debias = raw ? DEBIAS_TWO : DEBIAS_ONE;
   { Str4 xs = x_strides(d); p.o_sn = xs.s[0]; p.o_sh = xs.s[2]; p.o_sw = xs.s[3]; }
   return run_gemm<true>(g, ta, tb, p, dx, nullptr, part, part_bytes, st);
 }
@@ -1537,16 +1538,23 @@ int tc_stage_weights(const cpgb_conv_desc &d, const float *w, const float *piggy
                         : implicit_stage_weights(d, w, piggy, thr, staged, bytes, st);
 }
 
+// The raw fp32 weight tensor is itself a valid operand of the in-place path when the layer is linear /
+// 1x1 with whole 32-channel blocks and no piggymask: same [K][C] layout, the tensor core truncates it to
+// TF32 (hence DEBIAS_TWO).  Saves the staging pass for the FC layers of task 1 (56 % of VGG16's weights).
+bool tc_weights_usable_raw(const cpgb_conv_desc &d) {
+  return !prefer_xcol(d) && d.groups == 1 && d.R * d.S == 1 && d.C % 32 == 0 && d.K % 4 == 0;
+}
+
 int tc_fprop(const cpgb_conv_desc &d, const float *x, const float *staged, const float *bias, float *y, void *part,
-             size_t part_bytes, cudaStream_t st) {
+             size_t part_bytes, cudaStream_t st, bool raw) {
   return tc_mode(d, 0) == TC_XCOL ? xcol_fprop(d, x, staged, bias, y, part, part_bytes, st)
-                                  : implicit_fprop(d, x, staged, bias, y, part, part_bytes, st);
+                                  : implicit_fprop(d, x, staged, bias, y, part, part_bytes, st, raw);
 }
 
 int tc_dgrad(const cpgb_conv_desc &d, const float *dy, const float *staged, float *dx, void *part, size_t part_bytes,
-             cudaStream_t st) {
+             cudaStream_t st, bool raw) {
   return tc_mode(d, 1) == TC_XCOL ? xcol_dgrad(d, dy, staged, dx, part, part_bytes, st)
-                                  : implicit_dgrad(d, dy, staged, dx, part, part_bytes, st);
+                                  : implicit_dgrad(d, dy, staged, dx, part, part_bytes, st, raw);
 }
 
 int tc_wgrad_fused(const cpgb_conv_desc &d, const float *x, const float *dy, const float *w, const float *piggy,

@@ -36,6 +36,9 @@ def _stage(lib, d, w, p, threshold, prestaged=None):
     nbytes = lib.cpgb_staged_weight_bytes(d)
     if nbytes == 0:
         return None, None
+    if lib.cpgb_weights_usable_raw(d, 1 if p is not None else 0):
+        # linear / 1x1 layer without a piggymask: the weight tensor itself is the operand
+        return w, _ws(lib.cpgb_workspace_bytes(d) - nbytes, w.device)
     if prestaged is not None and prestaged.numel() >= nbytes and prestaged.device == w.device:
         staged = prestaged
     else:

@@ -99,6 +99,8 @@ class SparsePruner(object):
                 (K, C), R, S, sh, sw, groups = w.shape, 1, 1, 1, 1, 1
             nbytes = lib.cpgb_staged_weight_bytes_for(K, C, R, S, sh, sw, groups)
             p = m.piggymask
+            if lib.cpgb_weights_usable_raw_for(K, C, R, S, sh, sw, groups, 1 if p is not None else 0):
+                continue        # consumed as is, nothing to stage
             if nbytes == 0 or (p is not None and (not p.is_contiguous() or p.device != w.device)):
                 continue
             key = (name, str(w.device))

@@ -87,6 +87,13 @@ size_t cpgb_staged_weight_bytes(const cpgb_conv_desc *d);
 int cpgb_stage_weights(const cpgb_conv_desc *d, const float *w, const float *piggy, float thr, void *staged,
                        size_t staged_bytes, void *stream);
 
+/* Linear / 1x1 layers without a piggymask (task 1) need no staging: the fp32 weight tensor has the
+ * operand's layout and the tensor core truncates it to TF32.  When this returns 1 the caller may pass
+ * `staged = w` (or NULL) to cpgb_conv2d_fprop / _dgrad and skip cpgb_stage_weights. */
+int cpgb_weights_usable_raw(const cpgb_conv_desc *d, int32_t has_piggymask);
+int cpgb_weights_usable_raw_for(int32_t K, int32_t C, int32_t R, int32_t S, int32_t stride_h, int32_t stride_w,
+                                int32_t groups, int32_t has_piggymask);
+
 /* The same staging for every sharable layer of a model in ONE launch (weights do not depend on the
  * activations, so a model-level pre-forward hook can build all operands at once).  All arrays are HOST
  * arrays of n entries; piggy[i] may be NULL; staged[i] must hold

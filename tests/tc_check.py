@@ -63,14 +63,17 @@ def run(op, cases):
     torch.backends.cuda.matmul.allow_tf32 = False
     lib = _lib.load()
     worst = 0.0
+    # linear / 1x1 cases are run twice: with a piggymask (staged operand) and without (raw weights as operand)
+    cases = [c + ((1,) if len(c) == 8 else ()) + (True,) for c in cases] + \
+            [c + ((1,) if len(c) == 8 else ()) + (False,) for c in cases if c[5] == 1]
     for case in cases:
-        (N, C, H, W, K, R, pad, dil), stride = case[:8], (case[8] if len(case) > 8 else 1)
+        (N, C, H, W, K, R, pad, dil), stride, with_piggy = case[:8], case[8], case[9]
         torch.manual_seed(N * 7 + C + K)
         m = nl.SharableConv2d(C, K, R, stride=stride, padding=pad, dilation=dil, bias=True).to(DEV)
         with torch.no_grad():
             m.weight.normal_(0, (2.0 / (C * R * R)) ** 0.5)
             m.bias.normal_()
-        m.piggymask = nn.Parameter(torch.rand_like(m.weight) * 0.01)
+        m.piggymask = nn.Parameter(torch.rand_like(m.weight) * 0.01) if with_piggy else None
         x = torch.randn(N, C, H, W, device=DEV).contiguous(memory_format=torch.channels_last)
         if C % 4:
             xp = torch.empty((N, (C + 3) // 4 * 4, H, W), device=DEV).contiguous(memory_format=torch.channels_last)
@@ -78,14 +81,14 @@ def run(op, cases):
             xv = xp[:, :C]
             xv.copy_(x)
             x = xv
-        weff = ((m.piggymask > 5e-3).float() * m.weight).detach()
+        weff = ((m.piggymask > 5e-3).float() * m.weight).detach() if with_piggy else m.weight.detach()
         yr = F.conv2d(x, weff, m.bias, stride, pad, dil)
         dy = torch.randn_like(yr).contiguous(memory_format=torch.channels_last)
         d = _lib.conv_desc(x.shape, x.stride(), m.weight.shape, dy.shape, dy.stride(), (stride, stride), (pad, pad),
                            (dil, dil), 1)
         ws = torch.empty(max(lib.cpgb_workspace_bytes(d), 256), dtype=torch.uint8, device=DEV)
         P, st = _lib.ptr, _lib.stream_ptr()
-        tag = f'N{N} C{C} {H}x{W} K{K} R{R} p{pad} d{dil} s{stride}'
+        tag = f'N{N} C{C} {H}x{W} K{K} R{R} p{pad} d{dil} s{stride}' + ('' if with_piggy else ' nopiggy')
         _lib.set_path(_lib.PATH_TCGEN05)
         try:
             t0 = time.time()
@@ -105,23 +108,23 @@ def run(op, cases):
             else:
                 gr = torch.nn.grad.conv2d_weight(x, m.weight.shape, dy, stride, pad, dil)
                 dW = torch.full_like(m.weight, float('nan'))
-                dP = torch.full_like(m.weight, float('nan'))
+                dP = torch.full_like(m.weight, float('nan')) if with_piggy else None
                 tm = torch.randint(0, 4, m.weight.shape, device=DEV, dtype=torch.uint8)
                 cur, wd = 3, 0.05
                 _lib.check(lib.cpgb_conv2d_wgrad_fused(d, P(x), P(dy), P(m.weight), P(m.piggymask), P(tm), cur, wd,
                                                        _lib.GRAD_FINETUNE, P(dW), P(dP), None, 5e-3, P(ws), ws.numel(),
                                                        st), 'wgrad')
                 torch.cuda.synchronize()
-                b = (m.piggymask > 5e-3).float()
+                b = (m.piggymask > 5e-3).float() if with_piggy else 1.0
                 rW = (gr * b + wd * m.weight) * (tm == cur)
                 rP = gr * m.weight * ((tm >= 1) & (tm < cur))
-                e = max(rel(dW, rW), rel(dP, rP))
-                bf = proj(dP, rP)
-            print(f'{op:6s} {tag:38s} rel {e:.3e}  proj {bf:+.3e}  {"OK" if e <= 1e-3 else "FAIL"} '
+                e = max(rel(dW, rW), rel(dP, rP)) if with_piggy else rel(dW, rW)
+                bf = proj(dP, rP) if with_piggy else proj(dW, rW)
+            print(f'{op:6s} {tag:46s} rel {e:.3e}  proj {bf:+.3e}  {"OK" if e <= 1e-3 else "FAIL"} '
                   f'({(time.time() - t0) * 1e3:.1f} ms)', flush=True)
             worst = max(worst, e)
         except Exception as ex:  # noqa: BLE001
-            print(f'{op:6s} {tag:38s} EXCEPTION {type(ex).__name__}: {ex}', flush=True)
+            print(f'{op:6s} {tag:46s} EXCEPTION {type(ex).__name__}: {ex}', flush=True)
             if 'CUDA' in str(ex) or 'cuda' in str(ex):
                 print('context is gone; stopping', flush=True)
                 return
