@@ -787,12 +787,18 @@ static size_t implicit_staged_bytes(const cpgb_conv_desc &d) {
   return align_up((size_t)d.K * d.R * d.S * cp_of(d) * sizeof(float) + 256, 256);
 }
 
+// SM count the grids are planned for.  CPGB_SM_MARGIN=m plans for (SMs - m): under data parallelism the NCCL
+// all-reduce kernels overlap the backward pass and hold a few SMs, which would turn the "exactly one wave"
+// grids of the split-K / split-pixel plans into two waves.
 static int num_sms() {
   static int n = 0;
   if (n == 0) {
     int dev = 0, v = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-    n = v > 0 ? v : 148;
+    if (v <= 0) v = 148;
+    const char *m = getenv("CPGB_SM_MARGIN");
+    if (m) { int mv = atoi(m); if (mv > 0 && mv < v / 2) v -= mv; }
+    n = v;
   }
   return n;
 }

@@ -62,15 +62,18 @@ class GradAllReducer:
         self.pending = []
         rest = [p.grad for p in self.params if p.grad is not None and p.grad.data_ptr() not in done]
         if rest:
+            # one flat bucket for the ~75 small tensors (BN, biases, heads, the first conv layers); packed
+            # and unpacked with multi-tensor kernels instead of one launch per tensor
             flat = torch.cat([g.reshape(-1) for g in rest])
             dist.all_reduce(flat, op=self.op, group=self.group)
             if not self.avg:
                 flat.div_(self.world)
-            off = 0
+            views, off = [], 0
             for g in rest:
                 n = g.numel()
-                g.copy_(flat[off:off + n].view_as(g))
+                views.append(flat[off:off + n].view_as(g))
                 off += n
+            torch._foreach_copy_(rest, views)
 
     def remove(self):
         for h in self._hooks:
