@@ -384,7 +384,18 @@ splitk_reduce_kernel(const float4 *__restrict__ part, int splits, long long n4, 
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 a = __ldg(part + i);
-    for (int s = 1; s < splits; ++s) {
+    int s = 1;
+    for (; s + 4 <= splits; s += 4) {             // four loads in flight; the sum order stays 0,1,2,...
+      const float4 b0 = __ldg(part + (s + 0) * split_stride4 + i);
+      const float4 b1 = __ldg(part + (s + 1) * split_stride4 + i);
+      const float4 b2 = __ldg(part + (s + 2) * split_stride4 + i);
+      const float4 b3 = __ldg(part + (s + 3) * split_stride4 + i);
+      a.x += b0.x; a.y += b0.y; a.z += b0.z; a.w += b0.w;
+      a.x += b1.x; a.y += b1.y; a.z += b1.z; a.w += b1.w;
+      a.x += b2.x; a.y += b2.y; a.z += b2.z; a.w += b2.w;
+      a.x += b3.x; a.y += b3.y; a.z += b3.z; a.w += b3.w;
+    }
+    for (; s < splits; ++s) {
       const float4 b = __ldg(part + s * split_stride4 + i);
       a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
     }
@@ -645,7 +656,18 @@ wgrad_epilogue_krsc_kernel(const float *__restrict__ gpart, int splits, int K, i
     const int row = i / row4, c = (i - row * row4) * 4;     // row = kk * RS + t
     const float *src = gpart + ((long long)k0 * RS + row) * Cg + c0 + c;
     float4 a = __ldg(reinterpret_cast<const float4 *>(src));
-    for (int sp = 1; sp < splits; ++sp) {
+    int sp = 1;
+    for (; sp + 4 <= splits; sp += 4) {          // four loads in flight; the sum order stays 0,1,2,...
+      const float4 b0 = __ldg(reinterpret_cast<const float4 *>(src + (sp + 0) * split_stride));
+      const float4 b1 = __ldg(reinterpret_cast<const float4 *>(src + (sp + 1) * split_stride));
+      const float4 b2 = __ldg(reinterpret_cast<const float4 *>(src + (sp + 2) * split_stride));
+      const float4 b3 = __ldg(reinterpret_cast<const float4 *>(src + (sp + 3) * split_stride));
+      a.x += b0.x; a.y += b0.y; a.z += b0.z; a.w += b0.w;
+      a.x += b1.x; a.y += b1.y; a.z += b1.z; a.w += b1.w;
+      a.x += b2.x; a.y += b2.y; a.z += b2.z; a.w += b2.w;
+      a.x += b3.x; a.y += b3.y; a.z += b3.z; a.w += b3.w;
+    }
+    for (; sp < splits; ++sp) {
       const float4 b = __ldg(reinterpret_cast<const float4 *>(src + sp * split_stride));
       a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
     }
