@@ -83,3 +83,39 @@ def test_product_never_imports_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 src = open(os.path.join(dirpath, f)).read()
                 assert 'import oracle' not in src and 'from oracle' not in src, f
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/models'), reason='reference checkout not present (GPU box)')
+def test_install_makes_reference_models_build_on_our_layers():
+    """after cpg_b200.install() the UNMODIFIED reference model files build their
+    networks out of this package's layers (isinstance checks of utils/prune.py / utils/manager.py keep
+    firing) and the reference's SparsePruner name resolves to ours.  Runs in a subprocess so the
+    sys.modules aliasing does not leak into the other tests; no kernel is launched (CPU box)."""
+    import subprocess
+    import sys
+    code = r'''
+import sys
+sys.path.insert(0, %r); sys.path.insert(0, '/root/reference')
+import cpg_b200
+layers, prune = cpg_b200.install()
+import models, models.vgg, models.resnet, models.spherenet
+import models.layers as nl
+assert nl is layers and nl.SharableConv2d is layers.SharableConv2d
+net = models.vgg.custom_vgg_cifar100(custom_cfg=[64, 64, 'M', 128, 128, 'M', 256, 256, 256, 'M', 512, 512, 512, 'M', 512, 512, 512, 'M'],
+                                     dataset_history=[], dataset2num_classes={}, network_width_multiplier=1.0,
+                                     shared_layer_info={})
+convs = [m for m in net.modules() if isinstance(m, nl.SharableConv2d)]
+lins = [m for m in net.modules() if isinstance(m, nl.SharableLinear)]
+assert len(convs) == 13 and len(lins) == 2, (len(convs), len(lins))
+assert sorted(k for k in convs[0].state_dict()) == ['weight'] and convs[0].piggymask is None
+r50 = models.resnet.resnet50(dataset_history=[], dataset2num_classes={}, network_width_multiplier=1.0, shared_layer_info={})
+assert sum(isinstance(m, nl.SharableConv2d) for m in r50.modules()) == 53
+s20 = models.spherenet.spherenet20(dataset_history=[], dataset2num_classes={}, network_width_multiplier=1.0,
+                                   shared_layer_info={})
+assert sum(isinstance(m, nl.SharableConv2d) for m in s20.modules()) == 20
+import utils.prune, utils.manager
+assert utils.prune.SparsePruner is prune.SparsePruner and utils.manager.SparsePruner is prune.SparsePruner
+print('ok')
+''' % ROOT
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and 'ok' in out.stdout, out.stderr[-2000:]
