@@ -81,15 +81,24 @@ size_t cpgb_workspace_bytes(const cpgb_conv_desc *d) {
   // raw weight-gradient partial sums of the CUDA-core wgrad: one tensor per split of the pixel reduction
   size_t g_bytes = weight_elems(d) * sizeof(float) * (size_t)simt_wgrad_splits(make_geom(*d));
   size_t tc = tc_workspace_bytes(*d);                          // staged operand / split-K partial sums
+  size_t stem = stem_workspace_bytes(*d);                      // per-block partial sums of the stem wgrad
   g_bytes = (g_bytes + 255) & ~(size_t)255;
+  if (stem > g_bytes) g_bytes = stem;
   return g_bytes > tc ? g_bytes : tc;
 }
 
 size_t cpgb_staged_weight_bytes(const cpgb_conv_desc *d) {
   if (!d || validate_desc(d)) return 0;
   if (g_path.load() == CPGB_PATH_SIMT) return 0;
+  if (g_path.load() == CPGB_PATH_AUTO && stem_eligible(*d)) return 0;   // stem kernels mask while loading W
   if (!tc_eligible(*d, 0) && !tc_eligible(*d, 1)) return 0;
   return tc_staged_bytes(*d);
+}
+
+// The 3-channel 3x3 stem has its own direct fp32 kernels (stem_conv.cu) on the default path; the two
+// forced paths (CPGB_PATH_SIMT / CPGB_PATH_TCGEN05) keep their meaning for tests and cross-checks.
+static bool pick_stem(const cpgb_conv_desc *d, const void *y_or_dy) {
+  return g_path.load() == CPGB_PATH_AUTO && stem_eligible(*d) && (reinterpret_cast<uintptr_t>(y_or_dy) & 15) == 0;
 }
 
 static int pick_tc(const cpgb_conv_desc *d, int op, bool *use_tc) {
@@ -117,6 +126,7 @@ int cpgb_weights_usable_raw_for(int32_t K, int32_t C, int32_t R, int32_t S, int3
 size_t cpgb_staged_weight_bytes_for(int32_t K, int32_t C, int32_t R, int32_t S, int32_t stride_h, int32_t stride_w,
                                     int32_t groups) {
   if (g_path.load() == CPGB_PATH_SIMT) return 0;
+  if (g_path.load() == CPGB_PATH_AUTO && stem_weight_shape(K, C, R, S, groups)) return 0;
   return tc_staged_bytes_for_weight(K, C, R, S, stride_h, stride_w, groups);
 }
 
@@ -178,6 +188,8 @@ int cpgb_conv2d_fprop(const cpgb_conv_desc *d, const float *x, const float *w, c
   if (rc) return rc;
   if (d->N == 0) return CPGB_OK;  // empty batch: nothing to compute, y is empty
   if (!x || !w || !y) { set_error("cpgb_conv2d_fprop: null pointer"); return CPGB_EINVAL; }
+  if (pick_stem(d, y) && (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0))
+    return stem_fprop(*d, x, w, piggy, bias, y, thr, (cudaStream_t)stream);
   bool use_tc;
   if ((rc = pick_tc(d, 0, &use_tc))) return rc;
   if (use_tc) {
@@ -225,8 +237,12 @@ int cpgb_conv2d_wgrad_fused(const cpgb_conv_desc *d, const float *x, const float
   Geom g = make_geom(*d);
   float *gbuf = reinterpret_cast<float *>(ws);
   bool use_tc = false;
-  if (d->N != 0 && (rc = pick_tc(d, 2, &use_tc))) return rc;
-  if (use_tc) {
+  const bool use_stem = d->N != 0 && pick_stem(d, dy);
+  if (d->N != 0 && !use_stem && (rc = pick_tc(d, 2, &use_tc))) return rc;
+  if (use_stem) {
+    if ((rc = stem_wgrad_fused(*d, x, dy, w, piggy, tmask, cur, weight_decay, mode, thr, dW, dP, ws, ws_bytes, st)))
+      return rc;
+  } else if (use_tc) {
     // tensor-core wgrad: split-K partial sums in ws, summed inside the fused epilogue
     if ((rc = tc_wgrad_fused(*d, x, dy, w, piggy, tmask, cur, weight_decay, mode, thr, dW, dP, ws, ws_bytes, st)))
       return rc;

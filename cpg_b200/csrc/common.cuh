@@ -73,6 +73,16 @@ int bias_grad(const Geom &g, const float *dy, float *dbias, cudaStream_t st);
 int wgrad_epilogue(const float *gbuf, int splits, const float *w, const float *piggy, const uint8_t *tmask,
                    long long n, int cur, float wd, int mode, float thr, float *dW, float *dP, cudaStream_t st);
 
+// direct fp32 kernels for the 3-channel 3x3 stem (stem_conv.cu); y / dy must be NHWC
+bool stem_eligible(const cpgb_conv_desc &d);
+bool stem_weight_shape(int K, int C, int R, int S, int groups);
+size_t stem_workspace_bytes(const cpgb_conv_desc &d);
+int stem_fprop(const cpgb_conv_desc &d, const float *x, const float *w, const float *piggy, const float *bias, float *y,
+               float thr, cudaStream_t st);
+int stem_wgrad_fused(const cpgb_conv_desc &d, const float *x, const float *dy, const float *w, const float *piggy,
+                     const uint8_t *tmask, int cur, float wd, int mode, float thr, float *dW, float *dP, void *ws,
+                     size_t ws_bytes, cudaStream_t st);
+
 // tcgen05 implicit GEMM (tc_conv.cu).  tc_eligible() says whether the shape is supported.
 bool tc_eligible(const cpgb_conv_desc &d, int op);  // op: 0 fprop, 1 dgrad, 2 wgrad
 size_t tc_workspace_bytes(const cpgb_conv_desc &d);

@@ -534,3 +534,86 @@ def test_graph_capture_of_fwd_bwd():
     graph.replay()
     torch.cuda.synchronize()
     assert rel(m.weight.grad, ref) <= 1e-6
+
+
+# ---------------------------------------------------------------------------------------------
+# 3-channel 3x3 stem: direct fp32 kernels (csrc/stem_conv.cu) -- exact fp32, so the fp32 bar applies
+# ---------------------------------------------------------------------------------------------
+STEM_CASES = [
+    # N, H, W, K, stride, pad, dil, bias, piggy     (models/vgg.py:97, models/spherenet.py:201 shapes + edge cases)
+    (24, 32, 32, 64, 1, 1, 1, False, False),        # VGG16 stem (pixel pairs, more TMA chunks than SMs)
+    (3, 31, 29, 64, 1, 1, 1, True, True),           # ragged: last TMA chunk is partial
+    (2, 112, 112, 64, 2, 1, 1, True, True),         # SphereNet conv1_1 (stride 2, bias)
+    (2, 20, 20, 128, 1, 1, 1, False, True),         # K = 128: one warp per pixel
+    (5, 9, 9, 16, 1, 0, 1, True, False),            # no padding, narrow K
+    (4, 17, 17, 32, 1, 2, 2, False, True),          # dilation 2
+    (1, 3, 3, 8, 1, 1, 1, False, False),            # fewer pixels than one block covers
+]
+
+
+@pytest.mark.parametrize('case', STEM_CASES)
+@pytest.mark.parametrize('mode', ['raw', 'finetune'])
+def test_stem_direct_kernels_vs_oracle(case, mode):
+    N, H, W, K, stride, pad, dil, has_b, has_p = case
+    rng = np.random.RandomState(zlib.crc32(repr(case).encode()) & 0xffff)
+    x = rng.standard_normal((N, 3, H, W)).astype(np.float32)
+    w = (rng.standard_normal((K, 3, 3, 3)) * 0.2).astype(np.float32)
+    b = rng.standard_normal(K).astype(np.float32) if has_b else None
+    p = rng.uniform(0, 0.01, size=w.shape).astype(np.float32) if has_p else None
+    P = (H + 2 * pad - dil * 2 - 1) // stride + 1
+    Q = (W + 2 * pad - dil * 2 - 1) // stride + 1
+    dy = rng.standard_normal((N, K, P, Q)).astype(np.float32)
+    tt = lambda a: None if a is None else torch.from_numpy(a)
+    ry = O.conv2d_forward(tt(x), tt(w), tt(p), tt(b), stride, pad, dil, 1)
+    _, rdW, rdP, rdb, g_raw = O.conv2d_backward(tt(x), tt(w), tt(p), tt(b), tt(dy), stride, pad, dil, 1)
+    cur, wd = 2, 4e-5
+    t = rng.randint(0, 4, size=w.shape).astype(np.uint8)
+    if mode == 'finetune':
+        rdW, rdP = O.fused_weight_grads(g_raw, tt(w), tt(p), tt(t), cur, wd, 'finetune')
+
+    lib = _lib.load()
+    xd = G(x).contiguous(memory_format=torch.channels_last)
+    wdv, pd_, bd = G(w), (G(p) if has_p else None), (G(b) if has_b else None)
+    yd = torch.empty((N, K, P, Q), device=DEV).contiguous(memory_format=torch.channels_last)
+    dyd = G(dy).contiguous(memory_format=torch.channels_last)
+    d = _lib.conv_desc(xd.shape, xd.stride(), wdv.shape, yd.shape, yd.stride(), (stride,) * 2, (pad,) * 2, (dil,) * 2, 1)
+    assert lib.cpgb_staged_weight_bytes(d) == 0          # the stem path needs no staged operand
+    ws = torch.empty(max(lib.cpgb_workspace_bytes(d), 256), dtype=torch.uint8, device=DEV)
+    st = _lib.stream_ptr()
+    before = lib.cpgb_launch_count()
+    _lib.check(lib.cpgb_conv2d_fprop(d, _lib.ptr(xd), _lib.ptr(wdv), _lib.ptr(pd_), _lib.ptr(bd), _lib.ptr(yd), 5e-3,
+                                     None, _lib.ptr(ws), ws.numel(), st), 'fprop')
+    assert lib.cpgb_launch_count() - before == 1         # one direct kernel, no im2col / staging / split-K
+    dW = torch.full_like(wdv, float('nan'))
+    dP = torch.full_like(wdv, float('nan')) if has_p else None
+    db = torch.empty(K, device=DEV) if has_b else None
+    td = G(t)
+    for dy_view in (dyd, None):
+        if dy_view is None:
+            # dY that is NHWC but not pixel-dense (a channel slice of a wider tensor): plain-load variant
+            wide = torch.zeros((N, K + 8, P, Q), device=DEV).contiguous(memory_format=torch.channels_last)
+            wide[:, :K].copy_(dyd)
+            dy_view = wide[:, :K]
+        d2 = _lib.conv_desc(xd.shape, xd.stride(), wdv.shape, dy_view.shape, dy_view.stride(), (stride,) * 2,
+                            (pad,) * 2, (dil,) * 2, 1)
+        dW.fill_(float('nan'))
+        _lib.check(lib.cpgb_conv2d_wgrad_fused(
+            d2, _lib.ptr(xd), _lib.ptr(dy_view), _lib.ptr(wdv), _lib.ptr(pd_), _lib.ptr(td), cur, wd,
+            _lib.GRAD_FINETUNE if mode == 'finetune' else _lib.GRAD_RAW, _lib.ptr(dW), _lib.ptr(dP), _lib.ptr(db),
+            5e-3, _lib.ptr(ws), ws.numel(), st), 'wgrad')
+        torch.cuda.synchronize()
+        assert rel(dW, rdW) <= TOL_FP32
+        if has_p:
+            assert rel(dP, rdP) <= TOL_FP32
+        if has_b:
+            assert rel(db, rdb) <= TOL_FP32
+        if mode == 'finetune':
+            assert (dW.cpu()[torch.from_numpy(t) != cur] == 0).all()
+    assert rel(yd, ry) <= TOL_FP32
+    # deterministic: a second launch reproduces the bits
+    dW2 = torch.empty_like(dW)
+    _lib.check(lib.cpgb_conv2d_wgrad_fused(
+        d2, _lib.ptr(xd), _lib.ptr(dy_view), _lib.ptr(wdv), _lib.ptr(pd_), _lib.ptr(td), cur, wd,
+        _lib.GRAD_FINETUNE if mode == 'finetune' else _lib.GRAD_RAW, _lib.ptr(dW2), _lib.ptr(dP), _lib.ptr(db),
+        5e-3, _lib.ptr(ws), ws.numel(), st), 'wgrad')
+    assert torch.equal(dW, dW2)
