@@ -312,6 +312,8 @@ def dist_setup(gpus):
     local = int(os.environ.get('LOCAL_RANK', '0'))
     if world > 1:
         import torch.distributed as dist
+        from cpg_b200.ddp import tune_env
+        tune_env(world)
         torch.cuda.set_device(local)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     return world, rank, local

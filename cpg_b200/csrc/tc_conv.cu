@@ -835,6 +835,10 @@ static GemmPlan plan_gemm(int Qo, int Po, int No, int ncols, int iters, const St
   if (ncols <= 64) g.BN = 64;
   else if (ncols <= 128) g.BN = 128;
   else g.BN = (mtiles * cdiv_i(ncols, 256) >= sms) ? 256 : 128;
+  // experiment knobs (read per call): CPGB_GEMM_BN forces the tile width where the layer is at least that
+  // wide, CPGB_GEMM_SPLITS the split-K factor
+  const char *ebn = getenv("CPGB_GEMM_BN"), *esp = getenv("CPGB_GEMM_SPLITS");
+  if (ebn) { const int v = atoi(ebn); if ((v == 64 || v == 128 || v == 256) && ncols >= v) g.BN = v; }
   g.ntiles = cdiv_i(ncols, g.BN);
   g.iters = iters;
   // partial sums are addressed like the output, so splitting needs a dense NHWC output
@@ -847,6 +851,11 @@ static GemmPlan plan_gemm(int Qo, int Po, int No, int ncols, int iters, const St
     if (splits > iters / 4) splits = iters / 4;
     if (splits < 1) splits = 1;
   }
+  // One CTA per SM and a long reduction loop (conv 256->256 @ 8x8: 128 CTAs x 72 stages): halving the loop puts
+  // two CTAs on every SM, so one CTA's prologue / epilogue hides under the other's main loop (measured
+  // 36.9 -> 31.7 us; shorter loops lose more to the extra reduction pass than they gain)
+  if (g.dense && splits == 1 && g.BN <= 128 && ctas * 2 > sms && ctas <= sms && iters >= 64) splits = 2;
+  if (esp && g.dense) { const int v = atoi(esp); if (v >= 1 && v <= iters) splits = v; }
   g.ips = cdiv_i(iters, splits);
   g.splits = cdiv_i(iters, g.ips);
   return g;

@@ -617,3 +617,73 @@ def test_stem_direct_kernels_vs_oracle(case, mode):
         _lib.GRAD_FINETUNE if mode == 'finetune' else _lib.GRAD_RAW, _lib.ptr(dW2), _lib.ptr(dP), _lib.ptr(db),
         5e-3, _lib.ptr(ws), ws.numel(), st), 'wgrad')
     assert torch.equal(dW, dW2)
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json configs[3] / configs[4]: the distinct sharable-layer shapes of ResNet-50 @224 (batch 256
+# over 8 GPUs = 32 per GPU) and SphereNet-20 @112 (batch 512 over 8 = 64 per GPU), SURVEY appendix A2 / A3,
+# at full size through the module API: cuDNN fp32 on the same GPU + adjointness
+# ---------------------------------------------------------------------------------------------
+FULL_LAYERS = [
+    # name, N, C, H, W, K, R, stride, pad, bias
+    ('r50_stem7x7s2', 32, 3, 224, 224, 64, 7, 2, 3, False),
+    ('r50_1x1_64_256@56', 32, 64, 56, 56, 256, 1, 1, 0, False),
+    ('r50_1x1_256_64@56', 32, 256, 56, 56, 64, 1, 1, 0, False),
+    ('r50_3x3_64@56', 32, 64, 56, 56, 64, 3, 1, 1, False),
+    ('r50_3x3s2_128@56', 32, 128, 56, 56, 128, 3, 2, 1, False),
+    ('r50_1x1s2_256_512@56', 32, 256, 56, 56, 512, 1, 2, 0, False),
+    ('r50_3x3_128@28', 32, 128, 28, 28, 128, 3, 1, 1, False),
+    ('r50_1x1_1024_256@14', 32, 1024, 14, 14, 256, 1, 1, 0, False),
+    ('r50_3x3_256@14', 32, 256, 14, 14, 256, 3, 1, 1, False),
+    ('r50_1x1_512_2048@7', 32, 512, 7, 7, 2048, 1, 1, 0, False),
+    ('r50_3x3_512@7', 32, 512, 7, 7, 512, 3, 1, 1, False),
+    ('sph_conv1_1', 64, 3, 112, 112, 64, 3, 2, 1, True),
+    ('sph_conv1_2', 64, 64, 56, 56, 64, 3, 1, 1, True),
+    ('sph_conv2_1', 64, 64, 56, 56, 128, 3, 2, 1, True),
+    ('sph_conv3_2', 64, 256, 14, 14, 256, 3, 1, 1, True),
+    ('sph_conv4_1', 64, 256, 14, 14, 512, 3, 2, 1, True),
+    ('sph_conv4_2', 64, 512, 7, 7, 512, 3, 1, 1, True),
+    ('sph_face_112x96', 16, 64, 56, 48, 64, 3, 1, 1, True),     # the 112x96 face crop of BASELINE.json configs[4]
+]
+
+
+@pytest.mark.parametrize('layer', FULL_LAYERS, ids=[l[0] for l in FULL_LAYERS])
+def test_full_size_resnet_spherenet_layers(layer):
+    _, N, C, H, W, K, R, stride, pad, has_b = layer
+    torch.manual_seed(N + C + H + K + R)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        m = nl.SharableConv2d(C, K, R, stride=stride, padding=pad, bias=has_b).to(DEV)
+        with torch.no_grad():
+            m.weight.normal_(0, (2.0 / (K * R * R)) ** 0.5)
+            if has_b:
+                m.bias.normal_()
+        m.piggymask = nn.Parameter(torch.rand_like(m.weight) * 0.01)
+        need_dx = C > 4
+        x = torch.randn(N, C, H, W, device=DEV).contiguous(memory_format=torch.channels_last).requires_grad_(need_dx)
+        y = m(x)
+        dy = torch.randn_like(y)
+        y.backward(dy)
+        b = (m.piggymask > 5e-3).float()
+        w_eff = (m.weight * b).detach()
+        y_ref = torch.nn.functional.conv2d(x.detach(), w_eff, m.bias.detach() if has_b else None, stride, pad)
+        assert y.shape == y_ref.shape
+        assert rel(y, y_ref) <= TOL_TC
+        g_ref = torch.nn.grad.conv2d_weight(x.detach(), w_eff.shape, dy, stride, pad)
+        assert rel(m.weight.grad, g_ref * b) <= TOL_TC
+        assert rel(m.piggymask.grad, g_ref * m.weight.detach()) <= TOL_TC
+        assert (m.weight.grad[b == 0] == 0).all()
+        if has_b:
+            assert rel(m.bias.grad, dy.sum((0, 2, 3))) <= 1e-5
+        lhs = ((y.detach() - (m.bias.detach().view(1, -1, 1, 1) if has_b else 0)).double() * dy.double()).sum().item()
+        rhs = (m.weight.detach().double() * m.weight.grad.double()).sum().item()
+        scale = y.detach().double().norm().item() * dy.double().norm().item()
+        assert abs(lhs - rhs) <= 1e-3 * scale
+        if need_dx:
+            dx_ref = torch.nn.grad.conv2d_input(x.shape, w_eff, dy, stride, pad)
+            assert rel(x.grad, dx_ref) <= TOL_TC
+            mid = (x.detach().double() * x.grad.double()).sum().item()
+            assert abs(lhs - mid) <= 1e-3 * scale
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
