@@ -639,7 +639,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
 template <int RS_T>
 __global__ void __launch_bounds__(256)
 wgrad_epilogue_krsc_kernel(const float *__restrict__ gpart, int splits, int K, int C, int Cg, int RS_rt, int kb, int cc,
-                           const float *__restrict__ w, const float *__restrict__ piggy,
+                           int sgroups, const float *__restrict__ w, const float *__restrict__ piggy,
                            const uint8_t *__restrict__ tmask, int cur, float wd, int mode, float thr,
                            float *__restrict__ dW, float *__restrict__ dP) {
   extern __shared__ float sh[];  // [kb][RS][cc + 1]
@@ -652,12 +652,12 @@ wgrad_epilogue_krsc_kernel(const float *__restrict__ gpart, int splits, int K, i
   const int ld = cc + 1;
   const long long split_stride = (long long)K * RS * Cg;
   const int row4 = ncc >> 2;                     // float4 per (k, t) row segment
-  for (int i = threadIdx.x; i < nk * RS * row4; i += blockDim.x) {
-    const int row = i / row4, c = (i - row * row4) * 4;     // row = kk * RS + t
-    const float *src = gpart + ((long long)k0 * RS + row) * Cg + c0 + c;
-    float4 a = __ldg(reinterpret_cast<const float4 *>(src));
-    int sp = 1;
-    for (; sp + 4 <= splits; sp += 4) {          // four loads in flight; the sum order stays 0,1,2,...
+  const int items = nk * RS * row4;
+  // sum of splits [s0, s1) of one float4 of G, four loads in flight, ascending order
+  auto sum_range = [&](const float *src, int s0, int s1) {
+    float4 a = __ldg(reinterpret_cast<const float4 *>(src + s0 * split_stride));
+    int sp = s0 + 1;
+    for (; sp + 4 <= s1; sp += 4) {
       const float4 b0 = __ldg(reinterpret_cast<const float4 *>(src + (sp + 0) * split_stride));
       const float4 b1 = __ldg(reinterpret_cast<const float4 *>(src + (sp + 1) * split_stride));
       const float4 b2 = __ldg(reinterpret_cast<const float4 *>(src + (sp + 2) * split_stride));
@@ -667,12 +667,47 @@ wgrad_epilogue_krsc_kernel(const float *__restrict__ gpart, int splits, int K, i
       a.x += b2.x; a.y += b2.y; a.z += b2.z; a.w += b2.w;
       a.x += b3.x; a.y += b3.y; a.z += b3.z; a.w += b3.w;
     }
-    for (; sp < splits; ++sp) {
+    for (; sp < s1; ++sp) {
       const float4 b = __ldg(reinterpret_cast<const float4 *>(src + sp * split_stride));
       a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
     }
-    float *d = sh + row * ld + c;
-    d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w;
+    return a;
+  };
+  if (sgroups > 1) {
+    // few float4 per block and many splits (the 32x32 / 16x16 layers: 72 items x 49 splits): `sgroups`
+    // thread groups each sum a contiguous range of splits, the ranges are then added in order --
+    // the serial chain of L2 round trips per thread shrinks by the group count, the result stays
+    // deterministic
+    float4 *gsum = reinterpret_cast<float4 *>(sh + kb * RS * ld + 4) ;   // [sgroups][items], 16-byte aligned below
+    gsum = reinterpret_cast<float4 *>((reinterpret_cast<uintptr_t>(gsum) + 15) & ~uintptr_t(15));
+    const int grp = threadIdx.x / items, i = threadIdx.x - grp * items;
+    const int per = (splits + sgroups - 1) / sgroups;
+    if (grp < sgroups) {
+      const int s0 = grp * per, s1 = min(splits, s0 + per);
+      const int row = i / row4, c = (i - row * row4) * 4;
+      const float *src = gpart + ((long long)k0 * RS + row) * Cg + c0 + c;
+      gsum[grp * items + i] = s0 < s1 ? sum_range(src, s0, s1) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    if (threadIdx.x < items) {
+      const int ii = threadIdx.x;
+      float4 a = gsum[ii];
+      for (int gq = 1; gq < sgroups; ++gq) {
+        const float4 b = gsum[gq * items + ii];
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      }
+      const int row = ii / row4, c = (ii - row * row4) * 4;
+      float *d = sh + row * ld + c;
+      d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w;
+    }
+  } else {
+    for (int i = threadIdx.x; i < items; i += blockDim.x) {
+      const int row = i / row4, c = (i - row * row4) * 4;     // row = kk * RS + t
+      const float *src = gpart + ((long long)k0 * RS + row) * Cg + c0 + c;
+      const float4 a = sum_range(src, 0, splits);
+      float *d = sh + row * ld + c;
+      d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w;
+    }
   }
   __syncthreads();
   const bool has_p = piggy != nullptr;
@@ -1183,6 +1218,12 @@ static int implicit_wgrad_fused(const cpgb_conv_desc &d, const float *x, const f
     cc = (cc + 3) & ~3;
     while (kb < 8 && (long long)(d.K / (2 * kb)) * cdiv_i(d.C, cc) >= 2LL * num_sms() && 2 * kb * cc * RS <= 4608) kb *= 2;
     size_t sh = (size_t)kb * RS * (cc + 1) * sizeof(float);
+    // split groups of the partial-sum phase (see the kernel): only when every block is tile-complete
+    int sgroups = 1;
+    const int items = kb * RS * (cc / 4);
+    if (items <= 128 && d.K % kb == 0 && d.C % cc == 0 && pl.splits >= 8)
+      sgroups = std::min(std::min(256 / items, pl.splits / 4), 8);
+    if (sgroups > 1) sh += (size_t)sgroups * items * 16 + 48;
     if (sh <= 96 * 1024 && (cc * RS) % 4 == 0) {
       static bool attr_done = false;
       if (!attr_done) {
@@ -1193,10 +1234,10 @@ static int implicit_wgrad_fused(const cpgb_conv_desc &d, const float *x, const f
       const dim3 egrid(cdiv_i(d.K, kb), cdiv_i(d.C, cc));
       if (RS == 9)
         CPGB_CUDA_OK(launch_pdl(wgrad_epilogue_krsc_kernel<9>, egrid, dim3(256), sh, st, (const float *)p.gpart,
-                                pl.splits, d.K, d.C, p.Cg, RS, kb, cc, w, piggy, tmask, cur, wd, mode, thr, dW, dP));
+                                pl.splits, d.K, d.C, p.Cg, RS, kb, cc, sgroups, w, piggy, tmask, cur, wd, mode, thr, dW, dP));
       else
         CPGB_CUDA_OK(launch_pdl(wgrad_epilogue_krsc_kernel<0>, egrid, dim3(256), sh, st, (const float *)p.gpart,
-                                pl.splits, d.K, d.C, p.Cg, RS, kb, cc, w, piggy, tmask, cur, wd, mode, thr, dW, dP));
+                                pl.splits, d.K, d.C, p.Cg, RS, kb, cc, sgroups, w, piggy, tmask, cur, wd, mode, thr, dW, dP));
       CPGB_LAUNCH_OK("wgrad_epilogue_krsc");
       return CPGB_OK;
     }
@@ -1472,13 +1513,45 @@ __global__ void __launch_bounds__(256) stage_weights_batched_kernel(const __grid
     const int k = b / cchunks, c0 = (b - k * cchunks) * STAGE_CC;
     const int cc = min(STAGE_CC, Cp - c0), cv = max(0, min(STAGE_CC, C - c0)), ld = RS | 1;
     const long long base = ((long long)k * C + c0) * RS;
-    for (int i = threadIdx.x; i < cv * RS; i += blockDim.x)
-      sh[(i / RS) * ld + (i % RS)] = to_tf32_rna(masked_weight(__ldg(w + base + i), piggy, base + i, thr));
-    __syncthreads();
     float *dst = wt + (long long)k * RS * Cp + c0;
-    for (int i = threadIdx.x; i < cc * RS; i += blockDim.x) {
-      const int t = i / cc, c = i - t * cc;
-      dst[(long long)t * Cp + c] = c < cv ? sh[c * ld + t] : 0.f;
+    const bool vec = (C & 3) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
+                     (!piggy || (reinterpret_cast<uintptr_t>(piggy) & 15) == 0);
+    if (vec) {
+      // 16-byte loads of the contiguous [cv][RS] slab, 16-byte stores of the [RS][cc] rows (Cp, c0 % 4 == 0)
+      for (int i4 = threadIdx.x; i4 < (cv * RS) >> 2; i4 += blockDim.x) {
+        float4 v = __ldg(reinterpret_cast<const float4 *>(w + base) + i4);
+        if (piggy) {
+          const float4 pv = __ldg(reinterpret_cast<const float4 *>(piggy + base) + i4);
+          v.x *= binarize_val(pv.x, thr); v.y *= binarize_val(pv.y, thr);
+          v.z *= binarize_val(pv.z, thr); v.w *= binarize_val(pv.w, thr);
+        }
+        const float e[4] = {v.x, v.y, v.z, v.w};
+        int c = (i4 * 4) / RS, t = i4 * 4 - c * RS;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          sh[c * ld + t] = to_tf32_rna(e[j]);
+          if (++t == RS) { t = 0; ++c; }
+        }
+      }
+      __syncthreads();
+      const int cc4 = cc >> 2;
+      for (int i4 = threadIdx.x; i4 < cc4 * RS; i4 += blockDim.x) {
+        const int t = i4 / cc4, c = (i4 - t * cc4) * 4;
+        float4 o;
+        o.x = c + 0 < cv ? sh[(c + 0) * ld + t] : 0.f;
+        o.y = c + 1 < cv ? sh[(c + 1) * ld + t] : 0.f;
+        o.z = c + 2 < cv ? sh[(c + 2) * ld + t] : 0.f;
+        o.w = c + 3 < cv ? sh[(c + 3) * ld + t] : 0.f;
+        *reinterpret_cast<float4 *>(dst + (long long)t * Cp + c) = o;
+      }
+    } else {
+      for (int i = threadIdx.x; i < cv * RS; i += blockDim.x)
+        sh[(i / RS) * ld + (i % RS)] = to_tf32_rna(masked_weight(__ldg(w + base + i), piggy, base + i, thr));
+      __syncthreads();
+      for (int i = threadIdx.x; i < cc * RS; i += blockDim.x) {
+        const int t = i / cc, c = i - t * cc;
+        dst[(long long)t * Cp + c] = c < cv ? sh[c * ld + t] : 0.f;
+      }
     }
   } else if (sb.kind[it] == 1) {
     const long long n4 = (long long)K * C * RS / 4;

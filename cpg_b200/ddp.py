@@ -16,6 +16,8 @@ end.  Prune steps need no collective: every rank holds the same W and T.
 import torch
 import torch.distributed as dist
 
+from .functional import pending_side_stream
+
 BIG = 1 << 18   # elements; tensors at least this large get their own overlapped all-reduce
 
 
@@ -58,8 +60,17 @@ class GradAllReducer:
                     self._hooks.append(p.register_post_accumulate_grad_hook(self._hook))
 
     def _hook(self, p):
-        if p.grad is not None:
-            self.pending.append((p.grad, dist.all_reduce(p.grad, op=self.op, group=self.group, async_op=True)))
+        if p.grad is None:
+            return
+        # the weight gradient may still be in flight on the wgrad side stream (cpg_b200.functional defers the
+        # join to the end of the backward pass): order the collective after that stream, not after the main one
+        side = pending_side_stream(p.grad.device) if p.grad.is_cuda else None
+        if side is not None:
+            with torch.cuda.stream(side):
+                work = dist.all_reduce(p.grad, op=self.op, group=self.group, async_op=True)
+        else:
+            work = dist.all_reduce(p.grad, op=self.op, group=self.group, async_op=True)
+        self.pending.append((p.grad, work))
 
     def reduce(self):
         """Call after backward(): waits for the overlapped reductions, reduces everything else

@@ -50,11 +50,18 @@ def _stage(lib, d, w, p, threshold, prestaged=None):
 
 
 _SIDE_STREAMS = {}
-OVERLAP_BACKWARD = True   # run wgrad on a side stream next to dgrad (both read dy; no data dependence)
+OVERLAP_BACKWARD = True   # run wgrad on a side stream (it only reads x and dy; nothing on the main chain needs it)
+DEFER_JOIN = True         # join the side stream once, at the end of the backward pass, instead of per layer
+_PENDING = {}             # device index -> tensors the side stream may still be reading (kept alive until the join)
+
+
+def _dev_index(device):
+    d = torch.device(device)
+    return d.index if d.index is not None else torch.cuda.current_device()
 
 
 def _side_stream(device):
-    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    key = _dev_index(device)
     st = _SIDE_STREAMS.get(key)
     if st is None:
         st = torch.cuda.Stream(device=device)
@@ -62,10 +69,40 @@ def _side_stream(device):
     return st
 
 
+def pending_side_stream(device):
+    """The side stream if weight-gradient kernels of the running backward pass are still queued on it
+    (their outputs must not be consumed on another stream before `join_side_stream`), else None."""
+    key = _dev_index(device)
+    return _SIDE_STREAMS.get(key) if key in _PENDING else None
+
+
+def join_side_stream(device=None):
+    """Make the current stream wait for the weight-gradient kernels of this backward pass and release
+    the tensors held for them.  Runs automatically at the end of every backward pass (autograd engine
+    callback); idempotent."""
+    keys = [_dev_index(device)] if device is not None else list(_PENDING.keys())
+    for key in keys:
+        if key in _PENDING:
+            with torch.cuda.device(key):
+                torch.cuda.current_stream().wait_stream(_SIDE_STREAMS[key])
+            del _PENDING[key]
+
+
+def _defer(device, tensors):
+    key = _dev_index(device)
+    if key not in _PENDING:
+        _PENDING[key] = []
+        # end-of-backward callback of the autograd engine (the mechanism DDP uses to finalise buckets)
+        torch.autograd.Variable._execution_engine.queue_callback(lambda: join_side_stream(key))
+    _PENDING[key].extend(t for t in tensors if t is not None)
+
+
 def _backward_kernels(lib, ctx, d, x, dy, w, p, threshold, staged, need_dx, need_w, has_bias, dx):
     """dgrad (+) wgrad with the fused epilogue for descriptor d.  Everything is allocated on the
-    current stream; when both passes are needed the wgrad launch is forked onto a side stream and
-    joined before returning (capturable: the fork/join become parallel branches of a CUDA graph)."""
+    current stream.  The wgrad launch is forked onto a side stream: wgrad(l) only reads x(l) and dy(l),
+    and nothing before optimizer.step() / the all-reduce reads dW, so the side stream is joined once at
+    the end of the backward pass -- wgrad then overlaps dgrad *and* the BN / ReLU / pooling backward
+    kernels of the following layers.  Capturable: fork and join become branches of the CUDA graph."""
     dW = dP = db = None
     device = x.device
     with torch.cuda.device(device):
@@ -77,13 +114,20 @@ def _backward_kernels(lib, ctx, d, x, dy, w, p, threshold, staged, need_dx, need
             dW = torch.empty_like(w)
             dP = torch.empty_like(w) if p is not None else None
             db = torch.empty(w.shape[0], dtype=torch.float32, device=device) if has_bias else None
-        fork = OVERLAP_BACKWARD and need_dx and need_w
+        fuse = ctx.fuse
+        in_backward = torch._C._current_graph_task_id() != -1
+        # a parameter that already holds a gradient gets `grad += dW` on the main stream as soon as this
+        # node returns (gradient accumulation): join immediately in that case
+        mod = ctx.module
+        fresh = mod is not None and all(getattr(mod, n, None) is None or getattr(mod, n).grad is None
+                                        for n in ('weight', 'piggymask', 'bias'))
+        defer = OVERLAP_BACKWARD and DEFER_JOIN and need_w and in_backward and fresh
+        fork = OVERLAP_BACKWARD and need_w and (need_dx or defer)
         if need_w:
             wstream = main
             if fork:
                 wstream = _side_stream(device)
                 wstream.wait_stream(main)
-            fuse = ctx.fuse
             mode = fuse.mode if fuse is not None else _lib.GRAD_RAW
             _lib.check(lib.cpgb_conv2d_wgrad_fused(
                 d, _lib.ptr(x), _lib.ptr(dy), _lib.ptr(w), _lib.ptr(p),
@@ -98,7 +142,12 @@ def _backward_kernels(lib, ctx, d, x, dy, w, p, threshold, staged, need_dx, need
                                              threshold, _lib.ptr(staged), _lib.ptr(ws_d), ws_d.numel(),
                                              main.cuda_stream), 'cpgb_conv2d_dgrad')
         if fork:
-            main.wait_stream(wstream)
+            if defer:
+                # inputs and scratch only: holding the outputs too would raise their use count and make
+                # AccumulateGrad clone them on the main stream instead of adopting them
+                _defer(device, (x, dy, w, p, ws_w, fuse.tmask if fuse is not None else None))
+            else:
+                main.wait_stream(wstream)
     return dW, dP, db
 
 

@@ -687,3 +687,34 @@ def test_full_size_resnet_spherenet_layers(layer):
             assert abs(lhs - mid) <= 1e-3 * scale
     finally:
         torch.backends.cudnn.allow_tf32 = old
+
+
+def test_deferred_wgrad_join_and_grad_accumulation():
+    """The weight-gradient kernels run on a side stream that is joined at the end of the backward pass
+    (autograd engine callback).  (1) gradients read right after backward() are complete; (2) a second
+    backward into existing .grad tensors (accumulation happens on the main stream) joins per layer:
+    the result is exactly twice the first gradient."""
+    import cpg_b200.functional as Fn
+    torch.manual_seed(5)
+    net = nn.Sequential(nl.SharableConv2d(32, 64, 3, padding=1, bias=True), nn.ReLU(),
+                        nl.SharableConv2d(64, 64, 3, padding=1, bias=False)).to(DEV)
+    with torch.no_grad():                       # the reference layers leave their parameters uninitialised
+        for p in net.parameters():
+            p.normal_(0, 0.05)
+    x = torch.randn(8, 32, 16, 16, device=DEV)
+    dy = torch.randn(8, 64, 16, 16, device=DEV)
+    net(x).backward(dy)
+    assert not Fn._PENDING                      # joined by the end-of-backward callback
+    g1 = [p.grad.clone() for p in net.parameters()]
+    Fn.DEFER_JOIN = False
+    try:
+        net.zero_grad(set_to_none=True)
+        net(x).backward(dy)
+        for a, p in zip(g1, net.parameters()):
+            assert torch.equal(a, p.grad)       # same bits with the per-layer join
+    finally:
+        Fn.DEFER_JOIN = True
+    net(x).backward(dy)                         # accumulate into the existing gradients
+    assert not Fn._PENDING
+    for a, p in zip(g1, net.parameters()):
+        assert torch.equal(2 * a, p.grad)
