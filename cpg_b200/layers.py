@@ -60,9 +60,12 @@ class _SharableBase(nn.Module):
         pre, self._cpg_prestaged = self._cpg_prestaged, None
         if pre is None:
             return None
-        buf, wptr, pptr = pre
+        buf, wptr, pptr, ev = pre
         if wptr != weight.data_ptr() or pptr != (piggy.data_ptr() if piggy is not None else 0):
             return None          # e.g. a DataParallel replica on another device
+        if ev is not None:       # the operand was built on the staging stream
+            with torch.cuda.device(weight.device):
+                torch.cuda.current_stream().wait_event(ev)
         return buf
 
     def _effective(self):
