@@ -89,6 +89,7 @@ def make_args(datasets, mode='finetune'):
     return a
 
 
+FUSE_BN_RELU = os.environ.get('CPGB_FUSE_BN', '1') != '0'   # cpg_b200.fused_norm on the product arm
 FUSED_OPTIM = True   # torch.optim.{SGD,Adam}(fused=True): same update rule, one pass over the parameters
 
 
@@ -247,6 +248,9 @@ class Trainer:
             import cpg_b200.layers as nl
             from cpg_b200.prune import SparsePruner
             self.net, self.masks, datasets, self.cur = build_model(nl.SharableConv2d, nl.SharableLinear, regime, device)
+            if FUSE_BN_RELU:
+                from cpg_b200.fused_norm import fuse_bn_relu
+                fuse_bn_relu(self.net)
             self.pruner = SparsePruner(self.net, self.masks, make_args(datasets), 0, 1, self.cur)
         else:
             self.net, self.masks, datasets, self.cur = build_model(TorchSharableConv2d, TorchSharableLinear, regime,

@@ -18,7 +18,7 @@ EXPORTS = [
     'cpgb_conv2d_wgrad_fused', 'cpgb_grad_epilogue', 'cpgb_prune_workspace_bytes', 'cpgb_prune_select',
     'cpgb_prune_batched_workspace_bytes', 'cpgb_prune_select_batched',
     'cpgb_apply_mask', 'cpgb_make_finetuning_mask', 'cpgb_mask_stats', 'cpgb_mask_stats_batched', 'cpgb_merge_grads',
-    'cpgb_split_merged_grad',
+    'cpgb_split_merged_grad', 'cpgb_bn_workspace_bytes', 'cpgb_bn_relu_fwd', 'cpgb_bn_relu_bwd',
 ]
 
 
@@ -80,6 +80,9 @@ def load():
                                                    i32, vp, vp]),
         'cpgb_merge_grads': (ctypes.c_int, [vp, vp, vp, i64, vp]),
         'cpgb_split_merged_grad': (ctypes.c_int, [vp, vp, i64, i32, vp, vp, vp]),
+        'cpgb_bn_workspace_bytes': (sz, [i64, i32]),
+        'cpgb_bn_relu_fwd': (ctypes.c_int, [vp, i64, i32, vp, vp, vp, vp, i32, f32, f32, i32, vp, vp, vp, vp, sz, vp]),
+        'cpgb_bn_relu_bwd': (ctypes.c_int, [vp, vp, i64, i32, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, sz, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -1,0 +1,371 @@
+// BatchNorm2d (+ ReLU) over NHWC fp32 activations: the consumer of every masked convolution in
+// models/vgg.py:109-118 and models/resnet.py:60-100 (conv -> nn.BatchNorm2d -> nn.ReLU(inplace=True)).
+// the step right after the hot path.  All four kernels are HBM-bound streaming
+// passes over an [M = N*H*W pixels][C channels] array (C % 4 == 0), 16 bytes per access:
+//
+//   training forward : stats   -- per-channel sum / sum of squares, one partial pair per block
+//                      finalize -- mean, biased variance, rstd, running statistics, a = gamma*rstd,
+//                                  b = beta - mean*a                        (C threads)
+//                      apply   -- y = max(0, a*x + b)
+//   backward         : stats   -- g = dy * [a*x + b > 0];  sum g, sum g*xhat
+//                      finalize -- dbeta, dgamma, c1 = sum g / M, c2 = sum g*xhat / M
+//                      apply   -- dx = a * (g - c1 - xhat * c2)
+//
+// A thread owns one float4 of channels for the whole kernel (its coefficients live in registers) and
+// walks pixel rows, so there is no per-element index arithmetic.  Partial sums are combined in a fixed
+// order in double precision: results are deterministic and do not depend on the grid size chosen.
+#include "common.cuh"
+
+namespace cpgb {
+
+namespace {
+
+constexpr int NA_THREADS = 256;
+constexpr int NA_STATS_PER_SM = 4;   // blocks per SM of the two reduction passes (= partial pairs per channel / SMs)
+
+int na_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0, v = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n = v > 0 ? v : 148;
+  }
+  return n;
+}
+
+struct NaGeom {
+  long long M;      // pixels
+  int C;            // channels
+  int lanes;        // float4 channel groups handled by one block (<= NA_THREADS)
+  int slots;        // pixel rows in flight per block = NA_THREADS / lanes
+  int cchunks;      // blockIdx.y extent
+};
+
+NaGeom na_geom(long long M, int C) {
+  NaGeom g;
+  g.M = M; g.C = C;
+  const int c4 = C / 4;
+  g.lanes = c4 < NA_THREADS ? c4 : NA_THREADS;
+  g.slots = NA_THREADS / g.lanes;
+  g.cchunks = (c4 + g.lanes - 1) / g.lanes;
+  return g;
+}
+
+int na_blocks(const NaGeom &g, int per_sm) {
+  long long want = (g.M + g.slots - 1) / g.slots;
+  long long cap = (long long)na_sms() * per_sm / g.cchunks;
+  if (cap < 1) cap = 1;
+  if (want < 1) want = 1;
+  return (int)(want < cap ? want : cap);
+}
+
+// Reduce the per-thread float4 pairs (s, q) of the pixel slots of a block and write one partial pair
+// per channel: part[(block * C + c) * 2 + {0, 1}].
+__device__ __forceinline__ void block_reduce_pairs(const NaGeom &g, float4 s, float4 q, int lane, int slot, int c4,
+                                                   bool active, float *__restrict__ part) {
+  __shared__ float4 red[2][NA_THREADS];
+  red[0][threadIdx.x] = s;
+  red[1][threadIdx.x] = q;
+  __syncthreads();
+  if (slot == 0 && active) {
+    for (int k = 1; k < g.slots; ++k) {
+      const float4 a = red[0][k * g.lanes + lane], b = red[1][k * g.lanes + lane];
+      s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+      q.x += b.x; q.y += b.y; q.z += b.z; q.w += b.w;
+    }
+    float *dst = part + ((long long)blockIdx.x * g.C + c4 * 4) * 2;
+    reinterpret_cast<float4 *>(dst)[0] = make_float4(s.x, q.x, s.y, q.y);
+    reinterpret_cast<float4 *>(dst)[1] = make_float4(s.z, q.z, s.w, q.w);
+  }
+}
+
+__global__ void __launch_bounds__(NA_THREADS)
+bn_stats_kernel(const NaGeom g, const float *__restrict__ x, float *__restrict__ part) {
+  const int lane = threadIdx.x % g.lanes, slot = threadIdx.x / g.lanes;
+  const int c4 = blockIdx.y * g.lanes + lane;
+  const bool active = slot < g.slots && c4 * 4 < g.C;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+  if (active) {
+    const float4 *xp = reinterpret_cast<const float4 *>(x) + c4;
+    const long long stride = (long long)gridDim.x * g.slots, cq = g.C / 4;
+#pragma unroll 4
+    for (long long r = (long long)blockIdx.x * g.slots + slot; r < g.M; r += stride) {
+      const float4 v = __ldg(xp + r * cq);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
+    }
+  }
+  block_reduce_pairs(g, s, q, lane, slot, c4, active, part);
+}
+
+// Sum the per-block partial pairs of channel c: one warp per channel, lanes stride over the blocks,
+// fixed butterfly in double precision (deterministic for a given grid).
+__device__ __forceinline__ void sum_partials(const float *__restrict__ part, int nblocks, int C, int c, double &s,
+                                             double &q) {
+  const int lane = threadIdx.x & 31;
+  s = 0.0; q = 0.0;
+  const float2 *p2 = reinterpret_cast<const float2 *>(part) + c;
+  int b = lane;
+  for (; b + 96 < nblocks; b += 128) {          // four independent loads in flight per lane
+    const float2 v0 = __ldg(p2 + (long long)b * C), v1 = __ldg(p2 + (long long)(b + 32) * C);
+    const float2 v2 = __ldg(p2 + (long long)(b + 64) * C), v3 = __ldg(p2 + (long long)(b + 96) * C);
+    s += (double)v0.x; q += (double)v0.y;
+    s += (double)v1.x; q += (double)v1.y;
+    s += (double)v2.x; q += (double)v2.y;
+    s += (double)v3.x; q += (double)v3.y;
+  }
+  for (; b < nblocks; b += 32) {
+    const float2 v = __ldg(p2 + (long long)b * C);
+    s += (double)v.x; q += (double)v.y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+}
+
+// mean / biased variance / rstd, running statistics (torch.nn.BatchNorm2d: unbiased variance, momentum;
+// momentum < 0 means cumulative average with factor 1 / num_batches_tracked passed as -momentum),
+// coefficients a = gamma * rstd, b = beta - mean * a.
+__global__ void __launch_bounds__(256)
+bn_finalize_kernel(const float *__restrict__ part, int nblocks, int C, long long M, const float *__restrict__ gamma,
+                   const float *__restrict__ beta, float *__restrict__ running_mean, float *__restrict__ running_var,
+                   float momentum, float eps, float *__restrict__ save_mean, float *__restrict__ save_rstd,
+                   float *__restrict__ coef_a, float *__restrict__ coef_b) {
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (c >= C) return;
+  double s, q;
+  sum_partials(part, nblocks, C, c, s, q);
+  if ((threadIdx.x & 31) != 0) return;
+  const double mean = s / (double)M;
+  double var = q / (double)M - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  save_mean[c] = (float)mean;
+  save_rstd[c] = rstd;
+  const float a = (gamma ? gamma[c] : 1.f) * rstd;
+  coef_a[c] = a;
+  coef_b[c] = (beta ? beta[c] : 0.f) - (float)mean * a;
+  if (running_mean) {
+    const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
+    running_mean[c] = (float)((1.0 - (double)momentum) * (double)running_mean[c] + (double)momentum * mean);
+    running_var[c] = (float)((1.0 - (double)momentum) * (double)running_var[c] + (double)momentum * unbiased);
+  }
+}
+
+// evaluation mode: coefficients out of the running statistics
+__global__ void __launch_bounds__(128)
+bn_eval_coef_kernel(int C, const float *__restrict__ gamma, const float *__restrict__ beta,
+                    const float *__restrict__ running_mean, const float *__restrict__ running_var, float eps,
+                    float *__restrict__ coef_a, float *__restrict__ coef_b) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float rstd = 1.0f / sqrtf(running_var[c] + eps);
+  const float a = (gamma ? gamma[c] : 1.f) * rstd;
+  coef_a[c] = a;
+  coef_b[c] = (beta ? beta[c] : 0.f) - running_mean[c] * a;
+}
+
+__global__ void __launch_bounds__(128)
+bn_coef_from_stats_kernel(int C, const float *__restrict__ gamma, const float *__restrict__ beta,
+                          const float *__restrict__ mean, const float *__restrict__ rstd, float *__restrict__ coef_a,
+                          float *__restrict__ coef_b) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float a = (gamma ? gamma[c] : 1.f) * rstd[c];
+  coef_a[c] = a;
+  coef_b[c] = (beta ? beta[c] : 0.f) - mean[c] * a;
+}
+
+__global__ void __launch_bounds__(NA_THREADS)
+bn_apply_kernel(const NaGeom g, const float *__restrict__ x, const float *__restrict__ coef_a,
+                const float *__restrict__ coef_b, int relu, float *__restrict__ y) {
+  const int lane = threadIdx.x % g.lanes, slot = threadIdx.x / g.lanes;
+  const int c4 = blockIdx.y * g.lanes + lane;
+  if (slot >= g.slots || c4 * 4 >= g.C) return;
+  const float4 a = __ldg(reinterpret_cast<const float4 *>(coef_a) + c4);
+  const float4 b = __ldg(reinterpret_cast<const float4 *>(coef_b) + c4);
+  const float4 *xp = reinterpret_cast<const float4 *>(x) + c4;
+  float4 *yp = reinterpret_cast<float4 *>(y) + c4;
+  const long long stride = (long long)gridDim.x * g.slots, cq = g.C / 4;
+#pragma unroll 4
+  for (long long r = (long long)blockIdx.x * g.slots + slot; r < g.M; r += stride) {
+    const float4 v = __ldg(xp + r * cq);
+    float4 o = make_float4(fmaf(v.x, a.x, b.x), fmaf(v.y, a.y, b.y), fmaf(v.z, a.z, b.z), fmaf(v.w, a.w, b.w));
+    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+    yp[r * cq] = o;
+  }
+}
+
+// g = dy * [relu ? a*x + b > 0 : 1];  xhat = (x - mean) * rstd
+#define NA_GRAD_ELEM(G, XH, V, D, A, B, MU, RS)                     \
+  {                                                                 \
+    const float z_ = fmaf(V, A, B);                                 \
+    G = (relu && !(z_ > 0.f)) ? 0.f : D;                            \
+    XH = (V - MU) * RS;                                             \
+  }
+
+__global__ void __launch_bounds__(NA_THREADS)
+bn_bwd_stats_kernel(const NaGeom g, const float *__restrict__ x, const float *__restrict__ dy,
+                    const float *__restrict__ coef_a, const float *__restrict__ coef_b,
+                    const float *__restrict__ save_mean, const float *__restrict__ save_rstd, int relu,
+                    float *__restrict__ part) {
+  const int lane = threadIdx.x % g.lanes, slot = threadIdx.x / g.lanes;
+  const int c4 = blockIdx.y * g.lanes + lane;
+  const bool active = slot < g.slots && c4 * 4 < g.C;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+  if (active) {
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(coef_a) + c4);
+    const float4 b = __ldg(reinterpret_cast<const float4 *>(coef_b) + c4);
+    const float4 mu = __ldg(reinterpret_cast<const float4 *>(save_mean) + c4);
+    const float4 rs = __ldg(reinterpret_cast<const float4 *>(save_rstd) + c4);
+    const float4 *xp = reinterpret_cast<const float4 *>(x) + c4;
+    const float4 *dp = reinterpret_cast<const float4 *>(dy) + c4;
+    const long long stride = (long long)gridDim.x * g.slots, cq = g.C / 4;
+#pragma unroll 4
+    for (long long r = (long long)blockIdx.x * g.slots + slot; r < g.M; r += stride) {
+      const float4 v = __ldg(xp + r * cq), d = __ldg(dp + r * cq);
+      float gx, gy, gz, gw, hx, hy, hz, hw;
+      NA_GRAD_ELEM(gx, hx, v.x, d.x, a.x, b.x, mu.x, rs.x)
+      NA_GRAD_ELEM(gy, hy, v.y, d.y, a.y, b.y, mu.y, rs.y)
+      NA_GRAD_ELEM(gz, hz, v.z, d.z, a.z, b.z, mu.z, rs.z)
+      NA_GRAD_ELEM(gw, hw, v.w, d.w, a.w, b.w, mu.w, rs.w)
+      s.x += gx; s.y += gy; s.z += gz; s.w += gw;
+      q.x = fmaf(gx, hx, q.x); q.y = fmaf(gy, hy, q.y); q.z = fmaf(gz, hz, q.z); q.w = fmaf(gw, hw, q.w);
+    }
+  }
+  block_reduce_pairs(g, s, q, lane, slot, c4, active, part);
+}
+
+// dbeta = sum g, dgamma = sum g * xhat; c1 = dbeta / M, c2 = dgamma / M (training) or 0 (evaluation
+// mode: the statistics are constants, dx = a * g)
+__global__ void __launch_bounds__(256)
+bn_bwd_finalize_kernel(const float *__restrict__ part, int nblocks, int C, long long M, int training,
+                       float *__restrict__ dgamma, float *__restrict__ dbeta, float *__restrict__ c1,
+                       float *__restrict__ c2) {
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (c >= C) return;
+  double s, q;
+  sum_partials(part, nblocks, C, c, s, q);
+  if ((threadIdx.x & 31) != 0) return;
+  if (dbeta) dbeta[c] = (float)s;
+  if (dgamma) dgamma[c] = (float)q;
+  c1[c] = training ? (float)(s / (double)M) : 0.f;
+  c2[c] = training ? (float)(q / (double)M) : 0.f;
+}
+
+__global__ void __launch_bounds__(NA_THREADS)
+bn_bwd_apply_kernel(const NaGeom g, const float *__restrict__ x, const float *__restrict__ dy,
+                    const float *__restrict__ coef_a, const float *__restrict__ coef_b,
+                    const float *__restrict__ save_mean, const float *__restrict__ save_rstd,
+                    const float *__restrict__ c1, const float *__restrict__ c2, int relu, float *__restrict__ dx) {
+  const int lane = threadIdx.x % g.lanes, slot = threadIdx.x / g.lanes;
+  const int c4 = blockIdx.y * g.lanes + lane;
+  if (slot >= g.slots || c4 * 4 >= g.C) return;
+  const float4 a = __ldg(reinterpret_cast<const float4 *>(coef_a) + c4);
+  const float4 b = __ldg(reinterpret_cast<const float4 *>(coef_b) + c4);
+  const float4 mu = __ldg(reinterpret_cast<const float4 *>(save_mean) + c4);
+  const float4 rs = __ldg(reinterpret_cast<const float4 *>(save_rstd) + c4);
+  const float4 k1 = __ldg(reinterpret_cast<const float4 *>(c1) + c4);
+  const float4 k2 = __ldg(reinterpret_cast<const float4 *>(c2) + c4);
+  const float4 *xp = reinterpret_cast<const float4 *>(x) + c4;
+  const float4 *dp = reinterpret_cast<const float4 *>(dy) + c4;
+  float4 *op = reinterpret_cast<float4 *>(dx) + c4;
+  const long long stride = (long long)gridDim.x * g.slots, cq = g.C / 4;
+#pragma unroll 4
+  for (long long r = (long long)blockIdx.x * g.slots + slot; r < g.M; r += stride) {
+    const float4 v = __ldg(xp + r * cq), d = __ldg(dp + r * cq);
+    float gx, gy, gz, gw, hx, hy, hz, hw;
+    NA_GRAD_ELEM(gx, hx, v.x, d.x, a.x, b.x, mu.x, rs.x)
+    NA_GRAD_ELEM(gy, hy, v.y, d.y, a.y, b.y, mu.y, rs.y)
+    NA_GRAD_ELEM(gz, hz, v.z, d.z, a.z, b.z, mu.z, rs.z)
+    NA_GRAD_ELEM(gw, hw, v.w, d.w, a.w, b.w, mu.w, rs.w)
+    op[r * cq] = make_float4(a.x * (gx - k1.x - hx * k2.x), a.y * (gy - k1.y - hy * k2.y),
+                             a.z * (gz - k1.z - hz * k2.z), a.w * (gw - k1.w - hw * k2.w));
+  }
+}
+
+bool na_args_ok(const void *x, long long M, int C) {
+  return M > 0 && C > 0 && C % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+}
+
+}  // namespace
+
+// scratch layout: [coef_a C][coef_b C][c1 C][c2 C][partials blocks*C*2]
+static size_t na_ws_bytes(long long M, int C) {
+  NaGeom g = na_geom(M, C);
+  return ((size_t)4 * C + (size_t)na_blocks(g, NA_STATS_PER_SM) * C * 2) * sizeof(float) + 64;
+}
+
+}  // namespace cpgb
+
+using namespace cpgb;
+
+extern "C" {
+
+size_t cpgb_bn_workspace_bytes(int64_t M, int32_t C) {
+  if (M <= 0 || C <= 0 || C % 4) return 0;
+  return na_ws_bytes(M, C);
+}
+
+int cpgb_bn_relu_fwd(const float *x, int64_t M, int32_t C, const float *gamma, const float *beta, float *running_mean,
+                     float *running_var, int32_t training, float momentum, float eps, int32_t relu, float *y,
+                     float *save_mean, float *save_rstd, void *ws, size_t ws_bytes, void *stream) {
+  if (!na_args_ok(x, M, C) || !y || (reinterpret_cast<uintptr_t>(y) & 15)) {
+    set_error("cpgb_bn_relu_fwd: needs NHWC fp32 with C %% 4 == 0 and 16-byte aligned x / y"); return CPGB_EINVAL;
+  }
+  if (!ws || ws_bytes < na_ws_bytes(M, C) || (reinterpret_cast<uintptr_t>(ws) & 15)) {
+    set_error("cpgb_bn_relu_fwd: workspace %zu < %zu", ws_bytes, na_ws_bytes(M, C)); return CPGB_EWORKSPACE;
+  }
+  if (training ? (!save_mean || !save_rstd) : (!running_mean || !running_var)) {
+    set_error("cpgb_bn_relu_fwd: missing statistics buffers"); return CPGB_EINVAL;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  NaGeom g = na_geom(M, C);
+  float *coef_a = reinterpret_cast<float *>(ws), *coef_b = coef_a + C, *part = coef_a + 4 * C;
+  if (training) {
+    const int nb = na_blocks(g, NA_STATS_PER_SM);
+    bn_stats_kernel<<<dim3(nb, g.cchunks), NA_THREADS, 0, st>>>(g, x, part);
+    CPGB_LAUNCH_OK("bn_stats");
+    bn_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(part, nb, C, M, gamma, beta, running_mean, running_var, momentum,
+                                                        eps, save_mean, save_rstd, coef_a, coef_b);
+    CPGB_LAUNCH_OK("bn_finalize");
+  } else {
+    bn_eval_coef_kernel<<<(C + 127) / 128, 128, 0, st>>>(C, gamma, beta, running_mean, running_var, eps, coef_a, coef_b);
+    CPGB_LAUNCH_OK("bn_eval_coef");
+  }
+  bn_apply_kernel<<<dim3(na_blocks(g, 8), g.cchunks), NA_THREADS, 0, st>>>(g, x, coef_a, coef_b, relu, y);
+  CPGB_LAUNCH_OK("bn_apply");
+  return CPGB_OK;
+}
+
+int cpgb_bn_relu_bwd(const float *x, const float *dy, int64_t M, int32_t C, const float *gamma, const float *beta,
+                     const float *mean, const float *rstd, int32_t training, int32_t relu, float *dx, float *dgamma,
+                     float *dbeta, void *ws, size_t ws_bytes, void *stream) {
+  if (!na_args_ok(x, M, C) || !dy || !dx || !mean || !rstd || (reinterpret_cast<uintptr_t>(dy) & 15) ||
+      (reinterpret_cast<uintptr_t>(dx) & 15)) {
+    set_error("cpgb_bn_relu_bwd: needs NHWC fp32 with C %% 4 == 0 and 16-byte aligned tensors"); return CPGB_EINVAL;
+  }
+  if (!ws || ws_bytes < na_ws_bytes(M, C) || (reinterpret_cast<uintptr_t>(ws) & 15)) {
+    set_error("cpgb_bn_relu_bwd: workspace %zu < %zu", ws_bytes, na_ws_bytes(M, C)); return CPGB_EWORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  NaGeom g = na_geom(M, C);
+  float *coef_a = reinterpret_cast<float *>(ws), *coef_b = coef_a + C, *c1 = coef_a + 2 * C, *c2 = coef_a + 3 * C,
+        *part = coef_a + 4 * C;
+  // a = gamma * rstd, b = beta - mean * a from the saved statistics (eps is already inside rstd)
+  bn_coef_from_stats_kernel<<<(C + 127) / 128, 128, 0, st>>>(C, gamma, beta, mean, rstd, coef_a, coef_b);
+  CPGB_LAUNCH_OK("bn_coef_from_stats");
+  const int nb = na_blocks(g, NA_STATS_PER_SM);
+  bn_bwd_stats_kernel<<<dim3(nb, g.cchunks), NA_THREADS, 0, st>>>(g, x, dy, coef_a, coef_b, mean, rstd, relu, part);
+  CPGB_LAUNCH_OK("bn_bwd_stats");
+  bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(part, nb, C, M, training, dgamma, dbeta, c1, c2);
+  CPGB_LAUNCH_OK("bn_bwd_finalize");
+  bn_bwd_apply_kernel<<<dim3(na_blocks(g, 8), g.cchunks), NA_THREADS, 0, st>>>(g, x, dy, coef_a, coef_b, mean, rstd, c1, c2,
+                                                                              relu, dx);
+  CPGB_LAUNCH_OK("bn_bwd_apply");
+  return CPGB_OK;
+}
+
+}  // extern "C"

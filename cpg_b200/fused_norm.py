@@ -1,0 +1,149 @@
+"""BatchNorm2d (+ ReLU) for the consumers of the masked convolutions.
+
+Every SharableConv2d of models/vgg.py:109-118 and models/resnet.py:60-100 feeds
+``nn.BatchNorm2d -> nn.ReLU(inplace=True)``.  On B200 the stock pair costs three to four times its HBM
+floor (cuDNN's NHWC batch-norm kernels plus a separate ReLU pass in each direction).
+``FusedBatchNormReLU2d`` is a drop-in ``nn.BatchNorm2d`` subclass -- same constructor, parameters, buffers,
+``state_dict`` keys, running-statistics semantics, and ``isinstance(m, nn.BatchNorm2d)`` still holds for the
+reference's per-task BN bookkeeping (utils/manager.py:198-231) -- whose forward / backward are four
+streaming kernels of ``csrc/norm_act.cu`` with the ReLU folded in.
+
+``fuse_bn_relu(model)`` rewrites a built model in place: every ``nn.BatchNorm2d`` becomes a
+``FusedBatchNormReLU2d`` that *shares* the original parameter and buffer tensors, and inside
+``nn.Sequential`` containers a directly following ``nn.ReLU`` is absorbed (replaced by ``nn.Identity`` so
+the child indices -- and with them the mask keys ``features.<idx>`` -- do not move).
+
+Inputs the kernels do not take (CPU tensors, non-fp32, C % 4 != 0, momentum=None) go through
+``nn.BatchNorm2d.forward`` + ``F.relu``: batch-norm is not part of the masked-convolution path, so unlike
+the layers of ``cpg_b200.layers`` this module keeps the stock implementation as its general case.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+
+CL = torch.channels_last
+
+
+class _BNReLUFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, training, momentum, eps, relu):
+        lib = _lib.load()
+        if not x.is_contiguous(memory_format=CL):
+            x = x.contiguous(memory_format=CL)
+        N, C, H, W = x.shape
+        M = N * H * W
+        y = torch.empty_like(x)                      # keeps the NHWC strides
+        w = weight.detach().contiguous() if weight is not None else None
+        b = bias.detach().contiguous() if bias is not None else None
+        with torch.cuda.device(x.device):
+            ws = torch.empty(lib.cpgb_bn_workspace_bytes(M, C), dtype=torch.uint8, device=x.device)
+            if training:
+                mean = torch.empty(C, dtype=torch.float32, device=x.device)
+                rstd = torch.empty(C, dtype=torch.float32, device=x.device)
+            else:
+                mean, rstd = running_mean, torch.rsqrt(running_var + eps)
+            _lib.check(lib.cpgb_bn_relu_fwd(
+                _lib.ptr(x), M, C, _lib.ptr(w), _lib.ptr(b), _lib.ptr(running_mean), _lib.ptr(running_var),
+                1 if training else 0, float(momentum), float(eps), 1 if relu else 0, _lib.ptr(y),
+                _lib.ptr(mean) if training else None, _lib.ptr(rstd) if training else None,
+                _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), 'cpgb_bn_relu_fwd')
+        ctx.save_for_backward(x, w, b, mean, rstd)
+        ctx.cfg = (bool(training), bool(relu), weight is not None, bias is not None)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x, w, b, mean, rstd = ctx.saved_tensors
+        training, relu, has_w, has_b = ctx.cfg
+        if not dy.is_contiguous(memory_format=CL):
+            dy = dy.contiguous(memory_format=CL)
+        N, C, H, W = x.shape
+        M = N * H * W
+        dx = torch.empty_like(x)
+        dg = torch.empty(C, dtype=torch.float32, device=x.device) if has_w else None
+        db = torch.empty(C, dtype=torch.float32, device=x.device) if has_b else None
+        with torch.cuda.device(x.device):
+            ws = torch.empty(lib.cpgb_bn_workspace_bytes(M, C), dtype=torch.uint8, device=x.device)
+            _lib.check(lib.cpgb_bn_relu_bwd(
+                _lib.ptr(x), _lib.ptr(dy), M, C, _lib.ptr(w), _lib.ptr(b), _lib.ptr(mean), _lib.ptr(rstd),
+                1 if training else 0, 1 if relu else 0, _lib.ptr(dx), _lib.ptr(dg), _lib.ptr(db),
+                _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), 'cpgb_bn_relu_bwd')
+        return dx, dg, db, None, None, None, None, None, None
+
+
+class FusedBatchNormReLU2d(nn.BatchNorm2d):
+    """``nn.BatchNorm2d`` with an optional fused ReLU (``relu=True``: y = relu(batch_norm(x)))."""
+
+    def __init__(self, num_features, eps=1e-5, momentum=0.1, affine=True, track_running_stats=True, relu=False,
+                 device=None, dtype=None):
+        super().__init__(num_features, eps, momentum, affine, track_running_stats, device=device, dtype=dtype)
+        self.relu = bool(relu)
+
+    @classmethod
+    def from_bn(cls, bn, relu):
+        """A fused module over the SAME parameter / buffer tensors as `bn` (state_dict keys unchanged)."""
+        new = cls(bn.num_features, bn.eps, bn.momentum, bn.affine, bn.track_running_stats, relu=relu,
+                  device=torch.device('meta'))
+        for name in ('weight', 'bias'):
+            new._parameters[name] = bn._parameters.get(name)
+        for name in ('running_mean', 'running_var', 'num_batches_tracked'):
+            new._buffers[name] = bn._buffers.get(name)
+        new.training = bn.training
+        return new
+
+    def extra_repr(self):
+        return super().extra_repr() + f', relu={self.relu}'
+
+    def _fast(self, x):
+        if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] % 4 == 0 and x.numel() > 0):
+            return False
+        for t in (self.weight, self.bias, self.running_mean, self.running_var):
+            if t is not None and (t.dtype != torch.float32 or t.device != x.device):
+                return False
+        if self.training and self.track_running_stats and self.momentum is None:
+            return False          # cumulative average needs the step count on the host
+        return True
+
+    def forward(self, x):
+        if not self._fast(x):
+            y = super().forward(x)
+            return F.relu(y) if self.relu else y
+        self._check_input_dim(x)
+        training = self.training or (self.running_mean is None and self.running_var is None)
+        if training and x.numel() // x.shape[1] <= 1:
+            raise ValueError(f'Expected more than 1 value per channel when training, got input size {x.size()}')
+        update = self.training and self.track_running_stats
+        if update and self.num_batches_tracked is not None:
+            self.num_batches_tracked.add_(1)
+        rm = self.running_mean if (not training or update) else None
+        rv = self.running_var if (not training or update) else None
+        return _BNReLUFn.apply(x, self.weight, self.bias, rm, rv, training,
+                               self.momentum if self.momentum is not None else 0.0, self.eps, self.relu)
+
+
+def fuse_bn_relu(model):
+    """Swap every ``nn.BatchNorm2d`` of `model` for a ``FusedBatchNormReLU2d`` sharing its tensors; inside
+    ``nn.Sequential`` containers a directly following ``nn.ReLU`` is folded in and replaced by
+    ``nn.Identity`` (child indices, parameter names and mask keys are unchanged).  Returns the number of
+    (batch-norm, relu) pairs and of lone batch-norms converted."""
+    pairs = lone = 0
+    for parent in list(model.modules()):
+        names = list(parent._modules.keys())
+        for i, name in enumerate(names):
+            m = parent._modules[name]
+            if type(m) is not nn.BatchNorm2d:
+                continue
+            nxt = parent._modules[names[i + 1]] if (isinstance(parent, nn.Sequential) and i + 1 < len(names)) else None
+            relu = type(nxt) is nn.ReLU
+            parent._modules[name] = FusedBatchNormReLU2d.from_bn(m, relu=relu)
+            if relu:
+                parent._modules[names[i + 1]] = nn.Identity()
+                pairs += 1
+            else:
+                lone += 1
+    return pairs, lone

@@ -1,0 +1,43 @@
+"""Host-side checks of cpg_b200.fused_norm (no GPU): the model rewrite keeps names / tensors, and inputs
+the kernels do not take go through stock torch with identical results."""
+import torch
+import torch.nn as nn
+
+from cpg_b200.fused_norm import FusedBatchNormReLU2d, fuse_bn_relu
+
+
+def _net():
+    return nn.Sequential(nn.Conv2d(3, 8, 3, padding=1, bias=False), nn.BatchNorm2d(8), nn.ReLU(inplace=True),
+                         nn.MaxPool2d(2), nn.Conv2d(8, 12, 3, padding=1), nn.BatchNorm2d(12), nn.Sigmoid())
+
+
+def test_fuse_keeps_names_tensors_and_results():
+    torch.manual_seed(0)
+    ref, net = _net(), _net()
+    net.load_state_dict(ref.state_dict())
+    keys = list(net.state_dict().keys())
+    bn1 = net[1]
+    assert fuse_bn_relu(net) == (1, 1)
+    assert list(net.state_dict().keys()) == keys                      # checkpoint layout unchanged
+    assert isinstance(net[1], FusedBatchNormReLU2d) and isinstance(net[1], nn.BatchNorm2d) and net[1].relu
+    assert isinstance(net[2], nn.Identity) and isinstance(net[5], FusedBatchNormReLU2d) and not net[5].relu
+    assert net[1].weight is bn1.weight and net[1].running_mean is bn1.running_mean
+    assert fuse_bn_relu(net) == (0, 0)                                # idempotent
+    x = torch.randn(4, 3, 8, 8)
+    for train in (True, False):
+        ref.train(train); net.train(train)
+        xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+        ya, yb = ref(xa), net(xb)
+        assert torch.equal(ya, yb)                                    # CPU: stock path, bit for bit
+        ya.sum().backward(); yb.sum().backward()
+        assert torch.equal(xa.grad, xb.grad)
+    for (ka, va), (kb, vb) in zip(ref.state_dict().items(), net.state_dict().items()):
+        assert ka == kb and torch.equal(va, vb), ka                   # running statistics / step counters too
+
+
+def test_fused_module_state_dict_roundtrip():
+    m = FusedBatchNormReLU2d(8, relu=True)
+    plain = nn.BatchNorm2d(8)
+    plain.load_state_dict(m.state_dict())
+    m.load_state_dict(plain.state_dict())
+    assert 'relu=True' in repr(m)

@@ -718,3 +718,92 @@ def test_deferred_wgrad_join_and_grad_accumulation():
     assert not Fn._PENDING
     for a, p in zip(g1, net.parameters()):
         assert torch.equal(2 * a, p.grad)
+
+
+# ---------------------------------------------------------------------------------------------
+# BatchNorm2d (+ ReLU) kernels against torch.nn.BatchNorm2d + ReLU on the same GPU
+# ---------------------------------------------------------------------------------------------
+BN_CASES = [
+    # N, C, H, W, relu, affine
+    (128, 64, 32, 32, True, True),       # VGG16 first block at the bench size
+    (128, 512, 2, 2, True, True),        # VGG16 last block
+    (32, 256, 56, 56, False, True),      # ResNet-50 bottleneck output (no ReLU before the residual add)
+    (4, 156, 7, 5, True, True),          # width-multiplied channel count (39 float4 groups), ragged image
+    (2, 2048, 7, 7, True, True),         # more than 256 float4 groups: two channel chunks per block row
+    (3, 8, 5, 5, True, False),           # affine=False
+]
+
+
+@pytest.mark.parametrize('case', BN_CASES)
+def test_fused_bn_relu_vs_torch(case):
+    from cpg_b200.fused_norm import FusedBatchNormReLU2d
+    N, C, H, W, relu, affine = case
+    torch.manual_seed(N + C + H)
+    ref = nn.BatchNorm2d(C, affine=affine).to(DEV)
+    if affine:
+        with torch.no_grad():
+            ref.weight.uniform_(0.5, 1.5)
+            ref.bias.normal_(0, 0.3)
+    fused = FusedBatchNormReLU2d.from_bn(nn.BatchNorm2d(C, affine=affine).to(DEV), relu=relu)
+    fused.load_state_dict(ref.state_dict())
+    lib = _lib.load()
+    for step in range(2):                                   # two steps: running statistics accumulate
+        x = (torch.randn(N, C, H, W, device=DEV) * 2 + 0.7).contiguous(memory_format=torch.channels_last)
+        dy = torch.randn(N, C, H, W, device=DEV).contiguous(memory_format=torch.channels_last)
+        xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+        ya = ref(xa)
+        ya = torch.relu(ya) if relu else ya
+        before = lib.cpgb_launch_count()
+        yb = fused(xb)
+        assert lib.cpgb_launch_count() - before == 3        # stats, finalize, apply: the CUDA path ran
+        assert yb.is_contiguous(memory_format=torch.channels_last)
+        ya.backward(dy); yb.backward(dy)
+        assert rel(yb, ya) <= TOL_FP32
+        assert rel(xb.grad, xa.grad) <= 1e-4
+        if affine:
+            assert rel(fused.weight.grad, ref.weight.grad) <= 1e-4
+            assert rel(fused.bias.grad, ref.bias.grad) <= 1e-4
+            ref.weight.grad = None; ref.bias.grad = None; fused.weight.grad = None; fused.bias.grad = None
+        assert ((yb == 0) == (ya == 0)).float().mean().item() > 0.9999 or not relu
+    assert rel(fused.running_mean, ref.running_mean) <= TOL_FP32
+    assert rel(fused.running_var, ref.running_var) <= TOL_FP32
+    assert int(fused.num_batches_tracked) == int(ref.num_batches_tracked) == 2
+    ref.eval(); fused.eval()                                # evaluation mode: running statistics, same kernels
+    x = torch.randn(N, C, H, W, device=DEV).contiguous(memory_format=torch.channels_last)
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    ya = torch.relu(ref(xa)) if relu else ref(xa)
+    yb = fused(xb)
+    dy = torch.randn_like(ya)
+    ya.backward(dy); yb.backward(dy)
+    assert rel(yb, ya) <= TOL_FP32 and rel(xb.grad, xa.grad) <= 1e-4
+    if affine:
+        assert rel(fused.weight.grad, ref.weight.grad) <= 1e-4 and rel(fused.bias.grad, ref.bias.grad) <= 1e-4
+
+
+def test_fused_bn_model_step_matches_stock_modules():
+    """fuse_bn_relu on the VGG16-BN harness: one training step (fp32 CUDA-core conv path, so that the
+    comparison isolates the batch-norm kernels) gives the same loss, gradients and running statistics as
+    the stock nn.BatchNorm2d / nn.ReLU modules, and the state_dict keys do not change."""
+    from cpg_b200.fused_norm import fuse_bn_relu
+    from tests.trajectory import build
+    _lib.set_path(_lib.PATH_SIMT)
+    outs = []
+    for fuse in (False, True):
+        model, masks, loader = build(nl.SharableConv2d, nl.SharableLinear, DEV, width=0.5, batch=16)
+        keys = list(model.state_dict().keys())
+        if fuse:
+            assert fuse_bn_relu(model) == (13, 0)
+            assert list(model.state_dict().keys()) == keys
+        model.train()
+        data, target = loader[0]
+        loss = nn.CrossEntropyLoss()(model(data.to(DEV)), target.to(DEV))
+        loss.backward()
+        outs.append((loss.item(), {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None},
+                     {n: b.clone() for n, b in model.named_buffers()}))
+    (l0, g0, b0), (l1, g1, b1) = outs
+    assert abs(l0 - l1) <= 1e-5 * max(1.0, abs(l0))
+    for n in g0:
+        a, b = g1[n].double(), g0[n].double()
+        assert ((a - b).norm() / b.norm().clamp_min(1e-30)).item() <= 2e-3, n     # through 13 BN layers
+    for n in b0:
+        assert rel(b1[n].float(), b0[n].float()) <= 1e-5, n
