@@ -20,8 +20,9 @@ namespace cpgb {
 
 namespace {
 
-constexpr int NA_THREADS = 256;
-constexpr int NA_STATS_PER_SM = 4;   // blocks per SM of the two reduction passes (= partial pairs per channel / SMs)
+constexpr int NA_THREADS = 256;         // streaming (apply) passes: 8 blocks per SM
+constexpr int NA_STATS_THREADS = 1024;  // reduction passes: ONE fat block per SM, so that a channel has only
+constexpr int NA_STATS_PER_SM = 1;      // ~148 partial pairs and the finalize step is a single round of loads
 
 int na_sms() {
   static int n = 0;
@@ -41,12 +42,12 @@ struct NaGeom {
   int cchunks;      // blockIdx.y extent
 };
 
-NaGeom na_geom(long long M, int C) {
+NaGeom na_geom(long long M, int C, int threads = NA_THREADS) {
   NaGeom g;
   g.M = M; g.C = C;
   const int c4 = C / 4;
-  g.lanes = c4 < NA_THREADS ? c4 : NA_THREADS;
-  g.slots = NA_THREADS / g.lanes;
+  g.lanes = c4 < threads ? c4 : threads;
+  g.slots = threads / g.lanes;
   g.cchunks = (c4 + g.lanes - 1) / g.lanes;
   return g;
 }
@@ -63,7 +64,7 @@ int na_blocks(const NaGeom &g, int per_sm) {
 // per channel: part[(block * C + c) * 2 + {0, 1}].
 __device__ __forceinline__ void block_reduce_pairs(const NaGeom &g, float4 s, float4 q, int lane, int slot, int c4,
                                                    bool active, float *__restrict__ part) {
-  __shared__ float4 red[2][NA_THREADS];
+  __shared__ float4 red[2][NA_STATS_THREADS];
   red[0][threadIdx.x] = s;
   red[1][threadIdx.x] = q;
   __syncthreads();
@@ -79,7 +80,7 @@ __device__ __forceinline__ void block_reduce_pairs(const NaGeom &g, float4 s, fl
   }
 }
 
-__global__ void __launch_bounds__(NA_THREADS)
+__global__ void __launch_bounds__(NA_STATS_THREADS)
 bn_stats_kernel(const NaGeom g, const float *__restrict__ x, float *__restrict__ part) {
   const int lane = threadIdx.x % g.lanes, slot = threadIdx.x / g.lanes;
   const int c4 = blockIdx.y * g.lanes + lane;
@@ -167,15 +168,14 @@ bn_eval_coef_kernel(int C, const float *__restrict__ gamma, const float *__restr
   coef_b[c] = (beta ? beta[c] : 0.f) - running_mean[c] * a;
 }
 
-__global__ void __launch_bounds__(128)
-bn_coef_from_stats_kernel(int C, const float *__restrict__ gamma, const float *__restrict__ beta,
-                          const float *__restrict__ mean, const float *__restrict__ rstd, float *__restrict__ coef_a,
-                          float *__restrict__ coef_b) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const float a = (gamma ? gamma[c] : 1.f) * rstd[c];
-  coef_a[c] = a;
-  coef_b[c] = (beta ? beta[c] : 0.f) - mean[c] * a;
+// a = gamma * rstd, b = beta - mean * a for the four channels of a thread (the same expressions as the
+// forward finalize step, so the recomputed ReLU mask matches the forward pass bit for bit)
+__device__ __forceinline__ void coef_from_stats(const float *__restrict__ gamma, const float *__restrict__ beta, int c4,
+                                                const float4 &mu, const float4 &rs, float4 &a, float4 &b) {
+  const float4 gm = gamma ? __ldg(reinterpret_cast<const float4 *>(gamma) + c4) : make_float4(1.f, 1.f, 1.f, 1.f);
+  const float4 bt = beta ? __ldg(reinterpret_cast<const float4 *>(beta) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  a = make_float4(gm.x * rs.x, gm.y * rs.y, gm.z * rs.z, gm.w * rs.w);
+  b = make_float4(bt.x - mu.x * a.x, bt.y - mu.y * a.y, bt.z - mu.z * a.z, bt.w - mu.w * a.w);
 }
 
 __global__ void __launch_bounds__(NA_THREADS)
@@ -206,9 +206,9 @@ bn_apply_kernel(const NaGeom g, const float *__restrict__ x, const float *__rest
     XH = (V - MU) * RS;                                             \
   }
 
-__global__ void __launch_bounds__(NA_THREADS)
+__global__ void __launch_bounds__(NA_STATS_THREADS)
 bn_bwd_stats_kernel(const NaGeom g, const float *__restrict__ x, const float *__restrict__ dy,
-                    const float *__restrict__ coef_a, const float *__restrict__ coef_b,
+                    const float *__restrict__ gamma, const float *__restrict__ beta,
                     const float *__restrict__ save_mean, const float *__restrict__ save_rstd, int relu,
                     float *__restrict__ part) {
   const int lane = threadIdx.x % g.lanes, slot = threadIdx.x / g.lanes;
@@ -216,10 +216,10 @@ bn_bwd_stats_kernel(const NaGeom g, const float *__restrict__ x, const float *__
   const bool active = slot < g.slots && c4 * 4 < g.C;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
   if (active) {
-    const float4 a = __ldg(reinterpret_cast<const float4 *>(coef_a) + c4);
-    const float4 b = __ldg(reinterpret_cast<const float4 *>(coef_b) + c4);
     const float4 mu = __ldg(reinterpret_cast<const float4 *>(save_mean) + c4);
     const float4 rs = __ldg(reinterpret_cast<const float4 *>(save_rstd) + c4);
+    float4 a, b;
+    coef_from_stats(gamma, beta, c4, mu, rs, a, b);
     const float4 *xp = reinterpret_cast<const float4 *>(x) + c4;
     const float4 *dp = reinterpret_cast<const float4 *>(dy) + c4;
     const long long stride = (long long)gridDim.x * g.slots, cq = g.C / 4;
@@ -257,16 +257,16 @@ bn_bwd_finalize_kernel(const float *__restrict__ part, int nblocks, int C, long 
 
 __global__ void __launch_bounds__(NA_THREADS)
 bn_bwd_apply_kernel(const NaGeom g, const float *__restrict__ x, const float *__restrict__ dy,
-                    const float *__restrict__ coef_a, const float *__restrict__ coef_b,
+                    const float *__restrict__ gamma, const float *__restrict__ beta,
                     const float *__restrict__ save_mean, const float *__restrict__ save_rstd,
                     const float *__restrict__ c1, const float *__restrict__ c2, int relu, float *__restrict__ dx) {
   const int lane = threadIdx.x % g.lanes, slot = threadIdx.x / g.lanes;
   const int c4 = blockIdx.y * g.lanes + lane;
   if (slot >= g.slots || c4 * 4 >= g.C) return;
-  const float4 a = __ldg(reinterpret_cast<const float4 *>(coef_a) + c4);
-  const float4 b = __ldg(reinterpret_cast<const float4 *>(coef_b) + c4);
   const float4 mu = __ldg(reinterpret_cast<const float4 *>(save_mean) + c4);
   const float4 rs = __ldg(reinterpret_cast<const float4 *>(save_rstd) + c4);
+  float4 a, b;
+  coef_from_stats(gamma, beta, c4, mu, rs, a, b);
   const float4 k1 = __ldg(reinterpret_cast<const float4 *>(c1) + c4);
   const float4 k2 = __ldg(reinterpret_cast<const float4 *>(c2) + c4);
   const float4 *xp = reinterpret_cast<const float4 *>(x) + c4;
@@ -294,7 +294,7 @@ bool na_args_ok(const void *x, long long M, int C) {
 
 // scratch layout: [coef_a C][coef_b C][c1 C][c2 C][partials blocks*C*2]
 static size_t na_ws_bytes(long long M, int C) {
-  NaGeom g = na_geom(M, C);
+  NaGeom g = na_geom(M, C, NA_STATS_THREADS);
   return ((size_t)4 * C + (size_t)na_blocks(g, NA_STATS_PER_SM) * C * 2) * sizeof(float) + 64;
 }
 
@@ -325,8 +325,9 @@ int cpgb_bn_relu_fwd(const float *x, int64_t M, int32_t C, const float *gamma, c
   NaGeom g = na_geom(M, C);
   float *coef_a = reinterpret_cast<float *>(ws), *coef_b = coef_a + C, *part = coef_a + 4 * C;
   if (training) {
-    const int nb = na_blocks(g, NA_STATS_PER_SM);
-    bn_stats_kernel<<<dim3(nb, g.cchunks), NA_THREADS, 0, st>>>(g, x, part);
+    const NaGeom gs = na_geom(M, C, NA_STATS_THREADS);
+    const int nb = na_blocks(gs, NA_STATS_PER_SM);
+    bn_stats_kernel<<<dim3(nb, gs.cchunks), NA_STATS_THREADS, 0, st>>>(gs, x, part);
     CPGB_LAUNCH_OK("bn_stats");
     bn_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(part, nb, C, M, gamma, beta, running_mean, running_var, momentum,
                                                         eps, save_mean, save_rstd, coef_a, coef_b);
@@ -352,17 +353,14 @@ int cpgb_bn_relu_bwd(const float *x, const float *dy, int64_t M, int32_t C, cons
   }
   cudaStream_t st = (cudaStream_t)stream;
   NaGeom g = na_geom(M, C);
-  float *coef_a = reinterpret_cast<float *>(ws), *coef_b = coef_a + C, *c1 = coef_a + 2 * C, *c2 = coef_a + 3 * C,
-        *part = coef_a + 4 * C;
-  // a = gamma * rstd, b = beta - mean * a from the saved statistics (eps is already inside rstd)
-  bn_coef_from_stats_kernel<<<(C + 127) / 128, 128, 0, st>>>(C, gamma, beta, mean, rstd, coef_a, coef_b);
-  CPGB_LAUNCH_OK("bn_coef_from_stats");
-  const int nb = na_blocks(g, NA_STATS_PER_SM);
-  bn_bwd_stats_kernel<<<dim3(nb, g.cchunks), NA_THREADS, 0, st>>>(g, x, dy, coef_a, coef_b, mean, rstd, relu, part);
+  float *c1 = reinterpret_cast<float *>(ws) + 2 * C, *c2 = c1 + C, *part = c2 + C;
+  const NaGeom gs = na_geom(M, C, NA_STATS_THREADS);
+  const int nb = na_blocks(gs, NA_STATS_PER_SM);
+  bn_bwd_stats_kernel<<<dim3(nb, gs.cchunks), NA_STATS_THREADS, 0, st>>>(gs, x, dy, gamma, beta, mean, rstd, relu, part);
   CPGB_LAUNCH_OK("bn_bwd_stats");
   bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(part, nb, C, M, training, dgamma, dbeta, c1, c2);
   CPGB_LAUNCH_OK("bn_bwd_finalize");
-  bn_bwd_apply_kernel<<<dim3(na_blocks(g, 8), g.cchunks), NA_THREADS, 0, st>>>(g, x, dy, coef_a, coef_b, mean, rstd, c1, c2,
+  bn_bwd_apply_kernel<<<dim3(na_blocks(g, 8), g.cchunks), NA_THREADS, 0, st>>>(g, x, dy, gamma, beta, mean, rstd, c1, c2,
                                                                               relu, dx);
   CPGB_LAUNCH_OK("bn_bwd_apply");
   return CPGB_OK;
