@@ -286,6 +286,144 @@ bn_bwd_apply_kernel(const NaGeom g, const float *__restrict__ x, const float *__
   }
 }
 
+// ---- 2x2 / stride-2 max-pool folded in (models/vgg.py 'M' entries follow conv -> BN -> ReLU directly) ----
+// Rows are POOLED pixels; a thread reads the four window pixels of its channels.  pool(relu(z)) ==
+// relu(max z), and the gradient of a window goes to its first maximum in (h, w) scan order -- the element
+// torch's max_pool2d records (ties other than at z <= 0, where the ReLU zeroes the gradient anyway, are
+// measure-zero for float activations).
+struct PoolGeom { int H, W, Ho, Wo; long long Mo; };
+
+__device__ __forceinline__ long long pool_base(const PoolGeom &pg, long long r, long long cq) {
+  const int wo = (int)(r % pg.Wo);
+  const long long t = r / pg.Wo;
+  const int ho = (int)(t % pg.Ho);
+  const long long n = t / pg.Ho;
+  return ((n * pg.H + 2 * ho) * pg.W + 2 * wo) * cq;
+}
+
+__device__ __forceinline__ float max4_first(float z0, float z1, float z2, float z3, int &j) {
+  float m = z0; j = 0;
+  if (z1 > m) { m = z1; j = 1; }
+  if (z2 > m) { m = z2; j = 2; }
+  if (z3 > m) { m = z3; j = 3; }
+  return m;
+}
+
+__global__ void __launch_bounds__(NA_THREADS)
+bn_apply_pool_kernel(const NaGeom g, const PoolGeom pg, const float *__restrict__ x, const float *__restrict__ coef_a,
+                     const float *__restrict__ coef_b, int relu, float *__restrict__ y) {
+  const int lane = threadIdx.x % g.lanes, slot = threadIdx.x / g.lanes;
+  const int c4 = blockIdx.y * g.lanes + lane;
+  if (slot >= g.slots || c4 * 4 >= g.C) return;
+  const float4 a = __ldg(reinterpret_cast<const float4 *>(coef_a) + c4);
+  const float4 b = __ldg(reinterpret_cast<const float4 *>(coef_b) + c4);
+  const float4 *xp = reinterpret_cast<const float4 *>(x) + c4;
+  float4 *yp = reinterpret_cast<float4 *>(y) + c4;
+  const long long stride = (long long)gridDim.x * g.slots, cq = g.C / 4, down = (long long)pg.W * cq;
+#pragma unroll 2
+  for (long long r = (long long)blockIdx.x * g.slots + slot; r < pg.Mo; r += stride) {
+    const float4 *p = xp + pool_base(pg, r, cq);
+    const float4 v0 = __ldg(p), v1 = __ldg(p + cq), v2 = __ldg(p + down), v3 = __ldg(p + down + cq);
+    float4 o;
+    o.x = fmaxf(fmaxf(fmaf(v0.x, a.x, b.x), fmaf(v1.x, a.x, b.x)), fmaxf(fmaf(v2.x, a.x, b.x), fmaf(v3.x, a.x, b.x)));
+    o.y = fmaxf(fmaxf(fmaf(v0.y, a.y, b.y), fmaf(v1.y, a.y, b.y)), fmaxf(fmaf(v2.y, a.y, b.y), fmaf(v3.y, a.y, b.y)));
+    o.z = fmaxf(fmaxf(fmaf(v0.z, a.z, b.z), fmaf(v1.z, a.z, b.z)), fmaxf(fmaf(v2.z, a.z, b.z), fmaf(v3.z, a.z, b.z)));
+    o.w = fmaxf(fmaxf(fmaf(v0.w, a.w, b.w), fmaf(v1.w, a.w, b.w)), fmaxf(fmaf(v2.w, a.w, b.w), fmaf(v3.w, a.w, b.w)));
+    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+    yp[r * cq] = o;
+  }
+}
+
+// one channel of one window: gradient g of the winning pixel, its index j and its xhat
+#define NA_POOL_ELEM(G, J, XH, V0, V1, V2, V3, D, A, B, MU, RS)                                   \
+  {                                                                                                \
+    const float m_ = max4_first(fmaf(V0, A, B), fmaf(V1, A, B), fmaf(V2, A, B), fmaf(V3, A, B), J); \
+    G = (relu && !(m_ > 0.f)) ? 0.f : D;                                                           \
+    const float xv_ = J == 0 ? V0 : J == 1 ? V1 : J == 2 ? V2 : V3;                                \
+    XH = (xv_ - MU) * RS;                                                                          \
+  }
+
+__global__ void __launch_bounds__(NA_STATS_THREADS)
+bn_bwd_stats_pool_kernel(const NaGeom g, const PoolGeom pg, const float *__restrict__ x, const float *__restrict__ dy,
+                         const float *__restrict__ gamma, const float *__restrict__ beta,
+                         const float *__restrict__ save_mean, const float *__restrict__ save_rstd, int relu,
+                         float *__restrict__ part) {
+  const int lane = threadIdx.x % g.lanes, slot = threadIdx.x / g.lanes;
+  const int c4 = blockIdx.y * g.lanes + lane;
+  const bool active = slot < g.slots && c4 * 4 < g.C;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+  if (active) {
+    const float4 mu = __ldg(reinterpret_cast<const float4 *>(save_mean) + c4);
+    const float4 rs = __ldg(reinterpret_cast<const float4 *>(save_rstd) + c4);
+    float4 a, b;
+    coef_from_stats(gamma, beta, c4, mu, rs, a, b);
+    const float4 *xp = reinterpret_cast<const float4 *>(x) + c4;
+    const float4 *dp = reinterpret_cast<const float4 *>(dy) + c4;
+    const long long stride = (long long)gridDim.x * g.slots, cq = g.C / 4, down = (long long)pg.W * cq;
+#pragma unroll 2
+    for (long long r = (long long)blockIdx.x * g.slots + slot; r < pg.Mo; r += stride) {
+      const float4 *p = xp + pool_base(pg, r, cq);
+      const float4 v0 = __ldg(p), v1 = __ldg(p + cq), v2 = __ldg(p + down), v3 = __ldg(p + down + cq);
+      const float4 d = __ldg(dp + r * cq);
+      float gx, gy, gz, gw, hx, hy, hz, hw;
+      int jx, jy, jz, jw;
+      NA_POOL_ELEM(gx, jx, hx, v0.x, v1.x, v2.x, v3.x, d.x, a.x, b.x, mu.x, rs.x)
+      NA_POOL_ELEM(gy, jy, hy, v0.y, v1.y, v2.y, v3.y, d.y, a.y, b.y, mu.y, rs.y)
+      NA_POOL_ELEM(gz, jz, hz, v0.z, v1.z, v2.z, v3.z, d.z, a.z, b.z, mu.z, rs.z)
+      NA_POOL_ELEM(gw, jw, hw, v0.w, v1.w, v2.w, v3.w, d.w, a.w, b.w, mu.w, rs.w)
+      s.x += gx; s.y += gy; s.z += gz; s.w += gw;
+      q.x = fmaf(gx, hx, q.x); q.y = fmaf(gy, hy, q.y); q.z = fmaf(gz, hz, q.z); q.w = fmaf(gw, hw, q.w);
+    }
+  }
+  block_reduce_pairs(g, s, q, lane, slot, c4, active, part);
+}
+
+// dx of the four window pixels of one channel: a * ([j == J] * g - c1 - xhat_j * c2)
+#define NA_POOL_DX(O0, O1, O2, O3, V0, V1, V2, V3, D, A, B, MU, RS, K1, K2)                        \
+  {                                                                                                \
+    int j_;                                                                                        \
+    const float m_ = max4_first(fmaf(V0, A, B), fmaf(V1, A, B), fmaf(V2, A, B), fmaf(V3, A, B), j_); \
+    const float g_ = (relu && !(m_ > 0.f)) ? 0.f : D;                                              \
+    O0 = A * ((j_ == 0 ? g_ : 0.f) - K1 - (V0 - MU) * RS * K2);                                    \
+    O1 = A * ((j_ == 1 ? g_ : 0.f) - K1 - (V1 - MU) * RS * K2);                                    \
+    O2 = A * ((j_ == 2 ? g_ : 0.f) - K1 - (V2 - MU) * RS * K2);                                    \
+    O3 = A * ((j_ == 3 ? g_ : 0.f) - K1 - (V3 - MU) * RS * K2);                                    \
+  }
+
+__global__ void __launch_bounds__(NA_THREADS)
+bn_bwd_apply_pool_kernel(const NaGeom g, const PoolGeom pg, const float *__restrict__ x, const float *__restrict__ dy,
+                         const float *__restrict__ gamma, const float *__restrict__ beta,
+                         const float *__restrict__ save_mean, const float *__restrict__ save_rstd,
+                         const float *__restrict__ c1, const float *__restrict__ c2, int relu, float *__restrict__ dx) {
+  const int lane = threadIdx.x % g.lanes, slot = threadIdx.x / g.lanes;
+  const int c4 = blockIdx.y * g.lanes + lane;
+  if (slot >= g.slots || c4 * 4 >= g.C) return;
+  const float4 mu = __ldg(reinterpret_cast<const float4 *>(save_mean) + c4);
+  const float4 rs = __ldg(reinterpret_cast<const float4 *>(save_rstd) + c4);
+  float4 a, b;
+  coef_from_stats(gamma, beta, c4, mu, rs, a, b);
+  const float4 k1 = __ldg(reinterpret_cast<const float4 *>(c1) + c4);
+  const float4 k2 = __ldg(reinterpret_cast<const float4 *>(c2) + c4);
+  const float4 *xp = reinterpret_cast<const float4 *>(x) + c4;
+  const float4 *dp = reinterpret_cast<const float4 *>(dy) + c4;
+  float4 *op = reinterpret_cast<float4 *>(dx) + c4;
+  const long long stride = (long long)gridDim.x * g.slots, cq = g.C / 4, down = (long long)pg.W * cq;
+#pragma unroll 2
+  for (long long r = (long long)blockIdx.x * g.slots + slot; r < pg.Mo; r += stride) {
+    const long long base = pool_base(pg, r, cq);
+    const float4 *p = xp + base;
+    const float4 v0 = __ldg(p), v1 = __ldg(p + cq), v2 = __ldg(p + down), v3 = __ldg(p + down + cq);
+    const float4 d = __ldg(dp + r * cq);
+    float4 o0, o1, o2, o3;
+    NA_POOL_DX(o0.x, o1.x, o2.x, o3.x, v0.x, v1.x, v2.x, v3.x, d.x, a.x, b.x, mu.x, rs.x, k1.x, k2.x)
+    NA_POOL_DX(o0.y, o1.y, o2.y, o3.y, v0.y, v1.y, v2.y, v3.y, d.y, a.y, b.y, mu.y, rs.y, k1.y, k2.y)
+    NA_POOL_DX(o0.z, o1.z, o2.z, o3.z, v0.z, v1.z, v2.z, v3.z, d.z, a.z, b.z, mu.z, rs.z, k1.z, k2.z)
+    NA_POOL_DX(o0.w, o1.w, o2.w, o3.w, v0.w, v1.w, v2.w, v3.w, d.w, a.w, b.w, mu.w, rs.w, k1.w, k2.w)
+    float4 *o = op + base;
+    o[0] = o0; o[cq] = o1; o[down] = o2; o[down + cq] = o3;
+  }
+}
+
 bool na_args_ok(const void *x, long long M, int C) {
   return M > 0 && C > 0 && C % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
 }
@@ -309,9 +447,21 @@ size_t cpgb_bn_workspace_bytes(int64_t M, int32_t C) {
   return na_ws_bytes(M, C);
 }
 
+static bool pool_geom(int64_t M, int32_t pool_h, int32_t pool_w, PoolGeom *pg) {
+  if (pool_h <= 0 || pool_w <= 0 || (pool_h & 1) || (pool_w & 1) || M % ((int64_t)pool_h * pool_w)) return false;
+  pg->H = pool_h; pg->W = pool_w; pg->Ho = pool_h / 2; pg->Wo = pool_w / 2; pg->Mo = M / 4;
+  return true;
+}
+
 int cpgb_bn_relu_fwd(const float *x, int64_t M, int32_t C, const float *gamma, const float *beta, float *running_mean,
-                     float *running_var, int32_t training, float momentum, float eps, int32_t relu, float *y,
-                     float *save_mean, float *save_rstd, void *ws, size_t ws_bytes, void *stream) {
+                     float *running_var, int32_t training, float momentum, float eps, int32_t relu, int32_t pool_h,
+                     int32_t pool_w, float *y, float *save_mean, float *save_rstd, void *ws, size_t ws_bytes,
+                     void *stream) {
+  PoolGeom pg;
+  const bool pool = pool_h != 0 || pool_w != 0;
+  if (pool && !pool_geom(M, pool_h, pool_w, &pg)) {
+    set_error("cpgb_bn_relu_fwd: 2x2 pooling needs even H, W with M = N*H*W"); return CPGB_EINVAL;
+  }
   if (!na_args_ok(x, M, C) || !y || (reinterpret_cast<uintptr_t>(y) & 15)) {
     set_error("cpgb_bn_relu_fwd: needs NHWC fp32 with C %% 4 == 0 and 16-byte aligned x / y"); return CPGB_EINVAL;
   }
@@ -336,14 +486,25 @@ int cpgb_bn_relu_fwd(const float *x, int64_t M, int32_t C, const float *gamma, c
     bn_eval_coef_kernel<<<(C + 127) / 128, 128, 0, st>>>(C, gamma, beta, running_mean, running_var, eps, coef_a, coef_b);
     CPGB_LAUNCH_OK("bn_eval_coef");
   }
-  bn_apply_kernel<<<dim3(na_blocks(g, 8), g.cchunks), NA_THREADS, 0, st>>>(g, x, coef_a, coef_b, relu, y);
+  if (pool) {
+    NaGeom gp = g;
+    gp.M = pg.Mo;
+    bn_apply_pool_kernel<<<dim3(na_blocks(gp, 8), g.cchunks), NA_THREADS, 0, st>>>(g, pg, x, coef_a, coef_b, relu, y);
+  } else {
+    bn_apply_kernel<<<dim3(na_blocks(g, 8), g.cchunks), NA_THREADS, 0, st>>>(g, x, coef_a, coef_b, relu, y);
+  }
   CPGB_LAUNCH_OK("bn_apply");
   return CPGB_OK;
 }
 
 int cpgb_bn_relu_bwd(const float *x, const float *dy, int64_t M, int32_t C, const float *gamma, const float *beta,
-                     const float *mean, const float *rstd, int32_t training, int32_t relu, float *dx, float *dgamma,
-                     float *dbeta, void *ws, size_t ws_bytes, void *stream) {
+                     const float *mean, const float *rstd, int32_t training, int32_t relu, int32_t pool_h,
+                     int32_t pool_w, float *dx, float *dgamma, float *dbeta, void *ws, size_t ws_bytes, void *stream) {
+  PoolGeom pg;
+  const bool pool = pool_h != 0 || pool_w != 0;
+  if (pool && !pool_geom(M, pool_h, pool_w, &pg)) {
+    set_error("cpgb_bn_relu_bwd: 2x2 pooling needs even H, W with M = N*H*W"); return CPGB_EINVAL;
+  }
   if (!na_args_ok(x, M, C) || !dy || !dx || !mean || !rstd || (reinterpret_cast<uintptr_t>(dy) & 15) ||
       (reinterpret_cast<uintptr_t>(dx) & 15)) {
     set_error("cpgb_bn_relu_bwd: needs NHWC fp32 with C %% 4 == 0 and 16-byte aligned tensors"); return CPGB_EINVAL;
@@ -355,13 +516,29 @@ int cpgb_bn_relu_bwd(const float *x, const float *dy, int64_t M, int32_t C, cons
   NaGeom g = na_geom(M, C);
   float *c1 = reinterpret_cast<float *>(ws) + 2 * C, *c2 = c1 + C, *part = c2 + C;
   const NaGeom gs = na_geom(M, C, NA_STATS_THREADS);
-  const int nb = na_blocks(gs, NA_STATS_PER_SM);
-  bn_bwd_stats_kernel<<<dim3(nb, gs.cchunks), NA_STATS_THREADS, 0, st>>>(gs, x, dy, gamma, beta, mean, rstd, relu, part);
+  int nb;
+  if (pool) {
+    NaGeom gp = gs;
+    gp.M = pg.Mo;
+    nb = na_blocks(gp, NA_STATS_PER_SM);
+    bn_bwd_stats_pool_kernel<<<dim3(nb, gs.cchunks), NA_STATS_THREADS, 0, st>>>(gs, pg, x, dy, gamma, beta, mean, rstd, relu,
+                                                                               part);
+  } else {
+    nb = na_blocks(gs, NA_STATS_PER_SM);
+    bn_bwd_stats_kernel<<<dim3(nb, gs.cchunks), NA_STATS_THREADS, 0, st>>>(gs, x, dy, gamma, beta, mean, rstd, relu, part);
+  }
   CPGB_LAUNCH_OK("bn_bwd_stats");
   bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(part, nb, C, M, training, dgamma, dbeta, c1, c2);
   CPGB_LAUNCH_OK("bn_bwd_finalize");
-  bn_bwd_apply_kernel<<<dim3(na_blocks(g, 8), g.cchunks), NA_THREADS, 0, st>>>(g, x, dy, gamma, beta, mean, rstd, c1, c2,
-                                                                              relu, dx);
+  if (pool) {
+    NaGeom gp = g;
+    gp.M = pg.Mo;
+    bn_bwd_apply_pool_kernel<<<dim3(na_blocks(gp, 8), g.cchunks), NA_THREADS, 0, st>>>(g, pg, x, dy, gamma, beta, mean, rstd,
+                                                                                      c1, c2, relu, dx);
+  } else {
+    bn_bwd_apply_kernel<<<dim3(na_blocks(g, 8), g.cchunks), NA_THREADS, 0, st>>>(g, x, dy, gamma, beta, mean, rstd, c1, c2,
+                                                                                relu, dx);
+  }
   CPGB_LAUNCH_OK("bn_bwd_apply");
   return CPGB_OK;
 }

@@ -29,13 +29,16 @@ CL = torch.channels_last
 
 class _BNReLUFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, running_mean, running_var, training, momentum, eps, relu):
+    def forward(ctx, x, weight, bias, running_mean, running_var, training, momentum, eps, relu, pool):
         lib = _lib.load()
         if not x.is_contiguous(memory_format=CL):
             x = x.contiguous(memory_format=CL)
         N, C, H, W = x.shape
         M = N * H * W
-        y = torch.empty_like(x)                      # keeps the NHWC strides
+        if pool:
+            y = torch.empty((N, C, H // 2, W // 2), dtype=x.dtype, device=x.device, memory_format=CL)
+        else:
+            y = torch.empty_like(x)                  # keeps the NHWC strides
         w = weight.detach().contiguous() if weight is not None else None
         b = bias.detach().contiguous() if bias is not None else None
         with torch.cuda.device(x.device):
@@ -47,11 +50,12 @@ class _BNReLUFn(torch.autograd.Function):
                 mean, rstd = running_mean, torch.rsqrt(running_var + eps)
             _lib.check(lib.cpgb_bn_relu_fwd(
                 _lib.ptr(x), M, C, _lib.ptr(w), _lib.ptr(b), _lib.ptr(running_mean), _lib.ptr(running_var),
-                1 if training else 0, float(momentum), float(eps), 1 if relu else 0, _lib.ptr(y),
+                1 if training else 0, float(momentum), float(eps), 1 if relu else 0,
+                H if pool else 0, W if pool else 0, _lib.ptr(y),
                 _lib.ptr(mean) if training else None, _lib.ptr(rstd) if training else None,
                 _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), 'cpgb_bn_relu_fwd')
         ctx.save_for_backward(x, w, b, mean, rstd)
-        ctx.cfg = (bool(training), bool(relu), weight is not None, bias is not None)
+        ctx.cfg = (bool(training), bool(relu), weight is not None, bias is not None, bool(pool))
         return y
 
     @staticmethod
@@ -59,7 +63,7 @@ class _BNReLUFn(torch.autograd.Function):
     def backward(ctx, dy):
         lib = _lib.load()
         x, w, b, mean, rstd = ctx.saved_tensors
-        training, relu, has_w, has_b = ctx.cfg
+        training, relu, has_w, has_b, pool = ctx.cfg
         if not dy.is_contiguous(memory_format=CL):
             dy = dy.contiguous(memory_format=CL)
         N, C, H, W = x.shape
@@ -71,23 +75,25 @@ class _BNReLUFn(torch.autograd.Function):
             ws = torch.empty(lib.cpgb_bn_workspace_bytes(M, C), dtype=torch.uint8, device=x.device)
             _lib.check(lib.cpgb_bn_relu_bwd(
                 _lib.ptr(x), _lib.ptr(dy), M, C, _lib.ptr(w), _lib.ptr(b), _lib.ptr(mean), _lib.ptr(rstd),
-                1 if training else 0, 1 if relu else 0, _lib.ptr(dx), _lib.ptr(dg), _lib.ptr(db),
+                1 if training else 0, 1 if relu else 0, H if pool else 0, W if pool else 0,
+                _lib.ptr(dx), _lib.ptr(dg), _lib.ptr(db),
                 _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), 'cpgb_bn_relu_bwd')
-        return dx, dg, db, None, None, None, None, None, None
+        return dx, dg, db, None, None, None, None, None, None, None
 
 
 class FusedBatchNormReLU2d(nn.BatchNorm2d):
     """``nn.BatchNorm2d`` with an optional fused ReLU (``relu=True``: y = relu(batch_norm(x)))."""
 
     def __init__(self, num_features, eps=1e-5, momentum=0.1, affine=True, track_running_stats=True, relu=False,
-                 device=None, dtype=None):
+                 pool=False, device=None, dtype=None):
         super().__init__(num_features, eps, momentum, affine, track_running_stats, device=device, dtype=dtype)
         self.relu = bool(relu)
+        self.pool = bool(pool)        # also apply the nn.MaxPool2d(kernel_size=2, stride=2) that follows
 
     @classmethod
-    def from_bn(cls, bn, relu):
+    def from_bn(cls, bn, relu, pool=False):
         """A fused module over the SAME parameter / buffer tensors as `bn` (state_dict keys unchanged)."""
-        new = cls(bn.num_features, bn.eps, bn.momentum, bn.affine, bn.track_running_stats, relu=relu,
+        new = cls(bn.num_features, bn.eps, bn.momentum, bn.affine, bn.track_running_stats, relu=relu, pool=pool,
                   device=torch.device('meta'))
         for name in ('weight', 'bias'):
             new._parameters[name] = bn._parameters.get(name)
@@ -97,7 +103,7 @@ class FusedBatchNormReLU2d(nn.BatchNorm2d):
         return new
 
     def extra_repr(self):
-        return super().extra_repr() + f', relu={self.relu}'
+        return super().extra_repr() + f', relu={self.relu}, pool={self.pool}'
 
     def _fast(self, x):
         if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] % 4 == 0 and x.numel() > 0):
@@ -112,7 +118,8 @@ class FusedBatchNormReLU2d(nn.BatchNorm2d):
     def forward(self, x):
         if not self._fast(x):
             y = super().forward(x)
-            return F.relu(y) if self.relu else y
+            y = F.relu(y) if self.relu else y
+            return F.max_pool2d(y, 2, 2) if self.pool else y
         self._check_input_dim(x)
         training = self.training or (self.running_mean is None and self.running_var is None)
         if training and x.numel() // x.shape[1] <= 1:
@@ -122,14 +129,17 @@ class FusedBatchNormReLU2d(nn.BatchNorm2d):
             self.num_batches_tracked.add_(1)
         rm = self.running_mean if (not training or update) else None
         rv = self.running_var if (not training or update) else None
-        return _BNReLUFn.apply(x, self.weight, self.bias, rm, rv, training,
-                               self.momentum if self.momentum is not None else 0.0, self.eps, self.relu)
+        pool = self.pool and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0
+        y = _BNReLUFn.apply(x, self.weight, self.bias, rm, rv, training,
+                            self.momentum if self.momentum is not None else 0.0, self.eps, self.relu, pool)
+        return F.max_pool2d(y, 2, 2) if (self.pool and not pool) else y
 
 
-def fuse_bn_relu(model):
+def fuse_bn_relu(model, pool=True):
     """Swap every ``nn.BatchNorm2d`` of `model` for a ``FusedBatchNormReLU2d`` sharing its tensors; inside
     ``nn.Sequential`` containers a directly following ``nn.ReLU`` is folded in and replaced by
-    ``nn.Identity`` (child indices, parameter names and mask keys are unchanged).  Returns the number of
+    ``nn.Identity`` (child indices, parameter names and mask keys are unchanged); with `pool`, a
+    ``nn.MaxPool2d(kernel_size=2, stride=2)`` right after that ReLU is folded in as well.  Returns the number of
     (batch-norm, relu) pairs and of lone batch-norms converted."""
     pairs = lone = 0
     for parent in list(model.modules()):
@@ -140,10 +150,21 @@ def fuse_bn_relu(model):
                 continue
             nxt = parent._modules[names[i + 1]] if (isinstance(parent, nn.Sequential) and i + 1 < len(names)) else None
             relu = type(nxt) is nn.ReLU
-            parent._modules[name] = FusedBatchNormReLU2d.from_bn(m, relu=relu)
+            nxt2 = parent._modules[names[i + 2]] if (relu and pool and i + 2 < len(names)) else None
+            do_pool = _is_pool2x2(nxt2)
+            parent._modules[name] = FusedBatchNormReLU2d.from_bn(m, relu=relu, pool=do_pool)
             if relu:
                 parent._modules[names[i + 1]] = nn.Identity()
                 pairs += 1
             else:
                 lone += 1
+            if do_pool:
+                parent._modules[names[i + 2]] = nn.Identity()
     return pairs, lone
+
+
+def _is_pool2x2(m):
+    def two(v):
+        return v == 2 or v == (2, 2)
+    return (type(m) is nn.MaxPool2d and two(m.kernel_size) and two(m.stride) and m.padding in (0, (0, 0)) and
+            m.dilation in (1, (1, 1)) and not m.ceil_mode and not m.return_indices)

@@ -187,19 +187,24 @@ int cpgb_split_merged_grad(const float *merged, const uint8_t *tmask, int64_t n,
  *                  the batch mean and 1/sqrt(var + eps) for the backward pass;
  *   training == 0: running statistics normalise, save_* are not written.
  * gamma / beta may be NULL (affine=False).  relu != 0 applies max(0, .) in the same pass.
+ * pool_h = H, pool_w = W (both even, M = N*H*W) additionally folds the nn.MaxPool2d(kernel_size=2, stride=2) that
+ * follows conv -> BN -> ReLU at the 'M' entries of models/vgg.py:95-122 into the same pass: y (and dy of the
+ * backward call) are then [N*(H/2)*(W/2)][C]; the window gradient goes to the first maximum in (h, w) order as
+ * in torch.  pool_h = pool_w = 0: no pooling.
  * ws: cpgb_bn_workspace_bytes(M, C) bytes of scratch (per-block partial sums, deterministic). */
 size_t cpgb_bn_workspace_bytes(int64_t M, int32_t C);
 int cpgb_bn_relu_fwd(const float *x, int64_t M, int32_t C, const float *gamma, const float *beta, float *running_mean,
-                     float *running_var, int32_t training, float momentum, float eps, int32_t relu, float *y,
-                     float *save_mean, float *save_rstd, void *ws, size_t ws_bytes, void *stream);
+                     float *running_var, int32_t training, float momentum, float eps, int32_t relu, int32_t pool_h,
+                     int32_t pool_w, float *y, float *save_mean, float *save_rstd, void *ws, size_t ws_bytes,
+                     void *stream);
 /* Backward of the above: with g = dy * [y > 0] (relu) or dy,  xhat = (x - mean) * rstd:
  *   dbeta = sum g;  dgamma = sum g * xhat;
  *   training: dx = gamma * rstd * (g - mean(g) - xhat * mean(g * xhat));   evaluation: dx = gamma * rstd * g.
  * mean / rstd: save_mean / save_rstd of the forward call (training) or running_mean / 1/sqrt(running_var + eps).
  * dgamma / dbeta may be NULL. */
 int cpgb_bn_relu_bwd(const float *x, const float *dy, int64_t M, int32_t C, const float *gamma, const float *beta,
-                     const float *mean, const float *rstd, int32_t training, int32_t relu, float *dx, float *dgamma,
-                     float *dbeta, void *ws, size_t ws_bytes, void *stream);
+                     const float *mean, const float *rstd, int32_t training, int32_t relu, int32_t pool_h,
+                     int32_t pool_w, float *dx, float *dgamma, float *dbeta, void *ws, size_t ws_bytes, void *stream);
 
 #ifdef __cplusplus
 }

@@ -807,3 +807,31 @@ def test_fused_bn_model_step_matches_stock_modules():
         assert ((a - b).norm() / b.norm().clamp_min(1e-30)).item() <= 2e-3, n     # through 13 BN layers
     for n in b0:
         assert rel(b1[n].float(), b0[n].float()) <= 1e-5, n
+
+
+@pytest.mark.parametrize('shape', [(128, 64, 32, 32), (128, 512, 2, 2), (4, 156, 6, 10), (2, 2048, 4, 4)])
+@pytest.mark.parametrize('train', [True, False])
+def test_fused_bn_relu_maxpool_vs_torch(shape, train):
+    """conv -> BN -> ReLU -> MaxPool2d(2, 2) (the 'M' entries of models/vgg.py:95-122) with the pool folded
+    into the batch-norm kernels, against the three stock modules."""
+    from cpg_b200.fused_norm import FusedBatchNormReLU2d
+    N, C, H, W = shape
+    torch.manual_seed(C + H)
+    ref = nn.BatchNorm2d(C).to(DEV)
+    with torch.no_grad():
+        ref.weight.uniform_(0.5, 1.5); ref.bias.normal_(0, 0.3)
+        ref.running_mean.normal_(0, 0.2); ref.running_var.uniform_(0.5, 2.0)
+    fused = FusedBatchNormReLU2d.from_bn(nn.BatchNorm2d(C).to(DEV), relu=True, pool=True)
+    fused.load_state_dict(ref.state_dict())
+    ref.train(train); fused.train(train)
+    x = (torch.randn(N, C, H, W, device=DEV) * 1.5 + 0.3).contiguous(memory_format=torch.channels_last)
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    ya = torch.nn.functional.max_pool2d(torch.relu(ref(xa)), 2, 2)
+    yb = fused(xb)
+    assert yb.shape == ya.shape and yb.is_contiguous(memory_format=torch.channels_last)
+    dy = torch.randn_like(ya).contiguous(memory_format=torch.channels_last)
+    ya.backward(dy); yb.backward(dy)
+    assert rel(yb, ya) <= TOL_FP32
+    assert rel(xb.grad, xa.grad) <= 1e-4
+    assert rel(fused.weight.grad, ref.weight.grad) <= 1e-4 and rel(fused.bias.grad, ref.bias.grad) <= 1e-4
+    assert rel(fused.running_mean, ref.running_mean) <= TOL_FP32 and rel(fused.running_var, ref.running_var) <= TOL_FP32
