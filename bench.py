@@ -635,6 +635,8 @@ def main():
                        'step': 'utils/manager.py:54-75 sequence, SGD-nesterov (+Adam on piggymasks in task2); '
                                'torch.optim fused=True (same update rule as CPG_cifar100_main_normal.py:339-346)',
                        'cuda_graph': not args.no_graph,
+                       'bn_relu_pool': ('cpg_b200.fused_norm (BatchNorm2d+ReLU(+MaxPool2d) kernels, SURVEY 8f N4)'
+                                        if FUSE_BN_RELU else 'stock torch modules'),
                        'l2': 'per-step working set (weights+grads+momentum 400 MB, activations 280 MB) exceeds the 126 MB L2; 8 distinct input batches rotate'},
             'clocks': {k: r1['clocks'].get(k) for k in ('sm_mhz', 'sm_max_mhz', 'reasons')} if r1['clocks'] else None,
             'e2e': {'value': imgs / (r1['e2e_ms'] * 1e-3), 'unit': 'images/s', 'h2d_bytes_per_step': r1['h2d'],

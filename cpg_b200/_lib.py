@@ -81,7 +81,7 @@ def load():
         'cpgb_merge_grads': (ctypes.c_int, [vp, vp, vp, i64, vp]),
         'cpgb_split_merged_grad': (ctypes.c_int, [vp, vp, i64, i32, vp, vp, vp]),
         'cpgb_bn_workspace_bytes': (sz, [i64, i32]),
-        'cpgb_bn_relu_fwd': (ctypes.c_int, [vp, i64, i32, vp, vp, vp, vp, i32, f32, f32, i32, i32, i32, vp, vp, vp, vp,
+        'cpgb_bn_relu_fwd': (ctypes.c_int, [vp, i64, i32, vp, vp, vp, vp, vp, i32, f32, f32, i32, i32, i32, vp, vp, vp, vp,
                                             sz, vp]),
         'cpgb_bn_relu_bwd': (ctypes.c_int, [vp, vp, i64, i32, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, sz,
                                             vp]),

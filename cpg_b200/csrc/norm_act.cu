@@ -133,7 +133,8 @@ __global__ void __launch_bounds__(256)
 bn_finalize_kernel(const float *__restrict__ part, int nblocks, int C, long long M, const float *__restrict__ gamma,
                    const float *__restrict__ beta, float *__restrict__ running_mean, float *__restrict__ running_var,
                    float momentum, float eps, float *__restrict__ save_mean, float *__restrict__ save_rstd,
-                   float *__restrict__ coef_a, float *__restrict__ coef_b) {
+                   float *__restrict__ coef_a, float *__restrict__ coef_b, long long *__restrict__ num_batches_tracked) {
+  if (num_batches_tracked && blockIdx.x == 0 && threadIdx.x == 0) *num_batches_tracked += 1;   // nn.BatchNorm2d.forward
   const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= C) return;
   double s, q;
@@ -454,9 +455,9 @@ static bool pool_geom(int64_t M, int32_t pool_h, int32_t pool_w, PoolGeom *pg) {
 }
 
 int cpgb_bn_relu_fwd(const float *x, int64_t M, int32_t C, const float *gamma, const float *beta, float *running_mean,
-                     float *running_var, int32_t training, float momentum, float eps, int32_t relu, int32_t pool_h,
-                     int32_t pool_w, float *y, float *save_mean, float *save_rstd, void *ws, size_t ws_bytes,
-                     void *stream) {
+                     float *running_var, int64_t *num_batches_tracked, int32_t training, float momentum, float eps,
+                     int32_t relu, int32_t pool_h, int32_t pool_w, float *y, float *save_mean, float *save_rstd, void *ws,
+                     size_t ws_bytes, void *stream) {
   PoolGeom pg;
   const bool pool = pool_h != 0 || pool_w != 0;
   if (pool && !pool_geom(M, pool_h, pool_w, &pg)) {
@@ -480,7 +481,8 @@ int cpgb_bn_relu_fwd(const float *x, int64_t M, int32_t C, const float *gamma, c
     bn_stats_kernel<<<dim3(nb, gs.cchunks), NA_STATS_THREADS, 0, st>>>(gs, x, part);
     CPGB_LAUNCH_OK("bn_stats");
     bn_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(part, nb, C, M, gamma, beta, running_mean, running_var, momentum,
-                                                        eps, save_mean, save_rstd, coef_a, coef_b);
+                                                        eps, save_mean, save_rstd, coef_a, coef_b,
+                                                        reinterpret_cast<long long *>(num_batches_tracked));
     CPGB_LAUNCH_OK("bn_finalize");
   } else {
     bn_eval_coef_kernel<<<(C + 127) / 128, 128, 0, st>>>(C, gamma, beta, running_mean, running_var, eps, coef_a, coef_b);

@@ -29,7 +29,7 @@ CL = torch.channels_last
 
 class _BNReLUFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, running_mean, running_var, training, momentum, eps, relu, pool):
+    def forward(ctx, x, weight, bias, running_mean, running_var, nbt, training, momentum, eps, relu, pool):
         lib = _lib.load()
         if not x.is_contiguous(memory_format=CL):
             x = x.contiguous(memory_format=CL)
@@ -50,7 +50,7 @@ class _BNReLUFn(torch.autograd.Function):
                 mean, rstd = running_mean, torch.rsqrt(running_var + eps)
             _lib.check(lib.cpgb_bn_relu_fwd(
                 _lib.ptr(x), M, C, _lib.ptr(w), _lib.ptr(b), _lib.ptr(running_mean), _lib.ptr(running_var),
-                1 if training else 0, float(momentum), float(eps), 1 if relu else 0,
+                _lib.ptr(nbt) if training else None, 1 if training else 0, float(momentum), float(eps), 1 if relu else 0,
                 H if pool else 0, W if pool else 0, _lib.ptr(y),
                 _lib.ptr(mean) if training else None, _lib.ptr(rstd) if training else None,
                 _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), 'cpgb_bn_relu_fwd')
@@ -78,7 +78,7 @@ class _BNReLUFn(torch.autograd.Function):
                 1 if training else 0, 1 if relu else 0, H if pool else 0, W if pool else 0,
                 _lib.ptr(dx), _lib.ptr(dg), _lib.ptr(db),
                 _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), 'cpgb_bn_relu_bwd')
-        return dx, dg, db, None, None, None, None, None, None, None
+        return dx, dg, db, None, None, None, None, None, None, None, None
 
 
 class FusedBatchNormReLU2d(nn.BatchNorm2d):
@@ -125,12 +125,15 @@ class FusedBatchNormReLU2d(nn.BatchNorm2d):
         if training and x.numel() // x.shape[1] <= 1:
             raise ValueError(f'Expected more than 1 value per channel when training, got input size {x.size()}')
         update = self.training and self.track_running_stats
-        if update and self.num_batches_tracked is not None:
+        # the step counter is bumped by the finalize kernel (one launch less per layer)
+        nbt = self.num_batches_tracked if (update and self.num_batches_tracked is not None and
+                                           self.num_batches_tracked.device == x.device) else None
+        if update and self.num_batches_tracked is not None and nbt is None:
             self.num_batches_tracked.add_(1)
         rm = self.running_mean if (not training or update) else None
         rv = self.running_var if (not training or update) else None
         pool = self.pool and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0
-        y = _BNReLUFn.apply(x, self.weight, self.bias, rm, rv, training,
+        y = _BNReLUFn.apply(x, self.weight, self.bias, rm, rv, nbt, training,
                             self.momentum if self.momentum is not None else 0.0, self.eps, self.relu, pool)
         return F.max_pool2d(y, 2, 2) if (self.pool and not pool) else y
 

@@ -183,7 +183,8 @@ int cpgb_split_merged_grad(const float *merged, const uint8_t *tmask, int64_t n,
  * nn.ReLU(inplace=True) (models/vgg.py:109-118, models/resnet.py:60-100), on NHWC fp32 activations seen as
  * [M = N*H*W][C], C % 4 == 0.  Semantics of torch.nn.functional.batch_norm (+ relu):
  *   training != 0: batch statistics (biased variance) normalise; running_mean / running_var (may be NULL) are
- *                  updated in place with `momentum` and the unbiased variance; save_mean / save_rstd [C] receive
+ *                  updated in place with `momentum` and the unbiased variance, *num_batches_tracked (int64, may
+ *                  be NULL) is incremented as nn.BatchNorm2d.forward does; save_mean / save_rstd [C] receive
  *                  the batch mean and 1/sqrt(var + eps) for the backward pass;
  *   training == 0: running statistics normalise, save_* are not written.
  * gamma / beta may be NULL (affine=False).  relu != 0 applies max(0, .) in the same pass.
@@ -194,9 +195,9 @@ int cpgb_split_merged_grad(const float *merged, const uint8_t *tmask, int64_t n,
  * ws: cpgb_bn_workspace_bytes(M, C) bytes of scratch (per-block partial sums, deterministic). */
 size_t cpgb_bn_workspace_bytes(int64_t M, int32_t C);
 int cpgb_bn_relu_fwd(const float *x, int64_t M, int32_t C, const float *gamma, const float *beta, float *running_mean,
-                     float *running_var, int32_t training, float momentum, float eps, int32_t relu, int32_t pool_h,
-                     int32_t pool_w, float *y, float *save_mean, float *save_rstd, void *ws, size_t ws_bytes,
-                     void *stream);
+                     float *running_var, int64_t *num_batches_tracked, int32_t training, float momentum, float eps,
+                     int32_t relu, int32_t pool_h, int32_t pool_w, float *y, float *save_mean, float *save_rstd, void *ws,
+                     size_t ws_bytes, void *stream);
 /* Backward of the above: with g = dy * [y > 0] (relu) or dy,  xhat = (x - mean) * rstd:
  *   dbeta = sum g;  dgamma = sum g * xhat;
  *   training: dx = gamma * rstd * (g - mean(g) - xhat * mean(g * xhat));   evaluation: dx = gamma * rstd * g.

@@ -24,6 +24,8 @@ for k in kern.values():
     name = k['name']
     if 'stage_weights' in name:
         pas = 'stage'
+    elif 'stem_fprop' in name:
+        pas = last = 'fprop'
     elif 'conv_gemm_kernel' in name:
         pas = 'dgrad' if (', 1>' in name or 'true' in name) else 'fprop'
         last = pas
