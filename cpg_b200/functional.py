@@ -52,7 +52,7 @@ def _stage(lib, d, w, p, threshold, prestaged=None):
 _SIDE_STREAMS = {}
 OVERLAP_BACKWARD = True   # run wgrad on a side stream (it only reads x and dy; nothing on the main chain needs it)
 DEFER_JOIN = True         # join the side stream once, at the end of the backward pass, instead of per layer
-_PENDING = {}             # device index -> tensors the side stream may still be reading (kept alive until the join)
+_PENDING = {}             # device index -> (graph task id, tensors the side stream may still be reading)
 
 
 def _dev_index(device):
@@ -90,11 +90,18 @@ def join_side_stream(device=None):
 
 def _defer(device, tensors):
     key = _dev_index(device)
-    if key not in _PENDING:
-        _PENDING[key] = []
+    task = torch._C._current_graph_task_id()
+    entry = _PENDING.get(key)
+    if entry is not None and entry[0] != task:
+        # left over from a backward pass that never reached its callback (an exception in a later node):
+        # join now, then start afresh for the running pass
+        join_side_stream(key)
+        entry = None
+    if entry is None:
+        entry = _PENDING[key] = (task, [])
         # end-of-backward callback of the autograd engine (the mechanism DDP uses to finalise buckets)
         torch.autograd.Variable._execution_engine.queue_callback(lambda: join_side_stream(key))
-    _PENDING[key].extend(t for t in tensors if t is not None)
+    entry[1].extend(t for t in tensors if t is not None)
 
 
 def _backward_kernels(lib, ctx, d, x, dy, w, p, threshold, staged, need_dx, need_w, has_bias, dx):
