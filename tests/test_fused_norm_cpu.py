@@ -41,3 +41,27 @@ def test_fused_module_state_dict_roundtrip():
     plain.load_state_dict(m.state_dict())
     m.load_state_dict(plain.state_dict())
     assert 'relu=True' in repr(m)
+
+
+def test_fuse_handles_attribute_style_blocks():
+    """ResNet-style blocks keep their ReLU as a shared attribute and call it from forward(): only the
+    batch-norm is swapped there (relu=False), nothing else moves."""
+    class Block(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv1 = nn.Conv2d(4, 4, 1, bias=False)
+            self.bn1 = nn.BatchNorm2d(4)
+            self.relu = nn.ReLU(inplace=True)
+
+        def forward(self, x):
+            return self.relu(self.bn1(self.conv1(x)) + x)
+
+    torch.manual_seed(1)
+    a, b = Block(), Block()
+    b.load_state_dict(a.state_dict())
+    assert fuse_bn_relu(b) == (0, 1)
+    assert isinstance(b.bn1, FusedBatchNormReLU2d) and not b.bn1.relu and not b.bn1.pool
+    assert isinstance(b.relu, nn.ReLU)
+    x = torch.randn(2, 4, 5, 5)
+    assert torch.equal(a(x), b(x))
+    assert list(a.state_dict().keys()) == list(b.state_dict().keys())
