@@ -1,19 +1,25 @@
 // BatchNorm2d (+ ReLU) over NHWC fp32 activations: the consumer of every masked convolution in
 // models/vgg.py:109-118 and models/resnet.py:60-100 (conv -> nn.BatchNorm2d -> nn.ReLU(inplace=True)).
-// the step right after the hot path.  All four kernels are HBM-bound streaming
-// passes over an [M = N*H*W pixels][C channels] array (C % 4 == 0), 16 bytes per access:
+// the step right after the hot path.  Every kernel is an HBM-bound streaming pass
+// over an [M = N*H*W pixels][C channels] array (C % 4 == 0), 16 bytes per access:
 //
-//   training forward : stats   -- per-channel sum / sum of squares, one partial pair per block
-//                      finalize -- mean, biased variance, rstd, running statistics, a = gamma*rstd,
-//                                  b = beta - mean*a                        (C threads)
-//                      apply   -- y = max(0, a*x + b)
-//   backward         : stats   -- g = dy * [a*x + b > 0];  sum g, sum g*xhat
+//   training forward : stats    -- per-channel sum / sum of squares; ONE 1024-thread block per SM, so a
+//                                  channel has <= 148 partial pairs
+//                      finalize -- mean, biased variance, rstd, running statistics, num_batches_tracked,
+//                                  a = gamma*rstd, b = beta - mean*a           (one warp per channel, double)
+//                      apply    -- y = max(0, a*x + b), optionally the maximum over each 2x2 window
+//                                  (nn.MaxPool2d(2, 2) folded in: y is written at pooled resolution)
+//   backward         : stats    -- g = dy * [a*x + b > 0] (at the window's first maximum when pooled);
+//                                  sum g, sum g*xhat; a and b are recomputed from gamma, beta, mean, rstd
 //                      finalize -- dbeta, dgamma, c1 = sum g / M, c2 = sum g*xhat / M
-//                      apply   -- dx = a * (g - c1 - xhat * c2)
+//                      apply    -- dx = a * (g - c1 - xhat * c2)
+//   evaluation mode  : coefficients from the running statistics, then the same apply / backward kernels
+//                      with c1 = c2 = 0.
 //
 // A thread owns one float4 of channels for the whole kernel (its coefficients live in registers) and
-// walks pixel rows, so there is no per-element index arithmetic.  Partial sums are combined in a fixed
-// order in double precision: results are deterministic and do not depend on the grid size chosen.
+// walks pixel rows, so there is no per-element index arithmetic.  The ReLU mask and the pooling argmax are
+// recomputed from x in the backward kernels, nothing but mean / rstd is saved.  Partial sums are combined
+// in a fixed order in double precision: results are deterministic.
 #include "common.cuh"
 
 namespace cpgb {

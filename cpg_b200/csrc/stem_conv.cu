@@ -12,9 +12,13 @@
 //   fprop : y[n,p,q,k]  = bias[k] + sum_{c,r,s} x[n,c,p*sh-ph+r*dh,q*sw-pw+s*dw] * b(P[k,c,r,s]) * W[k,c,r,s]
 //   wgrad : g[k,c,r,s]  = sum_{n,p,q} dy[n,p,q,k] * x[n,c,...]      then the fused epilogue (a4 + a6)
 //
-// Thread mapping: K/4 lanes share one output pixel (lane j owns channels 4j..4j+3, so a pixel row
-// of Y is one contiguous 16*K-byte store); a warp covers 128/K pixels.  Exact fp32 FFMA -- no TF32.
-// wgrad is deterministic: per-block partial sums in a fixed order, then a fixed-shape tree.
+// Thread mapping: K/KPT lanes share one output pixel (KPT = 2 output channels per thread for K <= 64, 4 for
+// K = 128; lane j owns channels KPT*j ..), so a pixel row of Y is one contiguous 4*K-byte store.  The common
+// case (x as NHWC with a pixel stride of 4 floats, unit stride / dilation along w, K <= 64) runs the
+// pixel-PAIR kernels: a thread owns two horizontally adjacent pixels that share a 3 x 4 window of 16-byte
+// loads.  All arithmetic is exact fp32 on packed FFMA2 (fma.rn.f32x2) -- no TF32.  wgrad streams dY
+// through shared memory with 1-D TMA bulk copies and is deterministic: per-block partial sums in a fixed
+// order, then a fixed-shape tree.
 #include "common.cuh"
 #include "ptx.cuh"
 
