@@ -40,7 +40,12 @@ def run(M, N, K, bn, pair, nstage):
 
 if __name__ == '__main__':
     cases = [(8192, 256, 2304, 128, 0, 4), (8192, 256, 2304, 128, 1, 4), (8192, 256, 2304, 256, 0, 4),
-             (8192, 256, 2304, 256, 1, 4), (32768, 128, 1152, 128, 0, 4), (32768, 128, 1152, 128, 1, 4)]
+             (8192, 256, 2304, 256, 1, 4), (32768, 128, 1152, 128, 0, 4), (32768, 128, 1152, 128, 1, 4),
+             # three stages: two single CTAs (96 KB) or three pair halves (72 KB) fit on one SM
+             (8192, 256, 2304, 128, 0, 3), (8192, 256, 2304, 128, 1, 3), (32768, 128, 1152, 128, 0, 3),
+             (32768, 128, 1152, 128, 1, 3)]
+    if len(sys.argv) > 1 and sys.argv[1] == 'stages3':
+        cases = cases[6:]
     for c in cases:
         try:
             run(*c)
