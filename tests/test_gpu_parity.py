@@ -835,3 +835,28 @@ def test_fused_bn_relu_maxpool_vs_torch(shape, train):
     assert rel(xb.grad, xa.grad) <= 1e-4
     assert rel(fused.weight.grad, ref.weight.grad) <= 1e-4 and rel(fused.bias.grad, ref.bias.grad) <= 1e-4
     assert rel(fused.running_mean, ref.running_mean) <= TOL_FP32 and rel(fused.running_var, ref.running_var) <= TOL_FP32
+
+
+def test_merge_split_grads_roundtrip():
+    """after a6 dW and dP have disjoint supports, so one buffer m = dW + dP can travel through the
+    all-reduce and is split back by the task mask.  Exact: one addend is always zero."""
+    lib = _lib.load()
+    rng = np.random.RandomState(11)
+    n, cur = 100003, 3
+    t = rng.randint(0, 5, size=n).astype(np.uint8)
+    dW = (rng.standard_normal(n) * (t == cur)).astype(np.float32)
+    dP = (rng.standard_normal(n) * ((t > 0) & (t < cur))).astype(np.float32)
+    tW, tP, tT = G(dW), G(dP), G(t)
+    m = torch.full((n,), float('nan'), device=DEV)
+    st = _lib.stream_ptr()
+    _lib.check(lib.cpgb_merge_grads(_lib.ptr(tW), _lib.ptr(tP), _lib.ptr(m), n, st), 'merge')
+    assert np.array_equal(m.cpu().numpy(), dW + dP)
+    oW, oP = torch.full_like(m, float('nan')), torch.full_like(m, float('nan'))
+    _lib.check(lib.cpgb_split_merged_grad(_lib.ptr(m), _lib.ptr(tT), n, cur, _lib.ptr(oW), _lib.ptr(oP), st), 'split')
+    assert np.array_equal(oW.cpu().numpy(), dW) and np.array_equal(oP.cpu().numpy(), dP)
+    # task 1: no piggymask, dP == NULL on both sides
+    _lib.check(lib.cpgb_merge_grads(_lib.ptr(tW), None, _lib.ptr(m), n, st), 'merge')
+    assert np.array_equal(m.cpu().numpy(), dW)
+    oW.fill_(float('nan'))
+    _lib.check(lib.cpgb_split_merged_grad(_lib.ptr(m), _lib.ptr(tT), n, cur, _lib.ptr(oW), None, st), 'split')
+    assert np.array_equal(oW.cpu().numpy(), dW)
