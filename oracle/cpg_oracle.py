@@ -22,6 +22,11 @@ models/layers.py:108 and :194.  The oracle therefore calls the same third-party
 ``torch.nn.functional.conv2d`` / ``linear`` on CPU (torch 2.11.0 in this image) and
 additionally offers ``conv2d_f64`` (float64 accumulate) as the exact yardstick for
 tolerance statements.
+
+The next row built in round 1 (nn.BatchNorm2d -> nn.ReLU -> nn.MaxPool2d(2, 2) after
+every convolution, models/vgg.py:95-122) is restated at the end of this file in float64 numpy
+(``bn_relu_pool_forward`` / ``bn_relu_pool_backward``) and pinned against the stock torch modules on the
+CPU by tests/test_oracle_norm.py.
 """
 from __future__ import annotations
 
@@ -370,3 +375,77 @@ class OraclePruner:
         for name, m in self._layers():
             make_finetuning_mask(self.masks[name], cur)
         self.current_dataset_idx = cur + 1
+
+
+# ----------------------------------------------------------------------------
+# the consumer of every masked convolution
+#   nn.BatchNorm2d -> nn.ReLU(inplace=True) (-> nn.MaxPool2d(kernel_size=2, stride=2))
+#   models/vgg.py:95-122 (make_layers), models/resnet.py:60-100
+# The arithmetic lives in PyTorch (same pinned dependency as the convolution); this is its published
+# definition restated in float64 numpy, pinned against torch CPU by tests/test_oracle_norm.py.
+# ----------------------------------------------------------------------------
+def bn_relu_pool_forward(x, gamma, beta, running_mean, running_var, training: bool, momentum: float = 0.1,
+                         eps: float = 1e-5, relu: bool = True, pool: bool = False):
+    """x [N, C, H, W] (numpy).  Returns (y, new_running_mean, new_running_var, mean, rstd) in float64.
+    Training: batch statistics with the BIASED variance normalise; the running statistics are updated
+    with `momentum` and the UNBIASED variance.  Evaluation: the running statistics normalise."""
+    import numpy as np
+    x = np.asarray(x, dtype=np.float64)
+    C = x.shape[1]
+    g = np.ones(C) if gamma is None else np.asarray(gamma, dtype=np.float64)
+    b = np.zeros(C) if beta is None else np.asarray(beta, dtype=np.float64)
+    rm = None if running_mean is None else np.asarray(running_mean, dtype=np.float64)
+    rv = None if running_var is None else np.asarray(running_var, dtype=np.float64)
+    if training:
+        m = x.shape[0] * x.shape[2] * x.shape[3]
+        mean = x.mean(axis=(0, 2, 3))
+        var = x.var(axis=(0, 2, 3))                       # biased
+        if rm is not None:
+            rm = (1 - momentum) * rm + momentum * mean
+            rv = (1 - momentum) * rv + momentum * var * m / max(m - 1, 1)
+    else:
+        mean, var = rm, rv
+    rstd = 1.0 / np.sqrt(var + eps)
+    y = (x - mean[None, :, None, None]) * (rstd * g)[None, :, None, None] + b[None, :, None, None]
+    if relu:
+        y = np.maximum(y, 0.0)
+    if pool:
+        n, c, h, w = y.shape
+        y = y[:, :, :h // 2 * 2, :w // 2 * 2].reshape(n, c, h // 2, 2, w // 2, 2).max(axis=(3, 5))
+    return y, rm, rv, mean, rstd
+
+
+def bn_relu_pool_backward(x, dy, gamma, beta, mean, rstd, training: bool, relu: bool = True, pool: bool = False):
+    """Gradients of bn_relu_pool_forward w.r.t. x, gamma, beta (float64 numpy).  With g the gradient that
+    reaches the batch-norm output (dy routed to the FIRST maximum of each 2x2 window in (h, w) order, then
+    masked by y > 0) and xhat = (x - mean) * rstd:
+        dbeta = sum g;  dgamma = sum g * xhat;
+        training: dx = gamma * rstd * (g - mean(g) - xhat * mean(g * xhat));  evaluation: dx = gamma * rstd * g."""
+    import numpy as np
+    x = np.asarray(x, dtype=np.float64)
+    dy = np.asarray(dy, dtype=np.float64)
+    C = x.shape[1]
+    gm = np.ones(C) if gamma is None else np.asarray(gamma, dtype=np.float64)
+    bt = np.zeros(C) if beta is None else np.asarray(beta, dtype=np.float64)
+    bc = lambda v: np.asarray(v, dtype=np.float64)[None, :, None, None]
+    xhat = (x - bc(mean)) * bc(rstd)
+    z = xhat * bc(gm) + bc(bt)
+    if pool:
+        n, c, h, w = z.shape
+        win = z.reshape(n, c, h // 2, 2, w // 2, 2).transpose(0, 1, 2, 4, 3, 5).reshape(n, c, h // 2, w // 2, 4)
+        first = win.argmax(axis=-1)                      # numpy argmax returns the first maximum
+        g4 = np.zeros_like(win)
+        np.put_along_axis(g4, first[..., None], dy[..., None], axis=-1)
+        g = g4.reshape(n, c, h // 2, w // 2, 2, 2).transpose(0, 1, 2, 4, 3, 5).reshape(n, c, h, w)
+    else:
+        g = dy.copy()
+    if relu:
+        g = g * (z > 0)
+    dbeta = g.sum(axis=(0, 2, 3))
+    dgamma = (g * xhat).sum(axis=(0, 2, 3))
+    if training:
+        m = x.shape[0] * x.shape[2] * x.shape[3]
+        dx = bc(gm * np.asarray(rstd, dtype=np.float64)) * (g - bc(dbeta / m) - xhat * bc(dgamma / m))
+    else:
+        dx = bc(gm * np.asarray(rstd, dtype=np.float64)) * g
+    return dx, dgamma, dbeta
