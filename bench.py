@@ -54,9 +54,28 @@ class _Wrap(nn.Module):
         return self.module(*a, **k)
 
 
-def build_model(conv_cls, linear_cls, regime, device):
+REF_DIR = os.path.join(ROOT, 'baseline', '_ref')     # unmodified reference checkout (tools/stage_reference.py)
+VGG_CFG = [64, 64, 'M', 128, 128, 'M', 256, 256, 256, 'M', 512, 512, 512, 'M', 512, 512, 512, 'M']   # CPG_cifar100_main_normal.py:188
+
+
+def have_reference():
+    return os.path.isfile(os.path.join(REF_DIR, 'models', 'vgg.py'))
+
+
+def reference_vgg(width):
+    """The reference's own models.custom_vgg_cifar100 (models/vgg.py:276-278).  In the product arm
+    cpg_b200.install() has aliased models.layers first, so the unmodified model file builds itself out of the
+    product layers; in the reference arm nothing is aliased."""
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    import models
+    return models.custom_vgg_cifar100(list(VGG_CFG), dataset_history=[], dataset2num_classes={},
+                                      network_width_multiplier=width, shared_layer_info={})
+
+
+def build_model(conv_cls, linear_cls, regime, device, width=1.0, from_reference=False):
     torch.manual_seed(1)                      # --seed default, CPG_cifar100_main_normal.py:79
-    model = VGGCifar(conv_cls, linear_cls, width=1.0)
+    model = reference_vgg(width) if from_reference else VGGCifar(conv_cls, linear_cls, width=width)
     datasets = ['task1'] if regime == 'task1' else ['task1', 'task2']
     for d in datasets:
         model.add_dataset(d, 5)
@@ -241,20 +260,31 @@ class Trainer:
     """The training step of utils/manager.py:54-75 over the product layers/pruner, optionally
     captured into one CUDA graph (static input buffers)."""
 
-    def __init__(self, regime, device, world, use_graph=True, impl='ours'):
+    def __init__(self, regime, device, world, use_graph=True, impl='ours', width=1.0):
         from cpg_b200.ddp import GradAllReducer
         self.device, self.world = device, world
         if impl == 'ours':
+            import cpg_b200
             import cpg_b200.layers as nl
             from cpg_b200.prune import SparsePruner
-            self.net, self.masks, datasets, self.cur = build_model(nl.SharableConv2d, nl.SharableLinear, regime, device)
+            self.model_source = 'cpg_b200.vgg_cifar.VGGCifar (harness mirroring models/vgg.py)'
+            use_ref = have_reference() and os.environ.get('CPGB_BENCH_HARNESS_MODEL', '0') != '1'
+            if use_ref:
+                # the unmodified models/vgg.py of the staged reference checkout, built on the product layers
+                if REF_DIR not in sys.path:
+                    sys.path.insert(0, REF_DIR)
+                cpg_b200.install()
+                self.model_source = 'baseline/_ref/models/vgg.py custom_vgg_cifar100 (unmodified) after cpg_b200.install()'
+            self.net, self.masks, datasets, self.cur = build_model(nl.SharableConv2d, nl.SharableLinear, regime, device,
+                                                                   width=width, from_reference=use_ref)
             if FUSE_BN_RELU:
                 from cpg_b200.fused_norm import fuse_bn_relu
                 fuse_bn_relu(self.net)
             self.pruner = SparsePruner(self.net, self.masks, make_args(datasets), 0, 1, self.cur)
         else:
+            self.model_source = 'stock torch modules'
             self.net, self.masks, datasets, self.cur = build_model(TorchSharableConv2d, TorchSharableLinear, regime,
-                                                                   device)
+                                                                   device, width=width)
             self.pruner = TorchPruner(self.net, self.masks, self.cur)
         self.opts = make_optimizers(self.net, capturable=use_graph)
         self.crit = nn.CrossEntropyLoss()
@@ -498,8 +528,8 @@ def prune_table(device, iters=5):
 
 
 def cpu_port_step_time(regime, batch, steps, warmup, threads):
-    """The reference's CPU path (oracle port: OracleSharable* layers + OraclePruner), same step
-    sequence, on `threads` host cores."""
+    """Fallback when baseline/_ref is not staged: the oracle port of the reference's CPU path (OracleSharable*
+    layers + OraclePruner), same step sequence, on `threads` host cores."""
     from oracle import cpg_oracle as O
     torch.set_num_threads(threads)
     net, masks, datasets, cur = build_model(O.OracleSharableConv2d, O.OracleSharableLinear, regime, 'cpu')
@@ -526,35 +556,104 @@ def cpu_port_step_time(regime, batch, steps, warmup, threads):
     return sum(times), float(loss.item())
 
 
+def cpu_reference_step_time(regime, batch, steps, warmup, threads):
+    """The UNMODIFIED reference (baseline/_ref, staged by tools/stage_reference.py) on the host cores, through its
+    own public API and stock code path: models.custom_vgg_cifar100 (models/vgg.py:276) built on models.layers,
+    utils.prune.SparsePruner, and utils.manager.Manager.train (utils/manager.py:39-100) looping over a list of
+    synthetic (data, target) batches -- zero_grad, forward, loss, backward, do_weight_decay_and_make_grads_zero,
+    optimizers.step, plus the per-batch accuracy / sparsity bookkeeping the reference does.  Returns (seconds for
+    `steps` batches, last training accuracy)."""
+    torch.set_num_threads(threads)
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    import models.layers as ref_nl
+    assert ref_nl.__file__.startswith(REF_DIR), 'models.layers is not the staged reference (cpg_b200.install() ran?)'
+    from utils import Optimizers
+    from utils.manager import Manager
+    net, masks, datasets, cur = build_model(ref_nl.SharableConv2d, ref_nl.SharableLinear, regime, 'cpu',
+                                            from_reference=True)
+    args = make_args(datasets)
+    args.cuda, args.checkpoint_format = False, ''
+    data = synth_batches(2, batch, seed=11)
+
+    def run(n):
+        loader = [data[i % 2] for i in range(n)]
+        shared = {args.dataset: {'bias': {}, 'bn_layer_running_mean': {}, 'bn_layer_running_var': {},
+                                 'bn_layer_weight': {}, 'bn_layer_bias': {}, 'piggymask': {}}}
+        mgr = Manager(args, net, shared, masks, loader, loader, 0, 1)
+        opts = Optimizers()
+        for o, lr in zip(make_optimizers(net, capturable=False), (LR, LR_MASK)):
+            opts.add(o, lr)
+        t0 = time.perf_counter()
+        acc, _ = mgr.train(opts, 0, [LR], 0)
+        return time.perf_counter() - t0, acc
+
+    if warmup:
+        run(warmup)
+    return run(steps)
+
+
+def reference_arm_time(regime, batch, steps, warmup, threads):
+    """(seconds, kind, what) of the reference's CPU implementation of the path."""
+    if have_reference():
+        total, _ = cpu_reference_step_time(regime, batch, steps, warmup, threads)
+        return total, 'reference', ('unmodified ivclab/CPG from baseline/_ref: models.custom_vgg_cifar100 + '
+                                    'utils.prune.SparsePruner driven by utils.manager.Manager.train')
+    total, _ = cpu_port_step_time(regime, batch, steps, warmup, threads)
+    return total, 'port', 'oracle port of the reference step (baseline/_ref not staged)'
+
+
+def make_config(world, batch_per_gpu=BATCH):
+    """The workload description both arms print (same keys, same values): BASELINE.json configs[1]."""
+    return {'workload': WORKLOAD, 'regime': 'task1 (R1: no piggymask, T==1, cur=1)',
+            'global_batch': batch_per_gpu * world, 'parallelism': f'dp{world}',
+            'step': 'utils/manager.py:54-75 sequence: zero_grad, forward, CrossEntropyLoss, backward, '
+                    'do_weight_decay_and_make_grads_zero, SGD-nesterov step (CPG_cifar100_main_normal.py:339-346)'}
+
+
 def run_reference_arm(args):
-    """--impl reference: the reference's own CPU implementation of the path (the oracle port --
-    the reference is Python and cannot travel to the GPU box) on all host cores."""
-    world = int(os.environ.get('WORLD_SIZE', '1'))
+    """--impl reference: the reference's own CPU implementation of the path on all host cores (rank 0 only)."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     # calibrate the per-step sample so the whole run ends within a few minutes
-    t_cal, _ = cpu_port_step_time('task1', 16, 1, 1, cores)
+    t_cal, _, _ = reference_arm_time('task1', 16, 1, 1, cores)
     per_img = t_cal / 16
     budget = 150.0
     sample = BATCH
     while sample > 8 and per_img * sample * (args.steps + args.warmup) > budget:
         sample //= 2
-    total, _ = cpu_port_step_time('task1', sample, args.steps, args.warmup, cores)
+    total, kind, what = reference_arm_time('task1', sample, args.steps, args.warmup, cores)
     value = sample * args.steps / total
+    cfg = make_config(max(1, args.gpus))      # the product arm's config, verbatim; the bounded sample is in cpu_baseline
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total / args.steps * 1e3,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'regime': 'task1 (R1: no piggymask, T==1)', 'batch_per_step': sample},
-        'cpu_baseline': {'value': value, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-                         'sample': f'{args.steps} steps x {sample} images (torch {torch.__version__} CPU, '
-                                   f'{torch.get_num_threads()} threads)'},
+        'config': cfg,
+        'cpu_baseline': {'value': value, 'unit': 'images/s', 'cores': cores, 'kind': kind,
+                         'sample': f'{args.steps} steps x {sample} images after {args.warmup} warm-up ({what}; torch '
+                                   f'{torch.__version__} CPU, {torch.get_num_threads()} threads)'},
         'e2e': {'value': value, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
     print(json.dumps(line))
+
+
+def cpu_baseline_subprocess(steps=3, warmup=1):
+    """The product process has aliased models.layers (cpg_b200.install()), so the unmodified reference is timed in a
+    child process: `bench.py --impl reference`, whose JSON line is parsed."""
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', str(steps),
+                            '--warmup', str(warmup)], capture_output=True, text=True, timeout=600,
+                           env={k: v for k, v in os.environ.items() if k not in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK')})
+        for ln in reversed(r.stdout.strip().splitlines()):
+            if ln.startswith('{'):
+                return json.loads(ln)['cpu_baseline']
+        return {'error': (r.stderr or r.stdout)[-300:]}
+    except Exception as ex:  # noqa: BLE001
+        return {'error': f'{type(ex).__name__}: {ex}'[:200]}
 
 
 def main():
@@ -589,7 +688,8 @@ def main():
             sampler.start()
         ms, loss = timed_region(tr, dev_batches, args.steps, args.warmup, world)
         clocks = sampler.stop() if rank == 0 else None
-        res = {'ms': ms, 'loss': loss, 'clocks': clocks, 'launches_per_step': tr.launches_per_step}
+        res = {'ms': ms, 'loss': loss, 'clocks': clocks, 'launches_per_step': tr.launches_per_step,
+               'model_source': tr.model_source}
         if want_e2e:
             host = [(x.pin_memory(), t.pin_memory()) for x, t in batches]
             ms2, loss2 = timed_region(tr, None, args.steps, args.warmup, world, e2e_host=host)
@@ -630,14 +730,18 @@ def main():
             'warmup': args.warmup, 'ms_per_step': r1['ms'] / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'tf32 (fp32 in/out, fp32 accumulate)' if args.path == 'auto' else 'f32',
             'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'regime': 'task1 (R1: no piggymask, T==1, cur=1)',
-                       'global_batch': BATCH * world, 'parallelism': f'dp{world}',
-                       'step': 'utils/manager.py:54-75 sequence, SGD-nesterov (+Adam on piggymasks in task2); '
-                               'torch.optim fused=True (same update rule as CPG_cifar100_main_normal.py:339-346)',
-                       'cuda_graph': not args.no_graph,
-                       'bn_relu_pool': ('cpg_b200.fused_norm (BatchNorm2d+ReLU(+MaxPool2d) kernels, SURVEY 8f N4)'
-                                        if FUSE_BN_RELU else 'stock torch modules'),
-                       'l2': 'per-step working set (weights+grads+momentum 400 MB, activations 280 MB) exceeds the 126 MB L2; 8 distinct input batches rotate'},
+            'config': make_config(world),
+            'impl_detail': {'optimizer': 'torch.optim.SGD(fused=True) (+Adam(fused=True) on piggymasks in task2): same '
+                                         'update rule as CPG_cifar100_main_normal.py:339-346',
+                            'cuda_graph': not args.no_graph,
+                            'model': r1.get('model_source'),
+                            'bn_relu_pool': ('cpg_b200.fused_norm (BatchNorm2d+ReLU(+MaxPool2d) kernels, SURVEY 8f N4), '
+                                             'outputs rounded to TF32 for the tcgen05 convolutions'
+                                             if FUSE_BN_RELU else 'stock torch modules'),
+                            'not_in_step': 'the per-batch host reads of utils/manager.py:60 (accuracy .cpu()) and :77-88 '
+                                           '(calculate_sparsity for the progress bar)',
+                            'l2': 'per-step working set (weights+grads+momentum 400 MB, activations 280 MB) exceeds '
+                                  'the 126 MB L2; 8 distinct input batches rotate'},
             'clocks': {k: r1['clocks'].get(k) for k in ('sm_mhz', 'sm_max_mhz', 'reasons')} if r1['clocks'] else None,
             'e2e': {'value': imgs / (r1['e2e_ms'] * 1e-3), 'unit': 'images/s', 'h2d_bytes_per_step': r1['h2d'],
                     'd2h_bytes_per_step': r1['d2h'], 'ms_per_step': r1['e2e_ms'] / args.steps},
@@ -651,7 +755,11 @@ def main():
                 'e2e_value': imgs / (r2['e2e_ms'] * 1e-3), 'gpu_launches': int(r2['launches_per_step'] * args.steps),
                 'loss': r2['loss']}
     if extras and world == 1:
-        tf32_peak = measure_tf32_peak(device)
+        tf32_cublas = measure_tf32_peak(device)
+        # the roofline denominator is in MEASURED_PEAKS.json's terms: tcgen05 kind::tf32 issues at exactly half the
+        # kind::f16 rate (tools/mma_rate.py: 2047 MAC/clk/SM), so TF32 dense peak = bf16_tflops / 2 (burst figure:
+        # each kernel is timed alone); fallback 1590 / 2 when the file is absent (B200_PROFILING.md)
+        tf32_peak = (peaks.get('bf16_tflops') or 1590.0) / 2.0
         rows, tot, flops, dom = kernel_table(device, regime_has_piggy=False)
         step_ms = r1['ms'] / args.steps
         achieved = flops[dom] / (tot[dom] * 1e-3) / 1e12
@@ -668,9 +776,10 @@ def main():
             'traffic': traffic,
             'traffic_note': 'dram__bytes_read+write summed over the 15 launches of this pass (ncu, cold caches; '
                             'profiles/r1_dram_traffic.json); the pass is tensor/shared-memory bound, not HBM bound',
-            'peak_source': 'measured in this run: cuBLAS TF32 torch.matmul 8192^3 best of 10 (TF32 is not in '
-                           'MEASURED_PEAKS.json, which holds bf16 only); tcgen05 kind::tf32 issues at exactly half '
-                           'the bf16 rate (tests/mma_rate.py: 2047 MAC/clk/SM)',
+            'peak_source': ('MEASURED_PEAKS.json bf16_tflops (burst) / 2' if peaks.get('bf16_tflops') else
+                            'fallback 1590 / 2 (B200_PROFILING.md)') + ': tcgen05 kind::tf32 issues at half the '
+                           'kind::f16 rate (tools/mma_rate.py); cuBLAS TF32 8192^3 measured in this run: %.1f TF/s'
+                           % tf32_cublas,
             'share_of_step': tot[dom] / step_ms,
             'by_pass': {k: {'achieved_tflops': flops[k] / (tot[k] * 1e-3) / 1e12,
                             'frac': flops[k] / (tot[k] * 1e-3) / 1e12 / tf32_peak, 'ms': tot[k]} for k in tot},
@@ -687,7 +796,7 @@ def main():
                            'per_layer': [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()}
                                          for r in rows]}
         line['peaks'] = {'hbm_gbs': peaks.get('hbm_gbs'), 'bf16_tflops': peaks.get('bf16_tflops'),
-                         'tf32_tflops_measured_here': tf32_peak}
+                         'tf32_tflops_peak_used': tf32_peak, 'tf32_tflops_cublas_measured_here': tf32_cublas}
         try:
             pt = prune_table(device)
             pt['frac_of_hbm_peak'] = pt['achieved_gbs_algorithmic'] / peaks['hbm_gbs'] if peaks.get('hbm_gbs') else None
@@ -700,11 +809,7 @@ def main():
                     'graded reference arm',
             'task1_cuda_graph': run_torch_gpu('task1', True), 'task1_eager': run_torch_gpu('task1', False),
             'task2_cuda_graph': run_torch_gpu('task2', True)}
-        cores = os.cpu_count() or 1
-        total, _ = cpu_port_step_time('task1', BATCH, 3, 1, cores)
-        line['cpu_baseline'] = {'value': BATCH * 3 / total, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-                                'sample': f'3 steps x {BATCH} images after 1 warm-up (oracle port of the reference '
-                                          f'step on torch {torch.__version__} CPU, {torch.get_num_threads()} threads)'}
+        line['cpu_baseline'] = cpu_baseline_subprocess(3, 1)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

@@ -11,6 +11,10 @@ import sys
 __version__ = '0.1.0'
 
 
+def _view_forward(self, input):
+    return input.reshape(*self.shape)
+
+
 def install():
     """Make ``import models.layers`` / ``from utils.prune import SparsePruner`` resolve to this
     package inside a CPG checkout (call before importing ``utils.manager``)."""
@@ -21,6 +25,16 @@ def install():
         models.layers = layers
     except Exception:
         pass
+    # Conv outputs of cpg_b200.layers are physically NHWC (torch.channels_last): the reference's flatten module
+    # `input.view(*self.shape)` (models/vgg.py:30-31, models/spherenet.py:20-21) then raises for feature maps
+    # larger than 1x1.  reshape() keeps the logical (C, H, W) flatten order and is a view whenever view() is.
+    for modname in ('models.vgg', 'models.spherenet'):
+        try:
+            mod = __import__(modname, fromlist=['View'])
+            if hasattr(mod, 'View'):
+                mod.View.forward = _view_forward
+        except Exception:
+            pass
     try:
         import utils.prune as ref_prune
         ref_prune.SparsePruner = prune.SparsePruner

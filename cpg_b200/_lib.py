@@ -9,6 +9,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libcpgb200.so')
 
 GRAD_RAW, GRAD_FINETUNE, GRAD_PRUNE = 0, 1, 2
+GRAD_MERGED = 4                       # or'ed into FINETUNE / PRUNE: dW + dP in one buffer (data parallel)
+FLAG_X_TF32, FLAG_DY_TF32 = 1, 2      # cpgb_conv_desc.flags
 PATH_AUTO, PATH_SIMT, PATH_TCGEN05 = 0, 1, 2
 
 EXPORTS = [
@@ -19,13 +21,14 @@ EXPORTS = [
     'cpgb_prune_batched_workspace_bytes', 'cpgb_prune_select_batched',
     'cpgb_apply_mask', 'cpgb_make_finetuning_mask', 'cpgb_mask_stats', 'cpgb_mask_stats_batched', 'cpgb_merge_grads',
     'cpgb_split_merged_grad', 'cpgb_bn_workspace_bytes', 'cpgb_bn_relu_fwd', 'cpgb_bn_relu_bwd',
+    'cpgb_uses_tensor_cores', 'cpgb_round_tf32',
 ]
 
 
 class ConvDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in
                 ('N', 'C', 'H', 'W', 'K', 'R', 'S', 'P', 'Q', 'stride_h', 'stride_w', 'pad_h', 'pad_w',
-                 'dil_h', 'dil_w', 'groups')] + [('xs', ctypes.c_int64 * 4), ('ys', ctypes.c_int64 * 4)]
+                 'dil_h', 'dil_w', 'groups', 'flags')] + [('xs', ctypes.c_int64 * 4), ('ys', ctypes.c_int64 * 4)]
 
 
 class CpgbError(RuntimeError):
@@ -55,6 +58,8 @@ def load():
         'cpgb_launch_count': (ctypes.c_int64, []),
         'cpgb_linear_desc': (None, [dp, i32, i32, i32]),
         'cpgb_workspace_bytes': (sz, [dp]),
+        'cpgb_uses_tensor_cores': (ctypes.c_int, [dp, i32]),
+        'cpgb_round_tf32': (ctypes.c_int, [vp, vp, i64, vp]),
         'cpgb_binarize': (ctypes.c_int, [vp, vp, i64, f32, vp]),
         'cpgb_staged_weight_bytes': (sz, [dp]),
         'cpgb_stage_weights': (ctypes.c_int, [dp, vp, vp, f32, vp, sz, vp]),
@@ -81,10 +86,10 @@ def load():
         'cpgb_merge_grads': (ctypes.c_int, [vp, vp, vp, i64, vp]),
         'cpgb_split_merged_grad': (ctypes.c_int, [vp, vp, i64, i32, vp, vp, vp]),
         'cpgb_bn_workspace_bytes': (sz, [i64, i32]),
-        'cpgb_bn_relu_fwd': (ctypes.c_int, [vp, i64, i32, vp, vp, vp, vp, vp, i32, f32, f32, i32, i32, i32, vp, vp, vp, vp,
+        'cpgb_bn_relu_fwd': (ctypes.c_int, [vp, i64, i32, vp, vp, vp, vp, vp, i32, f32, f32, i32, i32, i32, i32, vp, vp, vp,
+                                            vp, sz, vp]),
+        'cpgb_bn_relu_bwd': (ctypes.c_int, [vp, vp, i64, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp,
                                             sz, vp]),
-        'cpgb_bn_relu_bwd': (ctypes.c_int, [vp, vp, i64, i32, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, sz,
-                                            vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -117,8 +122,9 @@ def set_path(path):
     return load().cpgb_set_path(int(path))
 
 
-def conv_desc(x_shape, x_strides, w_shape, y_shape, y_strides, stride, padding, dilation, groups):
+def conv_desc(x_shape, x_strides, w_shape, y_shape, y_strides, stride, padding, dilation, groups, flags=0):
     d = ConvDesc()
+    d.flags = int(flags)
     d.N, d.C, d.H, d.W = x_shape
     d.K, _, d.R, d.S = w_shape
     d.P, d.Q = y_shape[2], y_shape[3]

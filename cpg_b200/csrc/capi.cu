@@ -112,6 +112,13 @@ static int pick_tc(const cpgb_conv_desc *d, int op, bool *use_tc) {
   return CPGB_OK;
 }
 
+int cpgb_uses_tensor_cores(const cpgb_conv_desc *d, int32_t op) {
+  if (!d || op < 0 || op > 2 || validate_desc(d) || d->N == 0) return 0;
+  if (g_path.load() == CPGB_PATH_SIMT) return 0;
+  if (g_path.load() == CPGB_PATH_AUTO && stem_eligible(*d) && op != 1) return 0;   // direct fp32 stem kernels
+  return tc_eligible(*d, op) ? 1 : 0;
+}
+
 int cpgb_weights_usable_raw(const cpgb_conv_desc *d, int32_t has_piggymask) {
   if (!d || validate_desc(d) || has_piggymask || g_path.load() == CPGB_PATH_SIMT) return 0;
   return (tc_eligible(*d, 0) || tc_eligible(*d, 1)) && tc_weights_usable_raw(*d) ? 1 : 0;
@@ -119,8 +126,8 @@ int cpgb_weights_usable_raw(const cpgb_conv_desc *d, int32_t has_piggymask) {
 
 int cpgb_weights_usable_raw_for(int32_t K, int32_t C, int32_t R, int32_t S, int32_t stride_h, int32_t stride_w,
                                 int32_t groups, int32_t has_piggymask) {
-  if (has_piggymask || g_path.load() == CPGB_PATH_SIMT) return 0;
-  return groups == 1 && R * S == 1 && stride_h == 1 && stride_w == 1 && C % 32 == 0 && C >= 16 && K % 4 == 0;
+  (void)K; (void)C; (void)R; (void)S; (void)stride_h; (void)stride_w; (void)groups; (void)has_piggymask;
+  return 0;   // operands are always rounded to nearest TF32 now (see tc_weights_usable_raw)
 }
 
 size_t cpgb_staged_weight_bytes_for(int32_t K, int32_t C, int32_t R, int32_t S, int32_t stride_h, int32_t stride_w,
@@ -225,9 +232,16 @@ int cpgb_conv2d_wgrad_fused(const cpgb_conv_desc *d, const float *x, const float
   int rc = validate_desc(d);
   if (rc) return rc;
   if ((d->N != 0 && (!x || !dy)) || !w || !dW) { set_error("cpgb_conv2d_wgrad_fused: null pointer"); return CPGB_EINVAL; }
-  if (mode < CPGB_GRAD_RAW || mode > CPGB_GRAD_PRUNE) { set_error("bad grad mode %d", mode); return CPGB_EINVAL; }
-  if (mode != CPGB_GRAD_RAW && !tmask) { set_error("fused grad modes need the task mask"); return CPGB_EINVAL; }
-  if ((piggy == nullptr) != (dP == nullptr)) { set_error("dP must be given iff piggy is"); return CPGB_EINVAL; }
+  const int base_mode = mode & 3;
+  const bool merged = (mode & CPGB_GRAD_MERGED) != 0;
+  if (mode < 0 || (mode & ~7) || base_mode > CPGB_GRAD_PRUNE || (merged && base_mode == CPGB_GRAD_RAW)) {
+    set_error("bad grad mode %d", mode); return CPGB_EINVAL;
+  }
+  if (base_mode != CPGB_GRAD_RAW && !tmask) { set_error("fused grad modes need the task mask"); return CPGB_EINVAL; }
+  if (merged ? dP != nullptr : (piggy == nullptr) != (dP == nullptr)) {
+    set_error(merged ? "merged mode writes dW + dP to dW: pass dP = NULL" : "dP must be given iff piggy is");
+    return CPGB_EINVAL;
+  }
   const size_t n = weight_elems(d);
   if (!ws || ws_bytes < cpgb_workspace_bytes(d)) {
     set_error("workspace %zu < %zu", ws_bytes, cpgb_workspace_bytes(d));

@@ -58,6 +58,22 @@ __device__ __forceinline__ float masked_weight(float w, const float *piggy, long
   return piggy ? binarize_val(__ldg(piggy + idx), thr) * w : w;
 }
 
+// The fused gradient epilogue for one element: g is the raw weight gradient dL/dW_eff.
+//   RAW      : dW = g*b                     dP = g*W                      (models/layers.py:21-23,103)
+//   FINETUNE : dW = (g*b + wd*W)[T==cur]    dP = (g*W)[1<=T<cur]          (utils/prune.py:203-208)
+//   PRUNE    : dW = (g*b + wd*W)[T==cur]    dP = 0                        (utils/prune.py:203-205,210)
+// CPGB_GRAD_MERGED (or'ed into FINETUNE / PRUNE): the two results have disjoint support, so their sum is one
+// buffer that carries both through the data-parallel all-reduce; it is returned in dw.
+__device__ __forceinline__ void grad_epilogue_elem(float g, float w, float p, bool has_p, unsigned t, int cur, float wd,
+                                                   int mode, float thr, float &dw, float &dp) {
+  const float gb = has_p ? g * binarize_val(p, thr) : g;
+  const int m = mode & 3;
+  if (m == CPGB_GRAD_RAW) { dw = gb; dp = g * w; return; }
+  dw = (t == (unsigned)cur) ? fmaf(wd, w, gb) : 0.f;
+  dp = (m == CPGB_GRAD_FINETUNE && has_p && t != 0u && t < (unsigned)cur) ? g * w : 0.f;
+  if (mode & CPGB_GRAD_MERGED) dw += dp;
+}
+
 // ---- entry points implemented in the individual .cu files ----
 // CUDA-core (fp32 FFMA) implicit GEMM, any geometry.
 int simt_fprop(const Geom &g, const float *x, const float *w, const float *piggy, const float *bias,
@@ -68,6 +84,9 @@ int simt_dgrad(const Geom &g, const float *dy, const float *w, const float *pigg
 int simt_wgrad_splits(const Geom &g);
 int simt_wgrad_raw(const Geom &g, const float *x, const float *dy, float *gbuf, int *splits_out, cudaStream_t st);
 int bias_grad(const Geom &g, const float *dy, float *dbias, cudaStream_t st);
+
+// out = rna_tf32(in), elementwise (elementwise.cu)
+int round_tf32(const float *in, float *out, long long n, cudaStream_t st);
 
 // fused epilogue g -> (dW, dP)  
 int wgrad_epilogue(const float *gbuf, int splits, const float *w, const float *piggy, const uint8_t *tmask,

@@ -42,6 +42,34 @@ __global__ void __launch_bounds__(256) binarize_kernel(const float *__restrict__
   }
 }
 
+// ---------------- round-to-nearest TF32 (operand preparation of the tcgen05 kernels) ----------------
+__device__ __forceinline__ float rna_tf32(float v) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  return __uint_as_float(u);
+}
+__global__ void __launch_bounds__(256) round_tf32_kernel(const float *__restrict__ in, float *__restrict__ out,
+                                                         long long n, bool vec) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (vec) {
+    const long long n4 = n >> 2;
+    for (long long v = i; v < n4; v += stride) {
+      const float4 a = __ldg(reinterpret_cast<const float4 *>(in) + v);
+      reinterpret_cast<float4 *>(out)[v] = make_float4(rna_tf32(a.x), rna_tf32(a.y), rna_tf32(a.z), rna_tf32(a.w));
+    }
+    for (long long t = (n4 << 2) + i; t < n; t += stride) out[t] = rna_tf32(in[t]);
+  } else {
+    for (; i < n; i += stride) out[i] = rna_tf32(in[i]);
+  }
+}
+int round_tf32(const float *in, float *out, long long n, cudaStream_t st) {
+  if (n <= 0) return CPGB_OK;
+  round_tf32_kernel<<<grid_for(n / 4 + 1), 256, 0, st>>>(in, out, n, aligned16(in) && aligned16(out));
+  CPGB_LAUNCH_OK("round_tf32");
+  return CPGB_OK;
+}
+
 // ---------------- fused wgrad epilogue ----------------
 // g: raw weight gradient dL/dW_eff.  One pass produces what optimizers.step() must see:
 //   RAW      : dW = g*b                     dP = g*W                      (models/layers.py:21-23,103)
@@ -49,14 +77,7 @@ __global__ void __launch_bounds__(256) binarize_kernel(const float *__restrict__
 //   PRUNE    : dW = (g*b + wd*W)[T==cur]    dP = 0                        (utils/prune.py:203-205,210)
 __device__ __forceinline__ void epi_one(float g, float w, float p, bool has_p, unsigned t, int cur, float wd,
                                         int mode, float thr, float &dw, float &dp) {
-  float gb = has_p ? g * binarize_val(p, thr) : g;
-  if (mode == CPGB_GRAD_RAW) {
-    dw = gb;
-    dp = g * w;
-    return;
-  }
-  dw = (t == (unsigned)cur) ? fmaf(wd, w, gb) : 0.f;
-  dp = (mode == CPGB_GRAD_FINETUNE && t != 0u && t < (unsigned)cur) ? g * w : 0.f;
+  grad_epilogue_elem(g, w, p, has_p, t, cur, wd, mode, thr, dw, dp);
 }
 
 __global__ void __launch_bounds__(256)
@@ -233,10 +254,28 @@ merge_grads_kernel(const float *__restrict__ dW, const float *__restrict__ dP, f
     m[i] = dW[i] + (dP ? dP[i] : 0.f);
 }
 __global__ void __launch_bounds__(256)
-split_grads_kernel(const float *__restrict__ m, const uint8_t *__restrict__ tmask, long long n, int cur,
-                   float *__restrict__ dW, float *__restrict__ dP) {
+split_grads_kernel(const float *m, const uint8_t *__restrict__ tmask, long long n, int cur, float *dW,
+                   float *__restrict__ dP, bool vec) {
+  // dW may alias m (the data-parallel reducer splits in place inside its gradient bucket): every thread reads
+  // its own elements before it writes them
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long tail = 0;
+  if (vec) {
+    const long long n4 = n >> 2;
+    for (long long v = i0; v < n4; v += stride) {
+      const float4 a = reinterpret_cast<const float4 *>(m)[v];
+      const uchar4 t = __ldg(reinterpret_cast<const uchar4 *>(tmask) + v);
+      const unsigned c = (unsigned)cur;
+      reinterpret_cast<float4 *>(dW)[v] = make_float4(t.x == c ? a.x : 0.f, t.y == c ? a.y : 0.f, t.z == c ? a.z : 0.f,
+                                                      t.w == c ? a.w : 0.f);
+      if (dP)
+        reinterpret_cast<float4 *>(dP)[v] = make_float4((t.x != 0u && t.x < c) ? a.x : 0.f, (t.y != 0u && t.y < c) ? a.y : 0.f,
+                                                        (t.z != 0u && t.z < c) ? a.z : 0.f, (t.w != 0u && t.w < c) ? a.w : 0.f);
+    }
+    tail = n4 << 2;
+  }
+  for (long long i = tail + i0; i < n; i += stride) {
     unsigned t = tmask[i];
     float v = m[i];
     dW[i] = (t == (unsigned)cur) ? v : 0.f;
@@ -249,6 +288,11 @@ split_grads_kernel(const float *__restrict__ m, const uint8_t *__restrict__ tmas
 using namespace cpgb;
 
 extern "C" {
+
+int cpgb_round_tf32(const float *in, float *out, int64_t n, void *stream) {
+  if (n < 0 || (n > 0 && (!in || !out))) { set_error("cpgb_round_tf32: bad arguments"); return CPGB_EINVAL; }
+  return round_tf32(in, out, (long long)n, (cudaStream_t)stream);
+}
 
 int cpgb_binarize(const float *piggy, float *out, int64_t n, float thr, void *stream) {
   if (n < 0 || (n > 0 && (!piggy || !out))) { set_error("cpgb_binarize: null pointer"); return CPGB_EINVAL; }
@@ -334,7 +378,8 @@ int cpgb_split_merged_grad(const float *merged, const uint8_t *tmask, int64_t n,
                            void *stream) {
   if (n < 0 || (n > 0 && (!merged || !tmask || !dW))) { set_error("cpgb_split_merged_grad: null pointer"); return CPGB_EINVAL; }
   if (n == 0) return CPGB_OK;
-  split_grads_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(merged, tmask, n, cur, dW, dP);
+  const bool vec = aligned16(merged) && aligned16(dW) && (!dP || aligned16(dP)) && (reinterpret_cast<uintptr_t>(tmask) & 3) == 0;
+  split_grads_kernel<<<grid_for(n / 4 + 1), 256, 0, (cudaStream_t)stream>>>(merged, tmask, n, cur, dW, dP, vec);
   CPGB_LAUNCH_OK("cpgb_split_merged_grad");
   return CPGB_OK;
 }

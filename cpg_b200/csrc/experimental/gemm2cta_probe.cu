@@ -17,7 +17,7 @@
 // Build (syntax check on the build host, run on a B200):
 //   nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -shared \
 //        -o cpg_b200/libcpgb_probe.so cpg_b200/csrc/experimental/gemm2cta_probe.cu -lcudart
-// Driver: tests/gemm2cta_probe.py (compares against torch.matmul, times 1-CTA vs 2-CTA).
+// Driver: tools/gemm2cta_probe.py (compares against torch.matmul, times 1-CTA vs 2-CTA).
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>

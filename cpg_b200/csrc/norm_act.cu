@@ -185,9 +185,20 @@ __device__ __forceinline__ void coef_from_stats(const float *__restrict__ gamma,
   b = make_float4(bt.x - mu.x * a.x, bt.y - mu.y * a.y, bt.z - mu.z * a.z, bt.w - mu.w * a.w);
 }
 
+// round-to-nearest TF32 of the stored outputs (cpgb_bn_relu_*'s tf32_out): the consumer convolution's tensor-core
+// operand is then exact instead of truncated
+__device__ __forceinline__ float na_rna(float v) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ float4 na_out(float4 o, int tf32) {
+  return tf32 ? make_float4(na_rna(o.x), na_rna(o.y), na_rna(o.z), na_rna(o.w)) : o;
+}
+
 __global__ void __launch_bounds__(NA_THREADS)
 bn_apply_kernel(const NaGeom g, const float *__restrict__ x, const float *__restrict__ coef_a,
-                const float *__restrict__ coef_b, int relu, float *__restrict__ y) {
+                const float *__restrict__ coef_b, int relu, int tf32, float *__restrict__ y) {
   const int lane = threadIdx.x % g.lanes, slot = threadIdx.x / g.lanes;
   const int c4 = blockIdx.y * g.lanes + lane;
   if (slot >= g.slots || c4 * 4 >= g.C) return;
@@ -201,7 +212,7 @@ bn_apply_kernel(const NaGeom g, const float *__restrict__ x, const float *__rest
     const float4 v = __ldg(xp + r * cq);
     float4 o = make_float4(fmaf(v.x, a.x, b.x), fmaf(v.y, a.y, b.y), fmaf(v.z, a.z, b.z), fmaf(v.w, a.w, b.w));
     if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-    yp[r * cq] = o;
+    yp[r * cq] = na_out(o, tf32);
   }
 }
 
@@ -266,7 +277,8 @@ __global__ void __launch_bounds__(NA_THREADS)
 bn_bwd_apply_kernel(const NaGeom g, const float *__restrict__ x, const float *__restrict__ dy,
                     const float *__restrict__ gamma, const float *__restrict__ beta,
                     const float *__restrict__ save_mean, const float *__restrict__ save_rstd,
-                    const float *__restrict__ c1, const float *__restrict__ c2, int relu, float *__restrict__ dx) {
+                    const float *__restrict__ c1, const float *__restrict__ c2, int relu, int tf32,
+                    float *__restrict__ dx) {
   const int lane = threadIdx.x % g.lanes, slot = threadIdx.x / g.lanes;
   const int c4 = blockIdx.y * g.lanes + lane;
   if (slot >= g.slots || c4 * 4 >= g.C) return;
@@ -288,8 +300,8 @@ bn_bwd_apply_kernel(const NaGeom g, const float *__restrict__ x, const float *__
     NA_GRAD_ELEM(gy, hy, v.y, d.y, a.y, b.y, mu.y, rs.y)
     NA_GRAD_ELEM(gz, hz, v.z, d.z, a.z, b.z, mu.z, rs.z)
     NA_GRAD_ELEM(gw, hw, v.w, d.w, a.w, b.w, mu.w, rs.w)
-    op[r * cq] = make_float4(a.x * (gx - k1.x - hx * k2.x), a.y * (gy - k1.y - hy * k2.y),
-                             a.z * (gz - k1.z - hz * k2.z), a.w * (gw - k1.w - hw * k2.w));
+    op[r * cq] = na_out(make_float4(a.x * (gx - k1.x - hx * k2.x), a.y * (gy - k1.y - hy * k2.y),
+                                    a.z * (gz - k1.z - hz * k2.z), a.w * (gw - k1.w - hw * k2.w)), tf32);
   }
 }
 
@@ -318,7 +330,7 @@ __device__ __forceinline__ float max4_first(float z0, float z1, float z2, float 
 
 __global__ void __launch_bounds__(NA_THREADS)
 bn_apply_pool_kernel(const NaGeom g, const PoolGeom pg, const float *__restrict__ x, const float *__restrict__ coef_a,
-                     const float *__restrict__ coef_b, int relu, float *__restrict__ y) {
+                     const float *__restrict__ coef_b, int relu, int tf32, float *__restrict__ y) {
   const int lane = threadIdx.x % g.lanes, slot = threadIdx.x / g.lanes;
   const int c4 = blockIdx.y * g.lanes + lane;
   if (slot >= g.slots || c4 * 4 >= g.C) return;
@@ -337,7 +349,7 @@ bn_apply_pool_kernel(const NaGeom g, const PoolGeom pg, const float *__restrict_
     o.z = fmaxf(fmaxf(fmaf(v0.z, a.z, b.z), fmaf(v1.z, a.z, b.z)), fmaxf(fmaf(v2.z, a.z, b.z), fmaf(v3.z, a.z, b.z)));
     o.w = fmaxf(fmaxf(fmaf(v0.w, a.w, b.w), fmaf(v1.w, a.w, b.w)), fmaxf(fmaf(v2.w, a.w, b.w), fmaf(v3.w, a.w, b.w)));
     if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-    yp[r * cq] = o;
+    yp[r * cq] = na_out(o, tf32);
   }
 }
 
@@ -401,7 +413,8 @@ __global__ void __launch_bounds__(NA_THREADS)
 bn_bwd_apply_pool_kernel(const NaGeom g, const PoolGeom pg, const float *__restrict__ x, const float *__restrict__ dy,
                          const float *__restrict__ gamma, const float *__restrict__ beta,
                          const float *__restrict__ save_mean, const float *__restrict__ save_rstd,
-                         const float *__restrict__ c1, const float *__restrict__ c2, int relu, float *__restrict__ dx) {
+                         const float *__restrict__ c1, const float *__restrict__ c2, int relu, int tf32,
+                         float *__restrict__ dx) {
   const int lane = threadIdx.x % g.lanes, slot = threadIdx.x / g.lanes;
   const int c4 = blockIdx.y * g.lanes + lane;
   if (slot >= g.slots || c4 * 4 >= g.C) return;
@@ -427,7 +440,7 @@ bn_bwd_apply_pool_kernel(const NaGeom g, const PoolGeom pg, const float *__restr
     NA_POOL_DX(o0.z, o1.z, o2.z, o3.z, v0.z, v1.z, v2.z, v3.z, d.z, a.z, b.z, mu.z, rs.z, k1.z, k2.z)
     NA_POOL_DX(o0.w, o1.w, o2.w, o3.w, v0.w, v1.w, v2.w, v3.w, d.w, a.w, b.w, mu.w, rs.w, k1.w, k2.w)
     float4 *o = op + base;
-    o[0] = o0; o[cq] = o1; o[down] = o2; o[down + cq] = o3;
+    o[0] = na_out(o0, tf32); o[cq] = na_out(o1, tf32); o[down] = na_out(o2, tf32); o[down + cq] = na_out(o3, tf32);
   }
 }
 
@@ -462,8 +475,8 @@ static bool pool_geom(int64_t M, int32_t pool_h, int32_t pool_w, PoolGeom *pg) {
 
 int cpgb_bn_relu_fwd(const float *x, int64_t M, int32_t C, const float *gamma, const float *beta, float *running_mean,
                      float *running_var, int64_t *num_batches_tracked, int32_t training, float momentum, float eps,
-                     int32_t relu, int32_t pool_h, int32_t pool_w, float *y, float *save_mean, float *save_rstd, void *ws,
-                     size_t ws_bytes, void *stream) {
+                     int32_t relu, int32_t pool_h, int32_t pool_w, int32_t tf32_out, float *y, float *save_mean,
+                     float *save_rstd, void *ws, size_t ws_bytes, void *stream) {
   PoolGeom pg;
   const bool pool = pool_h != 0 || pool_w != 0;
   if (pool && !pool_geom(M, pool_h, pool_w, &pg)) {
@@ -497,9 +510,9 @@ int cpgb_bn_relu_fwd(const float *x, int64_t M, int32_t C, const float *gamma, c
   if (pool) {
     NaGeom gp = g;
     gp.M = pg.Mo;
-    bn_apply_pool_kernel<<<dim3(na_blocks(gp, 8), g.cchunks), NA_THREADS, 0, st>>>(g, pg, x, coef_a, coef_b, relu, y);
+    bn_apply_pool_kernel<<<dim3(na_blocks(gp, 8), g.cchunks), NA_THREADS, 0, st>>>(g, pg, x, coef_a, coef_b, relu, tf32_out, y);
   } else {
-    bn_apply_kernel<<<dim3(na_blocks(g, 8), g.cchunks), NA_THREADS, 0, st>>>(g, x, coef_a, coef_b, relu, y);
+    bn_apply_kernel<<<dim3(na_blocks(g, 8), g.cchunks), NA_THREADS, 0, st>>>(g, x, coef_a, coef_b, relu, tf32_out, y);
   }
   CPGB_LAUNCH_OK("bn_apply");
   return CPGB_OK;
@@ -507,7 +520,8 @@ int cpgb_bn_relu_fwd(const float *x, int64_t M, int32_t C, const float *gamma, c
 
 int cpgb_bn_relu_bwd(const float *x, const float *dy, int64_t M, int32_t C, const float *gamma, const float *beta,
                      const float *mean, const float *rstd, int32_t training, int32_t relu, int32_t pool_h,
-                     int32_t pool_w, float *dx, float *dgamma, float *dbeta, void *ws, size_t ws_bytes, void *stream) {
+                     int32_t pool_w, int32_t tf32_out, float *dx, float *dgamma, float *dbeta, void *ws, size_t ws_bytes,
+                     void *stream) {
   PoolGeom pg;
   const bool pool = pool_h != 0 || pool_w != 0;
   if (pool && !pool_geom(M, pool_h, pool_w, &pg)) {
@@ -542,10 +556,10 @@ int cpgb_bn_relu_bwd(const float *x, const float *dy, int64_t M, int32_t C, cons
     NaGeom gp = g;
     gp.M = pg.Mo;
     bn_bwd_apply_pool_kernel<<<dim3(na_blocks(gp, 8), g.cchunks), NA_THREADS, 0, st>>>(g, pg, x, dy, gamma, beta, mean, rstd,
-                                                                                      c1, c2, relu, dx);
+                                                                                      c1, c2, relu, tf32_out, dx);
   } else {
     bn_bwd_apply_kernel<<<dim3(na_blocks(g, 8), g.cchunks), NA_THREADS, 0, st>>>(g, x, dy, gamma, beta, mean, rstd, c1, c2,
-                                                                                relu, dx);
+                                                                                relu, tf32_out, dx);
   }
   CPGB_LAUNCH_OK("bn_bwd_apply");
   return CPGB_OK;

@@ -30,11 +30,8 @@ constexpr int STEM_THREADS = 128;
 constexpr int STEM_WG_THREADS = 256;
 
 __device__ __forceinline__ void epi_stem(float g, float w, float p, bool has_p, unsigned t, int cur, float wd,
-                                         int mode, float thr, float &dw, float &dp) {
-  float gb = has_p ? g * binarize_val(p, thr) : g;
-  if (mode == CPGB_GRAD_RAW) { dw = gb; dp = g * w; return; }
-  dw = (t == (unsigned)cur) ? fmaf(wd, w, gb) : 0.f;
-  dp = (mode == CPGB_GRAD_FINETUNE && t != 0u && t < (unsigned)cur) ? g * w : 0.f;
+                                        int mode, float thr, float &dw, float &dp) {
+  grad_epilogue_elem(g, w, p, has_p, t, cur, wd, mode, thr, dw, dp);
 }
 
 struct StemGeom {

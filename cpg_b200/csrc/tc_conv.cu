@@ -157,16 +157,13 @@ stage_weights_flat_kernel(const float4 *__restrict__ w, const float4 *__restrict
 }
 
 // ------------------------------------------------------------------------------------------
-// TF32 truncation debias.  tcgen05.mma kind::tf32 reads fp32 operands from shared memory and drops
-// the low 13 mantissa bits (truncation, not rounding): every truncated operand shrinks the product
-// by E[2^-11 / mantissa] = 2^-11 * 0.7213 = 3.52e-4 on average (log-uniform mantissas).  Measured on
-// B200 against fp32 cuDNN: <tc, ref>/<ref, ref> - 1 = -3.54e-4 for fprop/dgrad (activations
-// truncated, staged weights pre-rounded to nearest) and -7.07e-4 for wgrad (both operands raw).
-// The epilogues multiply the accumulator by the reciprocal, which turns a systematic 3.5e-4 / 7e-4
-// relative error into a zero-mean one of ~1e-4 (the parity bar is 1e-3).
+// TF32 numerics.  tcgen05.mma kind::tf32 reads fp32 bit patterns from shared memory and ignores the low
+// 13 mantissa bits (truncation).  Every operand is therefore made TF32-exact BEFORE it reaches the tensor
+// core, with round-to-nearest (cvt.rna.tf32.f32): the staged weights by the staging kernels, activations
+// and activation gradients by their producers (cpgb_bn_relu_* with tf32_out, the im2col kernel) or, when the
+// caller does not promise that (CPGB_FLAG_X_TF32 / CPGB_FLAG_DY_TF32), by a rounding pass into workspace.
+// The MMA then multiplies exactly the rounded values; no statistical correction is applied anywhere.
 // ------------------------------------------------------------------------------------------
-constexpr float DEBIAS_ONE = 1.0f / (1.0f - 3.54e-4f);
-constexpr float DEBIAS_TWO = 1.0f / (1.0f - 7.07e-4f);
 
 // ------------------------------------------------------------------------------------------
 // shared pieces of the GEMM kernels
@@ -226,7 +223,6 @@ struct ConvGemmParams {
   int kblocks;             // 32-wide reduction blocks per tap
   int ncols;               // valid output channels
   int iters_per_split;     // split-K over the (tap, k-block) loop; blockIdx.z = split
-  float debias;            // DEBIAS_ONE (staged, pre-rounded weights) or DEBIAS_TWO (raw fp32 weights)
   int nstage;              // depth of the smem ring (3: two CTAs share an SM; more: one CTA, deeper prefetch)
   int mn_layout, mn_lbo, mn_sbo, mn_kadv;   // MN-major operand descriptor fields
   long long o_sn, o_sh, o_sw;
@@ -357,7 +353,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         float *rp = rows[rr];
         const int col = col0 + h + c4;
         if (rp != nullptr && col < p.ncols) {   // ncols % 4 == 0
-          v.x *= p.debias; v.y *= p.debias; v.z *= p.debias; v.w *= p.debias;
           if (bias) {
             const float4 b = __ldg(reinterpret_cast<const float4 *>(bias + col));
             v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
@@ -410,12 +405,9 @@ splitk_reduce_kernel(const float4 *__restrict__ part, int splits, long long n4, 
 // ------------------------------------------------------------------------------------------
 // wgrad kernel: G[k][tap][c] = sum over 32-pixel chunks of dY^T X, both operands MN-major
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void epi_one_tc(float g, float w, float pv, bool has_p, unsigned t, int cur, float wd,
-                                           int mode, float thr, float &dw, float &dp) {
-  float gb = has_p ? g * binarize_val(pv, thr) : g;
-  if (mode == CPGB_GRAD_RAW) { dw = gb; dp = g * w; return; }
-  dw = (t == (unsigned)cur) ? fmaf(wd, w, gb) : 0.f;
-  dp = (mode == CPGB_GRAD_FINETUNE && t != 0u && t < (unsigned)cur) ? g * w : 0.f;
+__device__ __forceinline__ void epi_one_tc(float g, float w, float p, bool has_p, unsigned t, int cur, float wd,
+                                        int mode, float thr, float &dw, float &dp) {
+  grad_epilogue_elem(g, w, p, has_p, t, cur, wd, mode, thr, dw, dp);
 }
 
 struct WgradParams {
@@ -594,7 +586,6 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
       epilogue_rows<BN>(tmem_base, quad, 0, ts, lane, [&](int rr, int c4, float4 g) {
         const int row = quad * 32 + rr, k = kbase + rr, c = c0 + c4;
         if (k < p.K && c < p.C) {
-          g.x *= DEBIAS_TWO; g.y *= DEBIAS_TWO; g.z *= DEBIAS_TWO; g.w *= DEBIAS_TWO;
           const float4 wv = *reinterpret_cast<const float4 *>(w_s + row * 128 + c4);
           const float4 pv = has_p ? *reinterpret_cast<const float4 *>(p_s + row * 128 + c4) : make_float4(0, 0, 0, 0);
           const uchar4 tv = p.tmask ? *reinterpret_cast<const uchar4 *>(sT + row * 128 + c4) : make_uchar4(0, 0, 0, 0);
@@ -614,7 +605,6 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
         float *gbase = p.gpart + (((long long)split * p.K + kbase) * p.RS + (tap0 + s)) * p.Cg + c0;
         const long long row_stride = (long long)p.RS * p.Cg;
         epilogue_rows<BN>(tmem_base, quad, s * BN, ts, lane, [&](int rr, int c4, float4 g) {
-          g.x *= DEBIAS_TWO; g.y *= DEBIAS_TWO; g.z *= DEBIAS_TWO; g.w *= DEBIAS_TWO;
           if (kbase + rr < p.K && c0 + c4 < p.Cg) *reinterpret_cast<float4 *>(gbase + rr * row_stride + c4) = g;
         });
       }
@@ -840,6 +830,33 @@ static inline int cg_of(const cpgb_conv_desc &d) { return (d.C + 3) & ~3; }   //
 
 static inline int cp_of(const cpgb_conv_desc &d) { return (d.C + 31) / 32 * 32; }
 
+// ---- TF32 rounding pre-pass of an activation operand the caller did not declare exact ------------------
+// elements spanned by a strided 4-D tensor (its lowest address is the base pointer: strides are positive)
+static long long span_elems(int n0, int n1, int n2, int n3, const Str4 &st) {
+  return 1 + (long long)(n0 - 1) * st.s[0] + (long long)(n1 - 1) * st.s[1] + (long long)(n2 - 1) * st.s[2] +
+         (long long)(n3 - 1) * st.s[3];
+}
+static long long span_x(const cpgb_conv_desc &d) { return span_elems(d.N, d.C, d.H, d.W, x_strides(d)); }
+static long long span_dy(const cpgb_conv_desc &d) { return span_elems(d.N, d.K, d.P, d.Q, y_strides(d)); }
+static size_t round_bytes_x(const cpgb_conv_desc &d) {
+  return (d.flags & CPGB_FLAG_X_TF32) ? 0 : align_up((size_t)span_x(d) * 4, 256);
+}
+static size_t round_bytes_dy(const cpgb_conv_desc &d) {
+  return (d.flags & CPGB_FLAG_DY_TF32) ? 0 : align_up((size_t)span_dy(d) * 4, 256);
+}
+// Replace `src` by a rounded copy (same strides) carved from the front of the scratch region.
+static int round_operand(const float *&src, size_t bytes, long long span, void *&ws, size_t &ws_bytes, cudaStream_t st) {
+  if (bytes == 0) return CPGB_OK;
+  if (!ws || ws_bytes < bytes) { set_error("workspace %zu < %zu (TF32 rounding copy)", ws_bytes, bytes); return CPGB_EWORKSPACE; }
+  float *dst = reinterpret_cast<float *>(ws);
+  int rc = round_tf32(src, dst, span, st);
+  if (rc) return rc;
+  src = dst;
+  ws = reinterpret_cast<char *>(ws) + bytes;
+  ws_bytes -= bytes;
+  return CPGB_OK;
+}
+
 static size_t implicit_staged_bytes(const cpgb_conv_desc &d) {
   return align_up((size_t)d.K * d.R * d.S * cp_of(d) * sizeof(float) + 256, 256);
 }
@@ -936,7 +953,7 @@ static WgradPlan plan_wgrad(const cpgb_conv_desc &d) {
 static bool wgrad_fusable(const cpgb_conv_desc &d, const WgradPlan &pl) {
   // Linear / 1x1 layers with a single split CAN finish the gradient inside the GEMM (CPGB_WGRAD_FUSE=1): the
   // CTA's W / P / T tiles are prefetched into shared memory by TMA during the main loop and the epilogue only
-  // stores.  Measured on B200 (tests/time_ops.py, FC 4096x4096 @ batch 128) it loses to "write G (stays in
+  // stores.  Measured on B200 (tools/time_ops.py, FC 4096x4096 @ batch 128) it loses to "write G (stays in
   // L2) + streaming epilogue kernel": 93 us fused with TMA prefetch (one 183 KB CTA per SM, 7 rounds), 133 us
   // fused with the epilogue warps loading W / T themselves, 79 us unfused (two CTAs per SM).  Off by default.
   static const bool fuse = getenv("CPGB_WGRAD_FUSE") != nullptr;
@@ -953,8 +970,8 @@ static size_t implicit_workspace_bytes(const cpgb_conv_desc &d) {
     WgradPlan pl = plan_wgrad(d);
     if (!wgrad_fusable(d, pl)) b = std::max(b, (size_t)pl.splits * d.K * d.R * d.S * cg_of(d) * sizeof(float));
   }
-  // layout of ws: [staged operand (when the caller passes none)] [partial sums]
-  return staged + align_up(b, 256) + 256;
+  // layout of ws: [staged operand (when the caller passes none)] [rounded x] [rounded dy] [partial sums]
+  return staged + round_bytes_x(d) + round_bytes_dy(d) + align_up(b, 256) + 256;
 }
 
 static int implicit_stage_weights(const cpgb_conv_desc &d, const float *w, const float *piggy, float thr, void *staged,
@@ -1044,6 +1061,7 @@ static int implicit_fprop(const cpgb_conv_desc &d, const float *x, const float *
   GemmPlan g = plan_fprop(d);
   CUtensorMap ta, tb;
   int rc;
+  if ((rc = round_operand(x, round_bytes_x(d), span_x(d), part, part_bytes, st))) return rc;
   if ((rc = make_act_map(&ta, x, d.C, d.W, d.H, d.N, x_strides(d), g.box))) return rc;
   {
     uint64_t dims[3] = {(uint64_t)Cp, (uint64_t)RS, (uint64_t)d.K};
@@ -1054,7 +1072,7 @@ static int implicit_fprop(const cpgb_conv_desc &d, const float *x, const float *
   ConvGemmParams p;
   p.Qo = d.Q; p.Po = d.P; p.No = d.N; p.S = d.S; p.taps = RS;
   p.off_h = -d.pad_h; p.off_w = -d.pad_w; p.step_h = d.dil_h; p.step_w = d.dil_w;
-  p.kblocks = Cp / 32; p.ncols = d.K; p.debias = raw ? DEBIAS_TWO : DEBIAS_ONE;
+  p.kblocks = Cp / 32; p.ncols = d.K;
   { Str4 ys = y_strides(d); p.o_sn = ys.s[0]; p.o_sh = ys.s[2]; p.o_sw = ys.s[3]; }
   return run_gemm<false>(g, ta, tb, p, y, bias, part, part_bytes, st);
 }
@@ -1069,6 +1087,7 @@ static int implicit_dgrad(const cpgb_conv_desc &d, const float *dy, const float 
   GemmPlan g = plan_dgrad(d);
   CUtensorMap ta, tb;
   int rc;
+  if ((rc = round_operand(dy, round_bytes_dy(d), span_dy(d), part, part_bytes, st))) return rc;
   if ((rc = make_act_map(&ta, dy, d.K, d.Q, d.P, d.N, y_strides(d), g.box))) return rc;
   {
     // Wt[k][t][c] as (c_in_block 32, k, t, c_block): B tile = [BN/32][32 k rows][32 c]
@@ -1080,7 +1099,7 @@ static int implicit_dgrad(const cpgb_conv_desc &d, const float *dy, const float 
   ConvGemmParams p;
   p.Qo = d.W; p.Po = d.H; p.No = d.N; p.S = d.S; p.taps = RS;
   p.off_h = d.pad_h; p.off_w = d.pad_w; p.step_h = -d.dil_h; p.step_w = -d.dil_w;
-  p.kblocks = cdiv_i(d.K, 32); p.ncols = d.C; p.debias = raw ? DEBIAS_TWO : DEBIAS_ONE;
+  p.kblocks = cdiv_i(d.K, 32); p.ncols = d.C;
   { Str4 xs = x_strides(d); p.o_sn = xs.s[0]; p.o_sh = xs.s[2]; p.o_sw = xs.s[3]; }
   return run_gemm<true>(g, ta, tb, p, dx, nullptr, part, part_bytes, st);
 }
@@ -1125,10 +1144,12 @@ static int implicit_wgrad_fused(const cpgb_conv_desc &d, const float *x, const f
   const bool vec_ok = aligned16p(w) && aligned16p(dW) && (!piggy || aligned16p(piggy)) && (!dP || aligned16p(dP)) &&
                       (!tmask || (reinterpret_cast<uintptr_t>(tmask) & 3) == 0);
   const bool fused = wgrad_fusable(d, pl) && vec_ok && (!tmask || aligned16p(tmask));
+  int rc;
+  if ((rc = round_operand(x, round_bytes_x(d), span_x(d), ws, ws_bytes, st))) return rc;
+  if ((rc = round_operand(dy, round_bytes_dy(d), span_dy(d), ws, ws_bytes, st))) return rc;
   const size_t need = fused ? 0 : (size_t)pl.splits * d.K * RS * cg_of(d) * sizeof(float);
   if (ws_bytes < need) { set_error("workspace %zu < %zu", ws_bytes, need); return CPGB_EWORKSPACE; }
   CUtensorMap tdy, tx;
-  int rc;
   if ((rc = make_act_map5(&tdy, dy, d.K, d.Q, d.P, d.N, y_strides(d), pl.box, 4))) return rc;
   WgradParams p;
   if (pl.halo) {
@@ -1301,6 +1322,8 @@ static cpgb_conv_desc xcol_desc(const cpgb_conv_desc &d) {
   l.stride_h = l.stride_w = l.dil_h = l.dil_w = 1; l.groups = 1;
   l.xs[0] = kcp; l.xs[1] = 1; l.xs[2] = kcp; l.xs[3] = kcp;
   l.ys[0] = d.K; l.ys[1] = 1; l.ys[2] = d.K; l.ys[3] = d.K;
+  // X_col is rounded to TF32 by im2col_kernel (dX_col is an output); dy is the caller's tensor
+  l.flags = CPGB_FLAG_X_TF32 | (d.flags & CPGB_FLAG_DY_TF32);
   return l;
 }
 
@@ -1322,7 +1345,7 @@ im2col_kernel(Geom g, const float *__restrict__ x, float *__restrict__ xcol, int
         const int t = kc / g.C, c = kc - t * g.C, r = t / g.S, s = t - r * g.S;
         const int h = p * g.sh - g.ph + r * g.dh, ww = q * g.sw - g.pw + s * g.dw;
         if ((unsigned)h < (unsigned)g.H && (unsigned)ww < (unsigned)g.W)
-          val = __ldg(x + n * g.xs0 + c * g.xs1 + h * g.xs2 + ww * g.xs3);
+          val = to_tf32_rna(__ldg(x + n * g.xs0 + c * g.xs1 + h * g.xs2 + ww * g.xs3));
       }
       v[j] = val;
     }
@@ -1648,12 +1671,10 @@ int tc_stage_weights(const cpgb_conv_desc &d, const float *w, const float *piggy
                         : implicit_stage_weights(d, w, piggy, thr, staged, bytes, st);
 }
 
-// The raw fp32 weight tensor is itself a valid operand of the in-place path when the layer is linear /
-// 1x1 with whole 32-channel blocks and no piggymask: same [K][C] layout, the tensor core truncates it to
-// TF32 (hence DEBIAS_TWO).  Saves the staging pass for the FC layers of task 1 (56 % of VGG16's weights).
-bool tc_weights_usable_raw(const cpgb_conv_desc &d) {
-  return !prefer_xcol(d) && d.groups == 1 && d.R * d.S == 1 && d.C % 32 == 0 && d.K % 4 == 0;
-}
+// Round 1 fed the raw fp32 weight tensor of linear / 1x1 layers without a piggymask straight to the tensor
+// core (same [K][C] layout) and compensated the truncation statistically.  Operands are now always rounded to
+// nearest, so the weight is never consumed raw; the entry point stays for ABI stability.
+bool tc_weights_usable_raw(const cpgb_conv_desc &) { return false; }
 
 int tc_fprop(const cpgb_conv_desc &d, const float *x, const float *staged, const float *bias, float *y, void *part,
              size_t part_bytes, cudaStream_t st, bool raw) {

@@ -8,17 +8,24 @@ rank-invariant, so masking commutes with the reduction: it does not matter wheth
 wgrad epilogue (weight decay + grad mask) ran before the all-reduce -- avg_r((g_r*b + wd*W)[T==cur])
 == (avg_r(g_r)*b + wd*W)[T==cur].
 
-Large gradients (the sharable layers: 134 MB for VGG16) are all-reduced asynchronously from
-post-accumulate-grad hooks, i.e. while the rest of the backward pass is still running (FC2's
-67 MB bucket goes first); small ones (BN, biases, heads) are flattened into one bucket at the
-end.  Prune steps need no collective: every rank holds the same W and T.
+Gradient buckets.  The weight gradients of the sharable layers (134 MB for VGG16) are written by the wgrad
+epilogues STRAIGHT INTO a few large, pre-allocated flat buffers, laid out in backward order (the last layer
+first): ``.weight.grad`` becomes a view of its slot, so nothing is concatenated, copied or issued per parameter.
+A bucket's all-reduce is launched the moment the wgrad of its last layer has been issued, ordered after the
+wgrad side stream, and overlaps the rest of the backward pass (FC2's 67 MB bucket goes first).  With a piggymask
+(task >= 2) the epilogue writes the MERGED gradient m = dW + dP -- disjoint supports after the pruner's masking --
+so one buffer of n floats travels instead of two; ``reduce()`` splits it back into ``.weight.grad`` /
+``.piggymask.grad`` (cpgb_split_merged_grad).  Everything else (BN, biases, heads: < 1 MB) rides in one small flat
+bucket at the end.  Prune steps need no collective: every rank holds the same W and T.
 """
 import torch
 import torch.distributed as dist
 
-from .functional import pending_side_stream
+from . import _lib
+from .functional import pending_side_stream, _side_stream
 
-BIG = 1 << 18   # elements; tensors at least this large get their own overlapped all-reduce
+BIG = 1 << 18            # elements; other (non-sharable) tensors at least this large get their own overlapped all-reduce
+BUCKET_BYTES = 48 << 20  # a bucket is closed once it holds this much
 
 
 def tune_env(world):
@@ -43,8 +50,21 @@ def shard_batch(batch, rank, world):
     return batch[rank * per:(rank + 1) * per]
 
 
+class GradSlot:
+    """Where a sharable layer's wgrad epilogue writes: `n` floats at `offset` of bucket `bucket`."""
+    __slots__ = ('reducer', 'bucket', 'offset', 'n', 'state', 'fuse')
+
+    def __init__(self, reducer, bucket, offset, n):
+        self.reducer, self.bucket, self.offset, self.n = reducer, bucket, offset, n
+        self.state = 0          # 0: unused this step, 1: holds dW, 2: holds the merged dW + dP
+        self.fuse = None
+
+    def view(self, like):
+        return self.reducer.flat[self.bucket][self.offset:self.offset + self.n].view(like.shape)
+
+
 class GradAllReducer:
-    def __init__(self, model, world=None, overlap=True, group=None):
+    def __init__(self, model, world=None, overlap=True, group=None, bucket_bytes=None):
         self.world = world if world is not None else dist.get_world_size(group)
         self.group = group
         # NCCL averages inside the collective; gloo (CPU tests) only sums
@@ -54,11 +74,70 @@ class GradAllReducer:
         self.pending = []
         self.overlap = overlap
         self._hooks = []
+        self.flat, self._bucket_layers, self._bucket_left, self._slots = [], [], [], []
+        self._slot_params = set()
+        if self.world > 1:
+            self._make_slots(model, bucket_bytes or BUCKET_BYTES)
         if overlap and self.world > 1:
             for p in self.params:
-                if p.numel() >= BIG:
+                if p.numel() >= BIG and id(p) not in self._slot_params:
                     self._hooks.append(p.register_post_accumulate_grad_hook(self._hook))
 
+    # ------------------------------------------------------------------ buckets of the sharable layers
+    def _make_slots(self, model, bucket_bytes):
+        from . import layers as nl
+        mods = [m for m in model.modules() if isinstance(m, (nl.SharableConv2d, nl.SharableLinear))
+                and m.weight.is_cuda and m.weight.requires_grad and m.weight.dtype == torch.float32]
+        mods.reverse()                                   # backward order: the last layer's gradient is ready first
+        buckets, cur, cur_elems = [], [], 0
+        for m in mods:
+            cur.append(m)
+            cur_elems += (m.weight.numel() + 63) // 64 * 64          # 256-byte aligned slots
+            if cur_elems * 4 >= bucket_bytes:
+                buckets.append(cur)
+                cur, cur_elems = [], 0
+        if cur:
+            buckets.append(cur)
+        for b, layer_list in enumerate(buckets):
+            total = sum((m.weight.numel() + 63) // 64 * 64 for m in layer_list)
+            dev = layer_list[0].weight.device
+            self.flat.append(torch.zeros(total, dtype=torch.float32, device=dev))
+            off = 0
+            for m in layer_list:
+                slot = GradSlot(self, b, off, m.weight.numel())
+                m._cpg_grad_slot = slot
+                self._slots.append((m, slot))
+                self._slot_params.add(id(m.weight))
+                if m.piggymask is not None:
+                    self._slot_params.add(id(m.piggymask))
+                off += (m.weight.numel() + 63) // 64 * 64
+            self._bucket_layers.append(layer_list)
+            self._bucket_left.append(len(layer_list))
+
+    def layer_done(self, slot, device):
+        """Called by the backward pass right after the wgrad of a slotted layer was issued (on the side stream
+        when deferred).  Launches the bucket's all-reduce once every layer of the bucket has reported."""
+        b = slot.bucket
+        if self._bucket_left[b] > 0:
+            self._bucket_left[b] -= 1
+            if self._bucket_left[b] == 0 and self.overlap:
+                self._launch_bucket(b, device)
+
+    def _launch_bucket(self, b, device):
+        if self._bucket_left[b] < 0:
+            return
+        self._bucket_left[b] = -1                        # launched
+        buf = self.flat[b]
+        with torch.cuda.device(device):
+            side = _side_stream(device)
+            # after every wgrad issued so far: those on the side stream by stream order, those that joined the main
+            # stream immediately through this wait
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                work = dist.all_reduce(buf, op=self.op, group=self.group, async_op=True)
+        self.pending.append((buf, work))
+
+    # ------------------------------------------------------------------ other large parameters
     def _hook(self, p):
         if p.grad is None:
             return
@@ -66,28 +145,62 @@ class GradAllReducer:
         # join to the end of the backward pass): order the collective after that stream, not after the main one
         side = pending_side_stream(p.grad.device) if p.grad.is_cuda else None
         if side is not None:
+            # ... and after the main stream as well: this gradient may have been produced there (a stock
+            # nn.Linear / nn.Embedding parameter, or a layer whose wgrad joined immediately) while an earlier
+            # layer's wgrad is still deferred
+            side.wait_stream(torch.cuda.current_stream(p.grad.device))
             with torch.cuda.stream(side):
                 work = dist.all_reduce(p.grad, op=self.op, group=self.group, async_op=True)
         else:
             work = dist.all_reduce(p.grad, op=self.op, group=self.group, async_op=True)
         self.pending.append((p.grad, work))
 
+    # ------------------------------------------------------------------ end of the backward pass
     def reduce(self):
-        """Call after backward(): waits for the overlapped reductions, reduces everything else
-        in one flat bucket and divides by the world size (gradient of the global-batch mean)."""
+        """Call after backward(): launches what is still unlaunched, waits for the overlapped reductions, splits the
+        merged buffers, reduces everything else in one flat bucket and divides by the world size (gradient of the
+        global-batch mean)."""
         if self.world <= 1:
             return
         done = set()
+        used = [(m, s) for m, s in self._slots if s.state != 0]
+        if used:
+            dev = used[0][0].weight.device
+            for b in range(len(self.flat)):
+                if self._bucket_left[b] != -1 and any(s.bucket == b for _, s in used):
+                    self._bucket_left[b] = 0
+                    self._launch_bucket(b, dev)
         for g, work in self.pending:
             work.wait()
             if not self.avg:
                 g.div_(self.world)
             done.add(g.data_ptr())
         self.pending = []
+        lib = _lib.load() if used else None
+        for m, s in used:
+            view = s.view(m.weight)
+            done.add(view.data_ptr())
+            gW = m.weight.grad
+            if s.state == 2:
+                # m = dW + dP back into the pair the optimizers see: dW in place in its slot, dP into the tensor the
+                # backward pass handed to autograd as .piggymask.grad (left unwritten there)
+                gP = m.piggymask.grad if m.piggymask is not None else None
+                with torch.cuda.device(view.device):
+                    _lib.check(lib.cpgb_split_merged_grad(_lib.ptr(view), _lib.ptr(s.fuse.tmask), s.n, s.fuse.cur,
+                                                          _lib.ptr(view), _lib.ptr(gP), _lib.stream_ptr()),
+                               'cpgb_split_merged_grad')
+                if gP is not None:
+                    done.add(gP.data_ptr())
+            if gW is not None and gW.data_ptr() != view.data_ptr():
+                gW.copy_(view)           # autograd cloned instead of adopting the slot view (someone held a reference)
+                done.add(gW.data_ptr())
+            s.state, s.fuse = 0, None
+        for b in range(len(self.flat)):
+            self._bucket_left[b] = len(self._bucket_layers[b])
         rest = [p.grad for p in self.params if p.grad is not None and p.grad.data_ptr() not in done]
         if rest:
-            # one flat bucket for the ~75 small tensors (BN, biases, heads, the first conv layers); packed
-            # and unpacked with multi-tensor kernels instead of one launch per tensor
+            # one flat bucket for the ~75 small tensors (BN, biases, heads); packed and unpacked with multi-tensor
+            # kernels instead of one launch per tensor
             flat = torch.cat([g.reshape(-1) for g in rest])
             dist.all_reduce(flat, op=self.op, group=self.group)
             if not self.avg:
@@ -103,6 +216,9 @@ class GradAllReducer:
         for h in self._hooks:
             h.remove()
         self._hooks = []
+        for m, _ in self._slots:
+            m._cpg_grad_slot = None
+        self._slots = []
 
 
 def assert_masks_identical(masks, group=None):

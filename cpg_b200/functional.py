@@ -27,6 +27,63 @@ def _dense4(t):
     return t.contiguous()
 
 
+# ---- TF32 exactness of activation operands --------------------------------------------------------------
+# The tensor core truncates fp32 operands to TF32.  Tensors produced by our own kernels with round-to-nearest
+# (cpg_b200.fused_norm with tf32_out, round_tf32 below) are tagged; anything else is rounded once per pass
+# before it is handed to the tcgen05 kernels (include/cpgb200.h, CPGB_FLAG_X_TF32 / CPGB_FLAG_DY_TF32).
+_TF32_PRESERVING = frozenset((
+    'ViewBackward0', 'ReshapeAliasBackward0', 'UnsafeViewBackward0', 'AliasBackward0', 'ReluBackward0',
+    'MaxPool2DWithIndicesBackward0', 'SqueezeBackward0', 'SqueezeBackward1', 'UnsqueezeBackward0',
+    'TransposeBackward0', 'PermuteBackward0', 'TBackward0', 'CloneBackward0', 'SliceBackward0', 'SelectBackward0'))
+
+
+def mark_tf32(t):
+    """Tag `t` as holding TF32-representable values (valid until the next in-place modification)."""
+    t._cpgb_tf32 = t._version
+    return t
+
+
+def is_tf32(t):
+    """True when every element of `t` is known to be TF32-representable: tagged by its producer and not
+    modified in place since, or derived from such a tensor through value-preserving autograd nodes (view,
+    reshape, ReLU, max-pool, ...)."""
+    tag = getattr(t, '_cpgb_tf32', None)
+    if tag is not None and tag == t._version:
+        return True
+    fn = t.grad_fn
+    for _ in range(8):
+        if fn is None:
+            return False
+        if getattr(fn, 'cpgb_tf32_out', False):
+            return True
+        if type(fn).__name__ not in _TF32_PRESERVING or not fn.next_functions:
+            return False
+        fn = fn.next_functions[0][0]
+    return False
+
+
+def _is_dense(t):
+    return t.is_contiguous() or (t.dim() == 4 and t.is_contiguous(memory_format=CL))
+
+
+def round_tf32(lib, t):
+    """A tagged copy of the dense tensor `t` (same strides) rounded to the nearest TF32 value."""
+    out = torch.empty_like(t)          # preserves the strides of dense tensors
+    with torch.cuda.device(t.device):
+        _lib.check(lib.cpgb_round_tf32(_lib.ptr(t), _lib.ptr(out), t.numel(), _lib.stream_ptr()), 'cpgb_round_tf32')
+    return mark_tf32(out)
+
+
+def _prepare_operand(lib, t, exact, needed):
+    """(tensor to hand to the kernels, exact?) -- rounds `t` when a tcgen05 pass will read it and it is not
+    known to be exact.  Non-dense views are left to the library's own rounding pre-pass."""
+    if exact or not needed:
+        return t, exact
+    if _is_dense(t):
+        return round_tf32(lib, t), True
+    return t, False
+
+
 def _stage(lib, d, w, p, threshold, prestaged=None):
     """Build the tensor-core weight operand (masked, TF32, [K][RS][Cp]) for descriptor d, or
     None when d takes the CUDA-core path (which evaluates the mask while loading tiles).
@@ -104,6 +161,15 @@ def _defer(device, tensors):
     entry[1].extend(t for t in tensors if t is not None)
 
 
+def _backward_operands(lib, d, dy, dy_exact, x_exact, need_dx, need_w):
+    """Round dy once for dgrad + wgrad when a tcgen05 pass reads it; set the descriptor flags."""
+    tc_d = need_dx and lib.cpgb_uses_tensor_cores(d, 1)
+    tc_w = need_w and lib.cpgb_uses_tensor_cores(d, 2)
+    dy, dy_exact = _prepare_operand(lib, dy, dy_exact, bool(tc_d or tc_w))
+    d.flags = (_lib.FLAG_X_TF32 if x_exact else 0) | (_lib.FLAG_DY_TF32 if dy_exact else 0)
+    return dy
+
+
 def _backward_kernels(lib, ctx, d, x, dy, w, p, threshold, staged, need_dx, need_w, has_bias, dx):
     """dgrad (+) wgrad with the fused epilogue for descriptor d.  Everything is allocated on the
     current stream.  The wgrad launch is forked onto a side stream: wgrad(l) only reads x(l) and dy(l),
@@ -116,11 +182,6 @@ def _backward_kernels(lib, ctx, d, x, dy, w, p, threshold, staged, need_dx, need
         main = torch.cuda.current_stream()
         wbytes = lib.cpgb_workspace_bytes(d)
         ws_d = _ws(wbytes, device) if need_dx else None
-        if need_w:
-            ws_w = _ws(wbytes, device)
-            dW = torch.empty_like(w)
-            dP = torch.empty_like(w) if p is not None else None
-            db = torch.empty(w.shape[0], dtype=torch.float32, device=device) if has_bias else None
         fuse = ctx.fuse
         in_backward = torch._C._current_graph_task_id() != -1
         # a parameter that already holds a gradient gets `grad += dW` on the main stream as soon as this
@@ -128,22 +189,48 @@ def _backward_kernels(lib, ctx, d, x, dy, w, p, threshold, staged, need_dx, need
         mod = ctx.module
         fresh = mod is not None and all(getattr(mod, n, None) is None or getattr(mod, n).grad is None
                                         for n in ('weight', 'piggymask', 'bias'))
+        wd = fuse.weight_decay if fuse is not None else 0.0
+        if fuse is not None and mod is not None and not fresh:
+            # gradient accumulation: the reference adds wd*W ONCE, after the last backward pass
+            # (utils/prune.py:203).  If an earlier pass of this window already went through the fused epilogue
+            # the term is in .grad: mask only.  Otherwise (.grad did not come from us) hand out the raw
+            # autograd values and let do_weight_decay_and_make_grads_zero finish them.
+            if mod._cpg_grads_final:
+                wd = 0.0
+            else:
+                fuse = None
         defer = OVERLAP_BACKWARD and DEFER_JOIN and need_w and in_backward and fresh
         fork = OVERLAP_BACKWARD and need_w and (need_dx or defer)
         if need_w:
+            mode = fuse.mode if fuse is not None else _lib.GRAD_RAW
+            # data parallel (cpg_b200.ddp.GradAllReducer): the epilogue writes straight into the layer's slot of a
+            # flat gradient bucket -- .weight.grad becomes a view of it -- and, with a piggymask, writes the MERGED
+            # dW + dP (disjoint supports after the masking) so that one buffer travels through the all-reduce
+            slot = getattr(mod, '_cpg_grad_slot', None) if (mod is not None and fresh and in_backward) else None
+            if slot is not None and (slot.n != w.numel() or slot.reducer.flat[slot.bucket].device != w.device):
+                slot = None
+            ws_w = _ws(wbytes, device)
+            dW = slot.view(w) if slot is not None else torch.empty_like(w)
+            dP = torch.empty_like(w) if p is not None else None
+            db = torch.empty(w.shape[0], dtype=torch.float32, device=device) if has_bias else None
+            merged = slot is not None and p is not None and fuse is not None
             wstream = main
             if fork:
                 wstream = _side_stream(device)
                 wstream.wait_stream(main)
-            mode = fuse.mode if fuse is not None else _lib.GRAD_RAW
             _lib.check(lib.cpgb_conv2d_wgrad_fused(
                 d, _lib.ptr(x), _lib.ptr(dy), _lib.ptr(w), _lib.ptr(p),
                 _lib.ptr(fuse.tmask) if fuse is not None else None,
-                fuse.cur if fuse is not None else 0, fuse.weight_decay if fuse is not None else 0.0, mode,
-                _lib.ptr(dW), _lib.ptr(dP), _lib.ptr(db), threshold, _lib.ptr(ws_w), ws_w.numel(),
+                fuse.cur if fuse is not None else 0, wd, (mode | _lib.GRAD_MERGED) if merged else mode,
+                _lib.ptr(dW), None if merged else _lib.ptr(dP), _lib.ptr(db), threshold, _lib.ptr(ws_w), ws_w.numel(),
                 wstream.cuda_stream), 'cpgb_conv2d_wgrad_fused')
-            if fuse is not None and ctx.module is not None:
-                ctx.module._cpg_grads_final = True
+            if fuse is not None and mod is not None:
+                mod._cpg_grads_final = True
+            if slot is not None:
+                # dP (merged case) is filled by the reducer's split after the all-reduce; it must not be kept
+                # referenced here (AccumulateGrad would clone instead of adopting it)
+                slot.state, slot.fuse = (2 if merged else 1), fuse
+                slot.reducer.layer_done(slot, device)
         if need_dx:
             _lib.check(lib.cpgb_conv2d_dgrad(d, _lib.ptr(dy), _lib.ptr(w), _lib.ptr(p), _lib.ptr(dx),
                                              threshold, _lib.ptr(staged), _lib.ptr(ws_d), ws_d.numel(),
@@ -183,7 +270,7 @@ class MaskedConv2dFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, piggymask, bias, stride, padding, dilation, groups, threshold, fuse,
-                module, channels_last_out, prestaged=None):
+                module, channels_last_out, prestaged=None, x_exact=False):
         lib = _lib.load()
         _check_params(weight, piggymask, bias)
         if x.dim() != 4:
@@ -219,6 +306,11 @@ class MaskedConv2dFn(torch.autograd.Function):
             else torch.contiguous_format
         y = torch.empty((N, K, P, Q), dtype=torch.float32, device=x.device, memory_format=fmt)
         d = _lib.conv_desc(x.shape, x.stride(), w.shape, y.shape, y.stride(), stride, padding, dilation, groups)
+        # TF32 operands are rounded to nearest, once, and the rounded copy is what the backward pass reuses
+        need_w = weight.requires_grad or (piggymask is not None and piggymask.requires_grad)
+        uses_tc = lib.cpgb_uses_tensor_cores(d, 0) or (need_w and lib.cpgb_uses_tensor_cores(d, 2))
+        x, x_exact = _prepare_operand(lib, x, bool(x_exact), bool(uses_tc))
+        d.flags = _lib.FLAG_X_TF32 if x_exact else 0
         with torch.cuda.device(x.device):
             staged, ws = _stage(lib, d, w, p, threshold, prestaged)
             _lib.check(lib.cpgb_conv2d_fprop(d, _lib.ptr(x), _lib.ptr(w), _lib.ptr(p), _lib.ptr(b),
@@ -229,7 +321,7 @@ class MaskedConv2dFn(torch.autograd.Function):
         ctx.staged = staged     # masked TF32 operand, shared with this step's dgrad
         ctx.has_bias = bias is not None
         ctx.geom = (stride, padding, dilation, groups, threshold)
-        ctx.fuse, ctx.module = fuse, module
+        ctx.fuse, ctx.module, ctx.x_exact = fuse, module, x_exact
         return y
 
     @staticmethod
@@ -238,23 +330,25 @@ class MaskedConv2dFn(torch.autograd.Function):
         lib = _lib.load()
         x, w, p = ctx.saved_tensors
         stride, padding, dilation, groups, threshold = ctx.geom
+        dy_exact = is_tf32(dy)        # layout copies below keep the values
         dy = _dense4(dy)
         if x.is_contiguous(memory_format=CL) and not dy.is_contiguous(memory_format=CL):
             dy = dy.contiguous(memory_format=CL)
         d = _lib.conv_desc(x.shape, x.stride(), w.shape, dy.shape, dy.stride(), stride, padding, dilation, groups)
         need_dx = ctx.needs_input_grad[0]
         need_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
+        dy = _backward_operands(lib, d, dy, dy_exact, ctx.x_exact, need_dx, need_w)
         dx = torch.empty_strided(x.shape, x.stride(), dtype=x.dtype, device=x.device) if need_dx else None
         dW, dP, db = _backward_kernels(lib, ctx, d, x, dy, w, p, threshold, ctx.staged, need_dx, need_w,
                                        ctx.has_bias, dx)
-        return dx, dW, dP, db, None, None, None, None, None, None, None, None, None
+        return dx, dW, dP, db, None, None, None, None, None, None, None, None, None, None
 
 
 class MaskedLinearFn(torch.autograd.Function):
     """y = linear(x, (piggymask > thr) * weight, bias)  -- models/layers.py:184-194."""
 
     @staticmethod
-    def forward(ctx, x, weight, piggymask, bias, threshold, fuse, module, prestaged=None):
+    def forward(ctx, x, weight, piggymask, bias, threshold, fuse, module, prestaged=None, x_exact=False):
         lib = _lib.load()
         _check_params(weight, piggymask, bias)
         if x.dtype != torch.float32 or not x.is_cuda:
@@ -272,6 +366,10 @@ class MaskedLinearFn(torch.autograd.Function):
         y = torch.empty((*x.shape[:-1], O), dtype=torch.float32, device=x.device)
         d = _lib.ConvDesc()
         lib.cpgb_linear_desc(d, M, I, O)
+        need_w = weight.requires_grad or (piggymask is not None and piggymask.requires_grad)
+        uses_tc = lib.cpgb_uses_tensor_cores(d, 0) or (need_w and lib.cpgb_uses_tensor_cores(d, 2))
+        x2, x_exact = _prepare_operand(lib, x2, bool(x_exact), bool(uses_tc))
+        d.flags = _lib.FLAG_X_TF32 if x_exact else 0
         with torch.cuda.device(x.device):
             staged, ws = _stage(lib, d, w, p, threshold, prestaged)
             _lib.check(lib.cpgb_conv2d_fprop(d, _lib.ptr(x2), _lib.ptr(w), _lib.ptr(p), _lib.ptr(b), _lib.ptr(y),
@@ -281,7 +379,7 @@ class MaskedLinearFn(torch.autograd.Function):
         ctx.save_for_backward(x2, w, p)
         ctx.staged = staged
         ctx.has_bias, ctx.threshold, ctx.fuse, ctx.module = bias is not None, threshold, fuse, module
-        ctx.x_shape = x.shape
+        ctx.x_shape, ctx.x_exact = x.shape, x_exact
         return y
 
     @staticmethod
@@ -296,11 +394,12 @@ class MaskedLinearFn(torch.autograd.Function):
         lib.cpgb_linear_desc(d, M, I, O)
         need_dx = ctx.needs_input_grad[0]
         need_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
+        dy2 = _backward_operands(lib, d, dy2, is_tf32(dy), ctx.x_exact, need_dx, need_w)
         dx2 = torch.empty_like(x2) if need_dx else None
         dW, dP, db = _backward_kernels(lib, ctx, d, x2, dy2, w, p, ctx.threshold, ctx.staged, need_dx, need_w,
                                        ctx.has_bias, dx2)
         dx = dx2.reshape(ctx.x_shape) if need_dx else None
-        return dx, dW, dP, db, None, None, None, None
+        return dx, dW, dP, db, None, None, None, None, None
 
 
 class Binarizer(torch.autograd.Function):

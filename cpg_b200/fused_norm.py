@@ -23,13 +23,15 @@ import torch.nn.functional as F
 from torch.autograd.function import once_differentiable
 
 from . import _lib
+from .functional import mark_tf32
 
 CL = torch.channels_last
 
 
 class _BNReLUFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, running_mean, running_var, nbt, training, momentum, eps, relu, pool):
+    def forward(ctx, x, weight, bias, running_mean, running_var, nbt, training, momentum, eps, relu, pool,
+                tf32_out=False):
         lib = _lib.load()
         if not x.is_contiguous(memory_format=CL):
             x = x.contiguous(memory_format=CL)
@@ -51,11 +53,14 @@ class _BNReLUFn(torch.autograd.Function):
             _lib.check(lib.cpgb_bn_relu_fwd(
                 _lib.ptr(x), M, C, _lib.ptr(w), _lib.ptr(b), _lib.ptr(running_mean), _lib.ptr(running_var),
                 _lib.ptr(nbt) if training else None, 1 if training else 0, float(momentum), float(eps), 1 if relu else 0,
-                H if pool else 0, W if pool else 0, _lib.ptr(y),
+                H if pool else 0, W if pool else 0, 1 if tf32_out else 0, _lib.ptr(y),
                 _lib.ptr(mean) if training else None, _lib.ptr(rstd) if training else None,
                 _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), 'cpgb_bn_relu_fwd')
         ctx.save_for_backward(x, w, b, mean, rstd)
         ctx.cfg = (bool(training), bool(relu), weight is not None, bias is not None, bool(pool))
+        # y (and dx in backward) hold TF32-representable values: the masked convolutions on either side skip their
+        # rounding pass (cpg_b200.functional.is_tf32 reads this attribute off y.grad_fn)
+        ctx.cpgb_tf32_out = bool(tf32_out)
         return y
 
     @staticmethod
@@ -76,25 +81,30 @@ class _BNReLUFn(torch.autograd.Function):
             _lib.check(lib.cpgb_bn_relu_bwd(
                 _lib.ptr(x), _lib.ptr(dy), M, C, _lib.ptr(w), _lib.ptr(b), _lib.ptr(mean), _lib.ptr(rstd),
                 1 if training else 0, 1 if relu else 0, H if pool else 0, W if pool else 0,
-                _lib.ptr(dx), _lib.ptr(dg), _lib.ptr(db),
+                1 if ctx.cpgb_tf32_out else 0, _lib.ptr(dx), _lib.ptr(dg), _lib.ptr(db),
                 _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), 'cpgb_bn_relu_bwd')
-        return dx, dg, db, None, None, None, None, None, None, None, None
+        if ctx.cpgb_tf32_out:
+            mark_tf32(dx)
+        return dx, dg, db, None, None, None, None, None, None, None, None, None
 
 
 class FusedBatchNormReLU2d(nn.BatchNorm2d):
     """``nn.BatchNorm2d`` with an optional fused ReLU (``relu=True``: y = relu(batch_norm(x)))."""
 
     def __init__(self, num_features, eps=1e-5, momentum=0.1, affine=True, track_running_stats=True, relu=False,
-                 pool=False, device=None, dtype=None):
+                 pool=False, tf32_out=False, device=None, dtype=None):
         super().__init__(num_features, eps, momentum, affine, track_running_stats, device=device, dtype=dtype)
         self.relu = bool(relu)
         self.pool = bool(pool)        # also apply the nn.MaxPool2d(kernel_size=2, stride=2) that follows
+        # store y / dx rounded to the nearest TF32 value: what the tcgen05 convolutions on either side would
+        # otherwise do in a pass of their own (relative change of y <= 2^-11); fuse_bn_relu turns it on
+        self.tf32_out = bool(tf32_out)
 
     @classmethod
-    def from_bn(cls, bn, relu, pool=False):
+    def from_bn(cls, bn, relu, pool=False, tf32_out=False):
         """A fused module over the SAME parameter / buffer tensors as `bn` (state_dict keys unchanged)."""
         new = cls(bn.num_features, bn.eps, bn.momentum, bn.affine, bn.track_running_stats, relu=relu, pool=pool,
-                  device=torch.device('meta'))
+                  tf32_out=tf32_out, device=torch.device('meta'))
         for name in ('weight', 'bias'):
             new._parameters[name] = bn._parameters.get(name)
         for name in ('running_mean', 'running_var', 'num_batches_tracked'):
@@ -103,7 +113,7 @@ class FusedBatchNormReLU2d(nn.BatchNorm2d):
         return new
 
     def extra_repr(self):
-        return super().extra_repr() + f', relu={self.relu}, pool={self.pool}'
+        return super().extra_repr() + f', relu={self.relu}, pool={self.pool}, tf32_out={self.tf32_out}'
 
     def _fast(self, x):
         if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] % 4 == 0 and x.numel() > 0):
@@ -134,16 +144,21 @@ class FusedBatchNormReLU2d(nn.BatchNorm2d):
         rv = self.running_var if (not training or update) else None
         pool = self.pool and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0
         y = _BNReLUFn.apply(x, self.weight, self.bias, rm, rv, nbt, training,
-                            self.momentum if self.momentum is not None else 0.0, self.eps, self.relu, pool)
+                            self.momentum if self.momentum is not None else 0.0, self.eps, self.relu, pool,
+                            self.tf32_out)
+        if self.tf32_out:
+            mark_tf32(y)
         return F.max_pool2d(y, 2, 2) if (self.pool and not pool) else y
 
 
-def fuse_bn_relu(model, pool=True):
+def fuse_bn_relu(model, pool=True, tf32_out=True):
     """Swap every ``nn.BatchNorm2d`` of `model` for a ``FusedBatchNormReLU2d`` sharing its tensors; inside
     ``nn.Sequential`` containers a directly following ``nn.ReLU`` is folded in and replaced by
     ``nn.Identity`` (child indices, parameter names and mask keys are unchanged); with `pool`, a
     ``nn.MaxPool2d(kernel_size=2, stride=2)`` right after that ReLU is folded in as well.  Returns the number of
-    (batch-norm, relu) pairs and of lone batch-norms converted."""
+    (batch-norm, relu) pairs and of lone batch-norms converted.  `tf32_out` (default on): the converted modules
+    store their outputs and input gradients rounded to TF32, which is what the masked convolutions they sit
+    between consume (see FusedBatchNormReLU2d.tf32_out)."""
     pairs = lone = 0
     for parent in list(model.modules()):
         names = list(parent._modules.keys())
@@ -155,7 +170,7 @@ def fuse_bn_relu(model, pool=True):
             relu = type(nxt) is nn.ReLU
             nxt2 = parent._modules[names[i + 2]] if (relu and pool and i + 2 < len(names)) else None
             do_pool = _is_pool2x2(nxt2)
-            parent._modules[name] = FusedBatchNormReLU2d.from_bn(m, relu=relu, pool=do_pool)
+            parent._modules[name] = FusedBatchNormReLU2d.from_bn(m, relu=relu, pool=do_pool, tf32_out=tf32_out)
             if relu:
                 parent._modules[names[i + 1]] = nn.Identity()
                 pairs += 1

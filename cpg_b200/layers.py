@@ -13,7 +13,7 @@ from torch.nn.parameter import Parameter
 
 from . import _lib
 from .functional import (DEFAULT_THRESHOLD, Binarizer, FuseCtx, MaskedConv2dFn, MaskedLinearFn,
-                         Ternarizer)
+                         Ternarizer, is_tf32)
 
 __all__ = ['DEFAULT_THRESHOLD', 'Binarizer', 'Ternarizer', 'SharableConv2d', 'SharableLinear']
 
@@ -33,6 +33,7 @@ class _SharableBase(nn.Module):
         self._cpg_name = None
         self._cpg_grads_final = False
         self._cpg_prestaged = None    # (buffer, weight ptr, piggymask ptr): one-shot, set by the model-level hook
+        self._cpg_grad_slot = None    # set by cpg_b200.ddp.GradAllReducer: where the wgrad epilogue writes
 
     def _finish_init(self, threshold_fn, threshold):
         # Give real-valued mask weights per task to manage the shared part from previous tasks:
@@ -52,7 +53,24 @@ class _SharableBase(nn.Module):
         pr = ref() if ref is not None else None
         if pr is None or not torch.is_grad_enabled():
             return None
-        return pr._fuse_ctx_for(self._cpg_name)
+        # nn.DataParallel replicas (CPG_cifar100_main_normal.py:199) copy __dict__, so they see the pruner too,
+        # but their weights are non-leaf views on other devices, their gradients are summed by autograd's
+        # ReduceAddCoalesced afterwards, and the task mask lives on the pruner's device: a replica hands out the
+        # plain autograd gradients (immediate stream join) and the pruner finishes them once on the original.
+        w = self.weight
+        if getattr(self, '_is_replica', False) or not isinstance(w, Parameter) or not w.is_leaf:
+            return None
+        fc = pr._fuse_ctx_for(self._cpg_name)
+        if fc is not None and fc.tmask.device != w.device:
+            return None
+        return fc
+
+    def _owner(self, weight):
+        """`self` when this module owns leaf parameters the backward pass may finalise (fused epilogue flag,
+        gradient slots, deferred stream join); None for nn.DataParallel replicas and rebound weights."""
+        if weight is not self.weight or getattr(self, '_is_replica', False):
+            return None
+        return self if (isinstance(weight, Parameter) and weight.is_leaf) else None
 
     def _take_prestaged(self, weight, piggy):
         """The operand the model-level batched staging built for THIS forward pass, if any (consumed:
@@ -117,7 +135,7 @@ class SharableConv2d(_SharableBase):
         pre = self._take_prestaged(weight, piggy) if weight is self.weight else None
         return MaskedConv2dFn.apply(input, weight, piggy, self.bias, self.stride, self.padding,
                                     self.dilation, self.groups, float(self.info['threshold']), fuse,
-                                    self if fuse is not None else None, OUTPUT_CHANNELS_LAST, pre)
+                                    self._owner(weight), OUTPUT_CHANNELS_LAST, pre, is_tf32(input))
 
     def __repr__(self):
         s = ('{name} ({in_channels}, {out_channels}, kernel_size={kernel_size}'
@@ -158,7 +176,7 @@ class SharableLinear(_SharableBase):
         fuse = self._fuse_ctx() if piggy is self.piggymask and weight is self.weight else None
         pre = self._take_prestaged(weight, piggy) if weight is self.weight else None
         return MaskedLinearFn.apply(input, weight, piggy, self.bias, float(self.info['threshold']), fuse,
-                                    self if fuse is not None else None, pre)
+                                    self._owner(weight), pre, is_tf32(input))
 
     def __repr__(self):
         return self.__class__.__name__ + '(' \

@@ -75,8 +75,23 @@ class SparsePruner(object):
             module._cpg_grads_final = False
 
         if self._stage_hook is None:
-            self._stage_hook = self.model.register_forward_pre_hook(self._prestage_hook)
-            self._stage_post_hook = self.model.register_forward_hook(self._poststage_hook)
+            # The hooks hold the pruner weakly (the model must not keep a discarded pruner and its staging
+            # buffers alive) and there is one pair per model: a new pruner on the same model replaces the
+            # previous one's hooks instead of stacking a second staging pass on every forward.
+            for h in getattr(self.model, '_cpg_stage_hooks', ()):
+                h.remove()
+
+            def pre(model, inputs, _ref=ref):
+                pr = _ref()
+                return pr._prestage_hook(model, inputs) if pr is not None else None
+
+            def post(model, inputs, output, _ref=ref):
+                pr = _ref()
+                return pr._poststage_hook(model, inputs, output) if pr is not None else None
+
+            self._stage_hook = self.model.register_forward_pre_hook(pre)
+            self._stage_post_hook = self.model.register_forward_hook(post)
+            self.model._cpg_stage_hooks = (self._stage_hook, self._stage_post_hook)
 
     def detach(self):
         for name, module in self._sharable():
@@ -88,6 +103,8 @@ class SparsePruner(object):
             self._stage_hook = None
             self._stage_post_hook.remove()
             self._stage_post_hook = None
+            if getattr(self.model, '_cpg_stage_hooks', None) is not None:
+                self.model._cpg_stage_hooks = ()
 
     def _prestage_hook(self, model, inputs):
         """Forward pre-hook of the whole model: the masked TF32 weight operands of ALL sharable layers

@@ -21,7 +21,7 @@ class View(nn.Module):
         self.shape = shape
 
     def forward(self, x):
-        return x.reshape(*self.shape) if not x.is_contiguous() else x.view(*self.shape)
+        return x.reshape(*self.shape)
 
 
 def make_features(conv_cls, linear_cls, cfg=VGG16_CIFAR_CFG, width=1.0, batch_norm=True):

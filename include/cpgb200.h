@@ -42,11 +42,24 @@ extern "C" {
 #define CPGB_GRAD_RAW 0      /* autograd contract: dW = g*b, dP = g*W  (models/layers.py:21-23,103) */
 #define CPGB_GRAD_FINETUNE 1 /* + utils/prune.py:203-208: dW=(g*b+wd*W)[T==cur]; dP=g*W[1<=T<cur]    */
 #define CPGB_GRAD_PRUNE 2    /* + utils/prune.py:203-205,209-210: same dW; dP = 0                     */
+/* or'ed into FINETUNE / PRUNE for cpgb_conv2d_wgrad_fused: after a6 dW and dP have disjoint support (T==cur vs
+ * 1<=T<cur), so ONE buffer m = dW + dP is written to `dW` (pass dP = NULL) and travels through the data-parallel
+ * all-reduce; cpgb_split_merged_grad restores the pair afterwards (SURVEY 8e "Collective"). */
+#define CPGB_GRAD_MERGED 4
 
 /* kernel-path selection (process-wide, for tests/benchmarks) */
 #define CPGB_PATH_AUTO 0     /* tcgen05 implicit GEMM when eligible, else CUDA-core kernels */
 #define CPGB_PATH_SIMT 1     /* CUDA-core (fp32 FFMA) kernels only                         */
 #define CPGB_PATH_TCGEN05 2  /* tcgen05 only; CPGB_ENOTELIGIBLE when the shape is not      */
+
+/* cpgb_conv_desc.flags.  The tcgen05 kernels multiply TF32 operands (fp32 storage, 10 explicit mantissa
+ * bits) and the tensor core TRUNCATES whatever fp32 bits it is handed.  To get round-to-nearest TF32 -- an
+ * unbiased result -- the library rounds x (fprop, wgrad) and dy (dgrad, wgrad) into `ws` before the GEMM
+ * unless the caller promises that the tensor already holds TF32-representable values, e.g. because it was
+ * produced by cpgb_bn_relu_fwd / _bwd with tf32_out != 0 or by cpgb_round_tf32.  The CUDA-core and stem
+ * kernels compute in fp32 and ignore the flags. */
+#define CPGB_FLAG_X_TF32 1   /* x  holds TF32-representable values: no rounding pre-pass */
+#define CPGB_FLAG_DY_TF32 2  /* dy holds TF32-representable values: no rounding pre-pass */
 
 /* Geometry of one SharableConv2d call: F.conv2d(input, weight, bias, stride, padding,
  * dilation, groups) at models/layers.py:108.  SharableLinear (models/layers.py:194) is the
@@ -56,6 +69,7 @@ typedef struct cpgb_conv_desc {
   int32_t K, R, S;             /* weight [K, C/groups, R, S]               */
   int32_t P, Q;                /* output [N, K, P, Q]                      */
   int32_t stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, groups;
+  int32_t flags;               /* CPGB_FLAG_* (0 is always valid)          */
   int64_t xs[4];               /* element strides of input  (n, c, h, w)   */
   int64_t ys[4];               /* element strides of output (n, k, p, q)   */
 } cpgb_conv_desc;
@@ -71,8 +85,16 @@ int64_t cpgb_launch_count(void);
 void cpgb_linear_desc(cpgb_conv_desc *d, int32_t M, int32_t I, int32_t O);
 
 /* Scratch bytes the conv/linear entry points need for descriptor `d` (max over
- * fprop/dgrad/wgrad). */
+ * fprop/dgrad/wgrad; depends on d->flags: a tensor the library must round first needs room for the copy). */
 size_t cpgb_workspace_bytes(const cpgb_conv_desc *d);
+
+/* 1 when pass `op` (0 fprop, 1 dgrad, 2 wgrad) of descriptor `d` runs on the tcgen05 kernels under the
+ * current path selection (so that a caller can pre-round its operands once and share them between passes). */
+int cpgb_uses_tensor_cores(const cpgb_conv_desc *d, int32_t op);
+
+/* out[i] = round-to-nearest-TF32(in[i]) (cvt.rna.tf32.f32: ties away from zero, NaN/Inf kept); in == out is
+ * allowed.  What the masked weight operand gets inside cpgb_stage_weights, for activations. */
+int cpgb_round_tf32(const float *in, float *out, int64_t n, void *stream);
 
 /* a1: Binarizer.forward, models/layers.py:15-19.  b = (p > thr) ? 1 : 0, NaN -> NaN. */
 int cpgb_binarize(const float *piggy, float *out, int64_t n, float thr, void *stream);
@@ -196,8 +218,8 @@ int cpgb_split_merged_grad(const float *merged, const uint8_t *tmask, int64_t n,
 size_t cpgb_bn_workspace_bytes(int64_t M, int32_t C);
 int cpgb_bn_relu_fwd(const float *x, int64_t M, int32_t C, const float *gamma, const float *beta, float *running_mean,
                      float *running_var, int64_t *num_batches_tracked, int32_t training, float momentum, float eps,
-                     int32_t relu, int32_t pool_h, int32_t pool_w, float *y, float *save_mean, float *save_rstd, void *ws,
-                     size_t ws_bytes, void *stream);
+                     int32_t relu, int32_t pool_h, int32_t pool_w, int32_t tf32_out, float *y, float *save_mean,
+                     float *save_rstd, void *ws, size_t ws_bytes, void *stream);
 /* Backward of the above: with g = dy * [y > 0] (relu) or dy,  xhat = (x - mean) * rstd:
  *   dbeta = sum g;  dgamma = sum g * xhat;
  *   training: dx = gamma * rstd * (g - mean(g) - xhat * mean(g * xhat));   evaluation: dx = gamma * rstd * g.
@@ -205,7 +227,8 @@ int cpgb_bn_relu_fwd(const float *x, int64_t M, int32_t C, const float *gamma, c
  * dgamma / dbeta may be NULL. */
 int cpgb_bn_relu_bwd(const float *x, const float *dy, int64_t M, int32_t C, const float *gamma, const float *beta,
                      const float *mean, const float *rstd, int32_t training, int32_t relu, int32_t pool_h,
-                     int32_t pool_w, float *dx, float *dgamma, float *dbeta, void *ws, size_t ws_bytes, void *stream);
+                     int32_t pool_w, int32_t tf32_out, float *dx, float *dgamma, float *dbeta, void *ws, size_t ws_bytes,
+                     void *stream);
 
 #ifdef __cplusplus
 }

@@ -206,6 +206,18 @@ def pruning_mask(w: torch.Tensor, t: torch.Tensor, cur: int, ratio: float):
 
 
 # ----------------------------------------------------------------------------
+# a11  one_shot_prune                                   utils/prune.py:94-109
+# ----------------------------------------------------------------------------
+def one_shot_prune(weights, masks, cur: int, ratio: float):
+    """utils/prune.py:94-109 over parallel lists of layer weights / task masks (named_modules order): a7 at the
+    fixed ratio (:102-105), then W[T == 0] = 0 (:108) -- every free element, not only the freshly pruned ones."""
+    for w, t in zip(weights, masks):
+        pruning_mask(w, t, cur, ratio)
+        w[t.eq(0)] = 0.0
+    return weights, masks
+
+
+# ----------------------------------------------------------------------------
 # a8  schedule                                          utils/prune.py:55-92
 # ----------------------------------------------------------------------------
 def adjust_sparsity(step, begin, end, initial_sparsity, target_sparsity, exponent=3):

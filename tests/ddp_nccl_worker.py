@@ -1,0 +1,173 @@
+"""Worker of tests/test_ddp_nccl.py -- run under torchrun with >= 2 ranks on one node (NCCL):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29641 \
+        tests/ddp_nccl_worker.py
+
+SURVEY 8e "Parity check": 1-GPU batch B against G-GPU B/G gradients with the PRODUCT layers, pruner, fused BN kernels,
+gradient buckets (merged dW + dP in the task-2 regime), eagerly and from a CUDA graph; then a prune event and
+bit-identical task masks on every rank.  Batch-norm runs on its running statistics here so that samples are
+independent (per-shard batch statistics are what nn.DataParallel does too, and make B vs B/G differ by design).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def rel(a, b):
+    a, b = a.detach().double(), b.detach().double()
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
+
+
+def build(regime, device, mode='finetune'):
+    import cpg_b200.layers as nl
+    from cpg_b200.fused_norm import fuse_bn_relu
+    from cpg_b200.prune import SparsePruner
+    from cpg_b200.vgg_cifar import VGGCifar
+    from tests.toy import Wrap, make_args
+    torch.manual_seed(1)
+    model = VGGCifar(nl.SharableConv2d, nl.SharableLinear, width=0.5)
+    model.add_dataset('t1', 5)
+    model.add_dataset('t2', 5)
+    model.set_dataset('t2' if regime == 'task2' else 't1')
+    model = model.to(device)
+    fuse_bn_relu(model)
+    cur = 2 if regime == 'task2' else 1
+    rng = np.random.RandomState(7)
+    masks = {}
+    for n, m in model.named_modules():
+        if isinstance(m, (nl.SharableConv2d, nl.SharableLinear)):
+            shape = tuple(m.weight.shape)
+            if regime == 'task1':
+                t = np.ones(shape, dtype=np.uint8)
+            else:
+                t = np.where(rng.rand(*shape) < 0.5, 1, cur).astype(np.uint8)
+                p = np.full(shape, 0.01, dtype=np.float32)
+                old = t < cur
+                p[old] = rng.uniform(0, 0.01, size=int(old.sum())).astype(np.float32)
+                m.piggymask = nn.Parameter(torch.from_numpy(p).to(device))
+            masks['module.' + n] = torch.from_numpy(t).to(device)
+    net = Wrap(model)
+    args = make_args(mode, dataset='t2' if regime == 'task2' else 't1', wd=4e-5, freq=1, init_s=0.0, target_s=0.4)
+    args.finetune_again = True                 # cur = index(dataset) + 1
+    pruner = SparsePruner(net, masks, args, 0, 10, cur)
+    assert pruner.current_dataset_idx == cur
+    net.train()
+    for m in net.modules():
+        if isinstance(m, nn.BatchNorm2d):
+            m.eval()
+    return net, masks, pruner
+
+
+def grads_of(net):
+    return {n: p.grad.detach().clone() for n, p in net.named_parameters() if p.grad is not None}
+
+
+def main():
+    from cpg_b200 import ddp
+    rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
+    ddp.tune_env(world)
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    dist.init_process_group('nccl', device_id=device)
+    B = 16 * world
+    g = torch.Generator().manual_seed(5)
+    data = torch.randn(B, 3, 32, 32, generator=g).to(device)
+    target = torch.randint(0, 5, (B,), generator=g).to(device)
+    crit = nn.CrossEntropyLoss()
+    worst = {}
+    for regime in ('task2', 'task1'):
+        net, masks, pruner = build(regime, device)
+
+        def step(x, t, reducer):
+            for p in net.parameters():
+                p.grad = None
+            loss = crit(net(x), t)
+            loss.backward()
+            if reducer is not None:
+                reducer.reduce()
+            pruner.do_weight_decay_and_make_grads_zero()
+            return loss
+
+        # 1. one GPU, the whole batch
+        step(data, target, None)
+        full = grads_of(net)
+        # 2. G GPUs, B/G each, eager
+        red = ddp.GradAllReducer(net, world)
+        assert len(red.flat) >= 1 and sum(b.numel() for b in red.flat) >= sum(m.numel() for m in masks.values())
+        xs, ts = ddp.shard_batch(data, rank, world), ddp.shard_batch(target, rank, world)
+        for _ in range(2):
+            step(xs, ts, red)
+        torch.cuda.synchronize()
+        eager = grads_of(net)
+        assert set(eager) == set(full)
+        for n in full:
+            e = rel(eager[n], full[n])
+            worst[(regime, 'eager', n)] = e
+            assert e <= 2e-4, (regime, n, e)
+        # weight gradients really live in the buckets (no copies), and are masked
+        name0, mod0 = [(n, m) for n, m in net.named_modules() if hasattr(m, '_cpg_grad_slot') and m._cpg_grad_slot][-1]
+        base = red.flat[mod0._cpg_grad_slot.bucket]
+        assert base.data_ptr() <= mod0.weight.grad.data_ptr() < base.data_ptr() + base.numel() * 4
+        # 3. the same step from a CUDA graph (collectives captured)
+        sx, st_ = xs.clone(), ts.clone()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            step(sx, st_, red)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            step(sx, st_, red)
+        for _ in range(2):
+            graph.replay()
+        torch.cuda.synchronize()
+        captured = grads_of(net)
+        for n in full:
+            e = rel(captured[n], eager[n])
+            assert e <= 1e-6, (regime, 'graph', n, e)
+        # every rank holds the same reduced gradient
+        for n in sorted(full):
+            lo, hi = captured[n].clone(), captured[n].clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            assert torch.equal(lo, hi), (regime, n)
+        red.remove()
+        # 4. prune event: no collective, T bit-identical on every rank afterwards
+        from cpg_b200.prune import SparsePruner
+        from tests.toy import make_args
+        pargs = make_args('prune', dataset='t2' if regime == 'task2' else 't1', freq=1, init_s=0.0, target_s=0.4)
+        pr2 = SparsePruner(net, masks, pargs, 0, 10, pruner.current_dataset_idx)
+        with torch.no_grad():                  # a rank-identical "optimizer step"
+            for p_ in net.parameters():
+                if p_.grad is not None and p_.grad.shape == p_.shape:
+                    p_.add_(captured_name(net, captured, p_), alpha=-0.01)
+        ratio = pr2.gradually_prune(5)
+        assert ratio > 0
+        zeros = sum(int((m == 0).sum()) for m in masks.values())
+        assert zeros > 0
+        ddp.assert_masks_identical(masks)
+        pr2.detach()
+    if rank == 0:
+        top = sorted(worst.items(), key=lambda kv: -kv[1])[:3]
+        print('DDP_NCCL_OK world', world, 'worst', [(k[0], k[2], '%.2e' % v) for k, v in top], flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def captured_name(net, grads, p):
+    for n, q in net.named_parameters():
+        if q is p:
+            return grads[n]
+    raise KeyError
+
+
+if __name__ == '__main__':
+    main()

@@ -246,6 +246,35 @@ def pruner_cases():
     print('pruner')
 
 
+def one_shot_case():
+    """a11 one_shot_prune (utils/prune.py:94-109) on the toy model through the reference SparsePruner."""
+    rng = rs(31)
+    model = nn.DataParallel(_Toy())
+    out, names, masks = {}, [], {}
+    for name, mod in model.named_modules():
+        if isinstance(mod, (nl.SharableConv2d, nl.SharableLinear)):
+            names.append(name)
+            shp = tuple(mod.weight.shape)
+            w = rng.standard_normal(shp).astype(np.float32)
+            w.reshape(-1)[::9] = w.reshape(-1)[2]           # magnitude ties
+            tm = rng.randint(0, 4, size=shp).astype(np.uint8)
+            with torch.no_grad():
+                mod.weight.copy_(t(w))
+            masks[name] = t(tm.copy())
+            key = name.replace('.', '_')
+            out['W_' + key], out['T_' + key] = w, tm
+    pr = ref_prune.SparsePruner(model, masks, make_args('prune', dataset='t2'), 0, 8, 2)
+    pr.one_shot_prune(0.35)
+    for name, mod in model.named_modules():
+        if name in masks:
+            key = name.replace('.', '_')
+            out['W1_' + key] = mod.weight.data.numpy().copy()
+            out['T1_' + key] = pr.masks[name].numpy().copy()
+    out['names'], out['ratio'], out['cur'] = np.array(names), np.array(0.35), np.array(pr.current_dataset_idx)
+    np.savez_compressed(os.path.join(HERE, 'one_shot.npz'), **out)
+    print('one_shot')
+
+
 def trajectory_case(mode, name, steps=3, width=0.125, batch=8):
     """N training steps of a narrow VGG16-BN-cifar (task 2: piggymasks on every sharable
     layer) through the reference's unmodified Manager.train + SparsePruner."""
@@ -299,6 +328,9 @@ def trajectory_case(mode, name, steps=3, width=0.125, batch=8):
 
 
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'one_shot':     # added in round 2; leaves the other fixtures untouched
+        one_shot_case()
+        sys.exit(0)
     # BASELINE.json configs[0]: single SharableConv2d 3x3, batch 4x3x32x32
     conv_case('conv_cfg1', 4, 3, 32, 32, 64, 3, 1, 1, 1, 1, True, seed=1)
     conv_case('conv_cfg1_nopiggy', 4, 3, 32, 32, 64, 3, 1, 1, 1, 1, False, seed=2, piggy=False)
@@ -313,6 +345,7 @@ if __name__ == '__main__':
     pruner_cases()
     trajectory_case('prune', 'traj_prune')
     trajectory_case('finetune', 'traj_finetune')
+    one_shot_case()
     h = hashlib.sha256()
     for f in sorted(os.listdir(HERE)):
         if f.endswith('.npz'):

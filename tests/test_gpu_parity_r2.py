@@ -1,0 +1,492 @@
+"""Round-2 GPU parity tests for the path that bench.py times (PATH_AUTO, tcgen05 kernels):
+
+  * TF32-exact inputs must come back essentially exact (no statistical de-biasing anywhere);
+  * a full-width, batch-128 VGG16 step lock-stepped per layer against fp32 cuDNN / cuBLAS: every layer is fed
+    the reference network's own activations and output gradients, Y / dX / dW / dP within 1e-3, plus the loss
+    of the whole product network (fused BN + ReLU + pool kernels, pruner attached);
+  * a11 one_shot_prune against the live-reference golden fixture (utils/prune.py:94-109);
+  * gradient accumulation with a pruner attached: weight decay applied once (utils/prune.py:203);
+  * nn.DataParallel-style replicas never take the fused epilogue.
+
+relative error = max|a - b| / max|b| (north_star), as in test_gpu_parity.py.
+"""
+import copy
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from cpg_b200 import _lib  # noqa: E402
+import cpg_b200.layers as nl  # noqa: E402
+import cpg_b200.prune as cpg_prune  # noqa: E402
+from cpg_b200.functional import is_tf32  # noqa: E402
+from cpg_b200.vgg_cifar import VGGCifar  # noqa: E402
+from oracle import cpg_oracle as O  # noqa: E402
+from tests.toy import Toy, Wrap, make_args  # noqa: E402
+
+DEV = 'cuda:0'
+TOL_TC = 1e-3
+
+
+def G(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
+
+
+def _record(name, obj):
+    """Measured errors of the full-size checks, kept next to the profiles (gpurun_out/ comes back from the box)."""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = os.path.join(root, 'gpurun_out')
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, 'r2_parity_' + name + '.json'), 'w') as fh:
+            json.dump(obj, fh, indent=1)
+    except OSError:
+        pass
+
+
+@pytest.fixture(autouse=True)
+def _reset_path():
+    _lib.set_path(_lib.PATH_AUTO)
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    _lib.set_path(_lib.PATH_AUTO)
+
+
+# --------------------------------------------------------------------------------------------------------
+# TF32-representable operands: the tensor core multiplies them exactly, so the only difference to fp32 cuDNN
+# is the summation order.  Round 1 multiplied every result by 1/(1 - 3.5e-4) ("de-bias"): this test is the one
+# that would have caught it (a systematic +3.5e-4 / +7e-4).
+# --------------------------------------------------------------------------------------------------------
+def _quantised(shape, scale, seed):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randint(-8, 9, shape, generator=g).float() * scale).to(DEV)      # 5 significant bits
+
+
+@pytest.mark.parametrize('case', ['conv3x3', 'conv3x3_s2', 'conv1x1', 'linear'])
+def test_tf32_exact_inputs_are_exact(case):
+    _lib.set_path(_lib.PATH_TCGEN05)
+    if case == 'linear':
+        m = nl.SharableLinear(256, 128).to(DEV)
+        x = _quantised((64, 256), 0.125, 1).requires_grad_(True)
+    else:
+        k, s, p = {'conv3x3': (3, 1, 1), 'conv3x3_s2': (3, 2, 1), 'conv1x1': (1, 1, 0)}[case]
+        m = nl.SharableConv2d(64, 128, k, stride=s, padding=p, bias=True).to(DEV)
+        x = _quantised((8, 64, 16, 16), 0.125, 1).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    with torch.no_grad():
+        m.weight.copy_(_quantised(tuple(m.weight.shape), 2.0 ** -6, 2))
+        m.bias.copy_(_quantised(tuple(m.bias.shape), 0.25, 3))
+    pm = torch.full_like(m.weight, 0.01)
+    pm.view(-1)[::3] = 0.001
+    m.piggymask = nn.Parameter(pm)
+    y = m(x)
+    dy = _quantised(tuple(y.shape), 2.0 ** -4, 4)
+    if y.dim() == 4:
+        dy = dy.contiguous(memory_format=torch.channels_last)
+    y.backward(dy)
+    xr = x.detach().clone().requires_grad_(True)
+    wr = m.weight.detach().clone().requires_grad_(True)
+    pr = m.piggymask.detach().clone().requires_grad_(True)
+    b = (pr > 5e-3).float()
+    weff = (b - pr).detach() * wr + pr * wr            # value b*W, straight-through gradient for P
+    yr = F.linear(xr, weff, m.bias) if case == 'linear' else F.conv2d(xr, weff, m.bias, m.stride, m.padding)
+    yr.backward(dy)
+    for name, got, ref in (('y', y, yr), ('dx', x.grad, xr.grad), ('dW', m.weight.grad, wr.grad),
+                           ('dP', m.piggymask.grad, pr.grad)):
+        assert rel(got, ref) <= 1e-5, (case, name, rel(got, ref))
+
+
+def test_round_tf32_kernel_bit_exact():
+    """cpgb_round_tf32 == round-to-nearest (ties away) onto 10 explicit mantissa bits, NaN / Inf kept."""
+    lib = _lib.load()
+    rng = np.random.RandomState(5)
+    a = np.concatenate([rng.standard_normal(100003).astype(np.float32) * 10.0 ** rng.randint(-20, 20, 100003),
+                        np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1.0, 1.0 + 2.0 ** -11, 1.0 + 2.0 ** -11 + 2.0 ** -20,
+                                  1.0 + 3 * 2.0 ** -11, -1.0 - 2.0 ** -11, 1.1754944e-38],
+                                 dtype=np.float32)]).astype(np.float32)
+    src = G(a)
+    out = torch.empty_like(src)
+    _lib.check(lib.cpgb_round_tf32(_lib.ptr(src), _lib.ptr(out), src.numel(), _lib.stream_ptr()), 'round')
+    bits = a.view(np.uint32).astype(np.uint64)
+    finite = np.isfinite(a)
+    ref = np.where(finite, (bits + 0x1000) & 0xFFFFE000, bits).astype(np.uint32)       # magnitude + half ulp, truncate
+    got = out.cpu().numpy().view(np.uint32)
+    fin = finite & (np.abs(a) < 3.0e38)
+    assert np.array_equal(got[fin], ref[fin])
+    assert np.isnan(out.cpu().numpy()[np.isnan(a)]).all()
+    assert np.array_equal(np.isinf(out.cpu().numpy()), np.isinf(a))
+    # idempotent, and in place
+    _lib.check(lib.cpgb_round_tf32(_lib.ptr(out), _lib.ptr(out), out.numel(), _lib.stream_ptr()), 'round')
+    assert np.array_equal(out.cpu().numpy().view(np.uint32)[fin], ref[fin])
+
+
+def test_raw_c_abi_rounds_when_flags_are_clear():
+    """Without CPGB_FLAG_X_TF32 / _DY_TF32 the library rounds the operands itself (workspace grows by the copies);
+    with the flags set on pre-rounded tensors the result is bit-identical."""
+    lib = _lib.load()
+    _lib.set_path(_lib.PATH_TCGEN05)
+    torch.manual_seed(3)
+    x = torch.randn(8, 64, 12, 12, device=DEV).contiguous(memory_format=torch.channels_last)
+    w = torch.randn(128, 64, 3, 3, device=DEV) * 0.05
+    y0 = torch.empty(8, 128, 12, 12, device=DEV).contiguous(memory_format=torch.channels_last)
+    y1 = torch.empty_like(y0)
+    dy = torch.randn_like(y0)
+    P = _lib.ptr
+    res = {}
+    for flags in (0, _lib.FLAG_X_TF32 | _lib.FLAG_DY_TF32):
+        xx, dd = x, dy
+        if flags:
+            xx, dd = torch.empty_like(x), torch.empty_like(dy)
+            _lib.check(lib.cpgb_round_tf32(P(x), P(xx), x.numel(), _lib.stream_ptr()), 'round')
+            _lib.check(lib.cpgb_round_tf32(P(dy), P(dd), dy.numel(), _lib.stream_ptr()), 'round')
+        d = _lib.conv_desc(x.shape, x.stride(), w.shape, y0.shape, y0.stride(), (1, 1), (1, 1), (1, 1), 1, flags)
+        ws = torch.empty(lib.cpgb_workspace_bytes(d), dtype=torch.uint8, device=DEV)
+        y = torch.empty_like(y0)
+        dx = torch.empty_like(x)
+        dW = torch.empty_like(w)
+        _lib.check(lib.cpgb_conv2d_fprop(d, P(xx), P(w), None, None, P(y), 5e-3, None, P(ws), ws.numel(),
+                                         _lib.stream_ptr()), 'fprop')
+        _lib.check(lib.cpgb_conv2d_dgrad(d, P(dd), P(w), None, P(dx), 5e-3, None, P(ws), ws.numel(),
+                                         _lib.stream_ptr()), 'dgrad')
+        _lib.check(lib.cpgb_conv2d_wgrad_fused(d, P(xx), P(dd), P(w), None, None, 0, 0.0, _lib.GRAD_RAW, P(dW), None,
+                                               None, 5e-3, P(ws), ws.numel(), _lib.stream_ptr()), 'wgrad')
+        res[flags] = (y, dx, dW, ws.numel())
+    a, b = res[0], res[_lib.FLAG_X_TF32 | _lib.FLAG_DY_TF32]
+    assert a[3] > b[3]                                   # room for the rounded copies
+    for i in range(3):
+        assert torch.equal(a[i], b[i])
+    yr = F.conv2d(x, w, None, 1, 1)
+    assert rel(a[0], yr) <= TOL_TC
+
+
+# --------------------------------------------------------------------------------------------------------
+# full-width VGG16-BN, batch 128 (BASELINE.json configs[1]), task-2 regime (piggymask on all 15 layers)
+# --------------------------------------------------------------------------------------------------------
+class _RefConv(nn.Module):                                # models/layers.py:43-109 in stock torch ops
+    def __init__(self, cin, cout, kernel_size, stride=1, padding=0, bias=True, **kw):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(cout, cin, kernel_size, kernel_size))
+        self.bias = nn.Parameter(torch.empty(cout)) if bias else None
+        self.stride, self.padding, self.piggymask = stride, padding, None
+
+    def forward(self, x):
+        w = self.weight
+        if self.piggymask is not None:
+            b = (self.piggymask > 5e-3).float()
+            w = (b - self.piggymask).detach() * w + self.piggymask * w
+        return F.conv2d(x, w, self.bias, self.stride, self.padding)
+
+
+class _RefLinear(nn.Module):                              # models/layers.py:147-194
+    def __init__(self, fin, fout, bias=True, **kw):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(fout, fin))
+        self.bias = nn.Parameter(torch.empty(fout)) if bias else None
+        self.piggymask = None
+
+    def forward(self, x):
+        w = self.weight
+        if self.piggymask is not None:
+            b = (self.piggymask > 5e-3).float()
+            w = (b - self.piggymask).detach() * w + self.piggymask * w
+        return F.linear(x, w, self.bias)
+
+
+def _build_pair(width=1.0):
+    torch.manual_seed(1)
+    ref = VGGCifar(_RefConv, _RefLinear, width=width)
+    ours = VGGCifar(nl.SharableConv2d, nl.SharableLinear, width=width)
+    for m in (ref, ours):
+        m.add_dataset('t1', 5)
+        m.add_dataset('t2', 5)
+        m.set_dataset('t2')
+    ours.load_state_dict(ref.state_dict())
+    ref, ours = ref.to(DEV), ours.to(DEV)
+    rng = np.random.RandomState(7)
+    masks = {}
+    for (n, a), (_, b) in zip([(n, m) for n, m in ref.named_modules() if isinstance(m, (_RefConv, _RefLinear))],
+                              [(n, m) for n, m in ours.named_modules()
+                               if isinstance(m, (nl.SharableConv2d, nl.SharableLinear))]):
+        shape = tuple(a.weight.shape)
+        t = np.where(rng.rand(*shape) < 0.5, 1, 2).astype(np.uint8)
+        p = np.full(shape, 0.01, dtype=np.float32)
+        old = t < 2
+        p[old] = rng.uniform(0, 0.01, size=int(old.sum())).astype(np.float32)
+        a.piggymask = nn.Parameter(G(p))
+        b.piggymask = nn.Parameter(G(p.copy()))
+        masks['module.' + n] = G(t)
+    return ref, ours, masks
+
+
+def test_vgg16_full_width_batch128_lockstep_vs_fp32():
+    ref, ours, masks = _build_pair(1.0)
+    ref.train()
+    g = torch.Generator().manual_seed(11)
+    data = torch.randn(128, 3, 32, 32, generator=g).to(DEV)
+    target = torch.randint(0, 5, (128,), generator=g).to(DEV)
+
+    # 1. the reference network in fp32: record every sharable layer's input, output gradient and results
+    rec = {}
+    hooks = []
+    ref_layers = [(n, m) for n, m in ref.named_modules() if isinstance(m, (_RefConv, _RefLinear))]
+    for n, m in ref_layers:
+        def fwd_hook(mod, inp, out, n=n):
+            rec[n] = {'x': inp[0].detach().clone(), 'y': out.detach().clone()}
+            out.register_hook(lambda gy, n=n: rec[n].__setitem__('dy', gy.detach()))
+            if inp[0].requires_grad:
+                inp[0].register_hook(lambda gx, n=n: rec[n].__setitem__('dx', gx.detach()))
+        hooks.append(m.register_forward_hook(fwd_hook))
+    loss_ref = nn.CrossEntropyLoss()(ref(data), target)
+    loss_ref.backward()
+    for h in hooks:
+        h.remove()
+
+    # 2. every product layer on the SAME inputs / output gradients (PATH_AUTO, as benched)
+    worst = {}
+    our_layers = dict((n, m) for n, m in ours.named_modules() if isinstance(m, (nl.SharableConv2d, nl.SharableLinear)))
+    for n, rm in ref_layers:
+        m = our_layers[n]
+        r = rec[n]
+        x = r['x'].clone()
+        if x.dim() == 4:
+            x = x.contiguous(memory_format=torch.channels_last)
+        x.requires_grad_('dx' in r)
+        y = m(x)
+        y.backward(r['dy'])
+        errs = {'y': rel(y, r['y']), 'dW': rel(m.weight.grad, rm.weight.grad), 'dP': rel(m.piggymask.grad, rm.piggymask.grad)}
+        if 'dx' in r:
+            errs['dx'] = rel(x.grad, r['dx'])
+        if m.bias is not None:
+            errs['db'] = rel(m.bias.grad, rm.bias.grad)
+        worst[n] = errs
+        for k, v in errs.items():
+            assert v <= TOL_TC, (n, k, v, errs)
+        m.weight.grad = m.piggymask.grad = None
+        if m.bias is not None:
+            m.bias.grad = None
+
+    # 3. the whole product network as bench.py runs it: fused BN + ReLU (+ pool) kernels, pruner attached
+    from cpg_b200.fused_norm import fuse_bn_relu
+    fuse_bn_relu(ours)
+    net = Wrap(ours)
+    args = make_args('finetune')
+    args.finetune_again = True
+    pruner = cpg_prune.SparsePruner(net, masks, args, 0, 1, 2)
+    assert pruner.current_dataset_idx == 2
+    ours.train()
+    loss = nn.CrossEntropyLoss()(net(data), target)
+    loss.backward()
+    loss_err = abs(loss.item() - loss_ref.item()) / abs(loss_ref.item())
+    _record('lockstep_vgg16_b128', {'per_layer': worst, 'loss': loss.item(), 'loss_ref_fp32': loss_ref.item(),
+                                    'loss_rel_err': loss_err})
+    assert loss_err <= 2e-3, (loss.item(), loss_ref.item())
+    # the gradient of the LAST sharable layer sees an almost identical forward pass: checks the fused epilogue
+    # (weight decay + masks) at full size against the reference expressions of utils/prune.py:203-208
+    n_last, rm = ref_layers[-1]
+    m = our_layers[n_last]
+    t = masks['module.' + n_last]
+    want_w = (rm.weight.grad + 4e-5 * rm.weight.detach()) * (t == 2)
+    want_p = rm.piggymask.grad * ((t > 0) & (t < 2))
+    assert rel(m.weight.grad, want_w) <= 1e-2 and rel(m.piggymask.grad, want_p) <= 1e-2
+    assert bool((m.weight.grad[t != 2] == 0).all()) and bool((m.piggymask.grad[t == 2] == 0).all())
+
+
+def test_network_activations_are_tagged_tf32():
+    """In the benched configuration every tcgen05 convolution gets its operands pre-rounded by the producer: no
+    rounding pass is launched for the 12 BN-fed convolutions (forward) nor for their output gradients."""
+    from cpg_b200.fused_norm import fuse_bn_relu
+    torch.manual_seed(2)
+    model = VGGCifar(nl.SharableConv2d, nl.SharableLinear, width=0.25)
+    model.add_dataset('t1', 5)
+    model.set_dataset('t1')
+    model = model.to(DEV)
+    fuse_bn_relu(model)
+    model.train()
+    seen = {}
+    hooks = [m.register_forward_pre_hook(lambda mod, inp, n=n: seen.__setitem__(n, is_tf32(inp[0])))
+             for n, m in model.named_modules() if isinstance(m, (nl.SharableConv2d, nl.SharableLinear))]
+    lib = _lib.load()
+    x = torch.randn(32, 3, 32, 32, device=DEV)
+    out = model(x)
+    out.sum().backward()
+    for h in hooks:
+        h.remove()
+    names = list(seen)
+    assert not seen[names[0]]                    # raw images feed the (fp32) stem kernels
+    assert all(seen[n] for n in names[1:14]), seen    # 12 convs behind fused BN, FC1 behind BN+pool -> View
+    # rounded activations really are TF32 values
+    y = model.features[1](model.features[0](x))
+    assert bool(((y.view(torch.int32) & 0x1FFF) == 0).all())
+
+
+# --------------------------------------------------------------------------------------------------------
+# a11 one_shot_prune (utils/prune.py:94-109)
+# --------------------------------------------------------------------------------------------------------
+def test_a11_one_shot_prune_golden(golden, capsys):
+    g = golden('one_shot')
+    model = Wrap(Toy(nl)).to(DEV)
+    masks, w0 = {}, {}
+    for name, mod in model.named_modules():
+        if isinstance(mod, (nl.SharableConv2d, nl.SharableLinear)):
+            k = name.replace('.', '_')
+            with torch.no_grad():
+                mod.weight.copy_(G(g['W_' + k]))
+            masks[name] = G(g['T_' + k].copy())
+            w0[name] = g['W_' + k]
+    pr = cpg_prune.SparsePruner(model, masks, make_args('prune'), 0, 8, 2)
+    assert pr.current_dataset_idx == int(g['cur'])
+    pr.one_shot_prune(float(g['ratio']))
+    printed = capsys.readouterr().out
+    assert 'Pruning for dataset idx: 2' in printed and '35.00%' in printed
+    ws, ts = [], []
+    for name, mod in model.named_modules():
+        if name in masks:
+            k = name.replace('.', '_')
+            assert np.array_equal(pr.masks[name].cpu().numpy(), g['T1_' + k]), name          # bit-exact mask
+            assert np.array_equal(mod.weight.detach().cpu().numpy(), g['W1_' + k]), name    # W[T==0] = 0, rest untouched
+            ws.append(torch.from_numpy(w0[name].copy()))
+            ts.append(torch.from_numpy(g['T_' + k].copy()))
+    # the oracle restatement agrees with the live-reference fixture as well
+    O.one_shot_prune(ws, ts, 2, float(g['ratio']))
+    for (name, _), w, t in zip([(n, m) for n, m in model.named_modules() if n in masks], ws, ts):
+        k = name.replace('.', '_')
+        assert np.array_equal(t.numpy(), g['T1_' + k]) and np.array_equal(w.numpy(), g['W1_' + k])
+
+
+# --------------------------------------------------------------------------------------------------------
+# gradient accumulation with a pruner attached (utils/prune.py:203: weight decay is added once)
+# --------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('mode', ['finetune', 'prune'])
+def test_accumulate_twice_with_pruner_matches_unfused(mode):
+    res = {}
+    for fused in (False, True):
+        torch.manual_seed(4)
+        model = Wrap(Toy(nl)).to(DEV)
+        rng = np.random.RandomState(9)
+        masks = {}
+        for name, mod in model.named_modules():
+            if isinstance(mod, (nl.SharableConv2d, nl.SharableLinear)):
+                with torch.no_grad():
+                    mod.weight.copy_(G(rng.standard_normal(tuple(mod.weight.shape)).astype(np.float32) * 0.2))
+                    if mod.bias is not None:
+                        mod.bias.zero_()
+                mod.piggymask = nn.Parameter(G(rng.uniform(0, 0.01, tuple(mod.weight.shape)).astype(np.float32)))
+                masks[name] = G(rng.randint(0, 4, tuple(mod.weight.shape)).astype(np.uint8))
+        a = make_args(mode, wd=0.05)            # large enough that a double count is obvious
+        pr = cpg_prune.SparsePruner(model, masks, a, 0, 8, 2)
+        pr.fuse_grad_epilogue = fused
+        xs = [G(rng.standard_normal((4, 3, 8, 8)).astype(np.float32)) for _ in range(2)]
+        for x in xs:                            # two backward passes, one pruner call
+            model(x).square().mean().backward()
+        pr.do_weight_decay_and_make_grads_zero()
+        res[fused] = {n: (m.weight.grad.clone(), m.piggymask.grad.clone()) for n, m in model.named_modules()
+                      if n in masks}
+        # the closed-form reference for one layer: (g1 + g2)*b + wd*W on T == cur, zero elsewhere
+        if not fused:
+            m = model.module.fc
+            t = masks['module.fc']
+            assert bool((m.weight.grad[t != 2] == 0).all())
+    for n in res[True]:
+        for i in range(2):
+            assert rel(res[True][n][i], res[False][n][i]) <= 1e-5, (mode, n, i)
+
+
+def test_third_backward_after_pruner_call_accumulates_raw():
+    """.grad finalised by the pruner and NOT cleared: the next backward must add the plain autograd gradient
+    (the reference would), and the next pruner call decays / masks once more."""
+    torch.manual_seed(6)
+    res = {}
+    for fused in (False, True):
+        model = Wrap(Toy(nl)).to(DEV)
+        rng = np.random.RandomState(12)
+        masks = {}
+        for name, mod in model.named_modules():
+            if isinstance(mod, (nl.SharableConv2d, nl.SharableLinear)):
+                with torch.no_grad():
+                    mod.weight.copy_(G(rng.standard_normal(tuple(mod.weight.shape)).astype(np.float32) * 0.2))
+                    if mod.bias is not None:
+                        mod.bias.zero_()
+                masks[name] = G(rng.randint(0, 4, tuple(mod.weight.shape)).astype(np.uint8))
+        pr = cpg_prune.SparsePruner(model, masks, make_args('prune', wd=0.05), 0, 8, 2)
+        pr.fuse_grad_epilogue = fused
+        x = G(rng.standard_normal((4, 3, 8, 8)).astype(np.float32))
+        for _ in range(2):
+            model(x).square().mean().backward()
+            pr.do_weight_decay_and_make_grads_zero()
+        res[fused] = {n: m.weight.grad.clone() for n, m in model.named_modules() if n in masks}
+    for n in res[True]:
+        assert rel(res[True][n], res[False][n]) <= 1e-5, n
+
+
+# --------------------------------------------------------------------------------------------------------
+# nn.DataParallel replicas (CPG_cifar100_main_normal.py:199)
+# --------------------------------------------------------------------------------------------------------
+def test_replica_never_takes_the_fused_epilogue():
+    """torch's replicate() copies a module's __dict__ (so the replica sees the pruner weakref) and marks it
+    `_is_replica`; its parameters are non-leaf.  Such a module must hand out raw autograd gradients: the fused
+    epilogue would decay once per replica and read the task mask across devices."""
+    model = Wrap(Toy(nl)).to(DEV)
+    rng = np.random.RandomState(3)
+    masks = {}
+    for name, mod in model.named_modules():
+        if isinstance(mod, (nl.SharableConv2d, nl.SharableLinear)):
+            with torch.no_grad():
+                mod.weight.copy_(G(rng.standard_normal(tuple(mod.weight.shape)).astype(np.float32)))
+                if mod.bias is not None:
+                    mod.bias.zero_()
+            masks[name] = torch.full(tuple(mod.weight.shape), 2, dtype=torch.uint8, device=DEV)
+    pr = cpg_prune.SparsePruner(model, masks, make_args('prune', wd=0.5), 0, 8, 2)
+    m = model.module.c2
+    assert m._fuse_ctx() is not None
+    rep = copy.copy(m)                                  # what replicate() does: shallow copy ...
+    rep._parameters = dict(m._parameters)
+    rep._parameters['weight'] = m.weight * 1.0          # ... with non-leaf parameter tensors
+    rep._is_replica = True
+    assert rep._fuse_ctx() is None
+    x = G(rng.standard_normal((2, 8, 6, 6)).astype(np.float32)).contiguous(memory_format=torch.channels_last)
+    rep(x).sum().backward()
+    assert m._cpg_grads_final is False                  # nothing was finalised behind the pruner's back
+    g_raw = m.weight.grad.clone()
+    pr.do_weight_decay_and_make_grads_zero()            # decays exactly once
+    assert rel(m.weight.grad, g_raw + 0.5 * m.weight.detach()) <= 1e-6
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
+def test_dataparallel_two_gpus_matches_single():
+    """The reference's multi-GPU mode end to end: nn.DataParallel over two devices, product layers + pruner, one
+    training step against the same step on one device (BatchNorm-free toy, so the shards are independent)."""
+    res = {}
+    rng0 = np.random.RandomState(8)
+    w_init = {}
+    x = torch.from_numpy(rng0.standard_normal((8, 3, 8, 8)).astype(np.float32)).to(DEV)
+    for dp in (False, True):
+        inner = Toy(nl).to(DEV)
+        rng = np.random.RandomState(8)
+        masks = {}
+        model = nn.DataParallel(inner, device_ids=[0, 1]) if dp else Wrap(inner)
+        for name, mod in model.named_modules():
+            if isinstance(mod, (nl.SharableConv2d, nl.SharableLinear)):
+                with torch.no_grad():
+                    mod.weight.copy_(G(rng.standard_normal(tuple(mod.weight.shape)).astype(np.float32) * 0.2))
+                    if mod.bias is not None:
+                        mod.bias.zero_()
+                masks[name] = G(rng.randint(1, 3, tuple(mod.weight.shape)).astype(np.uint8))
+        pr = cpg_prune.SparsePruner(model, masks, make_args('prune', wd=0.05), 0, 8, 2)
+        model(x).square().mean().backward()
+        pr.do_weight_decay_and_make_grads_zero()
+        res[dp] = {n: m.weight.grad.clone() for n, m in model.named_modules() if n in masks}
+    for n in res[True]:
+        assert rel(res[True][n], res[False][n]) <= 1e-4, n

@@ -1,5 +1,5 @@
 """Small-shape pass over the round-1 additions (stem kernels, BatchNorm+ReLU+pool kernels) for
-compute-sanitizer:  compute-sanitizer --tool memcheck python tests/memcheck_new.py"""
+compute-sanitizer:  compute-sanitizer --tool memcheck python tools/memcheck_new.py"""
 import os
 import sys
 import torch
