@@ -443,6 +443,11 @@ def kernel_table(device, regime_has_piggy, iters=5):
         return statistics.median(ts)
 
     def bench_layer(kind, d, x, w, p, y, dy, t, flops, first):
+        # as in the real step, the activation operands arrive TF32-exact from their producers (fused BN kernels)
+        for tns in (x, dy):
+            base = tns if tns._base is None else tns._base
+            _lib.check(lib.cpgb_round_tf32(_lib.ptr(base), _lib.ptr(base), base.numel(), _lib.stream_ptr()), 'round')
+        d.flags = _lib.FLAG_X_TF32 | _lib.FLAG_DY_TF32
         ws = torch.empty(lib.cpgb_workspace_bytes(d), dtype=torch.uint8, device=device)
         dW, dP = torch.empty_like(w), (torch.empty_like(w) if p is not None else None)
         dx = torch.empty_strided(x.shape, x.stride(), dtype=x.dtype, device=device)
@@ -678,8 +683,8 @@ def main():
     if args.path == 'simt':
         _lib.set_path(_lib.PATH_SIMT)
 
-    def run_regime(regime, want_e2e):
-        tr = Trainer(regime, device, world, use_graph=not args.no_graph)
+    def run_regime(regime, want_e2e, width=1.0):
+        tr = Trainer(regime, device, world, use_graph=not args.no_graph, width=width)
         tr.prepare()
         batches = synth_batches(8, BATCH, seed=100 + rank)
         dev_batches = [(x.to(device), t.to(device)) for x, t in batches]
@@ -702,6 +707,9 @@ def main():
     r1 = run_regime('task1', True)
     extras = not args.no_extras
     r2 = run_regime('task2', True) if extras else None
+    # the grown network of experiment1/CPG_cifar100_scratch_mul_1.5.sh:89-94 (--network_width_multiplier 1.5 ->
+    # channel counts * sqrt(1.5) = 78 / 156 / 313 / 627 / 5016, CPG_cifar100_main_normal.py:115)
+    r15 = run_regime('task1', False, width=1.5 ** 0.5) if (extras and world == 1) else None
 
     def run_torch_gpu(regime, use_graph):
         """stock-PyTorch arm on the same GPU (context only)."""
@@ -754,6 +762,16 @@ def main():
                 'value': imgs / (r2['ms'] * 1e-3), 'ms_per_step': r2['ms'] / args.steps,
                 'e2e_value': imgs / (r2['e2e_ms'] * 1e-3), 'gpu_launches': int(r2['launches_per_step'] * args.steps),
                 'loss': r2['loss']}
+    if r15 is not None and rank == 0:
+        flop10, flop15 = VGG_TRAIN_FLOP_PER_IMG, 3 * 0.9911e9 - 2.0 * 78 * 3 * 9 * 32 * 32
+        rate10 = flop10 * BATCH / (r1['ms'] / args.steps * 1e-3) / 1e12
+        rate15 = flop15 * BATCH / (r15['ms'] / args.steps * 1e-3) / 1e12
+        line['regime_width_1p5'] = {
+            'regime': 'task1, --network_width_multiplier 1.5: channels 78/156/313/627, FC 627->5016->5016 (padded-NHWC '
+                      'activations, zero-padded weight blocks, all layers but the stem on the tcgen05 kernels)',
+            'value': imgs / (r15['ms'] * 1e-3), 'ms_per_step': r15['ms'] / args.steps,
+            'algorithmic_tflops': rate15, 'algorithmic_tflops_width_1p0': rate10, 'flop_rate_vs_width_1p0': rate15 / rate10,
+            'gpu_launches': int(r15['launches_per_step'] * args.steps), 'loss': r15['loss']}
     if extras and world == 1:
         tf32_cublas = measure_tf32_peak(device)
         # the roofline denominator is in MEASURED_PEAKS.json's terms: tcgen05 kind::tf32 issues at exactly half the

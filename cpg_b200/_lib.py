@@ -21,7 +21,7 @@ EXPORTS = [
     'cpgb_prune_batched_workspace_bytes', 'cpgb_prune_select_batched',
     'cpgb_apply_mask', 'cpgb_make_finetuning_mask', 'cpgb_mask_stats', 'cpgb_mask_stats_batched', 'cpgb_merge_grads',
     'cpgb_split_merged_grad', 'cpgb_bn_workspace_bytes', 'cpgb_bn_relu_fwd', 'cpgb_bn_relu_bwd',
-    'cpgb_uses_tensor_cores', 'cpgb_round_tf32',
+    'cpgb_uses_tensor_cores', 'cpgb_round_tf32', 'cpgb_conv2d_bias_grad',
 ]
 
 
@@ -60,6 +60,7 @@ def load():
         'cpgb_workspace_bytes': (sz, [dp]),
         'cpgb_uses_tensor_cores': (ctypes.c_int, [dp, i32]),
         'cpgb_round_tf32': (ctypes.c_int, [vp, vp, i64, vp]),
+        'cpgb_conv2d_bias_grad': (ctypes.c_int, [dp, vp, vp, vp]),
         'cpgb_binarize': (ctypes.c_int, [vp, vp, i64, f32, vp]),
         'cpgb_staged_weight_bytes': (sz, [dp]),
         'cpgb_stage_weights': (ctypes.c_int, [dp, vp, vp, f32, vp, sz, vp]),
@@ -86,10 +87,10 @@ def load():
         'cpgb_merge_grads': (ctypes.c_int, [vp, vp, vp, i64, vp]),
         'cpgb_split_merged_grad': (ctypes.c_int, [vp, vp, i64, i32, vp, vp, vp]),
         'cpgb_bn_workspace_bytes': (sz, [i64, i32]),
-        'cpgb_bn_relu_fwd': (ctypes.c_int, [vp, i64, i32, vp, vp, vp, vp, vp, i32, f32, f32, i32, i32, i32, i32, vp, vp, vp,
+        'cpgb_bn_relu_fwd': (ctypes.c_int, [vp, i64, i32, i32, vp, vp, vp, vp, vp, i32, f32, f32, i32, i32, i32, i32, vp, vp,
+                                            vp, vp, sz, vp]),
+        'cpgb_bn_relu_bwd': (ctypes.c_int, [vp, vp, i64, i32, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp,
                                             vp, sz, vp]),
-        'cpgb_bn_relu_bwd': (ctypes.c_int, [vp, vp, i64, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp,
-                                            sz, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -225,6 +225,14 @@ int cpgb_conv2d_dgrad(const cpgb_conv_desc *d, const float *dy, const float *w, 
   return simt_dgrad(make_geom(*d), dy, w, piggy, dx, thr, (cudaStream_t)stream);
 }
 
+int cpgb_conv2d_bias_grad(const cpgb_conv_desc *d, const float *dy, float *dbias, void *stream) {
+  int rc = validate_desc(d);
+  if (rc) return rc;
+  if (!dbias || (d->N != 0 && !dy)) { set_error("cpgb_conv2d_bias_grad: null pointer"); return CPGB_EINVAL; }
+  if (d->N == 0) { CPGB_CUDA_OK(cudaMemsetAsync(dbias, 0, d->K * sizeof(float), (cudaStream_t)stream)); return CPGB_OK; }
+  return bias_grad(make_geom(*d), dy, dbias, (cudaStream_t)stream);
+}
+
 int cpgb_conv2d_wgrad_fused(const cpgb_conv_desc *d, const float *x, const float *dy, const float *w,
                             const float *piggy, const uint8_t *tmask, int32_t cur, float weight_decay,
                             int32_t mode, float *dW, float *dP, float *dbias, float thr, void *ws,

@@ -43,15 +43,16 @@ int na_sms() {
 struct NaGeom {
   long long M;      // pixels
   int C;            // channels
+  int Cs;           // floats between consecutive pixels (>= C, a multiple of 4; lanes C..Cs-1 are padding)
   int lanes;        // float4 channel groups handled by one block (<= NA_THREADS)
   int slots;        // pixel rows in flight per block = NA_THREADS / lanes
   int cchunks;      // blockIdx.y extent
 };
 
-NaGeom na_geom(long long M, int C, int threads = NA_THREADS) {
+NaGeom na_geom(long long M, int C, int Cs, int threads = NA_THREADS) {
   NaGeom g;
-  g.M = M; g.C = C;
-  const int c4 = C / 4;
+  g.M = M; g.C = C; g.Cs = Cs;
+  const int c4 = Cs / 4;
   g.lanes = c4 < threads ? c4 : threads;
   g.slots = threads / g.lanes;
   g.cchunks = (c4 + g.lanes - 1) / g.lanes;
@@ -80,24 +81,48 @@ __device__ __forceinline__ void block_reduce_pairs(const NaGeom &g, float4 s, fl
       s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
       q.x += b.x; q.y += b.y; q.z += b.z; q.w += b.w;
     }
-    float *dst = part + ((long long)blockIdx.x * g.C + c4 * 4) * 2;
+    float *dst = part + ((long long)blockIdx.x * g.Cs + c4 * 4) * 2;
     reinterpret_cast<float4 *>(dst)[0] = make_float4(s.x, q.x, s.y, q.y);
     reinterpret_cast<float4 *>(dst)[1] = make_float4(s.z, q.z, s.w, q.w);
   }
+}
+
+// Four per-channel values of channel group c4 out of an array of C floats; lanes beyond C read as `fill`.
+__device__ __forceinline__ float4 ldp4(const float *__restrict__ p, int c4, int C, float fill) {
+  const int c = c4 * 4;
+  if (c + 4 <= C) return __ldg(reinterpret_cast<const float4 *>(p) + c4);
+  float4 v;
+  v.x = c + 0 < C ? __ldg(p + c + 0) : fill;
+  v.y = c + 1 < C ? __ldg(p + c + 1) : fill;
+  v.z = c + 2 < C ? __ldg(p + c + 2) : fill;
+  v.w = c + 3 < C ? __ldg(p + c + 3) : fill;
+  return v;
+}
+// Activation values of the padding lanes are undefined (whoever produced the tensor may not have written them):
+// force them to zero so that nothing non-finite can leak into the (zero-coefficient) pad outputs.
+__device__ __forceinline__ float4 pad0(float4 v, int c4, int C) {
+  const int c = c4 * 4;
+  if (c + 4 > C) {
+    if (c + 0 >= C) v.x = 0.f;
+    if (c + 1 >= C) v.y = 0.f;
+    if (c + 2 >= C) v.z = 0.f;
+    if (c + 3 >= C) v.w = 0.f;
+  }
+  return v;
 }
 
 __global__ void __launch_bounds__(NA_STATS_THREADS)
 bn_stats_kernel(const NaGeom g, const float *__restrict__ x, float *__restrict__ part) {
   const int lane = threadIdx.x % g.lanes, slot = threadIdx.x / g.lanes;
   const int c4 = blockIdx.y * g.lanes + lane;
-  const bool active = slot < g.slots && c4 * 4 < g.C;
+  const bool active = slot < g.slots && c4 * 4 < g.Cs;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
   if (active) {
     const float4 *xp = reinterpret_cast<const float4 *>(x) + c4;
-    const long long stride = (long long)gridDim.x * g.slots, cq = g.C / 4;
+    const long long stride = (long long)gridDim.x * g.slots, cq = g.Cs / 4;
 #pragma unroll 4
     for (long long r = (long long)blockIdx.x * g.slots + slot; r < g.M; r += stride) {
-      const float4 v = __ldg(xp + r * cq);
+      const float4 v = pad0(__ldg(xp + r * cq), c4, g.C);
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
       q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
     }
@@ -136,15 +161,19 @@ __device__ __forceinline__ void sum_partials(const float *__restrict__ part, int
 // momentum < 0 means cumulative average with factor 1 / num_batches_tracked passed as -momentum),
 // coefficients a = gamma * rstd, b = beta - mean * a.
 __global__ void __launch_bounds__(256)
-bn_finalize_kernel(const float *__restrict__ part, int nblocks, int C, long long M, const float *__restrict__ gamma,
+bn_finalize_kernel(const float *__restrict__ part, int nblocks, int C, int Cs, long long M, const float *__restrict__ gamma,
                    const float *__restrict__ beta, float *__restrict__ running_mean, float *__restrict__ running_var,
                    float momentum, float eps, float *__restrict__ save_mean, float *__restrict__ save_rstd,
                    float *__restrict__ coef_a, float *__restrict__ coef_b, long long *__restrict__ num_batches_tracked) {
   if (num_batches_tracked && blockIdx.x == 0 && threadIdx.x == 0) *num_batches_tracked += 1;   // nn.BatchNorm2d.forward
   const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (c >= C) return;
+  if (c >= Cs) return;
+  if (c >= C) {                       // padding lane: zero coefficients, so y = 0 there
+    if ((threadIdx.x & 31) == 0) { coef_a[c] = 0.f; coef_b[c] = 0.f; }
+    return;
+  }
   double s, q;
-  sum_partials(part, nblocks, C, c, s, q);
+  sum_partials(part, nblocks, Cs, c, s, q);
   if ((threadIdx.x & 31) != 0) return;
   const double mean = s / (double)M;
   double var = q / (double)M - mean * mean;
@@ -164,11 +193,12 @@ bn_finalize_kernel(const float *__restrict__ part, int nblocks, int C, long long
 
 // evaluation mode: coefficients out of the running statistics
 __global__ void __launch_bounds__(128)
-bn_eval_coef_kernel(int C, const float *__restrict__ gamma, const float *__restrict__ beta,
+bn_eval_coef_kernel(int C, int Cs, const float *__restrict__ gamma, const float *__restrict__ beta,
                     const float *__restrict__ running_mean, const float *__restrict__ running_var, float eps,
                     float *__restrict__ coef_a, float *__restrict__ coef_b) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  if (c >= Cs) return;
+  if (c >= C) { coef_a[c] = 0.f; coef_b[c] = 0.f; return; }
   const float rstd = 1.0f / sqrtf(running_var[c] + eps);
   const float a = (gamma ? gamma[c] : 1.f) * rstd;
   coef_a[c] = a;
@@ -178,9 +208,9 @@ bn_eval_coef_kernel(int C, const float *__restrict__ gamma, const float *__restr
 // a = gamma * rstd, b = beta - mean * a for the four channels of a thread (the same expressions as the
 // forward finalize step, so the recomputed ReLU mask matches the forward pass bit for bit)
 __device__ __forceinline__ void coef_from_stats(const float *__restrict__ gamma, const float *__restrict__ beta, int c4,
-                                                const float4 &mu, const float4 &rs, float4 &a, float4 &b) {
-  const float4 gm = gamma ? __ldg(reinterpret_cast<const float4 *>(gamma) + c4) : make_float4(1.f, 1.f, 1.f, 1.f);
-  const float4 bt = beta ? __ldg(reinterpret_cast<const float4 *>(beta) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                                int C, const float4 &mu, const float4 &rs, float4 &a, float4 &b) {
+  const float4 gm = gamma ? ldp4(gamma, c4, C, 0.f) : make_float4(1.f, 1.f, 1.f, 1.f);
+  const float4 bt = beta ? ldp4(beta, c4, C, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
   a = make_float4(gm.x * rs.x, gm.y * rs.y, gm.z * rs.z, gm.w * rs.w);
   b = make_float4(bt.x - mu.x * a.x, bt.y - mu.y * a.y, bt.z - mu.z * a.z, bt.w - mu.w * a.w);
 }
@@ -201,15 +231,15 @@ bn_apply_kernel(const NaGeom g, const float *__restrict__ x, const float *__rest
                 const float *__restrict__ coef_b, int relu, int tf32, float *__restrict__ y) {
   const int lane = threadIdx.x % g.lanes, slot = threadIdx.x / g.lanes;
   const int c4 = blockIdx.y * g.lanes + lane;
-  if (slot >= g.slots || c4 * 4 >= g.C) return;
+  if (slot >= g.slots || c4 * 4 >= g.Cs) return;
   const float4 a = __ldg(reinterpret_cast<const float4 *>(coef_a) + c4);
   const float4 b = __ldg(reinterpret_cast<const float4 *>(coef_b) + c4);
   const float4 *xp = reinterpret_cast<const float4 *>(x) + c4;
   float4 *yp = reinterpret_cast<float4 *>(y) + c4;
-  const long long stride = (long long)gridDim.x * g.slots, cq = g.C / 4;
+  const long long stride = (long long)gridDim.x * g.slots, cq = g.Cs / 4;
 #pragma unroll 4
   for (long long r = (long long)blockIdx.x * g.slots + slot; r < g.M; r += stride) {
-    const float4 v = __ldg(xp + r * cq);
+    const float4 v = pad0(__ldg(xp + r * cq), c4, g.C);
     float4 o = make_float4(fmaf(v.x, a.x, b.x), fmaf(v.y, a.y, b.y), fmaf(v.z, a.z, b.z), fmaf(v.w, a.w, b.w));
     if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
     yp[r * cq] = na_out(o, tf32);
@@ -231,19 +261,19 @@ bn_bwd_stats_kernel(const NaGeom g, const float *__restrict__ x, const float *__
                     float *__restrict__ part) {
   const int lane = threadIdx.x % g.lanes, slot = threadIdx.x / g.lanes;
   const int c4 = blockIdx.y * g.lanes + lane;
-  const bool active = slot < g.slots && c4 * 4 < g.C;
+  const bool active = slot < g.slots && c4 * 4 < g.Cs;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
   if (active) {
-    const float4 mu = __ldg(reinterpret_cast<const float4 *>(save_mean) + c4);
-    const float4 rs = __ldg(reinterpret_cast<const float4 *>(save_rstd) + c4);
+    const float4 mu = ldp4(save_mean, c4, g.C, 0.f);
+    const float4 rs = ldp4(save_rstd, c4, g.C, 0.f);
     float4 a, b;
-    coef_from_stats(gamma, beta, c4, mu, rs, a, b);
+    coef_from_stats(gamma, beta, c4, g.C, mu, rs, a, b);
     const float4 *xp = reinterpret_cast<const float4 *>(x) + c4;
     const float4 *dp = reinterpret_cast<const float4 *>(dy) + c4;
-    const long long stride = (long long)gridDim.x * g.slots, cq = g.C / 4;
+    const long long stride = (long long)gridDim.x * g.slots, cq = g.Cs / 4;
 #pragma unroll 4
     for (long long r = (long long)blockIdx.x * g.slots + slot; r < g.M; r += stride) {
-      const float4 v = __ldg(xp + r * cq), d = __ldg(dp + r * cq);
+      const float4 v = pad0(__ldg(xp + r * cq), c4, g.C), d = pad0(__ldg(dp + r * cq), c4, g.C);
       float gx, gy, gz, gw, hx, hy, hz, hw;
       NA_GRAD_ELEM(gx, hx, v.x, d.x, a.x, b.x, mu.x, rs.x)
       NA_GRAD_ELEM(gy, hy, v.y, d.y, a.y, b.y, mu.y, rs.y)
@@ -259,13 +289,17 @@ bn_bwd_stats_kernel(const NaGeom g, const float *__restrict__ x, const float *__
 // dbeta = sum g, dgamma = sum g * xhat; c1 = dbeta / M, c2 = dgamma / M (training) or 0 (evaluation
 // mode: the statistics are constants, dx = a * g)
 __global__ void __launch_bounds__(256)
-bn_bwd_finalize_kernel(const float *__restrict__ part, int nblocks, int C, long long M, int training,
+bn_bwd_finalize_kernel(const float *__restrict__ part, int nblocks, int C, int Cs, long long M, int training,
                        float *__restrict__ dgamma, float *__restrict__ dbeta, float *__restrict__ c1,
                        float *__restrict__ c2) {
   const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (c >= C) return;
+  if (c >= Cs) return;
+  if (c >= C) {
+    if ((threadIdx.x & 31) == 0) { c1[c] = 0.f; c2[c] = 0.f; }
+    return;
+  }
   double s, q;
-  sum_partials(part, nblocks, C, c, s, q);
+  sum_partials(part, nblocks, Cs, c, s, q);
   if ((threadIdx.x & 31) != 0) return;
   if (dbeta) dbeta[c] = (float)s;
   if (dgamma) dgamma[c] = (float)q;
@@ -281,20 +315,20 @@ bn_bwd_apply_kernel(const NaGeom g, const float *__restrict__ x, const float *__
                     float *__restrict__ dx) {
   const int lane = threadIdx.x % g.lanes, slot = threadIdx.x / g.lanes;
   const int c4 = blockIdx.y * g.lanes + lane;
-  if (slot >= g.slots || c4 * 4 >= g.C) return;
-  const float4 mu = __ldg(reinterpret_cast<const float4 *>(save_mean) + c4);
-  const float4 rs = __ldg(reinterpret_cast<const float4 *>(save_rstd) + c4);
+  if (slot >= g.slots || c4 * 4 >= g.Cs) return;
+  const float4 mu = ldp4(save_mean, c4, g.C, 0.f);
+  const float4 rs = ldp4(save_rstd, c4, g.C, 0.f);
   float4 a, b;
-  coef_from_stats(gamma, beta, c4, mu, rs, a, b);
+  coef_from_stats(gamma, beta, c4, g.C, mu, rs, a, b);
   const float4 k1 = __ldg(reinterpret_cast<const float4 *>(c1) + c4);
   const float4 k2 = __ldg(reinterpret_cast<const float4 *>(c2) + c4);
   const float4 *xp = reinterpret_cast<const float4 *>(x) + c4;
   const float4 *dp = reinterpret_cast<const float4 *>(dy) + c4;
   float4 *op = reinterpret_cast<float4 *>(dx) + c4;
-  const long long stride = (long long)gridDim.x * g.slots, cq = g.C / 4;
+  const long long stride = (long long)gridDim.x * g.slots, cq = g.Cs / 4;
 #pragma unroll 4
   for (long long r = (long long)blockIdx.x * g.slots + slot; r < g.M; r += stride) {
-    const float4 v = __ldg(xp + r * cq), d = __ldg(dp + r * cq);
+    const float4 v = pad0(__ldg(xp + r * cq), c4, g.C), d = pad0(__ldg(dp + r * cq), c4, g.C);
     float gx, gy, gz, gw, hx, hy, hz, hw;
     NA_GRAD_ELEM(gx, hx, v.x, d.x, a.x, b.x, mu.x, rs.x)
     NA_GRAD_ELEM(gy, hy, v.y, d.y, a.y, b.y, mu.y, rs.y)
@@ -333,16 +367,17 @@ bn_apply_pool_kernel(const NaGeom g, const PoolGeom pg, const float *__restrict_
                      const float *__restrict__ coef_b, int relu, int tf32, float *__restrict__ y) {
   const int lane = threadIdx.x % g.lanes, slot = threadIdx.x / g.lanes;
   const int c4 = blockIdx.y * g.lanes + lane;
-  if (slot >= g.slots || c4 * 4 >= g.C) return;
+  if (slot >= g.slots || c4 * 4 >= g.Cs) return;
   const float4 a = __ldg(reinterpret_cast<const float4 *>(coef_a) + c4);
   const float4 b = __ldg(reinterpret_cast<const float4 *>(coef_b) + c4);
   const float4 *xp = reinterpret_cast<const float4 *>(x) + c4;
   float4 *yp = reinterpret_cast<float4 *>(y) + c4;
-  const long long stride = (long long)gridDim.x * g.slots, cq = g.C / 4, down = (long long)pg.W * cq;
+  const long long stride = (long long)gridDim.x * g.slots, cq = g.Cs / 4, down = (long long)pg.W * cq;
 #pragma unroll 2
   for (long long r = (long long)blockIdx.x * g.slots + slot; r < pg.Mo; r += stride) {
     const float4 *p = xp + pool_base(pg, r, cq);
-    const float4 v0 = __ldg(p), v1 = __ldg(p + cq), v2 = __ldg(p + down), v3 = __ldg(p + down + cq);
+    const float4 v0 = pad0(__ldg(p), c4, g.C), v1 = pad0(__ldg(p + cq), c4, g.C), v2 = pad0(__ldg(p + down), c4, g.C),
+                 v3 = pad0(__ldg(p + down + cq), c4, g.C);
     float4 o;
     o.x = fmaxf(fmaxf(fmaf(v0.x, a.x, b.x), fmaf(v1.x, a.x, b.x)), fmaxf(fmaf(v2.x, a.x, b.x), fmaf(v3.x, a.x, b.x)));
     o.y = fmaxf(fmaxf(fmaf(v0.y, a.y, b.y), fmaf(v1.y, a.y, b.y)), fmaxf(fmaf(v2.y, a.y, b.y), fmaf(v3.y, a.y, b.y)));
@@ -369,21 +404,22 @@ bn_bwd_stats_pool_kernel(const NaGeom g, const PoolGeom pg, const float *__restr
                          float *__restrict__ part) {
   const int lane = threadIdx.x % g.lanes, slot = threadIdx.x / g.lanes;
   const int c4 = blockIdx.y * g.lanes + lane;
-  const bool active = slot < g.slots && c4 * 4 < g.C;
+  const bool active = slot < g.slots && c4 * 4 < g.Cs;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
   if (active) {
-    const float4 mu = __ldg(reinterpret_cast<const float4 *>(save_mean) + c4);
-    const float4 rs = __ldg(reinterpret_cast<const float4 *>(save_rstd) + c4);
+    const float4 mu = ldp4(save_mean, c4, g.C, 0.f);
+    const float4 rs = ldp4(save_rstd, c4, g.C, 0.f);
     float4 a, b;
-    coef_from_stats(gamma, beta, c4, mu, rs, a, b);
+    coef_from_stats(gamma, beta, c4, g.C, mu, rs, a, b);
     const float4 *xp = reinterpret_cast<const float4 *>(x) + c4;
     const float4 *dp = reinterpret_cast<const float4 *>(dy) + c4;
-    const long long stride = (long long)gridDim.x * g.slots, cq = g.C / 4, down = (long long)pg.W * cq;
+    const long long stride = (long long)gridDim.x * g.slots, cq = g.Cs / 4, down = (long long)pg.W * cq;
 #pragma unroll 2
     for (long long r = (long long)blockIdx.x * g.slots + slot; r < pg.Mo; r += stride) {
       const float4 *p = xp + pool_base(pg, r, cq);
-      const float4 v0 = __ldg(p), v1 = __ldg(p + cq), v2 = __ldg(p + down), v3 = __ldg(p + down + cq);
-      const float4 d = __ldg(dp + r * cq);
+      const float4 v0 = pad0(__ldg(p), c4, g.C), v1 = pad0(__ldg(p + cq), c4, g.C), v2 = pad0(__ldg(p + down), c4, g.C),
+                 v3 = pad0(__ldg(p + down + cq), c4, g.C);
+      const float4 d = pad0(__ldg(dp + r * cq), c4, g.C);
       float gx, gy, gz, gw, hx, hy, hz, hw;
       int jx, jy, jz, jw;
       NA_POOL_ELEM(gx, jx, hx, v0.x, v1.x, v2.x, v3.x, d.x, a.x, b.x, mu.x, rs.x)
@@ -417,23 +453,24 @@ bn_bwd_apply_pool_kernel(const NaGeom g, const PoolGeom pg, const float *__restr
                          float *__restrict__ dx) {
   const int lane = threadIdx.x % g.lanes, slot = threadIdx.x / g.lanes;
   const int c4 = blockIdx.y * g.lanes + lane;
-  if (slot >= g.slots || c4 * 4 >= g.C) return;
-  const float4 mu = __ldg(reinterpret_cast<const float4 *>(save_mean) + c4);
-  const float4 rs = __ldg(reinterpret_cast<const float4 *>(save_rstd) + c4);
+  if (slot >= g.slots || c4 * 4 >= g.Cs) return;
+  const float4 mu = ldp4(save_mean, c4, g.C, 0.f);
+  const float4 rs = ldp4(save_rstd, c4, g.C, 0.f);
   float4 a, b;
-  coef_from_stats(gamma, beta, c4, mu, rs, a, b);
+  coef_from_stats(gamma, beta, c4, g.C, mu, rs, a, b);
   const float4 k1 = __ldg(reinterpret_cast<const float4 *>(c1) + c4);
   const float4 k2 = __ldg(reinterpret_cast<const float4 *>(c2) + c4);
   const float4 *xp = reinterpret_cast<const float4 *>(x) + c4;
   const float4 *dp = reinterpret_cast<const float4 *>(dy) + c4;
   float4 *op = reinterpret_cast<float4 *>(dx) + c4;
-  const long long stride = (long long)gridDim.x * g.slots, cq = g.C / 4, down = (long long)pg.W * cq;
+  const long long stride = (long long)gridDim.x * g.slots, cq = g.Cs / 4, down = (long long)pg.W * cq;
 #pragma unroll 2
   for (long long r = (long long)blockIdx.x * g.slots + slot; r < pg.Mo; r += stride) {
     const long long base = pool_base(pg, r, cq);
     const float4 *p = xp + base;
-    const float4 v0 = __ldg(p), v1 = __ldg(p + cq), v2 = __ldg(p + down), v3 = __ldg(p + down + cq);
-    const float4 d = __ldg(dp + r * cq);
+    const float4 v0 = pad0(__ldg(p), c4, g.C), v1 = pad0(__ldg(p + cq), c4, g.C), v2 = pad0(__ldg(p + down), c4, g.C),
+                 v3 = pad0(__ldg(p + down + cq), c4, g.C);
+    const float4 d = pad0(__ldg(dp + r * cq), c4, g.C);
     float4 o0, o1, o2, o3;
     NA_POOL_DX(o0.x, o1.x, o2.x, o3.x, v0.x, v1.x, v2.x, v3.x, d.x, a.x, b.x, mu.x, rs.x, k1.x, k2.x)
     NA_POOL_DX(o0.y, o1.y, o2.y, o3.y, v0.y, v1.y, v2.y, v3.y, d.y, a.y, b.y, mu.y, rs.y, k1.y, k2.y)
@@ -444,16 +481,16 @@ bn_bwd_apply_pool_kernel(const NaGeom g, const PoolGeom pg, const float *__restr
   }
 }
 
-bool na_args_ok(const void *x, long long M, int C) {
-  return M > 0 && C > 0 && C % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+bool na_args_ok(const void *x, long long M, int C, int Cs) {
+  return M > 0 && C > 0 && Cs >= C && Cs % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
 }
 
 }  // namespace
 
-// scratch layout: [coef_a C][coef_b C][c1 C][c2 C][partials blocks*C*2]
-static size_t na_ws_bytes(long long M, int C) {
-  NaGeom g = na_geom(M, C, NA_STATS_THREADS);
-  return ((size_t)4 * C + (size_t)na_blocks(g, NA_STATS_PER_SM) * C * 2) * sizeof(float) + 64;
+// scratch layout: [coef_a Cs][coef_b Cs][c1 Cs][c2 Cs][partials blocks*Cs*2]
+static size_t na_ws_bytes(long long M, int Cs) {
+  NaGeom g = na_geom(M, Cs, Cs, NA_STATS_THREADS);
+  return ((size_t)4 * Cs + (size_t)na_blocks(g, NA_STATS_PER_SM) * Cs * 2) * sizeof(float) + 64;
 }
 
 }  // namespace cpgb
@@ -463,8 +500,8 @@ using namespace cpgb;
 extern "C" {
 
 size_t cpgb_bn_workspace_bytes(int64_t M, int32_t C) {
-  if (M <= 0 || C <= 0 || C % 4) return 0;
-  return na_ws_bytes(M, C);
+  if (M <= 0 || C <= 0) return 0;
+  return na_ws_bytes(M, (C + 3) & ~3);
 }
 
 static bool pool_geom(int64_t M, int32_t pool_h, int32_t pool_w, PoolGeom *pg) {
@@ -473,38 +510,44 @@ static bool pool_geom(int64_t M, int32_t pool_h, int32_t pool_w, PoolGeom *pg) {
   return true;
 }
 
-int cpgb_bn_relu_fwd(const float *x, int64_t M, int32_t C, const float *gamma, const float *beta, float *running_mean,
-                     float *running_var, int64_t *num_batches_tracked, int32_t training, float momentum, float eps,
-                     int32_t relu, int32_t pool_h, int32_t pool_w, int32_t tf32_out, float *y, float *save_mean,
-                     float *save_rstd, void *ws, size_t ws_bytes, void *stream) {
+// ldc: floats between consecutive pixels of x / y / dy / dx; 0 means dense (= C, which must then be a multiple of 4)
+static int na_stride(int32_t C, int32_t ldc) { return ldc > 0 ? ldc : C; }
+
+int cpgb_bn_relu_fwd(const float *x, int64_t M, int32_t C, int32_t ldc, const float *gamma, const float *beta,
+                     float *running_mean, float *running_var, int64_t *num_batches_tracked, int32_t training,
+                     float momentum, float eps, int32_t relu, int32_t pool_h, int32_t pool_w, int32_t tf32_out, float *y,
+                     float *save_mean, float *save_rstd, void *ws, size_t ws_bytes, void *stream) {
   PoolGeom pg;
   const bool pool = pool_h != 0 || pool_w != 0;
+  const int Cs = na_stride(C, ldc);
   if (pool && !pool_geom(M, pool_h, pool_w, &pg)) {
     set_error("cpgb_bn_relu_fwd: 2x2 pooling needs even H, W with M = N*H*W"); return CPGB_EINVAL;
   }
-  if (!na_args_ok(x, M, C) || !y || (reinterpret_cast<uintptr_t>(y) & 15)) {
-    set_error("cpgb_bn_relu_fwd: needs NHWC fp32 with C %% 4 == 0 and 16-byte aligned x / y"); return CPGB_EINVAL;
+  if (!na_args_ok(x, M, C, Cs) || !y || (reinterpret_cast<uintptr_t>(y) & 15)) {
+    set_error("cpgb_bn_relu_fwd: needs NHWC fp32 with a pixel stride that is a multiple of 4 and 16-byte aligned x / y");
+    return CPGB_EINVAL;
   }
-  if (!ws || ws_bytes < na_ws_bytes(M, C) || (reinterpret_cast<uintptr_t>(ws) & 15)) {
-    set_error("cpgb_bn_relu_fwd: workspace %zu < %zu", ws_bytes, na_ws_bytes(M, C)); return CPGB_EWORKSPACE;
+  if (!ws || ws_bytes < na_ws_bytes(M, Cs) || (reinterpret_cast<uintptr_t>(ws) & 15)) {
+    set_error("cpgb_bn_relu_fwd: workspace %zu < %zu", ws_bytes, na_ws_bytes(M, Cs)); return CPGB_EWORKSPACE;
   }
   if (training ? (!save_mean || !save_rstd) : (!running_mean || !running_var)) {
     set_error("cpgb_bn_relu_fwd: missing statistics buffers"); return CPGB_EINVAL;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  NaGeom g = na_geom(M, C);
-  float *coef_a = reinterpret_cast<float *>(ws), *coef_b = coef_a + C, *part = coef_a + 4 * C;
+  NaGeom g = na_geom(M, C, Cs);
+  float *coef_a = reinterpret_cast<float *>(ws), *coef_b = coef_a + Cs, *part = coef_a + 4 * Cs;
   if (training) {
-    const NaGeom gs = na_geom(M, C, NA_STATS_THREADS);
+    const NaGeom gs = na_geom(M, C, Cs, NA_STATS_THREADS);
     const int nb = na_blocks(gs, NA_STATS_PER_SM);
     bn_stats_kernel<<<dim3(nb, gs.cchunks), NA_STATS_THREADS, 0, st>>>(gs, x, part);
     CPGB_LAUNCH_OK("bn_stats");
-    bn_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(part, nb, C, M, gamma, beta, running_mean, running_var, momentum,
-                                                        eps, save_mean, save_rstd, coef_a, coef_b,
-                                                        reinterpret_cast<long long *>(num_batches_tracked));
+    bn_finalize_kernel<<<(Cs + 7) / 8, 256, 0, st>>>(part, nb, C, Cs, M, gamma, beta, running_mean, running_var, momentum,
+                                                         eps, save_mean, save_rstd, coef_a, coef_b,
+                                                         reinterpret_cast<long long *>(num_batches_tracked));
     CPGB_LAUNCH_OK("bn_finalize");
   } else {
-    bn_eval_coef_kernel<<<(C + 127) / 128, 128, 0, st>>>(C, gamma, beta, running_mean, running_var, eps, coef_a, coef_b);
+    bn_eval_coef_kernel<<<(Cs + 127) / 128, 128, 0, st>>>(C, Cs, gamma, beta, running_mean, running_var, eps, coef_a,
+                                                          coef_b);
     CPGB_LAUNCH_OK("bn_eval_coef");
   }
   if (pool) {
@@ -518,26 +561,28 @@ int cpgb_bn_relu_fwd(const float *x, int64_t M, int32_t C, const float *gamma, c
   return CPGB_OK;
 }
 
-int cpgb_bn_relu_bwd(const float *x, const float *dy, int64_t M, int32_t C, const float *gamma, const float *beta,
-                     const float *mean, const float *rstd, int32_t training, int32_t relu, int32_t pool_h,
-                     int32_t pool_w, int32_t tf32_out, float *dx, float *dgamma, float *dbeta, void *ws, size_t ws_bytes,
-                     void *stream) {
+int cpgb_bn_relu_bwd(const float *x, const float *dy, int64_t M, int32_t C, int32_t ldc, const float *gamma,
+                     const float *beta, const float *mean, const float *rstd, int32_t training, int32_t relu,
+                     int32_t pool_h, int32_t pool_w, int32_t tf32_out, float *dx, float *dgamma, float *dbeta, void *ws,
+                     size_t ws_bytes, void *stream) {
   PoolGeom pg;
   const bool pool = pool_h != 0 || pool_w != 0;
+  const int Cs = na_stride(C, ldc);
   if (pool && !pool_geom(M, pool_h, pool_w, &pg)) {
     set_error("cpgb_bn_relu_bwd: 2x2 pooling needs even H, W with M = N*H*W"); return CPGB_EINVAL;
   }
-  if (!na_args_ok(x, M, C) || !dy || !dx || !mean || !rstd || (reinterpret_cast<uintptr_t>(dy) & 15) ||
+  if (!na_args_ok(x, M, C, Cs) || !dy || !dx || !mean || !rstd || (reinterpret_cast<uintptr_t>(dy) & 15) ||
       (reinterpret_cast<uintptr_t>(dx) & 15)) {
-    set_error("cpgb_bn_relu_bwd: needs NHWC fp32 with C %% 4 == 0 and 16-byte aligned tensors"); return CPGB_EINVAL;
+    set_error("cpgb_bn_relu_bwd: needs NHWC fp32 with a pixel stride that is a multiple of 4 and 16-byte aligned tensors");
+    return CPGB_EINVAL;
   }
-  if (!ws || ws_bytes < na_ws_bytes(M, C) || (reinterpret_cast<uintptr_t>(ws) & 15)) {
-    set_error("cpgb_bn_relu_bwd: workspace %zu < %zu", ws_bytes, na_ws_bytes(M, C)); return CPGB_EWORKSPACE;
+  if (!ws || ws_bytes < na_ws_bytes(M, Cs) || (reinterpret_cast<uintptr_t>(ws) & 15)) {
+    set_error("cpgb_bn_relu_bwd: workspace %zu < %zu", ws_bytes, na_ws_bytes(M, Cs)); return CPGB_EWORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  NaGeom g = na_geom(M, C);
-  float *c1 = reinterpret_cast<float *>(ws) + 2 * C, *c2 = c1 + C, *part = c2 + C;
-  const NaGeom gs = na_geom(M, C, NA_STATS_THREADS);
+  NaGeom g = na_geom(M, C, Cs);
+  float *c1 = reinterpret_cast<float *>(ws) + 2 * Cs, *c2 = c1 + Cs, *part = c2 + Cs;
+  const NaGeom gs = na_geom(M, C, Cs, NA_STATS_THREADS);
   int nb;
   if (pool) {
     NaGeom gp = gs;
@@ -550,7 +595,7 @@ int cpgb_bn_relu_bwd(const float *x, const float *dy, int64_t M, int32_t C, cons
     bn_bwd_stats_kernel<<<dim3(nb, gs.cchunks), NA_STATS_THREADS, 0, st>>>(gs, x, dy, gamma, beta, mean, rstd, relu, part);
   }
   CPGB_LAUNCH_OK("bn_bwd_stats");
-  bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(part, nb, C, M, training, dgamma, dbeta, c1, c2);
+  bn_bwd_finalize_kernel<<<(Cs + 7) / 8, 256, 0, st>>>(part, nb, C, Cs, M, training, dgamma, dbeta, c1, c2);
   CPGB_LAUNCH_OK("bn_bwd_finalize");
   if (pool) {
     NaGeom gp = g;

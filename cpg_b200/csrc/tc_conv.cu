@@ -210,6 +210,18 @@ __device__ __forceinline__ void epilogue_rows(uint32_t tmem_base, int quad, int 
   __syncwarp();
 }
 
+// bias[col .. col+3], zero beyond the last real channel (ragged channel counts are stored padded to 4)
+__device__ __forceinline__ float4 load_bias4(const float *__restrict__ bias, int col, int nvalid) {
+  if (col + 4 <= nvalid && (reinterpret_cast<uintptr_t>(bias + col) & 15) == 0)
+    return __ldg(reinterpret_cast<const float4 *>(bias + col));
+  float4 b;
+  b.x = col + 0 < nvalid ? __ldg(bias + col + 0) : 0.f;
+  b.y = col + 1 < nvalid ? __ldg(bias + col + 1) : 0.f;
+  b.z = col + 2 < nvalid ? __ldg(bias + col + 2) : 0.f;
+  b.w = col + 3 < nvalid ? __ldg(bias + col + 3) : 0.f;
+  return b;
+}
+
 // ------------------------------------------------------------------------------------------
 // fprop / dgrad kernel
 // ------------------------------------------------------------------------------------------
@@ -221,7 +233,8 @@ struct ConvGemmParams {
   int off_h, off_w;        // input coord = output coord + off + tap_index * step
   int step_h, step_w;
   int kblocks;             // 32-wide reduction blocks per tap
-  int ncols;               // valid output channels
+  int ncols;               // output channels stored per pixel (the real count rounded up to 4: pad lanes get zeros)
+  int nvalid;              // real output channels (bias is only defined for these)
   int iters_per_split;     // split-K over the (tap, k-block) loop; blockIdx.z = split
   int nstage;              // depth of the smem ring (3: two CTAs share an SM; more: one CTA, deeper prefetch)
   int mn_layout, mn_lbo, mn_sbo, mn_kadv;   // MN-major operand descriptor fields
@@ -354,7 +367,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int col = col0 + h + c4;
         if (rp != nullptr && col < p.ncols) {   // ncols % 4 == 0
           if (bias) {
-            const float4 b = __ldg(reinterpret_cast<const float4 *>(bias + col));
+            const float4 b = load_bias4(bias, col, p.nvalid);
             v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
           }
           *reinterpret_cast<float4 *>(rp + h + c4) = v;
@@ -373,7 +386,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // out[i] = sum_s part[s][i] (+ bias[i % ncols])
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float4 *__restrict__ part, int splits, long long n4, long long split_stride4, int ncols4,
-                     const float4 *__restrict__ bias, float4 *__restrict__ out) {
+                     int nvalid, const float *__restrict__ bias, float4 *__restrict__ out) {
   griddep_launch_dependents();
   griddep_wait();
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -395,7 +408,7 @@ splitk_reduce_kernel(const float4 *__restrict__ part, int splits, long long n4, 
       a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
     }
     if (bias) {
-      const float4 b = __ldg(bias + (i % ncols4));
+      const float4 b = load_bias4(bias, (int)(i % ncols4) * 4, nvalid);
       a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
     }
     out[i] = a;
@@ -416,6 +429,7 @@ struct WgradParams {
   int S, RS;               // filter width, taps
   int pad_h, pad_w, dil_h, dil_w;
   int chunks, chunks_per_split;
+  int ragged;              // operands come as one bounded 4-D box per 32-channel block (ragged channel counts)
   int ctiles;              // number of BN-wide channel tiles
   int K, C, Cg;            // Cg = C rounded up to 4: row stride of gpart
   int mn_layout, mn_lbo, mn_sbo, mn_kadv;
@@ -520,18 +534,39 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
         if (HALO) {
           // one X tile with (S-1)*dil extra columns per block; the taps are row offsets into it
           mbar_arrive_expect_tx(full + stage, Cfg::A_BYTES + (BN / 32) * p.h_box_bytes);
-          tma_load_5d(sa, &tmDY, full + stage, 0, q0, p0, n0, k0 >> 5);
+          if (p.ragged) {
 #pragma unroll
-          for (int b = 0; b < BN / 32; ++b)
-            tma_load_5d(sa + Cfg::A_BYTES + b * p.h_pitch, &tmX, full + stage, 0, q0 - p.pad_w,
-                        p0 - p.pad_h + r * p.dil_h, n0, (c0 >> 5) + b);
+            for (int b = 0; b < 4; ++b) tma_load_4d(sa + b * 4096, &tmDY, full + stage, k0 + 32 * b, q0, p0, n0);
+#pragma unroll
+            for (int b = 0; b < BN / 32; ++b)
+              tma_load_4d(sa + Cfg::A_BYTES + b * p.h_pitch, &tmX, full + stage, c0 + 32 * b, q0 - p.pad_w,
+                          p0 - p.pad_h + r * p.dil_h, n0);
+          } else {
+            tma_load_5d(sa, &tmDY, full + stage, 0, q0, p0, n0, k0 >> 5);
+#pragma unroll
+            for (int b = 0; b < BN / 32; ++b)
+              tma_load_5d(sa + Cfg::A_BYTES + b * p.h_pitch, &tmX, full + stage, 0, q0 - p.pad_w,
+                          p0 - p.pad_h + r * p.dil_h, n0, (c0 >> 5) + b);
+          }
         } else {
           mbar_arrive_expect_tx(full + stage, Cfg::STAGE_BYTES);
-          tma_load_5d(sa, &tmDY, full + stage, 0, q0, p0, n0, k0 >> 5);
+          if (p.ragged) {
+            // out-of-range channels (and whole out-of-range blocks) are zero filled by the TMA unit
 #pragma unroll
-          for (int s = 0; s < TG; ++s)
-            tma_load_5d(sa + Cfg::A_BYTES + s * Cfg::B_BYTES, &tmX, full + stage, 0,
-                        q0 - p.pad_w + (s0 + s) * p.dil_w, p0 - p.pad_h + r * p.dil_h, n0, c0 >> 5);
+            for (int b = 0; b < 4; ++b) tma_load_4d(sa + b * 4096, &tmDY, full + stage, k0 + 32 * b, q0, p0, n0);
+#pragma unroll
+            for (int s = 0; s < TG; ++s)
+#pragma unroll
+              for (int b = 0; b < BN / 32; ++b)
+                tma_load_4d(sa + Cfg::A_BYTES + s * Cfg::B_BYTES + b * 4096, &tmX, full + stage, c0 + 32 * b,
+                            q0 - p.pad_w + (s0 + s) * p.dil_w, p0 - p.pad_h + r * p.dil_h, n0);
+          } else {
+            tma_load_5d(sa, &tmDY, full + stage, 0, q0, p0, n0, k0 >> 5);
+#pragma unroll
+            for (int s = 0; s < TG; ++s)
+              tma_load_5d(sa + Cfg::A_BYTES + s * Cfg::B_BYTES, &tmX, full + stage, 0,
+                          q0 - p.pad_w + (s0 + s) * p.dil_w, p0 - p.pad_h + r * p.dil_h, n0, c0 >> 5);
+          }
         }
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
       }
@@ -794,7 +829,8 @@ struct Str4 { int64_t s[4]; };
 static Str4 norm_strides(const int64_t in[4], int C, int H, int W, int N) {
   Str4 o;
   o.s[1] = in[1];
-  o.s[3] = W == 1 ? C : in[3];
+  // pixel stride of a one-pixel-wide tensor: whatever the outer dimensions say (a padded layout keeps its padding)
+  o.s[3] = W == 1 ? (H > 1 ? in[2] : N > 1 ? in[0] : (int64_t)((C + 3) & ~3)) : in[3];
   o.s[2] = H == 1 ? o.s[3] * W : in[2];
   o.s[0] = N == 1 ? o.s[2] * H : in[0];
   if (C == 1) o.s[1] = 1;
@@ -813,19 +849,26 @@ static Str4 y_strides(const cpgb_conv_desc &d) { return norm_strides(d.ys, d.K, 
 // count itself may be odd, e.g. the 3-channel stem stored with a pixel stride of 4), K % 4 == 0
 // for vector stores; dgrad additionally C % 4 == 0; wgrad K % 32 == 0, C % 32 == 0 or C < 32,
 // filter width 1 or 3.
+// Ragged channel counts (the grown networks: sqrt(1.5) * {64, 128, 256, 512, 4096} = 78 / 156 / 313 / 627 / 5016,
+// CPG_cifar100_main_normal.py:115) are "padded on pack": the staged weight operand is zero padded to whole
+// 32-channel blocks, TMA bounds every activation load at the real channel count (out-of-bounds lanes read as
+// zero), and an activation tensor whose channel count is not a multiple of 4 is STORED with its pixel stride
+// rounded up to 4 floats -- the kernels then write whole 16-byte groups, zeros in the pad lanes.
+static inline int up4(int v) { return (v + 3) & ~3; }
 static bool implicit_eligible(const cpgb_conv_desc &d, int op) {
   if (d.groups != 1 || d.stride_h != 1 || d.stride_w != 1) return false;
-  if (d.K % 4) return false;
   if (d.R * d.S > 49 || d.N < 1) return false;
-  if (!nhwc_ok(x_strides(d), d.C) || !nhwc_ok(y_strides(d), d.K)) return false;
+  const Str4 xs = x_strides(d), ys = y_strides(d);
+  if (!nhwc_ok(xs, d.C) || !nhwc_ok(ys, d.K)) return false;
   if (d.W > 4096 || d.H > 4096) return false;
-  if (op == 1 && d.C % 4) return false;
-  if (op == 2) {
-    if ((d.C % 32 && d.C > 32) || d.K % 32) return false;
-    if (d.S != 1 && d.S != 3) return false;
-  }
+  if (op == 0 && ys.s[3] < up4(d.K)) return false;     // y is written in 16-byte groups
+  if (op == 1 && xs.s[3] < up4(d.C)) return false;     // dx likewise
+  if (op == 2 && d.S != 1 && d.S != 3) return false;
   return true;
 }
+// wgrad operand loads: whole 32-channel blocks through one 5-D box per operand, or (ragged) one bounded 4-D box
+// per 32-channel block
+static inline bool wgrad_ragged(const cpgb_conv_desc &d) { return (d.C % 32 && d.C > 32) || d.K % 32; }
 static inline int cg_of(const cpgb_conv_desc &d) { return (d.C + 3) & ~3; }   // row stride of the wgrad partials
 
 static inline int cp_of(const cpgb_conv_desc &d) { return (d.C + 31) / 32 * 32; }
@@ -913,10 +956,10 @@ static GemmPlan plan_gemm(int Qo, int Po, int No, int ncols, int iters, const St
   return g;
 }
 static GemmPlan plan_fprop(const cpgb_conv_desc &d) {
-  return plan_gemm(d.Q, d.P, d.N, d.K, d.R * d.S * (cp_of(d) / 32), y_strides(d));
+  return plan_gemm(d.Q, d.P, d.N, up4(d.K), d.R * d.S * (cp_of(d) / 32), y_strides(d));
 }
 static GemmPlan plan_dgrad(const cpgb_conv_desc &d) {
-  return plan_gemm(d.W, d.H, d.N, d.C, d.R * d.S * cdiv_i(d.K, 32), x_strides(d));
+  return plan_gemm(d.W, d.H, d.N, up4(d.C), d.R * d.S * cdiv_i(d.K, 32), x_strides(d));
 }
 static size_t plan_partial_bytes(const GemmPlan &g) {
   return g.splits > 1 ? (size_t)g.splits * g.out_elems * sizeof(float) : 0;
@@ -1014,12 +1057,12 @@ static int launch_conv_gemm(const CUtensorMap &ta, const CUtensorMap &tb, ConvGe
 
 // map of an NHWC activation tensor: dims (C, W, H, N)
 static int make_act_map(CUtensorMap *m, const float *base, int C, int W, int H, int N, const Str4 &sv,
-                        const PixBox &b) {
+                        const PixBox &b, bool mn_major = false, int box_w = 0) {
   const int64_t *s = sv.s;
   uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N};
   uint64_t str[3] = {(uint64_t)s[3] * 4, (uint64_t)s[2] * 4, (uint64_t)s[0] * 4};
-  uint32_t box[4] = {32, 1u << b.lq, 1u << b.lp, 1u << b.ln};
-  return make_map(m, base, 4, dims, str, box);
+  uint32_t box[4] = {32, box_w ? (uint32_t)box_w : 1u << b.lq, 1u << b.lp, 1u << b.ln};
+  return make_map(m, base, 4, dims, str, box, mn_major);
 }
 
 // common tail of fprop / dgrad: launch the GEMM (split or not) and, when split, the reduction
@@ -1046,8 +1089,7 @@ static int run_gemm(const GemmPlan &g, const CUtensorMap &ta, const CUtensorMap 
   const long long n4 = g.out_elems / 4;
   int grid = (int)std::min<long long>((n4 + 255) / 256, (long long)num_sms() * 8);
   CPGB_CUDA_OK(launch_pdl(splitk_reduce_kernel, dim3(grid), dim3(256), 0, st, reinterpret_cast<const float4 *>(part),
-                          g.splits, n4, n4, p.ncols / 4, reinterpret_cast<const float4 *>(bias),
-                          reinterpret_cast<float4 *>(out)));
+                          g.splits, n4, n4, p.ncols / 4, p.nvalid, bias, reinterpret_cast<float4 *>(out)));
   CPGB_LAUNCH_OK("splitk_reduce");
   return CPGB_OK;
 }
@@ -1072,7 +1114,7 @@ static int implicit_fprop(const cpgb_conv_desc &d, const float *x, const float *
   ConvGemmParams p;
   p.Qo = d.Q; p.Po = d.P; p.No = d.N; p.S = d.S; p.taps = RS;
   p.off_h = -d.pad_h; p.off_w = -d.pad_w; p.step_h = d.dil_h; p.step_w = d.dil_w;
-  p.kblocks = Cp / 32; p.ncols = d.K;
+  p.kblocks = Cp / 32; p.ncols = up4(d.K); p.nvalid = d.K;
   { Str4 ys = y_strides(d); p.o_sn = ys.s[0]; p.o_sh = ys.s[2]; p.o_sw = ys.s[3]; }
   return run_gemm<false>(g, ta, tb, p, y, bias, part, part_bytes, st);
 }
@@ -1099,7 +1141,7 @@ static int implicit_dgrad(const cpgb_conv_desc &d, const float *dy, const float 
   ConvGemmParams p;
   p.Qo = d.W; p.Po = d.H; p.No = d.N; p.S = d.S; p.taps = RS;
   p.off_h = d.pad_h; p.off_w = d.pad_w; p.step_h = -d.dil_h; p.step_w = -d.dil_w;
-  p.kblocks = cdiv_i(d.K, 32); p.ncols = d.C;
+  p.kblocks = cdiv_i(d.K, 32); p.ncols = up4(d.C); p.nvalid = d.C;
   { Str4 xs = x_strides(d); p.o_sn = xs.s[0]; p.o_sh = xs.s[2]; p.o_sw = xs.s[3]; }
   return run_gemm<true>(g, ta, tb, p, dx, nullptr, part, part_bytes, st);
 }
@@ -1150,8 +1192,12 @@ static int implicit_wgrad_fused(const cpgb_conv_desc &d, const float *x, const f
   const size_t need = fused ? 0 : (size_t)pl.splits * d.K * RS * cg_of(d) * sizeof(float);
   if (ws_bytes < need) { set_error("workspace %zu < %zu", ws_bytes, need); return CPGB_EWORKSPACE; }
   CUtensorMap tdy, tx;
-  if ((rc = make_act_map5(&tdy, dy, d.K, d.Q, d.P, d.N, y_strides(d), pl.box, 4))) return rc;
+  const bool ragged = wgrad_ragged(d);
+  if (ragged) rc = make_act_map(&tdy, dy, d.K, d.Q, d.P, d.N, y_strides(d), pl.box, true);
+  else rc = make_act_map5(&tdy, dy, d.K, d.Q, d.P, d.N, y_strides(d), pl.box, 4);
+  if (rc) return rc;
   WgradParams p;
+  p.ragged = ragged ? 1 : 0;
   if (pl.halo) {
     const int bq = 1 << pl.box.lq, bp = 1 << pl.box.lp, bn = 1 << pl.box.ln;
     const int wq = bq + (d.S - 1) * d.dil_w;           // X-tile columns per image row
@@ -1170,11 +1216,15 @@ static int implicit_wgrad_fused(const cpgb_conv_desc &d, const float *x, const f
                         (uint64_t)((d.C + 31) / 32)};
     uint64_t str[4] = {(uint64_t)xs.s[3] * 4, (uint64_t)xs.s[2] * 4, (uint64_t)xs.s[0] * 4, 128};
     uint32_t box[5] = {32, (uint32_t)wq, (uint32_t)bp, (uint32_t)bn, 1};
-    if ((rc = make_map(&tx, x, 5, dims, str, box, true))) return rc;
+    if (ragged) rc = make_act_map(&tx, x, d.C, d.W, d.H, d.N, xs, pl.box, true, wq);
+    else rc = make_map(&tx, x, 5, dims, str, box, true);
+    if (rc) return rc;
   } else {
     p.h_pitch = p.h_box_bytes = p.h_stage_bytes = p.h_nstage = p.h_base_mode = 0;
     for (int ks = 0; ks < 4; ++ks) p.h_krow[ks] = 0;
-    if ((rc = make_act_map5(&tx, x, d.C, d.W, d.H, d.N, x_strides(d), pl.box, pl.BN / 32))) return rc;
+    if (ragged) rc = make_act_map(&tx, x, d.C, d.W, d.H, d.N, x_strides(d), pl.box, true);
+    else rc = make_act_map5(&tx, x, d.C, d.W, d.H, d.N, x_strides(d), pl.box, pl.BN / 32);
+    if (rc) return rc;
   }
   p.cq = pl.box.tq; p.cp = pl.box.tp; p.cn = pl.box.tn; p.lq = pl.box.lq; p.lp = pl.box.lp;
   p.S = d.S; p.RS = RS; p.pad_h = d.pad_h; p.pad_w = d.pad_w; p.dil_h = d.dil_h; p.dil_w = d.dil_w;
@@ -1615,8 +1665,10 @@ static cpgb_conv_desc weight_desc(int K, int C, int R, int S, int stride_h, int 
   return d;
 }
 size_t tc_staged_bytes_for_weight(int K, int C, int R, int S, int stride_h, int stride_w, int groups) {
-  if (groups != 1 || K % 4 || K <= 0 || C <= 0 || R * S > 49) return 0;
-  return tc_staged_bytes(weight_desc(K, C, R, S, stride_h, stride_w, groups));
+  if (groups != 1 || K <= 0 || C <= 0 || R * S > 49) return 0;
+  const cpgb_conv_desc d = weight_desc(K, C, R, S, stride_h, stride_w, groups);
+  if (prefer_xcol(d) && K % 4) return 0;           // the explicit-im2col tier stores whole 16-byte groups of K
+  return tc_staged_bytes(d);
 }
 
 int tc_stage_weights_batched(int n, const float *const *w, const float *const *piggy, void *const *staged,

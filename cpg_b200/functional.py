@@ -20,9 +20,50 @@ def _ws(nbytes, device):
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
+def _up4(c):
+    return (c + 3) // 4 * 4
+
+
+def nhwc_pixel_stride(t):
+    """Elements between consecutive pixels if the logical-NCHW tensor `t` is stored channels-innermost with its
+    pixels in (n, h, w) order and no gaps other than channel padding, else None.  Dense torch.channels_last gives C;
+    cpg_b200 stores activations whose channel count is not a multiple of 4 with the stride rounded up to 4
+    ("padded NHWC": TMA and 16-byte accesses need 16-byte aligned pixels; the pad lanes carry no information)."""
+    n, c, h, w = t.shape
+    s = t.stride()
+    if c > 1 and s[1] != 1:
+        return None
+    ps = s[3] if w > 1 else s[2] if h > 1 else s[0] if n > 1 else _up4(c)
+    if ps < c or (w > 1 and h > 1 and s[2] != w * ps) or (n > 1 and s[0] != h * w * ps):
+        return None
+    return ps
+
+
+def empty_nhwc(shape, device, ps=None):
+    """Uninitialised logical-NCHW fp32 tensor in (padded) NHWC storage with pixel stride `ps` (default: C rounded
+    up to 4)."""
+    n, c, h, w = shape
+    ps = _up4(c) if ps is None else ps
+    buf = torch.empty((n, ps, h, w), dtype=torch.float32, device=device, memory_format=CL)
+    return buf if ps == c else buf[:, :c]
+
+
+def to_nhwc_aligned(t):
+    """`t` itself if its pixels are channels-innermost and 16-byte aligned, else a (padded) NHWC copy."""
+    ps = nhwc_pixel_stride(t)
+    if ps is not None and ps % 4 == 0:
+        return t
+    out = empty_nhwc(t.shape, t.device)
+    out.copy_(t)
+    return out
+
+
 def _dense4(t):
-    """Return t if it is dense NCHW or dense NHWC, else a dense NCHW copy."""
+    """Return t if it is dense NCHW, dense NHWC or padded NHWC, else a dense NCHW copy."""
     if t.is_contiguous() or t.is_contiguous(memory_format=CL):
+        return t
+    ps = nhwc_pixel_stride(t)
+    if ps is not None and ps % 4 == 0:
         return t
     return t.contiguous()
 
@@ -63,14 +104,24 @@ def is_tf32(t):
 
 
 def _is_dense(t):
-    return t.is_contiguous() or (t.dim() == 4 and t.is_contiguous(memory_format=CL))
+    if t.is_contiguous() or (t.dim() == 4 and t.is_contiguous(memory_format=CL)):
+        return True
+    if t.dim() == 4:                      # padded NHWC: dense but for the pad lanes
+        ps = nhwc_pixel_stride(t)
+        return ps is not None and ps % 4 == 0
+    return t.dim() == 2 and t.stride(1) == 1 and t.stride(0) >= t.shape[1]      # row-padded matrix
+
+
+def _span(t):
+    return 1 + sum((n - 1) * st for n, st in zip(t.shape, t.stride()))
 
 
 def round_tf32(lib, t):
-    """A tagged copy of the dense tensor `t` (same strides) rounded to the nearest TF32 value."""
-    out = torch.empty_like(t)          # preserves the strides of dense tensors
+    """A tagged copy of `t` (same strides; dense, or dense but for channel / row padding) rounded to the nearest
+    TF32 value."""
+    out = torch.empty_strided(t.shape, t.stride(), dtype=t.dtype, device=t.device)
     with torch.cuda.device(t.device):
-        _lib.check(lib.cpgb_round_tf32(_lib.ptr(t), _lib.ptr(out), t.numel(), _lib.stream_ptr()), 'cpgb_round_tf32')
+        _lib.check(lib.cpgb_round_tf32(_lib.ptr(t), _lib.ptr(out), _span(t), _lib.stream_ptr()), 'cpgb_round_tf32')
     return mark_tf32(out)
 
 
@@ -162,15 +213,16 @@ def _defer(device, tensors):
 
 
 def _backward_operands(lib, d, dy, dy_exact, x_exact, need_dx, need_w):
-    """Round dy once for dgrad + wgrad when a tcgen05 pass reads it; set the descriptor flags."""
+    """Round dy once for dgrad + wgrad when a tcgen05 pass reads it; set the descriptor flags.  Returns
+    (dy for the kernels, the caller's dy if a rounded copy replaced it else None)."""
     tc_d = need_dx and lib.cpgb_uses_tensor_cores(d, 1)
     tc_w = need_w and lib.cpgb_uses_tensor_cores(d, 2)
-    dy, dy_exact = _prepare_operand(lib, dy, dy_exact, bool(tc_d or tc_w))
+    dy_k, dy_exact = _prepare_operand(lib, dy, dy_exact, bool(tc_d or tc_w))
     d.flags = (_lib.FLAG_X_TF32 if x_exact else 0) | (_lib.FLAG_DY_TF32 if dy_exact else 0)
-    return dy
+    return dy_k, (dy if dy_k is not dy else None)
 
 
-def _backward_kernels(lib, ctx, d, x, dy, w, p, threshold, staged, need_dx, need_w, has_bias, dx):
+def _backward_kernels(lib, ctx, d, x, dy, w, p, threshold, staged, need_dx, need_w, has_bias, dx, dy_raw=None):
     """dgrad (+) wgrad with the fused epilogue for descriptor d.  Everything is allocated on the
     current stream.  The wgrad launch is forked onto a side stream: wgrad(l) only reads x(l) and dy(l),
     and nothing before optimizer.step() / the all-reduce reads dW, so the side stream is joined once at
@@ -222,8 +274,12 @@ def _backward_kernels(lib, ctx, d, x, dy, w, p, threshold, staged, need_dx, need
                 d, _lib.ptr(x), _lib.ptr(dy), _lib.ptr(w), _lib.ptr(p),
                 _lib.ptr(fuse.tmask) if fuse is not None else None,
                 fuse.cur if fuse is not None else 0, wd, (mode | _lib.GRAD_MERGED) if merged else mode,
-                _lib.ptr(dW), None if merged else _lib.ptr(dP), _lib.ptr(db), threshold, _lib.ptr(ws_w), ws_w.numel(),
-                wstream.cuda_stream), 'cpgb_conv2d_wgrad_fused')
+                _lib.ptr(dW), None if merged else _lib.ptr(dP), _lib.ptr(db) if dy_raw is None else None, threshold,
+                _lib.ptr(ws_w), ws_w.numel(), wstream.cuda_stream), 'cpgb_conv2d_wgrad_fused')
+            if db is not None and dy_raw is not None:
+                # the bias gradient is a plain fp32 sum: take it from the caller's dy, not from the TF32-rounded copy
+                _lib.check(lib.cpgb_conv2d_bias_grad(d, _lib.ptr(dy_raw), _lib.ptr(db), wstream.cuda_stream),
+                           'cpgb_conv2d_bias_grad')
             if fuse is not None and mod is not None:
                 mod._cpg_grads_final = True
             if slot is not None:
@@ -239,7 +295,7 @@ def _backward_kernels(lib, ctx, d, x, dy, w, p, threshold, staged, need_dx, need
             if defer:
                 # inputs and scratch only: holding the outputs too would raise their use count and make
                 # AccumulateGrad clone them on the main stream instead of adopting them
-                _defer(device, (x, dy, w, p, ws_w, fuse.tmask if fuse is not None else None))
+                _defer(device, (x, dy, dy_raw, w, p, ws_w, fuse.tmask if fuse is not None else None))
             else:
                 main.wait_stream(wstream)
     return dW, dP, db
@@ -277,20 +333,14 @@ class MaskedConv2dFn(torch.autograd.Function):
             raise _lib.CpgbError('SharableConv2d expects a 4-D input')
         if x.dtype != torch.float32 or not x.is_cuda:
             raise _lib.CpgbError(f'input must be a float32 CUDA tensor, got {x.dtype} on {x.device}')
-        x = _dense4(x)
-        if groups == 1 and tuple(stride) == (1, 1) and weight.shape[0] % 4 == 0:
-            # the tcgen05 kernels TMA-load NHWC activations whose pixel stride is a multiple of 16 B
-            if x.shape[1] % 4 == 0:
-                if not x.is_contiguous(memory_format=CL):
-                    x = x.contiguous(memory_format=CL)
-            else:
-                # odd channel count (the 3-channel stem): NHWC with the pixel stride padded to 4; the
-                # pad lanes are never read (TMA bounds the channel dimension at C)
-                n_, c_, h_, w_ = x.shape
-                xp = torch.empty((n_, (c_ + 3) // 4 * 4, h_, w_), dtype=x.dtype, device=x.device, memory_format=CL)
-                xv = xp[:, :c_]
-                xv.copy_(x)
-                x = xv
+        if groups == 1 and tuple(stride) == (1, 1):
+            # the tcgen05 kernels TMA-load NHWC activations whose pixel stride is a multiple of 16 B: dense
+            # channels_last when C % 4 == 0, else NHWC with the pixel stride padded to 4 (the 3-channel stem, the
+            # 78 / 313 / 627-channel grown networks); the pad lanes are never read (TMA bounds the channel
+            # dimension at C)
+            x = to_nhwc_aligned(x)
+        else:
+            x = _dense4(x)
         w = weight.detach().contiguous()
         p = piggymask.detach().contiguous() if piggymask is not None else None
         b = bias.detach().contiguous() if bias is not None else None
@@ -302,9 +352,10 @@ class MaskedConv2dFn(torch.autograd.Function):
         Q = (W + 2 * padding[1] - dilation[1] * (S - 1) - 1) // stride[1] + 1
         if P <= 0 or Q <= 0:
             raise RuntimeError('kernel size larger than the (padded) input')
-        fmt = CL if (channels_last_out or (x.is_contiguous(memory_format=CL) and not x.is_contiguous())) \
-            else torch.contiguous_format
-        y = torch.empty((N, K, P, Q), dtype=torch.float32, device=x.device, memory_format=fmt)
+        if channels_last_out or (nhwc_pixel_stride(x) is not None and not x.is_contiguous()):
+            y = empty_nhwc((N, K, P, Q), x.device)        # padded NHWC when K % 4 != 0
+        else:
+            y = torch.empty((N, K, P, Q), dtype=torch.float32, device=x.device)
         d = _lib.conv_desc(x.shape, x.stride(), w.shape, y.shape, y.stride(), stride, padding, dilation, groups)
         # TF32 operands are rounded to nearest, once, and the rounded copy is what the backward pass reuses
         need_w = weight.requires_grad or (piggymask is not None and piggymask.requires_grad)
@@ -331,17 +382,38 @@ class MaskedConv2dFn(torch.autograd.Function):
         x, w, p = ctx.saved_tensors
         stride, padding, dilation, groups, threshold = ctx.geom
         dy_exact = is_tf32(dy)        # layout copies below keep the values
-        dy = _dense4(dy)
-        if x.is_contiguous(memory_format=CL) and not dy.is_contiguous(memory_format=CL):
-            dy = dy.contiguous(memory_format=CL)
+        if nhwc_pixel_stride(x) is not None and not x.is_contiguous():
+            dy = to_nhwc_aligned(dy)
+        else:
+            dy = _dense4(dy)
         d = _lib.conv_desc(x.shape, x.stride(), w.shape, dy.shape, dy.stride(), stride, padding, dilation, groups)
         need_dx = ctx.needs_input_grad[0]
         need_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
-        dy = _backward_operands(lib, d, dy, dy_exact, ctx.x_exact, need_dx, need_w)
+        dy, dy_raw = _backward_operands(lib, d, dy, dy_exact, ctx.x_exact, need_dx, need_w)
         dx = torch.empty_strided(x.shape, x.stride(), dtype=x.dtype, device=x.device) if need_dx else None
         dW, dP, db = _backward_kernels(lib, ctx, d, x, dy, w, p, threshold, ctx.staged, need_dx, need_w,
-                                       ctx.has_bias, dx)
+                                       ctx.has_bias, dx, dy_raw if ctx.has_bias else None)
         return dx, dW, dP, db, None, None, None, None, None, None, None, None, None, None
+
+
+def _rows16(m):
+    """The 2-D matrix `m` with unit column stride and 16-byte aligned rows: itself, or a copy whose row stride is
+    rounded up to 4 floats (feature counts like 627 that are not a multiple of 4)."""
+    if m.stride(1) == 1 and m.stride(0) % 4 == 0 and m.stride(0) >= m.shape[1] and m.data_ptr() % 16 == 0:
+        return m
+    if m.shape[1] % 4 == 0:
+        return m.contiguous()
+    out = torch.empty((m.shape[0], _up4(m.shape[1])), dtype=m.dtype, device=m.device)[:, :m.shape[1]]
+    out.copy_(m)
+    return out
+
+
+def _linear_desc(lib, M, I, O, ldx, ldy):
+    d = _lib.ConvDesc()
+    lib.cpgb_linear_desc(d, M, I, O)
+    d.xs[0] = d.xs[2] = d.xs[3] = ldx if M > 1 or ldx >= I else I
+    d.ys[0] = d.ys[2] = d.ys[3] = ldy if M > 1 or ldy >= O else O
+    return d
 
 
 class MaskedLinearFn(torch.autograd.Function):
@@ -359,13 +431,17 @@ class MaskedLinearFn(torch.autograd.Function):
         O, I = w.shape
         if x.shape[-1] != I:
             raise RuntimeError(f'size mismatch: input features {x.shape[-1]} vs weight {tuple(w.shape)}')
-        x2 = x.reshape(-1, I).contiguous()
+        x2 = _rows16(x.reshape(-1, I))
         M = x2.shape[0]
         # allocated in its final shape: returning a view of a custom Function's output would
         # forbid the in-place ReLU that follows it in models/vgg.py:116-118
-        y = torch.empty((*x.shape[:-1], O), dtype=torch.float32, device=x.device)
-        d = _lib.ConvDesc()
-        lib.cpgb_linear_desc(d, M, I, O)
+        if O % 4 == 0 or x.dim() != 2:
+            y = torch.empty((*x.shape[:-1], O), dtype=torch.float32, device=x.device)
+            ldy = O
+        else:                     # rows padded to 16 bytes (an odd O with ldy = O takes the CUDA-core kernels)
+            ldy = _up4(O)
+            y = torch.empty((M, ldy), dtype=torch.float32, device=x.device)[:, :O]
+        d = _linear_desc(lib, M, I, O, x2.stride(0), ldy)
         need_w = weight.requires_grad or (piggymask is not None and piggymask.requires_grad)
         uses_tc = lib.cpgb_uses_tensor_cores(d, 0) or (need_w and lib.cpgb_uses_tensor_cores(d, 2))
         x2, x_exact = _prepare_operand(lib, x2, bool(x_exact), bool(uses_tc))
@@ -389,15 +465,14 @@ class MaskedLinearFn(torch.autograd.Function):
         x2, w, p = ctx.saved_tensors
         O, I = w.shape
         M = x2.shape[0]
-        dy2 = dy.reshape(M, O).contiguous()
-        d = _lib.ConvDesc()
-        lib.cpgb_linear_desc(d, M, I, O)
+        dy2 = _rows16(dy.reshape(M, O))
+        d = _linear_desc(lib, M, I, O, x2.stride(0), dy2.stride(0))
         need_dx = ctx.needs_input_grad[0]
         need_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
-        dy2 = _backward_operands(lib, d, dy2, is_tf32(dy), ctx.x_exact, need_dx, need_w)
-        dx2 = torch.empty_like(x2) if need_dx else None
+        dy2, dy_raw = _backward_operands(lib, d, dy2, is_tf32(dy), ctx.x_exact, need_dx, need_w)
+        dx2 = torch.empty_strided(x2.shape, x2.stride(), dtype=x2.dtype, device=x2.device) if need_dx else None
         dW, dP, db = _backward_kernels(lib, ctx, d, x2, dy2, w, p, ctx.threshold, ctx.staged, need_dx, need_w,
-                                       ctx.has_bias, dx2)
+                                       ctx.has_bias, dx2, dy_raw if ctx.has_bias else None)
         dx = dx2.reshape(ctx.x_shape) if need_dx else None
         return dx, dW, dP, db, None, None, None, None, None
 

@@ -13,7 +13,7 @@ streaming kernels of ``csrc/norm_act.cu`` with the ReLU folded in.
 ``nn.Sequential`` containers a directly following ``nn.ReLU`` is absorbed (replaced by ``nn.Identity`` so
 the child indices -- and with them the mask keys ``features.<idx>`` -- do not move).
 
-Inputs the kernels do not take (CPU tensors, non-fp32, C % 4 != 0, momentum=None) go through
+Inputs the kernels do not take (CPU tensors, non-fp32, momentum=None) go through
 ``nn.BatchNorm2d.forward`` + ``F.relu``: batch-norm is not part of the masked-convolution path, so unlike
 the layers of ``cpg_b200.layers`` this module keeps the stock implementation as its general case.
 """
@@ -23,7 +23,7 @@ import torch.nn.functional as F
 from torch.autograd.function import once_differentiable
 
 from . import _lib
-from .functional import mark_tf32
+from .functional import empty_nhwc, mark_tf32, nhwc_pixel_stride, to_nhwc_aligned
 
 CL = torch.channels_last
 
@@ -33,25 +33,22 @@ class _BNReLUFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, running_mean, running_var, nbt, training, momentum, eps, relu, pool,
                 tf32_out=False):
         lib = _lib.load()
-        if not x.is_contiguous(memory_format=CL):
-            x = x.contiguous(memory_format=CL)
+        x = to_nhwc_aligned(x)          # dense channels_last, or NHWC with the pixel stride padded to 4 (C % 4 != 0)
+        ldc = nhwc_pixel_stride(x)
         N, C, H, W = x.shape
         M = N * H * W
-        if pool:
-            y = torch.empty((N, C, H // 2, W // 2), dtype=x.dtype, device=x.device, memory_format=CL)
-        else:
-            y = torch.empty_like(x)                  # keeps the NHWC strides
+        y = empty_nhwc((N, C, H // 2, W // 2) if pool else (N, C, H, W), x.device, ldc)
         w = weight.detach().contiguous() if weight is not None else None
         b = bias.detach().contiguous() if bias is not None else None
         with torch.cuda.device(x.device):
-            ws = torch.empty(lib.cpgb_bn_workspace_bytes(M, C), dtype=torch.uint8, device=x.device)
+            ws = torch.empty(lib.cpgb_bn_workspace_bytes(M, ldc), dtype=torch.uint8, device=x.device)
             if training:
                 mean = torch.empty(C, dtype=torch.float32, device=x.device)
                 rstd = torch.empty(C, dtype=torch.float32, device=x.device)
             else:
                 mean, rstd = running_mean, torch.rsqrt(running_var + eps)
             _lib.check(lib.cpgb_bn_relu_fwd(
-                _lib.ptr(x), M, C, _lib.ptr(w), _lib.ptr(b), _lib.ptr(running_mean), _lib.ptr(running_var),
+                _lib.ptr(x), M, C, ldc, _lib.ptr(w), _lib.ptr(b), _lib.ptr(running_mean), _lib.ptr(running_var),
                 _lib.ptr(nbt) if training else None, 1 if training else 0, float(momentum), float(eps), 1 if relu else 0,
                 H if pool else 0, W if pool else 0, 1 if tf32_out else 0, _lib.ptr(y),
                 _lib.ptr(mean) if training else None, _lib.ptr(rstd) if training else None,
@@ -69,17 +66,20 @@ class _BNReLUFn(torch.autograd.Function):
         lib = _lib.load()
         x, w, b, mean, rstd = ctx.saved_tensors
         training, relu, has_w, has_b, pool = ctx.cfg
-        if not dy.is_contiguous(memory_format=CL):
-            dy = dy.contiguous(memory_format=CL)
+        ldc = nhwc_pixel_stride(x)
+        if nhwc_pixel_stride(dy) != ldc:
+            t = empty_nhwc(dy.shape, dy.device, ldc)
+            t.copy_(dy)
+            dy = t
         N, C, H, W = x.shape
         M = N * H * W
-        dx = torch.empty_like(x)
+        dx = torch.empty_strided(x.shape, x.stride(), dtype=x.dtype, device=x.device)
         dg = torch.empty(C, dtype=torch.float32, device=x.device) if has_w else None
         db = torch.empty(C, dtype=torch.float32, device=x.device) if has_b else None
         with torch.cuda.device(x.device):
-            ws = torch.empty(lib.cpgb_bn_workspace_bytes(M, C), dtype=torch.uint8, device=x.device)
+            ws = torch.empty(lib.cpgb_bn_workspace_bytes(M, ldc), dtype=torch.uint8, device=x.device)
             _lib.check(lib.cpgb_bn_relu_bwd(
-                _lib.ptr(x), _lib.ptr(dy), M, C, _lib.ptr(w), _lib.ptr(b), _lib.ptr(mean), _lib.ptr(rstd),
+                _lib.ptr(x), _lib.ptr(dy), M, C, ldc, _lib.ptr(w), _lib.ptr(b), _lib.ptr(mean), _lib.ptr(rstd),
                 1 if training else 0, 1 if relu else 0, H if pool else 0, W if pool else 0,
                 1 if ctx.cpgb_tf32_out else 0, _lib.ptr(dx), _lib.ptr(dg), _lib.ptr(db),
                 _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), 'cpgb_bn_relu_bwd')
@@ -116,7 +116,7 @@ class FusedBatchNormReLU2d(nn.BatchNorm2d):
         return super().extra_repr() + f', relu={self.relu}, pool={self.pool}, tf32_out={self.tf32_out}'
 
     def _fast(self, x):
-        if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] % 4 == 0 and x.numel() > 0):
+        if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.numel() > 0):
             return False
         for t in (self.weight, self.bias, self.running_mean, self.running_var):
             if t is not None and (t.dtype != torch.float32 or t.device != x.device):

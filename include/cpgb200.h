@@ -150,6 +150,11 @@ int cpgb_conv2d_wgrad_fused(const cpgb_conv_desc *d, const float *x, const float
                             int32_t mode, float *dW, float *dP, float *dbias, float thr, void *ws,
                             size_t ws_bytes, void *stream);
 
+/* dbias[k] = sum over (n, p, q) of dy -- the bias gradient of F.conv2d / F.linear (models/layers.py:108,194) on its
+ * own, in fp32.  cpgb_conv2d_wgrad_fused computes it from the dy it is given; a caller that hands that function a
+ * TF32-rounded copy of dy (CPGB_FLAG_DY_TF32) passes dbias = NULL there and calls this with the unrounded tensor. */
+int cpgb_conv2d_bias_grad(const cpgb_conv_desc *d, const float *dy, float *dbias, void *stream);
+
 /* a6 standalone, in place on existing gradients: utils/prune.py:195-211.
  * mode is CPGB_GRAD_FINETUNE or CPGB_GRAD_PRUNE; dW / dP may each be NULL
  * ("if module.weight.grad is not None", "if module.piggymask is not None"). */
@@ -203,7 +208,7 @@ int cpgb_split_merged_grad(const float *merged, const uint8_t *tmask, int64_t n,
 
 /* SURVEY 8(f) N4 -- the consumer of every masked convolution: nn.BatchNorm2d followed by
  * nn.ReLU(inplace=True) (models/vgg.py:109-118, models/resnet.py:60-100), on NHWC fp32 activations seen as
- * [M = N*H*W][C], C % 4 == 0.  Semantics of torch.nn.functional.batch_norm (+ relu):
+ * [M = N*H*W][C] (pixel stride `ldc`).  Semantics of torch.nn.functional.batch_norm (+ relu):
  *   training != 0: batch statistics (biased variance) normalise; running_mean / running_var (may be NULL) are
  *                  updated in place with `momentum` and the unbiased variance, *num_batches_tracked (int64, may
  *                  be NULL) is incremented as nn.BatchNorm2d.forward does; save_mean / save_rstd [C] receive
@@ -214,21 +219,27 @@ int cpgb_split_merged_grad(const float *merged, const uint8_t *tmask, int64_t n,
  * follows conv -> BN -> ReLU at the 'M' entries of models/vgg.py:95-122 into the same pass: y (and dy of the
  * backward call) are then [N*(H/2)*(W/2)][C]; the window gradient goes to the first maximum in (h, w) order as
  * in torch.  pool_h = pool_w = 0: no pooling.
+ * ldc: floats between consecutive pixels of x / y (and dy / dx): 0 = dense (C, then a multiple of 4), or any multiple
+ * of 4 that is >= C -- how cpg_b200 stores activations whose channel count is not a multiple of 4 (the grown networks'
+ * 78 / 313 / 627 channels).  The lanes C..ldc-1 of the inputs are ignored, those of the outputs are written as zeros.
+ * tf32_out != 0: y (and dx of the backward call) are rounded to the nearest TF32-representable value as they are
+ * stored, so the masked convolution that consumes them can set CPGB_FLAG_X_TF32 / CPGB_FLAG_DY_TF32 (one ALU
+ * operation here instead of a rounding pass there; relative change of the output <= 2^-11).
  * ws: cpgb_bn_workspace_bytes(M, C) bytes of scratch (per-block partial sums, deterministic). */
 size_t cpgb_bn_workspace_bytes(int64_t M, int32_t C);
-int cpgb_bn_relu_fwd(const float *x, int64_t M, int32_t C, const float *gamma, const float *beta, float *running_mean,
-                     float *running_var, int64_t *num_batches_tracked, int32_t training, float momentum, float eps,
-                     int32_t relu, int32_t pool_h, int32_t pool_w, int32_t tf32_out, float *y, float *save_mean,
-                     float *save_rstd, void *ws, size_t ws_bytes, void *stream);
+int cpgb_bn_relu_fwd(const float *x, int64_t M, int32_t C, int32_t ldc, const float *gamma, const float *beta,
+                     float *running_mean, float *running_var, int64_t *num_batches_tracked, int32_t training,
+                     float momentum, float eps, int32_t relu, int32_t pool_h, int32_t pool_w, int32_t tf32_out, float *y,
+                     float *save_mean, float *save_rstd, void *ws, size_t ws_bytes, void *stream);
 /* Backward of the above: with g = dy * [y > 0] (relu) or dy,  xhat = (x - mean) * rstd:
  *   dbeta = sum g;  dgamma = sum g * xhat;
  *   training: dx = gamma * rstd * (g - mean(g) - xhat * mean(g * xhat));   evaluation: dx = gamma * rstd * g.
  * mean / rstd: save_mean / save_rstd of the forward call (training) or running_mean / 1/sqrt(running_var + eps).
  * dgamma / dbeta may be NULL. */
-int cpgb_bn_relu_bwd(const float *x, const float *dy, int64_t M, int32_t C, const float *gamma, const float *beta,
-                     const float *mean, const float *rstd, int32_t training, int32_t relu, int32_t pool_h,
-                     int32_t pool_w, int32_t tf32_out, float *dx, float *dgamma, float *dbeta, void *ws, size_t ws_bytes,
-                     void *stream);
+int cpgb_bn_relu_bwd(const float *x, const float *dy, int64_t M, int32_t C, int32_t ldc, const float *gamma,
+                     const float *beta, const float *mean, const float *rstd, int32_t training, int32_t relu,
+                     int32_t pool_h, int32_t pool_w, int32_t tf32_out, float *dx, float *dgamma, float *dbeta, void *ws,
+                     size_t ws_bytes, void *stream);
 
 #ifdef __cplusplus
 }

@@ -792,7 +792,7 @@ def test_fused_bn_model_step_matches_stock_modules():
         model, masks, loader = build(nl.SharableConv2d, nl.SharableLinear, DEV, width=0.5, batch=16)
         keys = list(model.state_dict().keys())
         if fuse:
-            assert fuse_bn_relu(model) == (13, 0)
+            assert fuse_bn_relu(model, tf32_out=False) == (13, 0)     # exact fp32 outputs: isolates the BN arithmetic
             assert list(model.state_dict().keys()) == keys
         model.train()
         data, target = loader[0]

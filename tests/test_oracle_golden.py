@@ -140,3 +140,17 @@ def test_trajectory_oracle(golden, mode):
     for n in masks:
         assert int((masks[n].numpy() == 0).sum()) == int(g['maskzeros_module.' + n])
         assert zlib.crc32(masks[n].numpy().tobytes()) == int(g['maskcrc_module.' + n])
+
+
+def test_a11_one_shot_prune(golden):
+    """oracle.one_shot_prune against the live reference's SparsePruner.one_shot_prune (utils/prune.py:94-109)."""
+    g = golden('one_shot')
+    names = [str(n) for n in g['names']]
+    ws = [T(g['W_' + n.replace('.', '_')].copy()) for n in names]
+    ts = [T(g['T_' + n.replace('.', '_')].copy()) for n in names]
+    O.one_shot_prune(ws, ts, int(g['cur']), float(g['ratio']))
+    for n, w, t in zip(names, ws, ts):
+        k = n.replace('.', '_')
+        assert np.array_equal(t.numpy(), g['T1_' + k]), n
+        assert np.array_equal(w.numpy(), g['W1_' + k]), n
+        assert (w.numpy()[g['T1_' + k] == 0] == 0).all()
