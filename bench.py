@@ -416,7 +416,7 @@ def measure_tf32_peak(device):
     return 2 * 8192 ** 3 / (best * 1e-3) / 1e12
 
 
-def kernel_table(device, regime_has_piggy, iters=5):
+def kernel_table(device, regime_has_piggy, iters=5, width=1.0):
     """Per-layer, per-pass device time of OUR conv/linear kernels at the bench workload, timed
     with CUDA events on the launching stream, L2 flushed between launches.  Returns rows and
     the dominant pass (largest summed time) with its algorithmic FLOPs."""
@@ -424,8 +424,11 @@ def kernel_table(device, regime_has_piggy, iters=5):
     from cpg_b200 import _lib
     lib = _lib.load()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
-    shapes = [(3, 64, 32), (64, 64, 32), (64, 128, 16), (128, 128, 16), (128, 256, 8), (256, 256, 8), (256, 256, 8),
-              (256, 512, 4), (512, 512, 4), (512, 512, 4), (512, 512, 2), (512, 512, 2), (512, 512, 2)]
+    ch = lambda v: int(v * width)
+    shapes = [(3, ch(64), 32), (ch(64), ch(64), 32), (ch(64), ch(128), 16), (ch(128), ch(128), 16), (ch(128), ch(256), 8),
+              (ch(256), ch(256), 8), (ch(256), ch(256), 8), (ch(256), ch(512), 4), (ch(512), ch(512), 4),
+              (ch(512), ch(512), 4), (ch(512), ch(512), 2), (ch(512), ch(512), 2), (ch(512), ch(512), 2)]
+    from cpg_b200.functional import empty_nhwc
     rows = []
 
     def time_call(fn):
@@ -446,6 +449,9 @@ def kernel_table(device, regime_has_piggy, iters=5):
         # as in the real step, the activation operands arrive TF32-exact from their producers (fused BN kernels)
         for tns in (x, dy):
             base = tns if tns._base is None else tns._base
+            if tns._base is not None:
+                base.zero_()
+                tns.copy_(torch.randn(tns.shape, device=device))
             _lib.check(lib.cpgb_round_tf32(_lib.ptr(base), _lib.ptr(base), base.numel(), _lib.stream_ptr()), 'round')
         d.flags = _lib.FLAG_X_TF32 | _lib.FLAG_DY_TF32
         ws = torch.empty(lib.cpgb_workspace_bytes(d), dtype=torch.uint8, device=device)
@@ -470,19 +476,21 @@ def kernel_table(device, regime_has_piggy, iters=5):
                      'n_weights': w.numel()})
 
     for i, (C, K, HW) in enumerate(shapes):
-        x = torch.randn(BATCH, C, HW, HW, device=device).contiguous(memory_format=torch.channels_last)
-        if C % 4:   # the stem: NHWC with the pixel stride padded to 4, as cpg_b200.functional stores it
-            xp = torch.empty(BATCH, 4, HW, HW, device=device).contiguous(memory_format=torch.channels_last)
-            xp[:, :C].copy_(x)
-            x = xp[:, :C]
+        # NHWC with the pixel stride padded to 4 where the channel count is not a multiple of 4, as
+        # cpg_b200.functional stores such activations (the stem's input, the grown widths)
+        x = empty_nhwc((BATCH, C, HW, HW), device)
+        x.copy_(torch.randn(BATCH, C, HW, HW, device=device))
         w = torch.randn(K, C, 3, 3, device=device) * 0.05
         p = torch.rand_like(w) * 0.01 if regime_has_piggy else None
-        y = torch.empty(BATCH, K, HW, HW, device=device).contiguous(memory_format=torch.channels_last)
-        dy = torch.randn_like(y)
+        y = empty_nhwc((BATCH, K, HW, HW), device)
+        dy = empty_nhwc((BATCH, K, HW, HW), device)
+        dy.copy_(torch.randn(BATCH, K, HW, HW, device=device))
         t = torch.ones(w.shape, dtype=torch.uint8, device=device)
         d = _lib.conv_desc(x.shape, x.stride(), w.shape, y.shape, y.stride(), (1, 1), (1, 1), (1, 1), 1)
         bench_layer(f'conv{C}x{K}@{HW}', d, x, w, p, y, dy, t, 2.0 * BATCH * K * C * 9 * HW * HW, i == 0)
-    for (I, O) in ((512, 4096), (4096, 4096)):
+    for (I, O) in ((ch(512), ch(4096)), (ch(4096), ch(4096))):
+        if I % 4:
+            continue          # row-padded matrices: timed inside the whole step only
         x = torch.randn(BATCH, I, device=device)
         w = torch.randn(O, I, device=device) * 0.01
         p = torch.rand_like(w) * 0.01 if regime_has_piggy else None
@@ -670,6 +678,8 @@ def main():
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-extras', action='store_true', help='skip kernel table / task-2 regime / cpu baseline')
     ap.add_argument('--path', default='auto', choices=['auto', 'simt'])
+    ap.add_argument('--layer-table', type=float, default=0.0,
+                    help='print only the per-layer kernel table at this area width multiplier (1.0, 1.5) and exit')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == 'reference':
@@ -682,6 +692,16 @@ def main():
     lib = _lib.load()
     if args.path == 'simt':
         _lib.set_path(_lib.PATH_SIMT)
+
+    if args.layer_table:
+        rows, tot, flops, dom = kernel_table(device, regime_has_piggy=False, width=args.layer_table ** 0.5)
+        for r in rows:
+            f = r['flop']
+            print('%-18s stage %6.1f  fprop %6.1f us (%4.0f TF)  dgrad %6.1f us (%4.0f TF)  wgrad %6.1f us (%4.0f TF)' % (
+                r['layer'], r['stage_ms'] * 1e3, r['fprop_ms'] * 1e3, f / r['fprop_ms'] / 1e9, r['dgrad_ms'] * 1e3,
+                (f / r['dgrad_ms'] / 1e9) if r['dgrad_ms'] else 0, r['wgrad_ms'] * 1e3, f / r['wgrad_ms'] / 1e9))
+        print('totals ms', tot)
+        return
 
     def run_regime(regime, want_e2e, width=1.0):
         tr = Trainer(regime, device, world, use_graph=not args.no_graph, width=width)

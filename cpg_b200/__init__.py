@@ -11,6 +11,32 @@ import sys
 __version__ = '0.1.0'
 
 
+def torch_compat_shims(device='cuda'):
+    """Keep the reference's host-side helpers running on current torch releases without editing them.
+
+    utils/__init__.py:37-38 (``Metric.update``) accumulates ``self.sum += val * num`` into a CPU scalar tensor while
+    ``val`` (the loss) lives on the GPU; torch releases that refuse the mixed-device in-place add get the value moved
+    to the host first -- the same arithmetic.  Returns the list of shims applied (empty when none was needed)."""
+    import torch
+    applied = []
+    try:
+        import utils
+    except Exception:
+        return applied
+    try:
+        t = torch.tensor(0.)
+        t += torch.tensor(1., device=device) * 2
+    except RuntimeError:
+        def update(self, val, num):
+            if torch.is_tensor(val):
+                val = val.detach().cpu()
+            self.sum += val * num
+            self.n += num
+        utils.Metric.update = update
+        applied.append('utils.Metric.update')
+    return applied
+
+
 def _view_forward(self, input):
     return input.reshape(*self.shape)
 

@@ -158,6 +158,32 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, bool a_mn, 
          (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// ---------------------------------------------------------------- thread-block clusters / distributed shared memory
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t caddr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(caddr)
+               : "memory");
+  return v;
+}
+// every thread of every CTA of the cluster; release / acquire: shared-memory writes made before it are visible to
+// the peers' ld.shared::cluster after it
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization
 // attribute may start while its predecessor drains; it must not touch global memory before
 // griddep_wait() (which returns once the predecessor grid has completed and flushed).

@@ -72,6 +72,20 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   cfg.attrs = attr; cfg.numAttrs = g_pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
+// the same with the grid's z extent grouped into thread-block clusters of (1, 1, cluster_z)
+template <class... KArgs, class... Args>
+static cudaError_t launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                      int cluster_z, Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = (unsigned)cluster_z;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = g_pdl ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // rank-`rank` fp32 tensor map with 128-byte swizzle; dims/strides innermost first; strides[0] is
 // implied (4 bytes) -- `strides_bytes[i]` is the stride of dim i+1.
@@ -236,6 +250,8 @@ struct ConvGemmParams {
   int ncols;               // output channels stored per pixel (the real count rounded up to 4: pad lanes get zeros)
   int nvalid;              // real output channels (bias is only defined for these)
   int iters_per_split;     // split-K over the (tap, k-block) loop; blockIdx.z = split
+  int cluster;             // > 1: the splits of one output tile form a thread-block cluster (1, 1, cluster) and are
+                           // summed through distributed shared memory -- no partial sums in global memory
   int nstage;              // depth of the smem ring (3: two CTAs share an SM; more: one CTA, deeper prefetch)
   int mn_layout, mn_lbo, mn_sbo, mn_kadv;   // MN-major operand descriptor fields
   long long o_sn, o_sh, o_sw;
@@ -256,9 +272,13 @@ struct ConvGemmCfg {
   static constexpr int NSTAGE_SOLO = BN == 256 ? 4 : BN == 128 ? 6 : 8;
   static constexpr int NSTAGE = NSTAGE_PAIR;   // minimum, for the scratch static_assert
   static constexpr int smem_bytes(int nstage) { return nstage * STAGE_BYTES + 1024 /*align slack*/ + TAIL_BYTES; }
+  // cluster split-K: the whole fp32 accumulator tile, [128][BN + 4], overlays the (then idle) stage ring
+  static constexpr int RED_LD = BN + 4;
+  static constexpr int RED_BYTES = 128 * RED_LD * 4;
   static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
   static constexpr int NC = BN < 128 ? BN : 128;       // columns per epilogue pass
   static_assert(4 * 32 * (NC + 4) * 4 <= NSTAGE * STAGE_BYTES, "epilogue scratch must fit in the stage ring");
+  static_assert(RED_BYTES <= NSTAGE * STAGE_BYTES, "cluster reduction tile must fit in the stage ring");
 };
 
 template <int BN, bool B_MN>
@@ -360,6 +380,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     float *ts = reinterpret_cast<float *>(smem) + quad * 32 * (Cfg::NC + 4);
     float *const *rows = tail->rowptr[quad];
     const float *bias = p.bias;
+    if (p.cluster > 1) {
+      // park this CTA's partial tile in shared memory for the cluster-wide sum below: thread = accumulator row
+      float *red = reinterpret_cast<float *>(smem) + m * Cfg::RED_LD;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4 *>(red + c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+    } else
 #pragma unroll 1
     for (int h = 0; h < BN; h += Cfg::NC) {
       epilogue_rows<Cfg::NC>(tmem_base, quad, h, ts, lane, [&](int rr, int c4, float4 v) {
@@ -375,6 +408,50 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       });
     }
     tc_fence_before();
+  }
+  if (p.cluster > 1) {
+    // Sum the `cluster` partial tiles through distributed shared memory: CTA r of the cluster owns the output rows
+    // r, r + cluster, ...; a warp takes whole rows (coalesced 16-byte global stores) and adds the peers' copies in
+    // rank order, so the result does not depend on scheduling.
+    __syncwarp();
+    cluster_sync_all();
+    if (warp >= 2) {
+      constexpr int LPR = BN / 4;                   // lanes per row
+      constexpr int RPP = LPR >= 32 ? 1 : 32 / LPR; // rows per warp pass
+      constexpr int CPL = LPR > 32 ? LPR / 32 : 1;  // float4 per lane and row (BN = 256: 2)
+      const uint32_t rank = cluster_ctarank();
+      const int nranks = p.cluster;
+      const int ew = warp - 2;                      // 0..3
+      const int rsub = LPR >= 32 ? 0 : lane / LPR;
+      const int lc = LPR >= 32 ? lane : lane % LPR;
+      const uint32_t red0 = smem_u32(smem);
+      const float *bias = p.bias;
+      for (int i = ew * RPP + rsub; ; i += 4 * RPP) {
+        const int row = (int)rank + i * nranks;
+        if (row >= 128) break;
+        float *rp = tail->rowptr[row >> 5][row & 31];
+#pragma unroll
+        for (int cc = 0; cc < CPL; ++cc) {
+          const int c4 = (lc + cc * 32) * 4;
+          const uint32_t off = red0 + (uint32_t)(row * Cfg::RED_LD + c4) * 4u;
+          float4 acc = ld_dsmem_f4(mapa_shared(off, 0));
+          for (int q = 1; q < nranks; ++q) {
+            const float4 b = ld_dsmem_f4(mapa_shared(off, (uint32_t)q));
+            acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+          }
+          const int col = col0 + c4;
+          if (rp != nullptr && col < p.ncols) {
+            if (bias) {
+              const float4 b = load_bias4(bias, col, p.nvalid);
+              acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+            }
+            *reinterpret_cast<float4 *>(rp + c4) = acc;
+          }
+        }
+      }
+    }
+    __syncwarp();
+    cluster_sync_all();                              // peers may still be reading this CTA's tile
   }
   __syncthreads();
   if (warp == 1) {
@@ -921,7 +998,11 @@ static int num_sms() {
 }
 
 // ---- fprop / dgrad plan: tile width and split-K factor -------------------------------------
-struct GemmPlan { PixBox box; int BN, ntiles, iters, splits, ips; bool dense; long long out_elems; };
+struct GemmPlan { PixBox box; int BN, ntiles, iters, splits, ips; bool dense, cluster; long long out_elems; };
+// split-K partial tiles summed inside a thread-block cluster (distributed shared memory) instead of through a
+// partial-sum buffer + splitk_reduce_kernel; CPGB_SPLITK_CLUSTER=0 restores the round trip through global memory
+static const bool g_splitk_cluster = !(getenv("CPGB_SPLITK_CLUSTER") && atoi(getenv("CPGB_SPLITK_CLUSTER")) == 0);
+constexpr int MAX_CLUSTER = 8;   // portable cluster size
 static GemmPlan plan_gemm(int Qo, int Po, int No, int ncols, int iters, const Str4 &os) {
   GemmPlan g;
   g.box = make_pixbox(128, Qo, Po, No);
@@ -941,18 +1022,25 @@ static GemmPlan plan_gemm(int Qo, int Po, int No, int ncols, int iters, const St
   g.out_elems = (long long)No * Po * Qo * ncols;
   const long long ctas = mtiles * g.ntiles;
   int splits = 1;
-  if (g.dense && ctas * 5 < sms * 4) {
-    splits = cdiv_i(sms * 3 / 2, ctas);
+  const bool splittable = g.dense || g_splitk_cluster;
+  if (splittable && ctas * 5 < sms * 4) {
+    // two CTAs share an SM: fill the 2 * sms slots as evenly as the cluster size allows (a 1.5-wave grid leaves half
+    // of the SMs with twice the work of the others)
+    splits = g_splitk_cluster ? std::min(MAX_CLUSTER, (int)(2LL * sms / ctas)) : cdiv_i(sms * 3 / 2, ctas);
     if (splits > iters / 4) splits = iters / 4;
     if (splits < 1) splits = 1;
   }
   // One CTA per SM and a long reduction loop (conv 256->256 @ 8x8: 128 CTAs x 72 stages): halving the loop puts
   // two CTAs on every SM, so one CTA's prologue / epilogue hides under the other's main loop (measured
   // 36.9 -> 31.7 us; shorter loops lose more to the extra reduction pass than they gain)
-  if (g.dense && splits == 1 && g.BN <= 128 && ctas * 2 > sms && ctas <= sms && iters >= 64) splits = 2;
-  if (esp && g.dense) { const int v = atoi(esp); if (v >= 1 && v <= iters) splits = v; }
+  if (splittable && splits == 1 && g.BN <= 128 && ctas * 2 > sms && ctas <= sms && iters >= 64) splits = 2;
+  if (esp && splittable) { const int v = atoi(esp); if (v >= 1 && v <= iters) splits = v; }
+  // cluster reduction: at most MAX_CLUSTER splits per tile, and no dense-output requirement (nothing is addressed
+  // "like the output" any more) -- a padded or strided output can be split as well
+  if (g_splitk_cluster && splits > MAX_CLUSTER) splits = MAX_CLUSTER;
   g.ips = cdiv_i(iters, splits);
   g.splits = cdiv_i(iters, g.ips);
+  g.cluster = g_splitk_cluster && g.splits > 1 && g.splits <= MAX_CLUSTER;
   return g;
 }
 static GemmPlan plan_fprop(const cpgb_conv_desc &d) {
@@ -962,7 +1050,7 @@ static GemmPlan plan_dgrad(const cpgb_conv_desc &d) {
   return plan_gemm(d.W, d.H, d.N, up4(d.C), d.R * d.S * cdiv_i(d.K, 32), x_strides(d));
 }
 static size_t plan_partial_bytes(const GemmPlan &g) {
-  return g.splits > 1 ? (size_t)g.splits * g.out_elems * sizeof(float) : 0;
+  return (g.splits > 1 && !g.cluster) ? (size_t)g.splits * g.out_elems * sizeof(float) : 0;
 }
 
 // ---- wgrad plan ------------------------------------------------------------------------------
@@ -1039,7 +1127,7 @@ static int implicit_stage_weights(const cpgb_conv_desc &d, const float *w, const
 
 template <int BN, bool B_MN>
 static int launch_conv_gemm(const CUtensorMap &ta, const CUtensorMap &tb, ConvGemmParams &p, int ntiles_n,
-                            int splits, cudaStream_t st) {
+                            int splits, cudaStream_t st, bool cluster = false) {
   using Cfg = ConvGemmCfg<BN, B_MN>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -1050,6 +1138,11 @@ static int launch_conv_gemm(const CUtensorMap &ta, const CUtensorMap &tb, ConvGe
   dim3 grid(p.tq * p.tp * p.tn, ntiles_n, splits);
   const long long ctas = (long long)grid.x * grid.y * grid.z;
   p.nstage = ctas > num_sms() ? Cfg::NSTAGE_PAIR : Cfg::NSTAGE_SOLO;   // solo only when no SM gets two CTAs anyway
+  p.cluster = cluster ? splits : 1;
+  if (cluster)
+    CPGB_CUDA_OK(launch_pdl_cluster(conv_gemm_kernel<BN, B_MN>, grid, dim3(192), Cfg::smem_bytes(p.nstage), st, splits,
+                                    ta, tb, p));
+  else
   CPGB_CUDA_OK(launch_pdl(conv_gemm_kernel<BN, B_MN>, grid, dim3(192), Cfg::smem_bytes(p.nstage), st, ta, tb, p));
   CPGB_LAUNCH_OK("conv_gemm_kernel");
   return CPGB_OK;
@@ -1072,7 +1165,7 @@ static int run_gemm(const GemmPlan &g, const CUtensorMap &ta, const CUtensorMap 
   p.tq = g.box.tq; p.tp = g.box.tp; p.tn = g.box.tn; p.lq = g.box.lq; p.lp = g.box.lp;
   p.iters_per_split = g.ips;
   p.mn_layout = g_mn.layout; p.mn_lbo = g_mn.lbo; p.mn_sbo = g_mn.sbo; p.mn_kadv = g_mn.kadv;
-  if (g.splits > 1) {
+  if (g.splits > 1 && !g.cluster) {
     if (!part || part_bytes < plan_partial_bytes(g)) {
       set_error("workspace %zu < %zu (split-K partial sums)", part_bytes, plan_partial_bytes(g));
       return CPGB_EWORKSPACE;
@@ -1082,10 +1175,10 @@ static int run_gemm(const GemmPlan &g, const CUtensorMap &ta, const CUtensorMap 
     p.out = out; p.bias = bias; p.split_stride = 0;
   }
   int rc;
-  if (g.BN == 256) rc = launch_conv_gemm<256, B_MN>(ta, tb, p, g.ntiles, g.splits, st);
-  else if (g.BN == 128) rc = launch_conv_gemm<128, B_MN>(ta, tb, p, g.ntiles, g.splits, st);
-  else rc = launch_conv_gemm<64, B_MN>(ta, tb, p, g.ntiles, g.splits, st);
-  if (rc || g.splits == 1) return rc;
+  if (g.BN == 256) rc = launch_conv_gemm<256, B_MN>(ta, tb, p, g.ntiles, g.splits, st, g.cluster);
+  else if (g.BN == 128) rc = launch_conv_gemm<128, B_MN>(ta, tb, p, g.ntiles, g.splits, st, g.cluster);
+  else rc = launch_conv_gemm<64, B_MN>(ta, tb, p, g.ntiles, g.splits, st, g.cluster);
+  if (rc || g.splits == 1 || g.cluster) return rc;
   const long long n4 = g.out_elems / 4;
   int grid = (int)std::min<long long>((n4 + 255) / 256, (long long)num_sms() * 8);
   CPGB_CUDA_OK(launch_pdl(splitk_reduce_kernel, dim3(grid), dim3(256), 0, st, reinterpret_cast<const float4 *>(part),

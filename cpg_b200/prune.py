@@ -50,6 +50,9 @@ class SparsePruner(object):
             sys.exit(-1)
 
         self.inference_dataset_idx = inference_dataset_idx
+        # data parallel: a cpg_b200.ddp.GradAllReducer whose reduce() runs at the top of
+        # do_weight_decay_and_make_grads_zero -- the call the unmodified Manager.train makes right after backward()
+        self.grad_reducer = None
         self.fuse_grad_epilogue = True
         self.batched_staging = True     # build every layer's tensor-core weight operand in one launch
         self._prune_ws = {}
@@ -345,6 +348,8 @@ class SparsePruner(object):
     def do_weight_decay_and_make_grads_zero(self):
         """Sets grads of fixed weights to 0.  (utils/prune.py:195-211)"""
         assert self.masks
+        if self.grad_reducer is not None:
+            self.grad_reducer.reduce()          # masks are rank-invariant: masking commutes with the mean over ranks
         lib = _lib.load()
         mode = _MODES.get(self.args.mode)
         for name, module in self._sharable():

@@ -45,24 +45,11 @@ def ref_env():
 
 
 def _torch_version_shims():
-    """utils/__init__.py:37-38 accumulates `self.sum += val * num` into a CPU scalar tensor with a CUDA loss; torch
-    releases that refuse the mixed-device in-place add get the value moved to the host first (same arithmetic).
-    This is the GPU twin of the `.cuda` no-op shim make_golden.py needs on a CUDA-less host; no reference file is
-    edited."""
-    import utils
-    try:
-        t = torch.tensor(0.)
-        t += torch.tensor(1., device=DEV) * 2
-        return
-    except RuntimeError:
-        pass
-
-    def update(self, val, num):
-        if torch.is_tensor(val):
-            val = val.detach().cpu()
-        self.sum += val * num
-        self.n += num
-    utils.Metric.update = update
+    """The GPU twin of the `.cuda` no-op shim make_golden.py needs on a CUDA-less host (cpg_b200.torch_compat_shims);
+    no reference file is edited."""
+    import cpg_b200
+    applied = cpg_b200.torch_compat_shims(DEV)
+    print('torch compat shims applied:', applied)
 
 
 def rel(a, b):
@@ -201,3 +188,102 @@ def test_checkpoint_round_trip_through_reference_manager(ref_env, tmp_path):
     x = torch.randn(4, 3, 32, 32, device=DEV)
     with torch.no_grad():
         assert torch.equal(model(x), model2(x))
+
+
+# --------------------------------------------------------------------------------------------------------
+# the reference's other model files, unmodified, built on the product layers (BASELINE.json configs[3], [4])
+# --------------------------------------------------------------------------------------------------------
+class _torch_ops_layers:
+    """Context manager: evaluate SharableConv2d / SharableLinear with the reference's expressions in stock torch ops
+    (models/layers.py:98-109, 184-194) -- same module objects, same weights -- as the fp32 yardstick."""
+
+    def __init__(self, nl):
+        self.nl = nl
+
+    def __enter__(self):
+        import torch.nn.functional as F
+        nl = self.nl
+        self.saved = (nl.SharableConv2d.forward, nl.SharableLinear.forward)
+
+        def eff(m):
+            if m.piggymask is None:
+                return m.weight
+            b = (m.piggymask > 5e-3).float()
+            return (b - m.piggymask).detach() * m.weight + m.piggymask * m.weight
+
+        nl.SharableConv2d.forward = lambda m, x, *a, **k: F.conv2d(x, eff(m), m.bias, m.stride, m.padding, m.dilation, m.groups)
+        nl.SharableLinear.forward = lambda m, x: F.linear(x, eff(m), m.bias)
+        self.flags = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        return self
+
+    def __exit__(self, *exc):
+        self.nl.SharableConv2d.forward, self.nl.SharableLinear.forward = self.saved
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = self.flags
+
+
+REF_ARCHS = {
+    # name: (constructor, constructor args, input shape, dataset name)
+    'resnet50': ('resnet50', (), (8, 3, 224, 224), 'cubs'),
+    'spherenet20': ('spherenet20', (), (8, 3, 112, 112), 'age'),
+    'spherenet20_face': ('spherenet20', (), (8, 3, 112, 112), 'face_verification'),
+    'custom_vgg_224': ('custom_vgg', ([64, 64, 'M', 128, 128, 'M', 256, 256, 256, 'M', 512, 512, 512, 'M', 512, 512, 512, 'M'],),
+                       (4, 3, 224, 224), 'imagenet'),
+    'custom_vgg_cifar100_x1.5': ('custom_vgg_cifar100',
+                                 ([64, 64, 'M', 128, 128, 'M', 256, 256, 256, 'M', 512, 512, 512, 'M', 512, 512, 512, 'M'],),
+                                 (16, 3, 32, 32), 'task'),
+}
+
+
+@pytest.mark.parametrize('arch', sorted(REF_ARCHS))
+def test_unmodified_reference_models_forward_backward(ref_env, arch):
+    """models/{resnet,spherenet,vgg}.py of the staged checkout, untouched, after cpg_b200.install(): forward + backward
+    on the GPU through the product kernels (piggymasks on every sharable layer) against the same modules evaluated
+    with the reference's torch expressions in fp32."""
+    models, nl = ref_env['models'], ref_env['nl']
+    ctor, cargs, shape, dataset = REF_ARCHS[arch]
+    width = 1.5 ** 0.5 if arch.endswith('x1.5') else 1.0
+    torch.manual_seed(3)
+    model = getattr(models, ctor)(*cargs, dataset_history=[], dataset2num_classes={}, network_width_multiplier=width,
+                                  shared_layer_info={})
+    model.add_dataset(dataset, 10)
+    model.set_dataset(dataset)
+    model = model.to(DEV)
+    if arch == 'resnet50':                # the reference initialises its convolutions to N(0, 0.001): signal dies in fp32
+        for m in model.modules():
+            if isinstance(m, nl.SharableConv2d):
+                nn.init.kaiming_normal_(m.weight, mode='fan_out', nonlinearity='relu')
+    sharable = [m for m in model.modules() if isinstance(m, (nl.SharableConv2d, nl.SharableLinear))]
+    assert len(sharable) == {'resnet50': 53, 'spherenet20': 20, 'spherenet20_face': 20, 'custom_vgg_224': 15,
+                             'custom_vgg_cifar100_x1.5': 15}[arch]
+    g = torch.Generator().manual_seed(1)
+    for m in sharable:
+        m.piggymask = nn.Parameter((torch.rand(m.weight.shape, generator=g) * 0.01).to(DEV))
+    model.eval()                           # dropout off, BN on running statistics: a deterministic function of x
+    x = torch.randn(*shape, generator=g).to(DEV)
+
+    def run():
+        for p in model.parameters():
+            p.grad = None
+        out = model(x)
+        if isinstance(out, tuple):         # AngleLinear returns (cos_theta, phi_theta)
+            out = out[0]
+        out.square().mean().backward()
+        return out.detach().clone(), {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+
+    from cpg_b200 import _lib
+    lib = _lib.load()
+    before = lib.cpgb_launch_count()
+    out, grads = run()
+    assert lib.cpgb_launch_count() - before >= 3 * len(sharable)
+    with _torch_ops_layers(nl):
+        out_ref, grads_ref = run()
+    assert out.shape[0] == shape[0] and torch.isfinite(out).all()
+    e_out = rel(out, out_ref)
+    assert e_out <= 5e-3, (arch, e_out)
+    assert set(grads) == set(grads_ref)
+    for n in grads:
+        a, b = grads[n].double(), grads_ref[n].double()
+        l2 = ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+        assert l2 <= 0.15, (arch, n, l2)      # first-layer gradients sit behind every ReLU gate flip of the network
