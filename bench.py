@@ -456,7 +456,8 @@ def kernel_table(device, regime_has_piggy, iters=5, width=1.0):
         d.flags = _lib.FLAG_X_TF32 | _lib.FLAG_DY_TF32
         ws = torch.empty(lib.cpgb_workspace_bytes(d), dtype=torch.uint8, device=device)
         dW, dP = torch.empty_like(w), (torch.empty_like(w) if p is not None else None)
-        dx = torch.empty_strided(x.shape, x.stride(), dtype=x.dtype, device=device)
+        from cpg_b200.functional import empty_like_padded
+        dx = empty_like_padded(x)
         st = _lib.stream_ptr()
         P = _lib.ptr
         nst = lib.cpgb_staged_weight_bytes(d)

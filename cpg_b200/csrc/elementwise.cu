@@ -70,6 +70,29 @@ int round_tf32(const float *in, float *out, long long n, cudaStream_t st) {
   return CPGB_OK;
 }
 
+// ---------------- packed {piggyback, task} bit masks (SURVEY 8b cpgb_pack_mask) ----------------
+// One 64-bit word per 32 consecutive elements: low half bit i = (piggy[32g + i] > thr) -- the Binarizer of
+// models/layers.py:15-19 -- high half bit i = (1 <= T[32g + i] <= inference_idx) -- the weights apply_mask keeps
+// (utils/prune.py:229-230).  A warp handles 32 elements per step: coalesced 128-byte reads, one ballot each.
+__global__ void __launch_bounds__(256)
+pack_mask_kernel(const float *__restrict__ piggy, const uint8_t *__restrict__ tmask, long long n, float thr, int inf_idx,
+                 unsigned long long *__restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long groups = (n + 31) >> 5;
+  for (long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < groups; g += warps) {
+    const long long i = (g << 5) + lane;
+    bool pb = false, tb = false;
+    if (i < n) {
+      pb = piggy ? (__ldg(piggy + i) > thr) : true;
+      const unsigned t = tmask ? (unsigned)__ldg(tmask + i) : 1u;
+      tb = tmask ? (t != 0u && t <= (unsigned)inf_idx) : true;
+    }
+    const unsigned lo = __ballot_sync(0xffffffffu, pb), hi = __ballot_sync(0xffffffffu, tb);
+    if (lane == 0) out[g] = ((unsigned long long)hi << 32) | lo;
+  }
+}
+
 // ---------------- fused wgrad epilogue ----------------
 // g: raw weight gradient dL/dW_eff.  One pass produces what optimizers.step() must see:
 //   RAW      : dW = g*b                     dP = g*W                      (models/layers.py:21-23,103)
@@ -292,6 +315,16 @@ extern "C" {
 int cpgb_round_tf32(const float *in, float *out, int64_t n, void *stream) {
   if (n < 0 || (n > 0 && (!in || !out))) { set_error("cpgb_round_tf32: bad arguments"); return CPGB_EINVAL; }
   return round_tf32(in, out, (long long)n, (cudaStream_t)stream);
+}
+
+int cpgb_pack_mask(const float *piggy, const uint8_t *tmask, int64_t n, float thr, int32_t inference_idx, uint64_t *packed,
+                   void *stream) {
+  if (n < 0 || (n > 0 && !packed)) { set_error("cpgb_pack_mask: bad arguments"); return CPGB_EINVAL; }
+  if (n == 0) return CPGB_OK;
+  pack_mask_kernel<<<grid_for((n + 31) / 32 * 32), 256, 0, (cudaStream_t)stream>>>(
+      piggy, tmask, (long long)n, thr, inference_idx, reinterpret_cast<unsigned long long *>(packed));
+  CPGB_LAUNCH_OK("pack_mask");
+  return CPGB_OK;
 }
 
 int cpgb_binarize(const float *piggy, float *out, int64_t n, float thr, void *stream) {

@@ -150,6 +150,12 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   d |= static_cast<uint64_t>(layout_type) << 61;
   return d;
 }
+// The 14-bit start-address field of a shared-memory matrix descriptor for the location `p` of THIS CTA's shared
+// memory.  Inside a thread-block cluster cvta.to.shared returns a shared::cluster window address,
+// (cluster rank << 24) | offset (measured: tools/cluster_probe.py, profiles/r2_cluster_probe.txt); the tensor core
+// wants the CTA-local offset, so everything above bit 17 has to go before the value is or'ed into a descriptor.
+__device__ __forceinline__ uint32_t desc_addr(const void *p) { return (smem_u32(p) & 0x3FFFFu) >> 4; }
+
 // Instruction descriptor for kind::tf32, FP32 accumulate, M x N tile.
 //   [4,6) D format (1 = F32)  [7,10) A format (2 = TF32)  [10,13) B format  [15] A MN-major
 //   [16] B MN-major  [17,23) N >> 3  [24,29) M >> 4

@@ -349,7 +349,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int it = it_beg; it < it_end; ++it) {
         mbar_wait(full + stage, phase);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES) >> 4;
+        const uint32_t sa = desc_addr(smem + stage * Cfg::STAGE_BYTES);
         const uint32_t sb = sa + (A_TILE_BYTES >> 4);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
@@ -667,7 +667,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
       for (int it = 0; it < iters; ++it) {
         mbar_wait(full + stage, phase);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES) >> 4;
+        const uint32_t sa = desc_addr(smem + stage * STAGE_BYTES);
 #pragma unroll
         for (int s = 0; s < TG; ++s) {
 #pragma unroll
@@ -1897,4 +1897,41 @@ extern "C" int cpgb_debug_mma_rate(int bn, int a_mn, int b_mn, int iters, int gr
                   mma_rate_kernel<256><<<grid, 128, smem, st>>>(a_mn, b_mn, iters, out_dev); }
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -3;
+}
+
+// bring-up probe: is a (1, 1, z) cluster launched through launch_pdl_cluster really a cluster, and what do shared
+// memory addresses look like inside one?  out[block][0..5] = {%cluster_ctarank, %cluster_nctarank, token read from
+// the next rank's shared memory, cvta.to.shared address of a static variable, of the dynamic window, mapa(own rank)}
+namespace cpgb {
+__global__ void cluster_probe_kernel(int *out) {
+  extern __shared__ uint8_t dyn[];
+  __shared__ int token;
+  uint32_t rank = ptx::cluster_ctarank(), n;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(n));
+  if (threadIdx.x == 0) token = 1000 + (int)blockIdx.z;
+  __syncthreads();
+  ptx::cluster_sync_all();
+  int peer = -1;
+  if (threadIdx.x == 0) {
+    const uint32_t a = ptx::mapa_shared(ptx::smem_u32(&token), (rank + 1) % n);
+    asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(peer) : "r"(a) : "memory");
+    int *o = out + blockIdx.z * 6;
+    o[0] = (int)rank; o[1] = (int)n; o[2] = peer;
+    o[3] = (int)ptx::smem_u32(&token); o[4] = (int)ptx::smem_u32(dyn); o[5] = (int)ptx::mapa_shared(ptx::smem_u32(dyn), rank);
+  }
+  ptx::cluster_sync_all();
+}
+}  // namespace cpgb
+
+extern "C" int cpgb_debug_cluster_probe(int z, int use_pdl, int smem, int *out_dev, void *stream) {
+  using namespace cpgb;
+  const bool saved = g_pdl;
+  g_pdl = use_pdl != 0;
+  cudaFuncSetAttribute(cluster_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaError_t e = launch_pdl_cluster(cluster_probe_kernel, dim3(1, 1, z), dim3(64), (size_t)smem, (cudaStream_t)stream, z,
+                                     out_dev);
+  g_pdl = saved;
+  if (e != cudaSuccess) return cuda_fail(e, "cluster probe launch");
+  e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : cuda_fail(e, "cluster probe");
 }

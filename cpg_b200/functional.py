@@ -48,6 +48,18 @@ def empty_nhwc(shape, device, ps=None):
     return buf if ps == c else buf[:, :c]
 
 
+def empty_like_padded(t):
+    """Uninitialised tensor with `t`'s shape and strides whose storage covers the pad lanes of the LAST pixel / row
+    too (torch.empty_strided stops at the last logical element; the kernels store whole 16-byte groups)."""
+    if t.dim() == 4:
+        ps = nhwc_pixel_stride(t)
+        if ps is not None and ps != t.shape[1]:
+            return empty_nhwc(t.shape, t.device, ps)
+    elif t.dim() == 2 and t.stride(1) == 1 and t.stride(0) > t.shape[1]:
+        return torch.empty((t.shape[0], t.stride(0)), dtype=t.dtype, device=t.device)[:, :t.shape[1]]
+    return torch.empty_strided(t.shape, t.stride(), dtype=t.dtype, device=t.device)
+
+
 def to_nhwc_aligned(t):
     """`t` itself if its pixels are channels-innermost and 16-byte aligned, else a (padded) NHWC copy."""
     ps = nhwc_pixel_stride(t)
@@ -119,7 +131,7 @@ def _span(t):
 def round_tf32(lib, t):
     """A tagged copy of `t` (same strides; dense, or dense but for channel / row padding) rounded to the nearest
     TF32 value."""
-    out = torch.empty_strided(t.shape, t.stride(), dtype=t.dtype, device=t.device)
+    out = empty_like_padded(t)
     with torch.cuda.device(t.device):
         _lib.check(lib.cpgb_round_tf32(_lib.ptr(t), _lib.ptr(out), _span(t), _lib.stream_ptr()), 'cpgb_round_tf32')
     return mark_tf32(out)
@@ -390,7 +402,7 @@ class MaskedConv2dFn(torch.autograd.Function):
         need_dx = ctx.needs_input_grad[0]
         need_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
         dy, dy_raw = _backward_operands(lib, d, dy, dy_exact, ctx.x_exact, need_dx, need_w)
-        dx = torch.empty_strided(x.shape, x.stride(), dtype=x.dtype, device=x.device) if need_dx else None
+        dx = empty_like_padded(x) if need_dx else None
         dW, dP, db = _backward_kernels(lib, ctx, d, x, dy, w, p, threshold, ctx.staged, need_dx, need_w,
                                        ctx.has_bias, dx, dy_raw if ctx.has_bias else None)
         return dx, dW, dP, db, None, None, None, None, None, None, None, None, None, None
@@ -470,7 +482,7 @@ class MaskedLinearFn(torch.autograd.Function):
         need_dx = ctx.needs_input_grad[0]
         need_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
         dy2, dy_raw = _backward_operands(lib, d, dy2, is_tf32(dy), ctx.x_exact, need_dx, need_w)
-        dx2 = torch.empty_strided(x2.shape, x2.stride(), dtype=x2.dtype, device=x2.device) if need_dx else None
+        dx2 = empty_like_padded(x2) if need_dx else None
         dW, dP, db = _backward_kernels(lib, ctx, d, x2, dy2, w, p, ctx.threshold, ctx.staged, need_dx, need_w,
                                        ctx.has_bias, dx2, dy_raw if ctx.has_bias else None)
         dx = dx2.reshape(ctx.x_shape) if need_dx else None

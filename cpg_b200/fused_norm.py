@@ -23,7 +23,7 @@ import torch.nn.functional as F
 from torch.autograd.function import once_differentiable
 
 from . import _lib
-from .functional import empty_nhwc, mark_tf32, nhwc_pixel_stride, to_nhwc_aligned
+from .functional import empty_like_padded, empty_nhwc, mark_tf32, nhwc_pixel_stride, to_nhwc_aligned
 
 CL = torch.channels_last
 
@@ -73,7 +73,7 @@ class _BNReLUFn(torch.autograd.Function):
             dy = t
         N, C, H, W = x.shape
         M = N * H * W
-        dx = torch.empty_strided(x.shape, x.stride(), dtype=x.dtype, device=x.device)
+        dx = empty_like_padded(x)
         dg = torch.empty(C, dtype=torch.float32, device=x.device) if has_w else None
         db = torch.empty(C, dtype=torch.float32, device=x.device) if has_b else None
         with torch.cuda.device(x.device):

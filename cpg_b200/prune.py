@@ -56,6 +56,8 @@ class SparsePruner(object):
         self.fuse_grad_epilogue = True
         self.batched_staging = True     # build every layer's tensor-core weight operand in one launch
         self._prune_ws = {}
+        self._mask_epoch = 0          # bumped whenever one of OUR kernels rewrites a task mask (they bypass torch's
+        self._stats_cache = None      # version counters); see _stats
         self._stage_bufs = {}
         self._stage_events = {}
         self._stage_hook = None
@@ -212,6 +214,7 @@ class SparsePruner(object):
     # ------------------------------------------------------------------ a7
     def _launch_prune(self, weights, mask, pruning_ratio, info):
         lib = _lib.load()
+        self._mask_epoch += 1
         ws = self._scratch(weights.device)
         with torch.cuda.device(weights.device):
             _lib.check(lib.cpgb_prune_select(_lib.ptr(self._dense(weights, 'weight')), _lib.ptr(mask),
@@ -222,6 +225,7 @@ class SparsePruner(object):
     def _launch_prune_batched(self, layers, pruning_ratio, infos):
         import ctypes
         lib = _lib.load()
+        self._mask_epoch += 1
         nl_ = len(layers)
         dev = layers[0][1].weight.device
         W = (ctypes.c_void_p * nl_)(*[_lib.ptr(self._dense(m.weight.data, 'weight')) for _, m in layers])
@@ -305,6 +309,16 @@ class SparsePruner(object):
         and statistic, utils/prune.py:111-193)."""
         import ctypes
         lib = _lib.load()
+        # Manager.train asks for the sparsity after EVERY batch (utils/manager.py:77-88) although the masks only change
+        # at prune events: the counters are cached against (our own mutation counter, every mask's identity and
+        # in-place version), so the per-batch call costs neither a kernel nor a host synchronisation (SURVEY 8f N3).
+        # Piggymask-dependent counters change with every optimizer step and are never cached.
+        key = None
+        if not with_piggy:
+            key = (self._mask_epoch, self.inference_dataset_idx,
+                   tuple((id(m), m._version) for m in (self.masks[n] for n, _ in self._sharable())))
+            if self._stats_cache is not None and self._stats_cache[0] == key:
+                return list(self._stats_cache[1])
         by_dev = {}
         for name, module in self._sharable():
             mask = self._mask(name)
@@ -325,6 +339,8 @@ class SparsePruner(object):
         for out in outs:
             for i, v in enumerate(out.cpu().tolist()):
                 total[i] += int(v)
+        if key is not None:
+            self._stats_cache = (key, list(total))
         return total
 
     def calculate_sparsity(self):
@@ -404,6 +420,7 @@ class SparsePruner(object):
            current dataset.  (utils/prune.py:233-243)"""
         assert self.masks
         self.current_dataset_idx += 1
+        self._mask_epoch += 1
         lib = _lib.load()
         for name, module in self._sharable():
             mask = self._mask(name)

@@ -99,6 +99,15 @@ int cpgb_round_tf32(const float *in, float *out, int64_t n, void *stream);
 /* a1: Binarizer.forward, models/layers.py:15-19.  b = (p > thr) ? 1 : 0, NaN -> NaN. */
 int cpgb_binarize(const float *piggy, float *out, int64_t n, float thr, void *stream);
 
+/* the {piggyback, task} bit masks of a layer, packed.  packed[g] (g = i / 32, n rounded up to 32 elements)
+ * holds for elements 32g .. 32g+31: low 32 bits, bit j = (piggy[32g+j] > thr) -- Binarizer.forward, models/layers.py:
+ * 15-19 (a NaN piggymask packs as 0; the unpacked kernels propagate it) -- all ones when piggy == NULL; high 32 bits,
+ * bit j = (1 <= T[32g+j] <= inference_idx) -- the elements apply_mask keeps, utils/prune.py:229-230 -- all ones when
+ * tmask == NULL.  4.1 B/element read, 0.25 B/element written.  Consumers: cpgb_conv2d_fprop / _dgrad with
+ * CPGB_FLAG_W_INTILE (the weight tile is masked in shared memory from these bits). */
+int cpgb_pack_mask(const float *piggy, const uint8_t *tmask, int64_t n, float thr, int32_t inference_idx, uint64_t *packed,
+                   void *stream);
+
 /* Staged weight operand of the tcgen05 path: tf32_rna((piggy > thr ? 1 : 0) * w) reordered from
  * the module's [K][C/g][R][S] to [K][R*S][Cp] (Cp = C rounded up to 32, zero padded) -- the
  * expression models/layers.py:101-103 evaluated once per layer per step.  fprop and dgrad of the

@@ -647,3 +647,68 @@ def test_grown_width_vgg16_step_runs_on_tensor_cores():
     assert err <= 2e-3, (loss.item(), loss_ref.item())
     for n, p in ours.named_parameters():
         assert p.grad is None or torch.isfinite(p.grad).all(), n
+
+
+def test_mask_statistics_are_cached_between_prune_events():
+    """Manager.train asks calculate_sparsity() after every batch (utils/manager.py:77-88); the counters
+    only change when a mask does, so repeated calls launch nothing and read nothing back."""
+    lib = _lib.load()
+    model = Wrap(Toy(nl)).to(DEV)
+    rng = np.random.RandomState(4)
+    masks = {}
+    for name, mod in model.named_modules():
+        if isinstance(mod, (nl.SharableConv2d, nl.SharableLinear)):
+            with torch.no_grad():
+                mod.weight.copy_(G(rng.standard_normal(tuple(mod.weight.shape)).astype(np.float32)))
+            masks[name] = G(rng.randint(0, 3, tuple(mod.weight.shape)).astype(np.uint8))
+    a = make_args('prune', freq=1, target_s=0.5)
+    pr = cpg_prune.SparsePruner(model, masks, a, 0, 10, 2)
+
+    def ref_sparsity():
+        z = sum(int((m == 0).sum()) for m in masks.values())
+        c = sum(int((m == 2).sum()) for m in masks.values())
+        return z / (z + c)
+
+    s0 = pr.calculate_sparsity()
+    assert abs(s0 - ref_sparsity()) < 1e-12
+    before = lib.cpgb_launch_count()
+    for _ in range(5):
+        assert pr.calculate_sparsity() == s0 and pr.calculate_zero_ratio() >= 0 and pr.calculate_curr_task_ratio() >= 0
+    assert lib.cpgb_launch_count() == before                  # served from the cache
+    pr.gradually_prune(5)                                     # our own kernels rewrite the masks
+    s1 = pr.calculate_sparsity()
+    assert s1 > s0 and abs(s1 - ref_sparsity()) < 1e-12
+    name = next(iter(masks))
+    masks[name].fill_(0)                                      # someone else rewrites one in place
+    assert abs(pr.calculate_sparsity() - ref_sparsity()) < 1e-12
+    masks[name] = torch.full_like(masks[name], 2)             # ... or replaces the tensor
+    assert abs(pr.calculate_sparsity() - ref_sparsity()) < 1e-12
+    pr.make_finetuning_mask()
+    assert pr.calculate_sparsity() == 0.0                     # no free weights left: every 0 became task 3
+
+
+def test_pack_mask_bits():
+    lib = _lib.load()
+    import ctypes
+    lib.cpgb_pack_mask.restype = ctypes.c_int
+    lib.cpgb_pack_mask.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_float, ctypes.c_int32,
+                                   ctypes.c_void_p, ctypes.c_void_p]
+    rng = np.random.RandomState(2)
+    for n in (1, 31, 32, 33, 4096 * 40 + 7):
+        p = rng.uniform(0, 0.01, n).astype(np.float32)
+        p[::7] = np.float32(5e-3)
+        p[1::7] = np.nextafter(np.float32(5e-3), np.float32(1))
+        t = rng.randint(0, 5, n).astype(np.uint8)
+        out = torch.zeros((n + 31) // 32, dtype=torch.int64, device=DEV)
+        _lib.check(lib.cpgb_pack_mask(_lib.ptr(G(p)), _lib.ptr(G(t)), n, 5e-3, 2, _lib.ptr(out), _lib.stream_ptr()), 'pack')
+        words = out.cpu().numpy().view(np.uint64)
+        idx = np.arange(n)
+        lo = (words[idx // 32] >> (idx % 32).astype(np.uint64)) & np.uint64(1)
+        hi = (words[idx // 32] >> (32 + idx % 32).astype(np.uint64)) & np.uint64(1)
+        assert np.array_equal(lo.astype(bool), p > np.float32(5e-3))
+        assert np.array_equal(hi.astype(bool), (t != 0) & (t <= 2))
+        # NULL inputs pack as all ones (within n)
+        _lib.check(lib.cpgb_pack_mask(None, None, n, 5e-3, 2, _lib.ptr(out), _lib.stream_ptr()), 'pack')
+        words = out.cpu().numpy().view(np.uint64)
+        lo = (words[idx // 32] >> (idx % 32).astype(np.uint64)) & np.uint64(1)
+        assert lo.all()
