@@ -416,7 +416,7 @@ def measure_tf32_peak(device):
     return 2 * 8192 ** 3 / (best * 1e-3) / 1e12
 
 
-def kernel_table(device, regime_has_piggy, iters=5, width=1.0):
+def kernel_table(device, regime_has_piggy, iters=5, width=1.0, only=None):
     """Per-layer, per-pass device time of OUR conv/linear kernels at the bench workload, timed
     with CUDA events on the launching stream, L2 flushed between launches.  Returns rows and
     the dominant pass (largest summed time) with its algorithmic FLOPs."""
@@ -446,6 +446,8 @@ def kernel_table(device, regime_has_piggy, iters=5, width=1.0):
         return statistics.median(ts)
 
     def bench_layer(kind, d, x, w, p, y, dy, t, flops, first):
+        if only and not any(f in kind for f in only):
+            return
         # as in the real step, the activation operands arrive TF32-exact from their producers (fused BN kernels)
         for tns in (x, dy):
             base = tns if tns._base is None else tns._base
@@ -463,7 +465,13 @@ def kernel_table(device, regime_has_piggy, iters=5, width=1.0):
         nst = lib.cpgb_staged_weight_bytes(d)
         staged = torch.empty(max(nst, 256), dtype=torch.uint8, device=device)
         stg = 0.0
-        if nst:
+        if nst and lib.cpgb_intile_eligible(d):
+            # in-tile masking: no staged copy; with a piggymask the only preparation is packing its bits
+            d.flags |= _lib.FLAG_W_INTILE
+            staged = torch.empty((w.numel() + 31) // 32, dtype=torch.int64, device=device)
+            if p is not None:
+                stg = time_call(lambda: _lib.check(lib.cpgb_pack_mask(P(p), None, w.numel(), 5e-3, 255, P(staged), st), 'pack'))
+        elif nst:
             stg = time_call(lambda: _lib.check(lib.cpgb_stage_weights(d, P(w), P(p), 5e-3, P(staged), nst, st), 'stage'))
         sp = P(staged) if nst else None
         f = time_call(lambda: _lib.check(lib.cpgb_conv2d_fprop(d, P(x), P(w), P(p), None, P(y), 5e-3, sp, P(ws),
@@ -679,6 +687,8 @@ def main():
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-extras', action='store_true', help='skip kernel table / task-2 regime / cpu baseline')
     ap.add_argument('--path', default='auto', choices=['auto', 'simt'])
+    ap.add_argument('--piggy', action='store_true', help='--layer-table: with piggymasks (task-2 regime)')
+    ap.add_argument('--layer-filter', default='', help='--layer-table: comma-separated substrings of layer names')
     ap.add_argument('--layer-table', type=float, default=0.0,
                     help='print only the per-layer kernel table at this area width multiplier (1.0, 1.5) and exit')
     args = ap.parse_args()
@@ -695,7 +705,8 @@ def main():
         _lib.set_path(_lib.PATH_SIMT)
 
     if args.layer_table:
-        rows, tot, flops, dom = kernel_table(device, regime_has_piggy=False, width=args.layer_table ** 0.5)
+        rows, tot, flops, dom = kernel_table(device, regime_has_piggy=args.piggy, width=args.layer_table ** 0.5,
+                                             only=[f for f in args.layer_filter.split(',') if f])
         for r in rows:
             f = r['flop']
             print('%-18s stage %6.1f  fprop %6.1f us (%4.0f TF)  dgrad %6.1f us (%4.0f TF)  wgrad %6.1f us (%4.0f TF)' % (

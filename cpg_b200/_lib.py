@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(_HERE, 'libcpgb200.so')
 
 GRAD_RAW, GRAD_FINETUNE, GRAD_PRUNE = 0, 1, 2
 GRAD_MERGED = 4                       # or'ed into FINETUNE / PRUNE: dW + dP in one buffer (data parallel)
-FLAG_X_TF32, FLAG_DY_TF32 = 1, 2      # cpgb_conv_desc.flags
+FLAG_X_TF32, FLAG_DY_TF32, FLAG_W_INTILE = 1, 2, 4      # cpgb_conv_desc.flags
 PATH_AUTO, PATH_SIMT, PATH_TCGEN05 = 0, 1, 2
 
 EXPORTS = [
@@ -21,7 +21,8 @@ EXPORTS = [
     'cpgb_prune_batched_workspace_bytes', 'cpgb_prune_select_batched',
     'cpgb_apply_mask', 'cpgb_make_finetuning_mask', 'cpgb_mask_stats', 'cpgb_mask_stats_batched', 'cpgb_merge_grads',
     'cpgb_split_merged_grad', 'cpgb_bn_workspace_bytes', 'cpgb_bn_relu_fwd', 'cpgb_bn_relu_bwd',
-    'cpgb_uses_tensor_cores', 'cpgb_round_tf32', 'cpgb_conv2d_bias_grad',
+    'cpgb_uses_tensor_cores', 'cpgb_round_tf32', 'cpgb_conv2d_bias_grad', 'cpgb_pack_mask', 'cpgb_intile_eligible',
+    'cpgb_intile_weight_shape',
 ]
 
 
@@ -61,6 +62,9 @@ def load():
         'cpgb_uses_tensor_cores': (ctypes.c_int, [dp, i32]),
         'cpgb_round_tf32': (ctypes.c_int, [vp, vp, i64, vp]),
         'cpgb_conv2d_bias_grad': (ctypes.c_int, [dp, vp, vp, vp]),
+        'cpgb_pack_mask': (ctypes.c_int, [vp, vp, i64, f32, i32, vp, vp]),
+        'cpgb_intile_eligible': (ctypes.c_int, [dp]),
+        'cpgb_intile_weight_shape': (ctypes.c_int, [i32] * 7),
         'cpgb_binarize': (ctypes.c_int, [vp, vp, i64, f32, vp]),
         'cpgb_staged_weight_bytes': (sz, [dp]),
         'cpgb_stage_weights': (ctypes.c_int, [dp, vp, vp, f32, vp, sz, vp]),

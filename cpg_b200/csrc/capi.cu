@@ -119,6 +119,17 @@ int cpgb_uses_tensor_cores(const cpgb_conv_desc *d, int32_t op) {
   return tc_eligible(*d, op) ? 1 : 0;
 }
 
+int cpgb_intile_eligible(const cpgb_conv_desc *d) {
+  if (!d || validate_desc(d) || d->N == 0 || g_path.load() == CPGB_PATH_SIMT) return 0;
+  return tc_eligible(*d, 0) && tc_eligible(*d, 1) && tc_intile_eligible(*d) ? 1 : 0;
+}
+
+int cpgb_intile_weight_shape(int32_t K, int32_t C, int32_t R, int32_t S, int32_t stride_h, int32_t stride_w,
+                             int32_t groups) {
+  if (g_path.load() == CPGB_PATH_SIMT) return 0;
+  return tc_intile_weight_shape(K, C, R, S, stride_h, stride_w, groups) ? 1 : 0;
+}
+
 int cpgb_weights_usable_raw(const cpgb_conv_desc *d, int32_t has_piggymask) {
   if (!d || validate_desc(d) || has_piggymask || g_path.load() == CPGB_PATH_SIMT) return 0;
   return (tc_eligible(*d, 0) || tc_eligible(*d, 1)) && tc_weights_usable_raw(*d) ? 1 : 0;
@@ -199,6 +210,12 @@ int cpgb_conv2d_fprop(const cpgb_conv_desc *d, const float *x, const float *w, c
     return stem_fprop(*d, x, w, piggy, bias, y, thr, (cudaStream_t)stream);
   bool use_tc;
   if ((rc = pick_tc(d, 0, &use_tc))) return rc;
+  if (use_tc && (d->flags & CPGB_FLAG_W_INTILE)) {
+    if (!cpgb_intile_eligible(d) || (piggy && !staged)) {
+      set_error("CPGB_FLAG_W_INTILE: layer not eligible (cpgb_intile_eligible) or packed mask missing"); return CPGB_EINVAL;
+    }
+    return tc_fprop_intile(*d, x, w, piggy ? staged : nullptr, bias, y, ws, ws_bytes, (cudaStream_t)stream);
+  }
   if (use_tc) {
     const float *wt; void *part; size_t part_bytes; bool raw;
     if ((rc = tc_operands(d, w, piggy, thr, staged, ws, ws_bytes, (cudaStream_t)stream, &wt, &part, &part_bytes, &raw)))
@@ -216,6 +233,12 @@ int cpgb_conv2d_dgrad(const cpgb_conv_desc *d, const float *dy, const float *w, 
   if (!dy || !w || !dx) { set_error("cpgb_conv2d_dgrad: null pointer"); return CPGB_EINVAL; }
   bool use_tc;
   if ((rc = pick_tc(d, 1, &use_tc))) return rc;
+  if (use_tc && (d->flags & CPGB_FLAG_W_INTILE)) {
+    if (!cpgb_intile_eligible(d) || (piggy && !staged)) {
+      set_error("CPGB_FLAG_W_INTILE: layer not eligible (cpgb_intile_eligible) or packed mask missing"); return CPGB_EINVAL;
+    }
+    return tc_dgrad_intile(*d, dy, w, piggy ? staged : nullptr, dx, ws, ws_bytes, (cudaStream_t)stream);
+  }
   if (use_tc) {
     const float *wt; void *part; size_t part_bytes; bool raw;
     if ((rc = tc_operands(d, w, piggy, thr, staged, ws, ws_bytes, (cudaStream_t)stream, &wt, &part, &part_bytes, &raw)))

@@ -121,6 +121,13 @@ int tc_fprop(const cpgb_conv_desc &d, const float *x, const float *staged, const
              size_t part_bytes, cudaStream_t st, bool raw);
 int tc_dgrad(const cpgb_conv_desc &d, const float *dy, const float *staged, float *dx, void *part, size_t part_bytes,
              cudaStream_t st, bool raw);
+// in-tile weight masking (CPGB_FLAG_W_INTILE): B operand = the raw weight tensor, masked from packed bits in shared memory
+bool tc_intile_eligible(const cpgb_conv_desc &d);
+bool tc_intile_weight_shape(int K, int C, int R, int S, int stride_h, int stride_w, int groups);
+int tc_fprop_intile(const cpgb_conv_desc &d, const float *x, const float *w, const void *bits, const float *bias, float *y,
+                    void *part, size_t part_bytes, cudaStream_t st);
+int tc_dgrad_intile(const cpgb_conv_desc &d, const float *dy, const float *w, const void *bits, float *dx, void *part,
+                    size_t part_bytes, cudaStream_t st);
 // wgrad + fused epilogue (dW, dP); partial sums live in ws
 int tc_wgrad_fused(const cpgb_conv_desc &d, const float *x, const float *dy, const float *w, const float *piggy,
                    const uint8_t *tmask, int cur, float wd, int mode, float thr, float *dW, float *dP, void *ws,

@@ -186,6 +186,7 @@ stage_weights_flat_kernel(const float4 *__restrict__ w, const float4 *__restrict
 struct SmemTail {
   uint64_t full[8];
   uint64_t empty[8];
+  uint64_t ready[8];        // in-tile weight masking: transform warps -> MMA issuer
   uint64_t acc_full;
   uint64_t aux_full;        // fused wgrad epilogue: W / P / T tiles have landed
   uint32_t tmem_slot;
@@ -250,6 +251,13 @@ struct ConvGemmParams {
   int ncols;               // output channels stored per pixel (the real count rounded up to 4: pad lanes get zeros)
   int nvalid;              // real output channels (bias is only defined for these)
   int iters_per_split;     // split-K over the (tap, k-block) loop; blockIdx.z = split
+  // In-tile weight masking (CPGB_FLAG_W_INTILE, linear / 1x1 layers with C % 32 == 0): the B operand is the module's
+  // raw fp32 weight tensor; the four epilogue warps mask each landed tile with the packed Binarizer bits and round
+  // it to TF32 in shared memory before the MMAs read it -- the masked copy never exists in global memory.
+  int xform;               // 0 off, 1 round only (no piggymask), 2 mask + round
+  int bits_ld;             // 64-bit mask words per weight row (= C / 32)
+  int w_rows;              // rows of the weight matrix (K)
+  const unsigned long long *bits;
   int cluster;             // > 1: the splits of one output tile form a thread-block cluster (1, 1, cluster) and are
                            // summed through distributed shared memory -- no partial sums in global memory
   int nstage;              // depth of the smem ring (3: two CTAs share an SM; more: one CTA, deeper prefetch)
@@ -281,7 +289,20 @@ struct ConvGemmCfg {
   static_assert(RED_BYTES <= NSTAGE * STAGE_BYTES, "cluster reduction tile must fit in the stage ring");
 };
 
-template <int BN, bool B_MN>
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// One 16-byte chunk of a landed weight tile: apply the Binarizer bits (b = 1 keeps, 0 multiplies by zero -- a true
+// multiply, so Inf / NaN weights behave as in models/layers.py:103) and round to the nearest TF32 value.
+__device__ __forceinline__ void xform_chunk(float4 *ptr, unsigned bits4, bool mask) {
+  float4 v = *ptr;
+  if (mask) {
+    v.x *= (bits4 & 1u) ? 1.f : 0.f; v.y *= (bits4 & 2u) ? 1.f : 0.f;
+    v.z *= (bits4 & 4u) ? 1.f : 0.f; v.w *= (bits4 & 8u) ? 1.f : 0.f;
+  }
+  *ptr = make_float4(to_tf32_rna(v.x), to_tf32_rna(v.y), to_tf32_rna(v.z), to_tf32_rna(v.w));
+}
+
+template <int BN, bool B_MN, bool XF = false>
 __global__ void __launch_bounds__(192)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const ConvGemmParams p) {
@@ -306,7 +327,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmA);
     prefetch_tensormap(&tmB);
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); mbar_init(tail->ready + s, 4); }
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
@@ -320,6 +341,49 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = tail->tmem_slot;
   griddep_launch_dependents();     // the next kernel may start its own prologue
   griddep_wait();                  // ours ends here: inputs are produced by the previous kernel
+  const bool xf = XF && p.xform != 0;
+
+  if (XF && warp >= 2 && xf) {
+    // ---- in-tile weight masking: the epilogue warps are idle during the main loop ----
+    // fprop (K-major B, [BN rows = output channels][32 c], 128-byte swizzle: the 16-byte chunk at physical position jp
+    // of row r holds input channels 4*(jp ^ (r & 7)) ..): warp tw owns rows [tw*BN/4, +BN/4).
+    // dgrad (MN-major B, [BN/32 blocks of 32 c][32 rows = k][32 c], 32-byte-atom swizzle: the 32-byte unit at physical
+    // position up of row r holds channels 8*(up ^ (r & 3)) ..): warp tw owns block tw.
+    const int tw = warp - 2;
+    const bool mask = p.xform == 2;
+    constexpr int ROWS_W = B_MN ? 32 : BN / 4;            // rows this warp transforms per stage
+    const bool active = B_MN ? (tw < BN / 32) : true;
+    const int r_sub = lane >> 3, ch = lane & 7;
+    int stage = 0; uint32_t phase = 0;
+    for (int it = it_beg; it < it_end; ++it) {
+      const int kb = it % p.kblocks;                       // one tap (R*S == 1)
+      // the mask word of "my" row: lane l <-> row l of the warp's share (fetched before the tile lands)
+      unsigned word = 0xffffffffu;
+      if (mask && active && lane < ROWS_W) {
+        long long wrow, wcol;
+        if (!B_MN) { wrow = col0 + tw * ROWS_W + lane; wcol = kb; }            // row = output channel, word = k-block
+        else       { wrow = kb * 32 + lane;            wcol = (col0 >> 5) + tw; }  // row = reduction index k, word = c-block
+        word = (wrow < p.w_rows && wcol < p.bits_ld) ? (unsigned)__ldg(p.bits + wrow * p.bits_ld + wcol) : 0u;
+      }
+      mbar_wait(full + stage, phase);
+      if (active) {
+        uint8_t *tile = smem + stage * Cfg::STAGE_BYTES + A_TILE_BYTES + (B_MN ? tw * 4096 : tw * ROWS_W * 128);
+#pragma unroll
+        for (int i = 0; i < ROWS_W / 4; ++i) {
+          const int r = 4 * i + r_sub;
+          const unsigned wr = __shfl_sync(0xffffffffu, word, r);
+          int cbase;
+          if (!B_MN) cbase = 4 * (ch ^ ((tw * ROWS_W + r) & 7));
+          else       cbase = 8 * ((ch >> 1) ^ (r & 3)) + 4 * (ch & 1);
+          xform_chunk(reinterpret_cast<float4 *>(tile + r * 128 + ch * 16), (wr >> cbase) & 0xFu, mask);
+        }
+      }
+      fence_proxy_async_smem();       // generic-proxy writes -> visible to the tensor core's async-proxy reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tail->ready + stage);
+      if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+    }
+  }
 
   if (warp == 0) {
     if (lane == 0) {
@@ -348,6 +412,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0; uint32_t phase = 0;
       for (int it = it_beg; it < it_end; ++it) {
         mbar_wait(full + stage, phase);
+        if (xf) mbar_wait(tail->ready + stage, phase);    // ... and the weight tile has been masked and rounded
         tc_fence_after();
         const uint32_t sa = desc_addr(smem + stage * Cfg::STAGE_BYTES);
         const uint32_t sb = sa + (A_TILE_BYTES >> 4);
@@ -1003,6 +1068,7 @@ struct GemmPlan { PixBox box; int BN, ntiles, iters, splits, ips; bool dense, cl
 // partial-sum buffer + splitk_reduce_kernel; CPGB_SPLITK_CLUSTER=0 restores the round trip through global memory
 static const bool g_splitk_cluster = !(getenv("CPGB_SPLITK_CLUSTER") && atoi(getenv("CPGB_SPLITK_CLUSTER")) == 0);
 constexpr int MAX_CLUSTER = 8;   // portable cluster size
+static const int g_cluster_max_splits = getenv("CPGB_CLUSTER_SPLITS") ? atoi(getenv("CPGB_CLUSTER_SPLITS")) : 8;
 static GemmPlan plan_gemm(int Qo, int Po, int No, int ncols, int iters, const Str4 &os) {
   GemmPlan g;
   g.box = make_pixbox(128, Qo, Po, No);
@@ -1026,7 +1092,14 @@ static GemmPlan plan_gemm(int Qo, int Po, int No, int ncols, int iters, const St
   if (splittable && ctas * 5 < sms * 4) {
     // two CTAs share an SM: fill the 2 * sms slots as evenly as the cluster size allows (a 1.5-wave grid leaves half
     // of the SMs with twice the work of the others)
-    splits = g_splitk_cluster ? std::min(MAX_CLUSTER, (int)(2LL * sms / ctas)) : cdiv_i(sms * 3 / 2, ctas);
+    splits = cdiv_i(sms * 3 / 2, ctas);
+    // up to MAX_CLUSTER splits: a cluster, filled towards the 2 * sms resident slots (7 -> 8 for the FC layers: a
+    // 1.5-wave grid leaves half of the SMs with twice the work of the others).  Layers that want more splits than
+    // a portable cluster holds (the 2x2 maps: 14) keep the partial-sum buffer: measured, 8 splits of 18 stages are
+    // slower there (30.7 us) than 14 splits of 10 stages plus the reduction kernel (21.5 us) -- these CTAs are
+    // latency-bound, their number matters more than the round trip.
+    if (g_splitk_cluster && splits <= MAX_CLUSTER && g_cluster_max_splits >= 2)
+      splits = std::max(splits, std::min(std::min(MAX_CLUSTER, g_cluster_max_splits), (int)(2LL * sms / ctas)));
     if (splits > iters / 4) splits = iters / 4;
     if (splits < 1) splits = 1;
   }
@@ -1037,10 +1110,12 @@ static GemmPlan plan_gemm(int Qo, int Po, int No, int ncols, int iters, const St
   if (esp && splittable) { const int v = atoi(esp); if (v >= 1 && v <= iters) splits = v; }
   // cluster reduction: at most MAX_CLUSTER splits per tile, and no dense-output requirement (nothing is addressed
   // "like the output" any more) -- a padded or strided output can be split as well
-  if (g_splitk_cluster && splits > MAX_CLUSTER) splits = MAX_CLUSTER;
   g.ips = cdiv_i(iters, splits);
   g.splits = cdiv_i(iters, g.ips);
   g.cluster = g_splitk_cluster && g.splits > 1 && g.splits <= MAX_CLUSTER;
+  if (g.splits > 1 && !g.cluster && !g.dense) {      // the partial-sum buffer is addressed like a dense output
+    g.splits = 1; g.ips = iters;
+  }
   return g;
 }
 static GemmPlan plan_fprop(const cpgb_conv_desc &d) {
@@ -1125,13 +1200,13 @@ static int implicit_stage_weights(const cpgb_conv_desc &d, const float *w, const
   return CPGB_OK;
 }
 
-template <int BN, bool B_MN>
+template <int BN, bool B_MN, bool XF = false>
 static int launch_conv_gemm(const CUtensorMap &ta, const CUtensorMap &tb, ConvGemmParams &p, int ntiles_n,
                             int splits, cudaStream_t st, bool cluster = false) {
   using Cfg = ConvGemmCfg<BN, B_MN>;
   static bool attr_done = false;
   if (!attr_done) {
-    CPGB_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<BN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CPGB_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<BN, B_MN, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       Cfg::smem_bytes(Cfg::NSTAGE_SOLO)));
     attr_done = true;
   }
@@ -1140,10 +1215,10 @@ static int launch_conv_gemm(const CUtensorMap &ta, const CUtensorMap &tb, ConvGe
   p.nstage = ctas > num_sms() ? Cfg::NSTAGE_PAIR : Cfg::NSTAGE_SOLO;   // solo only when no SM gets two CTAs anyway
   p.cluster = cluster ? splits : 1;
   if (cluster)
-    CPGB_CUDA_OK(launch_pdl_cluster(conv_gemm_kernel<BN, B_MN>, grid, dim3(192), Cfg::smem_bytes(p.nstage), st, splits,
+    CPGB_CUDA_OK(launch_pdl_cluster(conv_gemm_kernel<BN, B_MN, XF>, grid, dim3(192), Cfg::smem_bytes(p.nstage), st, splits,
                                     ta, tb, p));
   else
-  CPGB_CUDA_OK(launch_pdl(conv_gemm_kernel<BN, B_MN>, grid, dim3(192), Cfg::smem_bytes(p.nstage), st, ta, tb, p));
+  CPGB_CUDA_OK(launch_pdl(conv_gemm_kernel<BN, B_MN, XF>, grid, dim3(192), Cfg::smem_bytes(p.nstage), st, ta, tb, p));
   CPGB_LAUNCH_OK("conv_gemm_kernel");
   return CPGB_OK;
 }
@@ -1175,7 +1250,11 @@ static int run_gemm(const GemmPlan &g, const CUtensorMap &ta, const CUtensorMap 
     p.out = out; p.bias = bias; p.split_stride = 0;
   }
   int rc;
-  if (g.BN == 256) rc = launch_conv_gemm<256, B_MN>(ta, tb, p, g.ntiles, g.splits, st, g.cluster);
+  if (p.xform) {      // in-tile weight masking: 128- or 64-wide tiles (plan_gemm never picks 256 for these layers)
+    if (g.BN == 128) rc = launch_conv_gemm<128, B_MN, true>(ta, tb, p, g.ntiles, g.splits, st, g.cluster);
+    else if (g.BN == 64) rc = launch_conv_gemm<64, B_MN, true>(ta, tb, p, g.ntiles, g.splits, st, g.cluster);
+    else { set_error("in-tile weight masking needs a 64- or 128-wide tile"); rc = CPGB_EINVAL; }
+  } else if (g.BN == 256) rc = launch_conv_gemm<256, B_MN>(ta, tb, p, g.ntiles, g.splits, st, g.cluster);
   else if (g.BN == 128) rc = launch_conv_gemm<128, B_MN>(ta, tb, p, g.ntiles, g.splits, st, g.cluster);
   else rc = launch_conv_gemm<64, B_MN>(ta, tb, p, g.ntiles, g.splits, st, g.cluster);
   if (rc || g.splits == 1 || g.cluster) return rc;
@@ -1187,8 +1266,29 @@ static int run_gemm(const GemmPlan &g, const CUtensorMap &ta, const CUtensorMap 
   return CPGB_OK;
 }
 
+// in-tile weight masking (CPGB_FLAG_W_INTILE): which layers, and the operand description handed to the kernels
+static bool intile_shape(int K, int C, int R, int S, int stride_h, int stride_w, int groups) {
+  return groups == 1 && R * S == 1 && stride_h == 1 && stride_w == 1 && C % 32 == 0 && C >= 32 && K >= 1;
+}
+// Worth it where a weight tile is consumed by very few CTAs (the FC layers at batch <= 256: ONE pixel tile), so the
+// in-shared-memory work is not repeated; layers with many pixel tiles keep the staged operand.
+bool tc_intile_eligible(const cpgb_conv_desc &d) {
+  static const bool off = getenv("CPGB_NO_INTILE") != nullptr;
+  if (off || !intile_shape(d.K, d.C, d.R, d.S, d.stride_h, d.stride_w, d.groups)) return false;
+  if (!implicit_eligible(d, 0)) return false;
+  return (long long)d.N * d.P * d.Q <= 256 && d.K > 64 && d.C > 64;
+}
+struct IntileArgs { int xform; const unsigned long long *bits; };
+static void set_intile(ConvGemmParams &p, const cpgb_conv_desc &d, const IntileArgs *it) {
+  p.xform = it ? it->xform : 0;
+  p.bits = it ? it->bits : nullptr;
+  p.bits_ld = d.C / 32;
+  p.w_rows = d.K;
+}
+
 static int implicit_fprop(const cpgb_conv_desc &d, const float *x, const float *staged, const float *bias, float *y,
-                          void *part, size_t part_bytes, cudaStream_t st, bool raw = false) {
+                          void *part, size_t part_bytes, cudaStream_t st, bool raw = false,
+                          const IntileArgs *intile = nullptr) {
   if (!aligned16p(x) || !aligned16p(y) || !aligned16p(staged) || (bias && !aligned16p(bias)) || !aligned16p(part)) {
     set_error("tcgen05 path needs 16-byte aligned tensors"); return CPGB_EINVAL;
   }
@@ -1208,12 +1308,13 @@ static int implicit_fprop(const cpgb_conv_desc &d, const float *x, const float *
   p.Qo = d.Q; p.Po = d.P; p.No = d.N; p.S = d.S; p.taps = RS;
   p.off_h = -d.pad_h; p.off_w = -d.pad_w; p.step_h = d.dil_h; p.step_w = d.dil_w;
   p.kblocks = Cp / 32; p.ncols = up4(d.K); p.nvalid = d.K;
+  set_intile(p, d, intile);
   { Str4 ys = y_strides(d); p.o_sn = ys.s[0]; p.o_sh = ys.s[2]; p.o_sw = ys.s[3]; }
   return run_gemm<false>(g, ta, tb, p, y, bias, part, part_bytes, st);
 }
 
 static int implicit_dgrad(const cpgb_conv_desc &d, const float *dy, const float *staged, float *dx, void *part,
-                          size_t part_bytes, cudaStream_t st, bool raw = false) {
+                          size_t part_bytes, cudaStream_t st, bool raw = false, const IntileArgs *intile = nullptr) {
   if (!aligned16p(dy) || !aligned16p(dx) || !aligned16p(staged) || !aligned16p(part)) {
     set_error("tcgen05 path needs 16-byte aligned tensors"); return CPGB_EINVAL;
   }
@@ -1235,6 +1336,7 @@ static int implicit_dgrad(const cpgb_conv_desc &d, const float *dy, const float 
   p.Qo = d.W; p.Po = d.H; p.No = d.N; p.S = d.S; p.taps = RS;
   p.off_h = d.pad_h; p.off_w = d.pad_w; p.step_h = -d.dil_h; p.step_w = -d.dil_w;
   p.kblocks = cdiv_i(d.K, 32); p.ncols = up4(d.C); p.nvalid = d.C;
+  set_intile(p, d, intile);
   { Str4 xs = x_strides(d); p.o_sn = xs.s[0]; p.o_sh = xs.s[2]; p.o_sw = xs.s[3]; }
   return run_gemm<true>(g, ta, tb, p, dx, nullptr, part, part_bytes, st);
 }
@@ -1831,6 +1933,23 @@ int tc_dgrad(const cpgb_conv_desc &d, const float *dy, const float *staged, floa
              cudaStream_t st, bool raw) {
   return tc_mode(d, 1) == TC_XCOL ? xcol_dgrad(d, dy, staged, dx, part, part_bytes, st)
                                   : implicit_dgrad(d, dy, staged, dx, part, part_bytes, st, raw);
+}
+
+// CPGB_FLAG_W_INTILE: the B operand is `w` itself; `bits` (cpgb_pack_mask words, NULL = no piggymask) masks it in
+// shared memory
+int tc_fprop_intile(const cpgb_conv_desc &d, const float *x, const float *w, const void *bits, const float *bias, float *y,
+                    void *part, size_t part_bytes, cudaStream_t st) {
+  IntileArgs it{bits ? 2 : 1, reinterpret_cast<const unsigned long long *>(bits)};
+  return implicit_fprop(d, x, w, bias, y, part, part_bytes, st, false, &it);
+}
+int tc_dgrad_intile(const cpgb_conv_desc &d, const float *dy, const float *w, const void *bits, float *dx, void *part,
+                    size_t part_bytes, cudaStream_t st) {
+  IntileArgs it{bits ? 2 : 1, reinterpret_cast<const unsigned long long *>(bits)};
+  return implicit_dgrad(d, dy, w, dx, part, part_bytes, st, false, &it);
+}
+bool tc_intile_weight_shape(int K, int C, int R, int S, int stride_h, int stride_w, int groups) {
+  static const bool off = getenv("CPGB_NO_INTILE") != nullptr;
+  return !off && intile_shape(K, C, R, S, stride_h, stride_w, groups) && K > 64 && C > 64;
 }
 
 int tc_wgrad_fused(const cpgb_conv_desc &d, const float *x, const float *dy, const float *w, const float *piggy,

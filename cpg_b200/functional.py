@@ -156,6 +156,17 @@ def _stage(lib, d, w, p, threshold, prestaged=None):
     nbytes = lib.cpgb_staged_weight_bytes(d)
     if nbytes == 0:
         return None, None
+    if lib.cpgb_intile_eligible(d):
+        # in-tile masking (CPGB_FLAG_W_INTILE): the kernels TMA-load tiles of `w` itself and mask / round them in
+        # shared memory; all they need is the Binarizer's output packed to one bit per element (0.125 B instead of the
+        # 12 B per element a staged copy costs), shared by this step's fprop and dgrad
+        d.flags |= _lib.FLAG_W_INTILE
+        bits = None
+        if p is not None:
+            bits = torch.empty((w.numel() + 31) // 32, dtype=torch.int64, device=w.device)
+            _lib.check(lib.cpgb_pack_mask(_lib.ptr(p), None, w.numel(), threshold, 255, _lib.ptr(bits),
+                                          _lib.stream_ptr()), 'cpgb_pack_mask')
+        return bits, _ws(lib.cpgb_workspace_bytes(d) - nbytes, w.device)
     if lib.cpgb_weights_usable_raw(d, 1 if p is not None else 0):
         # linear / 1x1 layer without a piggymask: the weight tensor itself is the operand
         return w, _ws(lib.cpgb_workspace_bytes(d) - nbytes, w.device)
@@ -224,13 +235,14 @@ def _defer(device, tensors):
     entry[1].extend(t for t in tensors if t is not None)
 
 
-def _backward_operands(lib, d, dy, dy_exact, x_exact, need_dx, need_w):
+def _backward_operands(lib, d, dy, dy_exact, x_exact, need_dx, need_w, w_intile=False):
     """Round dy once for dgrad + wgrad when a tcgen05 pass reads it; set the descriptor flags.  Returns
     (dy for the kernels, the caller's dy if a rounded copy replaced it else None)."""
     tc_d = need_dx and lib.cpgb_uses_tensor_cores(d, 1)
     tc_w = need_w and lib.cpgb_uses_tensor_cores(d, 2)
     dy_k, dy_exact = _prepare_operand(lib, dy, dy_exact, bool(tc_d or tc_w))
-    d.flags = (_lib.FLAG_X_TF32 if x_exact else 0) | (_lib.FLAG_DY_TF32 if dy_exact else 0)
+    d.flags = (_lib.FLAG_X_TF32 if x_exact else 0) | (_lib.FLAG_DY_TF32 if dy_exact else 0) | \
+              (_lib.FLAG_W_INTILE if w_intile else 0)
     return dy_k, (dy if dy_k is not dy else None)
 
 
@@ -385,6 +397,7 @@ class MaskedConv2dFn(torch.autograd.Function):
         ctx.has_bias = bias is not None
         ctx.geom = (stride, padding, dilation, groups, threshold)
         ctx.fuse, ctx.module, ctx.x_exact = fuse, module, x_exact
+        ctx.w_intile = bool(d.flags & _lib.FLAG_W_INTILE)
         return y
 
     @staticmethod
@@ -401,7 +414,7 @@ class MaskedConv2dFn(torch.autograd.Function):
         d = _lib.conv_desc(x.shape, x.stride(), w.shape, dy.shape, dy.stride(), stride, padding, dilation, groups)
         need_dx = ctx.needs_input_grad[0]
         need_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
-        dy, dy_raw = _backward_operands(lib, d, dy, dy_exact, ctx.x_exact, need_dx, need_w)
+        dy, dy_raw = _backward_operands(lib, d, dy, dy_exact, ctx.x_exact, need_dx, need_w, ctx.w_intile)
         dx = empty_like_padded(x) if need_dx else None
         dW, dP, db = _backward_kernels(lib, ctx, d, x, dy, w, p, threshold, ctx.staged, need_dx, need_w,
                                        ctx.has_bias, dx, dy_raw if ctx.has_bias else None)
@@ -468,6 +481,7 @@ class MaskedLinearFn(torch.autograd.Function):
         ctx.staged = staged
         ctx.has_bias, ctx.threshold, ctx.fuse, ctx.module = bias is not None, threshold, fuse, module
         ctx.x_shape, ctx.x_exact = x.shape, x_exact
+        ctx.w_intile = bool(d.flags & _lib.FLAG_W_INTILE)
         return y
 
     @staticmethod
@@ -481,7 +495,7 @@ class MaskedLinearFn(torch.autograd.Function):
         d = _linear_desc(lib, M, I, O, x2.stride(0), dy2.stride(0))
         need_dx = ctx.needs_input_grad[0]
         need_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
-        dy2, dy_raw = _backward_operands(lib, d, dy2, is_tf32(dy), ctx.x_exact, need_dx, need_w)
+        dy2, dy_raw = _backward_operands(lib, d, dy2, is_tf32(dy), ctx.x_exact, need_dx, need_w, ctx.w_intile)
         dx2 = empty_like_padded(x2) if need_dx else None
         dW, dP, db = _backward_kernels(lib, ctx, d, x2, dy2, w, p, ctx.threshold, ctx.staged, need_dx, need_w,
                                        ctx.has_bias, dx2, dy_raw if ctx.has_bias else None)

@@ -137,6 +137,8 @@ class SparsePruner(object):
                 continue        # consumed as is, nothing to stage
             if nbytes == 0 or (p is not None and (not p.is_contiguous() or p.device != w.device)):
                 continue
+            if lib.cpgb_intile_weight_shape(K, C, R, S, sh, sw, groups):
+                continue        # masked in shared memory by the GEMM itself (CPGB_FLAG_W_INTILE); stages itself otherwise
             key = (name, str(w.device))
             buf = self._stage_bufs.get(key)
             if buf is None or buf.numel() != nbytes:

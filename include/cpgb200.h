@@ -60,6 +60,15 @@ extern "C" {
  * kernels compute in fp32 and ignore the flags. */
 #define CPGB_FLAG_X_TF32 1   /* x  holds TF32-representable values: no rounding pre-pass */
 #define CPGB_FLAG_DY_TF32 2  /* dy holds TF32-representable values: no rounding pre-pass */
+/* In-tile weight masking (north_star: "weight tiles staged via TMA, ANDed in shared memory with the packed bitmask").
+ * With this flag cpgb_conv2d_fprop / _dgrad TMA-load tiles of the module's own fp32 weight tensor `w`, and the CTA's
+ * epilogue warps -- idle during the main loop -- multiply each landed tile by the Binarizer bits and round it to TF32
+ * in shared memory before the MMAs read it: neither the masked weight (models/layers.py:101-103) nor a staged copy is
+ * ever written to global memory.  `staged` must then point to the layer's cpgb_pack_mask words (ignored when
+ * piggy == NULL: round only).  Only for layers cpgb_intile_eligible() accepts: linear / 1x1, C % 32 == 0, at most 256
+ * output pixels (the FC layers of VGG16: one pixel tile, every weight tile is consumed exactly once per pass); for
+ * convolutions with many pixel tiles the in-shared-memory work would be repeated per tile and the staged operand wins. */
+#define CPGB_FLAG_W_INTILE 4
 
 /* Geometry of one SharableConv2d call: F.conv2d(input, weight, bias, stride, padding,
  * dilation, groups) at models/layers.py:108.  SharableLinear (models/layers.py:194) is the
@@ -107,6 +116,11 @@ int cpgb_binarize(const float *piggy, float *out, int64_t n, float thr, void *st
  * CPGB_FLAG_W_INTILE (the weight tile is masked in shared memory from these bits). */
 int cpgb_pack_mask(const float *piggy, const uint8_t *tmask, int64_t n, float thr, int32_t inference_idx, uint64_t *packed,
                    void *stream);
+
+int cpgb_intile_eligible(const cpgb_conv_desc *d);
+/* weight-only view of the same decision (a model-level staging pass skips such layers; the batch size decides later) */
+int cpgb_intile_weight_shape(int32_t K, int32_t C, int32_t R, int32_t S, int32_t stride_h, int32_t stride_w,
+                             int32_t groups);
 
 /* Staged weight operand of the tcgen05 path: tf32_rna((piggy > thr ? 1 : 0) * w) reordered from
  * the module's [K][C/g][R][S] to [K][R*S][Cp] (Cp = C rounded up to 32, zero padded) -- the

@@ -689,10 +689,6 @@ def test_mask_statistics_are_cached_between_prune_events():
 
 def test_pack_mask_bits():
     lib = _lib.load()
-    import ctypes
-    lib.cpgb_pack_mask.restype = ctypes.c_int
-    lib.cpgb_pack_mask.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_float, ctypes.c_int32,
-                                   ctypes.c_void_p, ctypes.c_void_p]
     rng = np.random.RandomState(2)
     for n in (1, 31, 32, 33, 4096 * 40 + 7):
         p = rng.uniform(0, 0.01, n).astype(np.float32)
@@ -700,7 +696,8 @@ def test_pack_mask_bits():
         p[1::7] = np.nextafter(np.float32(5e-3), np.float32(1))
         t = rng.randint(0, 5, n).astype(np.uint8)
         out = torch.zeros((n + 31) // 32, dtype=torch.int64, device=DEV)
-        _lib.check(lib.cpgb_pack_mask(_lib.ptr(G(p)), _lib.ptr(G(t)), n, 5e-3, 2, _lib.ptr(out), _lib.stream_ptr()), 'pack')
+        pg, tg = G(p), G(t)               # keep the device copies alive across the (asynchronous) launch
+        _lib.check(lib.cpgb_pack_mask(_lib.ptr(pg), _lib.ptr(tg), n, 5e-3, 2, _lib.ptr(out), _lib.stream_ptr()), 'pack')
         words = out.cpu().numpy().view(np.uint64)
         idx = np.arange(n)
         lo = (words[idx // 32] >> (idx % 32).astype(np.uint64)) & np.uint64(1)
@@ -712,3 +709,58 @@ def test_pack_mask_bits():
         words = out.cpu().numpy().view(np.uint64)
         lo = (words[idx // 32] >> (idx % 32).astype(np.uint64)) & np.uint64(1)
         assert lo.all()
+
+
+@pytest.mark.parametrize('M,I,O_', [(128, 4096, 4096), (128, 512, 4096), (64, 256, 128), (256, 1024, 200)])
+@pytest.mark.parametrize('piggy', [True, False])
+def test_intile_masking_equals_the_staged_operand(M, I, O_, piggy):
+    """CPGB_FLAG_W_INTILE (weight tile masked from packed bits and rounded in shared memory, north_star) against the
+    staged-operand path of the same library on the same inputs: the tensor core sees identical operand values in an
+    identical order, so y and dx must agree BIT FOR BIT; both against fp32 cuBLAS within 1e-3."""
+    lib = _lib.load()
+    torch.manual_seed(M + I + O_)
+    x = torch.randn(M, I, device=DEV)
+    w = torch.randn(O_, I, device=DEV) * 0.02
+    w[3, 5] = float('inf')                      # masked out below: 0 * inf must give NaN on both paths (models/layers.py:103)
+    p = (torch.rand(O_, I, device=DEV) * 0.01) if piggy else None
+    if piggy:
+        p.view(-1)[::11] = 5e-3                 # == threshold -> 0
+        p[3, 5] = 0.0
+    dy = torch.randn(M, O_, device=DEV)
+    P = _lib.ptr
+    res = {}
+    for intile in (False, True):
+        d = _lib.ConvDesc()
+        lib.cpgb_linear_desc(d, M, I, O_)
+        assert lib.cpgb_intile_eligible(d) == 1
+        staged = None
+        if intile:
+            d.flags |= _lib.FLAG_W_INTILE
+            if piggy:
+                staged = torch.empty((w.numel() + 31) // 32, dtype=torch.int64, device=DEV)
+                _lib.check(lib.cpgb_pack_mask(P(p), None, w.numel(), 5e-3, 255, P(staged), _lib.stream_ptr()), 'pack')
+        ws = torch.empty(lib.cpgb_workspace_bytes(d), dtype=torch.uint8, device=DEV)
+        y = torch.full((M, O_), 7.0, device=DEV)
+        dx = torch.full((M, I), 7.0, device=DEV)
+        before = lib.cpgb_launch_count()
+        _lib.check(lib.cpgb_conv2d_fprop(d, P(x), P(w), P(p), None, P(y), 5e-3, P(staged), P(ws), ws.numel(),
+                                         _lib.stream_ptr()), 'fprop')
+        _lib.check(lib.cpgb_conv2d_dgrad(d, P(dy), P(w), P(p), P(dx), 5e-3, P(staged), P(ws), ws.numel(),
+                                         _lib.stream_ptr()), 'dgrad')
+        torch.cuda.synchronize()
+        res[intile] = (y, dx, lib.cpgb_launch_count() - before)
+    (y0, dx0, n0), (y1, dx1, n1) = res[False], res[True]
+    assert n1 < n0                               # no staging kernels on the in-tile path
+    assert torch.equal(torch.isnan(y0), torch.isnan(y1)) and torch.equal(torch.isnan(dx0), torch.isnan(dx1))
+    if piggy:
+        assert bool(torch.isnan(y1[:, 3]).all())      # 0 * inf propagated, as in the reference expression
+    assert torch.equal(torch.nan_to_num(y0), torch.nan_to_num(y1))
+    assert torch.equal(torch.nan_to_num(dx0), torch.nan_to_num(dx1))
+    w_eff = w.clone()
+    w_eff[3, 5] = 0.0
+    if piggy:
+        w_eff = w_eff * (p > 5e-3).float()
+    keep = [c for c in range(O_) if c != 3]
+    assert rel(y1[:, keep], (x @ w_eff.t())[:, keep]) <= TOL_TC
+    keep_i = [c for c in range(I) if c != 5]
+    assert rel(dx1[:, keep_i], (dy @ w_eff)[:, keep_i]) <= TOL_TC
