@@ -687,6 +687,8 @@ def main():
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-extras', action='store_true', help='skip kernel table / task-2 regime / cpu baseline')
     ap.add_argument('--path', default='auto', choices=['auto', 'simt'])
+    ap.add_argument('--workload', default='vgg16', choices=['vgg16', 'resnet50', 'spherenet20', 'vgg16_prune_cycle'],
+                    help='vgg16 = the headline (BASELINE.json configs[1]); the others are configs[3], [4], [2]')
     ap.add_argument('--piggy', action='store_true', help='--layer-table: with piggymasks (task-2 regime)')
     ap.add_argument('--layer-filter', default='', help='--layer-table: comma-separated substrings of layer names')
     ap.add_argument('--layer-table', type=float, default=0.0,
@@ -704,6 +706,14 @@ def main():
     if args.path == 'simt':
         _lib.set_path(_lib.PATH_SIMT)
 
+    if args.workload != 'vgg16':
+        import bench_workloads
+        bench_workloads.main(args, device, world, rank)
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     if args.layer_table:
         rows, tot, flops, dom = kernel_table(device, regime_has_piggy=args.piggy, width=args.layer_table ** 0.5,
                                              only=[f for f in args.layer_filter.split(',') if f])

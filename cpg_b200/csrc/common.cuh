@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "../../include/cpgb200.h"
 
@@ -27,6 +28,29 @@ void count_launches(int n);
     cpgb::count_launches(n);                                  \
   } while (0)
 #define CPGB_LAUNCH_OK(what) CPGB_LAUNCH_OK_N(what, 1)
+
+// Launch with programmatic dependent launch enabled: the kernel's blocks are scheduled while the previous kernel on
+// the stream drains; every kernel launched through here executes griddepcontrol.wait before its first global access.
+// CPGB_NO_PDL=1 turns the attribute off.
+inline bool pdl_enabled() {
+  static const bool on = getenv("CPGB_NO_PDL") == nullptr;
+  return on;
+}
+template <class... KArgs, class... Args>
+inline cudaError_t launch_dependent(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                    Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 
 // Device-side copy of cpgb_conv_desc with the derived per-group sizes.
 struct Geom {

@@ -76,11 +76,47 @@ int round_tf32(const float *in, float *out, long long n, cudaStream_t st) {
 // (utils/prune.py:229-230).  A warp handles 32 elements per step: coalesced 128-byte reads, one ballot each.
 __global__ void __launch_bounds__(256)
 pack_mask_kernel(const float *__restrict__ piggy, const uint8_t *__restrict__ tmask, long long n, float thr, int inf_idx,
-                 unsigned long long *__restrict__ out) {
+                 unsigned long long *__restrict__ out, bool vec) {
   const int lane = threadIdx.x & 31;
   const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (vec) {
+    // 128 elements per warp step: lane l holds elements 4l .. 4l+3 (one 16-byte load of the piggymask, one 4-byte
+    // load of the task mask); its four bits move to position 4*(l % 8) of the word of its 8-lane group and the
+    // group ORs them together with three shuffles.  Two steps in flight per warp.
+    const long long groups128 = n >> 7;
+    for (long long g = warp0; g < groups128; g += 2 * warps) {
+      const long long g2 = g + warps;
+      const bool two = g2 < groups128;
+      float4 p0 = make_float4(1.f, 1.f, 1.f, 1.f), p1 = p0;
+      uchar4 t0 = make_uchar4(1, 1, 1, 1), t1 = t0;
+      if (piggy) p0 = __ldg(reinterpret_cast<const float4 *>(piggy) + (g << 5) + lane);
+      if (tmask) t0 = __ldg(reinterpret_cast<const uchar4 *>(tmask) + (g << 5) + lane);
+      if (two && piggy) p1 = __ldg(reinterpret_cast<const float4 *>(piggy) + (g2 << 5) + lane);
+      if (two && tmask) t1 = __ldg(reinterpret_cast<const uchar4 *>(tmask) + (g2 << 5) + lane);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float4 pv = h ? p1 : p0;
+        const uchar4 tv = h ? t1 : t0;
+        const unsigned u = (unsigned)inf_idx;
+        unsigned lo = piggy ? ((pv.x > thr) | ((pv.y > thr) << 1) | ((pv.z > thr) << 2) | ((pv.w > thr) << 3)) : 0xFu;
+        unsigned hi = tmask ? ((tv.x != 0 && tv.x <= u) | ((tv.y != 0 && tv.y <= u) << 1) | ((tv.z != 0 && tv.z <= u) << 2) |
+                               ((tv.w != 0 && tv.w <= u) << 3)) : 0xFu;
+        lo <<= 4 * (lane & 7); hi <<= 4 * (lane & 7);
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+          lo |= __shfl_xor_sync(0xffffffffu, lo, o);
+          hi |= __shfl_xor_sync(0xffffffffu, hi, o);
+        }
+        if ((lane & 7) == 0 && (h == 0 || two))
+          out[((h ? g2 : g) << 2) + (lane >> 3)] = ((unsigned long long)hi << 32) | lo;
+      }
+    }
+  }
+  // tail (or everything when the pointers are not 16 / 4-byte aligned): 32 elements per warp step, one ballot each
+  const long long first = vec ? ((n >> 7) << 2) : 0;
   const long long groups = (n + 31) >> 5;
-  for (long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < groups; g += warps) {
+  for (long long g = first + warp0; g < groups; g += warps) {
     const long long i = (g << 5) + lane;
     bool pb = false, tb = false;
     if (i < n) {
@@ -321,8 +357,9 @@ int cpgb_pack_mask(const float *piggy, const uint8_t *tmask, int64_t n, float th
                    void *stream) {
   if (n < 0 || (n > 0 && !packed)) { set_error("cpgb_pack_mask: bad arguments"); return CPGB_EINVAL; }
   if (n == 0) return CPGB_OK;
-  pack_mask_kernel<<<grid_for((n + 31) / 32 * 32), 256, 0, (cudaStream_t)stream>>>(
-      piggy, tmask, (long long)n, thr, inference_idx, reinterpret_cast<unsigned long long *>(packed));
+  const bool vec = (!piggy || aligned16(piggy)) && (!tmask || (reinterpret_cast<uintptr_t>(tmask) & 3) == 0);
+  pack_mask_kernel<<<grid_for(n / 8 + 1), 256, 0, (cudaStream_t)stream>>>(
+      piggy, tmask, (long long)n, thr, inference_idx, reinterpret_cast<unsigned long long *>(packed), vec);
   CPGB_LAUNCH_OK("pack_mask");
   return CPGB_OK;
 }

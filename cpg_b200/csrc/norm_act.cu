@@ -113,6 +113,7 @@ __device__ __forceinline__ float4 pad0(float4 v, int c4, int C) {
 
 __global__ void __launch_bounds__(NA_STATS_THREADS)
 bn_stats_kernel(const NaGeom g, const float *__restrict__ x, float *__restrict__ part) {
+  pdl_wait();
   const int lane = threadIdx.x % g.lanes, slot = threadIdx.x / g.lanes;
   const int c4 = blockIdx.y * g.lanes + lane;
   const bool active = slot < g.slots && c4 * 4 < g.Cs;
@@ -165,6 +166,7 @@ bn_finalize_kernel(const float *__restrict__ part, int nblocks, int C, int Cs, l
                    const float *__restrict__ beta, float *__restrict__ running_mean, float *__restrict__ running_var,
                    float momentum, float eps, float *__restrict__ save_mean, float *__restrict__ save_rstd,
                    float *__restrict__ coef_a, float *__restrict__ coef_b, long long *__restrict__ num_batches_tracked) {
+  pdl_wait();
   if (num_batches_tracked && blockIdx.x == 0 && threadIdx.x == 0) *num_batches_tracked += 1;   // nn.BatchNorm2d.forward
   const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= Cs) return;
@@ -196,6 +198,7 @@ __global__ void __launch_bounds__(128)
 bn_eval_coef_kernel(int C, int Cs, const float *__restrict__ gamma, const float *__restrict__ beta,
                     const float *__restrict__ running_mean, const float *__restrict__ running_var, float eps,
                     float *__restrict__ coef_a, float *__restrict__ coef_b) {
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= Cs) return;
   if (c >= C) { coef_a[c] = 0.f; coef_b[c] = 0.f; return; }
@@ -229,6 +232,7 @@ __device__ __forceinline__ float4 na_out(float4 o, int tf32) {
 __global__ void __launch_bounds__(NA_THREADS)
 bn_apply_kernel(const NaGeom g, const float *__restrict__ x, const float *__restrict__ coef_a,
                 const float *__restrict__ coef_b, int relu, int tf32, float *__restrict__ y) {
+  pdl_wait();
   const int lane = threadIdx.x % g.lanes, slot = threadIdx.x / g.lanes;
   const int c4 = blockIdx.y * g.lanes + lane;
   if (slot >= g.slots || c4 * 4 >= g.Cs) return;
@@ -259,6 +263,7 @@ bn_bwd_stats_kernel(const NaGeom g, const float *__restrict__ x, const float *__
                     const float *__restrict__ gamma, const float *__restrict__ beta,
                     const float *__restrict__ save_mean, const float *__restrict__ save_rstd, int relu,
                     float *__restrict__ part) {
+  pdl_wait();
   const int lane = threadIdx.x % g.lanes, slot = threadIdx.x / g.lanes;
   const int c4 = blockIdx.y * g.lanes + lane;
   const bool active = slot < g.slots && c4 * 4 < g.Cs;
@@ -292,6 +297,7 @@ __global__ void __launch_bounds__(256)
 bn_bwd_finalize_kernel(const float *__restrict__ part, int nblocks, int C, int Cs, long long M, int training,
                        float *__restrict__ dgamma, float *__restrict__ dbeta, float *__restrict__ c1,
                        float *__restrict__ c2) {
+  pdl_wait();
   const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= Cs) return;
   if (c >= C) {
@@ -313,6 +319,7 @@ bn_bwd_apply_kernel(const NaGeom g, const float *__restrict__ x, const float *__
                     const float *__restrict__ save_mean, const float *__restrict__ save_rstd,
                     const float *__restrict__ c1, const float *__restrict__ c2, int relu, int tf32,
                     float *__restrict__ dx) {
+  pdl_wait();
   const int lane = threadIdx.x % g.lanes, slot = threadIdx.x / g.lanes;
   const int c4 = blockIdx.y * g.lanes + lane;
   if (slot >= g.slots || c4 * 4 >= g.Cs) return;
@@ -365,6 +372,7 @@ __device__ __forceinline__ float max4_first(float z0, float z1, float z2, float 
 __global__ void __launch_bounds__(NA_THREADS)
 bn_apply_pool_kernel(const NaGeom g, const PoolGeom pg, const float *__restrict__ x, const float *__restrict__ coef_a,
                      const float *__restrict__ coef_b, int relu, int tf32, float *__restrict__ y) {
+  pdl_wait();
   const int lane = threadIdx.x % g.lanes, slot = threadIdx.x / g.lanes;
   const int c4 = blockIdx.y * g.lanes + lane;
   if (slot >= g.slots || c4 * 4 >= g.Cs) return;
@@ -402,6 +410,7 @@ bn_bwd_stats_pool_kernel(const NaGeom g, const PoolGeom pg, const float *__restr
                          const float *__restrict__ gamma, const float *__restrict__ beta,
                          const float *__restrict__ save_mean, const float *__restrict__ save_rstd, int relu,
                          float *__restrict__ part) {
+  pdl_wait();
   const int lane = threadIdx.x % g.lanes, slot = threadIdx.x / g.lanes;
   const int c4 = blockIdx.y * g.lanes + lane;
   const bool active = slot < g.slots && c4 * 4 < g.Cs;
@@ -451,6 +460,7 @@ bn_bwd_apply_pool_kernel(const NaGeom g, const PoolGeom pg, const float *__restr
                          const float *__restrict__ save_mean, const float *__restrict__ save_rstd,
                          const float *__restrict__ c1, const float *__restrict__ c2, int relu, int tf32,
                          float *__restrict__ dx) {
+  pdl_wait();
   const int lane = threadIdx.x % g.lanes, slot = threadIdx.x / g.lanes;
   const int c4 = blockIdx.y * g.lanes + lane;
   if (slot >= g.slots || c4 * 4 >= g.Cs) return;
@@ -539,23 +549,23 @@ int cpgb_bn_relu_fwd(const float *x, int64_t M, int32_t C, int32_t ldc, const fl
   if (training) {
     const NaGeom gs = na_geom(M, C, Cs, NA_STATS_THREADS);
     const int nb = na_blocks(gs, NA_STATS_PER_SM);
-    bn_stats_kernel<<<dim3(nb, gs.cchunks), NA_STATS_THREADS, 0, st>>>(gs, x, part);
+    CPGB_CUDA_OK(launch_dependent(bn_stats_kernel, dim3(dim3(nb, gs.cchunks)), dim3(NA_STATS_THREADS), 0, st, gs, x, part));
     CPGB_LAUNCH_OK("bn_stats");
-    bn_finalize_kernel<<<(Cs + 7) / 8, 256, 0, st>>>(part, nb, C, Cs, M, gamma, beta, running_mean, running_var, momentum,
+    CPGB_CUDA_OK(launch_dependent(bn_finalize_kernel, dim3((Cs + 7) / 8), dim3(256), 0, st, part, nb, C, Cs, M, gamma, beta, running_mean, running_var, momentum,
                                                          eps, save_mean, save_rstd, coef_a, coef_b,
-                                                         reinterpret_cast<long long *>(num_batches_tracked));
+                                                         reinterpret_cast<long long *>(num_batches_tracked)));
     CPGB_LAUNCH_OK("bn_finalize");
   } else {
-    bn_eval_coef_kernel<<<(Cs + 127) / 128, 128, 0, st>>>(C, Cs, gamma, beta, running_mean, running_var, eps, coef_a,
-                                                          coef_b);
+    CPGB_CUDA_OK(launch_dependent(bn_eval_coef_kernel, dim3((Cs + 127) / 128), dim3(128), 0, st, C, Cs, gamma, beta, running_mean, running_var, eps, coef_a,
+                                                          coef_b));
     CPGB_LAUNCH_OK("bn_eval_coef");
   }
   if (pool) {
     NaGeom gp = g;
     gp.M = pg.Mo;
-    bn_apply_pool_kernel<<<dim3(na_blocks(gp, 8), g.cchunks), NA_THREADS, 0, st>>>(g, pg, x, coef_a, coef_b, relu, tf32_out, y);
+    CPGB_CUDA_OK(launch_dependent(bn_apply_pool_kernel, dim3(dim3(na_blocks(gp, 8), g.cchunks)), dim3(NA_THREADS), 0, st, g, pg, x, coef_a, coef_b, relu, tf32_out, y));
   } else {
-    bn_apply_kernel<<<dim3(na_blocks(g, 8), g.cchunks), NA_THREADS, 0, st>>>(g, x, coef_a, coef_b, relu, tf32_out, y);
+    CPGB_CUDA_OK(launch_dependent(bn_apply_kernel, dim3(dim3(na_blocks(g, 8), g.cchunks)), dim3(NA_THREADS), 0, st, g, x, coef_a, coef_b, relu, tf32_out, y));
   }
   CPGB_LAUNCH_OK("bn_apply");
   return CPGB_OK;
@@ -588,23 +598,23 @@ int cpgb_bn_relu_bwd(const float *x, const float *dy, int64_t M, int32_t C, int3
     NaGeom gp = gs;
     gp.M = pg.Mo;
     nb = na_blocks(gp, NA_STATS_PER_SM);
-    bn_bwd_stats_pool_kernel<<<dim3(nb, gs.cchunks), NA_STATS_THREADS, 0, st>>>(gs, pg, x, dy, gamma, beta, mean, rstd, relu,
-                                                                               part);
+    CPGB_CUDA_OK(launch_dependent(bn_bwd_stats_pool_kernel, dim3(dim3(nb, gs.cchunks)), dim3(NA_STATS_THREADS), 0, st, gs, pg, x, dy, gamma, beta, mean, rstd, relu,
+                                                                               part));
   } else {
     nb = na_blocks(gs, NA_STATS_PER_SM);
-    bn_bwd_stats_kernel<<<dim3(nb, gs.cchunks), NA_STATS_THREADS, 0, st>>>(gs, x, dy, gamma, beta, mean, rstd, relu, part);
+    CPGB_CUDA_OK(launch_dependent(bn_bwd_stats_kernel, dim3(dim3(nb, gs.cchunks)), dim3(NA_STATS_THREADS), 0, st, gs, x, dy, gamma, beta, mean, rstd, relu, part));
   }
   CPGB_LAUNCH_OK("bn_bwd_stats");
-  bn_bwd_finalize_kernel<<<(Cs + 7) / 8, 256, 0, st>>>(part, nb, C, Cs, M, training, dgamma, dbeta, c1, c2);
+  CPGB_CUDA_OK(launch_dependent(bn_bwd_finalize_kernel, dim3((Cs + 7) / 8), dim3(256), 0, st, part, nb, C, Cs, M, training, dgamma, dbeta, c1, c2));
   CPGB_LAUNCH_OK("bn_bwd_finalize");
   if (pool) {
     NaGeom gp = g;
     gp.M = pg.Mo;
-    bn_bwd_apply_pool_kernel<<<dim3(na_blocks(gp, 8), g.cchunks), NA_THREADS, 0, st>>>(g, pg, x, dy, gamma, beta, mean, rstd,
-                                                                                      c1, c2, relu, tf32_out, dx);
+    CPGB_CUDA_OK(launch_dependent(bn_bwd_apply_pool_kernel, dim3(dim3(na_blocks(gp, 8), g.cchunks)), dim3(NA_THREADS), 0, st, g, pg, x, dy, gamma, beta, mean, rstd,
+                                                                                      c1, c2, relu, tf32_out, dx));
   } else {
-    bn_bwd_apply_kernel<<<dim3(na_blocks(g, 8), g.cchunks), NA_THREADS, 0, st>>>(g, x, dy, gamma, beta, mean, rstd, c1, c2,
-                                                                                relu, tf32_out, dx);
+    CPGB_CUDA_OK(launch_dependent(bn_bwd_apply_kernel, dim3(dim3(na_blocks(g, 8), g.cchunks)), dim3(NA_THREADS), 0, st, g, x, dy, gamma, beta, mean, rstd, c1, c2,
+                                                                                relu, tf32_out, dx));
   }
   CPGB_LAUNCH_OK("bn_bwd_apply");
   return CPGB_OK;

@@ -154,6 +154,43 @@ stage_weights_kernel(const float *__restrict__ w, const float *__restrict__ pigg
   }
 }
 
+// RS == 1, C % 32 != 0 (the grown FC layers: 627, 5016 input features): rows copied into the zero-padded [K][Cp]
+// operand, 16 bytes of output per thread, a grid-stride loop over float4 index range [beg4, end4)
+__device__ __forceinline__ void stage_rows_range(const float *__restrict__ w, const float *__restrict__ piggy,
+                                                 float *__restrict__ wt, int C, int Cp, float thr, long long beg4,
+                                                 long long end4, long long first, long long step) {
+  const int cp4 = Cp >> 2;
+  const bool vec = (C & 3) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
+                   (!piggy || (reinterpret_cast<uintptr_t>(piggy) & 15) == 0);
+  for (long long i4 = beg4 + first; i4 < end4; i4 += step) {
+    const long long k = i4 / cp4;
+    const int c = (int)(i4 - k * cp4) << 2;
+    const long long src = k * C + c;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (vec && c + 4 <= C) {
+      float4 v = __ldg(reinterpret_cast<const float4 *>(w + src));
+      if (piggy) {
+        const float4 pv = __ldg(reinterpret_cast<const float4 *>(piggy + src));
+        v.x *= binarize_val(pv.x, thr); v.y *= binarize_val(pv.y, thr);
+        v.z *= binarize_val(pv.z, thr); v.w *= binarize_val(pv.w, thr);
+      }
+      o = make_float4(to_tf32_rna(v.x), to_tf32_rna(v.y), to_tf32_rna(v.z), to_tf32_rna(v.w));
+    } else {
+      if (c + 0 < C) o.x = to_tf32_rna(masked_weight(__ldg(w + src + 0), piggy, src + 0, thr));
+      if (c + 1 < C) o.y = to_tf32_rna(masked_weight(__ldg(w + src + 1), piggy, src + 1, thr));
+      if (c + 2 < C) o.z = to_tf32_rna(masked_weight(__ldg(w + src + 2), piggy, src + 2, thr));
+      if (c + 3 < C) o.w = to_tf32_rna(masked_weight(__ldg(w + src + 3), piggy, src + 3, thr));
+    }
+    reinterpret_cast<float4 *>(wt)[i4] = o;
+  }
+}
+__global__ void __launch_bounds__(256)
+stage_weights_rows_kernel(const float *__restrict__ w, const float *__restrict__ piggy, float *__restrict__ wt, int K,
+                          int C, int Cp, float thr) {
+  stage_rows_range(w, piggy, wt, C, Cp, thr, 0, (long long)K * (Cp >> 2), (long long)blockIdx.x * blockDim.x + threadIdx.x,
+                   (long long)gridDim.x * blockDim.x);
+}
+
 // RS == 1 and C == Cp: same element order, 16 bytes per thread
 __global__ void __launch_bounds__(256)
 stage_weights_flat_kernel(const float4 *__restrict__ w, const float4 *__restrict__ piggy, float4 *__restrict__ wt,
@@ -355,16 +392,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool active = B_MN ? (tw < BN / 32) : true;
     const int r_sub = lane >> 3, ch = lane & 7;
     int stage = 0; uint32_t phase = 0;
-    for (int it = it_beg; it < it_end; ++it) {
+    // the mask word of "my" row for k-block kb: lane l <-> row l of the warp's share.  Fetched one iteration ahead
+    // (an L2 round trip per stage would otherwise sit between the tile landing and the MMAs).
+    auto load_word = [&](int it) -> unsigned {
+      if (!(mask && active && lane < ROWS_W) || it >= it_end) return 0xffffffffu;
       const int kb = it % p.kblocks;                       // one tap (R*S == 1)
-      // the mask word of "my" row: lane l <-> row l of the warp's share (fetched before the tile lands)
-      unsigned word = 0xffffffffu;
-      if (mask && active && lane < ROWS_W) {
-        long long wrow, wcol;
-        if (!B_MN) { wrow = col0 + tw * ROWS_W + lane; wcol = kb; }            // row = output channel, word = k-block
-        else       { wrow = kb * 32 + lane;            wcol = (col0 >> 5) + tw; }  // row = reduction index k, word = c-block
-        word = (wrow < p.w_rows && wcol < p.bits_ld) ? (unsigned)__ldg(p.bits + wrow * p.bits_ld + wcol) : 0u;
-      }
+      long long wrow, wcol;
+      if (!B_MN) { wrow = col0 + tw * ROWS_W + lane; wcol = kb; }              // row = output channel, word = k-block
+      else       { wrow = kb * 32 + lane;            wcol = (col0 >> 5) + tw; }  // row = reduction index k, word = c-block
+      return (wrow < p.w_rows && wcol < p.bits_ld) ? (unsigned)__ldg(p.bits + wrow * p.bits_ld + wcol) : 0u;
+    };
+    unsigned next_word = load_word(it_beg);
+    for (int it = it_beg; it < it_end; ++it) {
+      const unsigned word = next_word;
+      next_word = load_word(it + 1);
       mbar_wait(full + stage, phase);
       if (active) {
         uint8_t *tile = smem + stage * Cfg::STAGE_BYTES + A_TILE_BYTES + (B_MN ? tw * 4096 : tw * ROWS_W * 128);
@@ -803,7 +844,10 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
 // chunk).  Phase 1: sum the splits of G[k][t][c0..c0+cc) (16-byte loads) into smem [k][t][c]; phase 2:
 // walk the module's [k][c][t] order -- cc*RS contiguous elements per k -- with 16-byte accesses to
 // W / P / T / dW / dP.  RS_T > 0: compile-time tap count.
-template <int RS_T>
+// SCALAR: channel counts that are not a multiple of 4 (78 / 313 / 627): the module-order pass uses 4-byte accesses
+// (still coalesced: consecutive threads, consecutive elements); the partial sums are read 16 bytes at a time either way
+// (their rows are padded to Cg).
+template <int RS_T, bool SCALAR = false>
 __global__ void __launch_bounds__(256)
 wgrad_epilogue_krsc_kernel(const float *__restrict__ gpart, int splits, int K, int C, int Cg, int RS_rt, int kb, int cc,
                            int sgroups, const float *__restrict__ w, const float *__restrict__ piggy,
@@ -815,10 +859,10 @@ wgrad_epilogue_krsc_kernel(const float *__restrict__ gpart, int splits, int K, i
   const int RS = RS_T > 0 ? RS_T : RS_rt;
   const int k0 = blockIdx.x * kb, c0 = blockIdx.y * cc;
   const int nk = min(kb, K - k0);
-  const int ncc = min(cc, C - c0);               // multiple of 4
+  const int ncc = min(cc, C - c0);               // multiple of 4 unless SCALAR
   const int ld = cc + 1;
   const long long split_stride = (long long)K * RS * Cg;
-  const int row4 = ncc >> 2;                     // float4 per (k, t) row segment
+  const int row4 = (ncc + 3) >> 2;               // float4 per (k, t) row segment (gpart rows are padded to Cg)
   const int items = nk * RS * row4;
   // sum of splits [s0, s1) of one float4 of G, four loads in flight, ascending order
   auto sum_range = [&](const float *src, int s0, int s1) {
@@ -879,6 +923,19 @@ wgrad_epilogue_krsc_kernel(const float *__restrict__ gpart, int splits, int K, i
   __syncthreads();
   const bool has_p = piggy != nullptr;
   const int per_k = ncc * RS;                    // contiguous elements of one k in this chunk (multiple of 4)
+  if (SCALAR) {
+    for (int i = threadIdx.x; i < nk * per_k; i += blockDim.x) {
+      const int kk = i / per_k, rem = i - kk * per_k;
+      const int c = rem / RS, t = rem - c * RS;
+      const long long idx = ((long long)(k0 + kk) * C + c0) * RS + rem;
+      float ow, op;
+      epi_one_tc(sh[(kk * RS + t) * ld + c], __ldg(w + idx), has_p ? __ldg(piggy + idx) : 0.f, has_p,
+                 tmask ? (unsigned)__ldg(tmask + idx) : 0u, cur, wd, mode, thr, ow, op);
+      dW[idx] = ow;
+      if (dP) dP[idx] = op;
+    }
+    return;
+  }
   for (int i4 = threadIdx.x; i4 < (nk * per_k) >> 2; i4 += blockDim.x) {
     const int i = i4 << 2;
     const int kk = i / per_k;
@@ -1191,6 +1248,13 @@ static int implicit_stage_weights(const cpgb_conv_desc &d, const float *w, const
                                                     reinterpret_cast<const float4 *>(piggy),
                                                     reinterpret_cast<float4 *>(staged), n4, thr);
     CPGB_LAUNCH_OK("stage_weights_flat");
+    return CPGB_OK;
+  }
+  if (RS == 1 && aligned16p(staged)) {
+    const long long n4 = (long long)d.K * (Cp / 4);
+    int grid = (int)std::min<long long>((n4 + 255) / 256, (long long)num_sms() * 8);
+    stage_weights_rows_kernel<<<grid, 256, 0, st>>>(w, piggy, reinterpret_cast<float *>(staged), d.K, d.C, Cp, thr);
+    CPGB_LAUNCH_OK("stage_weights_rows");
     return CPGB_OK;
   }
   dim3 grid(d.K, cdiv_i(Cp, STAGE_CC));
@@ -1508,6 +1572,31 @@ static int implicit_wgrad_fused(const cpgb_conv_desc &d, const float *x, const f
       return CPGB_OK;
     }
   }
+  if (d.C > 32 && aligned16p(p.gpart)) {
+    // ragged channel count: same two-phase kernel, module-order pass with 4-byte accesses
+    int cc = std::min((d.C + 3) & ~3, 128), kb = 1;
+    while (cc > 32 && (long long)d.K * cdiv_i(d.C, cc) < 2LL * num_sms()) cc >>= 1;
+    cc = (cc + 3) & ~3;
+    while (kb < 8 && (long long)(d.K / (2 * kb)) * cdiv_i(d.C, cc) >= 2LL * num_sms() && 2 * kb * cc * RS <= 4608) kb *= 2;
+    const size_t sh = (size_t)kb * RS * (cc + 1) * sizeof(float);
+    if (sh <= 96 * 1024) {
+      static bool attr_done2 = false;
+      if (!attr_done2) {
+        CPGB_CUDA_OK(cudaFuncSetAttribute(wgrad_epilogue_krsc_kernel<9, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        CPGB_CUDA_OK(cudaFuncSetAttribute(wgrad_epilogue_krsc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr_done2 = true;
+      }
+      const dim3 egrid(cdiv_i(d.K, kb), cdiv_i(d.C, cc));
+      if (RS == 9)
+        CPGB_CUDA_OK(launch_pdl(wgrad_epilogue_krsc_kernel<9, true>, egrid, dim3(256), sh, st, (const float *)p.gpart,
+                                pl.splits, d.K, d.C, p.Cg, RS, kb, cc, 1, w, piggy, tmask, cur, wd, mode, thr, dW, dP));
+      else
+        CPGB_CUDA_OK(launch_pdl(wgrad_epilogue_krsc_kernel<0, true>, egrid, dim3(256), sh, st, (const float *)p.gpart,
+                                pl.splits, d.K, d.C, p.Cg, RS, kb, cc, 1, w, piggy, tmask, cur, wd, mode, thr, dW, dP));
+      CPGB_LAUNCH_OK("wgrad_epilogue_krsc_ragged");
+      return CPGB_OK;
+    }
+  }
   const long long n = (long long)d.K * d.C * RS;
   int egrid = (int)std::min<long long>((n + 255) / 256, (long long)num_sms() * 8);
   wgrad_epilogue_krsc_scalar_kernel<<<egrid, 256, 0, st>>>(p.gpart, pl.splits, d.K, d.C, p.Cg, RS, w, piggy, tmask, cur,
@@ -1533,17 +1622,21 @@ static inline int kc_of(const cpgb_conv_desc &d) { return d.R * d.S * d.C; }
 static inline int kcp_of(const cpgb_conv_desc &d) { return (kc_of(d) + 31) / 32 * 32; }
 static inline long long pixels_of(const cpgb_conv_desc &d) { return (long long)d.N * d.P * d.Q; }
 
-static bool y_dense_nhwc(const cpgb_conv_desc &d) {
+// y / dy as a [pixels][K] matrix: NHWC, pixels in (n, p, q) order, the pixel stride a multiple of 4 floats that
+// holds at least K rounded up to 4 (dense when K % 4 == 0, padded otherwise)
+static bool y_pixel_matrix(const cpgb_conv_desc &d) {
   const Str4 ys = y_strides(d);
-  return ys.s[1] == 1 && ys.s[3] == d.K && ys.s[2] == (int64_t)d.Q * d.K && ys.s[0] == (int64_t)d.P * d.Q * d.K;
+  const int64_t ps = ys.s[3];
+  return ys.s[1] == 1 && ps % 4 == 0 && ps >= ((d.K + 3) & ~3) && ys.s[2] == (int64_t)d.Q * ps &&
+         ys.s[0] == (int64_t)d.P * d.Q * ps;
 }
 
 static bool xcol_eligible(const cpgb_conv_desc &d, int op) {
-  if (d.groups != 1 || d.N < 1 || d.K % 4) return false;
-  if (!y_dense_nhwc(d)) return false;
+  (void)op;
+  if (d.groups != 1 || d.N < 1) return false;
+  if (!y_pixel_matrix(d)) return false;
   if (pixels_of(d) >= (1ll << 31) - 256) return false;
   if ((size_t)pixels_of(d) * kcp_of(d) * sizeof(float) > ((size_t)8 << 30)) return false;   // X_col <= 8 GiB
-  if (op == 2 && d.K % 32) return false;
   return true;
 }
 
@@ -1565,8 +1658,9 @@ static cpgb_conv_desc xcol_desc(const cpgb_conv_desc &d) {
   const int kcp = kcp_of(d);
   l.N = (int)pixels_of(d); l.C = kcp; l.H = l.W = 1; l.K = d.K; l.R = l.S = 1; l.P = l.Q = 1;
   l.stride_h = l.stride_w = l.dil_h = l.dil_w = 1; l.groups = 1;
+  const int64_t yps = y_strides(d).s[3];            // pixel stride of y / dy (K rounded up to 4 when padded)
   l.xs[0] = kcp; l.xs[1] = 1; l.xs[2] = kcp; l.xs[3] = kcp;
-  l.ys[0] = d.K; l.ys[1] = 1; l.ys[2] = d.K; l.ys[3] = d.K;
+  l.ys[0] = yps; l.ys[1] = 1; l.ys[2] = yps; l.ys[3] = yps;
   // X_col is rounded to TF32 by im2col_kernel (dX_col is an output); dy is the caller's tensor
   l.flags = CPGB_FLAG_X_TF32 | (d.flags & CPGB_FLAG_DY_TF32);
   return l;
@@ -1757,7 +1851,7 @@ struct StageBatch {
   const float *piggy[STAGE_MAX_ITEMS];
   float *out[STAGE_MAX_ITEMS];
   int K[STAGE_MAX_ITEMS], C[STAGE_MAX_ITEMS], RS[STAGE_MAX_ITEMS];
-  int kind[STAGE_MAX_ITEMS];       // 0: [K][RS][Cp] through smem transpose, 1: flat copy, 2: tight [K][KCp]
+  int kind[STAGE_MAX_ITEMS];       // 0: [K][RS][Cp] through smem transpose, 1: flat copy, 2: tight [K][KCp], 3: padded rows
   int blk0[STAGE_MAX_ITEMS + 1];   // first block of each item
   float thr[STAGE_MAX_ITEMS];
   int n;
@@ -1821,6 +1915,11 @@ __global__ void __launch_bounds__(256) stage_weights_batched_kernel(const __grid
         dst[(long long)t * Cp + c] = c < cv ? sh[c * ld + t] : 0.f;
       }
     }
+  } else if (sb.kind[it] == 3) {
+    const int Cp = (C + 31) / 32 * 32;
+    const long long n4 = (long long)K * (Cp >> 2);
+    const long long beg = (long long)b * STAGE_FLAT_PER_BLOCK, end = min(n4, beg + STAGE_FLAT_PER_BLOCK);
+    stage_rows_range(w, piggy, wt, C, Cp, thr, beg, end, threadIdx.x, blockDim.x);
   } else if (sb.kind[it] == 1) {
     const long long n4 = (long long)K * C * RS / 4;
     const long long beg = (long long)b * STAGE_FLAT_PER_BLOCK, end = min(n4, beg + STAGE_FLAT_PER_BLOCK);
@@ -1862,7 +1961,6 @@ static cpgb_conv_desc weight_desc(int K, int C, int R, int S, int stride_h, int 
 size_t tc_staged_bytes_for_weight(int K, int C, int R, int S, int stride_h, int stride_w, int groups) {
   if (groups != 1 || K <= 0 || C <= 0 || R * S > 49) return 0;
   const cpgb_conv_desc d = weight_desc(K, C, R, S, stride_h, stride_w, groups);
-  if (prefer_xcol(d) && K % 4) return 0;           // the explicit-im2col tier stores whole 16-byte groups of K
   return tc_staged_bytes(d);
 }
 
@@ -1886,6 +1984,9 @@ int tc_stage_weights_batched(int n, const float *const *w, const float *const *p
       } else if (sb.RS[j] == 1 && C[i] % 32 == 0 && aligned16p(w[i]) && (!piggy[i] || aligned16p(piggy[i]))) {
         sb.kind[j] = 1;
         blocks += cdiv_i((long long)K[i] * C[i] / 4, STAGE_FLAT_PER_BLOCK);
+      } else if (sb.RS[j] == 1) {
+        sb.kind[j] = 3;
+        blocks += cdiv_i((long long)K[i] * (cp_of(d) / 4), STAGE_FLAT_PER_BLOCK);
       } else {
         sb.kind[j] = 0;
         blocks += K[i] * cdiv_i(cp_of(d), STAGE_CC);
