@@ -596,6 +596,8 @@ def test_stem_direct_kernels_vs_oracle(case, mode):
             dy_view = wide[:, :K]
         d2 = _lib.conv_desc(xd.shape, xd.stride(), wdv.shape, dy_view.shape, dy_view.stride(), (stride,) * 2,
                             (pad,) * 2, (dil,) * 2, 1)
+        if lib.cpgb_workspace_bytes(d2) > ws.numel():       # the workspace is a function of the descriptor (dY pitch)
+            ws = torch.empty(lib.cpgb_workspace_bytes(d2), dtype=torch.uint8, device=DEV)
         dW.fill_(float('nan'))
         _lib.check(lib.cpgb_conv2d_wgrad_fused(
             d2, _lib.ptr(xd), _lib.ptr(dy_view), _lib.ptr(wdv), _lib.ptr(pd_), _lib.ptr(td), cur, wd,
