@@ -491,6 +491,337 @@ bn_bwd_apply_pool_kernel(const NaGeom g, const PoolGeom pg, const float *__restr
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Single-kernel variants: one launch per direction instead of stats -> finalize -> apply.
+//
+// A CTA owns `lanes` float4 channel groups (blockIdx.y) for a share of the pixel rows; the `cs` CTAs of a thread-block
+// cluster (blockIdx.x = cluster rank) split the rows of the same channels.  Pass 1 accumulates the per-channel sums,
+// the CTA's partial pair goes to its own shared memory, ONE cluster barrier later every CTA adds the `cs` partials of
+// its channels through distributed shared memory in rank order (so all of them compute bit-identical statistics, in
+// double precision), derives the coefficients and walks its rows a second time (x / dy come out of L2 now) to write y
+// or dx.  No partial sums in global memory, no finalize kernel, no second and third launch.  Deterministic: every reduction is a
+// fixed tree (warp shuffles over the pixel slots of a warp, then the warps and the ranks in ascending order).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int NC_THREADS = 512;        // two CTAs per SM can co-reside (also next to a wgrad CTA of the side stream)
+constexpr int NC_WARPS = NC_THREADS / 32;
+constexpr int NC_MAXL = 32;            // channel groups per CTA: a power of two <= 32 (lanes of a warp)
+constexpr int NC_MAX_CLUSTER = 8;      // portable cluster size
+
+struct NcPlan { int lanes, slots, chunks, cs; };
+NcPlan nc_plan(long long rows, int Cs) {
+  NcPlan p;
+  const int c4 = Cs / 4;
+  // experiment knobs: CPGB_BN_TARGET_CHUNKS (channel chunks aimed at), CPGB_BN_CS (largest cluster)
+  const char *et = getenv("CPGB_BN_TARGET_CHUNKS"), *ec = getenv("CPGB_BN_CS");
+  const int target = et ? atoi(et) : 16, max_cs = ec ? atoi(ec) : NC_MAX_CLUSTER;
+  int L = 2;                                             // >= 32 contiguous bytes per pixel row and CTA: whole sectors
+  while (L < NC_MAXL && c4 / (L * 2) >= target) L *= 2;  // about `target` channel chunks ...
+  p.lanes = L; p.slots = NC_THREADS / L; p.chunks = (c4 + L - 1) / L;
+  int cs = na_sms() / p.chunks;                          // ... times up to 8 row shares: 64-148 CTAs
+  if (cs > max_cs) cs = max_cs;
+  if (cs > NC_MAX_CLUSTER) cs = NC_MAX_CLUSTER;
+  if (cs < 1) cs = 1;
+  while (cs > 1 && (long long)(cs - 1) * p.slots >= rows) --cs;   // tiny maps: no idle ranks
+  p.cs = cs;
+  return p;
+}
+
+__device__ __forceinline__ uint32_t nc_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float4 nc_ld_peer(const void *p, uint32_t rank) {
+  uint32_t a;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a) : "r"(nc_smem_u32(p)), "r"(rank));
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void nc_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void nc_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+struct NcShared {
+  float4 wred[2][NC_WARPS][NC_MAXL];   // per-warp partial pairs
+  float4 xch[2][NC_MAXL];              // this CTA's partial pair per channel group: read by the cluster peers
+  float4 coef[4][NC_MAXL];             // what pass 2 needs, per channel group
+};
+
+// Sum the (s, q) pairs of all pixel slots of the CTA: shuffles over the slots of a warp, then the warps in order (double).
+// The result lands in sh.xch[.][lane] (as fp32, like the per-block partials of the three-kernel path).
+__device__ __forceinline__ void nc_block_reduce(NcShared &sh, int L, float4 s, float4 q) {
+  for (int o = L; o < 32; o <<= 1) {
+    s.x += __shfl_xor_sync(0xffffffffu, s.x, o); s.y += __shfl_xor_sync(0xffffffffu, s.y, o);
+    s.z += __shfl_xor_sync(0xffffffffu, s.z, o); s.w += __shfl_xor_sync(0xffffffffu, s.w, o);
+    q.x += __shfl_xor_sync(0xffffffffu, q.x, o); q.y += __shfl_xor_sync(0xffffffffu, q.y, o);
+    q.z += __shfl_xor_sync(0xffffffffu, q.z, o); q.w += __shfl_xor_sync(0xffffffffu, q.w, o);
+  }
+  const int wl = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (wl < L) { sh.wred[0][w][wl] = s; sh.wred[1][w][wl] = q; }
+  __syncthreads();
+  if (threadIdx.x < L) {
+    double ds[4] = {0, 0, 0, 0}, dq[4] = {0, 0, 0, 0};
+#pragma unroll 4
+    for (int k = 0; k < NC_WARPS; ++k) {
+      const float4 a = sh.wred[0][k][threadIdx.x], b = sh.wred[1][k][threadIdx.x];
+      ds[0] += a.x; ds[1] += a.y; ds[2] += a.z; ds[3] += a.w;
+      dq[0] += b.x; dq[1] += b.y; dq[2] += b.z; dq[3] += b.w;
+    }
+    sh.xch[0][threadIdx.x] = make_float4((float)ds[0], (float)ds[1], (float)ds[2], (float)ds[3]);
+    sh.xch[1][threadIdx.x] = make_float4((float)dq[0], (float)dq[1], (float)dq[2], (float)dq[3]);
+  }
+}
+// After the cluster barrier: totals of channel group `l` over the cluster, ranks in ascending order.
+__device__ __forceinline__ void nc_cluster_total(const NcShared &sh, int l, int cs, double ds[4], double dq[4]) {
+  for (int j = 0; j < 4; ++j) { ds[j] = 0.0; dq[j] = 0.0; }
+  for (int r = 0; r < cs; ++r) {
+    const float4 a = nc_ld_peer(&sh.xch[0][l], (uint32_t)r), b = nc_ld_peer(&sh.xch[1][l], (uint32_t)r);
+    ds[0] += a.x; ds[1] += a.y; ds[2] += a.z; ds[3] += a.w;
+    dq[0] += b.x; dq[1] += b.y; dq[2] += b.z; dq[3] += b.w;
+  }
+}
+
+struct NcFwdArgs {
+  const float *x, *gamma, *beta;
+  float *running_mean, *running_var;
+  long long *nbt;
+  float *y, *save_mean, *save_rstd;
+  float momentum, eps;
+  int training, relu, tf32, cs;
+};
+
+template <bool POOL>
+__global__ void __launch_bounds__(NC_THREADS)
+bn_fwd_cluster_kernel(const NaGeom g, const PoolGeom pg, const NcFwdArgs p) {
+  __shared__ NcShared sh;
+  pdl_wait();
+  const int L = g.lanes;
+  const int lane = threadIdx.x % L, slot = threadIdx.x / L;
+  const int c4 = blockIdx.y * L + lane;
+  const bool active = c4 * 4 < g.Cs;
+  const long long cq = g.Cs / 4, stride = (long long)p.cs * g.slots;
+  const long long r0 = (long long)blockIdx.x * g.slots + slot;       // blockIdx.x == cluster rank
+  const float4 *xp = reinterpret_cast<const float4 *>(p.x) + c4;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+  if (p.training) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+    if (active) {
+#pragma unroll 4
+      for (long long r = r0; r < g.M; r += stride) {
+        const float4 v = pad0(__ldg(xp + r * cq), c4, g.C);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
+      }
+    }
+    nc_block_reduce(sh, L, s, q);
+    nc_cluster_arrive();
+    nc_cluster_wait();
+    if (threadIdx.x < L) {
+      const int cg = blockIdx.y * L + threadIdx.x;        // this thread's channel group
+      float mu[4] = {0, 0, 0, 0}, rs[4] = {0, 0, 0, 0};
+      if (cg * 4 < g.Cs) {
+        double ds[4], dq[4];
+        nc_cluster_total(sh, threadIdx.x, p.cs, ds, dq);
+        for (int j = 0; j < 4; ++j) {
+          const int c = cg * 4 + j;
+          if (c >= g.C) continue;                          // padding lane: zero coefficients, y = 0 there
+          const double mean = ds[j] / (double)g.M;
+          double var = dq[j] / (double)g.M - mean * mean;
+          if (var < 0.0) var = 0.0;
+          mu[j] = (float)mean;
+          rs[j] = (float)(1.0 / sqrt(var + (double)p.eps));
+          if (blockIdx.x == 0) {
+            p.save_mean[c] = mu[j];
+            p.save_rstd[c] = rs[j];
+            if (p.running_mean) {
+              const double unbiased = g.M > 1 ? var * (double)g.M / (double)(g.M - 1) : var;
+              p.running_mean[c] = (float)((1.0 - (double)p.momentum) * (double)p.running_mean[c] + (double)p.momentum * mean);
+              p.running_var[c] = (float)((1.0 - (double)p.momentum) * (double)p.running_var[c] + (double)p.momentum * unbiased);
+            }
+          }
+        }
+      }
+      sh.coef[2][threadIdx.x] = make_float4(mu[0], mu[1], mu[2], mu[3]);
+      sh.coef[3][threadIdx.x] = make_float4(rs[0], rs[1], rs[2], rs[3]);
+    }
+    if (p.nbt && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *p.nbt += 1;     // nn.BatchNorm2d.forward
+    nc_cluster_arrive();                                  // the peers' partials have been read; waited for at the end
+    __syncthreads();
+    if (active) coef_from_stats(p.gamma, p.beta, c4, g.C, sh.coef[2][lane], sh.coef[3][lane], a, b);
+  } else if (active) {
+    const float4 rm = ldp4(p.running_mean, c4, g.C, 0.f), rv = ldp4(p.running_var, c4, g.C, 1.f);
+    const float4 rs = make_float4(1.0f / sqrtf(rv.x + p.eps), 1.0f / sqrtf(rv.y + p.eps), 1.0f / sqrtf(rv.z + p.eps),
+                                  1.0f / sqrtf(rv.w + p.eps));
+    coef_from_stats(p.gamma, p.beta, c4, g.C, rm, rs, a, b);
+  }
+  if (active) {
+    // padding lanes (channels >= C of the last group): zero coefficients
+    const int c = c4 * 4;
+    if (c + 0 >= g.C) { a.x = 0.f; b.x = 0.f; }
+    if (c + 1 >= g.C) { a.y = 0.f; b.y = 0.f; }
+    if (c + 2 >= g.C) { a.z = 0.f; b.z = 0.f; }
+    if (c + 3 >= g.C) { a.w = 0.f; b.w = 0.f; }
+    float4 *yp = reinterpret_cast<float4 *>(p.y) + c4;
+    const int relu = p.relu, tf32 = p.tf32;
+    if (!POOL) {
+#pragma unroll 4
+      for (long long r = r0; r < g.M; r += stride) {
+        const float4 v = pad0(__ldg(xp + r * cq), c4, g.C);
+        float4 o = make_float4(fmaf(v.x, a.x, b.x), fmaf(v.y, a.y, b.y), fmaf(v.z, a.z, b.z), fmaf(v.w, a.w, b.w));
+        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        yp[r * cq] = na_out(o, tf32);
+      }
+    } else {
+      const long long down = (long long)pg.W * cq;
+#pragma unroll 2
+      for (long long r = r0; r < pg.Mo; r += stride) {
+        const float4 *w = xp + pool_base(pg, r, cq);
+        const float4 v0 = pad0(__ldg(w), c4, g.C), v1 = pad0(__ldg(w + cq), c4, g.C), v2 = pad0(__ldg(w + down), c4, g.C),
+                     v3 = pad0(__ldg(w + down + cq), c4, g.C);
+        float4 o;
+        o.x = fmaxf(fmaxf(fmaf(v0.x, a.x, b.x), fmaf(v1.x, a.x, b.x)), fmaxf(fmaf(v2.x, a.x, b.x), fmaf(v3.x, a.x, b.x)));
+        o.y = fmaxf(fmaxf(fmaf(v0.y, a.y, b.y), fmaf(v1.y, a.y, b.y)), fmaxf(fmaf(v2.y, a.y, b.y), fmaf(v3.y, a.y, b.y)));
+        o.z = fmaxf(fmaxf(fmaf(v0.z, a.z, b.z), fmaf(v1.z, a.z, b.z)), fmaxf(fmaf(v2.z, a.z, b.z), fmaf(v3.z, a.z, b.z)));
+        o.w = fmaxf(fmaxf(fmaf(v0.w, a.w, b.w), fmaf(v1.w, a.w, b.w)), fmaxf(fmaf(v2.w, a.w, b.w), fmaf(v3.w, a.w, b.w)));
+        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        yp[r * cq] = na_out(o, tf32);
+      }
+    }
+  }
+  if (p.training) nc_cluster_wait();                     // nobody leaves while a peer may still read its partials
+}
+
+struct NcBwdArgs {
+  const float *x, *dy, *gamma, *beta, *mean, *rstd;
+  float *dx, *dgamma, *dbeta;
+  int training, relu, tf32, cs;
+};
+
+template <bool POOL>
+__global__ void __launch_bounds__(NC_THREADS)
+bn_bwd_cluster_kernel(const NaGeom g, const PoolGeom pg, const NcBwdArgs p) {
+  __shared__ NcShared sh;
+  pdl_wait();
+  const int L = g.lanes;
+  const int lane = threadIdx.x % L, slot = threadIdx.x / L;
+  const int c4 = blockIdx.y * L + lane;
+  const bool active = c4 * 4 < g.Cs;
+  const long long cq = g.Cs / 4, stride = (long long)p.cs * g.slots, down = (long long)pg.W * cq;
+  const long long r0 = (long long)blockIdx.x * g.slots + slot;
+  const long long rows = POOL ? pg.Mo : g.M;
+  const int relu = p.relu, tf32 = p.tf32;
+  const float4 *xp = reinterpret_cast<const float4 *>(p.x) + c4;
+  const float4 *dp = reinterpret_cast<const float4 *>(p.dy) + c4;
+  float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), rs = mu, a = mu, b = mu;
+  float4 s = mu, q = mu;
+  if (active) {
+    mu = ldp4(p.mean, c4, g.C, 0.f);
+    rs = ldp4(p.rstd, c4, g.C, 0.f);
+    coef_from_stats(p.gamma, p.beta, c4, g.C, mu, rs, a, b);
+    if (!POOL) {
+#pragma unroll 4
+      for (long long r = r0; r < rows; r += stride) {
+        const float4 v = pad0(__ldg(xp + r * cq), c4, g.C), d = pad0(__ldg(dp + r * cq), c4, g.C);
+        float gx, gy, gz, gw, hx, hy, hz, hw;
+        NA_GRAD_ELEM(gx, hx, v.x, d.x, a.x, b.x, mu.x, rs.x)
+        NA_GRAD_ELEM(gy, hy, v.y, d.y, a.y, b.y, mu.y, rs.y)
+        NA_GRAD_ELEM(gz, hz, v.z, d.z, a.z, b.z, mu.z, rs.z)
+        NA_GRAD_ELEM(gw, hw, v.w, d.w, a.w, b.w, mu.w, rs.w)
+        s.x += gx; s.y += gy; s.z += gz; s.w += gw;
+        q.x = fmaf(gx, hx, q.x); q.y = fmaf(gy, hy, q.y); q.z = fmaf(gz, hz, q.z); q.w = fmaf(gw, hw, q.w);
+      }
+    } else {
+#pragma unroll 2
+      for (long long r = r0; r < rows; r += stride) {
+        const float4 *w = xp + pool_base(pg, r, cq);
+        const float4 v0 = pad0(__ldg(w), c4, g.C), v1 = pad0(__ldg(w + cq), c4, g.C), v2 = pad0(__ldg(w + down), c4, g.C),
+                     v3 = pad0(__ldg(w + down + cq), c4, g.C);
+        const float4 d = pad0(__ldg(dp + r * cq), c4, g.C);
+        float gx, gy, gz, gw, hx, hy, hz, hw;
+        int jx, jy, jz, jw;
+        NA_POOL_ELEM(gx, jx, hx, v0.x, v1.x, v2.x, v3.x, d.x, a.x, b.x, mu.x, rs.x)
+        NA_POOL_ELEM(gy, jy, hy, v0.y, v1.y, v2.y, v3.y, d.y, a.y, b.y, mu.y, rs.y)
+        NA_POOL_ELEM(gz, jz, hz, v0.z, v1.z, v2.z, v3.z, d.z, a.z, b.z, mu.z, rs.z)
+        NA_POOL_ELEM(gw, jw, hw, v0.w, v1.w, v2.w, v3.w, d.w, a.w, b.w, mu.w, rs.w)
+        s.x += gx; s.y += gy; s.z += gz; s.w += gw;
+        q.x = fmaf(gx, hx, q.x); q.y = fmaf(gy, hy, q.y); q.z = fmaf(gz, hz, q.z); q.w = fmaf(gw, hw, q.w);
+      }
+    }
+  }
+  nc_block_reduce(sh, L, s, q);
+  nc_cluster_arrive();
+  nc_cluster_wait();
+  if (threadIdx.x < L) {
+    const int cg = blockIdx.y * L + threadIdx.x;
+    float k1[4] = {0, 0, 0, 0}, k2[4] = {0, 0, 0, 0};
+    if (cg * 4 < g.Cs) {
+      double ds[4], dq[4];
+      nc_cluster_total(sh, threadIdx.x, p.cs, ds, dq);
+      for (int j = 0; j < 4; ++j) {
+        const int c = cg * 4 + j;
+        if (c >= g.C) continue;
+        if (blockIdx.x == 0) {
+          if (p.dbeta) p.dbeta[c] = (float)ds[j];
+          if (p.dgamma) p.dgamma[c] = (float)dq[j];
+        }
+        // statistics are constants in evaluation mode: dx = a * g
+        k1[j] = p.training ? (float)(ds[j] / (double)g.M) : 0.f;
+        k2[j] = p.training ? (float)(dq[j] / (double)g.M) : 0.f;
+      }
+    }
+    sh.coef[0][threadIdx.x] = make_float4(k1[0], k1[1], k1[2], k1[3]);
+    sh.coef[1][threadIdx.x] = make_float4(k2[0], k2[1], k2[2], k2[3]);
+  }
+  nc_cluster_arrive();
+  __syncthreads();
+  if (active) {
+    const float4 k1 = sh.coef[0][lane], k2 = sh.coef[1][lane];
+    float4 *op = reinterpret_cast<float4 *>(p.dx) + c4;
+    if (!POOL) {
+#pragma unroll 4
+      for (long long r = r0; r < rows; r += stride) {
+        const float4 v = pad0(__ldg(xp + r * cq), c4, g.C), d = pad0(__ldg(dp + r * cq), c4, g.C);
+        float gx, gy, gz, gw, hx, hy, hz, hw;
+        NA_GRAD_ELEM(gx, hx, v.x, d.x, a.x, b.x, mu.x, rs.x)
+        NA_GRAD_ELEM(gy, hy, v.y, d.y, a.y, b.y, mu.y, rs.y)
+        NA_GRAD_ELEM(gz, hz, v.z, d.z, a.z, b.z, mu.z, rs.z)
+        NA_GRAD_ELEM(gw, hw, v.w, d.w, a.w, b.w, mu.w, rs.w)
+        op[r * cq] = na_out(make_float4(a.x * (gx - k1.x - hx * k2.x), a.y * (gy - k1.y - hy * k2.y),
+                                        a.z * (gz - k1.z - hz * k2.z), a.w * (gw - k1.w - hw * k2.w)), tf32);
+      }
+    } else {
+#pragma unroll 2
+      for (long long r = r0; r < rows; r += stride) {
+        const long long base = pool_base(pg, r, cq);
+        const float4 *w = xp + base;
+        const float4 v0 = pad0(__ldg(w), c4, g.C), v1 = pad0(__ldg(w + cq), c4, g.C), v2 = pad0(__ldg(w + down), c4, g.C),
+                     v3 = pad0(__ldg(w + down + cq), c4, g.C);
+        const float4 d = pad0(__ldg(dp + r * cq), c4, g.C);
+        float4 o0, o1, o2, o3;
+        NA_POOL_DX(o0.x, o1.x, o2.x, o3.x, v0.x, v1.x, v2.x, v3.x, d.x, a.x, b.x, mu.x, rs.x, k1.x, k2.x)
+        NA_POOL_DX(o0.y, o1.y, o2.y, o3.y, v0.y, v1.y, v2.y, v3.y, d.y, a.y, b.y, mu.y, rs.y, k1.y, k2.y)
+        NA_POOL_DX(o0.z, o1.z, o2.z, o3.z, v0.z, v1.z, v2.z, v3.z, d.z, a.z, b.z, mu.z, rs.z, k1.z, k2.z)
+        NA_POOL_DX(o0.w, o1.w, o2.w, o3.w, v0.w, v1.w, v2.w, v3.w, d.w, a.w, b.w, mu.w, rs.w, k1.w, k2.w)
+        float4 *o = op + base;
+        o[0] = na_out(o0, tf32); o[cq] = na_out(o1, tf32); o[down] = na_out(o2, tf32); o[down + cq] = na_out(o3, tf32);
+      }
+    }
+  }
+  nc_cluster_wait();
+}
+
+// Opt-in (CPGB_BN_CLUSTER=1; read per call so that the tests compare both paths in one process).  Measured on B200
+// inside CUDA graphs with x left in L2 by a producer (tools/bn_ab.py, gpurun_out/r2_bn_ab*.txt), the single launch
+// LOSES to stats -> finalize -> apply on every VGG16 shape: 58.6 vs 23.6 us forward on 64 channels @ 32x32 (a CTA that
+// owns 8 channels touches 32 of every 256-byte pixel row: 16 L1 wavefronts per warp load, and 64-128 CTAs of 16
+// warps keep too few bytes in flight), 13.7 vs 10.3 us on 256 @ 8x8, 8.6 vs 7.2 us on the 1 MB 512 @ 2x2 tensor (the
+// serial finalize chain of a few threads per CTA costs more than two extra launches at ~2.4 us each under PDL).
+// CPGB_BN_CLUSTER_MB limits it to tensors up to that size.
+bool nc_enabled(long long M, int Cs) {
+  const char *e = getenv("CPGB_BN_CLUSTER");
+  if (!(e && atoi(e) != 0)) return false;
+  const char *t = getenv("CPGB_BN_CLUSTER_MB");
+  const double limit_mb = t ? atof(t) : 1e9;
+  return (double)M * Cs * 4.0 / 1e6 <= limit_mb;
+}
+
 bool na_args_ok(const void *x, long long M, int C, int Cs) {
   return M > 0 && C > 0 && Cs >= C && Cs % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
 }
@@ -544,6 +875,24 @@ int cpgb_bn_relu_fwd(const float *x, int64_t M, int32_t C, int32_t ldc, const fl
     set_error("cpgb_bn_relu_fwd: missing statistics buffers"); return CPGB_EINVAL;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (nc_enabled(M, Cs)) {
+    // one launch: clusters of CTAs split the pixel rows of a channel chunk and exchange their partial sums through
+    // distributed shared memory
+    const NcPlan pl = nc_plan(M, Cs);
+    NaGeom gc;
+    gc.M = M; gc.C = C; gc.Cs = Cs; gc.lanes = pl.lanes; gc.slots = pl.slots; gc.cchunks = pl.chunks;
+    NcFwdArgs a;
+    a.x = x; a.gamma = gamma; a.beta = beta; a.running_mean = running_mean; a.running_var = running_var;
+    a.nbt = training ? reinterpret_cast<long long *>(num_batches_tracked) : nullptr;
+    a.y = y; a.save_mean = save_mean; a.save_rstd = save_rstd; a.momentum = momentum; a.eps = eps;
+    a.training = training ? 1 : 0; a.relu = relu; a.tf32 = tf32_out; a.cs = pl.cs;
+    if (!pool) { pg.H = pg.W = pg.Ho = pg.Wo = 0; pg.Mo = 0; }
+    const dim3 grid(pl.cs, pl.chunks);
+    if (pool) CPGB_CUDA_OK(launch_dependent_cluster(bn_fwd_cluster_kernel<true>, grid, dim3(NC_THREADS), 0, st, pl.cs, gc, pg, a));
+    else CPGB_CUDA_OK(launch_dependent_cluster(bn_fwd_cluster_kernel<false>, grid, dim3(NC_THREADS), 0, st, pl.cs, gc, pg, a));
+    CPGB_LAUNCH_OK("bn_fwd_cluster");
+    return CPGB_OK;
+  }
   NaGeom g = na_geom(M, C, Cs);
   float *coef_a = reinterpret_cast<float *>(ws), *coef_b = coef_a + Cs, *part = coef_a + 4 * Cs;
   if (training) {
@@ -590,6 +939,21 @@ int cpgb_bn_relu_bwd(const float *x, const float *dy, int64_t M, int32_t C, int3
     set_error("cpgb_bn_relu_bwd: workspace %zu < %zu", ws_bytes, na_ws_bytes(M, Cs)); return CPGB_EWORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (nc_enabled(M, Cs)) {
+    const NcPlan pl = nc_plan(pool ? pg.Mo : M, Cs);
+    NaGeom gc;
+    gc.M = M; gc.C = C; gc.Cs = Cs; gc.lanes = pl.lanes; gc.slots = pl.slots; gc.cchunks = pl.chunks;
+    NcBwdArgs a;
+    a.x = x; a.dy = dy; a.gamma = gamma; a.beta = beta; a.mean = mean; a.rstd = rstd;
+    a.dx = dx; a.dgamma = dgamma; a.dbeta = dbeta; a.training = training ? 1 : 0; a.relu = relu; a.tf32 = tf32_out;
+    a.cs = pl.cs;
+    if (!pool) { pg.H = pg.W = pg.Ho = pg.Wo = 0; pg.Mo = 0; }
+    const dim3 grid(pl.cs, pl.chunks);
+    if (pool) CPGB_CUDA_OK(launch_dependent_cluster(bn_bwd_cluster_kernel<true>, grid, dim3(NC_THREADS), 0, st, pl.cs, gc, pg, a));
+    else CPGB_CUDA_OK(launch_dependent_cluster(bn_bwd_cluster_kernel<false>, grid, dim3(NC_THREADS), 0, st, pl.cs, gc, pg, a));
+    CPGB_LAUNCH_OK("bn_bwd_cluster");
+    return CPGB_OK;
+  }
   NaGeom g = na_geom(M, C, Cs);
   float *c1 = reinterpret_cast<float *>(ws) + 2 * Cs, *c2 = c1 + Cs, *part = c2 + Cs;
   const NaGeom gs = na_geom(M, C, Cs, NA_STATS_THREADS);

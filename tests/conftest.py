@@ -30,3 +30,11 @@ def golden():
     def load(name):
         return dict(np.load(os.path.join(GOLDEN, name + '.npz'), allow_pickle=False))
     return load
+
+
+@pytest.fixture(params=['cluster', 'three_kernels'])
+def bn_path(request, monkeypatch):
+    """Both implementations behind cpgb_bn_relu_fwd / _bwd: the stats -> finalize -> apply sequence (default) and the
+    single-launch cluster kernels (CPGB_BN_CLUSTER=1; the library reads the variable per call)."""
+    monkeypatch.setenv('CPGB_BN_CLUSTER', '1' if request.param == 'cluster' else '0')
+    return request.param

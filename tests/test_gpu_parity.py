@@ -737,7 +737,7 @@ BN_CASES = [
 
 
 @pytest.mark.parametrize('case', BN_CASES)
-def test_fused_bn_relu_vs_torch(case):
+def test_fused_bn_relu_vs_torch(case, bn_path):
     from cpg_b200.fused_norm import FusedBatchNormReLU2d
     N, C, H, W, relu, affine = case
     torch.manual_seed(N + C + H)
@@ -757,7 +757,8 @@ def test_fused_bn_relu_vs_torch(case):
         ya = torch.relu(ya) if relu else ya
         before = lib.cpgb_launch_count()
         yb = fused(xb)
-        assert lib.cpgb_launch_count() - before == 3        # stats, finalize, apply: the CUDA path ran
+        # the CUDA path ran: one cluster kernel, or stats -> finalize -> apply
+        assert lib.cpgb_launch_count() - before == (1 if bn_path == 'cluster' else 3)
         assert yb.is_contiguous(memory_format=torch.channels_last)
         ya.backward(dy); yb.backward(dy)
         assert rel(yb, ya) <= TOL_FP32
@@ -813,7 +814,7 @@ def test_fused_bn_model_step_matches_stock_modules():
 
 @pytest.mark.parametrize('shape', [(128, 64, 32, 32), (128, 512, 2, 2), (4, 156, 6, 10), (2, 2048, 4, 4)])
 @pytest.mark.parametrize('train', [True, False])
-def test_fused_bn_relu_maxpool_vs_torch(shape, train):
+def test_fused_bn_relu_maxpool_vs_torch(shape, train, bn_path):
     """conv -> BN -> ReLU -> MaxPool2d(2, 2) (the 'M' entries of models/vgg.py:95-122) with the pool folded
     into the batch-norm kernels, against the three stock modules."""
     from cpg_b200.fused_norm import FusedBatchNormReLU2d

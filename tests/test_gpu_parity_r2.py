@@ -565,7 +565,7 @@ def test_grown_width_linear_layers_on_tensor_cores(I, O_):
 
 @pytest.mark.parametrize('shape', [(128, 78, 32, 32), (64, 313, 8, 8), (32, 627, 2, 2)])
 @pytest.mark.parametrize('pool', [False, True])
-def test_fused_bn_relu_on_padded_channels(shape, pool):
+def test_fused_bn_relu_on_padded_channels(shape, pool, bn_path):
     """BatchNorm2d + ReLU (+ MaxPool2d(2, 2)) kernels on channel counts that are not a multiple of 4: padded-NHWC
     in and out, garbage in the pad lanes of the inputs, against the stock torch modules."""
     from cpg_b200.functional import empty_nhwc, nhwc_pixel_stride
