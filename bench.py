@@ -519,8 +519,8 @@ def kernel_table(device, regime_has_piggy, iters=5, width=1.0, only=None):
 def prune_table(device, iters=5):
     """a7 on the device: one prune event (utils/prune.py:78-92 -> _pruning_mask per layer) over the 15
     sharable layers of VGG16 (33.6 M weights), CUDA events, L2 flushed.  Algorithmic bytes = one pass:
-    read W 4 B + T 1 B, write T 1 B per element; the 3-digit radix select reads W and T four
-    times, which is what `passes` says."""
+    read W 4 B + T 1 B, write T 1 B per element; `passes` = how often the select streams W and T
+    (two: cpgb_prune_select_sampled; four: the 3-digit radix select, CPGB_PRUNE_SAMPLED=0)."""
     import cpg_b200.layers as nl
     from cpg_b200.prune import SparsePruner
     net, masks, datasets, cur = build_model(nl.SharableConv2d, nl.SharableLinear, 'task1', device)
@@ -544,9 +544,31 @@ def prune_table(device, iters=5):
         if i >= 2:
             ts.append(e0.elapsed_time(e1))
     ms = statistics.median(ts)
+    # the select alone (what the roofline fraction is about): events around the batched C call, no read-back inside
+    layers = list(pruner._sharable())
+    infos = torch.zeros(len(layers), 4, dtype=torch.int64, device=device)
+    tk = []
+    for i in range(iters + 2):
+        for m in masks.values():
+            m.fill_(cur)
+        flush.zero_()
+        torch.cuda._sleep(4000000)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        pruner._launch_prune_batched(layers, 0.0015, infos)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            tk.append(e0.elapsed_time(e1))
+    ms_k = statistics.median(tk)
+    assert int(infos[:, 0].abs().sum()) == 0
     zeros = sum(int((m == 0).sum()) for m in masks.values())
-    return {'ms_per_prune_event': ms, 'elements': n, 'algorithmic_bytes': 6 * n, 'passes': 4,
-            'achieved_gbs_algorithmic': 6 * n / (ms * 1e-3) / 1e9, 'pruned_fraction_check': zeros / n}
+    sampled = os.environ.get('CPGB_PRUNE_SAMPLED', '1') != '0'
+    return {'ms_per_prune_event': ms, 'elements': n, 'algorithmic_bytes': 6 * n, 'passes': 2 if sampled else 4,
+            'select': ('two-pass: sorted sample brackets the k-th magnitude, exact count + select inside the bracket '
+                       '(cpgb_prune_select_sampled)' if sampled else 'four-pass 11/11/9-bit radix select'),
+            'ms_select_kernels': ms_k, 'achieved_gbs_algorithmic': 6 * n / (ms_k * 1e-3) / 1e9,
+            'achieved_gbs_event_incl_readback': 6 * n / (ms * 1e-3) / 1e9, 'pruned_fraction_check': zeros / n}
 
 
 def cpu_port_step_time(regime, batch, steps, warmup, threads):

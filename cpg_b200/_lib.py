@@ -18,11 +18,12 @@ EXPORTS = [
     'cpgb_workspace_bytes', 'cpgb_staged_weight_bytes', 'cpgb_stage_weights', 'cpgb_staged_weight_bytes_for',
     'cpgb_stage_weights_batched', 'cpgb_weights_usable_raw', 'cpgb_weights_usable_raw_for', 'cpgb_binarize', 'cpgb_conv2d_fprop', 'cpgb_conv2d_dgrad',
     'cpgb_conv2d_wgrad_fused', 'cpgb_grad_epilogue', 'cpgb_prune_workspace_bytes', 'cpgb_prune_select',
-    'cpgb_prune_batched_workspace_bytes', 'cpgb_prune_select_batched',
+    'cpgb_prune_batched_workspace_bytes', 'cpgb_prune_select_batched', 'cpgb_prune_sampled_workspace_bytes',
+    'cpgb_prune_select_sampled',
     'cpgb_apply_mask', 'cpgb_make_finetuning_mask', 'cpgb_mask_stats', 'cpgb_mask_stats_batched', 'cpgb_merge_grads',
     'cpgb_split_merged_grad', 'cpgb_bn_workspace_bytes', 'cpgb_bn_relu_fwd', 'cpgb_bn_relu_bwd',
     'cpgb_uses_tensor_cores', 'cpgb_round_tf32', 'cpgb_conv2d_bias_grad', 'cpgb_pack_mask', 'cpgb_intile_eligible',
-    'cpgb_intile_weight_shape',
+    'cpgb_intile_weight_shape', 'cpgb_sgd_nesterov_step', 'cpgb_adam_step',
 ]
 
 
@@ -83,6 +84,14 @@ def load():
         'cpgb_prune_batched_workspace_bytes': (sz, [i32]),
         'cpgb_prune_select_batched': (ctypes.c_int, [i32, ctypes.POINTER(vp), ctypes.POINTER(vp),
                                                      ctypes.POINTER(i64), i32, dbl, vp, vp, sz, vp]),
+        'cpgb_prune_sampled_workspace_bytes': (sz, [i32]),
+        'cpgb_prune_select_sampled': (ctypes.c_int, [i32, ctypes.POINTER(vp), ctypes.POINTER(vp),
+                                                     ctypes.POINTER(i64), i32, dbl, vp, vp, sz, vp]),
+        'cpgb_sgd_nesterov_step': (ctypes.c_int, [i32, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp),
+                                                  ctypes.POINTER(i64), f32, f32, vp, vp]),
+        'cpgb_adam_step': (ctypes.c_int, [i32, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp),
+                                          ctypes.POINTER(vp), ctypes.POINTER(i64), dbl, dbl, dbl, dbl, vp, vp,
+                                          ctypes.POINTER(vp), ctypes.POINTER(vp), f32, i32, vp]),
         'cpgb_apply_mask': (ctypes.c_int, [vp, vp, i64, i32, vp]),
         'cpgb_make_finetuning_mask': (ctypes.c_int, [vp, i64, i32, vp]),
         'cpgb_mask_stats': (ctypes.c_int, [vp, vp, i64, i32, vp, vp]),

@@ -224,8 +224,12 @@ class SparsePruner(object):
                                              _lib.ptr(info), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
                        'cpgb_prune_select')
 
-    def _launch_prune_batched(self, layers, pruning_ratio, infos):
+    def _launch_prune_batched(self, layers, pruning_ratio, infos, sampled=None):
+        """a7 for up to 64 layers in one call.  `sampled` (default: on unless CPGB_PRUNE_SAMPLED=0) picks the two-pass
+        select (cpgb_prune_select_sampled); layers it reports as status 3 are finished by the caller with the
+        four-pass radix select."""
         import ctypes
+        import os
         lib = _lib.load()
         self._mask_epoch += 1
         nl_ = len(layers)
@@ -233,15 +237,19 @@ class SparsePruner(object):
         W = (ctypes.c_void_p * nl_)(*[_lib.ptr(self._dense(m.weight.data, 'weight')) for _, m in layers])
         T = (ctypes.c_void_p * nl_)(*[_lib.ptr(self._mask(n)) for n, _ in layers])
         N = (ctypes.c_int64 * nl_)(*[m.weight.numel() for _, m in layers])
-        nbytes = lib.cpgb_prune_batched_workspace_bytes(nl_)
-        key = ('batched', str(dev), nbytes)
+        if sampled is None:
+            sampled = os.environ.get('CPGB_PRUNE_SAMPLED', '1') != '0'
+        sampled = sampled and all(m.weight.numel() < 2 ** 32 for _, m in layers)
+        nbytes = (lib.cpgb_prune_sampled_workspace_bytes if sampled else lib.cpgb_prune_batched_workspace_bytes)(nl_)
+        key = ('sampled' if sampled else 'batched', str(dev), nbytes)
         if key not in self._prune_ws:
             self._prune_ws[key] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         ws = self._prune_ws[key]
+        fn, what = ((lib.cpgb_prune_select_sampled, 'cpgb_prune_select_sampled') if sampled else
+                    (lib.cpgb_prune_select_batched, 'cpgb_prune_select_batched'))
         with torch.cuda.device(dev):
-            _lib.check(lib.cpgb_prune_select_batched(nl_, W, T, N, self.current_dataset_idx, float(pruning_ratio),
-                                                     _lib.ptr(infos), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
-                       'cpgb_prune_select_batched')
+            _lib.check(fn(nl_, W, T, N, self.current_dataset_idx, float(pruning_ratio), _lib.ptr(infos), _lib.ptr(ws),
+                          ws.numel(), _lib.stream_ptr()), what)
 
     @staticmethod
     def _exit_not_enough():
@@ -288,7 +296,16 @@ class SparsePruner(object):
                 # zeroed here (utils/prune.py:88 is commented out)
                 for lo in range(0, len(layers), 64):
                     self._launch_prune_batched(layers[lo:lo + 64], curr_pruning_ratio, infos[lo:lo + 64])
-                if bool((infos[:, 0] != 0).any().item()):   # one read-back per prune event
+                status = infos[:, 0].cpu()                  # one read-back per prune event
+                if bool((status == 3).any()):
+                    # the two-pass select could not bracket these layers (adversarial value distributions):
+                    # finish them with the four-pass radix select
+                    redo = [layers[i] for i in range(len(layers)) if int(status[i]) == 3]
+                    infos2 = torch.zeros(len(redo), 4, dtype=torch.int64, device=dev)
+                    for lo in range(0, len(redo), 64):
+                        self._launch_prune_batched(redo[lo:lo + 64], curr_pruning_ratio, infos2[lo:lo + 64], sampled=False)
+                    status = torch.cat([status[status != 3], infos2[:, 0].cpu()])
+                if bool((status != 0).any()):
                     self._exit_not_enough()
         else:
             curr_pruning_ratio = self._adjust_sparsity(self.last_prune_step)

@@ -203,6 +203,19 @@ size_t cpgb_prune_batched_workspace_bytes(int32_t nlayers);
 int cpgb_prune_select_batched(int32_t nlayers, const float *const *w, uint8_t *const *tmask, const int64_t *n,
                               int32_t cur, double ratio, int64_t *info, void *ws, size_t ws_bytes, void *stream);
 
+/* The same result as cpgb_prune_select_batched with TWO streaming passes over W / T instead of four (a7 is HBM-bound:
+ * 5 B/element per pass): a sorted sample of 16384 pool keys per layer brackets the k-th magnitude, one pass counts
+ * |pool|, the keys below the bracket and a 2048-bin histogram inside it, a second pass prunes everything below the
+ * k-th element's bin and collects that bin's few elements, which one block per layer then selects from exactly.  The
+ * sample only places the bracket; counting and selection are exact.  info[l][0] == 3 reports a layer whose bracket
+ * missed the k-th element or whose bin overflowed the candidate list (possible only for adversarial value
+ * distributions): its mask holds a correct partial result and the caller must run cpgb_prune_select_batched on that
+ * layer to finish it (cpg_b200/prune.py does).  Layers of up to 2^32 - 1 elements.
+ * ws: cpgb_prune_sampled_workspace_bytes(nlayers), 8-byte aligned. */
+size_t cpgb_prune_sampled_workspace_bytes(int32_t nlayers);
+int cpgb_prune_select_sampled(int32_t nlayers, const float *const *w, uint8_t *const *tmask, const int64_t *n,
+                              int32_t cur, double ratio, int64_t *info, void *ws, size_t ws_bytes, void *stream);
+
 /* a9: apply_mask (utils/prune.py:223-231): w[T==0]=0; w[T>inference_idx]=0.
  *     make_pruned_zero (utils/prune.py:213-221): pass inference_idx = 255. */
 int cpgb_apply_mask(float *w, const uint8_t *tmask, int64_t n, int32_t inference_idx, void *stream);
@@ -228,6 +241,28 @@ int cpgb_mask_stats_batched(int32_t nlayers, const uint8_t *const *tmask, const 
 int cpgb_merge_grads(const float *dW, const float *dP, float *merged, int64_t n, void *stream);
 int cpgb_split_merged_grad(const float *merged, const uint8_t *tmask, int64_t n, int32_t cur,
                            float *dW, float *dP, void *stream);
+
+/* SURVEY 8(f) N2 -- the optimizer step right after the path (CPG_cifar100_main_normal.py:339-346), one launch per
+ * optimizer instead of one ATen kernel per operation and parameter list.  param / grad / state arrays are HOST arrays of
+ * `ntensors` device pointers, n the element counts.  Every element is updated, also where the masked gradient is zero
+ * (momentum drift of pruned weights).  The arithmetic reproduces torch's multi-tensor implementation
+ * operation by operation (same fp32 roundings); state buffers start as zeros, as torch's do.
+ *
+ * cpgb_sgd_nesterov_step: optim.SGD(lr, momentum, nesterov=True, weight_decay=0, dampening=0):
+ *   buf = momentum * buf + g;  p -= lr * (g + momentum * buf).   lr_dev (may be NULL): device fp32 that overrides lr
+ *   (a learning-rate schedule inside a captured CUDA graph). */
+int cpgb_sgd_nesterov_step(int32_t ntensors, float *const *param, const float *const *grad, float *const *momentum_buf,
+                           const int64_t *n, float lr, float momentum, const float *lr_dev, void *stream);
+/* cpgb_adam_step: optim.Adam(lr, betas, eps, weight_decay=0, amsgrad=False) on at most 40 tensors per call.
+ *   step_dev: device int64[2], zero-initialised by the caller once: [0] = steps taken so far (incremented by the
+ *   kernel: capturable), [1] = scratch.  lr_dev (may be NULL): device fp64 override of lr.
+ *   packed (may be NULL, entries may be NULL): per tensor, receives the cpgb_pack_mask words of the UPDATED parameter
+ *   (low half bit j = (p > thr), high half bit j = (1 <= tmask <= inference_idx), all ones when tmask[i] == NULL), so
+ *   the next forward pass of an in-tile masked layer (CPGB_FLAG_W_INTILE) needs no pack pass. */
+int cpgb_adam_step(int32_t ntensors, float *const *param, const float *const *grad, float *const *exp_avg,
+                   float *const *exp_avg_sq, const int64_t *n, double lr, double beta1, double beta2, double eps,
+                   int64_t *step_dev, const double *lr_dev, uint64_t *const *packed, const uint8_t *const *tmask,
+                   float thr, int32_t inference_idx, void *stream);
 
 /* SURVEY 8(f) N4 -- the consumer of every masked convolution: nn.BatchNorm2d followed by
  * nn.ReLU(inplace=True) (models/vgg.py:109-118, models/resnet.py:60-100), on NHWC fp32 activations seen as

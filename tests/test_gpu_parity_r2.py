@@ -764,3 +764,102 @@ def test_intile_masking_equals_the_staged_operand(M, I, O_, piggy):
     assert rel(y1[:, keep], (x @ w_eff.t())[:, keep]) <= TOL_TC
     keep_i = [c for c in range(I) if c != 5]
     assert rel(dx1[:, keep_i], (dy @ w_eff)[:, keep_i]) <= TOL_TC
+
+
+# ---------------------------------------------------------------------------------------------
+# a7, two-pass variant: cpgb_prune_select_sampled == the four-pass radix select == the oracle
+# ---------------------------------------------------------------------------------------------
+def _prune_cases():
+    rng = np.random.RandomState(17)
+    cases = []
+    for n in (1, 7, 63, 1000, 4099, 36864, 262145, (1 << 20) + 3):
+        cases.append(('normal', rng.standard_normal(n).astype(np.float32), rng.randint(0, 4, size=n).astype(np.uint8)))
+    n = 300000
+    w = rng.standard_normal(n).astype(np.float32)
+    t = rng.randint(0, 4, size=n).astype(np.uint8)
+    wz = w.copy(); wz[t == 0] = 0.0                       # freed weights were zeroed by apply_mask: a tie at |w| = 0
+    cases.append(('zeros_in_pool', wz, t.copy()))
+    cases.append(('constant', np.full(n, 0.25, dtype=np.float32), t.copy()))
+    wq = (np.round(w * 4) / 4).astype(np.float32)         # 20 distinct magnitudes: massive ties inside any bracket
+    cases.append(('quantised', wq, t.copy()))
+    ws = (w * np.where(np.arange(n) % 64 < 32, 1e-3, 10.0)).astype(np.float32)   # structure at the sample stride
+    cases.append(('striped_scale', ws, t.copy()))
+    tp = np.ones(n, dtype=np.uint8); tp[::5000] = 2       # a pool of 60 elements in 300000
+    cases.append(('tiny_pool', w.copy(), tp))
+    tn = np.ones(n, dtype=np.uint8)                       # no pool at all -> exit-2 path
+    cases.append(('no_pool', w.copy(), tn))
+    wn = w.copy(); wn[::1000] = np.nan; wn[5::1000] = np.inf
+    cases.append(('nan_inf', wn, t.copy()))
+    wl = np.exp(rng.uniform(-80, 80, size=n)).astype(np.float32)                 # every exponent
+    cases.append(('log_uniform', wl, t.copy()))
+    return cases
+
+
+@pytest.mark.parametrize('ratio', [1e-6, 0.0015, 0.1, 0.37, 0.5, 0.93, 1.0])
+def test_prune_sampled_equals_radix_select_and_oracle(ratio):
+    import ctypes
+    lib = _lib.load()
+    cases = _prune_cases()
+    cur = 2
+    nl_ = len(cases)
+    sizes = [len(c[1]) for c in cases]
+    wg = [G(c[1]) for c in cases]
+    ta = [G(c[2].copy()) for c in cases]
+    tb = [G(c[2].copy()) for c in cases]
+    W = (ctypes.c_void_p * nl_)(*[t.data_ptr() for t in wg])
+    N = (ctypes.c_int64 * nl_)(*sizes)
+    info_a = torch.zeros(nl_, 4, dtype=torch.int64, device=DEV)
+    info_b = torch.zeros(nl_, 4, dtype=torch.int64, device=DEV)
+    TA = (ctypes.c_void_p * nl_)(*[t.data_ptr() for t in ta])
+    TB = (ctypes.c_void_p * nl_)(*[t.data_ptr() for t in tb])
+    wsa = torch.empty(lib.cpgb_prune_sampled_workspace_bytes(nl_), dtype=torch.uint8, device=DEV)
+    wsb = torch.empty(lib.cpgb_prune_batched_workspace_bytes(nl_), dtype=torch.uint8, device=DEV)
+    _lib.check(lib.cpgb_prune_select_sampled(nl_, W, TA, N, cur, ratio, info_a.data_ptr(), wsa.data_ptr(), wsa.numel(),
+                                             _lib.stream_ptr()), 'sampled')
+    _lib.check(lib.cpgb_prune_select_batched(nl_, W, TB, N, cur, ratio, info_b.data_ptr(), wsb.data_ptr(), wsb.numel(),
+                                             _lib.stream_ptr()), 'batched')
+    ia, ib = info_a.cpu().numpy(), info_b.cpu().numpy()
+    fell_back = []
+    for i, (name, w, t) in enumerate(cases):
+        if ia[i, 0] == 3:
+            # reported, not guessed: the partial result only removed elements the exact select removes as well
+            fell_back.append(name)
+            a, b = ta[i].cpu().numpy(), tb[i].cpu().numpy()
+            assert np.all((a == t) | (a == b)), name
+            info = torch.zeros(1, 4, dtype=torch.int64, device=DEV)
+            W1 = (ctypes.c_void_p * 1)(wg[i].data_ptr()); T1 = (ctypes.c_void_p * 1)(ta[i].data_ptr())
+            N1 = (ctypes.c_int64 * 1)(sizes[i])
+            _lib.check(lib.cpgb_prune_select_batched(1, W1, T1, N1, cur, ratio, info.data_ptr(), wsb.data_ptr(),
+                                                     wsb.numel(), _lib.stream_ptr()), 'finish')
+            ia[i] = info.cpu().numpy()[0]
+        assert np.array_equal(ia[i], ib[i]), (name, ia[i], ib[i])
+        assert torch.equal(ta[i], tb[i]), name
+        tt = torch.from_numpy(t.copy())
+        try:
+            O.pruning_mask(torch.from_numpy(w), tt, cur, ratio)
+            assert ia[i, 0] == 0, name
+        except O.NotEnoughWeights:
+            assert ia[i, 0] == 2, name
+        assert np.array_equal(ta[i].cpu().numpy(), tt.numpy()), name
+    # the well-behaved distributions must take the two-pass route
+    assert not ({'normal', 'zeros_in_pool', 'constant', 'log_uniform', 'nan_inf'} & set(fell_back)), fell_back
+
+
+def test_gradually_prune_two_pass_equals_four_pass(monkeypatch):
+    """The pruner's prune events through both selects (CPGB_PRUNE_SAMPLED=1 / 0) on the VGG16 layer set."""
+    from cpg_b200.prune import SparsePruner
+    from tests.trajectory import Wrap, build, make_args
+    res = {}
+    for flag in ('1', '0'):
+        monkeypatch.setenv('CPGB_PRUNE_SAMPLED', flag)
+        model, masks, _ = build(nl.SharableConv2d, nl.SharableLinear, DEV, width=0.5, batch=4)
+        net = Wrap(model)
+        masks = {'module.' + n: v for n, v in masks.items()}
+        args = make_args('prune', freq=1, target_s=0.6)
+        pr = SparsePruner(net, masks, args, 0, 10, 2)
+        ratios = [pr.gradually_prune(s) for s in range(0, 11, 2)]
+        res[flag] = (ratios, {k: v.clone() for k, v in masks.items()})
+    assert res['1'][0] == res['0'][0]
+    for k in res['1'][1]:
+        assert torch.equal(res['1'][1][k], res['0'][1][k]), k
+        assert int((res['1'][1][k] == 0).sum()) > 0
