@@ -109,10 +109,12 @@ def make_args(datasets, mode='finetune'):
 
 
 FUSE_BN_RELU = os.environ.get('CPGB_FUSE_BN', '1') != '0'   # cpg_b200.fused_norm on the product arm
-FUSED_OPTIM = True   # torch.optim.{SGD,Adam}(fused=True): same update rule, one pass over the parameters
+# optimizer of the product arm: 'cpgb' = cpg_b200.optim (one launch per optimizer, bit-identical to
+# torch's multi-tensor update), 'torch' = torch.optim.{SGD,Adam}(fused=True)
+OPTIM = os.environ.get('CPGB_OPTIM', 'cpgb')
 
 
-def make_optimizers(net, capturable):
+def split_params(net):
     sgd_params, adam_params = [], []
     head = '.{}.'.format(len(net.module.datasets) - 1)
     for name, p in net.named_parameters():        # routing of CPG_cifar100_main_normal.py:326-346
@@ -123,13 +125,26 @@ def make_optimizers(net, capturable):
             adam_params.append(p)
         else:
             sgd_params.append(p)
+    return sgd_params, adam_params
+
+
+def make_optimizers(net, capturable, product=False):
+    """The two optimizers of CPG_cifar100_main_normal.py:339-346.  product: the arm under test (cpg_b200.optim unless
+    CPGB_OPTIM=torch); otherwise stock torch.optim (fused=True on the GPU: the same update rule in one pass)."""
+    sgd_params, adam_params = split_params(net)
     on_gpu = bool(sgd_params) and sgd_params[0].is_cuda
-    fused = FUSED_OPTIM and on_gpu
+    if product and on_gpu and OPTIM == 'cpgb':
+        from cpg_b200.optim import SGD, Adam
+        opts = [SGD(sgd_params, lr=LR, weight_decay=0.0, momentum=0.9, nesterov=True)]
+        if adam_params:
+            opts.append(Adam(adam_params, lr=LR_MASK))
+            opts[-1].emit_packed_masks(net)      # the FC layers' Binarizer bits come out of the Adam kernel
+        return opts
     opts = [torch.optim.SGD(sgd_params, lr=LR, weight_decay=0.0, momentum=0.9, nesterov=True,
-                            **({'fused': True} if fused else {}))]
+                            **({'fused': True} if on_gpu else {}))]
     if adam_params:
         opts.append(torch.optim.Adam(adam_params, lr=LR_MASK, capturable=capturable,
-                                     **({'fused': True} if fused else {})))
+                                     **({'fused': True} if on_gpu else {})))
     return opts
 
 
@@ -286,7 +301,7 @@ class Trainer:
             self.net, self.masks, datasets, self.cur = build_model(TorchSharableConv2d, TorchSharableLinear, regime,
                                                                    device, width=width)
             self.pruner = TorchPruner(self.net, self.masks, self.cur)
-        self.opts = make_optimizers(self.net, capturable=use_graph)
+        self.opts = make_optimizers(self.net, capturable=use_graph, product=(impl == 'ours'))
         self.crit = nn.CrossEntropyLoss()
         self.reducer = GradAllReducer(self.net, world) if world > 1 else None
         self.net.train()
@@ -803,8 +818,12 @@ def main():
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'tf32 (fp32 in/out, fp32 accumulate)' if args.path == 'auto' else 'f32',
             'data': 'synthetic',
             'config': make_config(world),
-            'impl_detail': {'optimizer': 'torch.optim.SGD(fused=True) (+Adam(fused=True) on piggymasks in task2): same '
-                                         'update rule as CPG_cifar100_main_normal.py:339-346',
+            'impl_detail': {'optimizer': ('cpg_b200.optim.SGD (+ cpg_b200.optim.Adam on the piggymasks in task2): '
+                                          'cpgb_sgd_nesterov_step / cpgb_adam_step, one launch each, bit-identical to '
+                                          'the torch.optim calls of CPG_cifar100_main_normal.py:339-346'
+                                          if OPTIM == 'cpgb' else
+                                          'torch.optim.SGD(fused=True) (+Adam(fused=True) on piggymasks in task2): same '
+                                          'update rule as CPG_cifar100_main_normal.py:339-346'),
                             'cuda_graph': not args.no_graph,
                             'model': r1.get('model_source'),
                             'bn_relu_pool': ('cpg_b200.fused_norm (BatchNorm2d+ReLU(+MaxPool2d) kernels, SURVEY 8f N4), '

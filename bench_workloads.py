@@ -111,9 +111,16 @@ def _build(workload, device, regime):
             adam.append(p)
         else:
             sgd.append(p)
-    opts = [torch.optim.SGD(sgd, lr=LR_OF.get(workload, LR), weight_decay=0.0, momentum=0.9, nesterov=True, fused=True)]
-    if adam:
-        opts.append(torch.optim.Adam(adam, lr=LR_MASK, capturable=True, fused=True))
+    if os.environ.get('CPGB_OPTIM', 'cpgb') == 'cpgb':          # the product's fused optimizer kernels
+        from cpg_b200.optim import SGD, Adam
+        opts = [SGD(sgd, lr=LR_OF.get(workload, LR), weight_decay=0.0, momentum=0.9, nesterov=True)]
+        if adam:
+            opts.append(Adam(adam, lr=LR_MASK))
+            opts[-1].emit_packed_masks(net)
+    else:
+        opts = [torch.optim.SGD(sgd, lr=LR_OF.get(workload, LR), weight_decay=0.0, momentum=0.9, nesterov=True, fused=True)]
+        if adam:
+            opts.append(torch.optim.Adam(adam, lr=LR_MASK, capturable=True, fused=True))
     net.train()
     return net, masks, pruner, opts, shape, batch, classes, gflop
 

@@ -336,9 +336,17 @@ def main(argv=None):
         else:
             sgd_params.append(param)
     optimizers = Optimizers()
-    optimizers.add(torch.optim.SGD(sgd_params, lr=args.lr, weight_decay=0.0, momentum=0.9, nesterov=True), args.lr)
+    # the same two optimizers (:339-346), each step one launch of cpg_b200.optim (bit-identical to torch's update;
+    # CPGB_OPTIM=torch keeps the stock classes, as does a model that is not on the GPU)
+    if os.environ.get('CPGB_OPTIM', 'cpgb') == 'cpgb' and sgd_params and sgd_params[0].is_cuda:
+        from ..optim import SGD, Adam
+    else:
+        SGD, Adam = torch.optim.SGD, torch.optim.Adam
+    optimizers.add(SGD(sgd_params, lr=args.lr, weight_decay=0.0, momentum=0.9, nesterov=True), args.lr)
     if adam_params:
-        optimizers.add(torch.optim.Adam(adam_params, lr=args.lr_mask), args.lr_mask)
+        optimizers.add(Adam(adam_params, lr=args.lr_mask), args.lr_mask)
+        if hasattr(optimizers.optimizers[-1], 'emit_packed_masks'):
+            optimizers.optimizers[-1].emit_packed_masks(model)
     manager.load_checkpoint(optimizers, resume_from_epoch, resume_folder)
     if world > 1:
         # the all-reduce rides on the pruner call Manager.train makes right after backward()

@@ -163,9 +163,18 @@ def _stage(lib, d, w, p, threshold, prestaged=None):
         d.flags |= _lib.FLAG_W_INTILE
         bits = None
         if p is not None:
-            bits = torch.empty((w.numel() + 31) // 32, dtype=torch.int64, device=w.device)
-            _lib.check(lib.cpgb_pack_mask(_lib.ptr(p), None, w.numel(), threshold, 255, _lib.ptr(bits),
-                                          _lib.stream_ptr()), 'cpgb_pack_mask')
+            # cpg_b200.optim.Adam leaves the packed words of the piggymask it just updated on the parameter
+            # (bits, parameter version at that moment, threshold): consumed once, anything else packs here
+            emitted = getattr(p, '_cpgb_bits', None)
+            if (emitted is not None and emitted[1] == p._version and emitted[2] == float(threshold) and
+                    emitted[0].device == w.device and emitted[0].numel() == (w.numel() + 31) // 32):
+                bits = emitted[0]
+            else:
+                bits = torch.empty((w.numel() + 31) // 32, dtype=torch.int64, device=w.device)
+                _lib.check(lib.cpgb_pack_mask(_lib.ptr(p), None, w.numel(), threshold, 255, _lib.ptr(bits),
+                                              _lib.stream_ptr()), 'cpgb_pack_mask')
+            if emitted is not None:
+                p._cpgb_bits = None
         return bits, _ws(lib.cpgb_workspace_bytes(d) - nbytes, w.device)
     if lib.cpgb_weights_usable_raw(d, 1 if p is not None else 0):
         # linear / 1x1 layer without a piggymask: the weight tensor itself is the operand

@@ -131,6 +131,38 @@ class Adam(_LrMixin, torch.optim.Optimizer):
         self.pack_inference_idx = int(pack_inference_idx)
         self._counters = {}          # (group index, device, chunk) -> int64[2] on the device
 
+    def emit_packed_masks(self, model, threshold=5e-3):
+        """Let step() also write the packed Binarizer bits (cpgb_pack_mask words) of every piggymask of `model` that
+        this optimizer owns and whose layer can mask its weight tiles in shared memory (CPGB_FLAG_W_INTILE: the FC
+        layers): the next forward pass then needs no pack pass.  The words are left on the parameter
+        (``p._cpgb_bits``) together with its version counter; cpg_b200.functional consumes them once and ignores
+        them if anything else touched the piggymask in between.  Returns the number of layers hooked up."""
+        from . import layers as nl
+        lib = _lib.load()
+        mine = {id(p) for g in self.param_groups for p in g['params']}
+        self.pack_threshold = float(threshold)
+        self.pack_inference_idx = 255
+        n = 0
+        for m in model.modules():
+            if not isinstance(m, (nl.SharableConv2d, nl.SharableLinear)):
+                continue
+            p = getattr(m, 'piggymask', None)
+            if p is None or id(p) not in mine or not p.is_cuda or m.info.get('threshold_fn') != 'binarizer':
+                continue
+            if float(m.info.get('threshold', threshold)) != float(threshold):
+                continue
+            w = m.weight
+            if w.dim() == 4:
+                (K, C, R, S), (sh, sw), groups = w.shape, m.stride, m.groups
+                C = C * groups
+            else:
+                (K, C), R, S, sh, sw, groups = w.shape, 1, 1, 1, 1, 1
+            if not lib.cpgb_intile_weight_shape(K, C, R, S, sh, sw, groups):
+                continue
+            self.pack[p] = (torch.zeros((p.numel() + 31) // 32, dtype=torch.int64, device=p.device), None)
+            n += 1
+        return n
+
     def _counter(self, gi, dev, chunk, start):
         key = (gi, str(dev), chunk)
         c = self._counters.get(key)
@@ -179,6 +211,9 @@ class Adam(_LrMixin, torch.optim.Optimizer):
                             N, float(group['lr']), float(b1), float(b2), float(group['eps']), counter.data_ptr(),
                             self._lr_pointer(gi, group), P, T, self.pack_threshold, self.pack_inference_idx,
                             _lib.stream_ptr()), 'cpgb_adam_step')
+                    for it, pk in zip(its, packs):
+                        if pk:      # (words, version of the parameter they describe, threshold)
+                            it[0]._cpgb_bits = (pk[0], it[0]._version, self.pack_threshold)
         return loss
 
     def state_dict(self):

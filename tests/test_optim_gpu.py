@@ -160,3 +160,38 @@ def test_optimizers_reject_what_they_do_not_implement():
     c.grad = torch.zeros(4)
     with pytest.raises(_lib.CpgbError):
         SGD([c], lr=0.1).step()
+
+
+def test_adam_emitted_mask_words_feed_the_in_tile_masked_layer():
+    """cpg_b200.optim.Adam.emit_packed_masks: the FC layer's next forward pass takes the Binarizer bits the Adam kernel
+    wrote (no pack launch), gives the same output bit for bit, and ignores them once anything else touched the
+    piggymask."""
+    import torch.nn as nn
+    import cpg_b200.layers as nl
+    from cpg_b200 import _lib
+    from cpg_b200.optim import Adam
+    lib = _lib.load()
+    torch.manual_seed(0)
+    lin = nl.SharableLinear(512, 1024).to(DEV)
+    lin.piggymask = nn.Parameter((torch.rand(1024, 512) * 0.01).to(DEV))
+    opt = Adam([lin.piggymask], lr=5e-4)
+    assert opt.emit_packed_masks(lin) == 1
+    x = torch.randn(128, 512, device=DEV)
+    lin(x).square().mean().backward()
+    opt.step()
+    assert lin.piggymask._cpgb_bits is not None
+    before = lib.cpgb_launch_count()
+    y1 = lin(x)
+    n1 = lib.cpgb_launch_count() - before
+    assert lin.piggymask._cpgb_bits is None                 # consumed
+    before = lib.cpgb_launch_count()
+    y2 = lin(x)                                             # packs by itself
+    n2 = lib.cpgb_launch_count() - before
+    assert n2 == n1 + 1 and torch.equal(y1, y2)
+    # stale words: a torch op on the piggymask after the optimizer step bumps its version
+    lin(x).square().mean().backward()
+    opt.step()
+    with torch.no_grad():
+        lin.piggymask.mul_(-1.0)                            # every bit flips to 0
+    y3 = lin(x)
+    assert torch.equal(y3, lin.bias.detach().expand_as(y3) if lin.bias is not None else torch.zeros_like(y3))
