@@ -29,6 +29,20 @@ void count_launches(int n);
   } while (0)
 #define CPGB_LAUNCH_OK(what) CPGB_LAUNCH_OK_N(what, 1)
 
+// cudaFuncSetAttribute (dynamic shared memory above 48 KB) is a per-DEVICE setting: a process that drives several GPUs
+// (nn.DataParallel replicas, one thread per device) has to apply it on each of them.  One flag per call site and device.
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool need() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess) d = 0;
+    d &= 63;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+
 // Launch with programmatic dependent launch enabled: the kernel's blocks are scheduled while the previous kernel on
 // the stream drains; every kernel launched through here executes griddepcontrol.wait before its first global access.
 // CPGB_NO_PDL=1 turns the attribute off.

@@ -513,11 +513,11 @@ NcPlan nc_plan(long long rows, int Cs) {
   const int c4 = Cs / 4;
   // experiment knobs: CPGB_BN_TARGET_CHUNKS (channel chunks aimed at), CPGB_BN_CS (largest cluster)
   const char *et = getenv("CPGB_BN_TARGET_CHUNKS"), *ec = getenv("CPGB_BN_CS");
-  const int target = et ? atoi(et) : 16, max_cs = ec ? atoi(ec) : NC_MAX_CLUSTER;
+  const int target = et ? atoi(et) : 32, max_cs = ec ? atoi(ec) : 4;     // measured best for tensors <= 9 MB
   int L = 2;                                             // >= 32 contiguous bytes per pixel row and CTA: whole sectors
   while (L < NC_MAXL && c4 / (L * 2) >= target) L *= 2;  // about `target` channel chunks ...
   p.lanes = L; p.slots = NC_THREADS / L; p.chunks = (c4 + L - 1) / L;
-  int cs = na_sms() / p.chunks;                          // ... times up to 8 row shares: 64-148 CTAs
+  int cs = na_sms() / p.chunks;                          // ... times up to `max_cs` row shares: 64-148 CTAs
   if (cs > max_cs) cs = max_cs;
   if (cs > NC_MAX_CLUSTER) cs = NC_MAX_CLUSTER;
   if (cs < 1) cs = 1;
@@ -556,26 +556,35 @@ __device__ __forceinline__ void nc_block_reduce(NcShared &sh, int L, float4 s, f
   const int wl = threadIdx.x & 31, w = threadIdx.x >> 5;
   if (wl < L) { sh.wred[0][w][wl] = s; sh.wred[1][w][wl] = q; }
   __syncthreads();
-  if (threadIdx.x < L) {
-    double ds[4] = {0, 0, 0, 0}, dq[4] = {0, 0, 0, 0};
-#pragma unroll 4
-    for (int k = 0; k < NC_WARPS; ++k) {
-      const float4 a = sh.wred[0][k][threadIdx.x], b = sh.wred[1][k][threadIdx.x];
-      ds[0] += a.x; ds[1] += a.y; ds[2] += a.z; ds[3] += a.w;
-      dq[0] += b.x; dq[1] += b.y; dq[2] += b.z; dq[3] += b.w;
-    }
-    sh.xch[0][threadIdx.x] = make_float4((float)ds[0], (float)ds[1], (float)ds[2], (float)ds[3]);
-    sh.xch[1][threadIdx.x] = make_float4((float)dq[0], (float)dq[1], (float)dq[2], (float)dq[3]);
+  if (threadIdx.x < 8 * L) {
+    // one thread per (pair member, channel): the warps in ascending order, double precision
+    const int which = threadIdx.x / (4 * L), ch = threadIdx.x % (4 * L);
+    const float *src = reinterpret_cast<const float *>(&sh.wred[which][0][0]) + ch;
+    double d = 0.0;
+#pragma unroll
+    for (int k = 0; k < NC_WARPS; ++k) d += (double)src[k * NC_MAXL * 4];
+    reinterpret_cast<float *>(&sh.xch[which][0])[ch] = (float)d;
   }
 }
-// After the cluster barrier: totals of channel group `l` over the cluster, ranks in ascending order.
-__device__ __forceinline__ void nc_cluster_total(const NcShared &sh, int l, int cs, double ds[4], double dq[4]) {
-  for (int j = 0; j < 4; ++j) { ds[j] = 0.0; dq[j] = 0.0; }
-  for (int r = 0; r < cs; ++r) {
-    const float4 a = nc_ld_peer(&sh.xch[0][l], (uint32_t)r), b = nc_ld_peer(&sh.xch[1][l], (uint32_t)r);
-    ds[0] += a.x; ds[1] += a.y; ds[2] += a.z; ds[3] += a.w;
-    dq[0] += b.x; dq[1] += b.y; dq[2] += b.z; dq[3] += b.w;
+__device__ __forceinline__ float nc_ld_peer_f(const float *p, uint32_t rank) {
+  uint32_t a;
+  asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a) : "r"(nc_smem_u32(p)), "r"(rank));
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+// After the cluster barrier: totals of channel `ch` (0 .. 4 * lanes - 1 of this CTA's chunk) over the cluster, ranks in
+// ascending order.  All loads are issued before the first add.
+__device__ __forceinline__ void nc_cluster_total(const NcShared &sh, int ch, int cs, double &ds, double &dq) {
+  float a[NC_MAX_CLUSTER], b[NC_MAX_CLUSTER];
+#pragma unroll
+  for (int r = 0; r < NC_MAX_CLUSTER; ++r) {
+    a[r] = r < cs ? nc_ld_peer_f(reinterpret_cast<const float *>(&sh.xch[0][0]) + ch, (uint32_t)r) : 0.f;
+    b[r] = r < cs ? nc_ld_peer_f(reinterpret_cast<const float *>(&sh.xch[1][0]) + ch, (uint32_t)r) : 0.f;
   }
+  ds = 0.0; dq = 0.0;
+#pragma unroll
+  for (int r = 0; r < NC_MAX_CLUSTER; ++r) { ds += (double)a[r]; dq += (double)b[r]; }
 }
 
 struct NcFwdArgs {
@@ -613,33 +622,29 @@ bn_fwd_cluster_kernel(const NaGeom g, const PoolGeom pg, const NcFwdArgs p) {
     nc_block_reduce(sh, L, s, q);
     nc_cluster_arrive();
     nc_cluster_wait();
-    if (threadIdx.x < L) {
-      const int cg = blockIdx.y * L + threadIdx.x;        // this thread's channel group
-      float mu[4] = {0, 0, 0, 0}, rs[4] = {0, 0, 0, 0};
-      if (cg * 4 < g.Cs) {
-        double ds[4], dq[4];
+    if (threadIdx.x < 4 * L) {
+      const int c = blockIdx.y * L * 4 + threadIdx.x;       // one thread per channel of this CTA's chunk
+      float mu = 0.f, rs = 0.f;                             // padding lane: zero coefficients, y = 0 there
+      if (c < g.C) {
+        double ds, dq;
         nc_cluster_total(sh, threadIdx.x, p.cs, ds, dq);
-        for (int j = 0; j < 4; ++j) {
-          const int c = cg * 4 + j;
-          if (c >= g.C) continue;                          // padding lane: zero coefficients, y = 0 there
-          const double mean = ds[j] / (double)g.M;
-          double var = dq[j] / (double)g.M - mean * mean;
-          if (var < 0.0) var = 0.0;
-          mu[j] = (float)mean;
-          rs[j] = (float)(1.0 / sqrt(var + (double)p.eps));
-          if (blockIdx.x == 0) {
-            p.save_mean[c] = mu[j];
-            p.save_rstd[c] = rs[j];
-            if (p.running_mean) {
-              const double unbiased = g.M > 1 ? var * (double)g.M / (double)(g.M - 1) : var;
-              p.running_mean[c] = (float)((1.0 - (double)p.momentum) * (double)p.running_mean[c] + (double)p.momentum * mean);
-              p.running_var[c] = (float)((1.0 - (double)p.momentum) * (double)p.running_var[c] + (double)p.momentum * unbiased);
-            }
+        const double mean = ds / (double)g.M;
+        double var = dq / (double)g.M - mean * mean;
+        if (var < 0.0) var = 0.0;
+        mu = (float)mean;
+        rs = (float)(1.0 / sqrt(var + (double)p.eps));
+        if (blockIdx.x == 0) {
+          p.save_mean[c] = mu;
+          p.save_rstd[c] = rs;
+          if (p.running_mean) {
+            const double unbiased = g.M > 1 ? var * (double)g.M / (double)(g.M - 1) : var;
+            p.running_mean[c] = (float)((1.0 - (double)p.momentum) * (double)p.running_mean[c] + (double)p.momentum * mean);
+            p.running_var[c] = (float)((1.0 - (double)p.momentum) * (double)p.running_var[c] + (double)p.momentum * unbiased);
           }
         }
       }
-      sh.coef[2][threadIdx.x] = make_float4(mu[0], mu[1], mu[2], mu[3]);
-      sh.coef[3][threadIdx.x] = make_float4(rs[0], rs[1], rs[2], rs[3]);
+      reinterpret_cast<float *>(&sh.coef[2][0])[threadIdx.x] = mu;
+      reinterpret_cast<float *>(&sh.coef[3][0])[threadIdx.x] = rs;
     }
     if (p.nbt && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *p.nbt += 1;     // nn.BatchNorm2d.forward
     nc_cluster_arrive();                                  // the peers' partials have been read; waited for at the end
@@ -748,26 +753,22 @@ bn_bwd_cluster_kernel(const NaGeom g, const PoolGeom pg, const NcBwdArgs p) {
   nc_block_reduce(sh, L, s, q);
   nc_cluster_arrive();
   nc_cluster_wait();
-  if (threadIdx.x < L) {
-    const int cg = blockIdx.y * L + threadIdx.x;
-    float k1[4] = {0, 0, 0, 0}, k2[4] = {0, 0, 0, 0};
-    if (cg * 4 < g.Cs) {
-      double ds[4], dq[4];
+  if (threadIdx.x < 4 * L) {
+    const int c = blockIdx.y * L * 4 + threadIdx.x;
+    float k1 = 0.f, k2 = 0.f;
+    if (c < g.C) {
+      double ds, dq;
       nc_cluster_total(sh, threadIdx.x, p.cs, ds, dq);
-      for (int j = 0; j < 4; ++j) {
-        const int c = cg * 4 + j;
-        if (c >= g.C) continue;
-        if (blockIdx.x == 0) {
-          if (p.dbeta) p.dbeta[c] = (float)ds[j];
-          if (p.dgamma) p.dgamma[c] = (float)dq[j];
-        }
-        // statistics are constants in evaluation mode: dx = a * g
-        k1[j] = p.training ? (float)(ds[j] / (double)g.M) : 0.f;
-        k2[j] = p.training ? (float)(dq[j] / (double)g.M) : 0.f;
+      if (blockIdx.x == 0) {
+        if (p.dbeta) p.dbeta[c] = (float)ds;
+        if (p.dgamma) p.dgamma[c] = (float)dq;
       }
+      // statistics are constants in evaluation mode: dx = a * g
+      k1 = p.training ? (float)(ds / (double)g.M) : 0.f;
+      k2 = p.training ? (float)(dq / (double)g.M) : 0.f;
     }
-    sh.coef[0][threadIdx.x] = make_float4(k1[0], k1[1], k1[2], k1[3]);
-    sh.coef[1][threadIdx.x] = make_float4(k2[0], k2[1], k2[2], k2[3]);
+    reinterpret_cast<float *>(&sh.coef[0][0])[threadIdx.x] = k1;
+    reinterpret_cast<float *>(&sh.coef[1][0])[threadIdx.x] = k2;
   }
   nc_cluster_arrive();
   __syncthreads();
@@ -807,18 +808,22 @@ bn_bwd_cluster_kernel(const NaGeom g, const PoolGeom pg, const NcBwdArgs p) {
   nc_cluster_wait();
 }
 
-// Opt-in (CPGB_BN_CLUSTER=1; read per call so that the tests compare both paths in one process).  Measured on B200
-// inside CUDA graphs with x left in L2 by a producer (tools/bn_ab.py, gpurun_out/r2_bn_ab*.txt), the single launch
-// LOSES to stats -> finalize -> apply on every VGG16 shape: 58.6 vs 23.6 us forward on 64 channels @ 32x32 (a CTA that
-// owns 8 channels touches 32 of every 256-byte pixel row: 16 L1 wavefronts per warp load, and 64-128 CTAs of 16
-// warps keep too few bytes in flight), 13.7 vs 10.3 us on 256 @ 8x8, 8.6 vs 7.2 us on the 1 MB 512 @ 2x2 tensor (the
-// serial finalize chain of a few threads per CTA costs more than two extra launches at ~2.4 us each under PDL).
-// CPGB_BN_CLUSTER_MB limits it to tensors up to that size.
+// Used for activation tensors up to CPGB_BN_CLUSTER_MB (default 5 MB: the 4x4 and 2x2 maps of VGG16, 6 of its 13
+// batch-norm layers; inside the training step the 8 MB tensors do better on three kernels: 1.499 ms per step with a
+// 5 MB limit, 1.517 with 9 MB, 1.541 without the cluster kernels); CPGB_BN_CLUSTER=0 turns it off (both read per call, so that the tests compare the two paths in
+// one process).  Measured on B200 inside CUDA graphs with x left in L2 by a producer (tools/bn_ab.py,
+// gpurun_out/r2_bn_ab3.txt; clusters of 4, ~32 channel chunks), single launch vs stats -> finalize -> apply, forward /
+// backward in us: 512 ch @ 2x2 (1 MB) 5.3 / 7.3 vs 7.2 / 9.7; 512 @ 4x4 (4 MB) 7.2 / 9.5 vs 9.2 / 17.1; 256 @ 8x8 (8 MB)
+// 11.4 / 14.7 vs 10.7 / 18.4 -- these layers are launch-latency bound, two launches fewer is what pays.  Above that the
+// three-kernel path wins and keeps the work: 128 @ 16x16 (17 MB) 30.6 / 42.8 vs 13.1 / 27.8, 64 @ 32x32 (33 MB) 58.6 /
+// 99.5 vs 23.6 / 42.3: a CTA that owns 8 of 64 channels touches 32 bytes of every 256-byte pixel row (16 L1
+// wavefronts per warp load), and 64-128 CTAs of 16 warps keep too few bytes in flight.  (A first version that left the
+// finalize arithmetic to `lanes` threads per CTA lost everywhere: the serial chain cost more than two launches.)
 bool nc_enabled(long long M, int Cs) {
   const char *e = getenv("CPGB_BN_CLUSTER");
-  if (!(e && atoi(e) != 0)) return false;
+  if (e && atoi(e) == 0) return false;
   const char *t = getenv("CPGB_BN_CLUSTER_MB");
-  const double limit_mb = t ? atof(t) : 1e9;
+  const double limit_mb = t ? atof(t) : 5.0;
   return (double)M * Cs * 4.0 / 1e6 <= limit_mb;
 }
 

@@ -839,11 +839,9 @@ int cpgb_prune_select_sampled(int32_t nlayers, const float *const *w, uint8_t *c
   unsigned int *cand_key = samples + (size_t)nlayers * SEL_SAMPLE;
   unsigned int *cand_idx = cand_key + (size_t)nlayers * SEL_CAP;
   CPGB_CUDA_OK(cudaMemsetAsync(stt, 0, (size_t)nlayers * sizeof(SelState), st));
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.need())
     CPGB_CUDA_OK(cudaFuncSetAttribute(sel_bracket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SEL_SAMPLE * 4));
-    attr_done = true;
-  }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -689,7 +689,8 @@ int stem_wgrad_fused(const cpgb_conv_desc &d, const float *x, const float *dy, c
   const size_t smem = dense && ring_bytes > red_bytes ? ring_bytes : red_bytes;
   if (dense && pair_ok(d, x) && d.Q % 2 == 0) {
     static int cap_pair = 0;
-    if (!cap_pair) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.need()) {
       CPGB_CUDA_OK(cudaFuncSetAttribute(stem_wgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_WG_SMEM));
       cap_pair = resident_blocks(stem_wgrad_pair_kernel, STEM_WG_THREADS, smem);
     }
@@ -706,7 +707,8 @@ int stem_wgrad_fused(const cpgb_conv_desc &d, const float *x, const float *dy, c
   }
   const WgradKern kern = dense ? kWgradTma[vec][k4] : kWgrad[vec][k4];
   static int cap[2][2][2] = {};
-  if (!cap[dense][vec][k4]) {
+  static PerDeviceOnce attr_once[2][2][2];
+  if (attr_once[dense][vec][k4].need()) {
     CPGB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_WG_SMEM));
     int c = resident_blocks(kern, STEM_WG_THREADS, smem);
     cap[dense][vec][k4] = c < nb_max ? c : nb_max;

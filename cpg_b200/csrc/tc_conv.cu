@@ -1268,12 +1268,10 @@ template <int BN, bool B_MN, bool XF = false>
 static int launch_conv_gemm(const CUtensorMap &ta, const CUtensorMap &tb, ConvGemmParams &p, int ntiles_n,
                             int splits, cudaStream_t st, bool cluster = false) {
   using Cfg = ConvGemmCfg<BN, B_MN>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.need())
     CPGB_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<BN, B_MN, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       Cfg::smem_bytes(Cfg::NSTAGE_SOLO)));
-    attr_done = true;
-  }
   dim3 grid(p.tq * p.tp * p.tn, ntiles_n, splits);
   const long long ctas = (long long)grid.x * grid.y * grid.z;
   p.nstage = ctas > num_sms() ? Cfg::NSTAGE_PAIR : Cfg::NSTAGE_SOLO;   // solo only when no SM gets two CTAs anyway
@@ -1412,12 +1410,10 @@ static int launch_wgrad(const CUtensorMap &tdy, const CUtensorMap &tx, const Fus
   using Cfg = WgradCfg<BN, TG>;
   int smem_bytes = HALO ? p.h_nstage * p.h_stage_bytes + 1024 + TAIL_BYTES : Cfg::SMEM_BYTES;
   if (p.fused) smem_bytes = p.f_region_bytes + 128 * 128 * 4 * (p.piggy ? 2 : 1) + 128 * 128 + 1024 + TAIL_BYTES;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.need())
     CPGB_CUDA_OK(cudaFuncSetAttribute(wgrad_gemm_kernel<BN, TG, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (HALO || (TG == 1 && BN == 128)) ? 227 * 1024 : Cfg::SMEM_BYTES));
-    attr_done = true;
-  }
   CPGB_CUDA_OK(launch_pdl(wgrad_gemm_kernel<BN, TG, HALO>, grid, dim3(192), (size_t)smem_bytes, st, tdy, tx, fm.w, fm.p,
                           fm.t, p));
   CPGB_LAUNCH_OK("wgrad_gemm_kernel");
@@ -1555,11 +1551,10 @@ static int implicit_wgrad_fused(const cpgb_conv_desc &d, const float *x, const f
       sgroups = std::min(std::min(256 / items, pl.splits / 4), 8);
     if (sgroups > 1) sh += (size_t)sgroups * items * 16 + 48;
     if (sh <= 96 * 1024 && (cc * RS) % 4 == 0) {
-      static bool attr_done = false;
-      if (!attr_done) {
+      static PerDeviceOnce attr_once;
+      if (attr_once.need()) {
         CPGB_CUDA_OK(cudaFuncSetAttribute(wgrad_epilogue_krsc_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         CPGB_CUDA_OK(cudaFuncSetAttribute(wgrad_epilogue_krsc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        attr_done = true;
       }
       const dim3 egrid(cdiv_i(d.K, kb), cdiv_i(d.C, cc));
       if (RS == 9)
@@ -1580,11 +1575,10 @@ static int implicit_wgrad_fused(const cpgb_conv_desc &d, const float *x, const f
     while (kb < 8 && (long long)(d.K / (2 * kb)) * cdiv_i(d.C, cc) >= 2LL * num_sms() && 2 * kb * cc * RS <= 4608) kb *= 2;
     const size_t sh = (size_t)kb * RS * (cc + 1) * sizeof(float);
     if (sh <= 96 * 1024) {
-      static bool attr_done2 = false;
-      if (!attr_done2) {
+      static PerDeviceOnce attr_once2;
+      if (attr_once2.need()) {
         CPGB_CUDA_OK(cudaFuncSetAttribute(wgrad_epilogue_krsc_kernel<9, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         CPGB_CUDA_OK(cudaFuncSetAttribute(wgrad_epilogue_krsc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        attr_done2 = true;
       }
       const dim3 egrid(cdiv_i(d.K, kb), cdiv_i(d.C, cc));
       if (RS == 9)

@@ -147,11 +147,12 @@ def _prepare_operand(lib, t, exact, needed):
     return t, False
 
 
-def _stage(lib, d, w, p, threshold, prestaged=None):
+def _stage(lib, d, w, p, threshold, prestaged=None, owner=None):
     """Build the tensor-core weight operand (masked, TF32, [K][RS][Cp]) for descriptor d, or
     None when d takes the CUDA-core path (which evaluates the mask while loading tiles).
     `prestaged`: operand already built for this forward pass by the model-level batched staging
-    (cpg_b200.prune.SparsePruner pre-forward hook).
+    (cpg_b200.prune.SparsePruner pre-forward hook).  `owner`: the piggymask Parameter object `p` was detached from
+    (cpg_b200.optim.Adam leaves the packed mask words there).
     Returns (staged, scratch): scratch is the split-K workspace of the fprop/dgrad call."""
     nbytes = lib.cpgb_staged_weight_bytes(d)
     if nbytes == 0:
@@ -165,8 +166,9 @@ def _stage(lib, d, w, p, threshold, prestaged=None):
         if p is not None:
             # cpg_b200.optim.Adam leaves the packed words of the piggymask it just updated on the parameter
             # (bits, parameter version at that moment, threshold): consumed once, anything else packs here
-            emitted = getattr(p, '_cpgb_bits', None)
-            if (emitted is not None and emitted[1] == p._version and emitted[2] == float(threshold) and
+            holder = owner if owner is not None else p
+            emitted = getattr(holder, '_cpgb_bits', None)
+            if (emitted is not None and emitted[1] == holder._version and emitted[2] == float(threshold) and
                     emitted[0].device == w.device and emitted[0].numel() == (w.numel() + 31) // 32):
                 bits = emitted[0]
             else:
@@ -174,7 +176,7 @@ def _stage(lib, d, w, p, threshold, prestaged=None):
                 _lib.check(lib.cpgb_pack_mask(_lib.ptr(p), None, w.numel(), threshold, 255, _lib.ptr(bits),
                                               _lib.stream_ptr()), 'cpgb_pack_mask')
             if emitted is not None:
-                p._cpgb_bits = None
+                holder._cpgb_bits = None
         return bits, _ws(lib.cpgb_workspace_bytes(d) - nbytes, w.device)
     if lib.cpgb_weights_usable_raw(d, 1 if p is not None else 0):
         # linear / 1x1 layer without a piggymask: the weight tensor itself is the operand
@@ -396,7 +398,7 @@ class MaskedConv2dFn(torch.autograd.Function):
         x, x_exact = _prepare_operand(lib, x, bool(x_exact), bool(uses_tc))
         d.flags = _lib.FLAG_X_TF32 if x_exact else 0
         with torch.cuda.device(x.device):
-            staged, ws = _stage(lib, d, w, p, threshold, prestaged)
+            staged, ws = _stage(lib, d, w, p, threshold, prestaged, owner=piggymask)
             _lib.check(lib.cpgb_conv2d_fprop(d, _lib.ptr(x), _lib.ptr(w), _lib.ptr(p), _lib.ptr(b),
                                              _lib.ptr(y), threshold, _lib.ptr(staged), _lib.ptr(ws),
                                              ws.numel() if ws is not None else 0,
@@ -481,7 +483,7 @@ class MaskedLinearFn(torch.autograd.Function):
         x2, x_exact = _prepare_operand(lib, x2, bool(x_exact), bool(uses_tc))
         d.flags = _lib.FLAG_X_TF32 if x_exact else 0
         with torch.cuda.device(x.device):
-            staged, ws = _stage(lib, d, w, p, threshold, prestaged)
+            staged, ws = _stage(lib, d, w, p, threshold, prestaged, owner=piggymask)
             _lib.check(lib.cpgb_conv2d_fprop(d, _lib.ptr(x2), _lib.ptr(w), _lib.ptr(p), _lib.ptr(b), _lib.ptr(y),
                                              threshold, _lib.ptr(staged), _lib.ptr(ws),
                                              ws.numel() if ws is not None else 0, _lib.stream_ptr()),

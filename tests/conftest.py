@@ -34,7 +34,9 @@ def golden():
 
 @pytest.fixture(params=['cluster', 'three_kernels'])
 def bn_path(request, monkeypatch):
-    """Both implementations behind cpgb_bn_relu_fwd / _bwd: the stats -> finalize -> apply sequence (default) and the
-    single-launch cluster kernels (CPGB_BN_CLUSTER=1; the library reads the variable per call)."""
+    """Both implementations behind cpgb_bn_relu_fwd / _bwd: the single-launch cluster kernels (default for tensors up
+    to 9 MB; forced for every size here) and the stats -> finalize -> apply sequence (CPGB_BN_CLUSTER=0).  The library
+    reads the variables per call."""
     monkeypatch.setenv('CPGB_BN_CLUSTER', '1' if request.param == 'cluster' else '0')
+    monkeypatch.setenv('CPGB_BN_CLUSTER_MB', '1e9')
     return request.param

@@ -15,5 +15,5 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_two_rank_nccl_gradients_equal_single_gpu():
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr',
            '127.0.0.1', '--master-port', '29641', os.path.join(ROOT, 'tests', 'ddp_nccl_worker.py')]
-    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and 'DDP_NCCL_OK' in r.stdout, (r.stdout[-3000:], r.stderr[-3000:])
