@@ -17,7 +17,7 @@ EXPORTS = [
     'cpgb_version', 'cpgb_last_error', 'cpgb_set_path', 'cpgb_get_path', 'cpgb_launch_count', 'cpgb_linear_desc',
     'cpgb_workspace_bytes', 'cpgb_staged_weight_bytes', 'cpgb_stage_weights', 'cpgb_staged_weight_bytes_for',
     'cpgb_stage_weights_batched', 'cpgb_weights_usable_raw', 'cpgb_weights_usable_raw_for', 'cpgb_binarize', 'cpgb_conv2d_fprop', 'cpgb_conv2d_dgrad',
-    'cpgb_conv2d_wgrad_fused', 'cpgb_grad_epilogue', 'cpgb_prune_workspace_bytes', 'cpgb_prune_select',
+    'cpgb_conv2d_wgrad_fused', 'cpgb_conv2d_wgrad_fused_async', 'cpgb_grad_epilogue', 'cpgb_prune_workspace_bytes', 'cpgb_prune_select',
     'cpgb_prune_batched_workspace_bytes', 'cpgb_prune_select_batched', 'cpgb_prune_sampled_workspace_bytes',
     'cpgb_prune_select_sampled',
     'cpgb_apply_mask', 'cpgb_make_finetuning_mask', 'cpgb_mask_stats', 'cpgb_mask_stats_batched', 'cpgb_merge_grads',
@@ -78,6 +78,8 @@ def load():
         'cpgb_conv2d_dgrad': (ctypes.c_int, [dp, vp, vp, vp, vp, f32, vp, vp, sz, vp]),
         'cpgb_conv2d_wgrad_fused': (ctypes.c_int, [dp, vp, vp, vp, vp, vp, i32, f32, i32, vp, vp, vp, f32,
                                                   vp, sz, vp]),
+        'cpgb_conv2d_wgrad_fused_async': (ctypes.c_int, [dp, vp, vp, vp, vp, vp, i32, f32, i32, vp, vp, vp, f32,
+                                                        vp, sz, vp, vp]),
         'cpgb_grad_epilogue': (ctypes.c_int, [vp, vp, vp, vp, i64, i32, f32, i32, vp]),
         'cpgb_prune_workspace_bytes': (sz, []),
         'cpgb_prune_select': (ctypes.c_int, [vp, vp, i64, i32, dbl, vp, vp, sz, vp]),

@@ -260,6 +260,14 @@ int cpgb_conv2d_wgrad_fused(const cpgb_conv_desc *d, const float *x, const float
                             const float *piggy, const uint8_t *tmask, int32_t cur, float weight_decay,
                             int32_t mode, float *dW, float *dP, float *dbias, float thr, void *ws,
                             size_t ws_bytes, void *stream) {
+  return cpgb_conv2d_wgrad_fused_async(d, x, dy, w, piggy, tmask, cur, weight_decay, mode, dW, dP, dbias, thr, ws,
+                                       ws_bytes, stream, stream);
+}
+
+int cpgb_conv2d_wgrad_fused_async(const cpgb_conv_desc *d, const float *x, const float *dy, const float *w,
+                                  const float *piggy, const uint8_t *tmask, int32_t cur, float weight_decay,
+                                  int32_t mode, float *dW, float *dP, float *dbias, float thr, void *ws,
+                                  size_t ws_bytes, void *stream, void *epilogue_stream) {
   int rc = validate_desc(d);
   if (rc) return rc;
   if ((d->N != 0 && (!x || !dy)) || !w || !dW) { set_error("cpgb_conv2d_wgrad_fused: null pointer"); return CPGB_EINVAL; }
@@ -289,7 +297,8 @@ int cpgb_conv2d_wgrad_fused(const cpgb_conv_desc *d, const float *x, const float
       return rc;
   } else if (use_tc) {
     // tensor-core wgrad: split-K partial sums in ws, summed inside the fused epilogue
-    if ((rc = tc_wgrad_fused(*d, x, dy, w, piggy, tmask, cur, weight_decay, mode, thr, dW, dP, ws, ws_bytes, st)))
+    if ((rc = tc_wgrad_fused(*d, x, dy, w, piggy, tmask, cur, weight_decay, mode, thr, dW, dP, ws, ws_bytes, st,
+                             (cudaStream_t)epilogue_stream)))
       return rc;
   } else {
     int splits = 1;

@@ -180,9 +180,10 @@ int tc_fprop_intile(const cpgb_conv_desc &d, const float *x, const float *w, con
                     void *part, size_t part_bytes, cudaStream_t st);
 int tc_dgrad_intile(const cpgb_conv_desc &d, const float *dy, const float *w, const void *bits, float *dx, void *part,
                     size_t part_bytes, cudaStream_t st);
-// wgrad + fused epilogue (dW, dP); partial sums live in ws
+// wgrad + fused epilogue (dW, dP); partial sums live in ws.  est: stream of the epilogue kernels (st, or a second
+// stream the caller joins before dW / dP are consumed)
 int tc_wgrad_fused(const cpgb_conv_desc &d, const float *x, const float *dy, const float *w, const float *piggy,
                    const uint8_t *tmask, int cur, float wd, int mode, float thr, float *dW, float *dP, void *ws,
-                   size_t ws_bytes, cudaStream_t st);
+                   size_t ws_bytes, cudaStream_t st, cudaStream_t est);
 
 }  // namespace cpgb

@@ -1430,9 +1430,27 @@ static int make_act_map5(CUtensorMap *m, const float *base, int C, int W, int H,
   return make_map(m, base, 5, dims, str, box, true);
 }
 
+// Fork of the epilogue stream: everything queued on `est` from here on runs after what `st` holds now.  One event per
+// device, re-recorded per call (a wait keeps the state the event had when the wait was queued).
+static int fork_epilogue_stream(cudaStream_t st, cudaStream_t est) {
+  static cudaEvent_t ev[64] = {};
+  int dev = 0;
+  CPGB_CUDA_OK(cudaGetDevice(&dev));
+  dev &= 63;
+  if (!ev[dev]) CPGB_CUDA_OK(cudaEventCreateWithFlags(&ev[dev], cudaEventDisableTiming));
+  CPGB_CUDA_OK(cudaEventRecord(ev[dev], st));
+  CPGB_CUDA_OK(cudaStreamWaitEvent(est, ev[dev], 0));
+  return CPGB_OK;
+}
+
+// est: stream of the epilogue kernels (== st: everything in order on one stream).  A different stream lets the
+// latency-bound epilogue of layer l run under the GEMM of layer l - 1 that follows on `st`; the caller joins `est`
+// before anything consumes dW / dP.
 static int implicit_wgrad_fused(const cpgb_conv_desc &d, const float *x, const float *dy, const float *w,
                                 const float *piggy, const uint8_t *tmask, int cur, float wd, int mode, float thr,
-                                float *dW, float *dP, void *ws, size_t ws_bytes, cudaStream_t st) {
+                                float *dW, float *dP, void *ws, size_t ws_bytes, cudaStream_t st,
+                                cudaStream_t est_in = nullptr, bool est_given = false) {
+  cudaStream_t est = est_given ? est_in : st;
   if (!aligned16p(x) || !aligned16p(dy) || !aligned16p(ws)) {
     set_error("tcgen05 path needs 16-byte aligned tensors"); return CPGB_EINVAL;
   }
@@ -1526,10 +1544,11 @@ static int implicit_wgrad_fused(const cpgb_conv_desc &d, const float *x, const f
     rc = pl.BN == 128 ? launch_wgrad<128, 1, false>(tdy, tx, fm, p, grid, st) : launch_wgrad<64, 1, false>(tdy, tx, fm, p, grid, st);
   }
   if (rc || fused) return rc;
+  if (est != st && (rc = fork_epilogue_stream(st, est))) return rc;
   if (RS == 1 && vec_ok && d.C % 4 == 0) {
     const long long n4 = (long long)d.K * d.C / 4;
     int egrid = (int)std::min<long long>((n4 + 255) / 256, (long long)num_sms() * 8);
-    CPGB_CUDA_OK(launch_pdl(wgrad_epilogue_flat_kernel, dim3(egrid), dim3(256), 0, st,
+    CPGB_CUDA_OK(launch_pdl(wgrad_epilogue_flat_kernel, dim3(egrid), dim3(256), 0, est,
                             reinterpret_cast<const float4 *>(p.gpart), pl.splits, n4, reinterpret_cast<const float4 *>(w),
                             reinterpret_cast<const float4 *>(piggy), reinterpret_cast<const uchar4 *>(tmask), cur, wd,
                             mode, thr, reinterpret_cast<float4 *>(dW), reinterpret_cast<float4 *>(dP)));
@@ -1558,10 +1577,10 @@ static int implicit_wgrad_fused(const cpgb_conv_desc &d, const float *x, const f
       }
       const dim3 egrid(cdiv_i(d.K, kb), cdiv_i(d.C, cc));
       if (RS == 9)
-        CPGB_CUDA_OK(launch_pdl(wgrad_epilogue_krsc_kernel<9>, egrid, dim3(256), sh, st, (const float *)p.gpart,
+        CPGB_CUDA_OK(launch_pdl(wgrad_epilogue_krsc_kernel<9>, egrid, dim3(256), sh, est, (const float *)p.gpart,
                                 pl.splits, d.K, d.C, p.Cg, RS, kb, cc, sgroups, w, piggy, tmask, cur, wd, mode, thr, dW, dP));
       else
-        CPGB_CUDA_OK(launch_pdl(wgrad_epilogue_krsc_kernel<0>, egrid, dim3(256), sh, st, (const float *)p.gpart,
+        CPGB_CUDA_OK(launch_pdl(wgrad_epilogue_krsc_kernel<0>, egrid, dim3(256), sh, est, (const float *)p.gpart,
                                 pl.splits, d.K, d.C, p.Cg, RS, kb, cc, sgroups, w, piggy, tmask, cur, wd, mode, thr, dW, dP));
       CPGB_LAUNCH_OK("wgrad_epilogue_krsc");
       return CPGB_OK;
@@ -1582,10 +1601,10 @@ static int implicit_wgrad_fused(const cpgb_conv_desc &d, const float *x, const f
       }
       const dim3 egrid(cdiv_i(d.K, kb), cdiv_i(d.C, cc));
       if (RS == 9)
-        CPGB_CUDA_OK(launch_pdl(wgrad_epilogue_krsc_kernel<9, true>, egrid, dim3(256), sh, st, (const float *)p.gpart,
+        CPGB_CUDA_OK(launch_pdl(wgrad_epilogue_krsc_kernel<9, true>, egrid, dim3(256), sh, est, (const float *)p.gpart,
                                 pl.splits, d.K, d.C, p.Cg, RS, kb, cc, 1, w, piggy, tmask, cur, wd, mode, thr, dW, dP));
       else
-        CPGB_CUDA_OK(launch_pdl(wgrad_epilogue_krsc_kernel<0, true>, egrid, dim3(256), sh, st, (const float *)p.gpart,
+        CPGB_CUDA_OK(launch_pdl(wgrad_epilogue_krsc_kernel<0, true>, egrid, dim3(256), sh, est, (const float *)p.gpart,
                                 pl.splits, d.K, d.C, p.Cg, RS, kb, cc, 1, w, piggy, tmask, cur, wd, mode, thr, dW, dP));
       CPGB_LAUNCH_OK("wgrad_epilogue_krsc_ragged");
       return CPGB_OK;
@@ -1593,7 +1612,7 @@ static int implicit_wgrad_fused(const cpgb_conv_desc &d, const float *x, const f
   }
   const long long n = (long long)d.K * d.C * RS;
   int egrid = (int)std::min<long long>((n + 255) / 256, (long long)num_sms() * 8);
-  wgrad_epilogue_krsc_scalar_kernel<<<egrid, 256, 0, st>>>(p.gpart, pl.splits, d.K, d.C, p.Cg, RS, w, piggy, tmask, cur,
+  wgrad_epilogue_krsc_scalar_kernel<<<egrid, 256, 0, est>>>(p.gpart, pl.splits, d.K, d.C, p.Cg, RS, w, piggy, tmask, cur,
                                                           wd, mode, thr, dW, dP);
   CPGB_LAUNCH_OK("wgrad_epilogue_krsc_scalar");
   return CPGB_OK;
@@ -2049,10 +2068,10 @@ bool tc_intile_weight_shape(int K, int C, int R, int S, int stride_h, int stride
 
 int tc_wgrad_fused(const cpgb_conv_desc &d, const float *x, const float *dy, const float *w, const float *piggy,
                    const uint8_t *tmask, int cur, float wd, int mode, float thr, float *dW, float *dP, void *ws,
-                   size_t ws_bytes, cudaStream_t st) {
+                   size_t ws_bytes, cudaStream_t st, cudaStream_t est) {
   return tc_mode(d, 2) == TC_XCOL
              ? xcol_wgrad_fused(d, x, dy, w, piggy, tmask, cur, wd, mode, thr, dW, dP, ws, ws_bytes, st)
-             : implicit_wgrad_fused(d, x, dy, w, piggy, tmask, cur, wd, mode, thr, dW, dP, ws, ws_bytes, st);
+             : implicit_wgrad_fused(d, x, dy, w, piggy, tmask, cur, wd, mode, thr, dW, dP, ws, ws_bytes, st, est, true);
 }
 
 }  // namespace cpgb

@@ -22,7 +22,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
-from .functional import pending_side_stream, _side_stream
+from .functional import join_epilogue_stream, pending_side_stream, _side_stream
 
 BIG = 1 << 18            # elements; other (non-sharable) tensors at least this large get their own overlapped all-reduce
 BUCKET_BYTES = 48 << 20  # a bucket is closed once it holds this much
@@ -133,6 +133,7 @@ class GradAllReducer:
             # after every wgrad issued so far: those on the side stream by stream order, those that joined the main
             # stream immediately through this wait
             side.wait_stream(torch.cuda.current_stream())
+            join_epilogue_stream(device, side)           # ... and after their epilogues (third stream)
             with torch.cuda.stream(side):
                 work = dist.all_reduce(buf, op=self.op, group=self.group, async_op=True)
         self.pending.append((buf, work))
@@ -149,6 +150,7 @@ class GradAllReducer:
             # nn.Linear / nn.Embedding parameter, or a layer whose wgrad joined immediately) while an earlier
             # layer's wgrad is still deferred
             side.wait_stream(torch.cuda.current_stream(p.grad.device))
+            join_epilogue_stream(p.grad.device, side)
             with torch.cuda.stream(side):
                 work = dist.all_reduce(p.grad, op=self.op, group=self.group, async_op=True)
         else:

@@ -7,6 +7,8 @@ produces dX, dW, dP (straight-through: dP = g * W, models/layers.py:21-23) and d
 the pruner's weight-decay / grad-mask step (utils/prune.py:195-211) optionally folded into
 the same epilogue.
 """
+import os
+
 import torch
 from torch.autograd.function import once_differentiable
 
@@ -192,6 +194,11 @@ def _stage(lib, d, w, p, threshold, prestaged=None, owner=None):
 
 
 _SIDE_STREAMS = {}
+_EPI_STREAMS = {}
+# the fused wgrad epilogues (sum of the split partial sums + weight decay + masks) of a deferred backward pass run
+# on a third stream, under the wgrad GEMM of the next layer (cpgb_conv2d_wgrad_fused_async); CPGB_EPILOGUE_STREAM=0
+# keeps them on the wgrad stream
+EPILOGUE_STREAM = os.environ.get('CPGB_EPILOGUE_STREAM', '1') != '0'
 OVERLAP_BACKWARD = True   # run wgrad on a side stream (it only reads x and dy; nothing on the main chain needs it)
 DEFER_JOIN = True         # join the side stream once, at the end of the backward pass, instead of per layer
 _PENDING = {}             # device index -> (graph task id, tensors the side stream may still be reading)
@@ -211,6 +218,24 @@ def _side_stream(device):
     return st
 
 
+def _epilogue_stream(device):
+    key = _dev_index(device)
+    st = _EPI_STREAMS.get(key)
+    if st is None:
+        st = torch.cuda.Stream(device=device)
+        _EPI_STREAMS[key] = st
+    return st
+
+
+def join_epilogue_stream(device, into=None):
+    """Make `into` (default: the wgrad side stream) wait for the epilogue kernels queued so far -- what has to happen
+    before a collective launched from that stream may read the gradients."""
+    key = _dev_index(device)
+    est = _EPI_STREAMS.get(key)
+    if est is not None and key in _PENDING:
+        (into if into is not None else _side_stream(device)).wait_stream(est)
+
+
 def pending_side_stream(device):
     """The side stream if weight-gradient kernels of the running backward pass are still queued on it
     (their outputs must not be consumed on another stream before `join_side_stream`), else None."""
@@ -227,6 +252,8 @@ def join_side_stream(device=None):
         if key in _PENDING:
             with torch.cuda.device(key):
                 torch.cuda.current_stream().wait_stream(_SIDE_STREAMS[key])
+                if key in _EPI_STREAMS:
+                    torch.cuda.current_stream().wait_stream(_EPI_STREAMS[key])
             del _PENDING[key]
 
 
@@ -305,12 +332,15 @@ def _backward_kernels(lib, ctx, d, x, dy, w, p, threshold, staged, need_dx, need
             if fork:
                 wstream = _side_stream(device)
                 wstream.wait_stream(main)
-            _lib.check(lib.cpgb_conv2d_wgrad_fused(
+            # deferred join: the epilogue goes to its own stream and overlaps the next layer's wgrad GEMM; both
+            # streams are joined by the end-of-backward callback
+            estream = _epilogue_stream(device) if (defer and fork and EPILOGUE_STREAM) else wstream
+            _lib.check(lib.cpgb_conv2d_wgrad_fused_async(
                 d, _lib.ptr(x), _lib.ptr(dy), _lib.ptr(w), _lib.ptr(p),
                 _lib.ptr(fuse.tmask) if fuse is not None else None,
                 fuse.cur if fuse is not None else 0, wd, (mode | _lib.GRAD_MERGED) if merged else mode,
                 _lib.ptr(dW), None if merged else _lib.ptr(dP), _lib.ptr(db) if dy_raw is None else None, threshold,
-                _lib.ptr(ws_w), ws_w.numel(), wstream.cuda_stream), 'cpgb_conv2d_wgrad_fused')
+                _lib.ptr(ws_w), ws_w.numel(), wstream.cuda_stream, estream.cuda_stream), 'cpgb_conv2d_wgrad_fused')
             if db is not None and dy_raw is not None:
                 # the bias gradient is a plain fp32 sum: take it from the caller's dy, not from the TF32-rounded copy
                 _lib.check(lib.cpgb_conv2d_bias_grad(d, _lib.ptr(dy_raw), _lib.ptr(db), wstream.cuda_stream),

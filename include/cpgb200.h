@@ -172,6 +172,16 @@ int cpgb_conv2d_wgrad_fused(const cpgb_conv_desc *d, const float *x, const float
                             const float *piggy, const uint8_t *tmask, int32_t cur, float weight_decay,
                             int32_t mode, float *dW, float *dP, float *dbias, float thr, void *ws,
                             size_t ws_bytes, void *stream);
+/* The same with the fused epilogue (the sum of the split partial sums + K6-K8) queued on `epilogue_stream` behind an
+ * event recorded on `stream` after the GEMM: the latency-bound epilogue of one layer then runs under the GEMM of the
+ * next layer queued on `stream`.  dW / dP are complete once `epilogue_stream` has drained: the caller joins it before
+ * the optimizer / all-reduce reads them (cpg_b200/functional.py joins once, at the end of the backward pass).  Kernels
+ * that finish the gradient themselves (stem, im2col tier, CUDA-core path) ignore epilogue_stream; dbias is written on
+ * `stream`.  epilogue_stream == stream is cpgb_conv2d_wgrad_fused. */
+int cpgb_conv2d_wgrad_fused_async(const cpgb_conv_desc *d, const float *x, const float *dy, const float *w,
+                                  const float *piggy, const uint8_t *tmask, int32_t cur, float weight_decay,
+                                  int32_t mode, float *dW, float *dP, float *dbias, float thr, void *ws,
+                                  size_t ws_bytes, void *stream, void *epilogue_stream);
 
 /* dbias[k] = sum over (n, p, q) of dy -- the bias gradient of F.conv2d / F.linear (models/layers.py:108,194) on its
  * own, in fp32.  cpgb_conv2d_wgrad_fused computes it from the dy it is given; a caller that hands that function a
