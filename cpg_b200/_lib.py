@@ -22,8 +22,9 @@ EXPORTS = [
     'cpgb_prune_select_sampled',
     'cpgb_apply_mask', 'cpgb_make_finetuning_mask', 'cpgb_mask_stats', 'cpgb_mask_stats_batched', 'cpgb_merge_grads',
     'cpgb_split_merged_grad', 'cpgb_bn_workspace_bytes', 'cpgb_bn_relu_fwd', 'cpgb_bn_relu_bwd',
-    'cpgb_uses_tensor_cores', 'cpgb_round_tf32', 'cpgb_conv2d_bias_grad', 'cpgb_pack_mask', 'cpgb_intile_eligible',
-    'cpgb_intile_weight_shape', 'cpgb_sgd_nesterov_step', 'cpgb_adam_step',
+    'cpgb_uses_tensor_cores', 'cpgb_round_tf32', 'cpgb_conv2d_bias_grad', 'cpgb_conv2d_bias_grad_ws', 'cpgb_pack_mask', 'cpgb_intile_eligible',
+    'cpgb_intile_weight_shape', 'cpgb_sgd_nesterov_step', 'cpgb_adam_step', 'cpgb_prelu_workspace_bytes',
+    'cpgb_prelu_fwd', 'cpgb_prelu_bwd',
 ]
 
 
@@ -63,6 +64,7 @@ def load():
         'cpgb_uses_tensor_cores': (ctypes.c_int, [dp, i32]),
         'cpgb_round_tf32': (ctypes.c_int, [vp, vp, i64, vp]),
         'cpgb_conv2d_bias_grad': (ctypes.c_int, [dp, vp, vp, vp]),
+        'cpgb_conv2d_bias_grad_ws': (ctypes.c_int, [dp, vp, vp, vp, sz, vp]),
         'cpgb_pack_mask': (ctypes.c_int, [vp, vp, i64, f32, i32, vp, vp]),
         'cpgb_intile_eligible': (ctypes.c_int, [dp]),
         'cpgb_intile_weight_shape': (ctypes.c_int, [i32] * 7),
@@ -101,6 +103,9 @@ def load():
                                                    i32, vp, vp]),
         'cpgb_merge_grads': (ctypes.c_int, [vp, vp, vp, i64, vp]),
         'cpgb_split_merged_grad': (ctypes.c_int, [vp, vp, i64, i32, vp, vp, vp]),
+        'cpgb_prelu_workspace_bytes': (sz, [i64, i32]),
+        'cpgb_prelu_fwd': (ctypes.c_int, [vp, i64, i32, i32, vp, i32, vp, vp]),
+        'cpgb_prelu_bwd': (ctypes.c_int, [vp, vp, i64, i32, i32, vp, i32, vp, vp, vp, sz, vp]),
         'cpgb_bn_workspace_bytes': (sz, [i64, i32]),
         'cpgb_bn_relu_fwd': (ctypes.c_int, [vp, i64, i32, i32, vp, vp, vp, vp, vp, i32, f32, f32, i32, i32, i32, i32, vp, vp,
                                             vp, vp, sz, vp]),

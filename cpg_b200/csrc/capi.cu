@@ -76,6 +76,10 @@ void cpgb_linear_desc(cpgb_conv_desc *d, int32_t M, int32_t I, int32_t O) {
   d->ys[0] = O; d->ys[1] = 1; d->ys[2] = O; d->ys[3] = O;
 }
 
+static size_t bias_scratch_bytes(const cpgb_conv_desc *d) {
+  return (bias_grad_scratch_bytes(make_geom(*d)) + 255) & ~(size_t)255;
+}
+
 size_t cpgb_workspace_bytes(const cpgb_conv_desc *d) {
   if (!d || d->groups <= 0) return 0;
   // raw weight-gradient partial sums of the CUDA-core wgrad: one tensor per split of the pixel reduction
@@ -84,7 +88,9 @@ size_t cpgb_workspace_bytes(const cpgb_conv_desc *d) {
   size_t stem = stem_workspace_bytes(*d);                      // per-block partial sums of the stem wgrad
   g_bytes = (g_bytes + 255) & ~(size_t)255;
   if (stem > g_bytes) g_bytes = stem;
-  return g_bytes > tc ? g_bytes : tc;
+  // the last bias_scratch_bytes(d) bytes are the partial column sums of the bias gradient (their own region: the wgrad
+  // epilogue may still be reading the partial sums in front of it on another stream)
+  return (((g_bytes > tc ? g_bytes : tc) + 255) & ~(size_t)255) + bias_scratch_bytes(d);
 }
 
 size_t cpgb_staged_weight_bytes(const cpgb_conv_desc *d) {
@@ -249,11 +255,19 @@ int cpgb_conv2d_dgrad(const cpgb_conv_desc *d, const float *dy, const float *w, 
 }
 
 int cpgb_conv2d_bias_grad(const cpgb_conv_desc *d, const float *dy, float *dbias, void *stream) {
+  return cpgb_conv2d_bias_grad_ws(d, dy, dbias, nullptr, 0, stream);
+}
+
+int cpgb_conv2d_bias_grad_ws(const cpgb_conv_desc *d, const float *dy, float *dbias, void *ws, size_t ws_bytes,
+                             void *stream) {
   int rc = validate_desc(d);
   if (rc) return rc;
   if (!dbias || (d->N != 0 && !dy)) { set_error("cpgb_conv2d_bias_grad: null pointer"); return CPGB_EINVAL; }
   if (d->N == 0) { CPGB_CUDA_OK(cudaMemsetAsync(dbias, 0, d->K * sizeof(float), (cudaStream_t)stream)); return CPGB_OK; }
-  return bias_grad(make_geom(*d), dy, dbias, (cudaStream_t)stream);
+  // ws is a cpgb_workspace_bytes(d) buffer: the bias partial sums live in its last bias_scratch_bytes(d) bytes
+  const size_t tail = bias_scratch_bytes(d), total = cpgb_workspace_bytes(d);
+  void *scratch = (ws && tail && ws_bytes >= total) ? reinterpret_cast<char *>(ws) + (total - tail) : nullptr;
+  return bias_grad(make_geom(*d), dy, dbias, scratch, scratch ? tail : 0, (cudaStream_t)stream);
 }
 
 int cpgb_conv2d_wgrad_fused(const cpgb_conv_desc *d, const float *x, const float *dy, const float *w,
@@ -312,7 +326,11 @@ int cpgb_conv2d_wgrad_fused_async(const cpgb_conv_desc *d, const float *x, const
   }
   if (dbias) {
     if (d->N == 0) CPGB_CUDA_OK(cudaMemsetAsync(dbias, 0, d->K * sizeof(float), st));
-    else if ((rc = bias_grad(g, dy, dbias, st))) return rc;
+    else {
+      const size_t tail = bias_scratch_bytes(d), total = cpgb_workspace_bytes(d);
+      void *scratch = tail ? reinterpret_cast<char *>(ws) + (total - tail) : nullptr;      // ws_bytes >= total was checked
+      if ((rc = bias_grad(g, dy, dbias, scratch, tail, st))) return rc;
+    }
   }
   return CPGB_OK;
 }

@@ -135,7 +135,10 @@ int simt_dgrad(const Geom &g, const float *dy, const float *w, const float *pigg
 // raw weight-gradient partial sums gbuf[splits][K*Cg*R*S] (fp32, overwritten; fixed reduction order)
 int simt_wgrad_splits(const Geom &g);
 int simt_wgrad_raw(const Geom &g, const float *x, const float *dy, float *gbuf, int *splits_out, cudaStream_t st);
-int bias_grad(const Geom &g, const float *dy, float *dbias, cudaStream_t st);
+// scratch: bias_grad_scratch_bytes(g) bytes (0: none needed) for the two-phase NHWC column sum; without it (or for other
+// layouts) a slow one-block-per-channel kernel runs
+size_t bias_grad_scratch_bytes(const Geom &g);
+int bias_grad(const Geom &g, const float *dy, float *dbias, void *scratch, size_t scratch_bytes, cudaStream_t st);
 
 // out = rna_tf32(in), elementwise (elementwise.cu)
 int round_tf32(const float *in, float *out, long long n, cudaStream_t st);

@@ -827,6 +827,64 @@ bool nc_enabled(long long M, int Cs) {
   return (double)M * Cs * 4.0 / 1e6 <= limit_mb;
 }
 
+// ---- PReLU (models/spherenet.py:204-249: every SharableConv2d of SphereNet-20 feeds nn.PReLU(channels)) ----
+// y = x > 0 ? x : alpha[c] * x;  dx = x > 0 ? dy : alpha[c] * dy;  dalpha[c] = sum over pixels of (x > 0 ? 0 : x * dy)
+// (torch's prelu_kernel / prelu_backward_kernel).  Same streaming layout as the batch-norm kernels.
+__global__ void __launch_bounds__(NA_THREADS)
+prelu_fwd_kernel(const NaGeom g, const float *__restrict__ x, const float *__restrict__ alpha, int tf32,
+                 float *__restrict__ y) {
+  pdl_wait();
+  const int lane = threadIdx.x % g.lanes, slot = threadIdx.x / g.lanes;
+  const int c4 = blockIdx.y * g.lanes + lane;
+  if (slot >= g.slots || c4 * 4 >= g.Cs) return;
+  const float4 a = ldp4(alpha, c4, g.C, 0.f);
+  const float4 *xp = reinterpret_cast<const float4 *>(x) + c4;
+  float4 *yp = reinterpret_cast<float4 *>(y) + c4;
+  const long long stride = (long long)gridDim.x * g.slots, cq = g.Cs / 4;
+#pragma unroll 4
+  for (long long r = (long long)blockIdx.x * g.slots + slot; r < g.M; r += stride) {
+    const float4 v = pad0(__ldg(xp + r * cq), c4, g.C);
+    yp[r * cq] = na_out(make_float4(v.x > 0.f ? v.x : a.x * v.x, v.y > 0.f ? v.y : a.y * v.y,
+                                    v.z > 0.f ? v.z : a.z * v.z, v.w > 0.f ? v.w : a.w * v.w), tf32);
+  }
+}
+
+__global__ void __launch_bounds__(NA_STATS_THREADS)
+prelu_bwd_kernel(const NaGeom g, const float *__restrict__ x, const float *__restrict__ dy,
+                 const float *__restrict__ alpha, int tf32, float *__restrict__ dx, float *__restrict__ part) {
+  pdl_wait();
+  const int lane = threadIdx.x % g.lanes, slot = threadIdx.x / g.lanes;
+  const int c4 = blockIdx.y * g.lanes + lane;
+  const bool active = slot < g.slots && c4 * 4 < g.Cs;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (active) {
+    const float4 a = ldp4(alpha, c4, g.C, 0.f);
+    const float4 *xp = reinterpret_cast<const float4 *>(x) + c4;
+    const float4 *dp = reinterpret_cast<const float4 *>(dy) + c4;
+    float4 *op = reinterpret_cast<float4 *>(dx) + c4;
+    const long long stride = (long long)gridDim.x * g.slots, cq = g.Cs / 4;
+#pragma unroll 4
+    for (long long r = (long long)blockIdx.x * g.slots + slot; r < g.M; r += stride) {
+      const float4 v = pad0(__ldg(xp + r * cq), c4, g.C), d = pad0(__ldg(dp + r * cq), c4, g.C);
+      op[r * cq] = na_out(make_float4(v.x > 0.f ? d.x : a.x * d.x, v.y > 0.f ? d.y : a.y * d.y,
+                                      v.z > 0.f ? d.z : a.z * d.z, v.w > 0.f ? d.w : a.w * d.w), tf32);
+      s.x += v.x > 0.f ? 0.f : v.x * d.x; s.y += v.y > 0.f ? 0.f : v.y * d.y;
+      s.z += v.z > 0.f ? 0.f : v.z * d.z; s.w += v.w > 0.f ? 0.f : v.w * d.w;
+    }
+  }
+  block_reduce_pairs(g, s, make_float4(0.f, 0.f, 0.f, 0.f), lane, slot, c4, active, part);
+}
+
+__global__ void __launch_bounds__(256)
+prelu_bwd_finalize_kernel(const float *__restrict__ part, int nblocks, int C, int Cs, float *__restrict__ dalpha) {
+  pdl_wait();
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (c >= C) return;
+  double s, q;
+  sum_partials(part, nblocks, Cs, c, s, q);
+  if ((threadIdx.x & 31) == 0) dalpha[c] = (float)s;
+}
+
 bool na_args_ok(const void *x, long long M, int C, int Cs) {
   return M > 0 && C > 0 && Cs >= C && Cs % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
 }
@@ -986,6 +1044,48 @@ int cpgb_bn_relu_bwd(const float *x, const float *dy, int64_t M, int32_t C, int3
                                                                                 relu, tf32_out, dx));
   }
   CPGB_LAUNCH_OK("bn_bwd_apply");
+  return CPGB_OK;
+}
+
+size_t cpgb_prelu_workspace_bytes(int64_t M, int32_t C) {
+  if (M <= 0 || C <= 0) return 0;
+  return na_ws_bytes(M, (C + 3) & ~3);
+}
+
+int cpgb_prelu_fwd(const float *x, int64_t M, int32_t C, int32_t ldc, const float *alpha, int32_t tf32_out, float *y,
+                   void *stream) {
+  const int Cs = na_stride(C, ldc);
+  if (!na_args_ok(x, M, C, Cs) || !y || !alpha || (reinterpret_cast<uintptr_t>(y) & 15)) {
+    set_error("cpgb_prelu_fwd: needs NHWC fp32 with a pixel stride that is a multiple of 4, 16-byte aligned x / y, and alpha[C]");
+    return CPGB_EINVAL;
+  }
+  NaGeom g = na_geom(M, C, Cs);
+  CPGB_CUDA_OK(launch_dependent(prelu_fwd_kernel, dim3(na_blocks(g, 8), g.cchunks), dim3(NA_THREADS), 0,
+                                (cudaStream_t)stream, g, x, alpha, tf32_out, y));
+  CPGB_LAUNCH_OK("prelu_fwd");
+  return CPGB_OK;
+}
+
+int cpgb_prelu_bwd(const float *x, const float *dy, int64_t M, int32_t C, int32_t ldc, const float *alpha,
+                   int32_t tf32_out, float *dx, float *dalpha, void *ws, size_t ws_bytes, void *stream) {
+  const int Cs = na_stride(C, ldc);
+  if (!na_args_ok(x, M, C, Cs) || !dy || !dx || !alpha || !dalpha || (reinterpret_cast<uintptr_t>(dy) & 15) ||
+      (reinterpret_cast<uintptr_t>(dx) & 15)) {
+    set_error("cpgb_prelu_bwd: needs NHWC fp32 with a pixel stride that is a multiple of 4 and 16-byte aligned tensors");
+    return CPGB_EINVAL;
+  }
+  if (!ws || ws_bytes < na_ws_bytes(M, Cs) || (reinterpret_cast<uintptr_t>(ws) & 15)) {
+    set_error("cpgb_prelu_bwd: workspace %zu < %zu", ws_bytes, na_ws_bytes(M, Cs)); return CPGB_EWORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const NaGeom gs = na_geom(M, C, Cs, NA_STATS_THREADS);
+  const int nb = na_blocks(gs, NA_STATS_PER_SM);
+  float *part = reinterpret_cast<float *>(ws) + 4 * Cs;
+  CPGB_CUDA_OK(launch_dependent(prelu_bwd_kernel, dim3(nb, gs.cchunks), dim3(NA_STATS_THREADS), 0, st, gs, x, dy, alpha,
+                                tf32_out, dx, part));
+  CPGB_LAUNCH_OK("prelu_bwd");
+  CPGB_CUDA_OK(launch_dependent(prelu_bwd_finalize_kernel, dim3((C + 7) / 8), dim3(256), 0, st, part, nb, C, Cs, dalpha));
+  CPGB_LAUNCH_OK("prelu_bwd_finalize");
   return CPGB_OK;
 }
 

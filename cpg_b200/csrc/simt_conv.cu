@@ -225,7 +225,100 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(Geom g, const float *__r
   }
 }
 
-int bias_grad(const Geom &g, const float *dy, float *dbias, cudaStream_t st) {
+// NHWC activations (channel stride 1, one uniform pixel stride): dbias = column sums of the [M pixels][ps] matrix.
+// The kernel above gives every channel its own block and walks the pixels with a stride of `ps` floats -- 4 useful
+// bytes per 32-byte sector; on SphereNet-20 (20 biased convolutions, up to 51 MB of dy each) it was 37 % of the device
+// time of a step.  Two deterministic phases instead: fat blocks stream whole pixel rows (a thread owns one float4 of
+// channels), per-block partial sums go to scratch, one thread per channel adds them in block order.
+constexpr int BG_THREADS = 512;
+struct BgGeom { long long M; int K, ps, lanes, slots, cchunks; };
+
+static bool bg_geom(const Geom &g, const float *dy, BgGeom *out) {
+  if (g.ys1 != 1 || (reinterpret_cast<uintptr_t>(dy) & 15)) return false;
+  long long ps;
+  if (g.P == 1 && g.Q == 1) ps = g.N > 1 ? g.ys0 : (long long)((g.K + 3) & ~3);
+  else {
+    ps = g.Q > 1 ? g.ys3 : g.ys2;
+    if (g.Q > 1 && g.P > 1 && g.ys2 != (long long)g.Q * ps) return false;
+    if (g.N > 1 && g.ys0 != (long long)g.P * g.Q * ps) return false;
+  }
+  if (ps < g.K || ps % 4 != 0 || ps > (1 << 20)) return false;
+  BgGeom b;
+  b.M = (long long)g.N * g.P * g.Q; b.K = g.K; b.ps = (int)ps;
+  const int c4 = (g.K + 3) / 4;
+  b.lanes = c4 < BG_THREADS ? c4 : BG_THREADS;
+  b.slots = BG_THREADS / b.lanes;
+  b.cchunks = (c4 + b.lanes - 1) / b.lanes;
+  *out = b;
+  return true;
+}
+static int bg_blocks(const BgGeom &b) {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  long long want = (b.M + b.slots - 1) / b.slots, cap = (long long)sms * 2 / b.cchunks;
+  if (cap < 1) cap = 1;
+  if (want < 1) want = 1;
+  return (int)(want < cap ? want : cap);
+}
+size_t bias_grad_scratch_bytes(const Geom &g) {
+  BgGeom b;
+  // alignment is a property of the pointer; the size only depends on the geometry
+  if (!bg_geom(g, nullptr, &b)) return 0;
+  return (size_t)bg_blocks(b) * b.cchunks * b.lanes * 4 * sizeof(float) + 256;
+}
+
+__global__ void __launch_bounds__(BG_THREADS)
+bias_grad_nhwc_kernel(const BgGeom b, const float *__restrict__ dy, float *__restrict__ part) {
+  __shared__ float4 red[BG_THREADS];
+  const int lane = threadIdx.x % b.lanes, slot = threadIdx.x / b.lanes;
+  const int c4 = blockIdx.y * b.lanes + lane;
+  const bool active = slot < b.slots && c4 * 4 < b.K;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (active) {
+    const float4 *p = reinterpret_cast<const float4 *>(dy) + c4;
+    const long long stride = (long long)gridDim.x * b.slots, cq = b.ps / 4;
+    const int c = c4 * 4;
+#pragma unroll 4
+    for (long long r = (long long)blockIdx.x * b.slots + slot; r < b.M; r += stride) {
+      const float4 v = __ldg(p + r * cq);
+      // lanes beyond K inside the last group are padding of the activation layout: not part of any channel
+      s.x += v.x; s.y += c + 1 < b.K ? v.y : 0.f; s.z += c + 2 < b.K ? v.z : 0.f; s.w += c + 3 < b.K ? v.w : 0.f;
+    }
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  if (slot == 0 && active) {
+    for (int k = 1; k < b.slots; ++k) {
+      const float4 a = red[k * b.lanes + lane];
+      s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+    }
+    const long long cols = (long long)b.cchunks * b.lanes * 4;
+    *reinterpret_cast<float4 *>(part + (long long)blockIdx.x * cols + c4 * 4) = s;
+  }
+}
+__global__ void __launch_bounds__(256)
+bias_grad_finish_kernel(const float *__restrict__ part, int nblk, int K, long long cols, float *__restrict__ dbias) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  double s = 0.0;
+  for (int b = 0; b < nblk; ++b) s += (double)__ldg(part + (long long)b * cols + k);
+  dbias[k] = (float)s;
+}
+
+int bias_grad(const Geom &g, const float *dy, float *dbias, void *scratch, size_t scratch_bytes, cudaStream_t st) {
+  BgGeom b;
+  if (scratch && (reinterpret_cast<uintptr_t>(scratch) & 15) == 0 && bg_geom(g, dy, &b)) {
+    const int nblk = bg_blocks(b);
+    const long long cols = (long long)b.cchunks * b.lanes * 4;
+    if ((size_t)nblk * cols * sizeof(float) <= scratch_bytes) {
+      float *part = reinterpret_cast<float *>(scratch);
+      bias_grad_nhwc_kernel<<<dim3(nblk, b.cchunks), BG_THREADS, 0, st>>>(b, dy, part);
+      CPGB_LAUNCH_OK("bias_grad_nhwc");
+      bias_grad_finish_kernel<<<(g.K + 255) / 256, 256, 0, st>>>(part, nblk, g.K, cols, dbias);
+      CPGB_LAUNCH_OK("bias_grad_finish");
+      return CPGB_OK;
+    }
+  }
   bias_grad_kernel<<<g.K, 256, 0, st>>>(g, dy, dbias);
   CPGB_LAUNCH_OK("bias_grad");
   return CPGB_OK;

@@ -151,6 +151,87 @@ class FusedBatchNormReLU2d(nn.BatchNorm2d):
         return F.max_pool2d(y, 2, 2) if (self.pool and not pool) else y
 
 
+class _PReLUFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, tf32_out):
+        lib = _lib.load()
+        x = to_nhwc_aligned(x)
+        ldc = nhwc_pixel_stride(x)
+        N, C, H, W = x.shape
+        y = empty_nhwc((N, C, H, W), x.device, ldc)
+        a = weight.detach().contiguous()
+        with torch.cuda.device(x.device):
+            _lib.check(lib.cpgb_prelu_fwd(_lib.ptr(x), N * H * W, C, ldc, _lib.ptr(a), 1 if tf32_out else 0, _lib.ptr(y),
+                                          _lib.stream_ptr()), 'cpgb_prelu_fwd')
+        ctx.save_for_backward(x, a)
+        ctx.cpgb_tf32_out = bool(tf32_out)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x, a = ctx.saved_tensors
+        ldc = nhwc_pixel_stride(x)
+        if nhwc_pixel_stride(dy) != ldc:
+            t = empty_nhwc(dy.shape, dy.device, ldc)
+            t.copy_(dy)
+            dy = t
+        N, C, H, W = x.shape
+        M = N * H * W
+        dx = empty_like_padded(x)
+        da = torch.empty(C, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            ws = torch.empty(lib.cpgb_prelu_workspace_bytes(M, ldc), dtype=torch.uint8, device=x.device)
+            _lib.check(lib.cpgb_prelu_bwd(_lib.ptr(x), _lib.ptr(dy), M, C, ldc, _lib.ptr(a),
+                                          1 if ctx.cpgb_tf32_out else 0, _lib.ptr(dx), _lib.ptr(da), _lib.ptr(ws),
+                                          ws.numel(), _lib.stream_ptr()), 'cpgb_prelu_bwd')
+        if ctx.cpgb_tf32_out:
+            mark_tf32(dx)
+        return dx, da, None
+
+
+class FusedPReLU(nn.PReLU):
+    """``nn.PReLU(num_parameters=C)`` on NHWC activations (models/spherenet.py:204-249: the consumer of every masked
+    convolution of SphereNet-20) as one streaming kernel per direction; the outputs can be stored TF32-rounded
+    (`tf32_out`) so that the tcgen05 convolutions on either side skip their rounding pass.  Same parameter
+    (``weight``), same ``state_dict`` key; anything but a CUDA fp32 4-D input with one slope per channel goes through
+    ``nn.PReLU.forward``."""
+
+    def __init__(self, num_parameters=1, init=0.25, tf32_out=False, device=None, dtype=None):
+        super().__init__(num_parameters, init, device=device, dtype=dtype)
+        self.tf32_out = bool(tf32_out)
+
+    @classmethod
+    def from_prelu(cls, m, tf32_out=False):
+        new = cls(m.num_parameters, tf32_out=tf32_out, device=torch.device('meta'))
+        new._parameters['weight'] = m._parameters['weight']
+        new.training = m.training
+        return new
+
+    def forward(self, x):
+        w = self.weight
+        if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.numel() > 0 and w.device == x.device and
+                w.dtype == torch.float32 and w.numel() == x.shape[1]):
+            return super().forward(x)
+        y = _PReLUFn.apply(x, w, self.tf32_out)
+        if self.tf32_out:
+            mark_tf32(y)
+        return y
+
+
+def fuse_prelu(model, tf32_out=True):
+    """Swap every per-channel ``nn.PReLU`` of `model` for a ``FusedPReLU`` sharing its parameter (module names and
+    ``state_dict`` keys unchanged).  Returns the number of modules converted."""
+    n = 0
+    for parent in list(model.modules()):
+        for name, m in list(parent._modules.items()):
+            if type(m) is nn.PReLU and m.num_parameters > 1:
+                parent._modules[name] = FusedPReLU.from_prelu(m, tf32_out=tf32_out)
+                n += 1
+    return n
+
+
 def fuse_bn_relu(model, pool=True, tf32_out=True):
     """Swap every ``nn.BatchNorm2d`` of `model` for a ``FusedBatchNormReLU2d`` sharing its tensors; inside
     ``nn.Sequential`` containers a directly following ``nn.ReLU`` is folded in and replaced by

@@ -187,6 +187,11 @@ int cpgb_conv2d_wgrad_fused_async(const cpgb_conv_desc *d, const float *x, const
  * own, in fp32.  cpgb_conv2d_wgrad_fused computes it from the dy it is given; a caller that hands that function a
  * TF32-rounded copy of dy (CPGB_FLAG_DY_TF32) passes dbias = NULL there and calls this with the unrounded tensor. */
 int cpgb_conv2d_bias_grad(const cpgb_conv_desc *d, const float *dy, float *dbias, void *stream);
+/* The same with scratch: ws = a cpgb_workspace_bytes(d) buffer (the one handed to cpgb_conv2d_wgrad_fused will do: the
+ * partial column sums use a region of their own at its end).  NHWC dy is then summed by row-streaming blocks in two
+ * deterministic phases instead of one strided walk per channel. */
+int cpgb_conv2d_bias_grad_ws(const cpgb_conv_desc *d, const float *dy, float *dbias, void *ws, size_t ws_bytes,
+                             void *stream);
 
 /* a6 standalone, in place on existing gradients: utils/prune.py:195-211.
  * mode is CPGB_GRAD_FINETUNE or CPGB_GRAD_PRUNE; dW / dP may each be NULL
@@ -308,6 +313,17 @@ int cpgb_bn_relu_bwd(const float *x, const float *dy, int64_t M, int32_t C, int3
                      const float *beta, const float *mean, const float *rstd, int32_t training, int32_t relu,
                      int32_t pool_h, int32_t pool_w, int32_t tf32_out, float *dx, float *dgamma, float *dbeta, void *ws,
                      size_t ws_bytes, void *stream);
+
+/* SURVEY 8(f) N4, SphereNet-20: every masked convolution feeds nn.PReLU(channels) (models/spherenet.py:204-249).
+ * NHWC fp32 activations as [M][C] with pixel stride ldc (0 = dense), alpha[C]:
+ *   y = x > 0 ? x : alpha[c] * x;   dx = x > 0 ? dy : alpha[c] * dy;   dalpha[c] = sum_pixels (x > 0 ? 0 : x * dy)
+ * (torch.nn.functional.prelu and its backward, deterministic partial sums).  tf32_out as in cpgb_bn_relu_fwd: the
+ * outputs feed the tcgen05 convolutions without a rounding pass.  ws: cpgb_prelu_workspace_bytes(M, C). */
+size_t cpgb_prelu_workspace_bytes(int64_t M, int32_t C);
+int cpgb_prelu_fwd(const float *x, int64_t M, int32_t C, int32_t ldc, const float *alpha, int32_t tf32_out, float *y,
+                   void *stream);
+int cpgb_prelu_bwd(const float *x, const float *dy, int64_t M, int32_t C, int32_t ldc, const float *alpha,
+                   int32_t tf32_out, float *dx, float *dalpha, void *ws, size_t ws_bytes, void *stream);
 
 #ifdef __cplusplus
 }

@@ -863,3 +863,80 @@ def test_gradually_prune_two_pass_equals_four_pass(monkeypatch):
     for k in res['1'][1]:
         assert torch.equal(res['1'][1][k], res['0'][1][k]), k
         assert int((res['1'][1][k] == 0).sum()) > 0
+
+
+# ---------------------------------------------------------------------------------------------
+# PReLU kernels (SphereNet-20) against nn.PReLU on the same GPU
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('shape', [(64, 64, 56, 56), (8, 512, 7, 7), (4, 78, 9, 5), (2, 156, 6, 6)])
+def test_fused_prelu_vs_torch(shape):
+    from cpg_b200.functional import empty_nhwc
+    from cpg_b200.fused_norm import FusedPReLU, fuse_prelu
+    N, C, H, W = shape
+    torch.manual_seed(C + H)
+    ref = nn.PReLU(C).to(DEV)
+    with torch.no_grad():
+        ref.weight.uniform_(-0.3, 0.6)
+    holder = nn.Sequential(nn.PReLU(C).to(DEV))
+    holder[0].load_state_dict(ref.state_dict())
+    assert fuse_prelu(holder, tf32_out=False) == 1 and isinstance(holder[0], FusedPReLU)
+    assert list(holder.state_dict().keys()) == ['0.weight']
+    ours = holder[0]
+    xv = torch.randn(N, C, H, W, device=DEV)
+    xv[0, :, 0, 0] = 0.0                                  # x == 0 takes the alpha branch in torch
+    xp = empty_nhwc(shape, DEV)
+    xp._base.fill_(float('nan')) if xp._base is not None else None
+    xp.copy_(xv)
+    xp.requires_grad_(True)
+    xr = xv.clone().requires_grad_(True)
+    lib = _lib.load()
+    before = lib.cpgb_launch_count()
+    y = ours(xp)
+    assert lib.cpgb_launch_count() - before == 1
+    yr = ref(xr)
+    assert torch.equal(y.contiguous(), yr.contiguous())   # one multiply per element: bit-identical
+    g = torch.randn_like(yr)
+    gp = empty_nhwc(shape, DEV)
+    gp.copy_(g)
+    y.backward(gp)
+    yr.backward(g)
+    assert torch.equal(xp.grad.contiguous(), xr.grad.contiguous())
+    assert rel(ours.weight.grad, ref.weight.grad) <= 2e-5
+    # TF32-rounded outputs: within 2^-11 of the exact ones, and tagged for the convolution that follows
+    from cpg_b200.functional import is_tf32
+    ours.tf32_out = True
+    y2 = ours(xv.contiguous(memory_format=torch.channels_last))
+    assert is_tf32(y2) and rel(y2, yr) <= 2 ** -11
+
+
+@pytest.mark.parametrize('shape', [(64, 64, 56, 56), (8, 78, 9, 7), (128, 4096, 1, 1), (3, 512, 1, 5), (1, 8, 4, 4)])
+def test_bias_grad_two_phase_nhwc(shape):
+    """dbias = sum over (n, p, q) of dy: the row-streaming two-phase kernel (scratch at the end of the layer's
+    workspace) against a float64 sum, for dense / padded NHWC activations and linear layers; deterministic."""
+    from cpg_b200.functional import empty_nhwc
+    lib = _lib.load()
+    N, K, P, Q = shape
+    torch.manual_seed(K + P)
+    dyv = torch.randn(N, K, P, Q, device=DEV)
+    dy = empty_nhwc(shape, DEV)
+    if dy._base is not None:
+        dy._base.fill_(1e30)                       # pad lanes must not leak into any channel
+    dy.copy_(dyv)
+    x = torch.zeros(N, 4, P, Q, device=DEV).contiguous(memory_format=torch.channels_last)
+    w = torch.zeros(K, 4, 1, 1, device=DEV)
+    d = _lib.conv_desc(x.shape, x.stride(), w.shape, dy.shape, dy.stride(), (1, 1), (0, 0), (1, 1), 1)
+    ws = torch.empty(max(lib.cpgb_workspace_bytes(d), 256), dtype=torch.uint8, device=DEV)
+    want = dyv.double().sum((0, 2, 3))
+    outs = []
+    for rep in range(2):
+        db = torch.full((K,), float('nan'), device=DEV)
+        before = lib.cpgb_launch_count()
+        _lib.check(lib.cpgb_conv2d_bias_grad_ws(d, _lib.ptr(dy), _lib.ptr(db), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+                   'bias_grad_ws')
+        assert lib.cpgb_launch_count() - before == 2          # the two-phase path ran
+        assert rel(db.double(), want) <= 2e-6
+        outs.append(db)
+    assert torch.equal(outs[0], outs[1])
+    db = torch.full((K,), float('nan'), device=DEV)
+    _lib.check(lib.cpgb_conv2d_bias_grad(d, _lib.ptr(dy), _lib.ptr(db), _lib.stream_ptr()), 'bias_grad')   # no scratch
+    assert rel(db.double(), want) <= 2e-5
