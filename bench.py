@@ -866,17 +866,22 @@ def main():
         achieved = flops[dom] / (tot[dom] * 1e-3) / 1e12
         kname = {'fprop': 'conv_gemm_kernel<BN,false>', 'dgrad': 'conv_gemm_kernel<BN,true>',
                  'wgrad': 'wgrad_gemm_kernel<BN,TG,HALO> + wgrad epilogue'}[dom]
-        traffic = None
+        traffic, traffic_file = None, 'profiles/r2_dram_traffic.json'
         try:   # DRAM bytes of the same launches from an ncu capture (profiles/dram_traffic_from_ncu.py)
-            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'r1_dram_traffic.json')))[dom]['dram_bytes']
+            for fn in ('r2_dram_traffic.json', 'r1_dram_traffic.json'):
+                path = os.path.join(ROOT, 'profiles', fn)
+                if os.path.exists(path):
+                    traffic = json.load(open(path))[dom]['dram_bytes']
+                    traffic_file = 'profiles/' + fn
+                    break
         except Exception:
             pass
         line['roofline'] = {
             'bound': 'tensor', 'kernel': f'{kname}: masked implicit-GEMM {dom}, the 15 sharable layers of one step',
             'achieved': achieved, 'peak': tf32_peak, 'unit': 'TFLOP/s', 'frac': achieved / tf32_peak,
             'traffic': traffic,
-            'traffic_note': 'dram__bytes_read+write summed over the 15 launches of this pass (ncu, cold caches; '
-                            'profiles/r1_dram_traffic.json); the pass is tensor/shared-memory bound, not HBM bound',
+            'traffic_note': 'dram__bytes_read+write summed over the launches of this pass for the 15 layers (ncu, cold '
+                            'caches; %s); the pass is tensor/shared-memory bound, not HBM bound' % traffic_file,
             'peak_source': ('MEASURED_PEAKS.json bf16_tflops (burst) / 2' if peaks.get('bf16_tflops') else
                             'fallback 1590 / 2 (B200_PROFILING.md)') + ': tcgen05 kind::tf32 issues at half the '
                            'kind::f16 rate (tools/mma_rate.py); cuBLAS TF32 8192^3 measured in this run: %.1f TF/s'

@@ -255,7 +255,8 @@ static bool bg_geom(const Geom &g, const float *dy, BgGeom *out) {
 static int bg_blocks(const BgGeom &b) {
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  long long want = (b.M + b.slots - 1) / b.slots, cap = (long long)sms * 2 / b.cchunks;
+  // at least 8 pixel rows per thread: few partial sums for short matrices (the FC layers: 128 rows)
+  long long want = (b.M + 8LL * b.slots - 1) / (8LL * b.slots), cap = (long long)sms * 2 / b.cchunks;
   if (cap < 1) cap = 1;
   if (want < 1) want = 1;
   return (int)(want < cap ? want : cap);
@@ -296,13 +297,30 @@ bias_grad_nhwc_kernel(const BgGeom b, const float *__restrict__ dy, float *__res
     *reinterpret_cast<float4 *>(part + (long long)blockIdx.x * cols + c4 * 4) = s;
   }
 }
+// 32 channels per block, 8 thread groups: group j adds the partials of blocks j, j + 8, ... (four loads in flight),
+// the groups are then combined in order -- fixed summation order, double precision
 __global__ void __launch_bounds__(256)
 bias_grad_finish_kernel(const float *__restrict__ part, int nblk, int K, long long cols, float *__restrict__ dbias) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= K) return;
+  __shared__ double red[8][32];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int k = blockIdx.x * 32 + lane;
   double s = 0.0;
-  for (int b = 0; b < nblk; ++b) s += (double)__ldg(part + (long long)b * cols + k);
-  dbias[k] = (float)s;
+  if (k < K) {
+    const float *p = part + k;
+    int b = grp;
+    for (; b + 24 < nblk; b += 32) {
+      const float v0 = __ldg(p + (long long)b * cols), v1 = __ldg(p + (long long)(b + 8) * cols);
+      const float v2 = __ldg(p + (long long)(b + 16) * cols), v3 = __ldg(p + (long long)(b + 24) * cols);
+      s += (double)v0; s += (double)v1; s += (double)v2; s += (double)v3;
+    }
+    for (; b < nblk; b += 8) s += (double)__ldg(p + (long long)b * cols);
+  }
+  red[grp][lane] = s;
+  __syncthreads();
+  if (grp == 0 && k < K) {
+    for (int j = 1; j < 8; ++j) s += red[j][lane];
+    dbias[k] = (float)s;
+  }
 }
 
 int bias_grad(const Geom &g, const float *dy, float *dbias, void *scratch, size_t scratch_bytes, cudaStream_t st) {
@@ -314,7 +332,7 @@ int bias_grad(const Geom &g, const float *dy, float *dbias, void *scratch, size_
       float *part = reinterpret_cast<float *>(scratch);
       bias_grad_nhwc_kernel<<<dim3(nblk, b.cchunks), BG_THREADS, 0, st>>>(b, dy, part);
       CPGB_LAUNCH_OK("bias_grad_nhwc");
-      bias_grad_finish_kernel<<<(g.K + 255) / 256, 256, 0, st>>>(part, nblk, g.K, cols, dbias);
+      bias_grad_finish_kernel<<<(g.K + 31) / 32, 256, 0, st>>>(part, nblk, g.K, cols, dbias);
       CPGB_LAUNCH_OK("bias_grad_finish");
       return CPGB_OK;
     }

@@ -1,12 +1,13 @@
 #!/usr/bin/env python
 """DRAM traffic per pass out of
   ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --csv \
-      --log-file traffic.csv python -m tests.prof_ops 1 vgg
+      --log-file traffic.csv python -m tools.prof_ops 1 vgg
 (the 15 sharable layers of VGG16-BN-cifar at batch 128, each pass launched once, no piggymask).
 usage: python profiles/dram_traffic_from_ncu.py traffic.csv > profiles/r1_dram_traffic.json"""
 import collections
 import csv
 import json
+import re
 import sys
 
 lines = [l for l in open(sys.argv[1]) if not l.startswith('==')]
@@ -27,7 +28,8 @@ for k in kern.values():
     elif 'stem_fprop' in name:
         pas = last = 'fprop'
     elif 'conv_gemm_kernel' in name:
-        pas = 'dgrad' if (', 1>' in name or 'true' in name) else 'fprop'
+        m = re.search(r'conv_gemm_kernel<\s*\d+,\s*(\w+)', name)      # second template argument: B_MN (dgrad)
+        pas = 'dgrad' if (m and m.group(1) in ('1', 'true')) else 'fprop'
         last = pas
     elif 'splitk_reduce' in name or 'im2col' in name or 'col2im' in name:
         pas = last

@@ -1,5 +1,5 @@
 """Launch a fixed set of hot-path ops a few times each (for ncu captures; GPU box only).
-usage: python -m tests.prof_ops [reps]"""
+usage: python -m tools.prof_ops [reps] [vgg]"""
 import sys
 import torch
 from cpg_b200 import _lib
