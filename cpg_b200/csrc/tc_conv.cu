@@ -1124,8 +1124,8 @@ struct GemmPlan { PixBox box; int BN, ntiles, iters, splits, ips; bool dense, cl
 // split-K partial tiles summed inside a thread-block cluster (distributed shared memory) instead of through a
 // partial-sum buffer + splitk_reduce_kernel; CPGB_SPLITK_CLUSTER=0 restores the round trip through global memory
 static const bool g_splitk_cluster = !(getenv("CPGB_SPLITK_CLUSTER") && atoi(getenv("CPGB_SPLITK_CLUSTER")) == 0);
-constexpr int MAX_CLUSTER = 8;   // portable cluster size
-static const int g_cluster_max_splits = getenv("CPGB_CLUSTER_SPLITS") ? atoi(getenv("CPGB_CLUSTER_SPLITS")) : 8;
+constexpr int MAX_CLUSTER = 16;  // 8 is the portable cluster size; 9..16 need cudaFuncAttributeNonPortableClusterSizeAllowed
+static const int g_cluster_max_splits = std::max(1, std::min(MAX_CLUSTER, getenv("CPGB_CLUSTER_SPLITS") ? atoi(getenv("CPGB_CLUSTER_SPLITS")) : 8));
 static GemmPlan plan_gemm(int Qo, int Po, int No, int ncols, int iters, const Str4 &os) {
   GemmPlan g;
   g.box = make_pixbox(128, Qo, Po, No);
@@ -1155,8 +1155,8 @@ static GemmPlan plan_gemm(int Qo, int Po, int No, int ncols, int iters, const St
     // a portable cluster holds (the 2x2 maps: 14) keep the partial-sum buffer: measured, 8 splits of 18 stages are
     // slower there (30.7 us) than 14 splits of 10 stages plus the reduction kernel (21.5 us) -- these CTAs are
     // latency-bound, their number matters more than the round trip.
-    if (g_splitk_cluster && splits <= MAX_CLUSTER && g_cluster_max_splits >= 2)
-      splits = std::max(splits, std::min(std::min(MAX_CLUSTER, g_cluster_max_splits), (int)(2LL * sms / ctas)));
+    if (g_splitk_cluster && splits <= g_cluster_max_splits && g_cluster_max_splits >= 2)
+      splits = std::max(splits, std::min(g_cluster_max_splits, (int)(2LL * sms / ctas)));
     if (splits > iters / 4) splits = iters / 4;
     if (splits < 1) splits = 1;
   }
@@ -1169,7 +1169,7 @@ static GemmPlan plan_gemm(int Qo, int Po, int No, int ncols, int iters, const St
   // "like the output" any more) -- a padded or strided output can be split as well
   g.ips = cdiv_i(iters, splits);
   g.splits = cdiv_i(iters, g.ips);
-  g.cluster = g_splitk_cluster && g.splits > 1 && g.splits <= MAX_CLUSTER;
+  g.cluster = g_splitk_cluster && g.splits > 1 && g.splits <= g_cluster_max_splits;
   if (g.splits > 1 && !g.cluster && !g.dense) {      // the partial-sum buffer is addressed like a dense output
     g.splits = 1; g.ips = iters;
   }
@@ -1269,9 +1269,12 @@ static int launch_conv_gemm(const CUtensorMap &ta, const CUtensorMap &tb, ConvGe
                             int splits, cudaStream_t st, bool cluster = false) {
   using Cfg = ConvGemmCfg<BN, B_MN>;
   static PerDeviceOnce attr_once;
-  if (attr_once.need())
+  if (attr_once.need()) {
     CPGB_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<BN, B_MN, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       Cfg::smem_bytes(Cfg::NSTAGE_SOLO)));
+    if (g_cluster_max_splits > 8)
+      CPGB_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<BN, B_MN, XF>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  }
   dim3 grid(p.tq * p.tp * p.tn, ntiles_n, splits);
   const long long ctas = (long long)grid.x * grid.y * grid.z;
   p.nstage = ctas > num_sms() ? Cfg::NSTAGE_PAIR : Cfg::NSTAGE_SOLO;   // solo only when no SM gets two CTAs anyway
