@@ -1134,6 +1134,13 @@ static GemmPlan plan_gemm(int Qo, int Po, int No, int ncols, int iters, const St
   if (ncols <= 64) g.BN = 64;
   else if (ncols <= 128) g.BN = 128;
   else g.BN = (mtiles * cdiv_i(ncols, 256) >= sms) ? 256 : 128;
+  // Very few pixel tiles (the 2x2 maps of VGG16: 4): at BN = 128 the layer wants more splits than a cluster holds and
+  // falls back to partial sums in global memory + a reduction kernel.  Half-width tiles double the CTA count, so that
+  // a cluster of <= 8 splits fills the machine and the sum stays in shared memory (CPGB_NARROW_FEW_TILES=0: off).
+  static const bool narrow = !(getenv("CPGB_NARROW_FEW_TILES") && atoi(getenv("CPGB_NARROW_FEW_TILES")) == 0);
+  if (narrow && g_splitk_cluster && g.BN == 128 && ncols >= 128 && ncols % 64 == 0 &&
+      mtiles * cdiv_i(ncols, 128) * g_cluster_max_splits < sms)
+    g.BN = 64;
   // experiment knobs (read per call): CPGB_GEMM_BN forces the tile width where the layer is at least that
   // wide, CPGB_GEMM_SPLITS the split-K factor
   const char *ebn = getenv("CPGB_GEMM_BN"), *esp = getenv("CPGB_GEMM_SPLITS");
