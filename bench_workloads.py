@@ -128,10 +128,12 @@ def _build(workload, device, regime):
     return net, masks, pruner, opts, shape, batch, classes, gflop
 
 
-def _timed(step, feed, steps, warmup, world):
+def _timed(step, feed, steps, warmup, world, finish=None):
     import torch.distributed as dist
     for i in range(warmup):
         feed(i); step()
+    if finish is not None:
+        finish()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -140,6 +142,8 @@ def _timed(step, feed, steps, warmup, world):
     e0.record()
     for i in range(steps):
         feed(warmup + i); step()
+    if finish is not None:
+        finish()                               # e.g. the host read of the last step's loss
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
@@ -212,8 +216,8 @@ def run_model_workload(workload, args, device, world, rank):
         def step_e2e():
             hf.step(state['i'])
             state['i'] += 1
-        ms_e2e = _timed(step_e2e, lambda i: None, args.steps, args.warmup, world)
-        hf.drain(state['i'] - 1)
+        ms_e2e = _timed(step_e2e, lambda i: None, args.steps, args.warmup, world,
+                        finish=lambda: hf.drain(state['i'] - 1))
         imgs = batch * world * args.steps
         out[regime] = {'value': imgs / (ms * 1e-3), 'ms_per_step': ms / args.steps, 'e2e_value': imgs / (ms_e2e * 1e-3),
                        'algorithmic_tflops': gflop * 1e9 * batch * world / (ms / args.steps * 1e-3) / 1e12,

@@ -1126,7 +1126,7 @@ struct GemmPlan { PixBox box; int BN, ntiles, iters, splits, ips; bool dense, cl
 static const bool g_splitk_cluster = !(getenv("CPGB_SPLITK_CLUSTER") && atoi(getenv("CPGB_SPLITK_CLUSTER")) == 0);
 constexpr int MAX_CLUSTER = 16;  // 8 is the portable cluster size; 9..16 need cudaFuncAttributeNonPortableClusterSizeAllowed
 static const int g_cluster_max_splits = std::max(1, std::min(MAX_CLUSTER, getenv("CPGB_CLUSTER_SPLITS") ? atoi(getenv("CPGB_CLUSTER_SPLITS")) : 8));
-static GemmPlan plan_gemm(int Qo, int Po, int No, int ncols, int iters, const Str4 &os) {
+static GemmPlan plan_gemm(int Qo, int Po, int No, int ncols, int iters, const Str4 &os, bool conv) {
   GemmPlan g;
   g.box = make_pixbox(128, Qo, Po, No);
   const long long mtiles = (long long)g.box.tq * g.box.tp * g.box.tn;
@@ -1134,11 +1134,13 @@ static GemmPlan plan_gemm(int Qo, int Po, int No, int ncols, int iters, const St
   if (ncols <= 64) g.BN = 64;
   else if (ncols <= 128) g.BN = 128;
   else g.BN = (mtiles * cdiv_i(ncols, 256) >= sms) ? 256 : 128;
-  // Very few pixel tiles (the 2x2 maps of VGG16: 4): at BN = 128 the layer wants more splits than a cluster holds and
-  // falls back to partial sums in global memory + a reduction kernel.  Half-width tiles double the CTA count, so that
-  // a cluster of <= 8 splits fills the machine and the sum stays in shared memory (CPGB_NARROW_FEW_TILES=0: off).
-  static const bool narrow = !(getenv("CPGB_NARROW_FEW_TILES") && atoi(getenv("CPGB_NARROW_FEW_TILES")) == 0);
-  if (narrow && g_splitk_cluster && g.BN == 128 && ncols >= 128 && ncols % 64 == 0 &&
+  // Experiment, off by default (CPGB_NARROW_FEW_TILES=1): half-width tiles for layers with very few pixel tiles (the 2x2
+  // maps of VGG16: 4), so that a cluster of <= 8 splits fills the machine and the split-K sum stays in shared memory
+  // instead of partial sums + a reduction kernel.  No gain in the step (1.474 vs 1.473-1.484 ms), and the half-width
+  // plans it creates at other batch sizes (non-cluster split-K at BN = 64 with several channel tiles) gave gradients
+  // that were 3 % off in the 16-vs-32 sample shard check (tools/shard_check.py): not a plan the tests cover, so not on.
+  static const bool narrow = getenv("CPGB_NARROW_FEW_TILES") && atoi(getenv("CPGB_NARROW_FEW_TILES")) == 1;
+  if (narrow && conv && g_splitk_cluster && g.BN == 128 && ncols >= 128 && ncols % 64 == 0 &&
       mtiles * cdiv_i(ncols, 128) * g_cluster_max_splits < sms)
     g.BN = 64;
   // experiment knobs (read per call): CPGB_GEMM_BN forces the tile width where the layer is at least that
@@ -1183,10 +1185,10 @@ static GemmPlan plan_gemm(int Qo, int Po, int No, int ncols, int iters, const St
   return g;
 }
 static GemmPlan plan_fprop(const cpgb_conv_desc &d) {
-  return plan_gemm(d.Q, d.P, d.N, up4(d.K), d.R * d.S * (cp_of(d) / 32), y_strides(d));
+  return plan_gemm(d.Q, d.P, d.N, up4(d.K), d.R * d.S * (cp_of(d) / 32), y_strides(d), d.R * d.S > 1);
 }
 static GemmPlan plan_dgrad(const cpgb_conv_desc &d) {
-  return plan_gemm(d.W, d.H, d.N, up4(d.C), d.R * d.S * cdiv_i(d.K, 32), x_strides(d));
+  return plan_gemm(d.W, d.H, d.N, up4(d.C), d.R * d.S * cdiv_i(d.K, 32), x_strides(d), d.R * d.S > 1);
 }
 static size_t plan_partial_bytes(const GemmPlan &g) {
   return (g.splits > 1 && !g.cluster) ? (size_t)g.splits * g.out_elems * sizeof(float) : 0;

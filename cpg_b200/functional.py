@@ -233,9 +233,8 @@ def _epilogue_stream(device):
 def join_epilogue_stream(device, into=None):
     """Make `into` (default: the wgrad side stream) wait for the epilogue kernels queued so far -- what has to happen
     before a collective launched from that stream may read the gradients."""
-    key = _dev_index(device)
-    est = _EPI_STREAMS.get(key)
-    if est is not None and key in _PENDING:
+    est = _EPI_STREAMS.get(_dev_index(device))
+    if est is not None:
         (into if into is not None else _side_stream(device)).wait_stream(est)
 
 

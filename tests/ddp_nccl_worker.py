@@ -115,10 +115,13 @@ def main():
         eager = grads_of(net)
         note('eager sharded steps done')
         assert set(eager) == set(full)
+        bad = []
         for n in full:
             e = rel(eager[n], full[n])
             worst[(regime, 'eager', n)] = e
-            assert e <= 2e-4, (regime, n, e)
+            if e > 2e-4:
+                bad.append((n, e))
+        assert not bad, (regime, bad)
         # weight gradients really live in the buckets (no copies), and are masked
         name0, mod0 = [(n, m) for n, m in net.named_modules() if hasattr(m, '_cpg_grad_slot') and m._cpg_grad_slot][-1]
         base = red.flat[mod0._cpg_grad_slot.bucket]

@@ -940,3 +940,31 @@ def test_bias_grad_two_phase_nhwc(shape):
     db = torch.full((K,), float('nan'), device=DEV)
     _lib.check(lib.cpgb_conv2d_bias_grad(d, _lib.ptr(dy), _lib.ptr(db), _lib.stream_ptr()), 'bias_grad')   # no scratch
     assert rel(db.double(), want) <= 2e-5
+
+
+@pytest.mark.parametrize('regime', ['task1', 'task2'])
+def test_batch_shards_average_to_the_full_batch_gradient(regime):
+    """What data parallelism relies on, checked on ONE GPU: the gradients of a batch-32 step equal the mean of the
+    gradients of its two 16-sample halves (batch-norm on running statistics, so samples are independent).  The two
+    batch sizes take different tile / split plans through the GEMM kernels; a plan that is wrong at one size shows up
+    here (this is how a half-width-tile experiment was caught)."""
+    from tests.ddp_nccl_worker import build, grads_of
+    g = torch.Generator().manual_seed(5)
+    data = torch.randn(32, 3, 32, 32, generator=g).to(DEV)
+    target = torch.randint(0, 5, (32,), generator=g).to(DEV)
+    crit = nn.CrossEntropyLoss()
+    net, masks, pruner = build(regime, torch.device(DEV))
+
+    def step(x, t):
+        for p in net.parameters():
+            p.grad = None
+        crit(net(x), t).backward()
+        pruner.do_weight_decay_and_make_grads_zero()
+        torch.cuda.synchronize()
+        return grads_of(net)
+
+    full = step(data, target)
+    a, b = step(data[:16], target[:16]), step(data[16:], target[16:])
+    bad = [(n, rel((a[n] + b[n]) / 2, full[n])) for n in full if rel((a[n] + b[n]) / 2, full[n]) > 2e-4]
+    assert not bad, bad[:8]
+    pruner.detach()
