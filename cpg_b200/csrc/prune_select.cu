@@ -723,6 +723,7 @@ sel_finish_kernel(const __grid_constant__ PruneBatch pb, int cur, SelState *__re
         if ((int)threadIdx.x >= o) incl += up;
       }
       unsigned acc = incl - tot;
+      __syncwarp();                                         // every lane has read s_remain / s_prefix
       if (acc < remain && remain <= incl) {                 // exactly one lane
         int j = 0;
         for (; j < 7; ++j) { if (acc + c[j] >= remain) break; acc += c[j]; }

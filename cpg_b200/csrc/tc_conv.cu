@@ -487,7 +487,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     float *const *rows = tail->rowptr[quad];
     const float *bias = p.bias;
     if (p.cluster > 1) {
-      // park this CTA's partial tile in shared memory for the cluster-wide sum below: thread = accumulator row
+      // park this CTA's partial tile in shared memory for the cluster-wide sum below: thread = accumulator row.
+      // The tile overlays the stage ring, which these four warps may have written themselves (in-tile weight
+      // masking): acc_full already orders every such write before this point through the mbarrier chain; the named
+      // barrier states the same thing in terms compute-sanitizer's racecheck understands.
+      asm volatile("bar.sync 1, 128;" ::: "memory");
       float *red = reinterpret_cast<float *>(smem) + m * Cfg::RED_LD;
 #pragma unroll 1
       for (int c = 0; c < BN; c += 32) {
