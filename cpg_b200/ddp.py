@@ -25,19 +25,23 @@ from . import _lib
 from .functional import join_epilogue_stream, pending_side_stream, _side_stream
 
 BIG = 1 << 18            # elements; other (non-sharable) tensors at least this large get their own overlapped all-reduce
-BUCKET_BYTES = 48 << 20  # a bucket is closed once it holds this much
+# a bucket is closed once it holds this much (CPGB_BUCKET_MB overrides: smaller buckets shorten the exposed tail of the
+# last all-reduce, larger ones amortise launch latency)
+BUCKET_BYTES = int(float(__import__('os').environ.get('CPGB_BUCKET_MB', '48')) * (1 << 20))
 
 
 def tune_env(world):
     """Environment defaults for the overlapped all-reduce; call before ``init_process_group`` and before
     the first cpg_b200 kernel.  The all-reduce of the 134 MB gradient runs next to dgrad / wgrad, whose
     grids are planned as exact waves of the SM count: NCCL's default CTA count evicts enough of those
-    CTAs to cost more than the collective itself.  Measured on 2 x B200 (bench.py, batch 128 per GPU):
-    default 2.33 ms/step; NCCL_MAX_CTAS=16 + grids planned for 8 fewer SMs 2.25 ms; 8 CTAs or fewer make
-    the collective the critical path (2.53 ms, 3.31 ms at 4).  Existing settings win."""
+    CTAs to cost more than the collective itself, too few CTAs make the collective the critical path.  Measured
+    with bench.py (batch 128 per GPU, ms per step): 2 x B200 -- default 2.33, NCCL_MAX_CTAS=16 + grids planned for 8
+    fewer SMs 2.25, 8 CTAs 2.53, 4 CTAs 3.31 (round 1); 4 x B200 -- 16 CTAs 1.753, 32 CTAs 1.720; 8 x B200 -- 16 CTAs
+    1.975, 32 CTAs 1.780 (round 2: the ring / NVLS schedule has more steps per byte, the CTA budget has to grow with
+    it).  Hence 16 CTAs up to two ranks, 32 beyond.  Existing settings win."""
     import os
     if world > 1:
-        os.environ.setdefault('NCCL_MAX_CTAS', '16')
+        os.environ.setdefault('NCCL_MAX_CTAS', '16' if world <= 2 else '32')
         os.environ.setdefault('CPGB_SM_MARGIN', '8')
 
 
