@@ -24,7 +24,8 @@ EXPORTS = [
     'cpgb_split_merged_grad', 'cpgb_bn_workspace_bytes', 'cpgb_bn_relu_fwd', 'cpgb_bn_relu_bwd',
     'cpgb_uses_tensor_cores', 'cpgb_round_tf32', 'cpgb_conv2d_bias_grad', 'cpgb_conv2d_bias_grad_ws', 'cpgb_pack_mask', 'cpgb_intile_eligible',
     'cpgb_intile_weight_shape', 'cpgb_sgd_nesterov_step', 'cpgb_adam_step', 'cpgb_prelu_workspace_bytes',
-    'cpgb_prelu_fwd', 'cpgb_prelu_bwd',
+    'cpgb_prelu_fwd', 'cpgb_prelu_bwd', 'cpgb_fprop_colstats_parts', 'cpgb_conv2d_fprop_stats',
+    'cpgb_bn_relu_fwd_stats',
 ]
 
 
@@ -77,6 +78,10 @@ def load():
         'cpgb_stage_weights_batched': (ctypes.c_int, [i32, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp)]
                                        + [ctypes.POINTER(i32)] * 6 + [ctypes.POINTER(f32), vp]),
         'cpgb_conv2d_fprop': (ctypes.c_int, [dp, vp, vp, vp, vp, vp, f32, vp, vp, sz, vp]),
+        'cpgb_fprop_colstats_parts': (i32, [dp]),
+        'cpgb_conv2d_fprop_stats': (ctypes.c_int, [dp, vp, vp, vp, vp, vp, f32, vp, vp, sz, vp, vp]),
+        'cpgb_bn_relu_fwd_stats': (ctypes.c_int, [vp, i64, i32, i32, vp, i32, vp, vp, vp, vp, vp, i32, f32, f32, i32, i32,
+                                                  i32, i32, vp, vp, vp, vp, sz, vp]),
         'cpgb_conv2d_dgrad': (ctypes.c_int, [dp, vp, vp, vp, vp, f32, vp, vp, sz, vp]),
         'cpgb_conv2d_wgrad_fused': (ctypes.c_int, [dp, vp, vp, vp, vp, vp, i32, f32, i32, vp, vp, vp, f32,
                                                   vp, sz, vp]),

@@ -205,13 +205,29 @@ static int tc_operands(const cpgb_conv_desc *d, const float *w, const float *pig
   return CPGB_OK;
 }
 
+int32_t cpgb_fprop_colstats_parts(const cpgb_conv_desc *d) {
+  if (!d || validate_desc(d) || d->N == 0 || g_path.load() == CPGB_PATH_SIMT) return 0;
+  if ((d->flags & CPGB_FLAG_W_INTILE) || pick_stem(d, nullptr)) return 0;
+  return tc_fprop_colstats_parts(*d);
+}
+
 int cpgb_conv2d_fprop(const cpgb_conv_desc *d, const float *x, const float *w, const float *piggy,
                       const float *bias, float *y, float thr, const void *staged, void *ws, size_t ws_bytes,
                       void *stream) {
+  return cpgb_conv2d_fprop_stats(d, x, w, piggy, bias, y, thr, staged, ws, ws_bytes, nullptr, stream);
+}
+
+int cpgb_conv2d_fprop_stats(const cpgb_conv_desc *d, const float *x, const float *w, const float *piggy,
+                            const float *bias, float *y, float thr, const void *staged, void *ws, size_t ws_bytes,
+                            float *colstats, void *stream) {
   int rc = validate_desc(d);
   if (rc) return rc;
   if (d->N == 0) return CPGB_OK;  // empty batch: nothing to compute, y is empty
   if (!x || !w || !y) { set_error("cpgb_conv2d_fprop: null pointer"); return CPGB_EINVAL; }
+  if (colstats && ((reinterpret_cast<uintptr_t>(colstats) & 15) || cpgb_fprop_colstats_parts(d) == 0)) {
+    set_error("cpgb_conv2d_fprop_stats: this layer cannot produce column statistics (cpgb_fprop_colstats_parts == 0)");
+    return CPGB_EINVAL;
+  }
   if (pick_stem(d, y) && (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0))
     return stem_fprop(*d, x, w, piggy, bias, y, thr, (cudaStream_t)stream);
   bool use_tc;
@@ -226,7 +242,7 @@ int cpgb_conv2d_fprop(const cpgb_conv_desc *d, const float *x, const float *w, c
     const float *wt; void *part; size_t part_bytes; bool raw;
     if ((rc = tc_operands(d, w, piggy, thr, staged, ws, ws_bytes, (cudaStream_t)stream, &wt, &part, &part_bytes, &raw)))
       return rc;
-    return tc_fprop(*d, x, wt, bias, y, part, part_bytes, (cudaStream_t)stream, raw);
+    return tc_fprop(*d, x, wt, bias, y, part, part_bytes, (cudaStream_t)stream, raw, colstats);
   }
   return simt_fprop(make_geom(*d), x, w, piggy, bias, y, thr, (cudaStream_t)stream);
 }

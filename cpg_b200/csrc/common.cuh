@@ -172,8 +172,10 @@ int tc_stage_weights_batched(int n, const float *const *w, const float *const *p
 // part: scratch for split-K partial sums (tc_workspace_bytes covers staged operand + partials)
 // raw: `staged` is the module's fp32 weight tensor itself (tc_weights_usable_raw)
 bool tc_weights_usable_raw(const cpgb_conv_desc &d);
+// colstats (may be NULL): [tc_fprop_colstats_parts(d)][up4(K)][2] per-tile column sums / sums of squares of y
 int tc_fprop(const cpgb_conv_desc &d, const float *x, const float *staged, const float *bias, float *y, void *part,
-             size_t part_bytes, cudaStream_t st, bool raw);
+             size_t part_bytes, cudaStream_t st, bool raw, float *colstats = nullptr);
+int tc_fprop_colstats_parts(const cpgb_conv_desc &d);
 int tc_dgrad(const cpgb_conv_desc &d, const float *dy, const float *staged, float *dx, void *part, size_t part_bytes,
              cudaStream_t st, bool raw);
 // in-tile weight masking (CPGB_FLAG_W_INTILE): B operand = the raw weight tensor, masked from packed bits in shared memory

@@ -921,6 +921,16 @@ int cpgb_bn_relu_fwd(const float *x, int64_t M, int32_t C, int32_t ldc, const fl
                      float *running_mean, float *running_var, int64_t *num_batches_tracked, int32_t training,
                      float momentum, float eps, int32_t relu, int32_t pool_h, int32_t pool_w, int32_t tf32_out, float *y,
                      float *save_mean, float *save_rstd, void *ws, size_t ws_bytes, void *stream) {
+  return cpgb_bn_relu_fwd_stats(x, M, C, ldc, nullptr, 0, gamma, beta, running_mean, running_var, num_batches_tracked,
+                                training, momentum, eps, relu, pool_h, pool_w, tf32_out, y, save_mean, save_rstd, ws,
+                                ws_bytes, stream);
+}
+
+int cpgb_bn_relu_fwd_stats(const float *x, int64_t M, int32_t C, int32_t ldc, const float *colstats, int32_t nparts,
+                           const float *gamma, const float *beta, float *running_mean, float *running_var,
+                           int64_t *num_batches_tracked, int32_t training, float momentum, float eps, int32_t relu,
+                           int32_t pool_h, int32_t pool_w, int32_t tf32_out, float *y, float *save_mean, float *save_rstd,
+                           void *ws, size_t ws_bytes, void *stream) {
   PoolGeom pg;
   const bool pool = pool_h != 0 || pool_w != 0;
   const int Cs = na_stride(C, ldc);
@@ -938,6 +948,10 @@ int cpgb_bn_relu_fwd(const float *x, int64_t M, int32_t C, int32_t ldc, const fl
     set_error("cpgb_bn_relu_fwd: missing statistics buffers"); return CPGB_EINVAL;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  // per-tile column statistics from the convolution that produced x (cpgb_conv2d_fprop_stats): the statistics pass over
+  // x is not needed, finalize sums the producer's partial pairs instead (same [part][Cs][2] layout).  Tensors small
+  // enough for the single-launch kernels keep using those: one launch beats finalize + apply.
+  const bool have_stats = training && colstats != nullptr && nparts > 0 && !nc_enabled(M, Cs);
   if (nc_enabled(M, Cs)) {
     // one launch: clusters of CTAs split the pixel rows of a channel chunk and exchange their partial sums through
     // distributed shared memory
@@ -960,10 +974,15 @@ int cpgb_bn_relu_fwd(const float *x, int64_t M, int32_t C, int32_t ldc, const fl
   float *coef_a = reinterpret_cast<float *>(ws), *coef_b = coef_a + Cs, *part = coef_a + 4 * Cs;
   if (training) {
     const NaGeom gs = na_geom(M, C, Cs, NA_STATS_THREADS);
-    const int nb = na_blocks(gs, NA_STATS_PER_SM);
-    CPGB_CUDA_OK(launch_dependent(bn_stats_kernel, dim3(dim3(nb, gs.cchunks)), dim3(NA_STATS_THREADS), 0, st, gs, x, part));
-    CPGB_LAUNCH_OK("bn_stats");
-    CPGB_CUDA_OK(launch_dependent(bn_finalize_kernel, dim3((Cs + 7) / 8), dim3(256), 0, st, part, nb, C, Cs, M, gamma, beta, running_mean, running_var, momentum,
+    int nb = na_blocks(gs, NA_STATS_PER_SM);
+    const float *fin_part = part;
+    if (have_stats) {
+      fin_part = colstats; nb = nparts;
+    } else {
+      CPGB_CUDA_OK(launch_dependent(bn_stats_kernel, dim3(dim3(nb, gs.cchunks)), dim3(NA_STATS_THREADS), 0, st, gs, x, part));
+      CPGB_LAUNCH_OK("bn_stats");
+    }
+    CPGB_CUDA_OK(launch_dependent(bn_finalize_kernel, dim3((Cs + 7) / 8), dim3(256), 0, st, fin_part, nb, C, Cs, M, gamma, beta, running_mean, running_var, momentum,
                                                          eps, save_mean, save_rstd, coef_a, coef_b,
                                                          reinterpret_cast<long long *>(num_batches_tracked)));
     CPGB_LAUNCH_OK("bn_finalize");

@@ -303,6 +303,11 @@ struct ConvGemmParams {
   long long split_stride;  // elements between the partial outputs of consecutive splits
   float *out;              // y / dx, or the partial-sum buffer when split
   const float *bias;       // only when not split
+  // fprop feeding a training-mode batch-norm (cpgb_conv2d_fprop_stats): per pixel tile, the column sums and sums of
+  // squares of the values this CTA stores, as [tile][cs_ld][2] -- the layout of the batch-norm kernels' partial sums,
+  // so that bn_finalize can consume them and the bn_stats pass over y is not needed.  Unsplit tiles, BN <= 128 only.
+  float *colstats;
+  int cs_ld;
 };
 
 constexpr int A_TILE_BYTES = 128 * 128;  // 128 pixels x 32 fp32
@@ -502,20 +507,64 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int j = 0; j < 32; j += 4)
           *reinterpret_cast<float4 *>(red + c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
       }
-    } else
+    } else {
+      float4 cs = make_float4(0.f, 0.f, 0.f, 0.f), cq = cs;    // column sums / sums of squares of this lane's columns
+      const bool stats = p.colstats != nullptr;
 #pragma unroll 1
-    for (int h = 0; h < BN; h += Cfg::NC) {
-      epilogue_rows<Cfg::NC>(tmem_base, quad, h, ts, lane, [&](int rr, int c4, float4 v) {
-        float *rp = rows[rr];
-        const int col = col0 + h + c4;
-        if (rp != nullptr && col < p.ncols) {   // ncols % 4 == 0
-          if (bias) {
-            const float4 b = load_bias4(bias, col, p.nvalid);
-            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+      for (int h = 0; h < BN; h += Cfg::NC) {
+        epilogue_rows<Cfg::NC>(tmem_base, quad, h, ts, lane, [&](int rr, int c4, float4 v) {
+          float *rp = rows[rr];
+          const int col = col0 + h + c4;
+          if (rp != nullptr && col < p.ncols) {   // ncols % 4 == 0
+            if (bias) {
+              const float4 b = load_bias4(bias, col, p.nvalid);
+              v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+            }
+            *reinterpret_cast<float4 *>(rp + h + c4) = v;
+            if (stats) {
+              cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
+              cq.x = fmaf(v.x, v.x, cq.x); cq.y = fmaf(v.y, v.y, cq.y);
+              cq.z = fmaf(v.z, v.z, cq.z); cq.w = fmaf(v.w, v.w, cq.w);
+            }
           }
-          *reinterpret_cast<float4 *>(rp + h + c4) = v;
+        });
+      }
+      if (stats) {
+        // (host side: BN <= 128, so NC == BN and a lane kept ONE column group throughout)
+        constexpr int NCs = Cfg::NC, LPR = NCs / 4;
+        if (LPR < 32) {                          // BN = 64: lanes l and l + 16 hold the same columns (even / odd rows)
+#pragma unroll
+          for (int o = LPR; o < 32; o <<= 1) {
+            cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
+            cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
+            cq.x += __shfl_xor_sync(0xffffffffu, cq.x, o); cq.y += __shfl_xor_sync(0xffffffffu, cq.y, o);
+            cq.z += __shfl_xor_sync(0xffffffffu, cq.z, o); cq.w += __shfl_xor_sync(0xffffffffu, cq.w, o);
+          }
         }
-      });
+        const int c4 = (lane % LPR) * 4;
+        // the warp's scratch is free again (epilogue_rows ends with __syncwarp): park the warp's sums there, ...
+        if (lane < LPR) {
+          *reinterpret_cast<float4 *>(ts + c4) = cs;
+          *reinterpret_cast<float4 *>(ts + NCs + c4) = cq;
+        }
+        asm volatile("bar.sync 2, 128;" ::: "memory");      // ... the four epilogue warps meet, ...
+        if (quad == 0 && lane < LPR && col0 + c4 < p.ncols) {
+          // ... and one warp adds the four in warp order and writes the tile's partial pairs
+          const float *base = reinterpret_cast<const float *>(smem);
+          constexpr int WS = 32 * (NCs + 4);     // floats between the scratch regions of consecutive warps
+          float4 s4 = *reinterpret_cast<const float4 *>(base + c4), q4 = *reinterpret_cast<const float4 *>(base + NCs + c4);
+#pragma unroll
+          for (int w = 1; w < 4; ++w) {
+            const float4 a = *reinterpret_cast<const float4 *>(base + w * WS + c4);
+            const float4 b = *reinterpret_cast<const float4 *>(base + w * WS + NCs + c4);
+            s4.x += a.x; s4.y += a.y; s4.z += a.z; s4.w += a.w;
+            q4.x += b.x; q4.y += b.y; q4.z += b.z; q4.w += b.w;
+          }
+          float *dst = p.colstats + ((long long)blockIdx.x * p.cs_ld + col0 + c4) * 2;
+          reinterpret_cast<float4 *>(dst)[0] = make_float4(s4.x, q4.x, s4.y, q4.y);
+          reinterpret_cast<float4 *>(dst)[1] = make_float4(s4.z, q4.z, s4.w, q4.w);
+        }
+      }
     }
     tc_fence_before();
   }
@@ -1364,9 +1413,18 @@ static void set_intile(ConvGemmParams &p, const cpgb_conv_desc &d, const IntileA
   p.w_rows = d.K;
 }
 
+// Can the fprop of d hand per-tile column statistics to a batch-norm that follows (ConvGemmParams::colstats)?  Only the
+// plain epilogue does it: an unsplit plan with tiles of at most 128 channels.  Returns the number of pixel tiles.
+static int implicit_colstats_parts(const cpgb_conv_desc &d) {
+  if (!implicit_eligible(d, 0)) return 0;
+  const GemmPlan g = plan_fprop(d);
+  if (g.splits != 1 || g.BN > 128) return 0;
+  return g.box.tq * g.box.tp * g.box.tn;
+}
+
 static int implicit_fprop(const cpgb_conv_desc &d, const float *x, const float *staged, const float *bias, float *y,
                           void *part, size_t part_bytes, cudaStream_t st, bool raw = false,
-                          const IntileArgs *intile = nullptr) {
+                          const IntileArgs *intile = nullptr, float *colstats = nullptr) {
   if (!aligned16p(x) || !aligned16p(y) || !aligned16p(staged) || (bias && !aligned16p(bias)) || !aligned16p(part)) {
     set_error("tcgen05 path needs 16-byte aligned tensors"); return CPGB_EINVAL;
   }
@@ -1387,6 +1445,8 @@ static int implicit_fprop(const cpgb_conv_desc &d, const float *x, const float *
   p.off_h = -d.pad_h; p.off_w = -d.pad_w; p.step_h = d.dil_h; p.step_w = d.dil_w;
   p.kblocks = Cp / 32; p.ncols = up4(d.K); p.nvalid = d.K;
   set_intile(p, d, intile);
+  p.colstats = (colstats && !intile && g.splits == 1 && g.BN <= 128) ? colstats : nullptr;
+  p.cs_ld = up4(d.K);
   { Str4 ys = y_strides(d); p.o_sn = ys.s[0]; p.o_sh = ys.s[2]; p.o_sw = ys.s[3]; }
   return run_gemm<false>(g, ta, tb, p, y, bias, part, part_bytes, st);
 }
@@ -1414,6 +1474,7 @@ static int implicit_dgrad(const cpgb_conv_desc &d, const float *dy, const float 
   p.Qo = d.W; p.Po = d.H; p.No = d.N; p.S = d.S; p.taps = RS;
   p.off_h = d.pad_h; p.off_w = d.pad_w; p.step_h = -d.dil_h; p.step_w = -d.dil_w;
   p.kblocks = cdiv_i(d.K, 32); p.ncols = up4(d.C); p.nvalid = d.C;
+  p.colstats = nullptr; p.cs_ld = 0;
   set_intile(p, d, intile);
   { Str4 xs = x_strides(d); p.o_sn = xs.s[0]; p.o_sh = xs.s[2]; p.o_sw = xs.s[3]; }
   return run_gemm<true>(g, ta, tb, p, dx, nullptr, part, part_bytes, st);
@@ -2054,9 +2115,12 @@ int tc_stage_weights(const cpgb_conv_desc &d, const float *w, const float *piggy
 bool tc_weights_usable_raw(const cpgb_conv_desc &) { return false; }
 
 int tc_fprop(const cpgb_conv_desc &d, const float *x, const float *staged, const float *bias, float *y, void *part,
-             size_t part_bytes, cudaStream_t st, bool raw) {
+             size_t part_bytes, cudaStream_t st, bool raw, float *colstats) {
   return tc_mode(d, 0) == TC_XCOL ? xcol_fprop(d, x, staged, bias, y, part, part_bytes, st)
-                                  : implicit_fprop(d, x, staged, bias, y, part, part_bytes, st, raw);
+                                  : implicit_fprop(d, x, staged, bias, y, part, part_bytes, st, raw, nullptr, colstats);
+}
+int tc_fprop_colstats_parts(const cpgb_conv_desc &d) {
+  return tc_mode(d, 0) == TC_IMPLICIT ? implicit_colstats_parts(d) : 0;
 }
 
 int tc_dgrad(const cpgb_conv_desc &d, const float *dy, const float *staged, float *dx, void *part, size_t part_bytes,

@@ -202,6 +202,9 @@ EPILOGUE_STREAM = os.environ.get('CPGB_EPILOGUE_STREAM', '1') != '0'
 # issue dgrad (the critical chain of the backward pass) before the forked wgrad, so that the block scheduler hands
 # free SMs to it first.  Measured: no difference (1.502 vs 1.499 ms per step), off by default (CPGB_DGRAD_FIRST=1)
 DGRAD_FIRST = os.environ.get('CPGB_DGRAD_FIRST', '0') != '0'
+# a convolution that feeds a fused batch-norm (cpg_b200.fused_norm.fuse_bn_relu marks it) accumulates the per-tile
+# column statistics of y in its epilogue (cpgb_conv2d_fprop_stats) and the batch-norm skips its statistics pass
+COLSTATS = os.environ.get('CPGB_COLSTATS', '1') != '0'
 OVERLAP_BACKWARD = True   # run wgrad on a side stream (it only reads x and dy; nothing on the main chain needs it)
 DEFER_JOIN = True         # join the side stream once, at the end of the backward pass, instead of per layer
 _PENDING = {}             # device index -> (graph task id, tensors the side stream may still be reading)
@@ -402,7 +405,7 @@ class MaskedConv2dFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, piggymask, bias, stride, padding, dilation, groups, threshold, fuse,
-                module, channels_last_out, prestaged=None, x_exact=False):
+                module, channels_last_out, prestaged=None, x_exact=False, emit_colstats=False):
         lib = _lib.load()
         _check_params(weight, piggymask, bias)
         if x.dim() != 4:
@@ -440,10 +443,21 @@ class MaskedConv2dFn(torch.autograd.Function):
         d.flags = _lib.FLAG_X_TF32 if x_exact else 0
         with torch.cuda.device(x.device):
             staged, ws = _stage(lib, d, w, p, threshold, prestaged, owner=piggymask)
-            _lib.check(lib.cpgb_conv2d_fprop(d, _lib.ptr(x), _lib.ptr(w), _lib.ptr(p), _lib.ptr(b),
-                                             _lib.ptr(y), threshold, _lib.ptr(staged), _lib.ptr(ws),
-                                             ws.numel() if ws is not None else 0,
-                                             _lib.stream_ptr()), 'cpgb_conv2d_fprop')
+            colstats, nparts = None, 0
+            if emit_colstats and COLSTATS:
+                # per pixel tile: column sums / sums of squares of y for the batch-norm behind this layer, when the
+                # plan of this shape can deliver them and y has the pixel stride that kernel family expects
+                nparts = lib.cpgb_fprop_colstats_parts(d)
+                if nparts > 0 and nhwc_pixel_stride(y) == _up4(K):
+                    colstats = torch.empty(nparts * _up4(K) * 2, dtype=torch.float32, device=x.device)
+                else:
+                    nparts = 0
+            _lib.check(lib.cpgb_conv2d_fprop_stats(d, _lib.ptr(x), _lib.ptr(w), _lib.ptr(p), _lib.ptr(b),
+                                                   _lib.ptr(y), threshold, _lib.ptr(staged), _lib.ptr(ws),
+                                                   ws.numel() if ws is not None else 0, _lib.ptr(colstats),
+                                                   _lib.stream_ptr()), 'cpgb_conv2d_fprop')
+        # read by FusedBatchNormReLU2d off y.grad_fn: (partial pairs, how many, channels)
+        ctx.cpgb_colstats = (colstats, nparts, K) if colstats is not None else None
         ctx.save_for_backward(x, w, p)
         ctx.staged = staged     # masked TF32 operand, shared with this step's dgrad
         ctx.has_bias = bias is not None
@@ -470,7 +484,7 @@ class MaskedConv2dFn(torch.autograd.Function):
         dx = empty_like_padded(x) if need_dx else None
         dW, dP, db = _backward_kernels(lib, ctx, d, x, dy, w, p, threshold, ctx.staged, need_dx, need_w,
                                        ctx.has_bias, dx, dy_raw if ctx.has_bias else None)
-        return dx, dW, dP, db, None, None, None, None, None, None, None, None, None, None
+        return dx, dW, dP, db, None, None, None, None, None, None, None, None, None, None, None
 
 
 def _rows16(m):

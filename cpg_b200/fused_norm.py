@@ -31,7 +31,7 @@ CL = torch.channels_last
 class _BNReLUFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, running_mean, running_var, nbt, training, momentum, eps, relu, pool,
-                tf32_out=False):
+                tf32_out=False, colstats=None):
         lib = _lib.load()
         x = to_nhwc_aligned(x)          # dense channels_last, or NHWC with the pixel stride padded to 4 (C % 4 != 0)
         ldc = nhwc_pixel_stride(x)
@@ -47,8 +47,10 @@ class _BNReLUFn(torch.autograd.Function):
                 rstd = torch.empty(C, dtype=torch.float32, device=x.device)
             else:
                 mean, rstd = running_mean, torch.rsqrt(running_var + eps)
-            _lib.check(lib.cpgb_bn_relu_fwd(
-                _lib.ptr(x), M, C, ldc, _lib.ptr(w), _lib.ptr(b), _lib.ptr(running_mean), _lib.ptr(running_var),
+            cs, nparts = (colstats[0], colstats[1]) if (training and colstats is not None) else (None, 0)
+            _lib.check(lib.cpgb_bn_relu_fwd_stats(
+                _lib.ptr(x), M, C, ldc, _lib.ptr(cs), nparts, _lib.ptr(w), _lib.ptr(b), _lib.ptr(running_mean),
+                _lib.ptr(running_var),
                 _lib.ptr(nbt) if training else None, 1 if training else 0, float(momentum), float(eps), 1 if relu else 0,
                 H if pool else 0, W if pool else 0, 1 if tf32_out else 0, _lib.ptr(y),
                 _lib.ptr(mean) if training else None, _lib.ptr(rstd) if training else None,
@@ -85,7 +87,7 @@ class _BNReLUFn(torch.autograd.Function):
                 _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), 'cpgb_bn_relu_bwd')
         if ctx.cpgb_tf32_out:
             mark_tf32(dx)
-        return dx, dg, db, None, None, None, None, None, None, None, None, None
+        return dx, dg, db, None, None, None, None, None, None, None, None, None, None
 
 
 class FusedBatchNormReLU2d(nn.BatchNorm2d):
@@ -143,9 +145,17 @@ class FusedBatchNormReLU2d(nn.BatchNorm2d):
         rm = self.running_mean if (not training or update) else None
         rv = self.running_var if (not training or update) else None
         pool = self.pool and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0
+        # statistics the producing convolution left on its autograd node (cpgb_conv2d_fprop_stats): valid for exactly
+        # this tensor, untouched since (version 0), same channel count, dense / padded NHWC as the kernels expect
+        colstats = None
+        if training:
+            cs = getattr(x.grad_fn, 'cpgb_colstats', None)
+            if (cs is not None and x._version == 0 and cs[2] == x.shape[1] and cs[0].device == x.device and
+                    nhwc_pixel_stride(x) == (x.shape[1] + 3) // 4 * 4):
+                colstats = cs
         y = _BNReLUFn.apply(x, self.weight, self.bias, rm, rv, nbt, training,
                             self.momentum if self.momentum is not None else 0.0, self.eps, self.relu, pool,
-                            self.tf32_out)
+                            self.tf32_out, colstats)
         if self.tf32_out:
             mark_tf32(y)
         return F.max_pool2d(y, 2, 2) if (self.pool and not pool) else y
@@ -252,6 +262,10 @@ def fuse_bn_relu(model, pool=True, tf32_out=True):
             nxt2 = parent._modules[names[i + 2]] if (relu and pool and i + 2 < len(names)) else None
             do_pool = _is_pool2x2(nxt2)
             parent._modules[name] = FusedBatchNormReLU2d.from_bn(m, relu=relu, pool=do_pool, tf32_out=tf32_out)
+            prev = parent._modules[names[i - 1]] if (isinstance(parent, nn.Sequential) and i > 0) else None
+            if type(prev).__name__ == 'SharableConv2d' and hasattr(prev, 'piggymask'):
+                # conv -> BN inside a Sequential: the convolution's epilogue hands the batch-norm its statistics
+                prev._cpg_emit_colstats = True
             if relu:
                 parent._modules[names[i + 1]] = nn.Identity()
                 pairs += 1

@@ -135,7 +135,8 @@ class SharableConv2d(_SharableBase):
         pre = self._take_prestaged(weight, piggy) if weight is self.weight else None
         return MaskedConv2dFn.apply(input, weight, piggy, self.bias, self.stride, self.padding,
                                     self.dilation, self.groups, float(self.info['threshold']), fuse,
-                                    self._owner(weight), OUTPUT_CHANNELS_LAST, pre, is_tf32(input))
+                                    self._owner(weight), OUTPUT_CHANNELS_LAST, pre, is_tf32(input),
+                                    bool(getattr(self, '_cpg_emit_colstats', False)) and self.training)
 
     def __repr__(self):
         s = ('{name} ({in_channels}, {out_channels}, kernel_size={kernel_size}'

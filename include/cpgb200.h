@@ -158,6 +158,16 @@ int cpgb_stage_weights_batched(int32_t n, const float *const *w, const float *co
 int cpgb_conv2d_fprop(const cpgb_conv_desc *d, const float *x, const float *w, const float *piggy,
                       const float *bias, float *y, float thr, const void *staged, void *ws, size_t ws_bytes,
                       void *stream);
+/* fprop that also hands the batch-norm behind it (conv -> nn.BatchNorm2d, models/vgg.py:109-118) its statistics: while
+ * the epilogue stores y it accumulates, per pixel tile, the column sums and sums of squares of exactly the stored values
+ * into colstats[cpgb_fprop_colstats_parts(d)][K rounded up to 4][2] -- the layout of the batch-norm kernels' partial
+ * sums -- and cpgb_bn_relu_fwd_stats then skips its statistics pass over y.  cpgb_fprop_colstats_parts(d) == 0: this
+ * layer / path cannot (stem, im2col tier, CUDA-core path, split-K plans, in-tile masked layers); colstats must then be
+ * NULL.  colstats == NULL is cpgb_conv2d_fprop. */
+int32_t cpgb_fprop_colstats_parts(const cpgb_conv_desc *d);
+int cpgb_conv2d_fprop_stats(const cpgb_conv_desc *d, const float *x, const float *w, const float *piggy,
+                            const float *bias, float *y, float thr, const void *staged, void *ws, size_t ws_bytes,
+                            float *colstats, void *stream);
 
 /* a4 dgrad: dx = conv_transpose(dy, W_eff).  dy uses d->ys strides, dx uses d->xs. */
 int cpgb_conv2d_dgrad(const cpgb_conv_desc *d, const float *dy, const float *w, const float *piggy,
@@ -304,6 +314,15 @@ int cpgb_bn_relu_fwd(const float *x, int64_t M, int32_t C, int32_t ldc, const fl
                      float *running_mean, float *running_var, int64_t *num_batches_tracked, int32_t training,
                      float momentum, float eps, int32_t relu, int32_t pool_h, int32_t pool_w, int32_t tf32_out, float *y,
                      float *save_mean, float *save_rstd, void *ws, size_t ws_bytes, void *stream);
+/* The same with the statistics of x supplied by its producer: colstats[nparts][ldc or C][2] partial (sum, sum of squares)
+ * pairs over disjoint pixel sets that together cover all M pixels (cpgb_conv2d_fprop_stats).  Used in training mode for
+ * tensors that take the three-kernel path; otherwise (evaluation mode, colstats == NULL, small tensors on the
+ * single-launch kernels) identical to cpgb_bn_relu_fwd. */
+int cpgb_bn_relu_fwd_stats(const float *x, int64_t M, int32_t C, int32_t ldc, const float *colstats, int32_t nparts,
+                           const float *gamma, const float *beta, float *running_mean, float *running_var,
+                           int64_t *num_batches_tracked, int32_t training, float momentum, float eps, int32_t relu,
+                           int32_t pool_h, int32_t pool_w, int32_t tf32_out, float *y, float *save_mean, float *save_rstd,
+                           void *ws, size_t ws_bytes, void *stream);
 /* Backward of the above: with g = dy * [y > 0] (relu) or dy,  xhat = (x - mean) * rstd:
  *   dbeta = sum g;  dgamma = sum g * xhat;
  *   training: dx = gamma * rstd * (g - mean(g) - xhat * mean(g * xhat));   evaluation: dx = gamma * rstd * g.

@@ -968,3 +968,66 @@ def test_batch_shards_average_to_the_full_batch_gradient(regime):
     bad = [(n, rel((a[n] + b[n]) / 2, full[n])) for n in full if rel((a[n] + b[n]) / 2, full[n]) > 2e-4]
     assert not bad, bad[:8]
     pruner.detach()
+
+
+@pytest.mark.parametrize('case', [(128, 64, 64, 32), (128, 64, 128, 16), (128, 128, 128, 16), (128, 64, 78, 16), (16, 32, 256, 8)])
+def test_conv_epilogue_hands_batchnorm_its_statistics(case):
+    """conv -> BN (training): the convolution's epilogue accumulates the per-tile column sums of y
+    (cpgb_conv2d_fprop_stats) and the batch-norm skips its statistics pass.  Same outputs, running statistics and
+    gradients as with the pass and as the stock modules, one launch fewer where the path applies (unsplit tcgen05
+    plans, tensors that take the three-kernel batch-norm path); elsewhere nothing changes."""
+    import cpg_b200.functional as Fn
+    from cpg_b200.fused_norm import fuse_bn_relu
+    N, C, K, HW = case
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(K + HW)
+    w0 = (torch.randn(K, C, 3, 3, generator=g) * 0.05).to(DEV)      # the reference layer leaves its weight uninitialised
+    b0 = (torch.randn(K, generator=g) * 0.1).to(DEV)
+    xv = (torch.randn(N, C, HW, HW, generator=g) * 1.5 + 0.2).to(DEV).contiguous(memory_format=torch.channels_last)
+    dy = torch.randn(N, K, HW, HW, generator=g).to(DEV).contiguous(memory_format=torch.channels_last)
+    res = {}
+    for on in (True, False):
+        seq = nn.Sequential(nl.SharableConv2d(C, K, 3, padding=1, bias=(K == 78)), nn.BatchNorm2d(K), nn.ReLU(inplace=True)).to(DEV)
+        with torch.no_grad():
+            seq[0].weight.copy_(w0)
+            if seq[0].bias is not None:
+                seq[0].bias.copy_(b0)
+            seq[1].weight.copy_(torch.linspace(0.5, 1.5, K)); seq[1].bias.copy_(torch.linspace(-0.3, 0.3, K))
+        assert fuse_bn_relu(seq, tf32_out=False) == (1, 0) and seq[0]._cpg_emit_colstats   # exact fp32 outputs
+        seq.train()
+        Fn.COLSTATS = on
+        try:
+            x = xv.clone().requires_grad_(True)
+            before = lib.cpgb_launch_count()
+            y = seq(x)
+            launches = lib.cpgb_launch_count() - before
+            y.backward(dy)
+        finally:
+            Fn.COLSTATS = True
+        torch.cuda.synchronize()
+        res[on] = (y.detach().clone(), x.grad.clone(), seq[0].weight.grad.clone(), seq[1].weight.grad.clone(),
+                   seq[1].running_mean.clone(), seq[1].running_var.clone(), launches)
+    a, b = res[True], res[False]
+    assert all(bool(torch.isfinite(t).all()) for t in a[:6] + b[:6])
+    big = N * HW * HW * ((K + 3) // 4 * 4) * 4 > 5e6            # above the single-launch batch-norm limit
+    assert a[6] == b[6] - (1 if big else 0), (a[6], b[6])
+    for name, u, v, tol in zip(('y', 'running_mean', 'running_var'), (a[0], a[4], a[5]), (b[0], b[4], b[5]), (2e-5, 1e-5, 1e-5)):
+        assert rel(u, v) <= tol, (name, rel(u, v))
+    # gradients in the L2 norm: the two arms' statistics differ in the last bits, which flips the recomputed ReLU gate
+    # of the odd element with |a * x + b| ~ 1e-7 and moves ITS gradient by a * dy (2 % of the max norm, seen once)
+    for name, u, v in zip(('dx', 'dW', 'dgamma'), a[1:4], b[1:4]):
+        l2 = ((u.double() - v.double()).norm() / v.double().norm()).item()
+        assert l2 <= 1e-3, (name, l2)
+    # and against the stock modules (fp32 convolution)
+    ref = nn.Sequential(nn.BatchNorm2d(K), nn.ReLU()).to(DEV)
+    with torch.no_grad():
+        ref[0].weight.copy_(seq[1].weight); ref[0].bias.copy_(seq[1].bias)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            yc = torch.nn.functional.conv2d(xv, w0, b0 if K == 78 else None, 1, 1)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert rel(a[0], ref(yc)) <= 3e-3
+    assert rel(a[4], ref[0].running_mean) <= 1e-3
