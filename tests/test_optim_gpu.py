@@ -173,6 +173,9 @@ def test_adam_emitted_mask_words_feed_the_in_tile_masked_layer():
     lib = _lib.load()
     torch.manual_seed(0)
     lin = nl.SharableLinear(512, 1024).to(DEV)
+    with torch.no_grad():                                  # the reference layer leaves its parameters uninitialised
+        lin.weight.normal_(0, 0.05)
+        lin.bias.normal_(0, 0.1)
     lin.piggymask = nn.Parameter((torch.rand(1024, 512) * 0.01).to(DEV))
     opt = Adam([lin.piggymask], lr=5e-4)
     assert opt.emit_packed_masks(lin) == 1
