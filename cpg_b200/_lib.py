@@ -116,6 +116,10 @@ def load():
                                             vp, vp, sz, vp]),
         'cpgb_bn_relu_bwd': (ctypes.c_int, [vp, vp, i64, i32, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp,
                                             vp, sz, vp]),
+        'cpgb_bn_add_relu_fwd': (ctypes.c_int, [vp, vp, i64, i32, i32, vp, vp, vp, vp, vp, i32, f32, f32, i32, vp, vp, vp,
+                                                vp, sz, vp]),
+        'cpgb_bn_add_relu_bwd': (ctypes.c_int, [vp, vp, vp, i64, i32, i32, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp,
+                                                sz, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -346,6 +346,67 @@ bn_bwd_apply_kernel(const NaGeom g, const float *__restrict__ x, const float *__
   }
 }
 
+// ---- residual add folded in (models/resnet.py:52-55, 95-98: out = bn(conv(..)); out += identity; out = relu(out)) ----
+// y = max(0, a*x + b + r).  The backward pass gates on the stored block output (y > 0, what torch's ReLU backward
+// reads): g = dy * [y > 0] is at once the gradient of the identity branch and the input of the batch-norm backward, so
+// the statistics kernel writes it out and bn_bwd_apply_kernel (relu = 0) finishes dx from it.
+__global__ void __launch_bounds__(NA_THREADS)
+bn_apply_res_kernel(const NaGeom g, const float *__restrict__ x, const float *__restrict__ res,
+                    const float *__restrict__ coef_a, const float *__restrict__ coef_b, int tf32,
+                    float *__restrict__ y) {
+  pdl_wait();
+  const int lane = threadIdx.x % g.lanes, slot = threadIdx.x / g.lanes;
+  const int c4 = blockIdx.y * g.lanes + lane;
+  if (slot >= g.slots || c4 * 4 >= g.Cs) return;
+  const float4 a = __ldg(reinterpret_cast<const float4 *>(coef_a) + c4);
+  const float4 b = __ldg(reinterpret_cast<const float4 *>(coef_b) + c4);
+  const float4 *xp = reinterpret_cast<const float4 *>(x) + c4;
+  const float4 *rp = reinterpret_cast<const float4 *>(res) + c4;
+  float4 *yp = reinterpret_cast<float4 *>(y) + c4;
+  const long long stride = (long long)gridDim.x * g.slots, cq = g.Cs / 4;
+#pragma unroll 4
+  for (long long r = (long long)blockIdx.x * g.slots + slot; r < g.M; r += stride) {
+    const float4 v = pad0(__ldg(xp + r * cq), c4, g.C), w = pad0(__ldg(rp + r * cq), c4, g.C);
+    float4 o = make_float4(fmaf(v.x, a.x, b.x) + w.x, fmaf(v.y, a.y, b.y) + w.y, fmaf(v.z, a.z, b.z) + w.z,
+                           fmaf(v.w, a.w, b.w) + w.w);
+    o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+    yp[r * cq] = na_out(o, tf32);
+  }
+}
+
+__global__ void __launch_bounds__(NA_STATS_THREADS)
+bn_bwd_stats_res_kernel(const NaGeom g, const float *__restrict__ x, const float *__restrict__ y,
+                        const float *__restrict__ dy, const float *__restrict__ save_mean,
+                        const float *__restrict__ save_rstd, float *__restrict__ gout, float *__restrict__ part) {
+  pdl_wait();
+  const int lane = threadIdx.x % g.lanes, slot = threadIdx.x / g.lanes;
+  const int c4 = blockIdx.y * g.lanes + lane;
+  const bool active = slot < g.slots && c4 * 4 < g.Cs;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+  if (active) {
+    const float4 mu = ldp4(save_mean, c4, g.C, 0.f);
+    const float4 rs = ldp4(save_rstd, c4, g.C, 0.f);
+    const float4 *xp = reinterpret_cast<const float4 *>(x) + c4;
+    const float4 *yp = reinterpret_cast<const float4 *>(y) + c4;
+    const float4 *dp = reinterpret_cast<const float4 *>(dy) + c4;
+    float4 *gp = reinterpret_cast<float4 *>(gout) + c4;
+    const long long stride = (long long)gridDim.x * g.slots, cq = g.Cs / 4;
+#pragma unroll 4
+    for (long long r = (long long)blockIdx.x * g.slots + slot; r < g.M; r += stride) {
+      const float4 v = pad0(__ldg(xp + r * cq), c4, g.C), o = pad0(__ldg(yp + r * cq), c4, g.C),
+                   d = pad0(__ldg(dp + r * cq), c4, g.C);
+      float4 gg;
+      gg.x = o.x > 0.f ? d.x : 0.f; gg.y = o.y > 0.f ? d.y : 0.f;
+      gg.z = o.z > 0.f ? d.z : 0.f; gg.w = o.w > 0.f ? d.w : 0.f;
+      gp[r * cq] = gg;
+      s.x += gg.x; s.y += gg.y; s.z += gg.z; s.w += gg.w;
+      q.x = fmaf(gg.x, (v.x - mu.x) * rs.x, q.x); q.y = fmaf(gg.y, (v.y - mu.y) * rs.y, q.y);
+      q.z = fmaf(gg.z, (v.z - mu.z) * rs.z, q.z); q.w = fmaf(gg.w, (v.w - mu.w) * rs.w, q.w);
+    }
+  }
+  block_reduce_pairs(g, s, q, lane, slot, c4, active, part);
+}
+
 // ---- 2x2 / stride-2 max-pool folded in (models/vgg.py 'M' entries follow conv -> BN -> ReLU directly) ----
 // Rows are POOLED pixels; a thread reads the four window pixels of its channels.  pool(relu(z)) ==
 // relu(max z), and the gradient of a window goes to its first maximum in (h, w) scan order -- the element
@@ -1062,6 +1123,78 @@ int cpgb_bn_relu_bwd(const float *x, const float *dy, int64_t M, int32_t C, int3
     CPGB_CUDA_OK(launch_dependent(bn_bwd_apply_kernel, dim3(dim3(na_blocks(g, 8), g.cchunks)), dim3(NA_THREADS), 0, st, g, x, dy, gamma, beta, mean, rstd, c1, c2,
                                                                                 relu, tf32_out, dx));
   }
+  CPGB_LAUNCH_OK("bn_bwd_apply");
+  return CPGB_OK;
+}
+
+int cpgb_bn_add_relu_fwd(const float *x, const float *res, int64_t M, int32_t C, int32_t ldc, const float *gamma,
+                         const float *beta, float *running_mean, float *running_var, int64_t *num_batches_tracked,
+                         int32_t training, float momentum, float eps, int32_t tf32_out, float *y, float *save_mean,
+                         float *save_rstd, void *ws, size_t ws_bytes, void *stream) {
+  const int Cs = na_stride(C, ldc);
+  if (!na_args_ok(x, M, C, Cs) || !y || !res || (reinterpret_cast<uintptr_t>(y) & 15) ||
+      (reinterpret_cast<uintptr_t>(res) & 15)) {
+    set_error("cpgb_bn_add_relu_fwd: needs NHWC fp32 with a pixel stride that is a multiple of 4 and 16-byte aligned x / res / y");
+    return CPGB_EINVAL;
+  }
+  if (!ws || ws_bytes < na_ws_bytes(M, Cs) || (reinterpret_cast<uintptr_t>(ws) & 15)) {
+    set_error("cpgb_bn_add_relu_fwd: workspace %zu < %zu", ws_bytes, na_ws_bytes(M, Cs)); return CPGB_EWORKSPACE;
+  }
+  if (training ? (!save_mean || !save_rstd) : (!running_mean || !running_var)) {
+    set_error("cpgb_bn_add_relu_fwd: missing statistics buffers"); return CPGB_EINVAL;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  NaGeom g = na_geom(M, C, Cs);
+  float *coef_a = reinterpret_cast<float *>(ws), *coef_b = coef_a + Cs, *part = coef_a + 4 * Cs;
+  if (training) {
+    const NaGeom gs = na_geom(M, C, Cs, NA_STATS_THREADS);
+    const int nb = na_blocks(gs, NA_STATS_PER_SM);
+    CPGB_CUDA_OK(launch_dependent(bn_stats_kernel, dim3(nb, gs.cchunks), dim3(NA_STATS_THREADS), 0, st, gs, x, part));
+    CPGB_LAUNCH_OK("bn_stats");
+    CPGB_CUDA_OK(launch_dependent(bn_finalize_kernel, dim3((Cs + 7) / 8), dim3(256), 0, st, (const float *)part, nb, C, Cs,
+                                  (long long)M, gamma, beta, running_mean, running_var, momentum, eps, save_mean, save_rstd,
+                                  coef_a, coef_b, reinterpret_cast<long long *>(num_batches_tracked)));
+    CPGB_LAUNCH_OK("bn_finalize");
+  } else {
+    CPGB_CUDA_OK(launch_dependent(bn_eval_coef_kernel, dim3((Cs + 127) / 128), dim3(128), 0, st, C, Cs, gamma, beta,
+                                  (const float *)running_mean, (const float *)running_var, eps, coef_a, coef_b));
+    CPGB_LAUNCH_OK("bn_eval_coef");
+  }
+  CPGB_CUDA_OK(launch_dependent(bn_apply_res_kernel, dim3(na_blocks(g, 8), g.cchunks), dim3(NA_THREADS), 0, st, g, x, res,
+                                (const float *)coef_a, (const float *)coef_b, tf32_out, y));
+  CPGB_LAUNCH_OK("bn_apply_res");
+  return CPGB_OK;
+}
+
+int cpgb_bn_add_relu_bwd(const float *x, const float *y, const float *dy, int64_t M, int32_t C, int32_t ldc,
+                         const float *gamma, const float *beta, const float *mean, const float *rstd, int32_t training,
+                         int32_t tf32_out, float *dx, float *dres, float *dgamma, float *dbeta, void *ws, size_t ws_bytes,
+                         void *stream) {
+  const int Cs = na_stride(C, ldc);
+  if (!na_args_ok(x, M, C, Cs) || !y || !dy || !dx || !dres || !mean || !rstd || (reinterpret_cast<uintptr_t>(y) & 15) ||
+      (reinterpret_cast<uintptr_t>(dy) & 15) || (reinterpret_cast<uintptr_t>(dx) & 15) ||
+      (reinterpret_cast<uintptr_t>(dres) & 15)) {
+    set_error("cpgb_bn_add_relu_bwd: needs NHWC fp32 with a pixel stride that is a multiple of 4 and 16-byte aligned tensors");
+    return CPGB_EINVAL;
+  }
+  if (!ws || ws_bytes < na_ws_bytes(M, Cs) || (reinterpret_cast<uintptr_t>(ws) & 15)) {
+    set_error("cpgb_bn_add_relu_bwd: workspace %zu < %zu", ws_bytes, na_ws_bytes(M, Cs)); return CPGB_EWORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  NaGeom g = na_geom(M, C, Cs);
+  float *c1 = reinterpret_cast<float *>(ws) + 2 * Cs, *c2 = c1 + Cs, *part = c2 + Cs;
+  const NaGeom gs = na_geom(M, C, Cs, NA_STATS_THREADS);
+  const int nb = na_blocks(gs, NA_STATS_PER_SM);
+  CPGB_CUDA_OK(launch_dependent(bn_bwd_stats_res_kernel, dim3(nb, gs.cchunks), dim3(NA_STATS_THREADS), 0, st, gs, x, y, dy,
+                                mean, rstd, dres, part));
+  CPGB_LAUNCH_OK("bn_bwd_stats_res");
+  CPGB_CUDA_OK(launch_dependent(bn_bwd_finalize_kernel, dim3((Cs + 7) / 8), dim3(256), 0, st, (const float *)part, nb, C, Cs,
+                                (long long)M, (int)training, dgamma, dbeta, c1, c2));
+  CPGB_LAUNCH_OK("bn_bwd_finalize");
+  // dx = a * (g - c1 - xhat * c2) from the gated gradient just written: the plain batch-norm backward, no ReLU gate
+  CPGB_CUDA_OK(launch_dependent(bn_bwd_apply_kernel, dim3(na_blocks(g, 8), g.cchunks), dim3(NA_THREADS), 0, st, g, x,
+                                (const float *)dres, gamma, beta, mean, rstd, (const float *)c1, (const float *)c2, 0,
+                                tf32_out, dx));
   CPGB_LAUNCH_OK("bn_bwd_apply");
   return CPGB_OK;
 }

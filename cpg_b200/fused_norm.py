@@ -90,6 +90,69 @@ class _BNReLUFn(torch.autograd.Function):
         return dx, dg, db, None, None, None, None, None, None, None, None, None, None
 
 
+class _BNAddReLUFn(torch.autograd.Function):
+    """y = relu(batch_norm(x) + res): the tail of a residual block (models/resnet.py:50-55, 92-98)."""
+
+    @staticmethod
+    def forward(ctx, x, res, weight, bias, running_mean, running_var, nbt, training, momentum, eps, tf32_out=False):
+        lib = _lib.load()
+        x = to_nhwc_aligned(x)
+        ldc = nhwc_pixel_stride(x)
+        res = to_nhwc_aligned(res)
+        if nhwc_pixel_stride(res) != ldc:
+            t = empty_nhwc(res.shape, res.device, ldc)
+            t.copy_(res)
+            res = t
+        N, C, H, W = x.shape
+        M = N * H * W
+        y = empty_nhwc((N, C, H, W), x.device, ldc)
+        w = weight.detach().contiguous() if weight is not None else None
+        b = bias.detach().contiguous() if bias is not None else None
+        with torch.cuda.device(x.device):
+            ws = torch.empty(lib.cpgb_bn_workspace_bytes(M, ldc), dtype=torch.uint8, device=x.device)
+            if training:
+                mean = torch.empty(C, dtype=torch.float32, device=x.device)
+                rstd = torch.empty(C, dtype=torch.float32, device=x.device)
+            else:
+                mean, rstd = running_mean, torch.rsqrt(running_var + eps)
+            _lib.check(lib.cpgb_bn_add_relu_fwd(
+                _lib.ptr(x), _lib.ptr(res), M, C, ldc, _lib.ptr(w), _lib.ptr(b), _lib.ptr(running_mean),
+                _lib.ptr(running_var), _lib.ptr(nbt) if training else None, 1 if training else 0, float(momentum),
+                float(eps), 1 if tf32_out else 0, _lib.ptr(y), _lib.ptr(mean) if training else None,
+                _lib.ptr(rstd) if training else None, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), 'cpgb_bn_add_relu_fwd')
+        ctx.save_for_backward(x, y, w, b, mean, rstd)
+        ctx.cfg = (bool(training), weight is not None, bias is not None)
+        ctx.cpgb_tf32_out = bool(tf32_out)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x, y, w, b, mean, rstd = ctx.saved_tensors
+        training, has_w, has_b = ctx.cfg
+        ldc = nhwc_pixel_stride(x)
+        if nhwc_pixel_stride(dy) != ldc:
+            t = empty_nhwc(dy.shape, dy.device, ldc)
+            t.copy_(dy)
+            dy = t
+        N, C, H, W = x.shape
+        M = N * H * W
+        dx = empty_like_padded(x)
+        dres = empty_like_padded(x)
+        dg = torch.empty(C, dtype=torch.float32, device=x.device) if has_w else None
+        db = torch.empty(C, dtype=torch.float32, device=x.device) if has_b else None
+        with torch.cuda.device(x.device):
+            ws = torch.empty(lib.cpgb_bn_workspace_bytes(M, ldc), dtype=torch.uint8, device=x.device)
+            _lib.check(lib.cpgb_bn_add_relu_bwd(
+                _lib.ptr(x), _lib.ptr(y), _lib.ptr(dy), M, C, ldc, _lib.ptr(w), _lib.ptr(b), _lib.ptr(mean),
+                _lib.ptr(rstd), 1 if training else 0, 1 if ctx.cpgb_tf32_out else 0, _lib.ptr(dx), _lib.ptr(dres),
+                _lib.ptr(dg), _lib.ptr(db), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), 'cpgb_bn_add_relu_bwd')
+        if ctx.cpgb_tf32_out:
+            mark_tf32(dx)
+        return dx, dres, dg, db, None, None, None, None, None, None, None
+
+
 class FusedBatchNormReLU2d(nn.BatchNorm2d):
     """``nn.BatchNorm2d`` with an optional fused ReLU (``relu=True``: y = relu(batch_norm(x)))."""
 
@@ -127,10 +190,16 @@ class FusedBatchNormReLU2d(nn.BatchNorm2d):
             return False          # cumulative average needs the step count on the host
         return True
 
-    def forward(self, x):
+    def forward(self, x, relu=None, residual=None):
+        """`relu` overrides the module's flag for this call; `residual` (a tensor of x's shape) selects
+        y = relu(batch_norm(x) + residual), the tail of a residual block -- both are what fuse_resnet_blocks' block
+        forward passes; a plain `bn(x)` call behaves as the constructor arguments say."""
+        relu = self.relu if relu is None else bool(relu)
+        if residual is not None:
+            return self._forward_residual(x, residual)
         if not self._fast(x):
             y = super().forward(x)
-            y = F.relu(y) if self.relu else y
+            y = F.relu(y) if relu else y
             return F.max_pool2d(y, 2, 2) if self.pool else y
         self._check_input_dim(x)
         training = self.training or (self.running_mean is None and self.running_var is None)
@@ -154,11 +223,34 @@ class FusedBatchNormReLU2d(nn.BatchNorm2d):
                     nhwc_pixel_stride(x) == (x.shape[1] + 3) // 4 * 4):
                 colstats = cs
         y = _BNReLUFn.apply(x, self.weight, self.bias, rm, rv, nbt, training,
-                            self.momentum if self.momentum is not None else 0.0, self.eps, self.relu, pool,
+                            self.momentum if self.momentum is not None else 0.0, self.eps, relu, pool,
                             self.tf32_out, colstats)
         if self.tf32_out:
             mark_tf32(y)
         return F.max_pool2d(y, 2, 2) if (self.pool and not pool) else y
+
+    def _forward_residual(self, x, residual):
+        if self.pool:
+            raise ValueError('a pooling batch-norm cannot take a residual')
+        if not (self._fast(x) and residual.is_cuda and residual.dtype == torch.float32 and residual.shape == x.shape and
+                residual.device == x.device):
+            return F.relu(super().forward(x) + residual)
+        self._check_input_dim(x)
+        training = self.training or (self.running_mean is None and self.running_var is None)
+        if training and x.numel() // x.shape[1] <= 1:
+            raise ValueError(f'Expected more than 1 value per channel when training, got input size {x.size()}')
+        update = self.training and self.track_running_stats
+        nbt = self.num_batches_tracked if (update and self.num_batches_tracked is not None and
+                                           self.num_batches_tracked.device == x.device) else None
+        if update and self.num_batches_tracked is not None and nbt is None:
+            self.num_batches_tracked.add_(1)
+        rm = self.running_mean if (not training or update) else None
+        rv = self.running_var if (not training or update) else None
+        y = _BNAddReLUFn.apply(x, residual, self.weight, self.bias, rm, rv, nbt, training,
+                               self.momentum if self.momentum is not None else 0.0, self.eps, self.tf32_out)
+        if self.tf32_out:
+            mark_tf32(y)
+        return y
 
 
 class _PReLUFn(torch.autograd.Function):
@@ -281,3 +373,77 @@ def _is_pool2x2(m):
         return v == 2 or v == (2, 2)
     return (type(m) is nn.MaxPool2d and two(m.kernel_size) and two(m.stride) and m.padding in (0, (0, 0)) and
             m.dilation in (1, (1, 1)) and not m.ceil_mode and not m.return_indices)
+
+
+# ---- residual blocks (models/resnet.py:41-57 BasicBlock.forward, :79-100 Bottleneck.forward) ----
+# The blocks call their modules from hand-written forward() code, so fuse_bn_relu can only swap the batch-norms in
+# place (the ReLU after bn1 / bn2, the residual add and the final ReLU stay torch kernels: 12 % of a ResNet-50 step).
+# fuse_resnet_blocks gives every block an equivalent forward() that passes the ReLU and the residual INTO the
+# batch-norm kernels; module tree, parameter names, state_dict and mask keys are untouched.
+def _basic_block_forward(self, x):
+    identity = x
+    out = self.bn1(self.conv1(x), relu=True)
+    out = self.conv2(out)
+    if self.downsample is not None:
+        identity = self.downsample(x)
+    return self.bn2(out, residual=identity)
+
+
+def _bottleneck_forward(self, x):
+    identity = x
+    out = self.bn1(self.conv1(x), relu=True)
+    out = self.bn2(self.conv2(out), relu=True)
+    out = self.conv3(out)
+    if self.downsample is not None:
+        identity = self.downsample(x)
+    return self.bn3(out, residual=identity)
+
+
+def fuse_resnet_blocks(model, tf32_out=True):
+    """Rewrite the forward pass of every `BasicBlock` / `Bottleneck` of the reference's models/resnet.py inside
+    `model` (matched by class name and attribute surface) so that `bn -> relu` and `bn -> (+ identity) -> relu` run
+    inside the batch-norm kernels (cpgb_bn_relu_fwd with relu = 1, cpgb_bn_add_relu_fwd).  Batch-norms of the blocks that
+    are still stock `nn.BatchNorm2d` are converted as fuse_bn_relu does.  Returns the number of blocks rewritten."""
+    n = 0
+    for m in model.modules():
+        if getattr(type(m), '_cpgb_fused_block', False):
+            continue
+        kind = type(m).__name__
+        if kind == 'BasicBlock':
+            bns, fwd = ('bn1', 'bn2'), _basic_block_forward
+            need = ('conv1', 'bn1', 'conv2', 'bn2', 'relu', 'downsample')
+        elif kind == 'Bottleneck':
+            bns, fwd = ('bn1', 'bn2', 'bn3'), _bottleneck_forward
+            need = ('conv1', 'bn1', 'conv2', 'bn2', 'conv3', 'bn3', 'relu', 'downsample')
+        else:
+            continue
+        if not all(hasattr(m, a) for a in need) or type(m.relu) is not nn.ReLU:
+            continue
+        if not all(type(getattr(m, b)) in (nn.BatchNorm2d, FusedBatchNormReLU2d) for b in bns):
+            continue
+        for b in bns:
+            bn = getattr(m, b)
+            if type(bn) is nn.BatchNorm2d:
+                m._modules[b] = FusedBatchNormReLU2d.from_bn(bn, relu=False, tf32_out=tf32_out)
+        if any(getattr(m, b).pool for b in bns):
+            continue
+        m.__class__ = _fused_block_class(type(m), fwd)
+        n += 1
+    return n
+
+
+_FUSED_BLOCK_CLASSES = {}
+
+
+def _fused_block_class(base, fwd):
+    """Subclass of the block class `base` whose only difference is the forward pass (a class, not an instance
+    attribute: nn.DataParallel replicas copy __dict__, and a bound method stored there would run the original
+    module).  Registered in this module's namespace so that a pickled model finds it again."""
+    cls = _FUSED_BLOCK_CLASSES.get(base)
+    if cls is None:
+        name = 'Fused' + base.__name__ + '_' + str(len(_FUSED_BLOCK_CLASSES))
+        cls = type(name, (base,), {'forward': fwd, '_cpgb_fused_block': True, '__module__': __name__})
+        cls.__qualname__ = name
+        globals()[name] = cls
+        _FUSED_BLOCK_CLASSES[base] = cls
+    return cls

@@ -34,6 +34,7 @@ class _SharableBase(nn.Module):
         self._cpg_grads_final = False
         self._cpg_prestaged = None    # (buffer, weight ptr, piggymask ptr): one-shot, set by the model-level hook
         self._cpg_grad_slot = None    # set by cpg_b200.ddp.GradAllReducer: where the wgrad epilogue writes
+        self._cpg_task_view = None    # set by cpg_b200.prune.SparsePruner.select_task: W * [1 <= T <= task], eval only
 
     def _finish_init(self, threshold_fn, threshold):
         # Give real-valued mask weights per task to manage the shared part from previous tasks:
@@ -86,12 +87,32 @@ class _SharableBase(nn.Module):
                 torch.cuda.current_stream().wait_event(ev)
         return buf
 
+    def _task_weight(self):
+        """The weight tensor of this forward pass: `self.weight`, or -- in evaluation mode, after
+        SparsePruner.select_task(t) -- the resident copy W * [1 <= T <= t] of it (what utils/prune.py:223-231 leaves
+        in `weight.data`, without destroying the later tasks' weights)."""
+        view = getattr(self, '_cpg_task_view', None)
+        if view is None or self.training:
+            return self.weight
+        if view.device != self.weight.device or view.shape != self.weight.shape:
+            raise _lib.CpgbError('the task view of this layer was built for another device or shape '
+                                 '(nn.DataParallel replica?): call SparsePruner.select_task() again')
+        return view
+
     def _effective(self):
         """(weight, piggymask) to hand to the fused kernels.  The ternarizer (dead code in the
         reference) is applied with torch ops and then treated as 'no piggymask'."""
+        weight = self._task_weight()
         if self.piggymask is not None and self.info['threshold_fn'] != 'binarizer':
-            return self.threshold_fn(self.piggymask, self.info['threshold']) * self.weight, None
-        return self.weight, self.piggymask
+            return self.threshold_fn(self.piggymask, self.info['threshold']) * weight, None
+        return weight, self.piggymask
+
+    def _staged_for(self, weight, piggy):
+        """The batched staging's operand for `weight` if the model-level hook built one (it stages the tensor
+        _task_weight() returns)."""
+        if weight is self.weight or weight is getattr(self, '_cpg_task_view', None):
+            return self._take_prestaged(weight, piggy)
+        return None
 
 
 class SharableConv2d(_SharableBase):
@@ -132,7 +153,7 @@ class SharableConv2d(_SharableBase):
     def forward(self, input, layer_info=None, name=None):
         weight, piggy = self._effective()
         fuse = self._fuse_ctx() if piggy is self.piggymask and weight is self.weight else None
-        pre = self._take_prestaged(weight, piggy) if weight is self.weight else None
+        pre = self._staged_for(weight, piggy)
         return MaskedConv2dFn.apply(input, weight, piggy, self.bias, self.stride, self.padding,
                                     self.dilation, self.groups, float(self.info['threshold']), fuse,
                                     self._owner(weight), OUTPUT_CHANNELS_LAST, pre, is_tf32(input),
@@ -175,7 +196,7 @@ class SharableLinear(_SharableBase):
     def forward(self, input):
         weight, piggy = self._effective()
         fuse = self._fuse_ctx() if piggy is self.piggymask and weight is self.weight else None
-        pre = self._take_prestaged(weight, piggy) if weight is self.weight else None
+        pre = self._staged_for(weight, piggy)
         return MaskedLinearFn.apply(input, weight, piggy, self.bias, float(self.info['threshold']), fuse,
                                     self._owner(weight), pre, is_tf32(input))
 

@@ -25,7 +25,28 @@ from .functional import FuseCtx, _side_stream
 # saves.  Off by default; CPGB_STAGE_SIDE=1 turns it on.
 STAGE_ON_SIDE_STREAM = os.environ.get('CPGB_STAGE_SIDE', '0') == '1'
 
+# `apply_mask()` (utils/prune.py:223-231) destroys the weights of the tasks after
+# `inference_dataset_idx` in memory, so evaluating task j of a model that holds t > j tasks means reloading the
+# checkpoint per task.  With this switch on (CPGB_NONDESTRUCTIVE_EVAL=1) `apply_mask()` leaves `weight.data` alone and
+# calls `select_task()` instead: evaluation-mode forward passes read W * [1 <= T <= idx] from a resident copy.  Off by
+# default: during training the reference relies on the destructive call to zero freshly pruned weights at every
+# validation (utils/manager.py:105), and a drop-in must reproduce that trajectory.
+NONDESTRUCTIVE_APPLY_MASK = os.environ.get('CPGB_NONDESTRUCTIVE_EVAL', '0') == '1'
+
 _MODES = {'finetune': _lib.GRAD_FINETUNE, 'prune': _lib.GRAD_PRUNE}
+
+
+class _TaskView(object):
+    def __init__(self, pruner, idx):
+        self.pruner, self.idx = pruner, idx
+
+    def __enter__(self):
+        self.pruner.select_task(self.idx)
+        return self.pruner
+
+    def __exit__(self, *exc):
+        self.pruner.clear_task_view()
+        return False
 
 
 class SparsePruner(object):
@@ -62,6 +83,7 @@ class SparsePruner(object):
         self._stage_events = {}
         self._stage_hook = None
         self._stage_post_hook = None
+        self._task_view_idx = None      # task of the resident evaluation view (select_task), None = no view
         self.attach()
         return
 
@@ -121,7 +143,7 @@ class SparsePruner(object):
         lib = _lib.load()
         items = []
         for name, m in self._sharable():
-            w = m.weight
+            w = m._task_weight()        # the resident task view in evaluation mode after select_task(), else m.weight
             if not w.is_cuda or w.dtype != torch.float32 or not w.is_contiguous() or m.info['threshold_fn'] != 'binarizer':
                 continue
             if w.dim() == 4:
@@ -431,8 +453,54 @@ class SparsePruner(object):
 
     def apply_mask(self):
         """To be done to retrieve weights just for a particular dataset.  (utils/prune.py:223-231)"""
+        if NONDESTRUCTIVE_APPLY_MASK:
+            self.select_task(self.inference_dataset_idx)
+            return
+        if self._task_view_idx is not None:
+            self.clear_task_view()  # a view taken before this call would show weights that no longer exist
         self._zero_weights(self.inference_dataset_idx)
         return
+
+    # ------------------------------------------------------------------ N4: non-destructive evaluation predicate
+    def select_task(self, inference_dataset_idx=None):
+        """Non-destructive twin of `apply_mask()`: every sharable layer gets a resident copy
+        W * [1 <= T <= inference_dataset_idx] of its weights (the tensor utils/prune.py:229-230 would leave in
+        `weight.data`) which its forward pass reads in evaluation mode; `weight.data` itself -- and with it the
+        weights of the later tasks -- stays as it is, so one resident model serves every task it holds:
+        `select_task(j)` per task instead of a checkpoint reload.  Training-mode forward passes ignore the view.
+        The copy is a snapshot: call again after the weights or the masks have changed (the per-task batch-norm /
+        bias / PReLU tensors are the caller's to re-bind, as in utils/manager.py:266-320).  One copy + one
+        `cpgb_apply_mask` launch per layer per call, nothing per forward pass."""
+        assert self.masks
+        idx = self.inference_dataset_idx if inference_dataset_idx is None else int(inference_dataset_idx)
+        lib = _lib.load()
+        for name, module in self._sharable():
+            weight = self._dense(module.weight.data, 'weight')
+            mask = self._mask(name)
+            if mask.device != weight.device:
+                mask = mask.to(weight.device)
+            view = module._cpg_task_view
+            if view is None or view.shape != weight.shape or view.device != weight.device:
+                view = torch.empty_like(weight)
+            view.copy_(weight)
+            with torch.cuda.device(weight.device):
+                _lib.check(lib.cpgb_apply_mask(_lib.ptr(view), _lib.ptr(mask), view.numel(), idx, _lib.stream_ptr()),
+                           'cpgb_apply_mask')
+            module._cpg_task_view = view
+            module._cpg_prestaged = None
+        self._task_view_idx = idx
+        return idx
+
+    def clear_task_view(self):
+        """Drop the copies `select_task()` made: evaluation reads `weight.data` again."""
+        for name, module in self._sharable():
+            module._cpg_task_view = None
+            module._cpg_prestaged = None
+        self._task_view_idx = None
+
+    def task_view(self, inference_dataset_idx=None):
+        """`with pruner.task_view(j): validate(...)` -- select_task(j) on entry, clear_task_view() on exit."""
+        return _TaskView(self, inference_dataset_idx)
 
     def make_finetuning_mask(self):
         """Turns previously pruned weights into trainable weights for

@@ -333,6 +333,25 @@ int cpgb_bn_relu_bwd(const float *x, const float *dy, int64_t M, int32_t C, int3
                      int32_t pool_h, int32_t pool_w, int32_t tf32_out, float *dx, float *dgamma, float *dbeta, void *ws,
                      size_t ws_bytes, void *stream);
 
+/* SURVEY 8(f) N4, ResNet blocks: the last batch-norm of a block is followed by the residual add and the ReLU
+ * (models/resnet.py:50-55 BasicBlock, :92-98 Bottleneck: out = bn(out); out += identity; out = relu(out)).
+ *   forward : y = max(0, batch_norm(x) + res)          -- statistics / running statistics / save_* / ldc / tf32_out
+ *                                                          exactly as cpgb_bn_relu_fwd; res has x's layout
+ *   backward: g = dy * [y > 0] (y: the stored output of the forward call -- what torch's ReLU backward gates on);
+ *             dres = g (gradient of the identity branch);  dbeta = sum g;  dgamma = sum g * xhat;
+ *             dx = gamma * rstd * (g - mean(g) - xhat * mean(g * xhat))  (training; evaluation: gamma * rstd * g).
+ * Three launches per direction (stats -> finalize -> apply); the three separate passes of the stock modules (batch-norm,
+ * add, ReLU) read and write the tensor 5 + 3 times in the forward direction, this reads it 3 times and writes it once.
+ * ws: cpgb_bn_workspace_bytes(M, C). */
+int cpgb_bn_add_relu_fwd(const float *x, const float *res, int64_t M, int32_t C, int32_t ldc, const float *gamma,
+                         const float *beta, float *running_mean, float *running_var, int64_t *num_batches_tracked,
+                         int32_t training, float momentum, float eps, int32_t tf32_out, float *y, float *save_mean,
+                         float *save_rstd, void *ws, size_t ws_bytes, void *stream);
+int cpgb_bn_add_relu_bwd(const float *x, const float *y, const float *dy, int64_t M, int32_t C, int32_t ldc,
+                         const float *gamma, const float *beta, const float *mean, const float *rstd, int32_t training,
+                         int32_t tf32_out, float *dx, float *dres, float *dgamma, float *dbeta, void *ws, size_t ws_bytes,
+                         void *stream);
+
 /* SURVEY 8(f) N4, SphereNet-20: every masked convolution feeds nn.PReLU(channels) (models/spherenet.py:204-249).
  * NHWC fp32 activations as [M][C] with pixel stride ldc (0 = dense), alpha[C]:
  *   y = x > 0 ? x : alpha[c] * x;   dx = x > 0 ? dy : alpha[c] * dy;   dalpha[c] = sum_pixels (x > 0 ? 0 : x * dy)

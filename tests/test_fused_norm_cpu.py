@@ -65,3 +65,100 @@ def test_fuse_handles_attribute_style_blocks():
     x = torch.randn(2, 4, 5, 5)
     assert torch.equal(a(x), b(x))
     assert list(a.state_dict().keys()) == list(b.state_dict().keys())
+
+
+def _blocks():
+    """Blocks with the attribute surface and forward code of models/resnet.py:20-100 (stock convolutions)."""
+    class BasicBlock(nn.Module):
+        def __init__(self, c, down):
+            super().__init__()
+            self.conv1 = nn.Conv2d(c, c, 3, stride=2 if down else 1, padding=1, bias=False)
+            self.bn1 = nn.BatchNorm2d(c)
+            self.relu = nn.ReLU(inplace=True)
+            self.conv2 = nn.Conv2d(c, c, 3, padding=1, bias=False)
+            self.bn2 = nn.BatchNorm2d(c)
+            self.downsample = nn.Sequential(nn.Conv2d(c, c, 1, stride=2, bias=False), nn.BatchNorm2d(c)) if down else None
+
+        def forward(self, x):
+            identity = x
+            out = self.relu(self.bn1(self.conv1(x)))
+            out = self.bn2(self.conv2(out))
+            if self.downsample is not None:
+                identity = self.downsample(x)
+            out += identity
+            return self.relu(out)
+
+    class Bottleneck(nn.Module):
+        def __init__(self, c, down):
+            super().__init__()
+            self.conv1 = nn.Conv2d(c, c // 2, 1, bias=False)
+            self.bn1 = nn.BatchNorm2d(c // 2)
+            self.conv2 = nn.Conv2d(c // 2, c // 2, 3, stride=2 if down else 1, padding=1, bias=False)
+            self.bn2 = nn.BatchNorm2d(c // 2)
+            self.conv3 = nn.Conv2d(c // 2, c, 1, bias=False)
+            self.bn3 = nn.BatchNorm2d(c)
+            self.relu = nn.ReLU(inplace=True)
+            self.downsample = nn.Sequential(nn.Conv2d(c, c, 1, stride=2, bias=False), nn.BatchNorm2d(c)) if down else None
+
+        def forward(self, x):
+            identity = x
+            out = self.relu(self.bn1(self.conv1(x)))
+            out = self.relu(self.bn2(self.conv2(out)))
+            out = self.bn3(self.conv3(out))
+            if self.downsample is not None:
+                identity = self.downsample(x)
+            out += identity
+            return self.relu(out)
+
+    return BasicBlock, Bottleneck
+
+
+def test_fuse_resnet_blocks_keeps_names_and_results():
+    """The rewritten block forward (ReLU and residual passed into the batch-norm modules) equals the reference's
+    forward code; on the CPU the modules run stock torch, so bit for bit."""
+    from cpg_b200.fused_norm import fuse_resnet_blocks
+    BasicBlock, Bottleneck = _blocks()
+    torch.manual_seed(3)
+
+    def net():
+        return nn.Sequential(BasicBlock(8, False), BasicBlock(8, True), Bottleneck(8, False), Bottleneck(8, True))
+    ref, new = net(), net()
+    new.load_state_dict(ref.state_dict())
+    keys = list(new.state_dict().keys())
+    fuse_bn_relu(new[0])                                   # blocks already converted by fuse_bn_relu are taken as well
+    assert fuse_resnet_blocks(new) == 4
+    assert fuse_resnet_blocks(new) == 0                    # idempotent
+    assert list(new.state_dict().keys()) == keys
+    assert all(isinstance(b, (BasicBlock, Bottleneck)) for b in new)     # still the reference's classes (subclassed)
+    import copy
+    assert type(copy.deepcopy(new)[2]) is type(new[2])
+    assert all(isinstance(m, FusedBatchNormReLU2d) for b in new for m in (b.bn1, b.bn2))
+    assert all(isinstance(b.downsample[1], nn.BatchNorm2d) for b in new if b.downsample is not None)
+    x = torch.randn(4, 8, 12, 12)
+    for train in (True, False):
+        ref.train(train); new.train(train)
+        xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+        ya, yb = ref(xa), new(xb)
+        assert torch.equal(ya, yb)
+        (ya * ya).sum().backward(); (yb * yb).sum().backward()
+        assert torch.equal(xa.grad, xb.grad)
+        for pa, pb in zip(ref.parameters(), new.parameters()):
+            assert torch.equal(pa.grad, pb.grad)
+    for (ka, va), (kb, vb) in zip(ref.state_dict().items(), new.state_dict().items()):
+        assert ka == kb and torch.equal(va, vb), ka
+
+
+def test_fuse_resnet_blocks_skips_what_it_does_not_know():
+    from cpg_b200.fused_norm import fuse_resnet_blocks
+
+    class Bottleneck(nn.Module):                            # same name, different surface (no bn3 / relu attribute)
+        def __init__(self):
+            super().__init__()
+            self.conv1 = nn.Conv2d(4, 4, 1)
+            self.bn1 = nn.GroupNorm(2, 4)
+
+        def forward(self, x):
+            return self.bn1(self.conv1(x))
+
+    m = nn.Sequential(Bottleneck())
+    assert fuse_resnet_blocks(m) == 0 and type(m[0]) is Bottleneck
