@@ -85,6 +85,9 @@ def _build(workload, device, regime):
                 nn.init.kaiming_normal_(m.weight, mode='fan_out', nonlinearity='relu')
     model = model.to(device)
     fuse_bn_relu(model)
+    if os.environ.get('CPGB_FUSE_RESNET_BLOCKS', '1') != '0':
+        from cpg_b200.fused_norm import fuse_resnet_blocks
+        fuse_resnet_blocks(model)             # ResNet: bn -> relu and bn -> (+ identity) -> relu inside the batch-norm kernels
     if os.environ.get('CPGB_FUSE_PRELU', '1') != '0':
         fuse_prelu(model)                     # SphereNet-20: nn.PReLU after every masked convolution
     cur = len(datasets)

@@ -110,6 +110,13 @@ assert len(convs) == 13 and len(lins) == 2, (len(convs), len(lins))
 assert sorted(k for k in convs[0].state_dict()) == ['weight'] and convs[0].piggymask is None
 r50 = models.resnet.resnet50(dataset_history=[], dataset2num_classes={}, network_width_multiplier=1.0, shared_layer_info={})
 assert sum(isinstance(m, nl.SharableConv2d) for m in r50.modules()) == 53
+from cpg_b200.fused_norm import FusedBatchNormReLU2d, fuse_bn_relu, fuse_resnet_blocks
+keys = list(r50.state_dict().keys())
+fuse_bn_relu(r50)
+assert fuse_resnet_blocks(r50) == 16 and fuse_resnet_blocks(r50) == 0      # every Bottleneck of models/resnet.py:60-100
+assert list(r50.state_dict().keys()) == keys
+assert all(isinstance(b, models.resnet.Bottleneck) and isinstance(b.bn3, FusedBatchNormReLU2d)
+           for b in r50.modules() if type(b).__name__.startswith('FusedBottleneck'))
 s20 = models.spherenet.spherenet20(dataset_history=[], dataset2num_classes={}, network_width_multiplier=1.0,
                                    shared_layer_info={})
 assert sum(isinstance(m, nl.SharableConv2d) for m in s20.modules()) == 20
