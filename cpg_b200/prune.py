@@ -491,6 +491,55 @@ class SparsePruner(object):
         self._task_view_idx = idx
         return idx
 
+    def serve_task(self, dataset, shared_layer_info):
+        """Switch ONE resident model to `dataset` (any task it holds) for evaluation, without touching `weight.data`:
+        the task's classifier (`set_dataset`), its per-task tensors out of the checkpoint's `shared_layer_info` -- conv /
+        linear biases, piggymasks, batch-norm weight / bias / running statistics, PReLU slopes: the re-binding of
+        utils/manager.py:305-325 and CPG_cifar100_main_normal.py:282-289 -- and `select_task(index + 1)`.  The reference
+        does the same per process: load_checkpoint_only_for_evaluate + apply_mask, one checkpoint load per task.  A task
+        trained at another network width (its tensors are sub-blocks of the resident ones,
+        utils/manager.py:281-297) needs a model built at that width and is refused here."""
+        import torch.nn as nn
+        inner = self.model.module
+        task_id = inner.datasets.index(dataset) + 1
+        info = shared_layer_info[dataset]
+
+        def bound(new, like, what, param):
+            if new is None:
+                raise _lib.CpgbError(f'shared_layer_info[{dataset!r}] has no {what}')
+            if tuple(new.shape) != tuple(like.shape):
+                raise _lib.CpgbError(f'{what} of task {dataset!r} has shape {tuple(new.shape)}, the resident model '
+                                     f'{tuple(like.shape)}: the task was trained at another network width')
+            if new.device != like.device:
+                new = new.detach().to(like.device)
+            if param and not isinstance(new, nn.Parameter):
+                new = nn.Parameter(new.detach(), requires_grad=False)
+            return new
+
+        def entry(key, name):
+            return info.get(key, {}).get(name)
+
+        for name, module in inner.named_modules():
+            if isinstance(module, nl.SharableConv2d) or isinstance(module, nl.SharableLinear):
+                if module.bias is not None:
+                    module.bias = bound(entry('bias', name), module.bias, f'bias[{name}]', True)
+                if task_id > 1:
+                    module.piggymask = bound(entry('piggymask', name), module.weight, f'piggymask[{name}]', True)
+                else:
+                    module.piggymask = None             # the first task has none (models/layers.py:104-105)
+            elif isinstance(module, nn.BatchNorm2d):
+                for attr, key, param in (('running_mean', 'bn_layer_running_mean', False),
+                                         ('running_var', 'bn_layer_running_var', False),
+                                         ('weight', 'bn_layer_weight', True), ('bias', 'bn_layer_bias', True)):
+                    cur = getattr(module, attr)
+                    if cur is not None:
+                        setattr(module, attr, bound(entry(key, name), cur, f'{key}[{name}]', param))
+            elif isinstance(module, nn.PReLU):
+                module.weight = bound(entry('prelu_layer_weight', name), module.weight, f'prelu_layer_weight[{name}]', True)
+        inner.set_dataset(dataset)
+        self.inference_dataset_idx = task_id
+        return self.select_task(task_id)
+
     def clear_task_view(self):
         """Drop the copies `select_task()` made: evaluation reads `weight.data` again."""
         for name, module in self._sharable():

@@ -113,3 +113,70 @@ def test_a_view_from_another_device_or_shape_is_refused(monkeypatch):
     m._cpg_task_view = torch.zeros(3)
     with pytest.raises(_lib.CpgbError):
         m._effective()
+
+
+def test_serve_task_rebinds_the_per_task_tensors(monkeypatch):
+    """One resident model, every task: classifier, biases, piggymasks, batch-norm tensors and PReLU slopes come out of
+    the checkpoint's shared_layer_info (utils/manager.py:198-225 writes it, :305-325 and
+    CPG_cifar100_main_normal.py:282-289 read it back, one process per task), the weights through select_task."""
+    import pytest
+    import torch.nn as nn
+    _setup(monkeypatch)                                              # stand-ins for the CUDA pieces
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.c1 = nl.SharableConv2d(3, 8, 3, padding=1, bias=True)
+            self.bn = nn.BatchNorm2d(8)
+            self.act = nn.PReLU(8)
+            self.fc = nl.SharableLinear(8, 6)
+            self.datasets = ['t1', 't2', 't3']
+            self.classifiers = nn.ModuleList([nn.Linear(6, 2) for _ in self.datasets])
+            self.classifier = None
+
+        def set_dataset(self, d):
+            self.classifier = self.classifiers[self.datasets.index(d)]
+
+    torch.manual_seed(2)
+    net = Net()
+    with torch.no_grad():
+        net.c1.weight.normal_(); net.fc.weight.normal_()
+    wrap = Wrap(net)
+    masks = {'module.c1': torch.randint(0, 4, net.c1.weight.shape, dtype=torch.uint8),
+             'module.fc': torch.randint(0, 4, net.fc.weight.shape, dtype=torch.uint8)}
+    pr = cpg_prune.SparsePruner(wrap, masks, make_args('inference', dataset='t3'), 0, 8, 3)
+    # what Manager.save_checkpoint leaves behind after each task (names relative to model.module)
+    info = {}
+    for t, d in enumerate(net.datasets, 1):
+        info[d] = {'bias': {'c1': nn.Parameter(torch.full((8,), float(t))), 'fc': nn.Parameter(torch.full((6,), -float(t)))},
+                   'piggymask': {} if t == 1 else {'c1': nn.Parameter(torch.full_like(net.c1.weight, 0.01 * t)),
+                                                   'fc': nn.Parameter(torch.full_like(net.fc.weight, 0.01 * t))},
+                   'bn_layer_running_mean': {'bn': torch.full((8,), 0.1 * t)},
+                   'bn_layer_running_var': {'bn': torch.full((8,), 1.0 + t)},
+                   'bn_layer_weight': {'bn': nn.Parameter(torch.full((8,), 2.0 * t))},
+                   'bn_layer_bias': {'bn': nn.Parameter(torch.full((8,), 3.0 * t))},
+                   'prelu_layer_weight': {'act': nn.Parameter(torch.full((8,), 0.05 * t))}}
+    w_c1 = net.c1.weight.detach().clone()
+    keys = list(net.state_dict().keys())
+    wrap.eval()
+    for d in ('t2', 't1', 't3', 't1'):
+        t = net.datasets.index(d) + 1
+        assert pr.serve_task(d, info) == t and pr.inference_dataset_idx == t
+        assert net.classifier is net.classifiers[t - 1]
+        assert net.c1.bias is info[d]['bias']['c1'] and net.fc.bias is info[d]['bias']['fc']
+        assert (net.c1.piggymask is None) if t == 1 else (net.c1.piggymask is info[d]['piggymask']['c1'])
+        assert net.bn.running_mean is info[d]['bn_layer_running_mean']['bn'] and net.bn.weight is info[d]['bn_layer_weight']['bn']
+        assert net.bn.running_var is info[d]['bn_layer_running_var']['bn'] and net.bn.bias is info[d]['bn_layer_bias']['bn']
+        assert net.act.weight is info[d]['prelu_layer_weight']['act']
+        keep = (masks['module.c1'] >= 1) & (masks['module.c1'] <= t)
+        assert torch.equal(net.c1._effective()[0], w_c1 * keep) and torch.equal(net.c1.weight.detach(), w_c1)
+        fixed = lambda ks: [k for k in ks if 'piggymask' not in k and not k.startswith('classifier.')]
+        assert fixed(net.state_dict().keys()) == fixed(keys)          # (set_dataset registers `classifier`, as in models/vgg.py:90-93)
+    # a task trained at another width is refused, a missing entry is named
+    bad = dict(info)
+    bad['t2'] = dict(info['t2'], bn_layer_weight={'bn': nn.Parameter(torch.ones(12))})
+    with pytest.raises(_lib.CpgbError, match='another network width'):
+        pr.serve_task('t2', bad)
+    bad['t2'] = dict(info['t2'], bias={'c1': info['t2']['bias']['c1']})
+    with pytest.raises(_lib.CpgbError, match=r"no bias\[fc\]"):
+        pr.serve_task('t2', bad)
