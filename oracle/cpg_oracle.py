@@ -461,3 +461,26 @@ def bn_relu_pool_backward(x, dy, gamma, beta, mean, rstd, training: bool, relu: 
     else:
         dx = bc(gm * np.asarray(rstd, dtype=np.float64)) * g
     return dx, dgamma, dbeta
+
+
+# ----------------------------------------------------------------------------
+# SURVEY 8(f) N4, residual blocks: out = bn(out); out += identity; out = relu(out)
+#   models/resnet.py:50-55 (BasicBlock.forward), :92-98 (Bottleneck.forward)
+# Restated on top of the batch-norm above; pinned against the stock torch modules by tests/test_oracle_norm.py.
+# ----------------------------------------------------------------------------
+def bn_add_relu_forward(x, res, gamma, beta, running_mean, running_var, training: bool, momentum: float = 0.1,
+                        eps: float = 1e-5):
+    """y = max(0, batch_norm(x) + res).  Returns (y, new_running_mean, new_running_var, mean, rstd), float64."""
+    import numpy as np
+    z, rm, rv, mean, rstd = bn_relu_pool_forward(x, gamma, beta, running_mean, running_var, training, momentum, eps,
+                                                 relu=False, pool=False)
+    return np.maximum(z + np.asarray(res, dtype=np.float64), 0.0), rm, rv, mean, rstd
+
+
+def bn_add_relu_backward(x, y, dy, gamma, beta, mean, rstd, training: bool):
+    """Gradients of bn_add_relu_forward: g = dy * [y > 0] is the gradient of the identity branch (dres) and enters the
+    batch-norm backward as its output gradient.  Returns (dx, dres, dgamma, dbeta)."""
+    import numpy as np
+    g = np.asarray(dy, dtype=np.float64) * (np.asarray(y, dtype=np.float64) > 0)
+    dx, dgamma, dbeta = bn_relu_pool_backward(x, g, gamma, beta, mean, rstd, training, relu=False, pool=False)
+    return dx, g, dgamma, dbeta
