@@ -68,7 +68,7 @@ class GradSlot:
 
 
 class GradAllReducer:
-    def __init__(self, model, world=None, overlap=True, group=None, bucket_bytes=None):
+    def __init__(self, model, world=None, overlap=True, group=None, bucket_bytes=None, slots=True):
         self.world = world if world is not None else dist.get_world_size(group)
         self.group = group
         # NCCL averages inside the collective; gloo (CPU tests) only sums
@@ -80,7 +80,10 @@ class GradAllReducer:
         self._hooks = []
         self.flat, self._bucket_layers, self._bucket_left, self._slots = [], [], [], []
         self._slot_params = set()
-        if self.world > 1:
+        # slots=False: no flat buckets -- every gradient stays the tensor autograd produced (large ones get their own
+        # overlapped all-reduce, the rest one flat bucket).  For models that apply one sharable layer at several call
+        # sites of a forward pass: two wgrad epilogues must not write the same slot.
+        if self.world > 1 and slots:
             self._make_slots(model, bucket_bytes or BUCKET_BYTES)
         if overlap and self.world > 1:
             for p in self.params:
