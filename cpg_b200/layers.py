@@ -94,9 +94,16 @@ class _SharableBase(nn.Module):
         view = getattr(self, '_cpg_task_view', None)
         if view is None or self.training:
             return self.weight
-        if view.device != self.weight.device or view.shape != self.weight.shape:
-            raise _lib.CpgbError('the task view of this layer was built for another device or shape '
-                                 '(nn.DataParallel replica?): call SparsePruner.select_task() again')
+        if view.shape != self.weight.shape:
+            raise _lib.CpgbError('the task view of this layer was built for another weight shape: call '
+                                 'SparsePruner.select_task() again')
+        if view.device != self.weight.device:
+            if getattr(self, '_is_replica', False):
+                # nn.DataParallel replica (CPG_cifar100_main_normal.py:199): its weight was broadcast from the original's
+                # device for this forward pass, the view follows the same way
+                return view.to(self.weight.device)
+            raise _lib.CpgbError('the task view of this layer lives on another device than its weight: call '
+                                 'SparsePruner.select_task() again')
         return view
 
     def _effective(self):
@@ -112,6 +119,7 @@ class _SharableBase(nn.Module):
         _task_weight() returns)."""
         if weight is self.weight or weight is getattr(self, '_cpg_task_view', None):
             return self._take_prestaged(weight, piggy)
+        self._cpg_prestaged = None      # built for another tensor (e.g. a replica's copy of the task view)
         return None
 
 
