@@ -84,6 +84,8 @@ def build_parser():
     a('--synthetic', type=int, default=0, help='N > 0: N seeded random batches per epoch instead of the ImageFolder data')
     a('--fuse_bn', action='store_true', default=False,
       help='swap BatchNorm2d+ReLU(+MaxPool2d) for the cpg_b200.fused_norm kernels (state_dict keys unchanged)')
+    a('--sync_free', action='store_true', default=False,
+      help='run the epochs through cpg_b200.train_loop.train_sync_free (Manager.train without its per-batch host reads)')
     return p
 
 
@@ -319,6 +321,9 @@ def main(argv=None):
     end_prune_step = curr_prune_step + args.pruning_interval * len(train_loader)
 
     manager = Manager(args, model, shared_layer_info, masks, train_loader, val_loader, begin_prune_step, end_prune_step)
+    if args.sync_free:
+        from cpg_b200.train_loop import install_sync_free_train
+        install_sync_free_train(manager)
     if args.mode == 'inference':
         manager.load_checkpoint_only_for_evaluate(resume_from_epoch, resume_folder)
         manager.validate(resume_from_epoch - 1)

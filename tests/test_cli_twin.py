@@ -38,7 +38,7 @@ def test_parser_matches_the_reference_command_line():
         assert opts in have, opts
         assert have[opts] == spec, (opts, have[opts], spec)
     extra = sorted(o[0] for o in set(have) - set(want))
-    assert extra == ['--cpg_root', '--fuse_bn', '--synthetic'], extra
+    assert extra == ['--cpg_root', '--fuse_bn', '--sync_free', '--synthetic'], extra
 
 
 def _run(args, tmp, nproc=1, timeout=900):
