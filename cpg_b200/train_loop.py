@@ -14,8 +14,12 @@ training accuracy the caller logs, and the prune step counter -- are bit-identic
 The only host reads left inside an epoch are the progress-bar refreshes and the one status read-back of a prune event
 (the ``sys.exit(2)`` condition of utils/prune.py:38-42).
 
+``validate_sync_free`` does the same for ``Manager.validate`` (utils/manager.py:103-152), whose progress bar costs two
+metric read-backs and up to four mask reductions per batch.
+
 Usage: ``install_sync_free_train(manager)`` right after ``Manager(...)`` is constructed; the rest of the reference's main
-script (``manager.train(optimizers, epoch_idx, curr_lrs, curr_prune_step)``) stays as it is.
+script (``manager.train(optimizers, epoch_idx, curr_lrs, curr_prune_step)``, ``manager.validate(epoch_idx)``) stays as it
+is.
 """
 import logging
 import types
@@ -100,8 +104,75 @@ def train_sync_free(self, optimizers, epoch_idx, curr_lrs, curr_prune_step, post
     return avg_acc, curr_prune_step
 
 
-def install_sync_free_train(manager, postfix_every=POSTFIX_EVERY):
-    """Replace ``manager.train`` (an unmodified ``utils.manager.Manager``) by the sync-free loop."""
+def validate_sync_free(self, epoch_idx, biases=None, postfix_every=None):
+    """Drop-in for ``Manager.validate`` (utils/manager.py:103-152): the reference refreshes the progress bar after
+    every batch with two metric read-backs and up to four mask statistics (``calculate_shared_part_ratio`` reduces every
+    piggymask each time); here the metrics stay on the device and the bar is refreshed every ``postfix_every`` batches.
+    Same ``apply_mask()`` first, same forward passes, same returned accuracy."""
+    from tqdm import tqdm
+    every = int(postfix_every if postfix_every is not None else getattr(self, 'postfix_every', POSTFIX_EVERY))
+    self.pruner.apply_mask()
+    self.model.eval()
+    loss_sum = acc_sum = count = None
+    total = len(self.val_loader)
+    idx = self.inference_dataset_idx
+
+    def averages():
+        if count is None:
+            nan = float('nan')
+            return nan, nan
+        return (loss_sum / count).item(), (acc_sum / count).item()
+
+    with tqdm(total=total, desc='Val Ep. #{}: '.format(epoch_idx + 1), ascii=True) as t:
+        with torch.no_grad():
+            for batch_idx, (data, target) in enumerate(self.val_loader):
+                if self.args.cuda:
+                    data, target = data.cuda(), target.cuda()
+
+                output = self.model(data)
+                num = data.size(0)
+                if count is None:
+                    loss_sum = torch.zeros((), dtype=torch.float32, device=output.device)
+                    acc_sum = torch.zeros((), dtype=torch.float32, device=output.device)
+                    count = torch.zeros((), dtype=torch.float32, device=output.device)
+                loss_sum += self.criterion(output, target) * num
+                acc_sum += _accuracy_on_device(output, target) * num
+                count += num
+
+                if every > 0 and ((batch_idx + 1) % every == 0 or batch_idx + 1 == total):
+                    avg_loss, avg_acc = averages()
+                    postfix = {'loss': avg_loss,
+                               'accuracy': '{:.2f}'.format(100. * avg_acc),
+                               'sparsity': self.pruner.calculate_sparsity(),
+                               'task{} ratio'.format(idx): self.pruner.calculate_curr_task_ratio()}
+                    if idx != 1:
+                        postfix['shared_ratio'] = self.pruner.calculate_shared_part_ratio()
+                    postfix['zero ratio'] = self.pruner.calculate_zero_ratio()
+                    postfix['mpl'] = self.args.network_width_multiplier
+                    t.set_postfix(postfix)
+                t.update(1)
+
+    avg_loss, avg_acc = averages()
+    summary = {'loss': '{:.3f}'.format(avg_loss),
+               'accuracy': '{:.2f}'.format(100. * avg_acc),
+               'sparsity': '{:.3f}'.format(self.pruner.calculate_sparsity()),
+               'task{} ratio'.format(idx): '{:.3f}'.format(self.pruner.calculate_curr_task_ratio()),
+               'zero ratio': '{:.3f}'.format(self.pruner.calculate_zero_ratio()),
+               'mpl': self.args.network_width_multiplier}
+    if idx != 1:
+        summary['shared_ratio'] = '{:.3f}'.format(self.pruner.calculate_shared_part_ratio())
+
+    if self.args.log_path:
+        logging.info(('In validate()-> Val Ep. #{} '.format(epoch_idx + 1)
+                      + ', '.join(['{}: {}'.format(k, v) for k, v in summary.items()])))
+    return avg_acc
+
+
+def install_sync_free_train(manager, postfix_every=POSTFIX_EVERY, validate=True):
+    """Replace ``manager.train`` (and, with `validate`, ``manager.validate``) of an unmodified
+    ``utils.manager.Manager`` by the sync-free loops."""
     manager.postfix_every = int(postfix_every)
     manager.train = types.MethodType(train_sync_free, manager)
+    if validate:
+        manager.validate = types.MethodType(validate_sync_free, manager)
     return manager

@@ -81,6 +81,10 @@ install_sync_free_train(mb, postfix_every=2)
 rb = mb.train(opts_b, 0, [1e-2], 0)
 same = lambda u, v: (u == v) or (u != u and v != v)
 assert same(ra[0], rb[0]) and ra[1] == rb[1], (ra, rb)
+# ... and the validation pass that follows every epoch (utils/manager.py:103-152: apply_mask, eval, accuracy)
+va, vb = ma.validate(0), mb.validate(0)
+assert same(va, vb), (va, vb)
+assert mb.validate.__func__.__name__ == 'validate_sync_free' and ma.validate.__func__.__name__ == 'validate'
 for (na, pa), (nb, pb) in zip(model_a.named_parameters(), model_b.named_parameters()):
     assert na == nb and torch.equal(pa, pb), na
 for (na, ba), (nb, bb) in zip(model_a.named_buffers(), model_b.named_buffers()):
