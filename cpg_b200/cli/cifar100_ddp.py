@@ -366,7 +366,9 @@ def main(argv=None):
         return {}
 
     def must_prune_ratio():
-        """:366-377 / :489-501: at the width cap with the goal still missed, the task may keep only its share."""
+        """:366-377 / :489-501: at the width cap with the goal still missed, the task may keep only its share.
+        None when that situation does not apply (the reference only compares inside the branch: for the last task
+        the share is the whole remainder, the ratio 0.0, and every sparsity "reaches" it)."""
         if (args.network_width_multiplier == args.max_allowed_network_width_multiplier
                 and record()['0.0'] < baseline_acc):
             logging.info('we reach the upperbound and still do not get the accuracy over our target on curr task')
@@ -375,7 +377,7 @@ def main(argv=None):
             logging.info('remain_num_tasks: {}'.format(remain))
             logging.info('ratio_allow_for_curr_task: {:.4f}'.format(allow))
             return 1.0 - allow
-        return 0.0
+        return None
 
     if args.mode == 'prune':
         if 'gradual_prune' in args.load_folder and args.save_folder == args.load_folder:
@@ -384,7 +386,7 @@ def main(argv=None):
         logging.info('Before pruning: ')
         logging.info('Sparsity range: {} -> {}'.format(args.initial_sparsity, args.target_sparsity))
         limit = must_prune_ratio()
-        if limit and args.initial_sparsity >= limit:
+        if limit is not None and args.initial_sparsity >= limit:
             _finish(world, 6)
         manager.validate(start_epoch - 1)
         logging.info('')
@@ -468,7 +470,7 @@ def main(argv=None):
                 if world > 1:
                     dist.barrier()
                 limit = must_prune_ratio()
-                if limit and args.target_sparsity >= limit:
+                if limit is not None and args.target_sparsity >= limit:
                     code = 6
             else:
                 code = 6
