@@ -35,8 +35,12 @@ void orc_grad_epilogue(float *dW, float *dP, const float *w, const uint8_t *t, i
   }
 }
 
+/* Total order with NaN last -- the order torch.kthvalue (utils/prune.py:39) and numpy's partition use; found by
+ * tests/test_prune_differential_cpu.py: with the plain (x > y) - (x < y) a NaN weight broke the sort. */
 static int cmp_float(const void *a, const void *b) {
   float x = *(const float *)a, y = *(const float *)b;
+  int nx = x != x, ny = y != y;
+  if (nx || ny) return nx - ny;
   return (x > y) - (x < y);
 }
 
