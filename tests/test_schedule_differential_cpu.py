@@ -26,6 +26,10 @@ def _ref_root():
     return None
 
 
+CTOR_CASES = [(mode, ds, again, has) for mode in ('prune', 'inference', 'finetune', 'train')
+              for ds in ('t1', 't3') for again, has in ((False, True), (True, True), (False, False))]
+
+
 def schedules(n=150):
     rng = np.random.RandomState(88)
     out = []
@@ -48,7 +52,7 @@ torch.Tensor.cuda = lambda self, *a, **k: self
 sys.path.insert(0, ROOT)
 sys.path.insert(0, REF)
 from utils.prune import SparsePruner
-from tests.test_schedule_differential_cpu import schedules
+from tests.test_schedule_differential_cpu import CTOR_CASES, schedules
 bits = lambda x: struct.unpack('<Q', struct.pack('<d', float(x)))[0]
 
 
@@ -73,7 +77,20 @@ for sc in schedules():
         fire = bool(s._time_to_update_masks(step))
         row.append([step, fire, bits(s._adjust_sparsity(step)), bits(s.gradually_prune(step)), s.last_prune_step])
     res.append(row)
-json.dump(res, open(OUT, 'w'))
+ctor = []
+for mode, dataset, again, has_attr in CTOR_CASES:
+    m = torch.nn.Module()
+    m.module = torch.nn.Module()
+    m.module.datasets = ['t1', 't2', 't3']
+    a = argparse.Namespace(mode=mode, dataset=dataset)
+    if has_attr:
+        a.finetune_again = again
+    try:
+        p = SparsePruner(m, {}, a, 3, 9, 2)
+        ctor.append([p.current_dataset_idx, p.inference_dataset_idx, p.last_prune_step, p.sparsity_func_exponent])
+    except SystemExit as e:
+        ctor.append(['exit', e.code])
+json.dump({'schedules': res, 'ctor': ctor}, open(OUT, 'w'))
 print('ok')
 '''
 
@@ -84,7 +101,21 @@ def test_schedule_equals_the_reference(tmp_path, monkeypatch):
     r = subprocess.run([sys.executable, '-c', REF_CODE, _ref_root(), ROOT, out], capture_output=True, text=True,
                        timeout=600)
     assert r.returncode == 0 and 'ok' in r.stdout, r.stderr[-3000:]
-    want = json.load(open(out))
+    both = json.load(open(out))
+    want = both['schedules']
+    # the constructor's task index per mode (utils/prune.py:18-25), incl. the unsupported-mode exit
+    for (mode, dataset, again, has_attr), exp in zip(CTOR_CASES, both['ctor']):
+        model = Wrap(Toy(nl))
+        import argparse
+        a = argparse.Namespace(mode=mode, dataset=dataset)
+        if has_attr:
+            a.finetune_again = again
+        try:
+            p = cpg_prune.SparsePruner(model, {}, a, 3, 9, 2)
+            got = [p.current_dataset_idx, p.inference_dataset_idx, p.last_prune_step, p.sparsity_func_exponent]
+        except SystemExit as e:
+            got = ['exit', e.code]
+        assert got == exp, (mode, dataset, again, has_attr, got, exp)
     bits = lambda x: struct.unpack('<Q', struct.pack('<d', float(x)))[0]
     fired = 0
     for sc, rows in zip(schedules(), want):
