@@ -1,4 +1,4 @@
-"""Differential tests of the a6 gradient epilogue and the a1 Binarizer on seeded adversarial inputs
+"""Differential tests of the a6 gradient epilogue, the a1 Binarizer and a9 / a10 on seeded adversarial inputs
 (tests/_epilogue_cases.py): the torch oracle and the UNMODIFIED reference code (SparsePruner.
 do_weight_decay_and_make_grads_zero on reference layers, utils/prune.py:195-211; Binarizer.apply,
 models/layers.py:15-19) must agree bit for bit -- NaN / inf gradients under masked positions come out as exact zeros
@@ -103,6 +103,21 @@ for i, (w, g, gp, t, cur, mode, wd) in enumerate(epilogue_cases()):
         res['p%d' % i] = layer.piggymask.grad.numpy().copy()
 for j, p in enumerate(binarizer_cases()):
     res['b%d' % j] = nl.Binarizer.apply(torch.from_numpy(p.copy()), 5e-3).numpy().copy()
+# a9 / a10 (utils/prune.py:213-243) on the same weights and masks (NaN / inf weights must become exact zeros too)
+for i, (w, g, gp, t, cur, mode, wd) in enumerate(epilogue_cases()):
+    mk = (lambda: nl.SharableConv2d(w.shape[1], w.shape[0], w.shape[2], bias=False)) if w.ndim == 4 else \
+         (lambda: nl.SharableLinear(w.shape[1], w.shape[0], bias=False))
+    for tag, call in (('a9z', 'make_pruned_zero'), ('a9a', 'apply_mask'), ('a10', 'make_finetuning_mask')):
+        layer = mk()
+        with torch.no_grad():
+            layer.weight.copy_(torch.from_numpy(g))          # the special-valued array as weights
+        s = Stub()
+        s.model, s.masks = nn.Sequential(layer), {'0': torch.from_numpy(t.copy())}
+        s.current_dataset_idx, s.inference_dataset_idx = cur, cur
+        getattr(SparsePruner, call)(s)
+        res['%s_w%d' % (tag, i)] = layer.weight.detach().numpy().copy()
+        res['%s_t%d' % (tag, i)] = s.masks['0'].numpy().copy()
+        res['%s_c%d' % (tag, i)] = np.array(s.current_dataset_idx)
 np.savez(OUT, **res)
 print('ok')
 '''
@@ -124,3 +139,14 @@ def test_oracle_equals_the_live_reference(tmp_path):
     for j, p in enumerate(binarizer_cases()):
         got = O.binarize(torch.from_numpy(p), 5e-3).numpy()
         assert np.array_equal(bits(got), bits(ref['b%d' % j])), ('binarizer', j)
+    for i, (w, g, gp, t, cur, mode, wd) in enumerate(epilogue_cases()):
+        for tag in ('a9z', 'a9a', 'a10'):
+            ww, tt, c = torch.from_numpy(g.copy()), torch.from_numpy(t.copy()), cur
+            if tag == 'a9z':
+                O.make_pruned_zero(ww, tt)
+            elif tag == 'a9a':
+                O.apply_mask(ww, tt, cur)
+            else:
+                c = O.make_finetuning_mask(tt, cur)
+            assert np.array_equal(bits(ww.numpy()), bits(ref['%s_w%d' % (tag, i)])), (tag, i)
+            assert np.array_equal(tt.numpy(), ref['%s_t%d' % (tag, i)]) and c == int(ref['%s_c%d' % (tag, i)]), (tag, i)
