@@ -1,7 +1,8 @@
 """a3 / a4 / a5 on random layer configurations: the oracle's forward and autograd (oracle.cpg_oracle.conv2d_* /
 linear_*) against the UNMODIFIED reference layers (models/layers.py:43-218) run in a second process -- kernel sizes 1 / 3 /
 5 / 7, strides, paddings, dilations, groups, with and without bias and piggymask, piggymask values on both sides of
-the threshold: outputs and all gradients bit for bit (same torch CPU kernels underneath).  Also the constructors'
+the threshold: outputs and all gradients to 1e-5 of the largest element (the same torch CPU kernels underneath; their
+summation order depends on the process's thread state).  Also the constructors'
 error behaviour of the drop-in classes (ValueError on non-divisible groups, models/layers.py:65-68)."""
 import os
 import subprocess
@@ -112,7 +113,10 @@ def test_oracle_layers_equal_the_reference(tmp_path):
             key = '%s%d' % (name, i)
             assert (got is None) == (key not in ref), (key, cfg)
             if got is not None:
-                assert np.array_equal(got.detach().numpy(), ref[key]), (key, cfg)
+                a, b = got.detach().numpy().astype(np.float64), ref[key].astype(np.float64)
+                # the same torch CPU kernels underneath, but their reduction order depends on the thread state of the
+                # process (oneDNN / OpenMP): equal to fp32 summation order, not bit for bit
+                assert a.shape == b.shape and np.abs(a - b).max() <= 1e-5 * max(np.abs(b).max(), 1e-30), (key, cfg)
 
 
 def test_constructor_errors_of_the_drop_in_layers():

@@ -25,6 +25,7 @@ import torch
 import torch.nn as nn
 REF, ROOT, MODE, DATASET = sys.argv[1], sys.argv[2], sys.argv[3], sys.argv[4]
 torch.Tensor.cuda = lambda self, *a, **k: self
+torch.set_num_threads(1)                                 # one summation order for both arms
 sys.path.insert(0, ROOT)
 sys.path.insert(0, REF)
 import models
